@@ -1,0 +1,51 @@
+"""pytest configuration: markers, repo root on sys.path, shared golden fixtures."""
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: takes more than a few seconds")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    with open(os.path.join(GOLDEN_DIR, "golden.json")) as f:
+        return json.load(f)
+
+
+_corpus_cache = {}
+
+
+def corpus_body(golden, name) -> bytes:
+    """Realise a corpus named in golden.json: the body of a .colibri.dat (bytes after the 0xA2 0x02 header)."""
+    if name in _corpus_cache:
+        return _corpus_cache[name]
+    spec = golden["corpora"][name]
+    if spec["kind"] == "file":
+        body = open(os.path.join(GOLDEN_DIR, spec["arg"]), "rb").read()[2:]
+    elif spec["kind"] == "hex":
+        body = bytes.fromhex(spec["arg"])
+    else:
+        import oracle
+
+        body = oracle.synth_corpus(**spec["arg"]).tobytes()
+    _corpus_cache[name] = body
+    return body
+
+
+def case_id(case) -> str:
+    return "%s-%s%s-%s" % (case["corpus"], "u" if case["unindexed"] else "i", "s" if case["skipgrams"] else "", "".join("%s%s" % kv for kv in sorted(case["cli"].items())) or "default")
+
+
+def load_cases():
+    with open(os.path.join(GOLDEN_DIR, "golden.json")) as f:
+        return json.load(f)["cases"]

@@ -1,0 +1,40 @@
+# Top-level build.  `make` builds the sm_100a shared library (CUDA kernels + C ABI), the host-side C++ front end
+# and the oracle checker library.  nvcc cross-compiles without a GPU.  Artefacts stay in-tree (git-ignored).
+NVCC     ?= /usr/local/cuda/bin/nvcc
+CXX      ?= g++
+PKG      := colibri-core_b200
+CSRC     := $(PKG)/csrc
+LIBDIR   := $(PKG)/lib
+BINDIR   := $(PKG)/bin
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
+LIB      := $(LIBDIR)/libcolibri_b200.so
+
+.PHONY: all lib oracle ref host clean
+all: lib oracle host
+
+lib: $(LIB)
+
+$(LIBDIR)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.h $(CSRC)/device_utils.cuh
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/kernels.ptxas.log || (cat $(LIBDIR)/kernels.ptxas.log; false)
+
+$(LIBDIR)/engine.o: $(CSRC)/engine.cu $(CSRC)/kernels.h include/colibri_b200.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/engine.ptxas.log || (cat $(LIBDIR)/engine.ptxas.log; false)
+
+$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^
+
+oracle:
+	$(MAKE) -C oracle oracle
+
+ref:
+	$(MAKE) -C oracle ref
+
+host: lib
+	@if [ -f $(PKG)/host/Makefile ]; then $(MAKE) -C $(PKG)/host; fi
+
+clean:
+	rm -rf $(LIBDIR) $(BINDIR)
+	$(MAKE) -C oracle clean

@@ -1,0 +1,1013 @@
+// engine.cu -- host-side driver of the device passes and the C ABI (include/colibri_b200.h).
+//
+// Restates the control flow of PatternModel::train (reference include/patternmodel.h:880-1345) around the kernels in
+// kernels.cu: option normalisation (:883-888), one pass per n (:981), "None found" early stop (:1189-1194),
+// totaltypes before the unigram prune (:1199-1201), prune after each pass (:1220), optional skipgram threshold
+// (:1233-1243), MINLENGTH clean-up (:1221-1229, :1337-1341).  No CPU implementation of the counting exists here:
+// without a CUDA device every entry point fails with COLIBRI_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/colibri_b200.h"
+#include "kernels.h"
+
+using namespace colibri;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                                        \
+    do {                                                                                                                      \
+        cudaError_t e__ = (expr);                                                                                             \
+        if (e__ != cudaSuccess) return set_err(COLIBRI_E_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    } while (0)
+#define TRY(expr)                 \
+    do {                          \
+        int rc__ = (expr);        \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+extern "C" const char* colibri_b200_last_error(void) {
+    return g_err;
+}
+extern "C" const char* colibri_b200_version(void) {
+    return "colibri-core_b200 0.1 (sm_100a)";
+}
+extern "C" int colibri_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+extern "C" void colibri_b200_options_default(colibri_b200_options* o) {
+    memset(o, 0, sizeof *o);
+    o->MINTOKENS           = -1;  // reference include/patternmodel.h:153-180
+    o->MINTOKENS_SKIPGRAMS = -1;
+    o->MINTOKENS_UNIGRAMS  = 1;
+    o->MINLENGTH           = 1;
+    o->MAXLENGTH           = 100;
+    o->MAXBACKOFFLENGTH    = 100;
+    o->MINSKIPTYPES        = 2;
+    o->MAXSKIPS            = 3;
+    o->model_type          = COLIBRI_UNINDEXEDPATTERNMODEL;
+    o->streamed            = 1;
+    o->device              = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ device memory pool
+// cudaMalloc/cudaFree of multi-gigabyte buffers costs milliseconds and synchronises the device; training the same
+// corpus repeatedly (the benchmark loop, or a CLI run with several models) reuses the blocks instead.
+namespace {
+struct Pool {
+    std::mutex                        mu;
+    std::multimap<size_t, void*>      free_blocks;  // size -> ptr
+    std::map<void*, size_t>           live;
+    size_t                            in_use = 0, peak = 0, cached = 0;
+    int alloc(void** out, size_t bytes) {
+        bytes = std::max<size_t>(256, (bytes + 255) / 256 * 256);
+        std::lock_guard<std::mutex> g(mu);
+        auto it = free_blocks.lower_bound(bytes);
+        if (it != free_blocks.end() && it->first <= bytes + bytes / 4 + (1 << 20)) {
+            *out = it->second;
+            live[*out] = it->first;
+            in_use += it->first;
+            cached -= it->first;
+            free_blocks.erase(it);
+        } else {
+            cudaError_t e = cudaMalloc(out, bytes);
+            if (e != cudaSuccess) {  // drop the cache and retry once
+                cudaGetLastError();
+                for (auto& kv : free_blocks) cudaFree(kv.second);
+                free_blocks.clear();
+                cached = 0;
+                e = cudaMalloc(out, bytes);
+            }
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return set_err(COLIBRI_E_CUDA, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            }
+            live[*out] = bytes;
+            in_use += bytes;
+        }
+        peak = std::max(peak, in_use);
+        return 0;
+    }
+    void release(void* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu);
+        auto it = live.find(p);
+        if (it == live.end()) return;
+        in_use -= it->second;
+        cached += it->second;
+        free_blocks.emplace(it->second, p);
+        live.erase(it);
+    }
+    void trim() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        cached = 0;
+    }
+};
+Pool g_pool[16];
+
+template <class T>
+struct DevBuf {
+    T*     p   = nullptr;
+    size_t n   = 0;
+    int    dev = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&)            = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), dev(o.dev) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            reset();
+            p = o.p; n = o.n; dev = o.dev;
+            o.p = nullptr; o.n = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { reset(); }
+    int alloc(int device, size_t count) {
+        reset();
+        dev = device;
+        void* q = nullptr;
+        TRY(g_pool[device & 15].alloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+        p = (T*)q;
+        n = count;
+        return 0;
+    }
+    void reset() {
+        if (p) g_pool[dev & 15].release(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct PhaseTimer {  // CUDA events on the library's stream, resolved after the final synchronise
+    struct Span { int phase; cudaEvent_t a, b; int level; };
+    std::vector<Span> spans;
+    cudaStream_t      s = nullptr;
+    int begin(int phase, int level = 0) {
+        Span sp{phase, nullptr, nullptr, level};
+        if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return -1;
+        cudaEventRecord(sp.a, s);
+        spans.push_back(sp);
+        return (int)spans.size() - 1;
+    }
+    void end(int h) { if (h >= 0) cudaEventRecord(spans[h].b, s); }
+    ~PhaseTimer() {
+        for (auto& sp : spans) {
+            cudaEventDestroy(sp.a);
+            cudaEventDestroy(sp.b);
+        }
+    }
+    void resolve(double ms[COLIBRI_T_NPHASES], std::map<int, double>* level_ms) {
+        for (auto& sp : spans) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) {
+                ms[sp.phase] += t;
+                if (level_ms && sp.phase == COLIBRI_T_COUNT) (*level_ms)[sp.level] += t;
+            }
+            cudaEventDestroy(sp.a);
+            cudaEventDestroy(sp.b);
+        }
+        spans.clear();
+    }
+};
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ corpus
+constexpr size_t kHalo = 16;  // zero bytes in front of the body: byte -1 must read as "< 128"
+struct colibri_b200_corpus {
+    int              device = 0;
+    DevBuf<uint8_t>  buf;            // [kHalo zeros][body][2 spare][0x80 padding to a tile multiple + one tile]
+    size_t           nbytes = 0;     // body bytes as given
+    bool             ends_with_delim = true;
+    uint8_t          last_byte = 0;
+    cudaStream_t     stream = nullptr;
+    double           h2d_ms = 0;
+    uint8_t*         body() const { return buf.p + kHalo; }
+    size_t           padded(size_t staged) const { return (staged + kTokTile - 1) / kTokTile * kTokTile; }
+};
+
+static int corpus_alloc(colibri_b200_corpus* c, int device, size_t nbytes) {
+    int ndev = colibri_b200_device_count();
+    if (ndev <= 0) return set_err(COLIBRI_E_CUDA, "no CUDA device available: the B200 path has no CPU fallback");
+    if (device < 0 || device >= ndev) return set_err(COLIBRI_E_INVALID, "device %d out of range (have %d)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    c->device = device;
+    c->nbytes = nbytes;
+    size_t total = kHalo + c->padded(nbytes + 2) + kTokTile;
+    TRY(c->buf.alloc(device, total));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMemsetAsync(c->buf.p, 0, kHalo, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->buf.p + kHalo + nbytes, 0x80, total - kHalo - nbytes, c->stream));
+    return 0;
+}
+static int corpus_finish(colibri_b200_corpus* c) {
+    // the last two body bytes decide whether the final sentence is terminated (delimiter = 0x00 not preceded by a continuation byte)
+    uint8_t tail[2] = {0, 0};
+    size_t  k       = std::min<size_t>(2, c->nbytes);
+    if (k) CUDA_TRY(cudaMemcpyAsync(tail + (2 - k), c->body() + c->nbytes - k, k, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->last_byte       = tail[1];
+    c->ends_with_delim = c->nbytes >= 1 && tail[1] == 0 && (c->nbytes == 1 || tail[0] < 128);
+    return 0;
+}
+
+extern "C" int colibri_b200_corpus_stage(const uint8_t* host_body, size_t nbytes, int device, colibri_b200_corpus** out) {
+    if (!out) return set_err(COLIBRI_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!host_body && nbytes) return set_err(COLIBRI_E_INVALID, "host_body is NULL");
+    auto* c = new colibri_b200_corpus();
+    int   rc = corpus_alloc(c, device, nbytes);
+    if (rc == 0 && nbytes) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+        cudaError_t e = cudaMemcpyAsync(c->body(), host_body, nbytes, cudaMemcpyHostToDevice, c->stream);
+        cudaEventRecord(b, c->stream);
+        if (e != cudaSuccess) rc = set_err(COLIBRI_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+        if (rc == 0) rc = corpus_finish(c);
+        float ms = 0;
+        if (rc == 0 && cudaEventElapsedTime(&ms, a, b) == cudaSuccess) c->h2d_ms = ms;
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    } else if (rc == 0) {
+        rc = corpus_finish(c);
+    }
+    if (rc) {
+        colibri_b200_corpus_free(c);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+extern "C" int colibri_b200_corpus_from_device(const void* dev_body, size_t nbytes, int device, colibri_b200_corpus** out) {
+    if (!out) return set_err(COLIBRI_E_INVALID, "out is NULL");
+    *out = nullptr;
+    auto* c = new colibri_b200_corpus();
+    int   rc = corpus_alloc(c, device, nbytes);
+    if (rc == 0 && nbytes) {
+        cudaError_t e = cudaMemcpyAsync(c->body(), dev_body, nbytes, cudaMemcpyDeviceToDevice, c->stream);
+        if (e != cudaSuccess) rc = set_err(COLIBRI_E_CUDA, "D2D copy failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == 0) rc = corpus_finish(c);
+    if (rc) {
+        colibri_b200_corpus_free(c);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+extern "C" size_t colibri_b200_corpus_bytes(const colibri_b200_corpus* c) {
+    return c ? c->nbytes : 0;
+}
+extern "C" void colibri_b200_corpus_free(colibri_b200_corpus* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    delete c;
+}
+extern "C" int colibri_b200_corpus_download(const colibri_b200_corpus* c, uint8_t* host, size_t cap) {
+    if (!c || !host) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    if (cap < c->nbytes) return set_err(COLIBRI_E_INVALID, "buffer too small");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(host, c->body(), c->nbytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ model
+struct PassStat { uint64_t n, found, foundskip, pruned; };
+struct LevelInfo { uint64_t windows = 0, cap = 0; double ms = 0; };
+struct colibri_b200_model {
+    int      device = 0;
+    int      model_type = COLIBRI_UNINDEXEDPATTERNMODEL;
+    uint64_t npatterns = 0, keybytes = 0, nrefs = 0;
+    uint64_t totaltokens = 0, totaltypes = 0;
+    int      maxn = 0, minn = 999, hasskipgrams = 0;
+    std::vector<PassStat> passes;
+    // device-resident flat export
+    DevBuf<uint8_t>  d_keys;
+    DevBuf<uint64_t> d_off;
+    DevBuf<uint32_t> d_counts;
+    // host copies (filled on first export / lookup)
+    bool                  host_ready = false;
+    std::vector<uint8_t>  h_keys;
+    std::vector<uint64_t> h_off;
+    std::vector<uint32_t> h_counts;
+    std::vector<uint32_t> h_sorted;  // lookup index
+    double   ms[COLIBRI_T_NPHASES] = {0};
+    uint64_t counters[8] = {0};
+    std::map<int, LevelInfo> levels;
+    cudaStream_t stream = nullptr;
+};
+
+extern "C" void colibri_b200_model_free(colibri_b200_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) {
+        cudaStreamSynchronize(m->stream);
+        cudaStreamDestroy(m->stream);
+    }
+    delete m;
+}
+extern "C" uint64_t colibri_b200_model_size(const colibri_b200_model* m) { return m->npatterns; }
+extern "C" uint64_t colibri_b200_model_tokens(const colibri_b200_model* m) { return m->totaltokens; }
+extern "C" uint64_t colibri_b200_model_types(const colibri_b200_model* m) { return m->totaltypes; }
+extern "C" int      colibri_b200_model_maxn(const colibri_b200_model* m) { return m->maxn; }
+extern "C" int      colibri_b200_model_minn(const colibri_b200_model* m) { return m->minn; }
+extern "C" int      colibri_b200_model_hasskipgrams(const colibri_b200_model* m) { return m->hasskipgrams; }
+extern "C" int      colibri_b200_model_type(const colibri_b200_model* m) { return m->model_type; }
+extern "C" int      colibri_b200_model_passes(const colibri_b200_model* m) { return (int)m->passes.size(); }
+extern "C" int colibri_b200_model_pass_stats(const colibri_b200_model* m, int pass, uint64_t out[4]) {
+    if (pass < 0 || pass >= (int)m->passes.size()) return set_err(COLIBRI_E_INVALID, "pass %d out of range", pass);
+    out[0] = m->passes[pass].n;
+    out[1] = m->passes[pass].found;
+    out[2] = m->passes[pass].foundskip;
+    out[3] = m->passes[pass].pruned;
+    return 0;
+}
+extern "C" int colibri_b200_model_timings(const colibri_b200_model* m, double ms[COLIBRI_T_NPHASES]) {
+    memcpy(ms, m->ms, sizeof m->ms);
+    return 0;
+}
+extern "C" int colibri_b200_model_counters(const colibri_b200_model* m, uint64_t out[8]) {
+    memcpy(out, m->counters, sizeof m->counters);
+    return 0;
+}
+extern "C" int colibri_b200_model_level_counters(const colibri_b200_model* m, int n, double out[3]) {
+    auto it = m->levels.find(n);
+    if (it == m->levels.end()) return set_err(COLIBRI_E_INVALID, "level %d was not run", n);
+    out[0] = (double)it->second.windows;
+    out[1] = (double)it->second.cap;
+    out[2] = it->second.ms;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ training
+namespace {
+struct Segment {  // survivors of one (level, category)
+    int              n = 0;
+    bool             skip = false;
+    uint64_t         count = 0;
+    DevBuf<uint32_t> pos, cnt, mask;
+};
+
+// compute_skip_configurations (reference src/algorithms.cpp:79-94): every non-empty subset of the inner positions
+// 1..n-2, dropped when it has more than maxskips separate gaps (and n-2 >= maxskips)
+int skip_masks(int n, int maxskips, std::vector<SkipMask>& out) {
+    out.clear();
+    if (n < 3) return 0;
+    if (n > 24) return set_err(COLIBRI_E_UNSUPPORTED, "skipgrams of %d tokens: the device key holds masks up to n=24", n);
+    for (uint32_t i = 1; i < (1u << (n - 2)); ++i) {
+        uint32_t mask = i << 1;
+        int      runs = 0;
+        for (int j = 0, in = 0; j < n; ++j) {
+            int bit = (mask >> j) & 1;
+            if (bit && !in) ++runs;
+            in = bit;
+        }
+        if (n - 2 >= maxskips && runs > maxskips) continue;
+        SkipMask sm;
+        memset(&sm, 0, sizeof sm);
+        sm.mask = mask;
+        int parts = 0;
+        for (int j = 0; j < n;) {
+            if ((mask >> j) & 1) { ++j; continue; }
+            int k = j;
+            while (k < n && !((mask >> k) & 1)) ++k;
+            if (parts < kMaxSkipParts) {
+                sm.start[parts] = (uint8_t)j;
+                sm.len[parts]   = (uint8_t)(k - j);
+            }
+            ++parts;
+            j = k;
+        }
+        if (parts > kMaxSkipParts)
+            return set_err(COLIBRI_E_UNSUPPORTED, "skipgram mask 0x%x of size %d has %d non-gap runs; the device path folds at most %d", mask, n, parts, kMaxSkipParts);
+        sm.nparts = (uint32_t)parts;
+        out.push_back(sm);
+        if ((int)out.size() > kMaxSkipMasks) return set_err(COLIBRI_E_UNSUPPORTED, "more than %d skip configurations for n=%d (the reference enumerates 2^(n-2) too)", kMaxSkipMasks, n);
+    }
+    return 0;
+}
+
+int check_options(colibri_b200_options& o) {
+    // include/patternmodel.h:883-888
+    if (o.MINTOKENS == -1) o.MINTOKENS = 2;
+    if (o.MINTOKENS == 0) o.MINTOKENS = 1;
+    if (o.MINTOKENS_SKIPGRAMS < o.MINTOKENS) o.MINTOKENS_SKIPGRAMS = o.MINTOKENS;
+    if (o.MINTOKENS < 1) return set_err(COLIBRI_E_INVALID, "MINTOKENS=%d", o.MINTOKENS);
+    if (o.DOSKIPGRAMS && o.DOSKIPGRAMS_EXHAUSTIVE)
+        return set_err(COLIBRI_E_INVALID, "Both DOSKIPGRAMS as well as DOSKIPGRAMS_EXHAUSTIVE are set, this shouldn't happen, choose one.");  // :958-963
+    if (o.model_type != COLIBRI_UNINDEXEDPATTERNMODEL && o.model_type != COLIBRI_INDEXEDPATTERNMODEL)
+        return set_err(COLIBRI_E_UNSUPPORTED, "model type %d (only 10 = unindexed and 20 = indexed run on the device)", o.model_type);
+    if (o.model_type == COLIBRI_INDEXEDPATTERNMODEL) return set_err(COLIBRI_E_UNSUPPORTED, "indexed models are not on the device path yet");
+    if (o.DOSKIPGRAMS) return set_err(COLIBRI_E_UNSUPPORTED, "non-exhaustive skipgrams (IndexedPatternModel::trainskipgrams) are not on the device path yet");
+    if (o.DOPATTERNPERLINE) return set_err(COLIBRI_E_UNSUPPORTED, "DOPATTERNPERLINE is not on the device path");
+    if (o.PRUNENONSUBSUMED || o.PRUNESUBSUMED) return set_err(COLIBRI_E_UNSUPPORTED, "PRUNE(NON)SUBSUMED is not on the device path");
+    if (o.MAXLENGTH < 1 || o.MAXLENGTH > 255) return set_err(COLIBRI_E_UNSUPPORTED, "MAXLENGTH=%d (device path supports 1..255)", o.MAXLENGTH);
+    if (o.MINLENGTH < 1) o.MINLENGTH = 1;
+    if (o.MINLENGTH > o.MAXLENGTH) return set_err(COLIBRI_E_INVALID, "MINLENGTH > MAXLENGTH");
+    if (o.MINTOKENS > 1 && o.MAXBACKOFFLENGTH < o.MAXLENGTH - 1)
+        return set_err(COLIBRI_E_UNSUPPORTED, "MAXBACKOFFLENGTH=%d < MAXLENGTH-1: truncated back-off is not on the device path", o.MAXBACKOFFLENGTH);
+    if ((o.MINLENGTH > 1 || o.MINTOKENS == 1) && o.MINTOKENS_UNIGRAMS > o.MINTOKENS)
+        return set_err(COLIBRI_E_UNSUPPORTED, "the separate unigram pre-pass (MINTOKENS_UNIGRAMS with MINLENGTH>1 or MINTOKENS=1, patternmodel.h:918-920) is not on the device path");
+    if (o.MINTOKENS == 1 && o.MINLENGTH > 1) return set_err(COLIBRI_E_UNSUPPORTED, "MINTOKENS=1 with MINLENGTH>1 is not on the device path");
+    return 0;
+}
+
+struct Trainer {
+    colibri_b200_corpus*       c;
+    colibri_b200_options       o;
+    colibri_b200_model*        m;
+    cudaStream_t               s;
+    int                        dev, sms = 148;
+    PhaseTimer                 timer;
+    uint64_t                   launches = 0;
+    DevBuf<DeviceStats>        d_stats;
+    DeviceStats                h_stats;
+    std::vector<Segment>       segs;
+    uint64_t                   slots_init = 0, ngram_upserts = 0, skip_upserts = 0;
+
+    int zero_stats(bool keep_global = true) {
+        // found/kept/kept_occ/cursor/valid_windows/probes are per-phase; totaltokens/maxclass/errflags live for the whole train
+        (void)keep_global;
+        CUDA_TRY(cudaMemsetAsync(&d_stats.p->found, 0, offsetof(DeviceStats, maxclass) - offsetof(DeviceStats, found), s));
+        return 0;
+    }
+    int read_stats() {
+        CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (h_stats.errflags & kErrTableFull) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow");
+        return 0;
+    }
+    int run();
+    int export_segments(const uint32_t* tok);
+};
+
+int Trainer::run() {
+    CUDA_TRY(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    sms = prop.multiProcessorCount;
+    timer.s = s;
+    int h_total = timer.begin(COLIBRI_T_TOTAL);
+
+    // ---- the sentence source quirk (see include/colibri_b200.h: streamed)
+    if (c->nbytes == 0) return set_err(COLIBRI_E_FORMAT, "Attempting to read pattern from file, but file is empty?");  // src/pattern.cpp:520-523
+    size_t staged = c->nbytes;
+    {
+        uint8_t tail[16];
+        memset(tail, 0x80, sizeof tail);
+        size_t k = 0;
+        if (!c->ends_with_delim) {
+            if (o.streamed) tail[k++] = c->last_byte;  // Pattern(istream) stores the last byte twice when the final 0x00 is missing
+            tail[k++] = 0;
+        }
+        staged += k;
+        CUDA_TRY(cudaMemcpyAsync(c->body() + c->nbytes, tail, sizeof tail, cudaMemcpyHostToDevice, s));
+    }
+    const uint32_t nblocks = (uint32_t)(c->padded(staged) / kTokTile);
+
+    TRY(d_stats.alloc(dev, 1));
+    CUDA_TRY(cudaMemsetAsync(d_stats.p, 0, sizeof(DeviceStats), s));
+
+    // ---- K0 tokenise
+    int h = timer.begin(COLIBRI_T_TOKENISE);
+    DevBuf<uint32_t> blk;
+    TRY(blk.alloc(dev, nblocks + 1));
+    launches += launch_tokenise_count(s, c->body(), staged, blk.p, nblocks);
+    launches += launch_scan_block_counts(s, blk.p, nblocks, &d_stats.p->cursor);
+    TRY(read_stats());
+    const uint64_t npos_real = h_stats.cursor;  // tokens + delimiters
+    if (npos_real >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "corpus has %llu positions; the device index is 32 bit", (unsigned long long)npos_real);
+    const uint64_t npos = npos_real + 1;  // one virtual delimiter closes the last sentence
+    DevBuf<uint32_t> tok;
+    TRY(tok.alloc(dev, npos + 8));
+    CUDA_TRY(cudaMemsetAsync(tok.p + npos_real, 0, 8 * sizeof(uint32_t), s));
+    launches += launch_tokenise_write(s, c->body(), staged, blk.p, nblocks, tok.p, d_stats.p);
+    timer.end(h);
+    TRY(read_stats());
+    if (h_stats.errflags & kErrTokenTooLong) return set_err(COLIBRI_E_FORMAT, "corpus contains a class wider than 32 bits / 5 bytes");
+    if (h_stats.errflags & kErrNonCanonical) return set_err(COLIBRI_E_FORMAT, "corpus contains a non-canonical class encoding (multi-byte token ending in 0x00)");
+    if (h_stats.errflags & kErrReservedClass)
+        return set_err(COLIBRI_E_UNSUPPORTED, "corpus contains the reserved skip/flex classes (3, 4) as running text; not on the device path");
+    m->totaltokens = h_stats.totaltokens;
+    const uint32_t nclasses = h_stats.maxclass + 1;
+    m->counters[0] = npos_real;
+    m->counters[1] = c->nbytes;
+
+    const uint32_t t  = (uint32_t)o.MINTOKENS;
+    const uint32_t t1 = (uint32_t)std::max(o.MINTOKENS, o.MINTOKENS_UNIGRAMS);  // what higher orders require of their unigrams (:1094-1104)
+    const uint32_t ts = o.MINSKIPTYPES > 1 ? (uint32_t)o.MINTOKENS_SKIPGRAMS : t;  // PatternModel::pruneskipgrams returns early when minskiptypes <= 1 (:2170-2171)
+    const bool     skipgrams = o.DOSKIPGRAMS_EXHAUSTIVE != 0;
+
+    // ---- K1 unigrams
+    h = timer.begin(COLIBRI_T_UNIGRAMS);
+    DevBuf<uint32_t> count1;
+    TRY(count1.alloc(dev, nclasses));
+    CUDA_TRY(cudaMemsetAsync(count1.p, 0, (size_t)nclasses * 4, s));
+    launches += launch_unigram_hist(s, tok.p, npos, count1.p, nclasses, sms);
+    TRY(zero_stats());
+    {
+        Segment sg;
+        sg.n = 1;
+        uint64_t bound = std::min<uint64_t>(nclasses, m->totaltokens / std::max<uint32_t>(t, 1) + 1);
+        TRY(sg.pos.alloc(dev, bound));
+        TRY(sg.cnt.alloc(dev, bound));
+        launches += launch_unigram_prune(s, count1.p, nclasses, t, sg.pos.p, sg.cnt.p, 0, d_stats.p);
+        TRY(read_stats());
+        sg.count = h_stats.kept;
+        segs.push_back(std::move(sg));
+    }
+    timer.end(h);
+    m->counters[6] = m->totaltokens;
+    std::vector<PassStat> passes;
+    uint64_t prev_kept = h_stats.kept, prev_occ = h_stats.kept_occ;
+    if (h_stats.found == 0) {  // nothing at all ("None found", :1189-1194): an empty model
+        segs.clear();
+    } else {
+        passes.push_back({1, h_stats.found, 0, h_stats.found - h_stats.kept});
+        m->maxn = 1;
+        m->minn = 1;
+        m->totaltypes = h_stats.found;  // :1199-1201 (t > 1) and totalwordtypesingroup(NGRAM,1) (t == 1, :1202-1208)
+    }
+    int last_pass = h_stats.found ? 1 : 0;
+
+    // ---- levels n >= 2
+    std::vector<DevBuf<uint32_t>> ids(2);  // ids[k] = id array of level k (all kept when skipgrams need their parts, else ping-pong)
+    DevBuf<NgramSlot>       table;
+    DevBuf<SkipSlot>        sktable;
+    DevBuf<const uint32_t*> d_idptrs;
+    DevBuf<SkipMask>        d_masks;
+    if (last_pass == 1 && o.MAXLENGTH >= 2) {
+        TRY(ids[1].alloc(dev, npos + 8));
+        launches += launch_make_id1(s, tok.p, npos + 1, count1.p, t1, ids[1].p);
+    }
+    for (int n = 2; n <= o.MAXLENGTH && last_pass == n - 1; ++n) {
+        // every valid window starts at a position whose (n-1)-gram survived, and is a pair of surviving (n-1)-grams
+        uint64_t bound = prev_occ;
+        if (prev_kept < (1ull << 31)) bound = std::min(bound, prev_kept * prev_kept);
+        if (bound == 0) break;  // nothing can be found
+        uint64_t cap = std::max<uint64_t>(64, bound + bound / 2 + 16);  // load factor <= 2/3
+        if (cap >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "level %d needs %llu table slots; slot ids are 32 bit", n, (unsigned long long)cap);
+        if (table.n < cap) TRY(table.alloc(dev, cap));
+        if ((int)ids.size() <= n) ids.resize(n + 1);
+        DevBuf<uint32_t>& prev = ids[n - 1];
+        DevBuf<uint32_t>& cur  = ids[n];
+        if (!cur.p) TRY(cur.alloc(dev, npos + 8));
+        CUDA_TRY(cudaMemsetAsync(cur.p + npos, 0, 8 * sizeof(uint32_t), s));
+
+        int hp = timer.begin(COLIBRI_T_PRUNE);
+        CUDA_TRY(cudaMemsetAsync(table.p, 0, cap * sizeof(NgramSlot), s));
+        timer.end(hp);
+        slots_init += cap;
+        TRY(zero_stats());
+        int hc = timer.begin(COLIBRI_T_COUNT, n);
+        launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms);
+        timer.end(hc);
+        TRY(read_stats());
+        const uint64_t windows = h_stats.valid_windows;
+        ngram_upserts += windows;
+        m->levels[n].windows = windows;
+        m->levels[n].cap     = cap;
+
+        hp = timer.begin(COLIBRI_T_PRUNE);
+        Segment sg;
+        sg.n = n;
+        uint64_t sv_bound = windows / std::max<uint32_t>(t, 1) + 1;
+        TRY(sg.pos.alloc(dev, sv_bound));
+        TRY(sg.cnt.alloc(dev, sv_bound));
+        launches += launch_prune_ngrams(s, table.p, cap, t, sg.pos.p, sg.cnt.p, 0, d_stats.p, sms);
+        timer.end(hp);
+        TRY(read_stats());
+        const uint64_t found = h_stats.found, kept = h_stats.kept, occ = h_stats.kept_occ;
+        sg.count = kept;
+
+        // ---- exhaustive skipgrams of this level (:1163-1171)
+        uint64_t foundskip = 0, keptskip = 0;
+        Segment  sk;
+        if (skipgrams && n >= 3 && windows > 0) {
+            std::vector<SkipMask> masks;
+            TRY(skip_masks(n, o.MAXSKIPS, masks));
+            if (!masks.empty()) {
+                uint64_t sbound = 0;  // distinct keys <= one per (window, mask) plus one helper per folding round
+                for (auto& sm : masks) sbound += windows * (1 + (sm.nparts > 3 ? (sm.nparts - 2) / 2 : 0));
+                uint64_t scap   = std::max<uint64_t>(64, sbound + sbound / 2 + 16);
+                size_t   freeb = 0, totalb = 0;
+                cudaMemGetInfo(&freeb, &totalb);
+                if (sktable.n < scap) {
+                    sktable.reset();
+                    if (scap * sizeof(SkipSlot) > freeb + g_pool[dev & 15].cached)
+                        return set_err(COLIBRI_E_CAPACITY, "skipgram table of level %d needs %.1f GB", n, scap * 32.0 / 1e9);
+                    TRY(sktable.alloc(dev, scap));
+                }
+                std::vector<const uint32_t*> ptrs(n, nullptr);
+                for (int k = 1; k < n; ++k) ptrs[k] = ids[k].p;
+                TRY(d_idptrs.alloc(dev, n));
+                TRY(d_masks.alloc(dev, masks.size()));
+                CUDA_TRY(cudaMemcpyAsync(d_idptrs.p, ptrs.data(), n * sizeof(uint32_t*), cudaMemcpyHostToDevice, s));
+                CUDA_TRY(cudaMemcpyAsync(d_masks.p, masks.data(), masks.size() * sizeof(SkipMask), cudaMemcpyHostToDevice, s));
+                CUDA_TRY(cudaMemsetAsync(sktable.p, 0, scap * sizeof(SkipSlot), s));
+                slots_init += scap * 2;
+                TRY(zero_stats());
+                int hs = timer.begin(COLIBRI_T_SKIPGRAMS, n);
+                launches += launch_count_skipgrams(s, d_idptrs.p, n, d_masks.p, (int)masks.size(), npos, sktable.p, scap, d_stats.p, sms);
+                timer.end(hs);
+                TRY(read_stats());  // also keeps ptrs/masks alive until the copies are done
+                skip_upserts += h_stats.valid_windows;
+                sk.n    = n;
+                sk.skip = true;
+                uint64_t kb = h_stats.valid_windows / std::max<uint32_t>(ts, 1) + 1;
+                TRY(sk.pos.alloc(dev, kb));
+                TRY(sk.cnt.alloc(dev, kb));
+                TRY(sk.mask.alloc(dev, kb));
+                TRY(zero_stats());
+                hp = timer.begin(COLIBRI_T_PRUNE);
+                launches += launch_prune_skipgrams(s, sktable.p, scap, ts, sk.pos.p, sk.cnt.p, sk.mask.p, 0, d_stats.p, sms);
+                timer.end(hp);
+                TRY(read_stats());
+                foundskip = h_stats.found;
+                keptskip  = h_stats.kept;
+                sk.count  = keptskip;
+            }
+        }
+        if (found == 0 && foundskip == 0) break;  // "None found" (:1189-1194): maxn/minn untouched, no prune
+        last_pass = n;
+        m->maxn   = std::max(m->maxn, n);
+        m->minn   = std::min(m->minn, n);
+        if (foundskip) m->hasskipgrams = 1;
+        passes.push_back({(uint64_t)n, found, foundskip, (found - kept) + (foundskip - keptskip)});
+        segs.push_back(std::move(sg));
+        if (sk.skip) segs.push_back(std::move(sk));
+
+        if (n < o.MAXLENGTH && kept > 0) {
+            if (t > 1) {
+                hp = timer.begin(COLIBRI_T_PRUNE);
+                launches += launch_relabel(s, cur.p, npos, table.p, t);
+                timer.end(hp);
+            }
+        }
+        if (!skipgrams) ids[n - 1].reset();  // ping-pong: only the newest level is needed
+        prev_kept = kept;
+        prev_occ  = occ;
+        if (kept == 0) {  // the next pass cannot find anything: it would print "None found" and stop
+            break;
+        }
+    }
+
+    // ---- which levels end up in the model
+    std::vector<Segment> keep;
+    for (auto& sg : segs) {
+        bool drop = false;
+        if (o.MINTOKENS > 1) {
+            if (!skipgrams) {
+                // :1221-1229: after pass n, level n-1 is emptied when it is below MINLENGTH
+                int k = sg.n;
+                if (k < o.MINLENGTH && last_pass >= k + 1 && k != o.MAXBACKOFFLENGTH && !(k == 1 && o.MINTOKENS_UNIGRAMS > o.MINTOKENS)) drop = true;
+            } else if (o.MINLENGTH > 1 && sg.n <= o.MINLENGTH - 1) {
+                drop = true;  // :1337-1341 prunebylength
+            }
+        }
+        if (!drop && sg.count > 0) keep.push_back(std::move(sg));
+    }
+    segs = std::move(keep);
+
+    // reference reports a single pass when MINTOKENS == 1 (all lengths extracted in one scan, :1062-1072, :1246-1247)
+    if (o.MINTOKENS == 1 && !passes.empty()) {
+        PassStat one{1, 0, 0, 0};
+        for (auto& p : passes) {
+            one.found += p.found;
+            one.foundskip += p.foundskip;
+            one.pruned += p.pruned;
+        }
+        passes.assign(1, one);
+        // postread (:1274-1277): maxn/minn come from the stored patterns
+        m->maxn = 0;
+        m->minn = 999;
+        for (auto& sg : segs) {
+            m->maxn = std::max(m->maxn, sg.n);
+            m->minn = std::min(m->minn, sg.n);
+        }
+    }
+    m->passes = passes;
+
+    h = timer.begin(COLIBRI_T_EXPORT);
+    TRY(export_segments(tok.p));
+    timer.end(h);
+    timer.end(h_total);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    {
+        std::map<int, double> lvl;
+        timer.resolve(m->ms, &lvl);
+        for (auto& kv : lvl) m->levels[kv.first].ms = kv.second;
+    }
+    m->counters[2] = launches;
+    m->counters[3] = ngram_upserts;
+    m->counters[4] = skip_upserts;
+    m->counters[5] = slots_init;
+    m->counters[7] = g_pool[dev & 15].peak;
+    return 0;
+}
+
+int Trainer::export_segments(const uint32_t* tok) {
+    uint64_t total = 0;
+    for (auto& sg : segs) total += sg.count;
+    m->npatterns = total;
+    TRY(m->d_off.alloc(dev, total + 1));
+    TRY(m->d_counts.alloc(dev, std::max<uint64_t>(total, 1)));
+    if (total == 0) {
+        CUDA_TRY(cudaMemsetAsync(m->d_off.p, 0, sizeof(uint64_t), s));
+        m->keybytes = 0;
+        TRY(m->d_keys.alloc(dev, 1));
+        return 0;
+    }
+    DevBuf<uint32_t> pos, nm, lens;
+    DevBuf<uint64_t> tmp;
+    TRY(pos.alloc(dev, total));
+    TRY(nm.alloc(dev, total));
+    TRY(lens.alloc(dev, total));
+    TRY(tmp.alloc(dev, total / 2048 + 4));
+    uint64_t base = 0;
+    for (auto& sg : segs) {
+        CUDA_TRY(cudaMemcpyAsync(pos.p + base, sg.pos.p, sg.count * 4, cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(m->d_counts.p + base, sg.cnt.p, sg.count * 4, cudaMemcpyDeviceToDevice, s));
+        if (sg.skip) {
+            // raw gap masks first; packed into n | mask << 8 below
+            CUDA_TRY(cudaMemcpyAsync(nm.p + base, sg.mask.p, sg.count * 4, cudaMemcpyDeviceToDevice, s));
+        } else {
+            launches += launch_fill_u32(s, nm.p + base, sg.count, (uint32_t)sg.n);
+        }
+        base += sg.count;
+    }
+    // skip segments hold raw masks in nm: turn them into n | mask << 8
+    base = 0;
+    for (auto& sg : segs) {
+        if (sg.skip) {
+            launches += launch_pack_nm(s, nm.p + base, sg.count, (uint32_t)sg.n);
+        }
+        base += sg.count;
+    }
+    launches += launch_export_lengths(s, tok, pos.p, nm.p, total, lens.p);
+    launches += launch_exclusive_scan_u32_u64(s, lens.p, m->d_off.p, total, tmp.p);
+    uint64_t kb = 0;
+    CUDA_TRY(cudaMemcpyAsync(&kb, m->d_off.p + total, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    m->keybytes = kb;
+    TRY(m->d_keys.alloc(dev, std::max<uint64_t>(kb, 1)));
+    launches += launch_export_write(s, tok, pos.p, nm.p, m->d_off.p, total, m->d_keys.p);
+    CUDA_TRY(cudaStreamSynchronize(s));  // the temporaries above go back to the pool when this returns
+    segs.clear();
+    return 0;
+}
+}  // namespace
+
+extern "C" int colibri_b200_train_corpus(colibri_b200_corpus* corpus, const colibri_b200_options* opt, colibri_b200_model** out) {
+    if (!out) return set_err(COLIBRI_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!corpus || !opt) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    colibri_b200_options o = *opt;
+    TRY(check_options(o));
+    if (o.device != corpus->device) return set_err(COLIBRI_E_INVALID, "options.device=%d but the corpus is staged on device %d", o.device, corpus->device);
+    CUDA_TRY(cudaSetDevice(corpus->device));
+    auto* m       = new colibri_b200_model();
+    m->device     = corpus->device;
+    m->model_type = o.model_type;
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete m;
+        return set_err(COLIBRI_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    int rc;
+    {
+        Trainer tr;
+        tr.c   = corpus;
+        tr.o   = o;
+        tr.m   = m;
+        tr.s   = m->stream;
+        tr.dev = corpus->device;
+        rc     = tr.run();
+        if (rc) cudaStreamSynchronize(m->stream);
+    }
+    if (rc) {
+        colibri_b200_model_free(m);
+        return rc;
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" int colibri_b200_train(const uint8_t* host_body, size_t nbytes, const colibri_b200_options* opt, colibri_b200_model** out) {
+    if (!out) return set_err(COLIBRI_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!opt) return set_err(COLIBRI_E_INVALID, "options is NULL");
+    colibri_b200_options o = *opt;
+    TRY(check_options(o));
+    colibri_b200_corpus* c = nullptr;
+    TRY(colibri_b200_corpus_stage(host_body, nbytes, o.device, &c));
+    int rc = colibri_b200_train_corpus(c, opt, out);
+    if (rc == 0) (*out)->ms[COLIBRI_T_H2D] = c->h2d_ms;
+    colibri_b200_corpus_free(c);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ export / lookup
+extern "C" int colibri_b200_model_export_sizes(colibri_b200_model* m, uint64_t* npatterns, uint64_t* keybytes, uint64_t* nrefs) {
+    if (!m) return set_err(COLIBRI_E_INVALID, "model is NULL");
+    if (npatterns) *npatterns = m->npatterns;
+    if (keybytes) *keybytes = m->keybytes;
+    if (nrefs) *nrefs = m->nrefs;
+    return 0;
+}
+extern "C" int colibri_b200_model_export(colibri_b200_model* m, uint8_t* keys, uint64_t* key_off, uint32_t* counts, uint32_t*, uint16_t*, uint64_t*) {
+    if (!m || !key_off) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    if (m->keybytes && keys) CUDA_TRY(cudaMemcpyAsync(keys, m->d_keys.p, m->keybytes, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(key_off, m->d_off.p, (m->npatterns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, m->stream));
+    if (m->npatterns && counts) CUDA_TRY(cudaMemcpyAsync(counts, m->d_counts.p, m->npatterns * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+static int ensure_host(colibri_b200_model* m) {
+    if (m->host_ready) return 0;
+    m->h_keys.resize(m->keybytes + 1);
+    m->h_off.resize(m->npatterns + 1);
+    m->h_counts.resize(m->npatterns + 1);
+    TRY(colibri_b200_model_export(m, m->h_keys.data(), m->h_off.data(), m->h_counts.data(), nullptr, nullptr, nullptr));
+    m->host_ready = true;
+    return 0;
+}
+extern "C" int colibri_b200_model_write(colibri_b200_model* m, uint8_t* buf, size_t cap, size_t* nbytes) {
+    // layout: include/patternmodel.h:1609-1624 + include/patternstore.h:534-542 + src/pattern.cpp:268-277 + include/datatypes.h:216-221
+    if (!m || !nbytes) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    size_t need = 3 + 24 + m->keybytes + m->npatterns * 5;
+    *nbytes     = need;
+    if (!buf) return 0;
+    if (cap < need) return set_err(COLIBRI_E_INVALID, "buffer too small: need %zu bytes", need);
+    TRY(ensure_host(m));
+    size_t w = 0;
+    buf[w++] = 0;
+    buf[w++] = (uint8_t)m->model_type;
+    buf[w++] = 2;
+    memcpy(buf + w, &m->totaltokens, 8); w += 8;
+    memcpy(buf + w, &m->totaltypes, 8);  w += 8;
+    memcpy(buf + w, &m->npatterns, 8);   w += 8;
+    for (uint64_t i = 0; i < m->npatterns; ++i) {
+        size_t l = (size_t)(m->h_off[i + 1] - m->h_off[i]);
+        memcpy(buf + w, m->h_keys.data() + m->h_off[i], l);
+        w += l;
+        buf[w++] = 0;
+        memcpy(buf + w, &m->h_counts[i], 4);
+        w += 4;
+    }
+    return 0;
+}
+extern "C" int colibri_b200_model_lookup(colibri_b200_model* m, const uint8_t* key, uint32_t len, uint32_t* count) {
+    if (!m || !count || (!key && len)) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    TRY(ensure_host(m));
+    auto cmp_key = [&](uint32_t idx, const uint8_t* k, uint32_t l) {  // <0: pattern idx sorts before (k,l)
+        size_t pl = (size_t)(m->h_off[idx + 1] - m->h_off[idx]);
+        int    c  = memcmp(m->h_keys.data() + m->h_off[idx], k, std::min<size_t>(pl, l));
+        if (c) return c;
+        return pl < l ? -1 : (pl > l ? 1 : 0);
+    };
+    if (m->h_sorted.size() != m->npatterns) {
+        m->h_sorted.resize(m->npatterns);
+        for (uint64_t i = 0; i < m->npatterns; ++i) m->h_sorted[i] = (uint32_t)i;
+        std::sort(m->h_sorted.begin(), m->h_sorted.end(), [&](uint32_t a, uint32_t b) {
+            size_t la = (size_t)(m->h_off[a + 1] - m->h_off[a]);
+            return cmp_key(b, m->h_keys.data() + m->h_off[a], (uint32_t)la) > 0;
+        });
+    }
+    *count = 0;
+    size_t lo = 0, hi = m->h_sorted.size();
+    while (lo < hi) {
+        size_t mid = (lo + hi) / 2;
+        int    c   = cmp_key(m->h_sorted[mid], key, len);
+        if (c == 0) {
+            *count = m->h_counts[m->h_sorted[mid]];
+            return 0;
+        }
+        if (c < 0) lo = mid + 1; else hi = mid;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ parity helpers
+extern "C" int colibri_b200_hash64_batch(const uint8_t* keys, const uint64_t* key_off, uint64_t n, uint64_t* out, int device) {
+    if (colibri_b200_device_count() <= 0) return set_err(COLIBRI_E_CUDA, "no CUDA device available: the B200 path has no CPU fallback");
+    if (!key_off || !out) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(device));
+    uint64_t kb = key_off[n];
+    DevBuf<uint8_t>  dk;
+    DevBuf<uint64_t> doff, dout;
+    TRY(dk.alloc(device, kb + 1));
+    TRY(doff.alloc(device, n + 1));
+    TRY(dout.alloc(device, n));
+    if (kb) CUDA_TRY(cudaMemcpy(dk.p, keys, kb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(doff.p, key_off, (n + 1) * 8, cudaMemcpyHostToDevice));
+    launch_hash64_batch(nullptr, dk.p, doff.p, n, dout.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, dout.p, n * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int colibri_b200_corpus_tokens(colibri_b200_corpus* c, uint32_t* out, uint64_t cap, uint64_t* npositions) {
+    if (!c || !npositions) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    uint8_t tail[16];
+    memset(tail, 0x80, sizeof tail);
+    CUDA_TRY(cudaMemcpyAsync(c->body() + c->nbytes, tail, sizeof tail, cudaMemcpyHostToDevice, s));
+    const uint32_t nblocks = (uint32_t)(c->padded(c->nbytes) / kTokTile);
+    DevBuf<uint32_t>    blk;
+    DevBuf<DeviceStats> st;
+    TRY(blk.alloc(c->device, nblocks + 1));
+    TRY(st.alloc(c->device, 1));
+    CUDA_TRY(cudaMemsetAsync(st.p, 0, sizeof(DeviceStats), s));
+    if (nblocks) {
+        launch_tokenise_count(s, c->body(), c->nbytes, blk.p, nblocks);
+        launch_scan_block_counts(s, blk.p, nblocks, &st.p->cursor);
+    }
+    DeviceStats h;
+    CUDA_TRY(cudaMemcpyAsync(&h, st.p, sizeof h, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *npositions = h.cursor;
+    if (!out) return 0;
+    if (cap < h.cursor) return set_err(COLIBRI_E_INVALID, "buffer too small: %llu positions", (unsigned long long)h.cursor);
+    DevBuf<uint32_t> tok;
+    TRY(tok.alloc(c->device, h.cursor + 8));
+    if (nblocks) launch_tokenise_write(s, c->body(), c->nbytes, blk.p, nblocks, tok.p, st.p);
+    CUDA_TRY(cudaMemcpyAsync(out, tok.p, h.cursor * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(&h, st.p, sizeof h, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (h.errflags & (kErrTokenTooLong | kErrNonCanonical)) return set_err(COLIBRI_E_FORMAT, "malformed class encoding in corpus (flags %u)", h.errflags);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ synthetic corpus
+extern "C" int colibri_b200_synth_corpus(const colibri_b200_synth_params* p, int device, colibri_b200_corpus** out) {
+    if (!p || !out) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    *out = nullptr;
+    if (colibri_b200_device_count() <= 0) return set_err(COLIBRI_E_CUDA, "no CUDA device available: the B200 path has no CPU fallback");
+    if (p->vocab == 0 || p->mean_sentence == 0 || p->ntokens == 0) return set_err(COLIBRI_E_INVALID, "vocab, mean_sentence and ntokens must be positive");
+    CUDA_TRY(cudaSetDevice(device));
+    std::vector<uint64_t> cdf(p->vocab);
+    uint64_t acc = 0;
+    for (uint32_t r = 0; r < p->vocab; ++r) {  // integer Zipf table, identical to oracle_synth_cdf
+        acc += (1ULL << 40) / (uint64_t)(r + 1);
+        cdf[r] = acc;
+    }
+    DevBuf<uint64_t> dcdf, off, tmp;
+    DevBuf<uint32_t> lens;
+    TRY(dcdf.alloc(device, p->vocab));
+    TRY(lens.alloc(device, p->ntokens));
+    TRY(off.alloc(device, p->ntokens + 1));
+    TRY(tmp.alloc(device, p->ntokens / 2048 + 4));
+    CUDA_TRY(cudaMemcpy(dcdf.p, cdf.data(), cdf.size() * 8, cudaMemcpyHostToDevice));
+    launch_synth_lengths(nullptr, p->seed, p->ntokens, p->vocab, p->mean_sentence, p->phrase_permille, p->nphrases, dcdf.p, lens.p);
+    launch_exclusive_scan_u32_u64(nullptr, lens.p, off.p, p->ntokens, tmp.p);
+    uint64_t nbytes = 0;
+    CUDA_TRY(cudaMemcpy(&nbytes, off.p + p->ntokens, 8, cudaMemcpyDeviceToHost));
+    auto* c = new colibri_b200_corpus();
+    int   rc = corpus_alloc(c, device, nbytes);
+    if (rc == 0) {
+        cudaStreamSynchronize(c->stream);
+        launch_synth_write(nullptr, p->seed, p->ntokens, p->vocab, p->mean_sentence, p->phrase_permille, p->nphrases, dcdf.p, off.p, c->body());
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = set_err(COLIBRI_E_CUDA, "synthetic corpus kernel failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == 0) rc = corpus_finish(c);
+    if (rc) {
+        colibri_b200_corpus_free(c);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}

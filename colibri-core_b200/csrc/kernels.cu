@@ -1,0 +1,717 @@
+// kernels.cu -- hand-written sm_100a kernels of the PatternModel::train path.
+//
+// The reference (include/patternmodel.h:880-1345) walks the corpus once per n, builds every n-token window as a
+// heap-allocated byte string, hashes it with SpookyV2 and bumps a std::unordered_map entry after looking up the two
+// (n-1)-sub-windows in the same map.  On the device the same result is produced with fixed-width work:
+//
+//   K0  tokenise      bytes -> one u32 class id per token, 0 for a sentence delimiter  (Pattern(istream) src/pattern.cpp:483-587,
+//                     bytestoint src/classdecoder.cpp:20-43)
+//   K1  unigrams      class-indexed histogram (no hashing needed: classes are dense), threshold -> level-1 ids
+//   K2  count_ngrams  level n >= 2: a window at position p is valid iff the surviving (n-1)-grams at p and p+1 both exist
+//                     (patternmodel.h:1139-1152); its identity IS the pair of their ids, so the table key is 8 bytes for every n.
+//                     One thread per position: coalesced id reads, one 32-byte-sector probe, CAS claim or RED increment.
+//   K3  prune/compact threshold scan of the table (prune(), patternmodel.h:2107-2128) + survivor compaction, then
+//       relabel       per position: id := slot+1 if the slot survived, else 0  -> input of level n+1
+//   K5  export        survivors -> varint pattern bytes in the reference's key format (Pattern(PatternPointer) src/pattern.cpp:873-909)
+//
+// All of it is integer/byte work bound by HBM sector traffic; there is nothing here for tensor cores.
+#include "kernels.h"
+
+#include "device_utils.cuh"
+
+namespace colibri {
+
+__host__ __device__ static inline unsigned div_up(uint64_t a, uint64_t b) {
+    return (unsigned)((a + b - 1) / b);
+}
+static inline uint64_t umin64(uint64_t a, uint64_t b) {
+    return a < b ? a : b;
+}
+
+// =============================================================================================
+// K0: tokenise
+// The staged body sits 16-byte aligned, preceded by 16 zero bytes (so "previous byte" exists for byte 0 and is < 128)
+// and padded to a multiple of kTokTile with 0x80 (a continuation byte: never ends a token).
+__device__ __forceinline__ uint32_t token_end_bits(uint32_t w) {
+    return ~w & 0x80808080u;  // bit 7 of each byte set where byte < 128
+}
+
+__global__ void __launch_bounds__(256) tokenise_count_kernel(const uint8_t* __restrict__ corpus, uint32_t* __restrict__ blk_counts) {
+    const uint4* src = reinterpret_cast<const uint4*>(corpus + (uint64_t)blockIdx.x * kTokTile);
+    uint4        v   = src[threadIdx.x];
+    uint32_t     c   = __popc(token_end_bits(v.x)) + __popc(token_end_bits(v.y)) + __popc(token_end_bits(v.z)) + __popc(token_end_bits(v.w));
+    __shared__ uint64_t scratch[8];
+    uint64_t            total = block_reduce_sum(c, scratch);
+    if (threadIdx.x == 0) blk_counts[blockIdx.x] = (uint32_t)total;
+}
+
+// exclusive scan of the per-tile counts, in place, by one block (at most a few hundred thousand entries)
+__global__ void __launch_bounds__(1024) scan_block_counts_kernel(uint32_t* __restrict__ counts, uint32_t n, unsigned long long* __restrict__ total) {
+    __shared__ uint64_t part[1024];
+    uint32_t            chunk = (n + blockDim.x - 1) / blockDim.x;
+    uint32_t            lo = threadIdx.x * chunk, hi = min(n, lo + chunk);
+    uint64_t            s = 0;
+    for (uint32_t i = lo; i < hi; ++i) s += counts[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < blockDim.x; ++i) {
+            uint64_t t = part[i];
+            part[i]    = acc;
+            acc += t;
+        }
+        *total = acc;
+    }
+    __syncthreads();
+    uint64_t acc = part[threadIdx.x];
+    for (uint32_t i = lo; i < hi; ++i) {
+        uint32_t t = counts[i];
+        counts[i]  = (uint32_t)acc;  // caller guarantees the total fits 32 bits
+        acc += t;
+    }
+}
+
+__global__ void __launch_bounds__(256) tokenise_write_kernel(const uint8_t* __restrict__ corpus, const uint32_t* __restrict__ blk_offsets, uint32_t* __restrict__ tok,
+                                                             DeviceStats* __restrict__ st) {
+    __shared__ __align__(16) uint8_t tile[16 + kTokTile];
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint64_t scratch[8];
+    const uint8_t* base = corpus + (uint64_t)blockIdx.x * kTokTile;
+    uint4          v    = reinterpret_cast<const uint4*>(base)[threadIdx.x];
+    reinterpret_cast<uint4*>(tile + 16)[threadIdx.x] = v;
+    if (threadIdx.x == 0) *reinterpret_cast<uint4*>(tile) = *reinterpret_cast<const uint4*>(base - 16);
+    uint32_t w[4]  = {v.x, v.y, v.z, v.w};
+    uint32_t ends  = 0;  // bit j set: byte j of this thread's 16 ends a token
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t e = token_end_bits(w[k]);
+        ends |= (((e >> 7) & 1u) | ((e >> 14) & 2u) | ((e >> 21) & 4u) | ((e >> 28) & 8u)) << (4 * k);
+    }
+    uint32_t c    = __popc(ends);
+    uint32_t incl = warp_inclusive_scan(c);
+    if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (uint32_t i = 0; i < (threadIdx.x >> 5); ++i) woff += warp_tot[i];
+    uint64_t out = (uint64_t)blk_offsets[blockIdx.x] + woff + (incl - c);
+
+    uint32_t ntok = 0, maxc = 0, err = 0;
+    const uint8_t* mine = tile + 16 + threadIdx.x * 16;
+    while (ends) {
+        int j = __ffs(ends) - 1;
+        ends &= ends - 1;
+        const uint8_t* q = mine + j;
+        uint64_t       val = q[0];
+        int            len = 1;
+        while (len < 6 && q[-len] >= 128) {  // continuation bytes precede the final byte; little-endian base 128
+            val = (val << 7) | (q[-len] & 0x7Fu);
+            ++len;
+        }
+        if (len == 6 || val > 0xFFFFFFFFull) err |= kErrTokenTooLong;
+        if (len > 1 && q[0] == 0) err |= kErrNonCanonical;
+        uint32_t cls = (uint32_t)val;
+        if (cls == 3 || cls == 4) err |= kErrReservedClass;
+        tok[out++] = cls;
+        ntok += cls != 0;
+        maxc = max(maxc, cls);
+    }
+    uint64_t tot = block_reduce_sum(ntok, scratch);
+    maxc         = warp_reduce_max(maxc);
+    if (threadIdx.x == 0 && tot) atomicAdd(&st->totaltokens, (unsigned long long)tot);
+    if (lane_id() == 0 && maxc) atomicMax(&st->maxclass, maxc);
+    if (err) atomicOr(&st->errflags, err);
+}
+
+int launch_tokenise_count(cudaStream_t s, const uint8_t* corpus, uint64_t, uint32_t* blk_counts, uint32_t nblocks) {
+    tokenise_count_kernel<<<nblocks, 256, 0, s>>>(corpus, blk_counts);
+    return 1;
+}
+int launch_scan_block_counts(cudaStream_t s, uint32_t* blk_counts, uint32_t nblocks, unsigned long long* total) {
+    scan_block_counts_kernel<<<1, 1024, 0, s>>>(blk_counts, nblocks, total);
+    return 1;
+}
+int launch_tokenise_write(cudaStream_t s, const uint8_t* corpus, uint64_t, const uint32_t* blk_offsets, uint32_t nblocks, uint32_t* tok, DeviceStats* st) {
+    tokenise_write_kernel<<<nblocks, 256, 0, s>>>(corpus, blk_offsets, tok, st);
+    return 1;
+}
+
+// =============================================================================================
+// K1: unigrams.  Classes are dense (the encoder hands out ids by descending frequency, src/classencoder.cpp:213-226),
+// so the "hash table" of level 1 is a plain array indexed by class.  The head of a Zipf distribution would serialise
+// global atomics on a handful of addresses, so each block first counts the most frequent kHotClasses in shared memory.
+constexpr uint32_t kHotClasses = 16384;  // 64 KB of shared memory per block
+
+__global__ void __launch_bounds__(512) unigram_hist_kernel(const uint32_t* __restrict__ tok, uint64_t npos, uint32_t* __restrict__ count1) {
+    extern __shared__ uint32_t hot[];
+    for (uint32_t i = threadIdx.x; i < kHotClasses; i += blockDim.x) hot[i] = 0;
+    __syncthreads();
+    const uint64_t nvec   = npos / 4;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        uint4    v    = __ldcs(reinterpret_cast<const uint4*>(tok) + i);
+        uint32_t c[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c[k] == 0) continue;
+            if (c[k] < kHotClasses)
+                atomicAdd(&hot[c[k]], 1u);
+            else
+                atomicAdd(&count1[c[k]], 1u);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (npos & 3)) {
+        uint32_t c = tok[nvec * 4 + threadIdx.x];
+        if (c) atomicAdd(&count1[c], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kHotClasses; i += blockDim.x)
+        if (hot[i]) atomicAdd(&count1[i], hot[i]);
+}
+
+// prune(MINTOKENS, 1) (patternmodel.h:2107-2128) over the class array + totaltypes (:1199-1201, counted BEFORE pruning)
+__global__ void __launch_bounds__(256) unigram_prune_kernel(const uint32_t* __restrict__ count1, uint32_t nclasses, uint32_t threshold, uint32_t* __restrict__ sv_pos,
+                                                            uint32_t* __restrict__ sv_count, uint64_t sv_base, DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    uint64_t found = 0, kept = 0, occ = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)div_up(nclasses, 32) * 32; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t c    = i < nclasses ? count1[i] : 0;
+        bool     keep = c >= threshold && c > 0;
+        found += c > 0;
+        uint64_t idx = warp_aggregated_inc(&st->cursor, keep);
+        if (keep) {
+            sv_pos[sv_base + idx]   = (uint32_t)i;  // level 1 survivors carry the class id instead of a position
+            sv_count[sv_base + idx] = c;
+            ++kept;
+            occ += c;
+        }
+    }
+    found = block_reduce_sum(found, scratch);
+    kept  = block_reduce_sum(kept, scratch);
+    occ   = block_reduce_sum(occ, scratch);
+    if (threadIdx.x == 0) {
+        if (found) atomicAdd(&st->found, (unsigned long long)found);
+        if (kept) atomicAdd(&st->kept, (unsigned long long)kept);
+        if (occ) atomicAdd(&st->kept_occ, (unsigned long long)occ);
+    }
+}
+
+// level-1 id of a position: its class if that unigram survived (and meets MINTOKENS_UNIGRAMS, patternmodel.h:1094-1104), else 0
+__global__ void __launch_bounds__(256) make_id1_kernel(const uint32_t* __restrict__ tok, uint64_t npos, const uint32_t* __restrict__ count1, uint32_t threshold,
+                                                       uint32_t* __restrict__ id1) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npos) return;
+    uint32_t c = tok[i];
+    id1[i]     = (c != 0 && __ldg(&count1[c]) >= threshold) ? c : 0;
+}
+
+int launch_unigram_hist(cudaStream_t s, const uint32_t* tok, uint64_t npos, uint32_t* count1, uint32_t, int sms) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(unigram_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHotClasses * 4);
+        configured = true;
+    }
+    unigram_hist_kernel<<<sms * 3, 512, kHotClasses * 4, s>>>(tok, npos, count1);
+    return 1;
+}
+int launch_unigram_prune(cudaStream_t s, const uint32_t* count1, uint32_t nclasses, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint64_t sv_base, DeviceStats* st) {
+    unsigned grid = min(div_up(nclasses, 256), 148u * 8u);
+    unigram_prune_kernel<<<grid, 256, 0, s>>>(count1, nclasses, threshold, sv_pos, sv_count, sv_base, st);
+    return 1;
+}
+int launch_make_id1(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* count1, uint32_t threshold, uint32_t* id1) {
+    make_id1_kernel<<<div_up(npos, 256), 256, 0, s>>>(tok, npos, count1, threshold, id1);
+    return 1;
+}
+
+// =============================================================================================
+// K2: the n-gram upsert kernel (n >= 2).  Replaces, per window: two has() lookups + add() of the reference
+// (patternmodel.h:1139-1161), i.e. 3 heap allocations, 3-4 SpookyV2 hashes and 3 chained-bucket walks.
+//
+// prev[p] = id of the surviving (n-1)-gram starting at position p, 0 if there is none (pruned, or the window
+// would cross a sentence delimiter).  Window p of size n is valid iff prev[p] and prev[p+1] are both non-zero,
+// and two valid windows are the same n-gram iff they agree on that pair: the pair is the key.
+__device__ __forceinline__ uint32_t upsert_ngram(NgramSlot* __restrict__ table, uint64_t cap, unsigned long long key, uint32_t pos, uint32_t& probes, bool& full) {
+    uint64_t slot = fast_range(spooky_hash64_u64(key, 0), cap);
+    for (uint64_t step = 0; step < cap; ++step) {
+        NgramSlot*         s   = table + slot;
+        unsigned long long cur = __ldcg(&s->key);  // keys never change once set, so a stale "empty" is the only possible staleness
+        ++probes;
+        if (cur == 0) {
+            cur = atomicCAS(&s->key, 0ull, key);
+            if (cur == 0) {  // claimed: remember where this n-gram can be read back from
+                s->pos = pos;
+                cur    = key;
+            }
+        }
+        if (cur == key) {
+            atomicAdd(&s->count, 1u);  // result unused -> RED
+            return (uint32_t)slot + 1;
+        }
+        slot = slot + 1 == cap ? 0 : slot + 1;
+    }
+    full = true;
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) count_ngrams_kernel(const uint32_t* __restrict__ prev, uint32_t* __restrict__ cur, uint64_t npos, NgramSlot* __restrict__ table,
+                                                           uint64_t cap, DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t       valid = 0, probes = 0;
+    bool           full = false;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += stride) {
+        uint32_t a  = __ldcs(prev + p);
+        uint32_t b  = __ldg(prev + p + 1);  // prev has npos+1 entries, the last one 0
+        uint32_t id = 0;
+        if (a != 0 && b != 0) {
+            ++valid;
+            id = upsert_ngram(table, cap, ((unsigned long long)a << 32) | b, (uint32_t)p, probes, full);
+        }
+        __stcs(cur + p, id);
+    }
+    uint64_t v  = block_reduce_sum(valid, scratch);
+    uint64_t pr = block_reduce_sum(probes, scratch);
+    if (threadIdx.x == 0) {
+        if (v) atomicAdd(&st->valid_windows, (unsigned long long)v);
+        if (pr) atomicAdd(&st->probes, (unsigned long long)pr);
+    }
+    if (full) atomicOr(&st->errflags, kErrTableFull);
+}
+
+// K3: prune(MINTOKENS, n) as a table scan: statistics + compaction of the survivors
+__global__ void __launch_bounds__(256) prune_ngrams_kernel(const NgramSlot* __restrict__ table, uint64_t cap, uint32_t threshold, uint32_t* __restrict__ sv_pos,
+                                                           uint32_t* __restrict__ sv_count, uint64_t sv_base, DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    uint64_t       found = 0, kept = 0, occ = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounded = (cap + 31) / 32 * 32;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (i < cap) raw = __ldcs(reinterpret_cast<const uint4*>(table) + i);
+        bool used = (raw.x | raw.y) != 0;
+        bool keep = used && raw.z >= threshold;
+        found += used;
+        uint64_t idx = warp_aggregated_inc(&st->cursor, keep);
+        if (keep) {
+            sv_pos[sv_base + idx]   = raw.w;
+            sv_count[sv_base + idx] = raw.z;
+            ++kept;
+            occ += raw.z;
+        }
+    }
+    found = block_reduce_sum(found, scratch);
+    kept  = block_reduce_sum(kept, scratch);
+    occ   = block_reduce_sum(occ, scratch);
+    if (threadIdx.x == 0) {
+        if (found) atomicAdd(&st->found, (unsigned long long)found);
+        if (kept) atomicAdd(&st->kept, (unsigned long long)kept);
+        if (occ) atomicAdd(&st->kept_occ, (unsigned long long)occ);
+    }
+}
+
+// after pruning: a position keeps its id only if its n-gram survived
+__global__ void __launch_bounds__(256) relabel_kernel(uint32_t* __restrict__ cur, uint64_t npos, const NgramSlot* __restrict__ table, uint32_t threshold) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npos) return;
+    uint32_t id = cur[i];
+    if (id != 0 && __ldcg(&table[id - 1].count) < threshold) cur[i] = 0;
+}
+
+static int blocks_per_sm(const void* fn, int threads, size_t smem) {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, threads, smem);
+    return n > 0 ? n : 1;
+}
+
+int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms) {
+    static int bps = blocks_per_sm((const void*)count_ngrams_kernel, 256, 0);
+    uint64_t   want = div_up(npos, 256);
+    unsigned   grid = (unsigned)umin64(want, (uint64_t)sms * bps * 4);
+    count_ngrams_kernel<<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, st);
+    return 1;
+}
+int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint64_t sv_base, DeviceStats* st, int sms) {
+    static int bps = blocks_per_sm((const void*)prune_ngrams_kernel, 256, 0);
+    unsigned   grid = (unsigned)umin64(div_up(cap, 256), (uint64_t)sms * bps * 2);
+    prune_ngrams_kernel<<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, sv_base, st);
+    return 1;
+}
+int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const NgramSlot* table, uint32_t threshold) {
+    relabel_kernel<<<div_up(npos, 256), 256, 0, s>>>(cur, npos, table, threshold);
+    return 1;
+}
+
+// =============================================================================================
+// Skipgrams (exhaustive mode, patternmodel.h:1163-1171 -> computeskipgrams :1370-1527).  A window that is valid for
+// the n-gram pass is valid for every gap mask.  The skipgram's identity is the mask plus the ids of its
+// contiguous non-gap runs, each of which is a surviving k-gram (k < n) whose id sits in ids[k][p + start].
+__device__ __forceinline__ void cas128(SkipSlot* addr, unsigned long long new0, unsigned long long new1, unsigned long long& old0, unsigned long long& old1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b128 cmp, val, old;\n\t"
+        "mov.b128 cmp, {%3, %3};\n\t"
+        "mov.b128 val, {%4, %5};\n\t"
+        "atom.global.cas.b128 old, [%2], cmp, val;\n\t"
+        "mov.b128 {%0, %1}, old;\n\t"
+        "}"
+        : "=l"(old0), "=l"(old1)
+        : "l"(addr), "l"(0ull), "l"(new0), "l"(new1)
+        : "memory");
+}
+
+// find-or-claim the slot of a 128-bit key; returns slot index + 1 (0 when the table is full)
+__device__ __forceinline__ uint32_t upsert_skipkey(SkipSlot* __restrict__ table, uint64_t cap, unsigned long long k0, unsigned long long k1, bool count, uint32_t pos) {
+    uint64_t slot = fast_range(spooky_hash64_u128(k0, k1, 0), cap);
+    for (uint64_t step = 0; step < cap; ++step) {
+        SkipSlot*          s  = table + slot;
+        ulonglong2         kv = __ldcg(reinterpret_cast<const ulonglong2*>(s));
+        unsigned long long c0 = kv.x, c1 = kv.y;
+        if (c0 == 0 || c1 == 0) {  // empty (or caught mid-claim): the CAS result is authoritative
+            cas128(s, k0, k1, c0, c1);
+            if (c0 == 0 && c1 == 0) {
+                s->pos = pos;
+                c0     = k0;
+                c1     = k1;
+            }
+        }
+        if (c0 == k0 && c1 == k1) {
+            if (count) atomicAdd(&s->count, 1u);
+            return (uint32_t)slot + 1;
+        }
+        slot = slot + 1 == cap ? 0 : slot + 1;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) count_skipgrams_kernel(const uint32_t* const* __restrict__ ids, int n, const SkipMask* __restrict__ masks, int nmasks, uint64_t npos,
+                                                              SkipSlot* __restrict__ table, uint64_t cap, DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    const uint32_t* prev  = ids[n - 1];
+    const uint64_t  total = npos * (uint64_t)nmasks;
+    uint32_t        valid = 0;
+    bool            full  = false;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t p = t / nmasks;
+        int      m = (int)(t - p * nmasks);
+        if (__ldg(prev + p) == 0 || __ldg(prev + p + 1) == 0) continue;
+        const SkipMask* sm     = masks + m;
+        const uint32_t  mask   = __ldg(&sm->mask);
+        const uint32_t  nparts = __ldg(&sm->nparts);
+        uint32_t part[kMaxSkipParts];
+#pragma unroll
+        for (int k = 0; k < kMaxSkipParts; ++k)
+            part[k] = (uint32_t)k < nparts ? __ldg(ids[__ldg(&sm->len[k])] + p + __ldg(&sm->start[k])) : 0;
+        // fold the three leading ids into one until at most three remain (only masks with > 3 runs, i.e. n >= 7)
+        uint32_t left = nparts, rounds = 0, first = 0;  // part[first..first+left) are the live ids
+        while (left > 3) {
+            ++rounds;
+            unsigned long long h0 = ((unsigned long long)(mask | kSkipCombiner | (rounds << kSkipRoundShift)) << 32) | part[first];
+            unsigned long long h1 = ((unsigned long long)part[first + 1] << 32) | part[first + 2];
+            uint32_t           u  = upsert_skipkey(table, cap, h0, h1, false, (uint32_t)p);
+            if (u == 0) full = true;
+            first += 2;
+            part[first] = u;
+            left -= 2;
+        }
+        unsigned long long k0 = ((unsigned long long)(mask | (rounds << kSkipRoundShift)) << 32) | part[first];
+        unsigned long long k1 = ((unsigned long long)part[first + 1] << 32) | (left > 2 ? part[first + 2] : 0u);
+        ++valid;
+        if (upsert_skipkey(table, cap, k0, k1, true, (uint32_t)p) == 0) full = true;
+    }
+    uint64_t v = block_reduce_sum(valid, scratch);
+    if (threadIdx.x == 0 && v) atomicAdd(&st->valid_windows, (unsigned long long)v);
+    if (full) atomicOr(&st->errflags, kErrTableFull);
+}
+
+__global__ void __launch_bounds__(256) prune_skipgrams_kernel(const SkipSlot* __restrict__ table, uint64_t cap, uint32_t threshold, uint32_t* __restrict__ sv_pos,
+                                                              uint32_t* __restrict__ sv_count, uint32_t* __restrict__ sv_mask, uint64_t sv_base, DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    uint64_t       found = 0, kept = 0, occ = 0;
+    const uint64_t rounded = (cap + 31) / 32 * 32;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
+        if (i < cap) {
+            lo = __ldcs(reinterpret_cast<const uint4*>(table + i));
+            hi = __ldcs(reinterpret_cast<const uint4*>(table + i) + 1);
+        }
+        bool used = (lo.x | lo.y) != 0 && (lo.y & kSkipCombiner) == 0;  // helper entries are ids, not patterns
+        bool keep = used && hi.x >= threshold;
+        found += used;
+        uint64_t idx = warp_aggregated_inc(&st->cursor, keep);
+        if (keep) {
+            sv_pos[sv_base + idx]   = hi.y;
+            sv_count[sv_base + idx] = hi.x;
+            sv_mask[sv_base + idx]  = lo.y & 0x00FFFFFFu;  // high word of k0 = gap mask (+ round bits, dropped)
+            ++kept;
+            occ += hi.x;
+        }
+    }
+    found = block_reduce_sum(found, scratch);
+    kept  = block_reduce_sum(kept, scratch);
+    occ   = block_reduce_sum(occ, scratch);
+    if (threadIdx.x == 0) {
+        if (found) atomicAdd(&st->found, (unsigned long long)found);
+        if (kept) atomicAdd(&st->kept, (unsigned long long)kept);
+        if (occ) atomicAdd(&st->kept_occ, (unsigned long long)occ);
+    }
+}
+
+int launch_count_skipgrams(cudaStream_t s, const uint32_t* const* ids, int n, const SkipMask* masks, int nmasks, uint64_t npos, SkipSlot* table, uint64_t cap, DeviceStats* st,
+                           int sms) {
+    static int bps  = blocks_per_sm((const void*)count_skipgrams_kernel, 256, 0);
+    unsigned   grid = (unsigned)umin64(div_up(npos * nmasks, 256), (uint64_t)sms * bps * 4);
+    count_skipgrams_kernel<<<grid ? grid : 1, 256, 0, s>>>(ids, n, masks, nmasks, npos, table, cap, st);
+    return 1;
+}
+int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask, uint64_t sv_base,
+                           DeviceStats* st, int sms) {
+    static int bps  = blocks_per_sm((const void*)prune_skipgrams_kernel, 256, 0);
+    unsigned   grid = (unsigned)umin64(div_up(cap, 256), (uint64_t)sms * bps * 2);
+    prune_skipgrams_kernel<<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, sv_mask, sv_base, st);
+    return 1;
+}
+
+// =============================================================================================
+// K5: export.  A survivor is (position | class, count, n | mask << 8); its key bytes are re-encoded from the token
+// array in the reference's pattern format: varint per token, gap tokens collapsed to the single byte 0x03
+// (Pattern(const PatternPointer&), src/pattern.cpp:873-909).
+__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t* __restrict__ dst, uint64_t n, uint32_t value) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = value;
+}
+
+__global__ void __launch_bounds__(256) pack_nm_kernel(uint32_t* __restrict__ nm, uint64_t count, uint32_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) nm[i] = n | (nm[i] << 8);
+}
+int launch_pack_nm(cudaStream_t s, uint32_t* nm, uint64_t count, uint32_t n) {
+    if (!count) return 0;
+    pack_nm_kernel<<<div_up(count, 256), 256, 0, s>>>(nm, count, n);
+    return 1;
+}
+
+__device__ __forceinline__ uint32_t pattern_bytes(const uint32_t* __restrict__ tok, uint32_t pos, uint32_t nm, uint8_t* out) {
+    uint32_t n = nm & 0xFFu, mask = nm >> 8, len = 0;
+    if (n == 1) return out ? varint_put(out, pos) : varint_len(pos);
+    for (uint32_t j = 0; j < n; ++j) {
+        bool gap = j < 24 && ((mask >> j) & 1u);
+        if (gap) {
+            if (out) out[len] = 3;
+            len += 1;
+        } else {
+            uint32_t c = __ldg(tok + pos + j);
+            len += out ? varint_put(out + len, c) : varint_len(c);
+        }
+    }
+    return len;
+}
+
+__global__ void __launch_bounds__(256) export_lengths_kernel(const uint32_t* __restrict__ tok, const uint32_t* __restrict__ sv_pos, const uint32_t* __restrict__ sv_nm, uint64_t n,
+                                                             uint32_t* __restrict__ lens) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lens[i] = pattern_bytes(tok, sv_pos[i], sv_nm[i], nullptr);
+}
+__global__ void __launch_bounds__(256) export_write_kernel(const uint32_t* __restrict__ tok, const uint32_t* __restrict__ sv_pos, const uint32_t* __restrict__ sv_nm,
+                                                           const uint64_t* __restrict__ off, uint64_t n, uint8_t* __restrict__ keys) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pattern_bytes(tok, sv_pos[i], sv_nm[i], keys + off[i]);
+}
+// record i occupies [off[i] + 5*i, ...): key bytes, 0x00, little-endian u32 count
+__global__ void __launch_bounds__(256) export_write_modelfile_kernel(const uint32_t* __restrict__ tok, const uint32_t* __restrict__ sv_pos, const uint32_t* __restrict__ sv_nm,
+                                                                     const uint32_t* __restrict__ sv_count, const uint64_t* __restrict__ off, uint64_t n,
+                                                                     uint8_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t* rec = out + off[i] + 5 * i;
+    uint32_t len = pattern_bytes(tok, sv_pos[i], sv_nm[i], rec);
+    uint32_t c   = sv_count[i];
+    rec[len]     = 0;
+    rec[len + 1] = (uint8_t)c;
+    rec[len + 2] = (uint8_t)(c >> 8);
+    rec[len + 3] = (uint8_t)(c >> 16);
+    rec[len + 4] = (uint8_t)(c >> 24);
+}
+
+// exclusive scan u32 -> u64 over n items, out has n+1 entries (out[n] = total).  Three small kernels, 2048 items per block.
+constexpr int kScanItems = 2048;
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ sums) {
+    __shared__ uint64_t scratch[32];
+    uint64_t base = (uint64_t)blockIdx.x * kScanItems;
+    uint64_t v    = 0;
+    for (int k = 0; k < 2; ++k) {
+        uint64_t i = base + threadIdx.x + (uint64_t)k * 1024;
+        if (i < n) v += in[i];
+    }
+    v = block_reduce_sum(v, scratch);
+    if (threadIdx.x == 0) sums[blockIdx.x] = v;
+}
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint64_t* __restrict__ sums, uint64_t nb) {
+    __shared__ uint64_t part[1024];
+    uint64_t chunk = (nb + blockDim.x - 1) / blockDim.x;
+    uint64_t lo = threadIdx.x * chunk, hi = min(nb, lo + chunk);
+    uint64_t s = 0;
+    for (uint64_t i = lo; i < hi; ++i) s += sums[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < blockDim.x; ++i) {
+            uint64_t t = part[i];
+            part[i]    = acc;
+            acc += t;
+        }
+        sums[nb] = acc;
+    }
+    __syncthreads();
+    uint64_t acc = part[threadIdx.x];
+    for (uint64_t i = lo; i < hi; ++i) {
+        uint64_t t = sums[i];
+        sums[i]    = acc;
+        acc += t;
+    }
+}
+__global__ void __launch_bounds__(1024) scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ sums, uint64_t nb, uint64_t* __restrict__ out) {
+    __shared__ uint32_t warp_tot[32];
+    uint64_t base = (uint64_t)blockIdx.x * kScanItems;
+    uint64_t i0 = base + (uint64_t)threadIdx.x * 2, i1 = i0 + 1;  // two consecutive items per thread
+    uint32_t a = i0 < n ? in[i0] : 0, b = i1 < n ? in[i1] : 0;
+    uint32_t c = a + b;  // a block covers 2048 items of < 2^20 each in practice; per-block sums stay far below 2^32
+    uint32_t incl = warp_inclusive_scan(c);
+    if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t t = warp_tot[threadIdx.x];
+        uint32_t s = warp_inclusive_scan(t);
+        warp_tot[threadIdx.x] = s - t;
+    }
+    __syncthreads();
+    uint64_t excl = sums[blockIdx.x] + warp_tot[threadIdx.x >> 5] + (incl - c);
+    if (i0 < n) out[i0] = excl;
+    if (i1 < n) out[i1] = excl + a;
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = sums[nb];
+}
+
+int launch_fill_u32(cudaStream_t s, uint32_t* dst, uint64_t n, uint32_t value) {
+    if (!n) return 0;
+    fill_u32_kernel<<<div_up(n, 256), 256, 0, s>>>(dst, n, value);
+    return 1;
+}
+int launch_export_lengths(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, uint64_t n, uint32_t* lens) {
+    if (!n) return 0;
+    export_lengths_kernel<<<div_up(n, 256), 256, 0, s>>>(tok, sv_pos, sv_nm, n, lens);
+    return 1;
+}
+int launch_exclusive_scan_u32_u64(cudaStream_t s, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* tmp) {
+    uint64_t nb = n ? (n + kScanItems - 1) / kScanItems : 1;
+    scan_block_sums_kernel<<<(unsigned)nb, 1024, 0, s>>>(in, n, tmp);
+    scan_sums_kernel<<<1, 1024, 0, s>>>(tmp, nb);
+    scan_apply_kernel<<<(unsigned)nb, 1024, 0, s>>>(in, n, tmp, nb, out);
+    return 3;
+}
+int launch_export_write(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, const uint64_t* off, uint64_t n, uint8_t* keys) {
+    if (!n) return 0;
+    export_write_kernel<<<div_up(n, 256), 256, 0, s>>>(tok, sv_pos, sv_nm, off, n, keys);
+    return 1;
+}
+int launch_export_write_modelfile(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, const uint32_t* sv_count, const uint64_t* off, uint64_t n,
+                                  uint8_t* out) {
+    if (!n) return 0;
+    export_write_modelfile_kernel<<<div_up(n, 256), 256, 0, s>>>(tok, sv_pos, sv_nm, sv_count, off, n, out);
+    return 1;
+}
+
+// =============================================================================================
+// Pattern::hash on the device for arbitrary pattern bytes (parity row a5)
+__global__ void __launch_bounds__(256) hash64_batch_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, uint64_t n, uint64_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t b = off[i], e = off[i + 1];
+    // src/pattern.cpp:234-236: an empty pattern hashes to 0
+    out[i] = (e == b || keys[b] == 0) ? 0 : spooky_hash64(keys + b, (uint32_t)(e - b), 0);
+}
+int launch_hash64_batch(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t n, uint64_t* out) {
+    if (!n) return 0;
+    hash64_batch_kernel<<<div_up(n, 256), 256, 0, s>>>(keys, off, n, out);
+    return 1;
+}
+
+// =============================================================================================
+// Synthetic corpus (measurement input).  Must stay bit-identical to oracle/oracle.c: oracle_synth_*.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t rnd(uint64_t seed, uint64_t stream, uint64_t i) {
+    return mix64((seed + stream * 0xD1B54A32D192ED03ULL) ^ mix64(i));
+}
+struct SynthArgs {
+    uint64_t        seed, ntokens;
+    uint32_t        vocab, mean_sentence, phrase_permille, nphrases;
+    const uint64_t* cdf;
+};
+__device__ __forceinline__ uint32_t zipf_rank(const SynthArgs& a, uint64_t u) {
+    uint64_t x  = u % __ldg(a.cdf + a.vocab - 1);
+    uint32_t lo = 0, hi = a.vocab - 1;
+    while (lo < hi) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (__ldg(a.cdf + mid) > x)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ bool phrase_info(const SynthArgs& a, uint64_t i, uint64_t& id, uint32_t& j, uint32_t& L) {
+    if (!a.phrase_permille || !a.nphrases) return false;
+    uint64_t b = i >> 3;
+    if (rnd(a.seed, 2, b) % 1000 >= a.phrase_permille) return false;
+    id         = rnd(a.seed, 4, b) % a.nphrases;
+    L          = 3 + (uint32_t)(rnd(a.seed, 3, id) % 4);
+    uint32_t k = (uint32_t)(i & 7);
+    if (k >= L) return false;
+    j = k;
+    return true;
+}
+__device__ __forceinline__ void synth_token(const SynthArgs& a, uint64_t i, uint32_t& cls, bool& brk) {
+    uint64_t id;
+    uint32_t j, L;
+    bool     inphrase = phrase_info(a, i, id, j, L);
+    cls               = 6 + zipf_rank(a, inphrase ? rnd(a.seed, 5, id * 8 + j) : rnd(a.seed, 0, i));
+    brk               = (inphrase && j + 1 < L) ? false : (rnd(a.seed, 1, i) % a.mean_sentence == 0);
+    if (i + 1 == a.ntokens) brk = true;
+}
+__global__ void __launch_bounds__(256) synth_lengths_kernel(SynthArgs a, uint32_t* __restrict__ lens) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.ntokens) return;
+    uint32_t cls;
+    bool     brk;
+    synth_token(a, i, cls, brk);
+    lens[i] = varint_len(cls) + (brk ? 1u : 0u);
+}
+__global__ void __launch_bounds__(256) synth_write_kernel(SynthArgs a, const uint64_t* __restrict__ off, uint8_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.ntokens) return;
+    uint32_t cls;
+    bool     brk;
+    synth_token(a, i, cls, brk);
+    uint8_t* o = out + off[i];
+    uint32_t l = varint_put(o, cls);
+    if (brk) o[l] = 0;
+}
+int launch_synth_lengths(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases, const uint64_t* cdf,
+                         uint32_t* lens) {
+    SynthArgs a{seed, ntokens, vocab, mean_sentence, phrase_permille, nphrases, cdf};
+    synth_lengths_kernel<<<div_up(ntokens, 256), 256, 0, s>>>(a, lens);
+    return 1;
+}
+int launch_synth_write(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases, const uint64_t* cdf,
+                       const uint64_t* off, uint8_t* out) {
+    SynthArgs a{seed, ntokens, vocab, mean_sentence, phrase_permille, nphrases, cdf};
+    synth_write_kernel<<<div_up(ntokens, 256), 256, 0, s>>>(a, off, out);
+    return 1;
+}
+
+}  // namespace colibri

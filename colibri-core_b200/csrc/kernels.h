@@ -1,0 +1,97 @@
+// kernels.h -- launch wrappers of the sm_100a kernels (definitions in kernels.cu).
+// Every wrapper enqueues on the given stream and returns the number of kernel launches it made.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace colibri {
+
+// One slot of the n-gram table: 16 bytes, two per 32-byte HBM sector.
+//   key   = (id of the surviving (n-1)-gram at p) << 32 | (id of the surviving (n-1)-gram at p+1); 0 = empty.
+//   count = occurrences, pos = a position where the n-gram occurs (any one; used to print its bytes).
+struct alignas(16) NgramSlot {
+    unsigned long long key;
+    uint32_t           count;
+    uint32_t           pos;
+};
+// One slot of the skipgram table: 32 bytes = one sector.  The 128-bit key is claimed with one atom.cas.b128.
+//   k0 = maskfield << 32 | id(part 1),  k1 = id(part 2) << 32 | id(part 3)   (ids of the contiguous non-gap runs).
+//   Masks with more than three runs first fold their leading three ids into one through a helper entry of the
+//   same table (flag kSkipCombiner; its slot index is the folded id), repeatedly, until three ids remain.
+struct alignas(32) SkipSlot {
+    unsigned long long k0, k1;
+    uint32_t           count;
+    uint32_t           pos;
+    uint32_t           pad[2];
+};
+
+// per-train device-side statistics block (zeroed by the host before each phase that uses it)
+struct DeviceStats {
+    unsigned long long totaltokens;    // non-delimiter positions
+    unsigned long long found;          // occupied slots of the table just scanned
+    unsigned long long kept;           // ... with count >= threshold
+    unsigned long long kept_occ;       // sum of their counts
+    unsigned long long cursor;         // compaction cursor into the survivor arrays
+    unsigned long long valid_windows;  // upserts issued by the last count kernel
+    unsigned long long probes;         // probe steps of the last count kernel (diagnostic)
+    unsigned int       maxclass;
+    unsigned int       errflags;       // kErr* bits
+};
+constexpr unsigned kErrTokenTooLong  = 1u;  // varint longer than 5 bytes / class >= 2^32
+constexpr unsigned kErrNonCanonical  = 2u;  // multi-byte token whose last byte is 0
+constexpr unsigned kErrReservedClass = 4u;  // class 3 (skip) or 4 (flex) in running text
+constexpr unsigned kErrTableFull     = 8u;  // a probe sequence wrapped the whole table
+
+// gap configuration of one skipgram mask, precomputed on the host (compute_skip_configurations, src/algorithms.cpp:79-94)
+constexpr int kMaxSkipParts = 12;
+struct SkipMask {
+    uint32_t mask;
+    uint32_t nparts;                 // number of contiguous non-gap runs (2 .. kMaxSkipParts)
+    uint8_t  start[kMaxSkipParts];   // first token of each run, relative to the window
+    uint8_t  len[kMaxSkipParts];     // tokens in each run
+};
+constexpr int      kMaxSkipMasks   = 4096;
+constexpr uint32_t kSkipCombiner   = 0x80000000u;  // mask-field flag: an id-combining helper entry, not a pattern
+constexpr uint32_t kSkipRoundShift = 24;           // mask-field bits 24..30: number of combining rounds behind the key
+
+// ---- K0: corpus bytes -> class ids (0 = sentence delimiter)
+constexpr int kTokTile = 4096;  // bytes per block
+int launch_tokenise_count(cudaStream_t s, const uint8_t* corpus, uint64_t nbytes, uint32_t* blk_counts, uint32_t nblocks);
+int launch_scan_block_counts(cudaStream_t s, uint32_t* blk_counts, uint32_t nblocks, unsigned long long* total);
+int launch_tokenise_write(cudaStream_t s, const uint8_t* corpus, uint64_t nbytes, const uint32_t* blk_offsets, uint32_t nblocks, uint32_t* tok, DeviceStats* st);
+
+// ---- K1: unigram histogram, unigram prune, level-1 ids
+int launch_unigram_hist(cudaStream_t s, const uint32_t* tok, uint64_t npos, uint32_t* count1, uint32_t nclasses, int sms);
+int launch_unigram_prune(cudaStream_t s, const uint32_t* count1, uint32_t nclasses, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint64_t sv_base, DeviceStats* st);
+int launch_make_id1(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* count1, uint32_t threshold, uint32_t* id1);
+
+// ---- K2: n-gram upsert (the dominant kernel), K3: prune/compact, relabel
+int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms);
+int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint64_t sv_base, DeviceStats* st, int sms);
+int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const NgramSlot* table, uint32_t threshold);
+
+// ---- skipgrams (config 3)
+int launch_count_skipgrams(cudaStream_t s, const uint32_t* const* ids /*device array, index = level*/, int n, const SkipMask* masks /*device*/, int nmasks, uint64_t npos,
+                           SkipSlot* table, uint64_t cap, DeviceStats* st, int sms);
+int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask, uint64_t sv_base,
+                           DeviceStats* st, int sms);
+
+// ---- export: survivors -> pattern bytes
+// sv_nm[i] = n | mask << 8 ; for n == 1 sv_pos holds the class id itself
+int launch_fill_u32(cudaStream_t s, uint32_t* dst, uint64_t n, uint32_t value);
+int launch_pack_nm(cudaStream_t s, uint32_t* nm /*in: gap masks, out: n | mask << 8*/, uint64_t count, uint32_t n);
+int launch_export_lengths(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, uint64_t n, uint32_t* lens);
+int launch_exclusive_scan_u32_u64(cudaStream_t s, const uint32_t* in, uint64_t* out /*n+1*/, uint64_t n, uint64_t* tmp /*>= n/2048+2*/);
+int launch_export_write(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, const uint64_t* off, uint64_t n, uint8_t* keys);
+// model-file body: per pattern  key bytes, 0x00, u32 count  (unindexed; patternstore.h:534-542 + datatypes.h:216-221)
+int launch_export_write_modelfile(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, const uint32_t* sv_count, const uint64_t* off, uint64_t n,
+                                  uint8_t* out);
+
+// ---- parity helpers / measurement input
+int launch_hash64_batch(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t n, uint64_t* out);
+int launch_synth_lengths(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases, const uint64_t* cdf,
+                         uint32_t* lens);
+int launch_synth_write(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases, const uint64_t* cdf,
+                       const uint64_t* off, uint8_t* out);
+
+}  // namespace colibri

@@ -1,0 +1,156 @@
+/* colibri_b200.h -- C ABI of the B200-native PatternModel::train path.
+ *
+ * The reference (proycon/colibri-core) has no FFI seam of its own: the boundary a
+ * caller sees is the C++ class API
+ *     PatternModel<uint32_t>::train(std::istream*, const PatternModelOptions&, ...)   include/patternmodel.h:880
+ *     PatternModel<uint32_t>::train(const std::string&, ...)                          include/patternmodel.h:1353
+ *     IndexedPatternModel<>::train(...)                                               include/patternmodel.h:2821-2844
+ * called from src/patternmodeller.cpp:319, src/benchmarks.cpp:224, src/test.cpp:1212/1226/1266 and the Cython
+ * wrapper colibricore_patternmodel.pxi:290/294.  This header is what an implementation of that method binds to:
+ * plain pointers and sizes, no C++ or torch types.  The host-side mirror of the class API that calls it lives in
+ * colibri-core_b200/host/ (C++), INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a COLIBRI_E_* code otherwise; the message is in
+ *     colibri_b200_last_error() (thread local).  The C++ wrapper prints it on std::cerr and throws InternalError,
+ *     which is the reference's error convention (include/common.h:41-44, patternmodel.h:958-963).
+ *   - "corpus" always means the BODY of a .colibri.dat v2 file: the bytes after the 0xA2 0x02 header
+ *     (src/classencoder.cpp:551-556; train() itself seeks to offset 2, patternmodel.h:997-1004).
+ *   - device memory is owned by the library; host buffers are owned by the caller.
+ *   - one host thread per handle (the reference is single threaded and not re-entrant either).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with COLIBRI_E_CUDA.
+ */
+#ifndef COLIBRI_B200_H
+#define COLIBRI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COLIBRI_OK 0
+#define COLIBRI_E_INVALID 1     /* bad argument */
+#define COLIBRI_E_UNSUPPORTED 2 /* option combination outside the accelerated subset */
+#define COLIBRI_E_CUDA 3        /* CUDA runtime failure, or no device */
+#define COLIBRI_E_FORMAT 4      /* corpus bytes are not a well-formed class-encoded v2 stream */
+#define COLIBRI_E_CAPACITY 5    /* a device table or index would exceed its addressable size */
+
+#define COLIBRI_UNINDEXEDPATTERNMODEL 10 /* include/patternmodel.h:68-75 */
+#define COLIBRI_INDEXEDPATTERNMODEL 20
+
+/* POD mirror of the PatternModelOptions fields train() reads (include/patternmodel.h:103-180; same defaults via
+ * colibri_b200_options_default) plus the two things the C++ caller decides outside the options struct. */
+typedef struct colibri_b200_options {
+    int32_t MINTOKENS;              /* -1 -> 2, 0 -> 1 (patternmodel.h:883-886) */
+    int32_t MINTOKENS_SKIPGRAMS;    /* raised to MINTOKENS (:887-888) */
+    int32_t MINTOKENS_UNIGRAMS;
+    int32_t MINLENGTH;
+    int32_t MAXLENGTH;
+    int32_t MAXBACKOFFLENGTH;
+    int32_t MINSKIPTYPES;
+    int32_t MAXSKIPS;
+    int32_t DOSKIPGRAMS;            /* non-exhaustive (indexed post-pass, :2969-3010) */
+    int32_t DOSKIPGRAMS_EXHAUSTIVE; /* counted inside train(), :1163-1171 */
+    int32_t DOPATTERNPERLINE;
+    int32_t PRUNENONSUBSUMED;
+    int32_t PRUNESUBSUMED;
+    int32_t QUIET;
+    int32_t DEBUG;
+    int32_t model_type;             /* COLIBRI_UNINDEXEDPATTERNMODEL or COLIBRI_INDEXEDPATTERNMODEL */
+    int32_t streamed;               /* 1: the caller's sentences come from Pattern(std::istream&) (src/pattern.cpp:483-587),
+                                       0: from a preloaded IndexedCorpus (src/pattern.cpp:1916-1967).  Only matters when the
+                                       last sentence lacks its 0x00 (the stream reader then repeats the last byte). */
+    int32_t device;                 /* CUDA device ordinal */
+} colibri_b200_options;
+
+typedef struct colibri_b200_corpus colibri_b200_corpus; /* a corpus body resident in HBM, tokenised lazily */
+typedef struct colibri_b200_model  colibri_b200_model;  /* a trained model: device-resident survivors + host-side stats */
+
+const char* colibri_b200_last_error(void);
+const char* colibri_b200_version(void);
+/* number of usable CUDA devices (0 when there is none or the driver is missing) */
+int         colibri_b200_device_count(void);
+void        colibri_b200_options_default(colibri_b200_options* opt);
+
+/* ---- corpus staging (replaces: std::ifstream reads of patternmodel.h:1353-1364 / IndexedCorpus::load src/pattern.cpp:1916-1967) */
+/* copy nbytes of corpus body from host memory to the device (one cudaMemcpyAsync; pinned or pageable source) */
+int  colibri_b200_corpus_stage(const uint8_t* host_body, size_t nbytes, int device, colibri_b200_corpus** out);
+/* adopt (copy, device-to-device) a body that already lives in device memory, e.g. produced by colibri_b200_synth_corpus */
+int  colibri_b200_corpus_from_device(const void* dev_body, size_t nbytes, int device, colibri_b200_corpus** out);
+size_t colibri_b200_corpus_bytes(const colibri_b200_corpus* c);
+void colibri_b200_corpus_free(colibri_b200_corpus* c);
+
+/* ---- training (replaces PatternModel::train, include/patternmodel.h:880-1345, for the subset documented in DESIGN.md) */
+/* end to end from host memory: stage + train + leave the result ready for export */
+int  colibri_b200_train(const uint8_t* host_body, size_t nbytes, const colibri_b200_options* opt, colibri_b200_model** out);
+/* from a staged corpus (device resident input); the corpus can be trained repeatedly with different options */
+int  colibri_b200_train_corpus(colibri_b200_corpus* corpus, const colibri_b200_options* opt, colibri_b200_model** out);
+void colibri_b200_model_free(colibri_b200_model* m);
+
+/* ---- what callers read after train(): size() :744, tokens() :1709, types() :1700, maxlength()/minlength() :1640-1648 */
+uint64_t colibri_b200_model_size(const colibri_b200_model* m);
+uint64_t colibri_b200_model_tokens(const colibri_b200_model* m);
+uint64_t colibri_b200_model_types(const colibri_b200_model* m);
+int      colibri_b200_model_maxn(const colibri_b200_model* m);
+int      colibri_b200_model_minn(const colibri_b200_model* m);
+int      colibri_b200_model_hasskipgrams(const colibri_b200_model* m);
+int      colibri_b200_model_type(const colibri_b200_model* m);
+/* the numbers of the progress lines " Found X ngrams...pruned Y...total kept: Z" (patternmodel.h:1195-1245):
+ * out[0]=n, out[1]=found n-grams (distinct, new), out[2]=found skipgrams (distinct, new), out[3]=pruned */
+int      colibri_b200_model_passes(const colibri_b200_model* m);
+int      colibri_b200_model_pass_stats(const colibri_b200_model* m, int pass, uint64_t out[4]);
+
+/* ---- export (replaces iteration over the PatternMap / PatternMapStore::write, include/patternstore.h:534-542)
+ * Flat form: keys = concatenated pattern bytes (no terminators), key_off[npatterns+1], counts[npatterns];
+ * indexed models add ref_off[npatterns+1] and (sentence 1-based, token 0-based) pairs sorted ascending
+ * (IndexReference, include/datatypes.h:33-89).  Pattern order is unspecified (so is the reference's). */
+int colibri_b200_model_export_sizes(colibri_b200_model* m, uint64_t* npatterns, uint64_t* keybytes, uint64_t* nrefs);
+int colibri_b200_model_export(colibri_b200_model* m, uint8_t* keys, uint64_t* key_off, uint32_t* counts, uint32_t* ref_sentence, uint16_t* ref_token, uint64_t* ref_off);
+/* the .colibri.patternmodel byte stream (include/patternmodel.h:1609-1624): returns needed size in *nbytes when buf is NULL */
+int colibri_b200_model_write(colibri_b200_model* m, uint8_t* buf, size_t cap, size_t* nbytes);
+/* occurrencecount(pattern) (include/patternmodel.h:1653-1669): key = pattern bytes without terminator; *count = 0 if absent */
+int colibri_b200_model_lookup(colibri_b200_model* m, const uint8_t* key, uint32_t len, uint32_t* count);
+
+/* ---- measurement hooks (bench.py): device time by phase, from CUDA events on the library's stream */
+#define COLIBRI_T_TOTAL 0     /* whole train_corpus call on the device (tokenise .. survivors ready) */
+#define COLIBRI_T_TOKENISE 1  /* K0 */
+#define COLIBRI_T_UNIGRAMS 2  /* K1 histogram + unigram prune */
+#define COLIBRI_T_COUNT 3     /* sum over n >= 2 of the n-gram upsert kernel (the dominant kernel) */
+#define COLIBRI_T_SKIPGRAMS 4 /* sum of the skipgram upsert kernel */
+#define COLIBRI_T_PRUNE 5     /* table scan + compaction + relabel, all levels */
+#define COLIBRI_T_EXPORT 6    /* device side of the flat export (lengths, scan, byte writer) */
+#define COLIBRI_T_H2D 7       /* corpus staging copy (colibri_b200_train only) */
+#define COLIBRI_T_INDEX 8     /* forward index fill + sort (indexed models) */
+#define COLIBRI_T_NPHASES 9
+int colibri_b200_model_timings(const colibri_b200_model* m, double ms[COLIBRI_T_NPHASES]);
+/* work counters of the last train: out[0]=positions (tokens+delimiters), out[1]=corpus bytes, out[2]=kernel launches,
+ * out[3]=n-gram upserts (valid windows, all n>=2), out[4]=skipgram upserts, out[5]=table slots initialised (sum),
+ * out[6]=unigram increments, out[7]=bytes of device memory at the peak */
+int colibri_b200_model_counters(const colibri_b200_model* m, uint64_t out[8]);
+/* per level n>=2: out[0]=valid windows (upserts), out[1]=table capacity in slots, out[2]=count-kernel ms */
+int colibri_b200_model_level_counters(const colibri_b200_model* m, int n, double out[3]);
+
+/* ---- L1 pieces exposed for parity tests of SURVEY.md 8(a) rows a1/a5/a10 */
+/* SpookyHash::Hash64(key, len, 0) computed ON THE DEVICE for n variable-length messages (Pattern::hash, src/pattern.cpp:234-238) */
+int colibri_b200_hash64_batch(const uint8_t* keys, const uint64_t* key_off, uint64_t n, uint64_t* out, int device);
+/* decode the corpus on the device and return class ids (0 = sentence delimiter) -- bytestoint, src/classdecoder.cpp:20-43 */
+int colibri_b200_corpus_tokens(colibri_b200_corpus* c, uint32_t* out, uint64_t cap, uint64_t* ntokens_and_delims);
+
+/* ---- synthetic corpus generator (measurement input, not part of the reference): counter based and integer only,
+ * bit-identical to oracle_synth_corpus.  Writes the body into a new staged corpus. */
+typedef struct colibri_b200_synth_params {
+    uint64_t seed;
+    uint64_t ntokens;
+    uint32_t vocab;
+    uint32_t mean_sentence;
+    uint32_t phrase_permille;
+    uint32_t nphrases;
+} colibri_b200_synth_params;
+int colibri_b200_synth_corpus(const colibri_b200_synth_params* p, int device, colibri_b200_corpus** out);
+/* copy a staged corpus body back to the host */
+int colibri_b200_corpus_download(const colibri_b200_corpus* c, uint8_t* host, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

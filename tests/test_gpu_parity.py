@@ -1,0 +1,176 @@
+"""Parity of the CUDA path (through the C ABI, include/colibri_b200.h) against the oracle and the committed golden
+vectors of the unmodified reference.  Bit-exact: patterns, counts, header numbers and per-pass statistics."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import case_id, corpus_body, load_cases
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_cases()
+
+
+def cb():
+    import colibri_core_b200
+
+    return colibri_core_b200
+
+
+def to_flat(model):
+    """Wrap the product's flat export into the oracle's comparison form (checker side only)."""
+    keys, key_off, counts, refs = model.export()
+    rs = rt = ro = None
+    if refs is not None:
+        rs, rt, ro = refs
+    return oracle.FlatModel(keys, key_off, counts, model.tokens(), model.types(), model.maxlength(), model.minlength(), model.hasskipgrams, model.model_type, rs, rt, ro,
+                            model.passes())
+
+
+def gpu_options(case):
+    o = case["options"]
+    return cb().PatternModelOptions(
+        MINTOKENS=o.get("mintokens", -1), MINTOKENS_SKIPGRAMS=o.get("mintokens_skipgrams", -1), MINTOKENS_UNIGRAMS=o.get("mintokens_unigrams", 1), MINLENGTH=o.get("minlength", 1),
+        MAXLENGTH=o.get("maxlength", 100), MAXBACKOFFLENGTH=o.get("maxbackofflength", 100), MINSKIPTYPES=o.get("minskiptypes", 2), DOSKIPGRAMS_EXHAUSTIVE=o["doskipgrams_exhaustive"],
+        model_type=20 if o["indexed"] else 10, streamed=o["streamed"], QUIET=1)
+
+
+def supported(case):
+    o = case["options"]
+    if o["indexed"]:
+        return False
+    if o.get("mintokens", 2) > 1 and o.get("maxbackofflength", 100) < o.get("maxlength", 100) - 1:
+        return False
+    return True
+
+
+@pytest.mark.parametrize("case", CASES, ids=[case_id(c) for c in CASES])
+def test_gpu_matches_reference_golden(golden, case):
+    body = corpus_body(golden, case["corpus"])
+    if not supported(case):
+        with pytest.raises(cb().ColibriError) as ei:
+            cb().train(body, gpu_options(case))
+        assert ei.value.code == 2  # COLIBRI_E_UNSUPPORTED: loud, never a silent fallback
+        return
+    if len(body) == 0:
+        pytest.skip("empty corpus")
+    m = cb().train(body, gpu_options(case))
+    assert m.tokens() == case["tokens"]
+    assert m.types() == case["types"]
+    assert len(m) == case["patterns"]
+    assert (m.maxlength(), m.minlength()) == (case["maxn"], case["minn"])
+    assert int(m.hasskipgrams) == case["hasskipgrams"]
+    assert [(p[1], p[3]) for p in m.passes()] == [(p[0], p[2]) for p in case["passes"]]
+    flat = to_flat(m)
+    assert int(flat.counts.sum()) == case["occurrences"]
+    assert flat.digest() == case["digest"]
+    # and against the oracle run on the same bytes
+    assert flat.same_patterns(oracle.train(body, **case["options"]))
+
+
+def test_device_spooky_matches_reference_kats(golden):
+    """Pattern::hash on the device (SpookyV2 Short, every length 1..191) against hashes produced by the reference library."""
+    msgs = [bytes.fromhex(h) for h, _ in golden["spooky"]]
+    want = np.array([v for _, v in golden["spooky"]], dtype=np.uint64)
+    got = cb().hash64_batch(msgs)
+    assert np.array_equal(got, want)
+    assert cb().hash64_batch([b""])[0] == 0
+
+
+def test_device_tokeniser_matches_codec(golden):
+    for name in ("hamlet", "republic", "threebyte", "empty_sentences", "zipf300k_phr"):
+        body = corpus_body(golden, name)
+        c = cb().Corpus.from_bytes(body)
+        got = c.tokens()
+        want, i = [], 0
+        while i < len(body):
+            v, ln = oracle.bytestoint(body[i:i + 8])
+            want.append(v)
+            i += ln
+        assert got.tolist() == want, name
+
+
+def test_device_synth_corpus_is_bit_identical_to_oracle():
+    for kw in (dict(ntokens=100000, vocab=5000, seed=1, mean_sentence=22), dict(ntokens=250000, vocab=300000, seed=9, mean_sentence=7, phrase_permille=250, nphrases=1000)):
+        dev = cb().Corpus.synthetic(**kw).download()
+        host = oracle.synth_corpus(**kw)
+        assert dev.size == host.size and np.array_equal(dev, host)
+
+
+def test_modelfile_written_by_gpu_is_reference_layout(golden):
+    body = corpus_body(golden, "hamlet")
+    m = cb().train(body, MINTOKENS=2, MAXLENGTH=3, QUIET=1)
+    blob = m.to_bytes()
+    assert len(blob) == 563 and blob[:3] == bytes([0, 10, 2])
+    assert oracle.parse_modelfile(blob).same_patterns(oracle.train(body, mintokens=2, maxlength=3))
+    assert m.occurrencecount(bytes([6])) == oracle.train(body, mintokens=2, maxlength=3).as_dict().get(bytes([6]), 0)
+    assert m.occurrencecount(bytes([5, 5, 5])) == 0
+
+
+@pytest.mark.parametrize("kw", [dict(ntokens=3000000, vocab=100000, seed=11, mean_sentence=22), dict(ntokens=2000000, vocab=50000, seed=12, mean_sentence=18, phrase_permille=200, nphrases=5000)])
+@pytest.mark.parametrize("skip", [0, 1])
+def test_gpu_matches_oracle_on_seeded_synthetic(kw, skip):
+    corpus = cb().Corpus.synthetic(**kw)
+    body = corpus.download()
+    m = cb().train(corpus, MINTOKENS=2, MAXLENGTH=5, DOSKIPGRAMS_EXHAUSTIVE=skip, streamed=0 if skip else 1, QUIET=1)
+    want = oracle.train(body, mintokens=2, maxlength=5, doskipgrams_exhaustive=skip, streamed=0 if skip else 1)
+    got = to_flat(m)
+    assert (got.tokens, got.types, len(got)) == (want.tokens, want.types, len(want))
+    assert got.passes == want.passes
+    assert got.same_patterns(want)
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref (the compiled reference) is not present")
+def test_gpu_matches_unmodified_reference_binary():
+    kw = dict(ntokens=1500000, vocab=80000, seed=21, mean_sentence=20, phrase_permille=100, nphrases=3000)
+    corpus = cb().Corpus.synthetic(**kw)
+    body = corpus.download()
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "c.colibri.dat")
+        with open(path, "wb") as f:
+            f.write(b"\xa2\x02" + body.tobytes())
+        st, err = oracle.ref_train(path, os.path.join(td, "m"), unindexed=True, t=2, l=5)
+        ref = oracle.parse_modelfile(open(os.path.join(td, "m"), "rb").read())
+    m = cb().train(corpus, MINTOKENS=2, MAXLENGTH=5, QUIET=1)
+    got = to_flat(m)
+    assert (got.tokens, got.types, len(got)) == (st["tokens"], st["types"], st["patterns"])
+    assert [(p[1], p[3]) for p in got.passes] == [(p[0], p[2]) for p in oracle.parse_ref_passes(err)]
+    assert got.same_patterns(ref)
+
+
+def test_large_corpus_invariants():
+    """BASELINE-sized properties that need no oracle: idempotence, count conservation, monotone levels."""
+    corpus = cb().Corpus.synthetic(ntokens=20000000, vocab=100000, seed=1, mean_sentence=22)
+    a = to_flat(cb().train(corpus, MINTOKENS=2, MAXLENGTH=5, QUIET=1))
+    b = to_flat(cb().train(corpus, MINTOKENS=2, MAXLENGTH=5, QUIET=1))
+    assert a.tokens == 20000000
+    assert a.digest() == b.digest()  # same corpus, same options -> same model (table order differs, canonical form does not)
+    # an n-gram cannot occur more often than its prefix: occurrences per level are non-increasing
+    n_of = np.add.reduceat((a.keys < 128).astype(np.int64), a.key_off[:-1].astype(np.int64)) if len(a) else np.zeros(0)
+    occ = [int(a.counts[n_of == n].sum()) for n in range(1, 6)]
+    assert all(x >= y for x, y in zip(occ, occ[1:]))
+    assert occ[0] <= a.tokens
+    assert int(a.counts.min()) >= 2
+    # raising the threshold can only remove patterns, and keeps the counts of the survivors
+    c = to_flat(cb().train(corpus, MINTOKENS=3, MAXLENGTH=3, QUIET=1)).canonical()
+    d = to_flat(cb().train(corpus, MINTOKENS=2, MAXLENGTH=3, QUIET=1)).canonical()
+    dd = dict(zip(d.padded_keys(32).tolist(), d.counts.tolist()))
+    ck = c.padded_keys(32).tolist()
+    assert all(dd.get(k) == v for k, v in zip(ck[:50000], c.counts.tolist()[:50000]))
+
+
+def test_error_paths():
+    lib = cb()
+    with pytest.raises(lib.ColibriError):
+        lib.train(b"", MINTOKENS=2)  # reference: "file is empty?" -> InternalError (src/pattern.cpp:520-523)
+    with pytest.raises(lib.ColibriError) as ei:
+        lib.train(bytes([6, 3, 7, 0]), MINTOKENS=1)  # reserved skip class in running text
+    assert ei.value.code == 2
+    with pytest.raises(lib.ColibriError) as ei:
+        lib.train(bytes([6, 0x80, 0x00, 7, 0]), MINTOKENS=1)  # non-canonical varint
+    assert ei.value.code == 4
+    with pytest.raises(lib.ColibriError):
+        lib.train(bytes([6, 7, 0]), DOSKIPGRAMS=1, DOSKIPGRAMS_EXHAUSTIVE=1)  # patternmodel.h:958-963

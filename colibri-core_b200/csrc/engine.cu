@@ -213,6 +213,9 @@ static int corpus_alloc(colibri_b200_corpus* c, int device, size_t nbytes) {
     if (ndev <= 0) return set_err(COLIBRI_E_CUDA, "no CUDA device available: the B200 path has no CPU fallback");
     if (device < 0 || device >= ndev) return set_err(COLIBRI_E_INVALID, "device %d out of range (have %d)", device, ndev);
     CUDA_TRY(cudaSetDevice(device));
+    // the tables are probed one 32-byte sector at a time at random addresses: ask L2 not to fetch the neighbouring sector too
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    cudaGetLastError();
     c->device = device;
     c->nbytes = nbytes;
     size_t total = kHalo + c->padded(nbytes + 2) + kTokTile;
@@ -472,9 +475,7 @@ struct Trainer {
 
 int Trainer::run() {
     CUDA_TRY(cudaSetDevice(dev));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-    sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));  // (cudaGetDeviceProperties costs milliseconds per call)
     timer.s = s;
     int h_total = timer.begin(COLIBRI_T_TOTAL);
 
@@ -562,6 +563,7 @@ int Trainer::run() {
     // ---- levels n >= 2
     std::vector<DevBuf<uint32_t>> ids(2);  // ids[k] = id array of level k (all kept when skipgrams need their parts, else ping-pong)
     DevBuf<NgramSlot>       table;
+    DevBuf<uint32_t>        bitmap;  // survivor bit per table slot of the level just pruned
     DevBuf<SkipSlot>        sktable;
     DevBuf<const uint32_t*> d_idptrs;
     DevBuf<SkipMask>        d_masks;
@@ -603,7 +605,8 @@ int Trainer::run() {
         uint64_t sv_bound = windows / std::max<uint32_t>(t, 1) + 1;
         TRY(sg.pos.alloc(dev, sv_bound));
         TRY(sg.cnt.alloc(dev, sv_bound));
-        launches += launch_prune_ngrams(s, table.p, cap, t, sg.pos.p, sg.cnt.p, 0, d_stats.p, sms);
+        if (bitmap.n < cap / 32 + 8) TRY(bitmap.alloc(dev, cap / 32 + 8));
+        launches += launch_prune_ngrams(s, table.p, cap, t, sg.pos.p, sg.cnt.p, bitmap.p, d_stats.p, sms);
         timer.end(hp);
         TRY(read_stats());
         const uint64_t found = h_stats.found, kept = h_stats.kept, occ = h_stats.kept_occ;
@@ -649,7 +652,7 @@ int Trainer::run() {
                 TRY(sk.mask.alloc(dev, kb));
                 TRY(zero_stats());
                 hp = timer.begin(COLIBRI_T_PRUNE);
-                launches += launch_prune_skipgrams(s, sktable.p, scap, ts, sk.pos.p, sk.cnt.p, sk.mask.p, 0, d_stats.p, sms);
+                launches += launch_prune_skipgrams(s, sktable.p, scap, ts, sk.pos.p, sk.cnt.p, sk.mask.p, d_stats.p, sms);
                 timer.end(hp);
                 TRY(read_stats());
                 foundskip = h_stats.found;
@@ -669,7 +672,7 @@ int Trainer::run() {
         if (n < o.MAXLENGTH && kept > 0) {
             if (t > 1) {
                 hp = timer.begin(COLIBRI_T_PRUNE);
-                launches += launch_relabel(s, cur.p, npos, table.p, t);
+                launches += launch_relabel(s, cur.p, npos, bitmap.p);
                 timer.end(hp);
             }
         }

@@ -231,6 +231,21 @@ int launch_make_id1(cudaStream_t s, const uint32_t* tok, uint64_t npos, const ui
 // prev[p] = id of the surviving (n-1)-gram starting at position p, 0 if there is none (pruned, or the window
 // would cross a sentence delimiter).  Window p of size n is valid iff prev[p] and prev[p+1] are both non-zero,
 // and two valid windows are the same n-gram iff they agree on that pair: the pair is the key.
+// 16-byte compare-and-swap against the all-zero (empty) slot: atom.global.cas.b128 (sm_90+)
+__device__ __forceinline__ void cas128(void* addr, unsigned long long new0, unsigned long long new1, unsigned long long& old0, unsigned long long& old1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b128 cmp, val, old;\n\t"
+        "mov.b128 cmp, {%3, %3};\n\t"
+        "mov.b128 val, {%4, %5};\n\t"
+        "atom.global.cas.b128 old, [%2], cmp, val;\n\t"
+        "mov.b128 {%0, %1}, old;\n\t"
+        "}"
+        : "=l"(old0), "=l"(old1)
+        : "l"(addr), "l"(0ull), "l"(new0), "l"(new1)
+        : "memory");
+}
+
 __device__ __forceinline__ uint32_t upsert_ngram(NgramSlot* __restrict__ table, uint64_t cap, unsigned long long key, uint32_t pos, uint32_t& probes, bool& full) {
     uint64_t slot = fast_range(spooky_hash64_u64(key, 0), cap);
     for (uint64_t step = 0; step < cap; ++step) {
@@ -238,11 +253,11 @@ __device__ __forceinline__ uint32_t upsert_ngram(NgramSlot* __restrict__ table, 
         unsigned long long cur = __ldcg(&s->key);  // keys never change once set, so a stale "empty" is the only possible staleness
         ++probes;
         if (cur == 0) {
-            cur = atomicCAS(&s->key, 0ull, key);
-            if (cur == 0) {  // claimed: remember where this n-gram can be read back from
-                s->pos = pos;
-                cur    = key;
-            }
+            // claim the whole slot at once: {key, count = 1, pos} -- one 128-bit CAS instead of CAS + store + RED
+            unsigned long long o0, o1;
+            cas128(s, key, 1ull | ((unsigned long long)pos << 32), o0, o1);
+            if (o0 == 0) return (uint32_t)slot + 1;
+            cur = o0;
         }
         if (cur == key) {
             atomicAdd(&s->count, 1u);  // result unused -> RED
@@ -279,26 +294,91 @@ __global__ void __launch_bounds__(256) count_ngrams_kernel(const uint32_t* __res
     if (full) atomicOr(&st->errflags, kErrTableFull);
 }
 
-// K3: prune(MINTOKENS, n) as a table scan: statistics + compaction of the survivors
-__global__ void __launch_bounds__(256) prune_ngrams_kernel(const NgramSlot* __restrict__ table, uint64_t cap, uint32_t threshold, uint32_t* __restrict__ sv_pos,
-                                                           uint32_t* __restrict__ sv_count, uint64_t sv_base, DeviceStats* __restrict__ st) {
+// K3: prune(MINTOKENS, n) as a table scan: statistics, compaction of the survivors, and a 1-bit-per-slot survivor
+// bitmap (cap/8 bytes: L2 resident) that the relabel step tests instead of going back to the table in HBM.
+// A block handles tiles of 2048 slots: each warp reads 8 x 32 consecutive slots (coalesced 512-byte loads), the block
+// reserves its output range with ONE atomicAdd per tile (a per-warp cursor atomic serialises on a single L2 address).
+constexpr int kPruneTile = 2048;
+
+template <class Slot>
+__device__ __forceinline__ void load_slot(const Slot* table, uint64_t i, uint64_t cap, uint32_t& k_lo, uint32_t& k_hi, uint32_t& count, uint32_t& pos);
+template <>
+__device__ __forceinline__ void load_slot<NgramSlot>(const NgramSlot* table, uint64_t i, uint64_t cap, uint32_t& k_lo, uint32_t& k_hi, uint32_t& count, uint32_t& pos) {
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (i < cap) raw = __ldcs(reinterpret_cast<const uint4*>(table) + i);
+    k_lo = raw.x; k_hi = raw.y; count = raw.z; pos = raw.w;
+}
+template <>
+__device__ __forceinline__ void load_slot<SkipSlot>(const SkipSlot* table, uint64_t i, uint64_t cap, uint32_t& k_lo, uint32_t& k_hi, uint32_t& count, uint32_t& pos) {
+    uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
+    if (i < cap) {
+        lo = __ldcs(reinterpret_cast<const uint4*>(table + i));
+        hi = __ldcs(reinterpret_cast<const uint4*>(table + i) + 1);
+    }
+    k_lo = lo.x; k_hi = lo.y; count = hi.x; pos = hi.y;
+}
+
+template <class Slot, bool kSkip>
+__global__ void __launch_bounds__(256) prune_table_kernel(const Slot* __restrict__ table, uint64_t cap, uint32_t threshold, uint32_t* __restrict__ sv_pos,
+                                                          uint32_t* __restrict__ sv_count, uint32_t* __restrict__ sv_mask, uint32_t* __restrict__ bitmap,
+                                                          DeviceStats* __restrict__ st) {
     __shared__ uint64_t scratch[8];
-    uint64_t       found = 0, kept = 0, occ = 0;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t rounded = (cap + 31) / 32 * 32;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
-        uint4 raw = make_uint4(0, 0, 0, 0);
-        if (i < cap) raw = __ldcs(reinterpret_cast<const uint4*>(table) + i);
-        bool used = (raw.x | raw.y) != 0;
-        bool keep = used && raw.z >= threshold;
-        found += used;
-        uint64_t idx = warp_aggregated_inc(&st->cursor, keep);
-        if (keep) {
-            sv_pos[sv_base + idx]   = raw.w;
-            sv_count[sv_base + idx] = raw.z;
-            ++kept;
-            occ += raw.z;
+    __shared__ uint32_t warp_cnt[8];
+    __shared__ unsigned long long tile_base;
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint64_t ntiles = (cap + kPruneTile - 1) / kPruneTile;
+    uint64_t found = 0, kept = 0, occ = 0;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t base = tile * kPruneTile + (uint64_t)warp * 256;
+        uint32_t pos[8], cnt[8], msk[8], keepbits[8];
+        uint32_t wtotal = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t k_lo, k_hi;
+            load_slot<Slot>(table, base + k * 32 + lane, cap, k_lo, k_hi, cnt[k], pos[k]);
+            bool used = (k_lo | k_hi) != 0;
+            if (kSkip) used = used && (k_hi & kSkipCombiner) == 0;  // helper entries are ids, not patterns
+            bool keep = used && cnt[k] >= threshold;
+            msk[k]    = k_hi & 0x00FFFFFFu;                         // skipgram: high word of k0 = gap mask (+ round bits, dropped)
+            keepbits[k] = __ballot_sync(0xffffffffu, keep);
+            found += used;
+            if (keep) {
+                ++kept;
+                occ += cnt[k];
+            }
+            wtotal += __popc(keepbits[k]);
         }
+        if (bitmap != nullptr && lane < 8) {
+            uint64_t word = (base >> 5) + lane;  // 8 consecutive words per warp: one 32-byte store
+            uint32_t bits = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bits = lane == (uint32_t)k ? keepbits[k] : bits;
+            if (word * 32 < (cap + 31) / 32 * 32) bitmap[word] = bits;
+        }
+        if (lane == 0) warp_cnt[warp] = wtotal;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; ++w) {
+                uint32_t c  = warp_cnt[w];
+                warp_cnt[w] = tot;
+                tot += c;
+            }
+            tile_base = tot ? atomicAdd(&st->cursor, (unsigned long long)tot) : 0ull;
+        }
+        __syncthreads();
+        uint64_t out = tile_base + warp_cnt[warp];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if ((keepbits[k] >> lane) & 1u) {
+                uint64_t idx = out + __popc(keepbits[k] & ((1u << lane) - 1));
+                sv_pos[idx]   = pos[k];
+                sv_count[idx] = cnt[k];
+                if (kSkip) sv_mask[idx] = msk[k];
+            }
+            out += __popc(keepbits[k]);
+        }
+        __syncthreads();  // warp_cnt / tile_base are reused by the next tile
     }
     found = block_reduce_sum(found, scratch);
     kept  = block_reduce_sum(kept, scratch);
@@ -310,12 +390,23 @@ __global__ void __launch_bounds__(256) prune_ngrams_kernel(const NgramSlot* __re
     }
 }
 
-// after pruning: a position keeps its id only if its n-gram survived
-__global__ void __launch_bounds__(256) relabel_kernel(uint32_t* __restrict__ cur, uint64_t npos, const NgramSlot* __restrict__ table, uint32_t threshold) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// after pruning: a position keeps its id only if its n-gram survived (bit test in the L2-resident survivor bitmap)
+__global__ void __launch_bounds__(256) relabel_kernel(uint32_t* __restrict__ cur, uint64_t npos, const uint32_t* __restrict__ bitmap) {
+    uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= npos) return;
-    uint32_t id = cur[i];
-    if (id != 0 && __ldcg(&table[id - 1].count) < threshold) cur[i] = 0;
+    if (i + 4 <= npos) {
+        uint4    v    = *reinterpret_cast<uint4*>(cur + i);
+        uint32_t c[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c[k] != 0 && ((__ldg(bitmap + ((c[k] - 1) >> 5)) >> ((c[k] - 1) & 31)) & 1u) == 0) c[k] = 0;
+        *reinterpret_cast<uint4*>(cur + i) = make_uint4(c[0], c[1], c[2], c[3]);
+    } else {
+        for (; i < npos; ++i) {
+            uint32_t id = cur[i];
+            if (id != 0 && ((__ldg(bitmap + ((id - 1) >> 5)) >> ((id - 1) & 31)) & 1u) == 0) cur[i] = 0;
+        }
+    }
 }
 
 static int blocks_per_sm(const void* fn, int threads, size_t smem) {
@@ -331,14 +422,14 @@ int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uin
     count_ngrams_kernel<<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, st);
     return 1;
 }
-int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint64_t sv_base, DeviceStats* st, int sms) {
-    static int bps = blocks_per_sm((const void*)prune_ngrams_kernel, 256, 0);
-    unsigned   grid = (unsigned)umin64(div_up(cap, 256), (uint64_t)sms * bps * 2);
-    prune_ngrams_kernel<<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, sv_base, st);
+int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap, DeviceStats* st, int sms) {
+    static int bps = blocks_per_sm((const void*)prune_table_kernel<NgramSlot, false>, 256, 0);
+    unsigned   grid = (unsigned)umin64(div_up(cap, kPruneTile), (uint64_t)sms * bps);
+    prune_table_kernel<NgramSlot, false><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, nullptr, bitmap, st);
     return 1;
 }
-int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const NgramSlot* table, uint32_t threshold) {
-    relabel_kernel<<<div_up(npos, 256), 256, 0, s>>>(cur, npos, table, threshold);
+int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap) {
+    relabel_kernel<<<div_up(div_up(npos, 4), 256), 256, 0, s>>>(cur, npos, bitmap);
     return 1;
 }
 
@@ -346,20 +437,6 @@ int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const NgramSlot
 // Skipgrams (exhaustive mode, patternmodel.h:1163-1171 -> computeskipgrams :1370-1527).  A window that is valid for
 // the n-gram pass is valid for every gap mask.  The skipgram's identity is the mask plus the ids of its
 // contiguous non-gap runs, each of which is a surviving k-gram (k < n) whose id sits in ids[k][p + start].
-__device__ __forceinline__ void cas128(SkipSlot* addr, unsigned long long new0, unsigned long long new1, unsigned long long& old0, unsigned long long& old1) {
-    asm volatile(
-        "{\n\t"
-        ".reg .b128 cmp, val, old;\n\t"
-        "mov.b128 cmp, {%3, %3};\n\t"
-        "mov.b128 val, {%4, %5};\n\t"
-        "atom.global.cas.b128 old, [%2], cmp, val;\n\t"
-        "mov.b128 {%0, %1}, old;\n\t"
-        "}"
-        : "=l"(old0), "=l"(old1)
-        : "l"(addr), "l"(0ull), "l"(new0), "l"(new1)
-        : "memory");
-}
-
 // find-or-claim the slot of a 128-bit key; returns slot index + 1 (0 when the table is full)
 __device__ __forceinline__ uint32_t upsert_skipkey(SkipSlot* __restrict__ table, uint64_t cap, unsigned long long k0, unsigned long long k1, bool count, uint32_t pos) {
     uint64_t slot = fast_range(spooky_hash64_u128(k0, k1, 0), cap);
@@ -424,39 +501,6 @@ __global__ void __launch_bounds__(256) count_skipgrams_kernel(const uint32_t* co
     if (full) atomicOr(&st->errflags, kErrTableFull);
 }
 
-__global__ void __launch_bounds__(256) prune_skipgrams_kernel(const SkipSlot* __restrict__ table, uint64_t cap, uint32_t threshold, uint32_t* __restrict__ sv_pos,
-                                                              uint32_t* __restrict__ sv_count, uint32_t* __restrict__ sv_mask, uint64_t sv_base, DeviceStats* __restrict__ st) {
-    __shared__ uint64_t scratch[8];
-    uint64_t       found = 0, kept = 0, occ = 0;
-    const uint64_t rounded = (cap + 31) / 32 * 32;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
-        if (i < cap) {
-            lo = __ldcs(reinterpret_cast<const uint4*>(table + i));
-            hi = __ldcs(reinterpret_cast<const uint4*>(table + i) + 1);
-        }
-        bool used = (lo.x | lo.y) != 0 && (lo.y & kSkipCombiner) == 0;  // helper entries are ids, not patterns
-        bool keep = used && hi.x >= threshold;
-        found += used;
-        uint64_t idx = warp_aggregated_inc(&st->cursor, keep);
-        if (keep) {
-            sv_pos[sv_base + idx]   = hi.y;
-            sv_count[sv_base + idx] = hi.x;
-            sv_mask[sv_base + idx]  = lo.y & 0x00FFFFFFu;  // high word of k0 = gap mask (+ round bits, dropped)
-            ++kept;
-            occ += hi.x;
-        }
-    }
-    found = block_reduce_sum(found, scratch);
-    kept  = block_reduce_sum(kept, scratch);
-    occ   = block_reduce_sum(occ, scratch);
-    if (threadIdx.x == 0) {
-        if (found) atomicAdd(&st->found, (unsigned long long)found);
-        if (kept) atomicAdd(&st->kept, (unsigned long long)kept);
-        if (occ) atomicAdd(&st->kept_occ, (unsigned long long)occ);
-    }
-}
-
 int launch_count_skipgrams(cudaStream_t s, const uint32_t* const* ids, int n, const SkipMask* masks, int nmasks, uint64_t npos, SkipSlot* table, uint64_t cap, DeviceStats* st,
                            int sms) {
     static int bps  = blocks_per_sm((const void*)count_skipgrams_kernel, 256, 0);
@@ -464,11 +508,10 @@ int launch_count_skipgrams(cudaStream_t s, const uint32_t* const* ids, int n, co
     count_skipgrams_kernel<<<grid ? grid : 1, 256, 0, s>>>(ids, n, masks, nmasks, npos, table, cap, st);
     return 1;
 }
-int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask, uint64_t sv_base,
-                           DeviceStats* st, int sms) {
-    static int bps  = blocks_per_sm((const void*)prune_skipgrams_kernel, 256, 0);
-    unsigned   grid = (unsigned)umin64(div_up(cap, 256), (uint64_t)sms * bps * 2);
-    prune_skipgrams_kernel<<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, sv_mask, sv_base, st);
+int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask, DeviceStats* st, int sms) {
+    static int bps  = blocks_per_sm((const void*)prune_table_kernel<SkipSlot, true>, 256, 0);
+    unsigned   grid = (unsigned)umin64(div_up(cap, kPruneTile), (uint64_t)sms * bps);
+    prune_table_kernel<SkipSlot, true><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, sv_mask, nullptr, st);
     return 1;
 }
 

@@ -67,14 +67,15 @@ int launch_make_id1(cudaStream_t s, const uint32_t* tok, uint64_t npos, const ui
 
 // ---- K2: n-gram upsert (the dominant kernel), K3: prune/compact, relabel
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms);
-int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint64_t sv_base, DeviceStats* st, int sms);
-int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const NgramSlot* table, uint32_t threshold);
+// bitmap: (cap+31)/32 words, bit = slot survived (may be NULL)
+int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap, DeviceStats* st, int sms);
+int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap);
 
 // ---- skipgrams (config 3)
 int launch_count_skipgrams(cudaStream_t s, const uint32_t* const* ids /*device array, index = level*/, int n, const SkipMask* masks /*device*/, int nmasks, uint64_t npos,
                            SkipSlot* table, uint64_t cap, DeviceStats* st, int sms);
-int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask, uint64_t sv_base,
-                           DeviceStats* st, int sms);
+int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask, DeviceStats* st,
+                           int sms);
 
 // ---- export: survivors -> pattern bytes
 // sv_nm[i] = n | mask << 8 ; for n == 1 sv_pos holds the class id itself

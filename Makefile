@@ -15,15 +15,19 @@ all: lib oracle host
 
 lib: $(LIB)
 
-$(LIBDIR)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.h $(CSRC)/device_utils.cuh
+$(LIBDIR)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.h $(CSRC)/device_utils.cuh $(CSRC)/spooky.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/kernels.ptxas.log || (cat $(LIBDIR)/kernels.ptxas.log; false)
 
-$(LIBDIR)/engine.o: $(CSRC)/engine.cu $(CSRC)/kernels.h include/colibri_b200.h
+$(LIBDIR)/engine.o: $(CSRC)/engine.cu $(CSRC)/kernels.h $(CSRC)/engine_common.h include/colibri_b200.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/engine.ptxas.log || (cat $(LIBDIR)/engine.ptxas.log; false)
 
-$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o
+$(LIBDIR)/shard.o: $(CSRC)/shard.cu $(CSRC)/kernels.h $(CSRC)/engine_common.h include/colibri_b200.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/shard.ptxas.log || (cat $(LIBDIR)/shard.ptxas.log; false)
+
+$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^
 
 oracle:

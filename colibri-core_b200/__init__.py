@@ -48,7 +48,8 @@ class COptions(C.Structure):
 
 
 class CSynthParams(C.Structure):
-    _fields_ = [("seed", C.c_uint64), ("ntokens", C.c_uint64), ("vocab", C.c_uint32), ("mean_sentence", C.c_uint32), ("phrase_permille", C.c_uint32), ("nphrases", C.c_uint32)]
+    _fields_ = [("seed", C.c_uint64), ("ntokens", C.c_uint64), ("vocab", C.c_uint32), ("mean_sentence", C.c_uint32), ("phrase_permille", C.c_uint32), ("nphrases", C.c_uint32),
+                ("first_token", C.c_uint64)]
 
 
 _lib = None
@@ -94,6 +95,19 @@ def library():
     L.colibri_b200_model_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.colibri_b200_model_counters.argtypes = [C.c_void_p, _u64p]
     L.colibri_b200_model_level_counters.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    L.colibri_b200_shard_begin.argtypes = [C.c_void_p, C.POINTER(COptions), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.colibri_b200_shard_info.argtypes = [C.c_void_p, _u64p]
+    L.colibri_b200_shard_device_ms.argtypes = [C.c_void_p]
+    L.colibri_b200_shard_device_ms.restype = C.c_double
+    L.colibri_b200_shard_unigram_counts.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.colibri_b200_shard_unigram_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]
+    L.colibri_b200_shard_level_count.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p]
+    L.colibri_b200_shard_level_pack.argtypes = [C.c_void_p, C.c_void_p]
+    L.colibri_b200_shard_level_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, _u64p]
+    L.colibri_b200_shard_level_finish.argtypes = [C.c_void_p, C.c_void_p, _u64p]
+    L.colibri_b200_shard_finish.argtypes = [C.c_void_p, _u64p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.colibri_b200_shard_free.argtypes = [C.c_void_p]
+    L.colibri_b200_shard_free.restype = None
     L.colibri_b200_hash64_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
     L.colibri_b200_synth_corpus.argtypes = [C.POINTER(CSynthParams), C.c_int, C.POINTER(C.c_void_p)]
     _lib = L
@@ -180,8 +194,8 @@ class Corpus:
         return cls.from_bytes(data[2:], device)
 
     @classmethod
-    def synthetic(cls, ntokens, vocab=100000, seed=1, mean_sentence=22, phrase_permille=0, nphrases=0, device=0):
-        p = CSynthParams(seed, ntokens, vocab, mean_sentence, phrase_permille, nphrases)
+    def synthetic(cls, ntokens, vocab=100000, seed=1, mean_sentence=22, phrase_permille=0, nphrases=0, device=0, first_token=0):
+        p = CSynthParams(seed, ntokens, vocab, mean_sentence, phrase_permille, nphrases, first_token)
         h = C.c_void_p()
         _check(library().colibri_b200_synth_corpus(C.byref(p), device, C.byref(h)))
         return cls(h, device)

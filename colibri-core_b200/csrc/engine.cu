@@ -5,41 +5,12 @@
 // totaltypes before the unigram prune (:1199-1201), prune after each pass (:1220), optional skipgram threshold
 // (:1233-1243), MINLENGTH clean-up (:1221-1229, :1337-1341).  No CPU implementation of the counting exists here:
 // without a CUDA device every entry point fails with COLIBRI_E_CUDA.
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <map>
-#include <mutex>
-#include <string>
-#include <vector>
-
-#include "../../include/colibri_b200.h"
-#include "kernels.h"
+#include "engine_common.h"
 
 using namespace colibri;
 
-// ------------------------------------------------------------------------------------------------ errors
-static thread_local char g_err[1024] = "";
-static int set_err(int code, const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof g_err, fmt, ap);
-    va_end(ap);
-    return code;
-}
-#define CUDA_TRY(expr)                                                                                                        \
-    do {                                                                                                                      \
-        cudaError_t e__ = (expr);                                                                                             \
-        if (e__ != cudaSuccess) return set_err(COLIBRI_E_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__)); \
-    } while (0)
-#define TRY(expr)                 \
-    do {                          \
-        int rc__ = (expr);        \
-        if (rc__ != 0) return rc__; \
-    } while (0)
+thread_local char colibri::g_err[1024] = "";
+colibri::Pool colibri::g_pool[16];
 
 extern "C" const char* colibri_b200_last_error(void) {
     return g_err;
@@ -69,144 +40,6 @@ extern "C" void colibri_b200_options_default(colibri_b200_options* o) {
     o->streamed            = 1;
     o->device              = 0;
 }
-
-// ------------------------------------------------------------------------------------------------ device memory pool
-// cudaMalloc/cudaFree of multi-gigabyte buffers costs milliseconds and synchronises the device; training the same
-// corpus repeatedly (the benchmark loop, or a CLI run with several models) reuses the blocks instead.
-namespace {
-struct Pool {
-    std::mutex                        mu;
-    std::multimap<size_t, void*>      free_blocks;  // size -> ptr
-    std::map<void*, size_t>           live;
-    size_t                            in_use = 0, peak = 0, cached = 0;
-    int alloc(void** out, size_t bytes) {
-        bytes = std::max<size_t>(256, (bytes + 255) / 256 * 256);
-        std::lock_guard<std::mutex> g(mu);
-        auto it = free_blocks.lower_bound(bytes);
-        if (it != free_blocks.end() && it->first <= bytes + bytes / 4 + (1 << 20)) {
-            *out = it->second;
-            live[*out] = it->first;
-            in_use += it->first;
-            cached -= it->first;
-            free_blocks.erase(it);
-        } else {
-            cudaError_t e = cudaMalloc(out, bytes);
-            if (e != cudaSuccess) {  // drop the cache and retry once
-                cudaGetLastError();
-                for (auto& kv : free_blocks) cudaFree(kv.second);
-                free_blocks.clear();
-                cached = 0;
-                e = cudaMalloc(out, bytes);
-            }
-            if (e != cudaSuccess) {
-                cudaGetLastError();
-                return set_err(COLIBRI_E_CUDA, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
-            }
-            live[*out] = bytes;
-            in_use += bytes;
-        }
-        peak = std::max(peak, in_use);
-        return 0;
-    }
-    void release(void* p) {
-        if (!p) return;
-        std::lock_guard<std::mutex> g(mu);
-        auto it = live.find(p);
-        if (it == live.end()) return;
-        in_use -= it->second;
-        cached += it->second;
-        free_blocks.emplace(it->second, p);
-        live.erase(it);
-    }
-    void trim() {
-        std::lock_guard<std::mutex> g(mu);
-        for (auto& kv : free_blocks) cudaFree(kv.second);
-        free_blocks.clear();
-        cached = 0;
-    }
-};
-Pool g_pool[16];
-
-template <class T>
-struct DevBuf {
-    T*     p   = nullptr;
-    size_t n   = 0;
-    int    dev = 0;
-    DevBuf() {}
-    DevBuf(const DevBuf&)            = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), dev(o.dev) { o.p = nullptr; o.n = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) {
-            reset();
-            p = o.p; n = o.n; dev = o.dev;
-            o.p = nullptr; o.n = 0;
-        }
-        return *this;
-    }
-    ~DevBuf() { reset(); }
-    int alloc(int device, size_t count) {
-        reset();
-        dev = device;
-        void* q = nullptr;
-        TRY(g_pool[device & 15].alloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
-        p = (T*)q;
-        n = count;
-        return 0;
-    }
-    void reset() {
-        if (p) g_pool[dev & 15].release(p);
-        p = nullptr;
-        n = 0;
-    }
-};
-
-struct PhaseTimer {  // CUDA events on the library's stream, resolved after the final synchronise
-    struct Span { int phase; cudaEvent_t a, b; int level; };
-    std::vector<Span> spans;
-    cudaStream_t      s = nullptr;
-    int begin(int phase, int level = 0) {
-        Span sp{phase, nullptr, nullptr, level};
-        if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return -1;
-        cudaEventRecord(sp.a, s);
-        spans.push_back(sp);
-        return (int)spans.size() - 1;
-    }
-    void end(int h) { if (h >= 0) cudaEventRecord(spans[h].b, s); }
-    ~PhaseTimer() {
-        for (auto& sp : spans) {
-            cudaEventDestroy(sp.a);
-            cudaEventDestroy(sp.b);
-        }
-    }
-    void resolve(double ms[COLIBRI_T_NPHASES], std::map<int, double>* level_ms) {
-        for (auto& sp : spans) {
-            float t = 0;
-            if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) {
-                ms[sp.phase] += t;
-                if (level_ms && sp.phase == COLIBRI_T_COUNT) (*level_ms)[sp.level] += t;
-            }
-            cudaEventDestroy(sp.a);
-            cudaEventDestroy(sp.b);
-        }
-        spans.clear();
-    }
-};
-}  // namespace
-
-// ------------------------------------------------------------------------------------------------ corpus
-constexpr size_t kHalo = 16;  // zero bytes in front of the body: byte -1 must read as "< 128"
-struct colibri_b200_corpus {
-    int              device = 0;
-    DevBuf<uint8_t>  buf;            // [kHalo zeros][body][2 spare][0x80 padding to a tile multiple + one tile]
-    size_t           nbytes = 0;     // body bytes as given
-    bool             ends_with_delim = true;
-    uint8_t          last_byte = 0;
-    cudaStream_t     stream = nullptr;
-    double           h2d_ms = 0;
-    uint8_t*         body() const { return buf.p + kHalo; }
-    size_t           padded(size_t staged) const { return (staged + kTokTile - 1) / kTokTile * kTokTile; }
-};
 
 static int corpus_alloc(colibri_b200_corpus* c, int device, size_t nbytes) {
     int ndev = colibri_b200_device_count();
@@ -303,32 +136,6 @@ extern "C" int colibri_b200_corpus_download(const colibri_b200_corpus* c, uint8_
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------------ model
-struct PassStat { uint64_t n, found, foundskip, pruned; };
-struct LevelInfo { uint64_t windows = 0, cap = 0; double ms = 0; };
-struct colibri_b200_model {
-    int      device = 0;
-    int      model_type = COLIBRI_UNINDEXEDPATTERNMODEL;
-    uint64_t npatterns = 0, keybytes = 0, nrefs = 0;
-    uint64_t totaltokens = 0, totaltypes = 0;
-    int      maxn = 0, minn = 999, hasskipgrams = 0;
-    std::vector<PassStat> passes;
-    // device-resident flat export
-    DevBuf<uint8_t>  d_keys;
-    DevBuf<uint64_t> d_off;
-    DevBuf<uint32_t> d_counts;
-    // host copies (filled on first export / lookup)
-    bool                  host_ready = false;
-    std::vector<uint8_t>  h_keys;
-    std::vector<uint64_t> h_off;
-    std::vector<uint32_t> h_counts;
-    std::vector<uint32_t> h_sorted;  // lookup index
-    double   ms[COLIBRI_T_NPHASES] = {0};
-    uint64_t counters[8] = {0};
-    std::map<int, LevelInfo> levels;
-    cudaStream_t stream = nullptr;
-};
-
 extern "C" void colibri_b200_model_free(colibri_b200_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
@@ -373,12 +180,6 @@ extern "C" int colibri_b200_model_level_counters(const colibri_b200_model* m, in
 
 // ------------------------------------------------------------------------------------------------ training
 namespace {
-struct Segment {  // survivors of one (level, category)
-    int              n = 0;
-    bool             skip = false;
-    uint64_t         count = 0;
-    DevBuf<uint32_t> pos, cnt, mask;
-};
 
 // compute_skip_configurations (reference src/algorithms.cpp:79-94): every non-empty subset of the inner positions
 // 1..n-2, dropped when it has more than maxskips separate gaps (and n-2 >= maxskips)
@@ -419,7 +220,8 @@ int skip_masks(int n, int maxskips, std::vector<SkipMask>& out) {
     return 0;
 }
 
-int check_options(colibri_b200_options& o) {
+}  // namespace
+int colibri::check_options(colibri_b200_options& o) {
     // include/patternmodel.h:883-888
     if (o.MINTOKENS == -1) o.MINTOKENS = 2;
     if (o.MINTOKENS == 0) o.MINTOKENS = 1;
@@ -444,6 +246,7 @@ int check_options(colibri_b200_options& o) {
     return 0;
 }
 
+namespace {
 struct Trainer {
     colibri_b200_corpus*       c;
     colibri_b200_options       o;
@@ -470,7 +273,6 @@ struct Trainer {
         return 0;
     }
     int run();
-    int export_segments(const uint32_t* tok);
 };
 
 int Trainer::run() {
@@ -721,7 +523,7 @@ int Trainer::run() {
     m->passes = passes;
 
     h = timer.begin(COLIBRI_T_EXPORT);
-    TRY(export_segments(tok.p));
+    TRY(colibri::export_segments(dev, s, segs, tok.p, m, launches));
     timer.end(h);
     timer.end(h_total);
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -738,7 +540,10 @@ int Trainer::run() {
     return 0;
 }
 
-int Trainer::export_segments(const uint32_t* tok) {
+}  // namespace
+
+// survivors of all levels -> the flat device-resident export (keys blob, offsets, counts) of the model
+int colibri::export_segments(int dev, cudaStream_t s, std::vector<Segment>& segs, const uint32_t* tok, colibri_b200_model* m, uint64_t& launches) {
     uint64_t total = 0;
     for (auto& sg : segs) total += sg.count;
     m->npatterns = total;
@@ -788,7 +593,6 @@ int Trainer::export_segments(const uint32_t* tok) {
     segs.clear();
     return 0;
 }
-}  // namespace
 
 extern "C" int colibri_b200_train_corpus(colibri_b200_corpus* corpus, const colibri_b200_options* opt, colibri_b200_model** out) {
     if (!out) return set_err(COLIBRI_E_INVALID, "out is NULL");
@@ -994,7 +798,7 @@ extern "C" int colibri_b200_synth_corpus(const colibri_b200_synth_params* p, int
     TRY(off.alloc(device, p->ntokens + 1));
     TRY(tmp.alloc(device, p->ntokens / 2048 + 4));
     CUDA_TRY(cudaMemcpy(dcdf.p, cdf.data(), cdf.size() * 8, cudaMemcpyHostToDevice));
-    launch_synth_lengths(nullptr, p->seed, p->ntokens, p->vocab, p->mean_sentence, p->phrase_permille, p->nphrases, dcdf.p, lens.p);
+    launch_synth_lengths(nullptr, p->seed, p->ntokens, p->first_token, p->vocab, p->mean_sentence, p->phrase_permille, p->nphrases, dcdf.p, lens.p);
     launch_exclusive_scan_u32_u64(nullptr, lens.p, off.p, p->ntokens, tmp.p);
     uint64_t nbytes = 0;
     CUDA_TRY(cudaMemcpy(&nbytes, off.p + p->ntokens, 8, cudaMemcpyDeviceToHost));
@@ -1002,7 +806,7 @@ extern "C" int colibri_b200_synth_corpus(const colibri_b200_synth_params* p, int
     int   rc = corpus_alloc(c, device, nbytes);
     if (rc == 0) {
         cudaStreamSynchronize(c->stream);
-        launch_synth_write(nullptr, p->seed, p->ntokens, p->vocab, p->mean_sentence, p->phrase_permille, p->nphrases, dcdf.p, off.p, c->body());
+        launch_synth_write(nullptr, p->seed, p->ntokens, p->first_token, p->vocab, p->mean_sentence, p->phrase_permille, p->nphrases, dcdf.p, off.p, c->body());
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) rc = set_err(COLIBRI_E_CUDA, "synthetic corpus kernel failed: %s", cudaGetErrorString(e));
     }

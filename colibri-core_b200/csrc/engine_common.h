@@ -1,0 +1,220 @@
+// engine_common.h -- host-side plumbing shared by engine.cu (single-GPU driver + C ABI) and shard.cu (multi-GPU phases):
+// error reporting, the device memory pool, phase timers and the handle structs behind the opaque C types.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/colibri_b200.h"
+#include "kernels.h"
+
+namespace colibri {
+
+// ------------------------------------------------------------------------------------------------ errors
+extern thread_local char g_err[1024];
+inline int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                                        \
+    do {                                                                                                                      \
+        cudaError_t e__ = (expr);                                                                                             \
+        if (e__ != cudaSuccess) return set_err(COLIBRI_E_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    } while (0)
+#define TRY(expr)                 \
+    do {                          \
+        int rc__ = (expr);        \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ device memory pool
+// cudaMalloc/cudaFree of multi-gigabyte buffers costs milliseconds and synchronises the device; training the same
+// corpus repeatedly (the benchmark loop, or a CLI run with several models) reuses the blocks instead.
+struct Pool {
+    std::mutex                        mu;
+    std::multimap<size_t, void*>      free_blocks;  // size -> ptr
+    std::map<void*, size_t>           live;
+    size_t                            in_use = 0, peak = 0, cached = 0;
+    int alloc(void** out, size_t bytes) {
+        bytes = std::max<size_t>(256, (bytes + 255) / 256 * 256);
+        std::lock_guard<std::mutex> g(mu);
+        auto it = free_blocks.lower_bound(bytes);
+        if (it != free_blocks.end() && it->first <= bytes + bytes / 4 + (1 << 20)) {
+            *out = it->second;
+            live[*out] = it->first;
+            in_use += it->first;
+            cached -= it->first;
+            free_blocks.erase(it);
+        } else {
+            cudaError_t e = cudaMalloc(out, bytes);
+            if (e != cudaSuccess) {  // drop the cache and retry once
+                cudaGetLastError();
+                for (auto& kv : free_blocks) cudaFree(kv.second);
+                free_blocks.clear();
+                cached = 0;
+                e = cudaMalloc(out, bytes);
+            }
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return set_err(COLIBRI_E_CUDA, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            }
+            live[*out] = bytes;
+            in_use += bytes;
+        }
+        peak = std::max(peak, in_use);
+        return 0;
+    }
+    void release(void* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu);
+        auto it = live.find(p);
+        if (it == live.end()) return;
+        in_use -= it->second;
+        cached += it->second;
+        free_blocks.emplace(it->second, p);
+        live.erase(it);
+    }
+    void trim() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        cached = 0;
+    }
+};
+extern Pool g_pool[16];
+
+template <class T>
+struct DevBuf {
+    T*     p   = nullptr;
+    size_t n   = 0;
+    int    dev = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&)            = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), dev(o.dev) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            reset();
+            p = o.p; n = o.n; dev = o.dev;
+            o.p = nullptr; o.n = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { reset(); }
+    int alloc(int device, size_t count) {
+        reset();
+        dev = device;
+        void* q = nullptr;
+        TRY(g_pool[device & 15].alloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+        p = (T*)q;
+        n = count;
+        return 0;
+    }
+    void reset() {
+        if (p) g_pool[dev & 15].release(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct PhaseTimer {  // CUDA events on the library's stream, resolved after the final synchronise
+    struct Span { int phase; cudaEvent_t a, b; int level; };
+    std::vector<Span> spans;
+    cudaStream_t      s = nullptr;
+    int begin(int phase, int level = 0) {
+        Span sp{phase, nullptr, nullptr, level};
+        if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return -1;
+        cudaEventRecord(sp.a, s);
+        spans.push_back(sp);
+        return (int)spans.size() - 1;
+    }
+    void end(int h) { if (h >= 0) cudaEventRecord(spans[h].b, s); }
+    ~PhaseTimer() {
+        for (auto& sp : spans) {
+            cudaEventDestroy(sp.a);
+            cudaEventDestroy(sp.b);
+        }
+    }
+    void resolve(double ms[COLIBRI_T_NPHASES], std::map<int, double>* level_ms) {
+        for (auto& sp : spans) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) {
+                ms[sp.phase] += t;
+                if (level_ms && sp.phase == COLIBRI_T_COUNT) (*level_ms)[sp.level] += t;
+            }
+            cudaEventDestroy(sp.a);
+            cudaEventDestroy(sp.b);
+        }
+        spans.clear();
+    }
+};
+
+struct Segment {  // survivors of one (level, category)
+    int              n = 0;
+    bool             skip = false;
+    uint64_t         count = 0;
+    DevBuf<uint32_t> pos, cnt, mask;
+};
+
+int check_options(colibri_b200_options& o);
+
+}  // namespace colibri
+
+using colibri::DevBuf;
+using colibri::kTokTile;
+
+// ------------------------------------------------------------------------------------------------ corpus
+constexpr size_t kHalo = 16;  // zero bytes in front of the body: byte -1 must read as "< 128"
+struct colibri_b200_corpus {
+    int              device = 0;
+    DevBuf<uint8_t>  buf;            // [kHalo zeros][body][2 spare][0x80 padding to a tile multiple + one tile]
+    size_t           nbytes = 0;     // body bytes as given
+    bool             ends_with_delim = true;
+    uint8_t          last_byte = 0;
+    cudaStream_t     stream = nullptr;
+    double           h2d_ms = 0;
+    uint8_t*         body() const { return buf.p + kHalo; }
+    size_t           padded(size_t staged) const { return (staged + kTokTile - 1) / kTokTile * kTokTile; }
+};
+
+
+struct PassStat { uint64_t n, found, foundskip, pruned; };
+struct LevelInfo { uint64_t windows = 0, cap = 0; double ms = 0; };
+struct colibri_b200_model {
+    int      device = 0;
+    int      model_type = COLIBRI_UNINDEXEDPATTERNMODEL;
+    uint64_t npatterns = 0, keybytes = 0, nrefs = 0;
+    uint64_t totaltokens = 0, totaltypes = 0;
+    int      maxn = 0, minn = 999, hasskipgrams = 0;
+    std::vector<PassStat> passes;
+    // device-resident flat export
+    DevBuf<uint8_t>  d_keys;
+    DevBuf<uint64_t> d_off;
+    DevBuf<uint32_t> d_counts;
+    // host copies (filled on first export / lookup)
+    bool                  host_ready = false;
+    std::vector<uint8_t>  h_keys;
+    std::vector<uint64_t> h_off;
+    std::vector<uint32_t> h_counts;
+    std::vector<uint32_t> h_sorted;  // lookup index
+    double   ms[COLIBRI_T_NPHASES] = {0};
+    uint64_t counters[8] = {0};
+    std::map<int, LevelInfo> levels;
+    cudaStream_t stream = nullptr;
+};
+
+namespace colibri {
+// survivors of all levels -> the flat device-resident export of the model (engine.cu)
+int export_segments(int dev, cudaStream_t s, std::vector<Segment>& segs, const uint32_t* tok, colibri_b200_model* m, uint64_t& launches);
+}  // namespace colibri

@@ -170,18 +170,22 @@ __global__ void __launch_bounds__(512) unigram_hist_kernel(const uint32_t* __res
 }
 
 // prune(MINTOKENS, 1) (patternmodel.h:2107-2128) over the class array + totaltypes (:1199-1201, counted BEFORE pruning)
+// (part_mod, part_rem): in multi-GPU mode every rank sees the same global counts and exports the classes c with c % part_mod == part_rem
 __global__ void __launch_bounds__(256) unigram_prune_kernel(const uint32_t* __restrict__ count1, uint32_t nclasses, uint32_t threshold, uint32_t* __restrict__ sv_pos,
-                                                            uint32_t* __restrict__ sv_count, uint64_t sv_base, DeviceStats* __restrict__ st) {
+                                                            uint32_t* __restrict__ sv_count, uint64_t sv_base, DeviceStats* __restrict__ st, uint32_t part_mod, uint32_t part_rem) {
     __shared__ uint64_t scratch[8];
     uint64_t found = 0, kept = 0, occ = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)div_up(nclasses, 32) * 32; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t c    = i < nclasses ? count1[i] : 0;
         bool     keep = c >= threshold && c > 0;
+        bool     mine = keep && (uint32_t)(i % part_mod) == part_rem;
         found += c > 0;
-        uint64_t idx = warp_aggregated_inc(&st->cursor, keep);
-        if (keep) {
+        uint64_t idx = warp_aggregated_inc(&st->cursor, mine);
+        if (mine) {
             sv_pos[sv_base + idx]   = (uint32_t)i;  // level 1 survivors carry the class id instead of a position
             sv_count[sv_base + idx] = c;
+        }
+        if (keep) {
             ++kept;
             occ += c;
         }
@@ -214,9 +218,10 @@ int launch_unigram_hist(cudaStream_t s, const uint32_t* tok, uint64_t npos, uint
     unigram_hist_kernel<<<sms * 3, 512, kHotClasses * 4, s>>>(tok, npos, count1);
     return 1;
 }
-int launch_unigram_prune(cudaStream_t s, const uint32_t* count1, uint32_t nclasses, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint64_t sv_base, DeviceStats* st) {
+int launch_unigram_prune(cudaStream_t s, const uint32_t* count1, uint32_t nclasses, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint64_t sv_base, DeviceStats* st,
+                         uint32_t part_mod, uint32_t part_rem) {
     unsigned grid = min(div_up(nclasses, 256), 148u * 8u);
-    unigram_prune_kernel<<<grid, 256, 0, s>>>(count1, nclasses, threshold, sv_pos, sv_count, sv_base, st);
+    unigram_prune_kernel<<<grid, 256, 0, s>>>(count1, nclasses, threshold, sv_pos, sv_count, sv_base, st, part_mod ? part_mod : 1u, part_rem);
     return 1;
 }
 int launch_make_id1(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* count1, uint32_t threshold, uint32_t* id1) {
@@ -364,13 +369,13 @@ __global__ void __launch_bounds__(256) prune_table_kernel(const Slot* __restrict
                 warp_cnt[w] = tot;
                 tot += c;
             }
-            tile_base = tot ? atomicAdd(&st->cursor, (unsigned long long)tot) : 0ull;
+            tile_base = (tot && sv_pos != nullptr) ? atomicAdd(&st->cursor, (unsigned long long)tot) : 0ull;
         }
         __syncthreads();
         uint64_t out = tile_base + warp_cnt[warp];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            if ((keepbits[k] >> lane) & 1u) {
+            if (sv_pos != nullptr && ((keepbits[k] >> lane) & 1u)) {
                 uint64_t idx = out + __popc(keepbits[k] & ((1u << lane) - 1));
                 sv_pos[idx]   = pos[k];
                 sv_count[idx] = cnt[k];
@@ -665,6 +670,172 @@ int launch_export_write_modelfile(cudaStream_t s, const uint32_t* tok, const uin
 }
 
 // =============================================================================================
+// Multi-GPU (hash-partitioned model).  Every rank counts its own sentences into a local table keyed by GLOBAL
+// (n-1)-gram ids; the distinct local entries travel as 16-byte records {key, partial count, source slot} to the owner
+// rank = hash(key) mod G, which merges them, applies the threshold and answers each record with {global id, global count
+// if this record's sender is the one that exports the pattern}.
+__device__ __forceinline__ uint32_t owner_of(unsigned long long key, uint32_t world) {
+    return (uint32_t)fast_range(spooky_hash64_u64(key, 0x5eedull), world);
+}
+
+__global__ void __launch_bounds__(256) shard_dest_count_kernel(const NgramSlot* __restrict__ table, uint64_t cap, uint32_t world, unsigned long long* __restrict__ dest_counts) {
+    __shared__ uint32_t hist[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long key = __ldcs(&table[i].key);
+        if (key != 0) atomicAdd(&hist[owner_of(key, world)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < world && hist[threadIdx.x]) atomicAdd(&dest_counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+}
+
+// records grouped by destination: send[dest_base[d] + k]; send_slot remembers which local slot each record came from
+__global__ void __launch_bounds__(256) shard_pack_kernel(const NgramSlot* __restrict__ table, uint64_t cap, uint32_t world, const unsigned long long* __restrict__ dest_base,
+                                                         unsigned long long* __restrict__ cursors, uint4* __restrict__ send, uint32_t* __restrict__ send_slot) {
+    const uint64_t rounded = (cap + 31) / 32 * 32;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (i < cap) raw = __ldcs(reinterpret_cast<const uint4*>(table) + i);
+        bool     used = (raw.x | raw.y) != 0;
+        uint32_t dest = used ? owner_of(((unsigned long long)raw.y << 32) | raw.x, world) : 0xFFFFFFFFu;
+        // lanes with the same destination share one cursor atomic
+        uint32_t peers  = __match_any_sync(0xffffffffu, dest);
+        if (!used) continue;
+        int      leader = __ffs(peers) - 1;
+        uint64_t base   = 0;
+        if ((int)lane_id() == leader) base = atomicAdd(&cursors[dest], (unsigned long long)__popc(peers));
+        base         = __shfl_sync(peers, base, leader);
+        uint64_t idx = dest_base[dest] + base + __popc(peers & ((1u << lane_id()) - 1));
+        send[idx]      = make_uint4(raw.x, raw.y, raw.z, (uint32_t)i);
+        send_slot[idx] = (uint32_t)i;
+    }
+}
+
+// owner side: fold the received partial counts into the owner table; reply_slot[i] = slot + 1 of record i
+__global__ void __launch_bounds__(256) shard_merge_kernel(const uint4* __restrict__ recv, uint64_t nrecv, NgramSlot* __restrict__ table, uint64_t cap,
+                                                          uint32_t* __restrict__ reply_slot, DeviceStats* __restrict__ st) {
+    bool full = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrecv; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4              r    = __ldcs(recv + i);
+        unsigned long long key  = ((unsigned long long)r.y << 32) | r.x;
+        uint64_t           slot = fast_range(spooky_hash64_u64(key, 0), cap);
+        uint32_t           out  = 0;
+        for (uint64_t step = 0; step < cap; ++step) {
+            NgramSlot*         s   = table + slot;
+            unsigned long long cur = __ldcg(&s->key);
+            if (cur == 0) {
+                unsigned long long o0, o1;
+                cas128(s, key, (unsigned long long)r.z | ((unsigned long long)(uint32_t)i << 32), o0, o1);  // pos = index of the claiming record
+                if (o0 == 0) {
+                    out = (uint32_t)slot + 1;
+                    break;
+                }
+                cur = o0;
+            }
+            if (cur == key) {
+                atomicAdd(&s->count, r.z);
+                out = (uint32_t)slot + 1;
+                break;
+            }
+            slot = slot + 1 == cap ? 0 : slot + 1;
+        }
+        if (out == 0) full = true;
+        reply_slot[i] = out;
+    }
+    if (full) atomicOr(&st->errflags, kErrTableFull);
+}
+
+// reply[i] = {global id (0 if pruned), global count if record i is the one that claimed the slot (its sender exports the pattern) else 0}
+__global__ void __launch_bounds__(256) shard_reply_kernel(const uint32_t* __restrict__ reply_slot, uint64_t nrecv, const NgramSlot* __restrict__ table,
+                                                          const uint32_t* __restrict__ bitmap, uint32_t world, uint32_t rank, uint2* __restrict__ reply) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrecv) return;
+    uint32_t s = reply_slot[i];
+    uint2    r = make_uint2(0, 0);
+    if (s != 0 && ((__ldg(bitmap + ((s - 1) >> 5)) >> ((s - 1) & 31)) & 1u)) {
+        uint4 raw = __ldcg(reinterpret_cast<const uint4*>(table) + (s - 1));
+        r.x       = (s - 1) * world + rank + 1;
+        r.y       = raw.w == (uint32_t)i ? raw.z : 0u;
+    }
+    reply[i] = r;
+}
+
+// sender side: the j-th reply belongs to the j-th record sent
+__global__ void __launch_bounds__(256) shard_apply_kernel(const uint2* __restrict__ reply, const uint32_t* __restrict__ send_slot, uint64_t nsent,
+                                                          const NgramSlot* __restrict__ table, uint32_t* __restrict__ gid_of_slot, uint32_t* __restrict__ sv_pos,
+                                                          uint32_t* __restrict__ sv_count, DeviceStats* __restrict__ st) {
+    const uint64_t rounded = (nsent + 31) / 32 * 32;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < rounded; j += (uint64_t)gridDim.x * blockDim.x) {
+        uint2    r    = j < nsent ? __ldcs(reply + j) : make_uint2(0, 0);
+        uint32_t slot = j < nsent ? send_slot[j] : 0;
+        if (j < nsent) gid_of_slot[slot] = r.x;
+        bool     mine = r.y != 0;
+        uint64_t idx  = warp_aggregated_inc(&st->cursor, mine);
+        if (mine) {
+            sv_pos[idx]   = __ldcg(&table[slot].pos);
+            sv_count[idx] = r.y;
+        }
+    }
+}
+
+// cur[p]: local slot + 1  ->  global id of the surviving n-gram (0 if pruned); also counts the survivors' positions
+__global__ void __launch_bounds__(256) shard_relabel_kernel(uint32_t* __restrict__ cur, uint64_t npos, const uint32_t* __restrict__ gid_of_slot, DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    uint32_t valid = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npos; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t id = cur[i];
+        if (id != 0) {
+            id     = __ldg(gid_of_slot + (id - 1));
+            cur[i] = id;
+            valid += id != 0;
+        }
+    }
+    uint64_t v = block_reduce_sum(valid, scratch);
+    if (threadIdx.x == 0 && v) atomicAdd(&st->kept_occ, (unsigned long long)v);
+}
+
+int launch_shard_dest_count(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t world, unsigned long long* dest_counts, int sms) {
+    unsigned grid = (unsigned)umin64(div_up(cap, 256), (uint64_t)sms * 8);
+    shard_dest_count_kernel<<<grid ? grid : 1, 256, 0, s>>>(table, cap, world, dest_counts);
+    return 1;
+}
+int launch_shard_pack(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t world, const unsigned long long* dest_base, unsigned long long* cursors, void* send,
+                      uint32_t* send_slot, int sms) {
+    unsigned grid = (unsigned)umin64(div_up(cap, 256), (uint64_t)sms * 8);
+    shard_pack_kernel<<<grid ? grid : 1, 256, 0, s>>>(table, cap, world, dest_base, cursors, (uint4*)send, send_slot);
+    return 1;
+}
+int launch_shard_merge(cudaStream_t s, const void* recv, uint64_t nrecv, NgramSlot* table, uint64_t cap, uint32_t* reply_slot, DeviceStats* st, int sms) {
+    if (!nrecv) return 0;
+    unsigned grid = (unsigned)umin64(div_up(nrecv, 256), (uint64_t)sms * 32);
+    shard_merge_kernel<<<grid, 256, 0, s>>>((const uint4*)recv, nrecv, table, cap, reply_slot, st);
+    return 1;
+}
+int launch_shard_prune_owner(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* bitmap, DeviceStats* st, int sms) {
+    unsigned grid = (unsigned)umin64(div_up(cap, kPruneTile), (uint64_t)sms * 4);
+    prune_table_kernel<NgramSlot, false><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, nullptr, nullptr, nullptr, bitmap, st);
+    return 1;
+}
+int launch_shard_reply(cudaStream_t s, const uint32_t* reply_slot, uint64_t nrecv, const NgramSlot* table, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* reply) {
+    if (!nrecv) return 0;
+    shard_reply_kernel<<<div_up(nrecv, 256), 256, 0, s>>>(reply_slot, nrecv, table, bitmap, world, rank, (uint2*)reply);
+    return 1;
+}
+int launch_shard_apply(cudaStream_t s, const void* reply, const uint32_t* send_slot, uint64_t nsent, const NgramSlot* table, uint32_t* gid_of_slot, uint32_t* sv_pos,
+                       uint32_t* sv_count, DeviceStats* st, int sms) {
+    if (!nsent) return 0;
+    unsigned grid = (unsigned)umin64(div_up(nsent, 256), (uint64_t)sms * 8);
+    shard_apply_kernel<<<grid, 256, 0, s>>>((const uint2*)reply, send_slot, nsent, table, gid_of_slot, sv_pos, sv_count, st);
+    return 1;
+}
+int launch_shard_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* gid_of_slot, DeviceStats* st, int sms) {
+    unsigned grid = (unsigned)umin64(div_up(npos, 256), (uint64_t)sms * 8);
+    shard_relabel_kernel<<<grid ? grid : 1, 256, 0, s>>>(cur, npos, gid_of_slot, st);
+    return 1;
+}
+
+// =============================================================================================
 // Pattern::hash on the device for arbitrary pattern bytes (parity row a5)
 __global__ void __launch_bounds__(256) hash64_batch_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, uint64_t n, uint64_t* __restrict__ out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -691,7 +862,7 @@ __host__ __device__ __forceinline__ uint64_t rnd(uint64_t seed, uint64_t stream,
     return mix64((seed + stream * 0xD1B54A32D192ED03ULL) ^ mix64(i));
 }
 struct SynthArgs {
-    uint64_t        seed, ntokens;
+    uint64_t        seed, ntokens, first;
     uint32_t        vocab, mean_sentence, phrase_permille, nphrases;
     const uint64_t* cdf;
 };
@@ -718,13 +889,14 @@ __device__ __forceinline__ bool phrase_info(const SynthArgs& a, uint64_t i, uint
     j = k;
     return true;
 }
-__device__ __forceinline__ void synth_token(const SynthArgs& a, uint64_t i, uint32_t& cls, bool& brk) {
+__device__ __forceinline__ void synth_token(const SynthArgs& a, uint64_t local, uint32_t& cls, bool& brk) {
+    const uint64_t i = a.first + local;  // index in the global stream
     uint64_t id;
     uint32_t j, L;
     bool     inphrase = phrase_info(a, i, id, j, L);
     cls               = 6 + zipf_rank(a, inphrase ? rnd(a.seed, 5, id * 8 + j) : rnd(a.seed, 0, i));
     brk               = (inphrase && j + 1 < L) ? false : (rnd(a.seed, 1, i) % a.mean_sentence == 0);
-    if (i + 1 == a.ntokens) brk = true;
+    if (local + 1 == a.ntokens) brk = true;  // a corpus (or shard) always ends with a delimiter
 }
 __global__ void __launch_bounds__(256) synth_lengths_kernel(SynthArgs a, uint32_t* __restrict__ lens) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -744,15 +916,15 @@ __global__ void __launch_bounds__(256) synth_write_kernel(SynthArgs a, const uin
     uint32_t l = varint_put(o, cls);
     if (brk) o[l] = 0;
 }
-int launch_synth_lengths(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases, const uint64_t* cdf,
-                         uint32_t* lens) {
-    SynthArgs a{seed, ntokens, vocab, mean_sentence, phrase_permille, nphrases, cdf};
+int launch_synth_lengths(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint64_t first, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases,
+                         const uint64_t* cdf, uint32_t* lens) {
+    SynthArgs a{seed, ntokens, first, vocab, mean_sentence, phrase_permille, nphrases, cdf};
     synth_lengths_kernel<<<div_up(ntokens, 256), 256, 0, s>>>(a, lens);
     return 1;
 }
-int launch_synth_write(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases, const uint64_t* cdf,
-                       const uint64_t* off, uint8_t* out) {
-    SynthArgs a{seed, ntokens, vocab, mean_sentence, phrase_permille, nphrases, cdf};
+int launch_synth_write(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint64_t first, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases,
+                       const uint64_t* cdf, const uint64_t* off, uint8_t* out) {
+    SynthArgs a{seed, ntokens, first, vocab, mean_sentence, phrase_permille, nphrases, cdf};
     synth_write_kernel<<<div_up(ntokens, 256), 256, 0, s>>>(a, off, out);
     return 1;
 }

@@ -62,7 +62,8 @@ int launch_tokenise_write(cudaStream_t s, const uint8_t* corpus, uint64_t nbytes
 
 // ---- K1: unigram histogram, unigram prune, level-1 ids
 int launch_unigram_hist(cudaStream_t s, const uint32_t* tok, uint64_t npos, uint32_t* count1, uint32_t nclasses, int sms);
-int launch_unigram_prune(cudaStream_t s, const uint32_t* count1, uint32_t nclasses, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint64_t sv_base, DeviceStats* st);
+int launch_unigram_prune(cudaStream_t s, const uint32_t* count1, uint32_t nclasses, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint64_t sv_base, DeviceStats* st,
+                         uint32_t part_mod = 1, uint32_t part_rem = 0);
 int launch_make_id1(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* count1, uint32_t threshold, uint32_t* id1);
 
 // ---- K2: n-gram upsert (the dominant kernel), K3: prune/compact, relabel
@@ -88,11 +89,22 @@ int launch_export_write(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_
 int launch_export_write_modelfile(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, const uint32_t* sv_count, const uint64_t* off, uint64_t n,
                                   uint8_t* out);
 
+// ---- multi-GPU phases (hash-partitioned model): see shard.cu
+int launch_shard_dest_count(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t world, unsigned long long* dest_counts, int sms);
+int launch_shard_pack(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t world, const unsigned long long* dest_base, unsigned long long* cursors, void* send /*16 B records*/,
+                      uint32_t* send_slot, int sms);
+int launch_shard_merge(cudaStream_t s, const void* recv, uint64_t nrecv, NgramSlot* table, uint64_t cap, uint32_t* reply_slot, DeviceStats* st, int sms);
+int launch_shard_prune_owner(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* bitmap, DeviceStats* st, int sms);
+int launch_shard_reply(cudaStream_t s, const uint32_t* reply_slot, uint64_t nrecv, const NgramSlot* table, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* reply /*8 B records*/);
+int launch_shard_apply(cudaStream_t s, const void* reply, const uint32_t* send_slot, uint64_t nsent, const NgramSlot* table, uint32_t* gid_of_slot, uint32_t* sv_pos, uint32_t* sv_count,
+                       DeviceStats* st, int sms);
+int launch_shard_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* gid_of_slot, DeviceStats* st, int sms);
+
 // ---- parity helpers / measurement input
 int launch_hash64_batch(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t n, uint64_t* out);
-int launch_synth_lengths(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases, const uint64_t* cdf,
-                         uint32_t* lens);
-int launch_synth_write(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases, const uint64_t* cdf,
-                       const uint64_t* off, uint8_t* out);
+int launch_synth_lengths(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint64_t first, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases,
+                         const uint64_t* cdf, uint32_t* lens);
+int launch_synth_write(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint64_t first, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases,
+                       const uint64_t* cdf, const uint64_t* off, uint8_t* out);
 
 }  // namespace colibri

@@ -1,0 +1,331 @@
+// shard.cu -- multi-GPU training as a sequence of per-rank phases (C ABI section "multi-GPU" of include/colibri_b200.h).
+//
+// The reference has no notion of several devices.  The corpus shards at sentence boundaries (windows
+// never cross the 0x00 delimiter, reference include/patternmodel.h:1063), one shard per GPU, and the model is partitioned
+// by hash: owner(key) = hash(key) mod G.  One process per GPU drives these phases and moves the buffers between ranks
+// with torch.distributed (NCCL all-to-all over NVLink); this file contains no communication and no torch types.
+//
+// Per level n >= 2 and per rank:
+//   level_count   local upsert of every valid window into a local table keyed by GLOBAL (n-1)-gram ids (same kernel as 1 GPU)
+//   level_pack    distinct local entries -> 16-byte records {key, partial count, source slot}, grouped by owner rank
+//   [all-to-all]
+//   level_merge   owner: fold records into the owner table, threshold (prune(), patternmodel.h:2107-2128), reply per record
+//                 {global id | 0, global count if this sender exports the pattern}
+//   [all-to-all back]
+//   level_finish  sender: local slot -> global id, relabel the positions, keep the survivors this rank exports
+// Level 1 needs no table: the class histograms are summed with an all-reduce.
+#include "engine_common.h"
+
+using namespace colibri;
+
+struct colibri_b200_shard {
+    colibri_b200_corpus* corpus = nullptr;
+    colibri_b200_options o;
+    int                  dev = 0, sms = 148;
+    uint32_t             rank = 0, world = 1;
+    cudaStream_t         s = nullptr;
+    uint64_t             launches = 0;
+    DevBuf<DeviceStats>  d_stats;
+    DeviceStats          h_stats;
+    uint64_t             npos = 0, local_tokens = 0;
+    uint32_t             local_maxclass = 0, nclasses = 0;
+    DevBuf<uint32_t>     tok, count1, prev, cur, bitmap, send_slot, reply_slot, gid_of_slot;
+    DevBuf<NgramSlot>    table, owner_table;
+    DevBuf<unsigned long long> d_dest;  // [0..world): counts, [world..2*world): exclusive bases, [2*world..3*world): cursors
+    uint64_t             local_cap = 0, owner_cap = 0, nsent = 0, prev_valid = 0;
+    int                  level = 1;
+    uint32_t             t = 2;
+    std::vector<Segment> segs;
+    uint64_t             global_tokens = 0, global_types = 0;
+    cudaEvent_t          ev0 = nullptr, ev1 = nullptr;
+    double               device_ms = 0;
+};
+
+static int zero_phase_stats(colibri_b200_shard* sh) {
+    CUDA_TRY(cudaMemsetAsync(&sh->d_stats.p->found, 0, offsetof(DeviceStats, maxclass) - offsetof(DeviceStats, found), sh->s));
+    return 0;
+}
+static int read_stats(colibri_b200_shard* sh) {
+    CUDA_TRY(cudaMemcpyAsync(&sh->h_stats, sh->d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, sh->s));
+    CUDA_TRY(cudaStreamSynchronize(sh->s));
+    if (sh->h_stats.errflags & kErrTableFull) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow");
+    return 0;
+}
+struct PhaseClock {  // accumulates device time of one ABI call into shard->device_ms
+    colibri_b200_shard* sh;
+    explicit PhaseClock(colibri_b200_shard* s) : sh(s) { cudaEventRecord(sh->ev0, sh->s); }
+    ~PhaseClock() {
+        cudaEventRecord(sh->ev1, sh->s);
+        cudaEventSynchronize(sh->ev1);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sh->ev0, sh->ev1) == cudaSuccess) sh->device_ms += ms;
+    }
+};
+
+extern "C" void colibri_b200_shard_free(colibri_b200_shard* sh) {
+    if (!sh) return;
+    cudaSetDevice(sh->dev);
+    if (sh->s) {
+        cudaStreamSynchronize(sh->s);
+        cudaStreamDestroy(sh->s);
+    }
+    if (sh->ev0) cudaEventDestroy(sh->ev0);
+    if (sh->ev1) cudaEventDestroy(sh->ev1);
+    delete sh;
+}
+
+extern "C" int colibri_b200_shard_begin(colibri_b200_corpus* corpus, const colibri_b200_options* opt, int rank, int world, colibri_b200_shard** out) {
+    if (!out) return set_err(COLIBRI_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!corpus || !opt) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    if (world < 1 || world > 64 || rank < 0 || rank >= world) return set_err(COLIBRI_E_INVALID, "rank %d / world %d", rank, world);
+    colibri_b200_options o = *opt;
+    TRY(check_options(o));
+    if (o.DOSKIPGRAMS_EXHAUSTIVE) return set_err(COLIBRI_E_UNSUPPORTED, "skipgrams are not on the multi-GPU path yet");
+    if (o.MINLENGTH > 1) return set_err(COLIBRI_E_UNSUPPORTED, "MINLENGTH > 1 is not on the multi-GPU path yet");
+    if (corpus->nbytes == 0) return set_err(COLIBRI_E_FORMAT, "Attempting to read pattern from file, but file is empty?");
+    CUDA_TRY(cudaSetDevice(corpus->device));
+    auto* sh   = new colibri_b200_shard();
+    sh->corpus = corpus;
+    sh->o      = o;
+    sh->dev    = corpus->device;
+    sh->rank   = (uint32_t)rank;
+    sh->world  = (uint32_t)world;
+    sh->t      = (uint32_t)o.MINTOKENS;
+    int rc     = [&]() -> int {
+        CUDA_TRY(cudaDeviceGetAttribute(&sh->sms, cudaDevAttrMultiProcessorCount, sh->dev));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sh->s, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&sh->ev0));
+        CUDA_TRY(cudaEventCreate(&sh->ev1));
+        PhaseClock clk(sh);
+        cudaStream_t s = sh->s;
+        // sentence-source quirk exactly as in the single-GPU driver (a shard is a whole file of its own here)
+        size_t staged = corpus->nbytes;
+        uint8_t tail[16];
+        memset(tail, 0x80, sizeof tail);
+        size_t k = 0;
+        if (!corpus->ends_with_delim) {
+            if (o.streamed) tail[k++] = corpus->last_byte;
+            tail[k++] = 0;
+        }
+        staged += k;
+        CUDA_TRY(cudaMemcpyAsync(corpus->body() + corpus->nbytes, tail, sizeof tail, cudaMemcpyHostToDevice, s));
+        const uint32_t nblocks = (uint32_t)(corpus->padded(staged) / kTokTile);
+        TRY(sh->d_stats.alloc(sh->dev, 1));
+        TRY(sh->d_dest.alloc(sh->dev, 3 * 64));
+        CUDA_TRY(cudaMemsetAsync(sh->d_stats.p, 0, sizeof(DeviceStats), s));
+        DevBuf<uint32_t> blk;
+        TRY(blk.alloc(sh->dev, nblocks + 1));
+        sh->launches += launch_tokenise_count(s, corpus->body(), staged, blk.p, nblocks);
+        sh->launches += launch_scan_block_counts(s, blk.p, nblocks, &sh->d_stats.p->cursor);
+        TRY(read_stats(sh));
+        const uint64_t npos_real = sh->h_stats.cursor;
+        if (npos_real >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "shard has %llu positions; the device index is 32 bit", (unsigned long long)npos_real);
+        sh->npos = npos_real + 1;
+        TRY(sh->tok.alloc(sh->dev, sh->npos + 8));
+        CUDA_TRY(cudaMemsetAsync(sh->tok.p + npos_real, 0, 8 * sizeof(uint32_t), s));
+        sh->launches += launch_tokenise_write(s, corpus->body(), staged, blk.p, nblocks, sh->tok.p, sh->d_stats.p);
+        TRY(read_stats(sh));
+        if (sh->h_stats.errflags & (kErrTokenTooLong | kErrNonCanonical)) return set_err(COLIBRI_E_FORMAT, "malformed class encoding in corpus");
+        if (sh->h_stats.errflags & kErrReservedClass) return set_err(COLIBRI_E_UNSUPPORTED, "corpus contains the reserved skip/flex classes (3, 4) as running text");
+        sh->local_tokens   = sh->h_stats.totaltokens;
+        sh->local_maxclass = sh->h_stats.maxclass;
+        return 0;
+    }();
+    if (rc) {
+        colibri_b200_shard_free(sh);
+        return rc;
+    }
+    *out = sh;
+    return 0;
+}
+
+extern "C" int colibri_b200_shard_info(const colibri_b200_shard* sh, uint64_t out[4]) {
+    if (!sh || !out) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    out[0] = sh->local_tokens;
+    out[1] = sh->local_maxclass;
+    out[2] = sh->npos;
+    out[3] = sh->launches;
+    return 0;
+}
+extern "C" double colibri_b200_shard_device_ms(const colibri_b200_shard* sh) {
+    return sh ? sh->device_ms : 0.0;
+}
+
+// local class histogram into the caller's device buffer (u32[nclasses], zeroed here); the caller all-reduces it
+extern "C" int colibri_b200_shard_unigram_counts(colibri_b200_shard* sh, uint32_t nclasses, void* dev_counts) {
+    if (!sh || !dev_counts) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    if (nclasses <= sh->local_maxclass) return set_err(COLIBRI_E_INVALID, "nclasses %u <= local maximum class %u", nclasses, sh->local_maxclass);
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    PhaseClock clk(sh);
+    sh->nclasses = nclasses;
+    CUDA_TRY(cudaMemsetAsync(dev_counts, 0, (size_t)nclasses * 4, sh->s));
+    sh->launches += launch_unigram_hist(sh->s, sh->tok.p, sh->npos, (uint32_t*)dev_counts, nclasses, sh->sms);
+    CUDA_TRY(cudaStreamSynchronize(sh->s));
+    return 0;
+}
+
+// global counts in: prune (identical on every rank), export this rank's share of the surviving unigrams, level-1 ids
+extern "C" int colibri_b200_shard_unigram_finish(colibri_b200_shard* sh, const void* dev_global_counts, uint64_t global_tokens, uint64_t stats[3]) {
+    if (!sh || !dev_global_counts || !stats) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    PhaseClock clk(sh);
+    cudaStream_t s = sh->s;
+    TRY(sh->count1.alloc(sh->dev, sh->nclasses));
+    CUDA_TRY(cudaMemcpyAsync(sh->count1.p, dev_global_counts, (size_t)sh->nclasses * 4, cudaMemcpyDeviceToDevice, s));
+    sh->global_tokens = global_tokens;
+    TRY(zero_phase_stats(sh));
+    Segment sg;
+    sg.n = 1;
+    uint64_t bound = (uint64_t)sh->nclasses / sh->world + 2;
+    TRY(sg.pos.alloc(sh->dev, bound));
+    TRY(sg.cnt.alloc(sh->dev, bound));
+    sh->launches += launch_unigram_prune(s, sh->count1.p, sh->nclasses, sh->t, sg.pos.p, sg.cnt.p, 0, sh->d_stats.p, sh->world, sh->rank);
+    TRY(read_stats(sh));
+    sg.count = sh->h_stats.cursor;
+    sh->segs.push_back(std::move(sg));
+    stats[0] = sh->h_stats.found;
+    stats[1] = sh->h_stats.kept;
+    stats[2] = sh->h_stats.kept_occ;
+    sh->global_types = sh->h_stats.found;
+    const uint32_t t1 = (uint32_t)std::max(sh->o.MINTOKENS, sh->o.MINTOKENS_UNIGRAMS);
+    TRY(sh->prev.alloc(sh->dev, sh->npos + 8));
+    TRY(sh->cur.alloc(sh->dev, sh->npos + 8));
+    sh->launches += launch_make_id1(s, sh->tok.p, sh->npos + 1, sh->count1.p, t1, sh->prev.p);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    sh->prev_valid = sh->local_tokens;
+    sh->level      = 1;
+    return 0;
+}
+
+// local counting of level n; dest_counts[world] = records this rank will send to each owner; stats = {valid windows, distinct local keys}
+extern "C" int colibri_b200_shard_level_count(colibri_b200_shard* sh, int n, uint64_t* dest_counts, uint64_t stats[2]) {
+    if (!sh || !dest_counts || !stats) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    if (n != sh->level + 1) return set_err(COLIBRI_E_INVALID, "level %d requested after level %d", n, sh->level);
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    PhaseClock clk(sh);
+    cudaStream_t s = sh->s;
+    uint64_t bound = std::max<uint64_t>(sh->prev_valid, 1);
+    uint64_t cap   = std::max<uint64_t>(64, bound + bound / 2 + 16);
+    if (cap >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "level %d needs %llu local table slots", n, (unsigned long long)cap);
+    if (sh->table.n < cap) TRY(sh->table.alloc(sh->dev, cap));
+    sh->local_cap = cap;
+    CUDA_TRY(cudaMemsetAsync(sh->table.p, 0, cap * sizeof(NgramSlot), s));
+    CUDA_TRY(cudaMemsetAsync(sh->cur.p + sh->npos, 0, 8 * sizeof(uint32_t), s));
+    CUDA_TRY(cudaMemsetAsync(sh->d_dest.p, 0, 3 * 64 * sizeof(unsigned long long), s));
+    TRY(zero_phase_stats(sh));
+    sh->launches += launch_count_ngrams(s, sh->prev.p, sh->cur.p, sh->npos, sh->table.p, cap, sh->d_stats.p, sh->sms);
+    sh->launches += launch_shard_dest_count(s, sh->table.p, cap, sh->world, sh->d_dest.p, sh->sms);
+    unsigned long long h_dest[64];
+    CUDA_TRY(cudaMemcpyAsync(h_dest, sh->d_dest.p, sh->world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    TRY(read_stats(sh));
+    unsigned long long bases[64];
+    uint64_t total = 0;
+    for (uint32_t d = 0; d < sh->world; ++d) {
+        dest_counts[d] = h_dest[d];
+        bases[d]       = total;
+        total += h_dest[d];
+    }
+    CUDA_TRY(cudaMemcpyAsync(sh->d_dest.p + 64, bases, sh->world * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    sh->nsent = total;
+    stats[0]  = sh->h_stats.valid_windows;
+    stats[1]  = total;
+    return 0;
+}
+
+// write the nsent 16-byte records, grouped by destination rank in rank order, into dev_send
+extern "C" int colibri_b200_shard_level_pack(colibri_b200_shard* sh, void* dev_send) {
+    if (!sh || (!dev_send && sh->nsent)) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    PhaseClock clk(sh);
+    TRY(sh->send_slot.alloc(sh->dev, sh->nsent + 1));
+    if (sh->nsent) sh->launches += launch_shard_pack(sh->s, sh->table.p, sh->local_cap, sh->world, sh->d_dest.p + 64, sh->d_dest.p + 128, dev_send, sh->send_slot.p, sh->sms);
+    CUDA_TRY(cudaStreamSynchronize(sh->s));
+    return 0;
+}
+
+// owner side: merge nrecv records, prune, write nrecv 8-byte replies; stats = {distinct keys owned, kept, kept occurrences}
+extern "C" int colibri_b200_shard_level_merge(colibri_b200_shard* sh, const void* dev_recv, uint64_t nrecv, void* dev_reply, uint64_t stats[3]) {
+    if (!sh || !stats || (nrecv && (!dev_recv || !dev_reply))) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    PhaseClock clk(sh);
+    cudaStream_t s = sh->s;
+    uint64_t cap = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);
+    if (cap * sh->world >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner table of %llu slots x %u ranks exceeds the 32-bit id space", (unsigned long long)cap, sh->world);
+    if (sh->owner_table.n < cap) TRY(sh->owner_table.alloc(sh->dev, cap));
+    sh->owner_cap = cap;
+    TRY(sh->reply_slot.alloc(sh->dev, nrecv + 1));
+    if (sh->bitmap.n < cap / 32 + 8) TRY(sh->bitmap.alloc(sh->dev, cap / 32 + 8));
+    CUDA_TRY(cudaMemsetAsync(sh->owner_table.p, 0, cap * sizeof(NgramSlot), s));
+    TRY(zero_phase_stats(sh));
+    sh->launches += launch_shard_merge(s, dev_recv, nrecv, sh->owner_table.p, cap, sh->reply_slot.p, sh->d_stats.p, sh->sms);
+    sh->launches += launch_shard_prune_owner(s, sh->owner_table.p, cap, sh->t, sh->bitmap.p, sh->d_stats.p, sh->sms);
+    sh->launches += launch_shard_reply(s, sh->reply_slot.p, nrecv, sh->owner_table.p, sh->bitmap.p, sh->world, sh->rank, dev_reply);
+    TRY(read_stats(sh));
+    stats[0] = sh->h_stats.found;
+    stats[1] = sh->h_stats.kept;
+    stats[2] = sh->h_stats.kept_occ;
+    return 0;
+}
+
+// sender side: replies (send order) -> global ids per position; keeps the survivors this rank exports. local_valid = positions with a surviving n-gram
+extern "C" int colibri_b200_shard_level_finish(colibri_b200_shard* sh, const void* dev_reply_back, uint64_t* local_valid) {
+    if (!sh || (sh->nsent && !dev_reply_back)) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    PhaseClock clk(sh);
+    cudaStream_t s = sh->s;
+    const int n = sh->level + 1;
+    if (sh->gid_of_slot.n < sh->local_cap) TRY(sh->gid_of_slot.alloc(sh->dev, sh->local_cap));
+    Segment sg;
+    sg.n = n;
+    TRY(sg.pos.alloc(sh->dev, sh->nsent + 1));
+    TRY(sg.cnt.alloc(sh->dev, sh->nsent + 1));
+    TRY(zero_phase_stats(sh));
+    sh->launches += launch_shard_apply(s, dev_reply_back, sh->send_slot.p, sh->nsent, sh->table.p, sh->gid_of_slot.p, sg.pos.p, sg.cnt.p, sh->d_stats.p, sh->sms);
+    sh->launches += launch_shard_relabel(s, sh->cur.p, sh->npos, sh->gid_of_slot.p, sh->d_stats.p, sh->sms);
+    TRY(read_stats(sh));
+    sg.count = sh->h_stats.cursor;
+    if (sg.count) sh->segs.push_back(std::move(sg));
+    sh->prev_valid = sh->h_stats.kept_occ;
+    if (local_valid) *local_valid = sh->prev_valid;
+    std::swap(sh->prev, sh->cur);
+    sh->level = n;
+    return 0;
+}
+
+// export this rank's share of the model.  passes = npasses x {n, found, foundskip, pruned} (global numbers, reduced by the caller)
+extern "C" int colibri_b200_shard_finish(colibri_b200_shard* sh, const uint64_t* passes, int npasses, uint64_t global_types, int maxn, int minn, colibri_b200_model** out) {
+    if (!sh || !out) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    auto* m       = new colibri_b200_model();
+    m->device     = sh->dev;
+    m->model_type = sh->o.model_type;
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete m;
+        return set_err(COLIBRI_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    m->totaltokens = sh->global_tokens;
+    m->totaltypes  = global_types;
+    m->maxn        = maxn;
+    m->minn        = minn;
+    for (int p = 0; p < npasses; ++p) m->passes.push_back({passes[4 * p], passes[4 * p + 1], passes[4 * p + 2], passes[4 * p + 3]});
+    int rc;
+    {
+        PhaseClock clk(sh);
+        rc = export_segments(sh->dev, sh->s, sh->segs, sh->tok.p, m, sh->launches);
+        cudaStreamSynchronize(sh->s);
+    }
+    if (rc) {
+        colibri_b200_model_free(m);
+        return rc;
+    }
+    m->counters[0]          = sh->npos - 1;
+    m->counters[1]          = sh->corpus->nbytes;
+    m->counters[2]          = sh->launches;
+    m->ms[COLIBRI_T_TOTAL]  = sh->device_ms;
+    *out = m;
+    return 0;
+}

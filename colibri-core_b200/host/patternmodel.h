@@ -1,0 +1,367 @@
+// patternmodel.h -- the reference's C++ training API, re-implemented on top of the B200 C ABI (include/colibri_b200.h).
+//
+// Same class names, method names, argument order and error behaviour as the reference for the training path:
+//   PatternModelOptions                       reference include/patternmodel.h:103-213
+//   IndexedCorpus                             reference include/patternstore.h:43-401, src/pattern.cpp:1900-2162 (load / sentences only)
+//   PatternModel<uint32_t>::train(...)        reference include/patternmodel.h:880 (istream) and :1353 (filename)
+//   IndexedPatternModel<>::train(...)         reference include/patternmodel.h:2821-2844
+//   size/has/occurrencecount/types/tokens/maxlength/minlength/begin/end/write   reference :744, :751, :1653, :1700, :1709, :1640-1648, :1609-1629
+// so that a caller such as src/patternmodeller.cpp:316-319 compiles against this header unchanged.  train() stages the
+// corpus bytes in HBM, runs every counting pass on the GPU and keeps the resulting patterns as flat host arrays; the
+// std::unordered_map view the reference exposes is materialised lazily, only if a caller iterates or looks patterns up.
+// Progress lines on std::cerr are the reference's own (patternmodel.h:922-931, :1005-1019, :1190-1245) unless options.QUIET.
+// Errors print a message on std::cerr and throw InternalError (reference include/common.h:41-44).  There is no CPU
+// implementation behind this header: option combinations outside the accelerated subset throw, they do not fall back.
+#pragma once
+#include <cstdint>
+#include <fstream>
+#include <iostream>
+#include <istream>
+#include <iterator>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../../include/colibri_b200.h"
+#include "pattern.h"
+
+enum ModelType {  // reference include/patternmodel.h:68-75
+    UNINDEXEDPATTERNMODEL = 10,
+    UNINDEXEDPATTERNPOINTERMODEL = 11,
+    INDEXEDPATTERNMODEL = 20,
+    INDEXEDPATTERNPOINTERMODEL = 21,
+    PATTERNSETMODEL = 30,
+    PATTERNALIGNMENTMODEL = 40,
+};
+
+/// Same public fields and defaults as the reference (include/patternmodel.h:105-180).
+class PatternModelOptions {
+  public:
+    int  MINTOKENS = -1;
+    int  MINTOKENS_SKIPGRAMS = -1;
+    int  MINTOKENS_UNIGRAMS = 1;
+    int  MINLENGTH = 1;
+    int  MAXLENGTH = 100;
+    int  MAXBACKOFFLENGTH = 100;
+    bool DOSKIPGRAMS = false;
+    bool DOSKIPGRAMS_EXHAUSTIVE = false;
+    int  MINSKIPTYPES = 2;
+    int  MAXSKIPS = 3;
+    bool DOREVERSEINDEX = true;
+    bool DOPATTERNPERLINE = false;
+    int  PRUNENONSUBSUMED = 0;
+    int  PRUNESUBSUMED = 0;
+    bool DOREMOVEINDEX = false;
+    bool DOREMOVENGRAMS = false;
+    bool DOREMOVESKIPGRAMS = false;
+    bool DOREMOVEFLEXGRAMS = false;
+    bool DORESET = false;
+    bool QUIET = false;
+    bool DEBUG = false;
+};
+
+/// A corpus held in host memory (the reference's "reverse index").  Only what the training path uses: load(), sentences().
+class IndexedCorpus {
+    std::vector<unsigned char> body_;  // bytes after the 0xA2 0x02 header
+    uint32_t                   sentences_ = 0;
+
+  public:
+    IndexedCorpus() {}
+    explicit IndexedCorpus(std::istream& in, bool debug = false) { load(in, debug); }
+    explicit IndexedCorpus(const std::string& filename, bool debug = false) { load(filename, debug); }
+    void load(std::istream& in, bool = false) {
+        if (!in.good()) {
+            std::cerr << "ERROR: Supplied data file can not be opened. Check whether it exists and whether you have proper permissions..." << std::endl;
+            throw InternalError();
+        }
+        std::vector<unsigned char> all((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        if (all.size() < 2 || all[0] != 0xA2 || all[1] != 2) {
+            std::cerr << "ERROR: the B200 build reads class-encoded corpora of data version 2 only (0xA2 0x02 header)" << std::endl;
+            throw InternalError();
+        }
+        body_.assign(all.begin() + 2, all.end());
+        // sentence index as in reference src/pattern.cpp:1944-1958: a sentence starts at byte 0 and after every delimiter
+        sentences_         = 0;
+        bool prevdelimiter = true, prevhigh = false;
+        for (unsigned char c : body_) {
+            if (prevdelimiter) {
+                ++sentences_;
+                prevdelimiter = false;
+            }
+            if (!prevhigh && c == 0) prevdelimiter = true;
+            prevhigh = c >= 128;
+        }
+    }
+    void load(const std::string& filename, bool debug = false) {
+        std::ifstream in(filename, std::ios::in | std::ios::binary);
+        if (!in.good()) {
+            std::cerr << "ERROR: Unable to load file " << filename << std::endl;
+            throw InternalError();
+        }
+        load(in, debug);
+    }
+    unsigned int         sentences() const { return sentences_; }
+    size_t               bytesize() const { return body_.size(); }
+    const unsigned char* beginpointer() const { return body_.data(); }
+};
+
+class PatternModelInterface {  // reference include/patternmodel.h:234-287
+  public:
+    virtual ~PatternModelInterface() {}
+    virtual int    getmodeltype() const = 0;
+    virtual int    getmodelversion() const = 0;
+    virtual size_t occurrencecount(const Pattern& pattern) = 0;
+    virtual int    maxlength() const = 0;
+    virtual int    minlength() const = 0;
+    virtual size_t types() = 0;
+    virtual size_t tokens() const = 0;
+};
+
+/// Placeholder so that the train() signatures match the reference's (filter argument); filters are not on the device path.
+template <class T = uint32_t>
+class PatternSet {
+  public:
+    size_t size() const { return 0; }
+};
+
+namespace colibri_b200_detail {
+inline int& default_device() {  // CUDA device the next train() call uses (the reference has no such notion)
+    static int device = 0;
+    return device;
+}
+inline void fail(const std::string& msg) {
+    std::cerr << "ERROR: " << msg << std::endl;
+    throw InternalError();
+}
+struct ModelHandle {  // frees the C-ABI handle
+    colibri_b200_model* h = nullptr;
+    ~ModelHandle() { colibri_b200_model_free(h); }
+};
+}  // namespace colibri_b200_detail
+
+template <class ValueType, int kModelType>
+class DevicePatternModel : public PatternModelInterface {
+  protected:
+    std::vector<uint8_t>  keys_;
+    std::vector<uint64_t> off_;
+    std::vector<uint32_t> counts_;
+    std::vector<uint32_t> ref_sentence_;
+    std::vector<uint16_t> ref_token_;
+    std::vector<uint64_t> ref_off_;
+    uint64_t              totaltokens = 0, totaltypes = 0;
+    int                   maxn = 0, minn = 999;
+    IndexedCorpus*        reverseindex = nullptr;
+    std::unordered_map<Pattern, ValueType> map_;  // lazily built view
+    bool                                   map_ready_ = false;
+
+    void materialise();
+
+    void train_body(const unsigned char* body, size_t nbytes, bool streamed, const PatternModelOptions& options, PatternModelInterface* constrainbymodel, PatternSet<>* filter,
+                    bool continued, uint32_t firstsentence) {
+        using colibri_b200_detail::fail;
+        if (constrainbymodel != nullptr) fail("training constrained by another model is not available in the B200 build");
+        if (filter != nullptr && filter->size() > 0) fail("training with a pattern filter is not available in the B200 build");
+        if (continued) fail("continued training is not available in the B200 build");
+        if (firstsentence != 1) fail("firstsentence != 1 is not available in the B200 build");
+        colibri_b200_options o;
+        colibri_b200_options_default(&o);
+        o.MINTOKENS              = options.MINTOKENS;
+        o.MINTOKENS_SKIPGRAMS    = options.MINTOKENS_SKIPGRAMS;
+        o.MINTOKENS_UNIGRAMS     = options.MINTOKENS_UNIGRAMS;
+        o.MINLENGTH              = options.MINLENGTH;
+        o.MAXLENGTH              = options.MAXLENGTH;
+        o.MAXBACKOFFLENGTH       = options.MAXBACKOFFLENGTH;
+        o.MINSKIPTYPES           = options.MINSKIPTYPES;
+        o.MAXSKIPS               = options.MAXSKIPS;
+        o.DOSKIPGRAMS            = options.DOSKIPGRAMS;
+        o.DOSKIPGRAMS_EXHAUSTIVE = options.DOSKIPGRAMS_EXHAUSTIVE;
+        o.DOPATTERNPERLINE       = options.DOPATTERNPERLINE;
+        o.PRUNENONSUBSUMED       = options.PRUNENONSUBSUMED;
+        o.PRUNESUBSUMED          = options.PRUNESUBSUMED;
+        o.QUIET                  = options.QUIET;
+        o.DEBUG                  = options.DEBUG;
+        o.model_type             = kModelType;
+        o.streamed               = streamed ? 1 : 0;
+        o.device                 = colibri_b200_detail::default_device();
+        const int mintokens      = options.MINTOKENS == -1 ? 2 : (options.MINTOKENS == 0 ? 1 : options.MINTOKENS);
+        if (!options.QUIET) std::cerr << "Training patternmodel, occurrence threshold: " << mintokens << std::endl;  // reference :922-931
+        colibri_b200_detail::ModelHandle mh;
+        if (colibri_b200_train(body, nbytes, &o, &mh.h) != COLIBRI_OK) fail(colibri_b200_last_error());
+        totaltokens  = colibri_b200_model_tokens(mh.h);
+        totaltypes   = colibri_b200_model_types(mh.h);
+        maxn         = colibri_b200_model_maxn(mh.h);
+        minn         = colibri_b200_model_minn(mh.h);
+        hasskipgrams = colibri_b200_model_hasskipgrams(mh.h) != 0;
+        if (!options.QUIET) {  // the reference's per-pass progress lines (:1005-1019, :1190-1245)
+            const int np = colibri_b200_model_passes(mh.h);
+            for (int p = 0; p < np; ++p) {
+                uint64_t st[4];
+                colibri_b200_model_pass_stats(mh.h, p, st);
+                if (mintokens > 1)
+                    std::cerr << "Counting " << st[0] << "-grams" << std::endl;
+                else
+                    std::cerr << "Counting *all* n-grams (occurrence threshold=1)" << std::endl;
+                std::cerr << " Found " << st[1] << " ngrams...";
+                if (options.DOSKIPGRAMS_EXHAUSTIVE) std::cerr << st[2] << " skipgram occurrences...";
+                std::cerr << "pruned " << st[3] << "...total kept: " << (st[1] + st[2]) - st[3] << std::endl;
+            }
+            if (mintokens > 1 && np > 0 && np < options.MAXLENGTH) {
+                uint64_t st[4];
+                colibri_b200_model_pass_stats(mh.h, np - 1, st);
+                std::cerr << "Counting " << st[0] + 1 << "-grams" << std::endl << "None found" << std::endl;
+            }
+        }
+        uint64_t np = 0, kb = 0, nr = 0;
+        if (colibri_b200_model_export_sizes(mh.h, &np, &kb, &nr) != COLIBRI_OK) fail(colibri_b200_last_error());
+        keys_.assign(kb + 1, 0);
+        off_.assign(np + 1, 0);
+        counts_.assign(np + 1, 0);
+        if (kModelType == INDEXEDPATTERNMODEL) {
+            ref_sentence_.assign(nr + 1, 0);
+            ref_token_.assign(nr + 1, 0);
+            ref_off_.assign(np + 1, 0);
+        }
+        if (colibri_b200_model_export(mh.h, keys_.data(), off_.data(), counts_.data(), kModelType == INDEXEDPATTERNMODEL ? ref_sentence_.data() : nullptr,
+                                      kModelType == INDEXEDPATTERNMODEL ? ref_token_.data() : nullptr, kModelType == INDEXEDPATTERNMODEL ? ref_off_.data() : nullptr) != COLIBRI_OK)
+            fail(colibri_b200_last_error());
+        counts_.resize(np);
+        map_.clear();
+        map_ready_ = false;
+    }
+
+  public:
+    bool hasskipgrams = false;
+    bool hasflexgrams = false;
+
+    DevicePatternModel(IndexedCorpus* corpus = nullptr) : reverseindex(corpus) {}
+    virtual ~DevicePatternModel() {}
+
+    int getmodeltype() const override { return kModelType; }
+    int getmodelversion() const override { return 2; }
+    unsigned char type() const { return (unsigned char)kModelType; }
+    unsigned char version() const { return 2; }
+
+    /// Train on corpus data read from a stream (a *.colibri.dat); `in` may be NULL if a preloaded corpus was given to the constructor.
+    virtual void train(std::istream* in, const PatternModelOptions& options, PatternModelInterface* constrainbymodel = nullptr, PatternSet<>* filter = nullptr, bool continued = false,
+                       uint32_t firstsentence = 1, bool ignoreerrors = false) {
+        (void)ignoreerrors;
+        if (reverseindex != nullptr) {  // reference :1030-1037: sentences come from the preloaded corpus when there is one
+            train_body(reverseindex->beginpointer(), reverseindex->bytesize(), false, options, constrainbymodel, filter, continued, firstsentence);
+            return;
+        }
+        if (in == nullptr) colibri_b200_detail::fail("train() needs an input stream or a preloaded IndexedCorpus");
+        if (!in->good()) {
+            std::cerr << "ERROR: Supplied data file can not be opened. Check whether it exists and whether you have proper permissions..." << std::endl;  // classdecoder.cpp:263-266
+            throw InternalError();
+        }
+        in->clear();
+        in->seekg(0);
+        std::vector<unsigned char> all((std::istreambuf_iterator<char>(*in)), std::istreambuf_iterator<char>());
+        if (all.size() < 2 || all[0] != 0xA2 || all[1] != 2)
+            colibri_b200_detail::fail("the B200 build reads class-encoded corpora of data version 2 only (0xA2 0x02 header)");
+        train_body(all.data() + 2, all.size() - 2, true, options, constrainbymodel, filter, continued, firstsentence);
+    }
+    /// Train on a corpus file (*.colibri.dat).
+    virtual void train(const std::string& filename, const PatternModelOptions& options, PatternModelInterface* constrainbymodel = nullptr, PatternSet<>* filter = nullptr,
+                       bool continued = false, uint32_t firstsentence = 1, bool ignoreerrors = false) {
+        if (filename.size() > 3 && filename.substr(filename.size() - 3) == ".bz2") colibri_b200_detail::fail("bz2-compressed corpora are not read by the B200 build");
+        std::ifstream in(filename, std::ios::in | std::ios::binary);
+        this->train(&in, options, constrainbymodel, filter, continued, firstsentence, ignoreerrors);
+    }
+
+    size_t size() const { return counts_.size(); }
+    size_t tokens() const override { return totaltokens; }
+    size_t types() override { return totaltypes; }
+    int    maxlength() const override { return maxn; }
+    int    minlength() const override { return minn; }
+
+    bool has(const Pattern& pattern) {
+        materialise();
+        return map_.find(pattern) != map_.end();
+    }
+    size_t occurrencecount(const Pattern& pattern) override;
+    ValueType* getdata(const Pattern& pattern, bool = false) {
+        materialise();
+        auto it = map_.find(pattern);
+        return it == map_.end() ? nullptr : &it->second;
+    }
+
+    typedef typename std::unordered_map<Pattern, ValueType>::iterator       iterator;
+    typedef typename std::unordered_map<Pattern, ValueType>::const_iterator const_iterator;
+    iterator begin() { materialise(); return map_.begin(); }
+    iterator end() { materialise(); return map_.end(); }
+
+    /// The i-th pattern of the flat result (no map involved): fast path for bulk consumers.
+    Pattern  flat_pattern(size_t i) const { return Pattern(keys_.data() + off_[i], (int)(off_[i + 1] - off_[i])); }
+    uint32_t flat_count(size_t i) const { return counts_[i]; }
+
+    /// Write the model in the reference's binary format (reference :1609-1624, patternstore.h:534-542, datatypes.h:216-221, :263-270).
+    void write(std::ostream& out) {
+        const char    null = 0;
+        unsigned char t = (unsigned char)kModelType, v = 2;
+        out.write(&null, 1);
+        out.write(reinterpret_cast<char*>(&t), 1);
+        out.write(reinterpret_cast<char*>(&v), 1);
+        out.write(reinterpret_cast<char*>(&totaltokens), sizeof(uint64_t));
+        const uint64_t tp = totaltypes;
+        out.write(reinterpret_cast<const char*>(&tp), sizeof(uint64_t));
+        const uint64_t s = counts_.size();
+        out.write(reinterpret_cast<const char*>(&s), sizeof(uint64_t));
+        for (size_t i = 0; i < counts_.size(); ++i) {
+            out.write(reinterpret_cast<const char*>(keys_.data() + off_[i]), (std::streamsize)(off_[i + 1] - off_[i]));
+            out.write(&null, 1);
+            out.write(reinterpret_cast<const char*>(&counts_[i]), sizeof(uint32_t));
+            if (kModelType == INDEXEDPATTERNMODEL) {
+                for (uint64_t j = ref_off_[i]; j < ref_off_[i + 1]; ++j) {
+                    out.write(reinterpret_cast<const char*>(&ref_sentence_[j]), 4);
+                    out.write(reinterpret_cast<const char*>(&ref_token_[j]), 2);
+                }
+            }
+        }
+    }
+    void write(const std::string& filename) {
+        std::ofstream out(filename, std::ios::out | std::ios::binary);
+        this->write(out);
+    }
+};
+
+// ---- unindexed: value = occurrence count
+template <class ValueType, int kModelType>
+inline void DevicePatternModel<ValueType, kModelType>::materialise() {
+    if (map_ready_) return;
+    map_.reserve(counts_.size());
+    for (size_t i = 0; i < counts_.size(); ++i) {
+        if constexpr (kModelType == INDEXEDPATTERNMODEL) {
+            ValueType& v = map_[flat_pattern(i)];
+            for (uint64_t j = ref_off_[i]; j < ref_off_[i + 1]; ++j) v.data.push_back(IndexReference(ref_sentence_[j], ref_token_[j]));
+        } else {
+            map_[flat_pattern(i)] = (ValueType)counts_[i];
+        }
+    }
+    map_ready_ = true;
+}
+template <class ValueType, int kModelType>
+inline size_t DevicePatternModel<ValueType, kModelType>::occurrencecount(const Pattern& pattern) {
+    materialise();
+    auto it = map_.find(pattern);
+    if (it == map_.end()) return 0;
+    if constexpr (kModelType == INDEXEDPATTERNMODEL)
+        return it->second.count();
+    else
+        return (size_t)it->second;
+}
+
+/// PatternModel<uint32_t>: the unindexed model (reference include/patternmodel.h:545)
+template <class ValueType = uint32_t>
+class PatternModel : public DevicePatternModel<ValueType, UNINDEXEDPATTERNMODEL> {
+  public:
+    PatternModel(IndexedCorpus* corpus = nullptr) : DevicePatternModel<ValueType, UNINDEXEDPATTERNMODEL>(corpus) {}
+};
+
+/// IndexedPatternModel<>: value = sorted list of positions (reference include/patternmodel.h:2681)
+template <class MapType = void>
+class IndexedPatternModel : public DevicePatternModel<IndexedData, INDEXEDPATTERNMODEL> {
+  public:
+    IndexedPatternModel(IndexedCorpus* corpus = nullptr) : DevicePatternModel<IndexedData, INDEXEDPATTERNMODEL>(corpus) {}
+};

@@ -1,0 +1,229 @@
+"""Multi-GPU PatternModel::train: one process per GPU, corpus sharded at sentence boundaries, model partitioned by hash.
+
+The library (csrc/shard.cu) exposes each rank's work as phases with plain device pointers; this module is the plumbing
+between them: torch.distributed collectives over NCCL/NVLink (gloo on CPU in the tests, with a stand-in engine).
+
+Per level n >= 2:
+    level_count -> level_pack -> all_to_all(16-byte records) -> level_merge -> all_to_all(8-byte replies) -> level_finish
+Level 1 is an all-reduce of the class histograms.  Every rank ends with its own share of the surviving patterns
+(the rank that first delivered a pattern to its owner exports it, with the global count).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+
+class CudaShardEngine:
+    """Thin wrapper over the colibri_b200_shard_* phases for one rank; buffers are torch CUDA tensors."""
+
+    def __init__(self, corpus, options, rank, world, device):
+        import torch
+
+        from . import _check, library
+
+        self.torch, self._check, self.lib = torch, _check, library()
+        self.device = torch.device("cuda", device)
+        self.rank, self.world = rank, world
+        self.corpus = corpus
+        self._h = C.c_void_p()
+        _check(self.lib.colibri_b200_shard_begin(corpus._h, C.byref(options._c), rank, world, C.byref(self._h)))
+
+    def new_buffer(self, nwords):
+        return self.torch.empty(max(int(nwords), 1), dtype=self.torch.int32, device=self.device)
+
+    def info(self):
+        out = (C.c_uint64 * 4)()
+        self._check(self.lib.colibri_b200_shard_info(self._h, out))
+        return {"tokens": int(out[0]), "maxclass": int(out[1]), "positions": int(out[2]), "launches": int(out[3])}
+
+    def device_ms(self):
+        return float(self.lib.colibri_b200_shard_device_ms(self._h))
+
+    def unigram_counts(self, nclasses):
+        buf = self.new_buffer(nclasses)
+        self._check(self.lib.colibri_b200_shard_unigram_counts(self._h, nclasses, buf.data_ptr()))
+        return buf
+
+    def unigram_finish(self, global_counts, global_tokens):
+        st = (C.c_uint64 * 3)()
+        self._check(self.lib.colibri_b200_shard_unigram_finish(self._h, global_counts.data_ptr(), global_tokens, st))
+        return tuple(int(x) for x in st)
+
+    def level_count(self, n):
+        dest = (C.c_uint64 * self.world)()
+        st = (C.c_uint64 * 2)()
+        self._check(self.lib.colibri_b200_shard_level_count(self._h, n, dest, st))
+        return [int(x) for x in dest], int(st[0]), int(st[1])
+
+    def level_pack(self, nsend):
+        buf = self.new_buffer(nsend * 4)
+        self._check(self.lib.colibri_b200_shard_level_pack(self._h, buf.data_ptr()))
+        return buf
+
+    def level_merge(self, recv, nrecv):
+        reply = self.new_buffer(nrecv * 2)
+        st = (C.c_uint64 * 3)()
+        self._check(self.lib.colibri_b200_shard_level_merge(self._h, recv.data_ptr(), nrecv, reply.data_ptr(), st))
+        return reply, tuple(int(x) for x in st)
+
+    def level_finish(self, reply_back):
+        v = C.c_uint64()
+        self._check(self.lib.colibri_b200_shard_level_finish(self._h, reply_back.data_ptr(), C.byref(v)))
+        return int(v.value)
+
+    def finish(self, passes, types, maxn, minn):
+        from . import Model
+
+        flat = (C.c_uint64 * (4 * max(len(passes), 1)))()
+        for i, p in enumerate(passes):
+            for j in range(4):
+                flat[4 * i + j] = int(p[j])
+        h = C.c_void_p()
+        self._check(self.lib.colibri_b200_shard_finish(self._h, flat, len(passes), types, maxn, minn, C.byref(h)))
+        return Model(h)
+
+    def sync(self):
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    def close(self):
+        if self._h:
+            self.lib.colibri_b200_shard_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _exchange(dist, torch, engine, send, send_counts, width):
+    """all-to-all of variable-length record groups; returns (recv buffer, recv_counts)."""
+    world = len(send_counts)
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=send.device)
+    rc = torch.empty(world, dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(rc, sc)
+    recv_counts = [int(x) for x in rc.tolist()]
+    recv = engine.new_buffer(sum(recv_counts) * width)
+    nsend, nrecv = sum(send_counts) * width, sum(recv_counts) * width
+    dist.all_to_all_single(recv[:nrecv], send[:nsend], output_split_sizes=[c * width for c in recv_counts], input_split_sizes=[c * width for c in send_counts])
+    engine.sync()
+    return recv, recv_counts
+
+
+def train_distributed(engine, dist, torch, mintokens=2, maxlength=5):
+    """Drive one rank through all levels.  Returns (local model share, global passes, global header dict)."""
+    world = dist.get_world_size()
+    info = engine.info()
+    dev = engine.new_buffer(1).device
+    head = torch.tensor([info["tokens"], 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(head[:1], op=dist.ReduceOp.SUM)
+    mx = torch.tensor([info["maxclass"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    global_tokens, nclasses = int(head[0].item()), int(mx.item()) + 1
+
+    counts = engine.unigram_counts(nclasses)
+    dist.all_reduce(counts[:nclasses], op=dist.ReduceOp.SUM)  # u32 counts carried as int32 bit patterns: exact below 2^31 occurrences per class
+    engine.sync()
+    found, kept, kept_occ = engine.unigram_finish(counts, global_tokens)
+    passes, maxn, minn, types = [], 0, 999, found
+    if found:
+        passes.append((1, found, 0, found - kept))
+        maxn = minn = 1
+    prev_kept = kept
+    n = 2
+    while found and n <= maxlength and prev_kept > 0:
+        dest_counts, _windows, nsend = engine.level_count(n)
+        send = engine.level_pack(nsend)
+        recv, recv_counts = _exchange(dist, torch, engine, send, dest_counts, 4)
+        reply, (f, k, occ) = engine.level_merge(recv, sum(recv_counts))
+        # replies travel back along the same routes: what I received from rank r goes back to r
+        nrep, nback = sum(recv_counts) * 2, nsend * 2
+        back = engine.new_buffer(nback)
+        dist.all_to_all_single(back[:nback], reply[:nrep], output_split_sizes=[c * 2 for c in dest_counts], input_split_sizes=[c * 2 for c in recv_counts])
+        st = torch.tensor([f, k, occ], dtype=torch.int64, device=dev)
+        dist.all_reduce(st, op=dist.ReduceOp.SUM)
+        engine.sync()
+        engine.level_finish(back)
+        gf, gk, _gocc = (int(x) for x in st.tolist())
+        if gf == 0:
+            break  # "None found" (reference include/patternmodel.h:1189-1194)
+        passes.append((n, gf, 0, gf - gk))
+        maxn, minn = max(maxn, n), min(minn, n)
+        prev_kept = gk
+        n += 1
+    if mintokens == 1 and passes:  # the reference reports one pass when every length is extracted in a single scan
+        passes = [(1, sum(p[1] for p in passes), 0, sum(p[3] for p in passes))]
+    model = engine.finish(passes, types, maxn, minn)
+    return model, passes, {"tokens": global_tokens, "types": types, "maxn": maxn, "minn": minn}
+
+
+def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, measured_peaks):
+    """bench.py --gpus N under torchrun: weak scaling, every rank trains its own `--tokens` shard of one global stream."""
+    import torch
+
+    import colibri_core_b200 as cb
+
+    ntok = int(a.tokens)
+    opts = cb.PatternModelOptions(MINTOKENS=a.mintokens, MAXLENGTH=a.maxlength, streamed=1, QUIET=1, device=local)
+    corpus = cb.Corpus.synthetic(ntok, vocab=a.vocab, seed=a.seed, device=local, first_token=rank * ntok)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        eng = CudaShardEngine(corpus, opts, rank, world, local)
+        model, passes, head = train_distributed(eng, dist, torch, a.mintokens, a.maxlength)
+        out = (len(model), head, passes, eng.device_ms(), eng.info()["launches"])
+        model.close()
+        eng.close()
+        return out
+
+    for _ in range(a.warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    launches, dev_ms, last = 0, 0.0, None
+    for _ in range(a.steps):
+        last = step()
+        launches += last[4]
+        dev_ms += last[3]
+    e1.record()
+    barrier()
+    elapsed = max(time.perf_counter() - t0, e0.elapsed_time(e1) / 1e3)
+    t = torch.tensor([elapsed, dev_ms / 1e3], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)  # the slowest rank defines the step
+    npat = torch.tensor([last[0], launches], dtype=torch.int64, device="cuda")
+    dist.all_reduce(npat, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        clocks = sampler.stop()
+        elapsed = float(t[0].item())
+        tokens = last[1]["tokens"]
+        peak, peak_src = measured_peaks()
+        line = {
+            "metric": metric, "value": tokens * a.steps / elapsed, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * elapsed / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 (integer)", "data": "synthetic",
+            "config": {"workload": workload + " PER GPU (shards of one global stream)", "global_tokens": tokens, "patterns": int(npat[0].item()),
+                       "parallelism": "corpus sharded by sentence x%d, model hash-partitioned, NCCL all-to-all of (key,count) records per level" % world,
+                       "l2": "inputs exceed L2", "timing": "max over ranks of max(CUDA events, wall clock) around K steps"},
+            "device_ms_per_step_max_rank": 1e3 * float(t[1].item()) / a.steps, "passes": last[2],
+            "roofline": {"bound": "hbm", "kernel": "count_ngrams_kernel", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "peak_source": peak_src, "traffic": None,
+                         "note": "per-kernel roofline is reported by the 1-GPU run; the N-GPU line reports whole-job throughput",
+                         "hbm_read_roofline_frac": (a.maxlength * corpus.nbytes / (elapsed / a.steps) / 1e9) / peak},
+            "clocks": clocks, "gpu_launches": int(npat[1].item()),
+            "e2e": None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

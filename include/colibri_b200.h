@@ -130,6 +130,30 @@ int colibri_b200_model_counters(const colibri_b200_model* m, uint64_t out[8]);
 /* per level n>=2: out[0]=valid windows (upserts), out[1]=table capacity in slots, out[2]=count-kernel ms */
 int colibri_b200_model_level_counters(const colibri_b200_model* m, int n, double out[3]);
 
+/* ---- multi-GPU: one process per GPU drives these per-rank phases and moves the buffers between ranks itself
+ * (torch.distributed / NCCL all-to-all); the library does no communication.  Model = hash-partitioned across ranks,
+ * corpus = sharded at sentence boundaries (nothing in the reference corresponds to this).
+ * Order per rank: shard_begin, shard_unigram_counts, [all-reduce SUM of the u32 counts], shard_unigram_finish, then for
+ * n = 2.. : shard_level_count, shard_level_pack, [all-to-all of 16-byte records], shard_level_merge,
+ * [all-to-all back of 8-byte replies], shard_level_finish; finally shard_finish. */
+typedef struct colibri_b200_shard colibri_b200_shard;
+int    colibri_b200_shard_begin(colibri_b200_corpus* corpus, const colibri_b200_options* opt, int rank, int world, colibri_b200_shard** out);
+/* out[0]=local tokens, out[1]=local maximum class, out[2]=positions, out[3]=kernel launches so far */
+int    colibri_b200_shard_info(const colibri_b200_shard* sh, uint64_t out[4]);
+double colibri_b200_shard_device_ms(const colibri_b200_shard* sh);
+int    colibri_b200_shard_unigram_counts(colibri_b200_shard* sh, uint32_t nclasses, void* dev_counts /* u32[nclasses] */);
+/* stats[0]=distinct unigrams (global), [1]=kept, [2]=occurrences kept */
+int    colibri_b200_shard_unigram_finish(colibri_b200_shard* sh, const void* dev_global_counts, uint64_t global_tokens, uint64_t stats[3]);
+/* dest_counts[world]: records this rank sends to each owner; stats[0]=valid windows, [1]=distinct local keys */
+int    colibri_b200_shard_level_count(colibri_b200_shard* sh, int n, uint64_t* dest_counts, uint64_t stats[2]);
+int    colibri_b200_shard_level_pack(colibri_b200_shard* sh, void* dev_send /* 16 B per record, grouped by owner */);
+/* stats[0]=distinct keys owned, [1]=kept, [2]=occurrences kept (this owner) */
+int    colibri_b200_shard_level_merge(colibri_b200_shard* sh, const void* dev_recv, uint64_t nrecv, void* dev_reply /* 8 B per record */, uint64_t stats[3]);
+int    colibri_b200_shard_level_finish(colibri_b200_shard* sh, const void* dev_reply_back, uint64_t* local_valid);
+/* passes: npasses x {n, found, foundskip, pruned} global numbers; the returned model holds THIS RANK'S share of the patterns */
+int    colibri_b200_shard_finish(colibri_b200_shard* sh, const uint64_t* passes, int npasses, uint64_t global_types, int maxn, int minn, colibri_b200_model** out);
+void   colibri_b200_shard_free(colibri_b200_shard* sh);
+
 /* ---- L1 pieces exposed for parity tests of SURVEY.md 8(a) rows a1/a5/a10 */
 /* SpookyHash::Hash64(key, len, 0) computed ON THE DEVICE for n variable-length messages (Pattern::hash, src/pattern.cpp:234-238) */
 int colibri_b200_hash64_batch(const uint8_t* keys, const uint64_t* key_off, uint64_t n, uint64_t* out, int device);
@@ -145,6 +169,7 @@ typedef struct colibri_b200_synth_params {
     uint32_t mean_sentence;
     uint32_t phrase_permille;
     uint32_t nphrases;
+    uint64_t first_token;   /* index of this corpus's first token in the global stream (multi-GPU shards); 0 for a whole corpus */
 } colibri_b200_synth_params;
 int colibri_b200_synth_corpus(const colibri_b200_synth_params* p, int device, colibri_b200_corpus** out);
 /* copy a staged corpus body back to the host */

@@ -56,6 +56,7 @@ class SynthParams(C.Structure):
         ("mean_sentence", C.c_uint32),
         ("phrase_permille", C.c_uint32),
         ("nphrases", C.c_uint32),
+        ("first_token", C.c_uint64),
     ]
 
 
@@ -364,9 +365,9 @@ def encode_corpus(sentences) -> bytes:
     return bytes(out)
 
 
-def synth_corpus(ntokens: int, vocab: int = 100000, seed: int = 1, mean_sentence: int = 22, phrase_permille: int = 0, nphrases: int = 0) -> np.ndarray:
+def synth_corpus(ntokens: int, vocab: int = 100000, seed: int = 1, mean_sentence: int = 22, phrase_permille: int = 0, nphrases: int = 0, first_token: int = 0) -> np.ndarray:
     """The counter-based synthetic corpus (body only, no 0xA2 0x02 header), CPU realisation."""
-    p = SynthParams(seed, ntokens, vocab, mean_sentence, phrase_permille, nphrases)
+    p = SynthParams(seed, ntokens, vocab, mean_sentence, phrase_permille, nphrases, first_token)
     need = lib().oracle_synth_corpus(C.byref(p), None, 0)
     buf = np.zeros(need, dtype=np.uint8)
     lib().oracle_synth_corpus(C.byref(p), _ptr(buf, _u8p), need)

@@ -955,12 +955,13 @@ size_t oracle_synth_corpus(const oracle_synth_params* p, uint8_t* out, size_t ca
     oracle_synth_cdf(p->vocab, cdf);
     size_t  n = 0;
     uint8_t buf[8];
-    for (uint64_t i = 0; i < p->ntokens; ++i) {
+    for (uint64_t k = 0; k < p->ntokens; ++k) {
+        uint64_t i = p->first_token + k; /* index in the global stream */
         unsigned l = oracle_inttobytes(buf, (uint32_t)oracle_synth_token(p, cdf, i));
         if (out && n + l <= cap)
             memcpy(out + n, buf, l);
         n += l;
-        if (synth_break_after(p, i) || i + 1 == p->ntokens) {
+        if (synth_break_after(p, i) || k + 1 == p->ntokens) {
             if (out && n < cap)
                 out[n] = 0;
             ++n;

@@ -96,6 +96,7 @@ typedef struct oracle_synth_params {
     uint32_t mean_sentence; /* a sentence ends after token i iff mix(seed^K, i) % mean_sentence == 0 */
     uint32_t phrase_permille; /* 0..1000: probability (per mille) that a position starts an injected phrase */
     uint32_t nphrases;      /* number of distinct fixed phrases (each 3..6 tokens) */
+    uint64_t first_token;   /* index of the first token in the global stream (multi-GPU shards); 0 for a whole corpus */
 } oracle_synth_params;
 uint64_t    oracle_synth_token(const oracle_synth_params* p, const uint64_t* cdf, uint64_t i); /* class id of token i */
 size_t      oracle_synth_corpus(const oracle_synth_params* p, uint8_t* out, size_t cap);

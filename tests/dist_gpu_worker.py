@@ -1,0 +1,52 @@
+"""Worker for tests/test_multigpu_gpu.py (launched by torch.distributed.run): every rank trains its shard through the
+CUDA shard phases + NCCL; rank 0 gathers the shares and compares with the oracle on the concatenated corpus."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import colibri_core_b200 as cb  # noqa: E402
+import colibri_core_b200.multigpu as mg  # noqa: E402
+
+
+def main():
+    per, vocab, seed, maxlength, mintokens = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    kw = dict(vocab=vocab, seed=seed, mean_sentence=15, phrase_permille=150, nphrases=500)
+    corpus = cb.Corpus.synthetic(per, device=local, first_token=rank * per, **kw)
+    opts = cb.PatternModelOptions(MINTOKENS=mintokens, MAXLENGTH=maxlength, QUIET=1, device=local)
+    eng = mg.CudaShardEngine(corpus, opts, rank, world, local)
+    model, passes, head = mg.train_distributed(eng, dist, torch, mintokens, maxlength)
+    keys, off, counts, _ = model.export()
+    share = (keys.tobytes(), off.tolist(), counts.tolist())
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object((share, passes, head), gathered, dst=0)
+    ok = True
+    if rank == 0:
+        import oracle
+
+        merged = {}
+        for (kb, of, cn), p, h in gathered:
+            for i in range(len(cn)):
+                k = kb[of[i]:of[i + 1]]
+                assert k not in merged, "pattern exported twice"
+                merged[k] = cn[i]
+            assert p == passes and h == head
+        body = b"".join(oracle.synth_corpus(per, first_token=r * per, **kw).tobytes() for r in range(world))
+        want = oracle.train(body, mintokens=mintokens, maxlength=maxlength)
+        ok = merged == want.as_dict() and [tuple(p) for p in passes] == want.passes and (head["tokens"], head["types"], head["maxn"], head["minn"]) == (
+            want.tokens, want.types, want.maxn, want.minn)
+        print("DIST_RESULT", "OK" if ok else "MISMATCH", len(merged), len(want), passes, want.passes, flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,32 @@
+"""The multi-GPU phases on real GPUs through NCCL.  world_size 1 (all-to-all with itself) runs on any GPU box and exercises
+every shard kernel; world_size 2 needs two GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(world, per, vocab, seed, maxlength, mintokens, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "dist_gpu_worker.py"), str(per), str(vocab), str(seed), str(maxlength), str(mintokens)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DIST_RESULT OK" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("per,vocab,seed,maxlength,mintokens", [(300000, 20000, 4, 5, 2), (120000, 3000, 8, 6, 3)])
+def test_shard_phases_world1(per, vocab, seed, maxlength, mintokens):
+    _run(1, per, vocab, seed, maxlength, mintokens, 29711)
+
+
+def test_shard_phases_world2():
+    import colibri_core_b200 as cb
+
+    if cb.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run(2, 400000, 30000, 6, 5, 2, 29713)

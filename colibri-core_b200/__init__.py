@@ -99,6 +99,7 @@ def library():
     L.colibri_b200_shard_info.argtypes = [C.c_void_p, _u64p]
     L.colibri_b200_shard_device_ms.argtypes = [C.c_void_p]
     L.colibri_b200_shard_device_ms.restype = C.c_double
+    L.colibri_b200_shard_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.colibri_b200_shard_unigram_counts.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.colibri_b200_shard_unigram_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]
     L.colibri_b200_shard_level_count.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p]

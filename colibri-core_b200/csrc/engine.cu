@@ -258,7 +258,7 @@ struct Trainer {
     DevBuf<DeviceStats>        d_stats;
     DeviceStats                h_stats;
     std::vector<Segment>       segs;
-    uint64_t                   slots_init = 0, ngram_upserts = 0, skip_upserts = 0;
+    uint64_t                   slots_init = 0, ngram_upserts = 0, skip_upserts = 0, filtered_windows = 0;
 
     int zero_stats(bool keep_global = true) {
         // found/kept/kept_occ/cursor/valid_windows/probes are per-phase; totaltokens/maxclass/errflags live for the whole train
@@ -366,6 +366,7 @@ int Trainer::run() {
     std::vector<DevBuf<uint32_t>> ids(2);  // ids[k] = id array of level k (all kept when skipgrams need their parts, else ping-pong)
     DevBuf<NgramSlot>       table;
     DevBuf<uint32_t>        bitmap;  // survivor bit per table slot of the level just pruned
+    DevBuf<uint32_t>        filter;  // 2-bit occurrence filter of the level being counted
     DevBuf<SkipSlot>        sktable;
     DevBuf<const uint32_t*> d_idptrs;
     DevBuf<SkipMask>        d_masks;
@@ -378,30 +379,63 @@ int Trainer::run() {
         uint64_t bound = prev_occ;
         if (prev_kept < (1ull << 31)) bound = std::min(bound, prev_kept * prev_kept);
         if (bound == 0) break;  // nothing can be found
-        uint64_t cap = std::max<uint64_t>(64, bound + bound / 2 + 16);  // load factor <= 2/3
-        if (cap >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "level %d needs %llu table slots; slot ids are 32 bit", n, (unsigned long long)cap);
-        if (table.n < cap) TRY(table.alloc(dev, cap));
         if ((int)ids.size() <= n) ids.resize(n + 1);
         DevBuf<uint32_t>& prev = ids[n - 1];
         DevBuf<uint32_t>& cur  = ids[n];
         if (!cur.p) TRY(cur.alloc(dev, npos + 8));
         CUDA_TRY(cudaMemsetAsync(cur.p + npos, 0, 8 * sizeof(uint32_t), s));
 
-        int hp = timer.begin(COLIBRI_T_PRUNE);
-        CUDA_TRY(cudaMemsetAsync(table.p, 0, cap * sizeof(NgramSlot), s));
-        timer.end(hp);
-        slots_init += cap;
-        TRY(zero_stats());
-        int hc = timer.begin(COLIBRI_T_COUNT, n);
-        launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms);
-        timer.end(hc);
-        TRY(read_stats());
-        const uint64_t windows = h_stats.valid_windows;
-        ngram_upserts += windows;
+        // ---- occurrence filter (t >= 2, worth its two extra launches only on large levels)
+        const bool use_filter = t >= 2 && bound >= (1ull << 25) && !getenv("COLIBRI_B200_NO_FILTER");
+        uint64_t   nbuckets = 0, cap = 0;
+        if (use_filter) {
+            nbuckets = 1ull << 20;
+            while (nbuckets < 2 * bound && nbuckets < (1ull << 28)) nbuckets <<= 1;  // <= 64 MB of 2-bit counters: L2 resident
+            if (filter.n < nbuckets / 16) TRY(filter.alloc(dev, nbuckets / 16));
+            int hf = timer.begin(COLIBRI_T_COUNT, n);
+            CUDA_TRY(cudaMemsetAsync(filter.p, 0, nbuckets / 4, s));
+            TRY(zero_stats());
+            launches += launch_ngram_filter(s, prev.p, npos, filter.p, nbuckets, d_stats.p, sms);
+            timer.end(hf);
+            TRY(read_stats());
+            // keys that reach the table live in buckets hit at least twice; there are at most ~2 such keys per bucket
+            // when the filter is crowded with singletons, ~1 otherwise.  Overflow is detected and retried.
+            cap = std::max<uint64_t>(1024, 3 * h_stats.found + 1024);
+            cap = std::min(cap, std::max<uint64_t>(64, bound + bound / 2 + 16));
+        } else {
+            cap = std::max<uint64_t>(64, bound + bound / 2 + 16);  // load factor <= 2/3
+        }
+        uint64_t windows = 0, singles = 0;
+        for (int attempt = 0;; ++attempt) {
+            if (cap >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "level %d needs %llu table slots; slot ids are 32 bit", n, (unsigned long long)cap);
+            if (table.n < cap) TRY(table.alloc(dev, cap));
+            int hp0 = timer.begin(COLIBRI_T_PRUNE);
+            CUDA_TRY(cudaMemsetAsync(table.p, 0, cap * sizeof(NgramSlot), s));
+            timer.end(hp0);
+            slots_init += cap;
+            TRY(zero_stats());
+            int hc = timer.begin(COLIBRI_T_COUNT, n);
+            launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms, use_filter ? filter.p : nullptr, nbuckets);
+            timer.end(hc);
+            CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            if (h_stats.errflags & kErrTableFull) {  // the estimate was too small: clear the flag and go again with twice the slots
+                if (attempt >= 6) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow at level %d", n);
+                CUDA_TRY(cudaMemsetAsync(&d_stats.p->errflags, 0, sizeof(unsigned int), s));
+                cap *= 2;
+                continue;
+            }
+            windows = h_stats.valid_windows;
+            singles = h_stats.singletons;
+            break;
+        }
+        ngram_upserts += windows - singles;
+        filtered_windows += singles;
         m->levels[n].windows = windows;
         m->levels[n].cap     = cap;
+        m->levels[n].singles = singles;
 
-        hp = timer.begin(COLIBRI_T_PRUNE);
+        int hp = timer.begin(COLIBRI_T_PRUNE);
         Segment sg;
         sg.n = n;
         uint64_t sv_bound = windows / std::max<uint32_t>(t, 1) + 1;
@@ -411,7 +445,8 @@ int Trainer::run() {
         launches += launch_prune_ngrams(s, table.p, cap, t, sg.pos.p, sg.cnt.p, bitmap.p, d_stats.p, sms);
         timer.end(hp);
         TRY(read_stats());
-        const uint64_t found = h_stats.found, kept = h_stats.kept, occ = h_stats.kept_occ;
+        // a window the filter held back is a distinct n-gram with exactly one occurrence: found, and pruned (t >= 2)
+        const uint64_t found = h_stats.found + singles, kept = h_stats.kept, occ = h_stats.kept_occ;
         sg.count = kept;
 
         // ---- exhaustive skipgrams of this level (:1163-1171)

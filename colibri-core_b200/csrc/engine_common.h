@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -190,7 +191,7 @@ struct colibri_b200_corpus {
 
 
 struct PassStat { uint64_t n, found, foundskip, pruned; };
-struct LevelInfo { uint64_t windows = 0, cap = 0; double ms = 0; };
+struct LevelInfo { uint64_t windows = 0, cap = 0, singles = 0; double ms = 0; };
 struct colibri_b200_model {
     int      device = 0;
     int      model_type = COLIBRI_UNINDEXEDPATTERNMODEL;

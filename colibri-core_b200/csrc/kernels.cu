@@ -251,9 +251,11 @@ __device__ __forceinline__ void cas128(void* addr, unsigned long long new0, unsi
         : "memory");
 }
 
-__device__ __forceinline__ uint32_t upsert_ngram(NgramSlot* __restrict__ table, uint64_t cap, unsigned long long key, uint32_t pos, uint32_t& probes, bool& full) {
-    uint64_t slot = fast_range(spooky_hash64_u64(key, 0), cap);
-    for (uint64_t step = 0; step < cap; ++step) {
+constexpr uint64_t kMaxProbe = 8192;  // a probe run this long means the table was sized too small: report, the host retries bigger
+
+__device__ __forceinline__ uint32_t upsert_ngram_at(NgramSlot* __restrict__ table, uint64_t cap, uint64_t slot, unsigned long long key, uint32_t pos, uint32_t& probes, bool& full) {
+    const uint64_t limit = cap < kMaxProbe ? cap : kMaxProbe;
+    for (uint64_t step = 0; step < limit; ++step) {
         NgramSlot*         s   = table + slot;
         unsigned long long cur = __ldcg(&s->key);  // keys never change once set, so a stale "empty" is the only possible staleness
         ++probes;
@@ -273,12 +275,62 @@ __device__ __forceinline__ uint32_t upsert_ngram(NgramSlot* __restrict__ table, 
     full = true;
     return 0;
 }
+__device__ __forceinline__ uint32_t upsert_ngram(NgramSlot* __restrict__ table, uint64_t cap, unsigned long long key, uint32_t pos, uint32_t& probes, bool& full) {
+    return upsert_ngram_at(table, cap, fast_range(spooky_hash64_u64(key, 0), cap), key, pos, probes, full);
+}
 
-__global__ void __launch_bounds__(256) count_ngrams_kernel(const uint32_t* __restrict__ prev, uint32_t* __restrict__ cur, uint64_t npos, NgramSlot* __restrict__ table,
-                                                           uint64_t cap, DeviceStats* __restrict__ st) {
+// ---- the occurrence filter (MINTOKENS >= 2 only).  Most distinct n-grams of a corpus occur once and are pruned right
+// after the pass (86 % of the bigrams of a Zipf corpus).  A first streaming pass counts every valid window into a
+// 2-bit saturating counter per hash bucket (bit 0: seen, bit 1: seen twice); the array is small enough to live in L2.
+// The counting pass then sends a window to the HBM table only if its bucket was hit at least twice.  A window whose
+// bucket was hit once is the ONLY window of its key, so it is a distinct n-gram with count 1: it is counted as "found"
+// and as "pruned" without ever touching the table.  Keys that reach the table are counted exactly as before, so the
+// surviving patterns, their counts and the found/pruned statistics are unchanged.
+__device__ __forceinline__ void filter_locate(uint64_t h, uint64_t nbuckets_mask, uint64_t& word, uint32_t& shift) {
+    uint64_t bucket = h & nbuckets_mask;  // low hash bits; the table slot uses the high bits (fast_range)
+    word            = bucket >> 4;
+    shift           = (uint32_t)(bucket & 15) * 2;
+}
+
+__global__ void __launch_bounds__(256) ngram_filter_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t* __restrict__ filter, uint64_t nbuckets_mask,
+                                                           DeviceStats* __restrict__ st) {
     __shared__ uint64_t scratch[8];
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint32_t       valid = 0, probes = 0;
+    uint32_t       valid = 0, twice = 0;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += stride) {
+        uint32_t a = __ldcs(prev + p);
+        uint32_t b = __ldg(prev + p + 1);
+        if (a == 0 || b == 0) continue;
+        ++valid;
+        uint64_t word;
+        uint32_t shift;
+        filter_locate(spooky_hash64_u64(((unsigned long long)a << 32) | b, 0), nbuckets_mask, word, shift);
+        uint32_t bits = (__ldcg(filter + word) >> shift) & 3u;
+        if (bits == 3u) continue;  // already saturated: hot keys stop here with a plain L2 read
+        if ((bits & 1u) == 0) {
+            uint32_t old = atomicOr(filter + word, 1u << shift);
+            if (((old >> shift) & 1u) == 0) continue;  // first hit of this bucket
+            bits = (old >> shift) & 3u;
+        }
+        if ((bits & 2u) == 0) {
+            uint32_t old = atomicOr(filter + word, 2u << shift);
+            twice += ((old >> shift) & 2u) == 0;  // this thread moved the bucket to "seen twice"
+        }
+    }
+    uint64_t v  = block_reduce_sum(valid, scratch);
+    uint64_t tw = block_reduce_sum(twice, scratch);
+    if (threadIdx.x == 0) {
+        if (v) atomicAdd(&st->valid_windows, (unsigned long long)v);
+        if (tw) atomicAdd(&st->found, (unsigned long long)tw);  // buckets hit at least twice
+    }
+}
+
+template <bool kFilter>
+__global__ void __launch_bounds__(256) count_ngrams_kernel(const uint32_t* __restrict__ prev, uint32_t* __restrict__ cur, uint64_t npos, NgramSlot* __restrict__ table,
+                                                           uint64_t cap, const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t       valid = 0, probes = 0, singles = 0;
     bool           full = false;
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += stride) {
         uint32_t a  = __ldcs(prev + p);
@@ -286,15 +338,27 @@ __global__ void __launch_bounds__(256) count_ngrams_kernel(const uint32_t* __res
         uint32_t id = 0;
         if (a != 0 && b != 0) {
             ++valid;
-            id = upsert_ngram(table, cap, ((unsigned long long)a << 32) | b, (uint32_t)p, probes, full);
+            const unsigned long long key = ((unsigned long long)a << 32) | b;
+            const uint64_t           h   = spooky_hash64_u64(key, 0);
+            bool                     go  = true;
+            if (kFilter) {
+                uint64_t word;
+                uint32_t shift;
+                filter_locate(h, nbuckets_mask, word, shift);
+                go = ((__ldg(filter + word) >> shift) & 2u) != 0;
+                singles += !go;
+            }
+            if (go) id = upsert_ngram_at(table, cap, fast_range(h, cap), key, (uint32_t)p, probes, full);
         }
         __stcs(cur + p, id);
     }
     uint64_t v  = block_reduce_sum(valid, scratch);
     uint64_t pr = block_reduce_sum(probes, scratch);
+    uint64_t sg = block_reduce_sum(singles, scratch);
     if (threadIdx.x == 0) {
         if (v) atomicAdd(&st->valid_windows, (unsigned long long)v);
         if (pr) atomicAdd(&st->probes, (unsigned long long)pr);
+        if (sg) atomicAdd(&st->singletons, (unsigned long long)sg);
     }
     if (full) atomicOr(&st->errflags, kErrTableFull);
 }
@@ -420,11 +484,24 @@ static int blocks_per_sm(const void* fn, int threads, size_t smem) {
     return n > 0 ? n : 1;
 }
 
-int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms) {
-    static int bps = blocks_per_sm((const void*)count_ngrams_kernel, 256, 0);
+int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms) {
+    static int bps = blocks_per_sm((const void*)ngram_filter_kernel, 256, 0);
+    unsigned   grid = (unsigned)umin64(div_up(npos, 256), (uint64_t)sms * bps * 4);
+    ngram_filter_kernel<<<grid ? grid : 1, 256, 0, s>>>(prev, npos, filter, nbuckets - 1, st);
+    return 1;
+}
+int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms, const uint32_t* filter,
+                        uint64_t nbuckets) {
+    static int bps0 = blocks_per_sm((const void*)count_ngrams_kernel<false>, 256, 0);
+    static int bps1 = blocks_per_sm((const void*)count_ngrams_kernel<true>, 256, 0);
     uint64_t   want = div_up(npos, 256);
-    unsigned   grid = (unsigned)umin64(want, (uint64_t)sms * bps * 4);
-    count_ngrams_kernel<<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, st);
+    if (filter != nullptr) {
+        unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bps1 * 4);
+        count_ngrams_kernel<true><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, filter, nbuckets - 1, st);
+    } else {
+        unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bps0 * 4);
+        count_ngrams_kernel<false><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, nullptr, 0, st);
+    }
     return 1;
 }
 int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap, DeviceStats* st, int sms) {
@@ -690,25 +767,43 @@ __global__ void __launch_bounds__(256) shard_dest_count_kernel(const NgramSlot* 
     if (threadIdx.x < world && hist[threadIdx.x]) atomicAdd(&dest_counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
 
-// records grouped by destination: send[dest_base[d] + k]; send_slot remembers which local slot each record came from
+// records grouped by destination: send[dest_base[d] + k]; send_slot remembers which local slot each record came from.
+// A block handles tiles of 2048 slots and reserves its output ranges with ONE atomicAdd per destination per tile
+// (per-warp cursor atomics on G addresses serialise: 7.9 ms for a 150 M-slot table in the first version).
 __global__ void __launch_bounds__(256) shard_pack_kernel(const NgramSlot* __restrict__ table, uint64_t cap, uint32_t world, const unsigned long long* __restrict__ dest_base,
                                                          unsigned long long* __restrict__ cursors, uint4* __restrict__ send, uint32_t* __restrict__ send_slot) {
-    const uint64_t rounded = (cap + 31) / 32 * 32;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint4 raw = make_uint4(0, 0, 0, 0);
-        if (i < cap) raw = __ldcs(reinterpret_cast<const uint4*>(table) + i);
-        bool     used = (raw.x | raw.y) != 0;
-        uint32_t dest = used ? owner_of(((unsigned long long)raw.y << 32) | raw.x, world) : 0xFFFFFFFFu;
-        // lanes with the same destination share one cursor atomic
-        uint32_t peers  = __match_any_sync(0xffffffffu, dest);
-        if (!used) continue;
-        int      leader = __ffs(peers) - 1;
-        uint64_t base   = 0;
-        if ((int)lane_id() == leader) base = atomicAdd(&cursors[dest], (unsigned long long)__popc(peers));
-        base         = __shfl_sync(peers, base, leader);
-        uint64_t idx = dest_base[dest] + base + __popc(peers & ((1u << lane_id()) - 1));
-        send[idx]      = make_uint4(raw.x, raw.y, raw.z, (uint32_t)i);
-        send_slot[idx] = (uint32_t)i;
+    __shared__ uint32_t tile_cnt[64];             // per destination: records of this tile, then running offset
+    __shared__ unsigned long long tile_base[64];  // per destination: reserved start in the send buffer
+    const uint64_t ntiles = (cap + kPruneTile - 1) / kPruneTile;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x < 64) tile_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint4    raw[8];
+        uint32_t dest[8], rank_in_tile[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint64_t i = tile * kPruneTile + (uint64_t)k * 256 + threadIdx.x;
+            raw[k]     = make_uint4(0, 0, 0, 0);
+            if (i < cap) raw[k] = __ldcs(reinterpret_cast<const uint4*>(table) + i);
+            bool used = (raw[k].x | raw[k].y) != 0;
+            dest[k]   = used ? owner_of(((unsigned long long)raw[k].y << 32) | raw[k].x, world) : 0xFFFFFFFFu;
+            if (used) rank_in_tile[k] = atomicAdd(&tile_cnt[dest[k]], 1u);  // shared-memory atomic: order inside a tile is free
+        }
+        __syncthreads();
+        if (threadIdx.x < world) {
+            uint32_t c = tile_cnt[threadIdx.x];
+            tile_base[threadIdx.x] = c ? dest_base[threadIdx.x] + atomicAdd(&cursors[threadIdx.x], (unsigned long long)c) : 0ull;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (dest[k] == 0xFFFFFFFFu) continue;
+            uint64_t i   = tile * kPruneTile + (uint64_t)k * 256 + threadIdx.x;
+            uint64_t idx = tile_base[dest[k]] + rank_in_tile[k];
+            send[idx]      = make_uint4(raw[k].x, raw[k].y, raw[k].z, (uint32_t)i);
+            send_slot[idx] = (uint32_t)i;
+        }
+        __syncthreads();
     }
 }
 
@@ -802,7 +897,7 @@ int launch_shard_dest_count(cudaStream_t s, const NgramSlot* table, uint64_t cap
 }
 int launch_shard_pack(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t world, const unsigned long long* dest_base, unsigned long long* cursors, void* send,
                       uint32_t* send_slot, int sms) {
-    unsigned grid = (unsigned)umin64(div_up(cap, 256), (uint64_t)sms * 8);
+    unsigned grid = (unsigned)umin64(div_up(cap, kPruneTile), (uint64_t)sms * 4);
     shard_pack_kernel<<<grid ? grid : 1, 256, 0, s>>>(table, cap, world, dest_base, cursors, (uint4*)send, send_slot);
     return 1;
 }

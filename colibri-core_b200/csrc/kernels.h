@@ -34,6 +34,7 @@ struct DeviceStats {
     unsigned long long cursor;         // compaction cursor into the survivor arrays
     unsigned long long valid_windows;  // upserts issued by the last count kernel
     unsigned long long probes;         // probe steps of the last count kernel (diagnostic)
+    unsigned long long singletons;     // windows the occurrence filter proved to be the only one of their n-gram
     unsigned int       maxclass;
     unsigned int       errflags;       // kErr* bits
 };
@@ -67,7 +68,11 @@ int launch_unigram_prune(cudaStream_t s, const uint32_t* count1, uint32_t nclass
 int launch_make_id1(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* count1, uint32_t threshold, uint32_t* id1);
 
 // ---- K2: n-gram upsert (the dominant kernel), K3: prune/compact, relabel
-int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms);
+// occurrence filter: nbuckets (power of two) 2-bit saturating counters, nbuckets/4 bytes, zeroed by the caller; st->found := buckets hit twice
+int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms);
+// filter == NULL: every valid window goes to the table
+int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms,
+                        const uint32_t* filter = nullptr, uint64_t nbuckets = 0);
 // bitmap: (cap+31)/32 words, bit = slot survived (may be NULL)
 int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap, DeviceStats* st, int sms);
 int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap);

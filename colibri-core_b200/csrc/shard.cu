@@ -39,6 +39,7 @@ struct colibri_b200_shard {
     uint64_t             global_tokens = 0, global_types = 0;
     cudaEvent_t          ev0 = nullptr, ev1 = nullptr;
     double               device_ms = 0;
+    double               phase_ms[8] = {0};  // begin, unigrams, count, pack, merge, finish, export
 };
 
 static int zero_phase_stats(colibri_b200_shard* sh) {
@@ -51,14 +52,18 @@ static int read_stats(colibri_b200_shard* sh) {
     if (sh->h_stats.errflags & kErrTableFull) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow");
     return 0;
 }
-struct PhaseClock {  // accumulates device time of one ABI call into shard->device_ms
+struct PhaseClock {  // accumulates device time of one ABI call into shard->device_ms / phase_ms[phase]
     colibri_b200_shard* sh;
-    explicit PhaseClock(colibri_b200_shard* s) : sh(s) { cudaEventRecord(sh->ev0, sh->s); }
+    int                 phase;
+    explicit PhaseClock(colibri_b200_shard* s, int ph) : sh(s), phase(ph) { cudaEventRecord(sh->ev0, sh->s); }
     ~PhaseClock() {
         cudaEventRecord(sh->ev1, sh->s);
         cudaEventSynchronize(sh->ev1);
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, sh->ev0, sh->ev1) == cudaSuccess) sh->device_ms += ms;
+        if (cudaEventElapsedTime(&ms, sh->ev0, sh->ev1) == cudaSuccess) {
+            sh->device_ms += ms;
+            sh->phase_ms[phase] += ms;
+        }
     }
 };
 
@@ -97,7 +102,7 @@ extern "C" int colibri_b200_shard_begin(colibri_b200_corpus* corpus, const colib
         CUDA_TRY(cudaStreamCreateWithFlags(&sh->s, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreate(&sh->ev0));
         CUDA_TRY(cudaEventCreate(&sh->ev1));
-        PhaseClock clk(sh);
+        PhaseClock clk(sh, 0);
         cudaStream_t s = sh->s;
         // sentence-source quirk exactly as in the single-GPU driver (a shard is a whole file of its own here)
         size_t staged = corpus->nbytes;
@@ -151,13 +156,18 @@ extern "C" int colibri_b200_shard_info(const colibri_b200_shard* sh, uint64_t ou
 extern "C" double colibri_b200_shard_device_ms(const colibri_b200_shard* sh) {
     return sh ? sh->device_ms : 0.0;
 }
+extern "C" int colibri_b200_shard_phase_ms(const colibri_b200_shard* sh, double out[8]) {
+    if (!sh || !out) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    memcpy(out, sh->phase_ms, sizeof sh->phase_ms);
+    return 0;
+}
 
 // local class histogram into the caller's device buffer (u32[nclasses], zeroed here); the caller all-reduces it
 extern "C" int colibri_b200_shard_unigram_counts(colibri_b200_shard* sh, uint32_t nclasses, void* dev_counts) {
     if (!sh || !dev_counts) return set_err(COLIBRI_E_INVALID, "NULL argument");
     if (nclasses <= sh->local_maxclass) return set_err(COLIBRI_E_INVALID, "nclasses %u <= local maximum class %u", nclasses, sh->local_maxclass);
     CUDA_TRY(cudaSetDevice(sh->dev));
-    PhaseClock clk(sh);
+    PhaseClock clk(sh, 1);
     sh->nclasses = nclasses;
     CUDA_TRY(cudaMemsetAsync(dev_counts, 0, (size_t)nclasses * 4, sh->s));
     sh->launches += launch_unigram_hist(sh->s, sh->tok.p, sh->npos, (uint32_t*)dev_counts, nclasses, sh->sms);
@@ -169,7 +179,7 @@ extern "C" int colibri_b200_shard_unigram_counts(colibri_b200_shard* sh, uint32_
 extern "C" int colibri_b200_shard_unigram_finish(colibri_b200_shard* sh, const void* dev_global_counts, uint64_t global_tokens, uint64_t stats[3]) {
     if (!sh || !dev_global_counts || !stats) return set_err(COLIBRI_E_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(sh->dev));
-    PhaseClock clk(sh);
+    PhaseClock clk(sh, 1);
     cudaStream_t s = sh->s;
     TRY(sh->count1.alloc(sh->dev, sh->nclasses));
     CUDA_TRY(cudaMemcpyAsync(sh->count1.p, dev_global_counts, (size_t)sh->nclasses * 4, cudaMemcpyDeviceToDevice, s));
@@ -203,7 +213,7 @@ extern "C" int colibri_b200_shard_level_count(colibri_b200_shard* sh, int n, uin
     if (!sh || !dest_counts || !stats) return set_err(COLIBRI_E_INVALID, "NULL argument");
     if (n != sh->level + 1) return set_err(COLIBRI_E_INVALID, "level %d requested after level %d", n, sh->level);
     CUDA_TRY(cudaSetDevice(sh->dev));
-    PhaseClock clk(sh);
+    PhaseClock clk(sh, 2);
     cudaStream_t s = sh->s;
     uint64_t bound = std::max<uint64_t>(sh->prev_valid, 1);
     uint64_t cap   = std::max<uint64_t>(64, bound + bound / 2 + 16);
@@ -238,7 +248,7 @@ extern "C" int colibri_b200_shard_level_count(colibri_b200_shard* sh, int n, uin
 extern "C" int colibri_b200_shard_level_pack(colibri_b200_shard* sh, void* dev_send) {
     if (!sh || (!dev_send && sh->nsent)) return set_err(COLIBRI_E_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(sh->dev));
-    PhaseClock clk(sh);
+    PhaseClock clk(sh, 3);
     TRY(sh->send_slot.alloc(sh->dev, sh->nsent + 1));
     if (sh->nsent) sh->launches += launch_shard_pack(sh->s, sh->table.p, sh->local_cap, sh->world, sh->d_dest.p + 64, sh->d_dest.p + 128, dev_send, sh->send_slot.p, sh->sms);
     CUDA_TRY(cudaStreamSynchronize(sh->s));
@@ -249,7 +259,7 @@ extern "C" int colibri_b200_shard_level_pack(colibri_b200_shard* sh, void* dev_s
 extern "C" int colibri_b200_shard_level_merge(colibri_b200_shard* sh, const void* dev_recv, uint64_t nrecv, void* dev_reply, uint64_t stats[3]) {
     if (!sh || !stats || (nrecv && (!dev_recv || !dev_reply))) return set_err(COLIBRI_E_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(sh->dev));
-    PhaseClock clk(sh);
+    PhaseClock clk(sh, 4);
     cudaStream_t s = sh->s;
     uint64_t cap = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);
     if (cap * sh->world >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner table of %llu slots x %u ranks exceeds the 32-bit id space", (unsigned long long)cap, sh->world);
@@ -273,7 +283,7 @@ extern "C" int colibri_b200_shard_level_merge(colibri_b200_shard* sh, const void
 extern "C" int colibri_b200_shard_level_finish(colibri_b200_shard* sh, const void* dev_reply_back, uint64_t* local_valid) {
     if (!sh || (sh->nsent && !dev_reply_back)) return set_err(COLIBRI_E_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(sh->dev));
-    PhaseClock clk(sh);
+    PhaseClock clk(sh, 5);
     cudaStream_t s = sh->s;
     const int n = sh->level + 1;
     if (sh->gid_of_slot.n < sh->local_cap) TRY(sh->gid_of_slot.alloc(sh->dev, sh->local_cap));
@@ -314,7 +324,7 @@ extern "C" int colibri_b200_shard_finish(colibri_b200_shard* sh, const uint64_t*
     for (int p = 0; p < npasses; ++p) m->passes.push_back({passes[4 * p], passes[4 * p + 1], passes[4 * p + 2], passes[4 * p + 3]});
     int rc;
     {
-        PhaseClock clk(sh);
+        PhaseClock clk(sh, 6);
         rc = export_segments(sh->dev, sh->s, sh->segs, sh->tok.p, m, sh->launches);
         cudaStreamSynchronize(sh->s);
     }

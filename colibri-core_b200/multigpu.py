@@ -44,6 +44,11 @@ class CudaShardEngine:
     def device_ms(self):
         return float(self.lib.colibri_b200_shard_device_ms(self._h))
 
+    def phase_ms(self):
+        out = (C.c_double * 8)()
+        self._check(self.lib.colibri_b200_shard_phase_ms(self._h, out))
+        return dict(zip(["tokenise", "unigrams", "count", "pack", "merge", "finish", "export"], [float(x) for x in out]))
+
     def unigram_counts(self, nclasses):
         buf = self.new_buffer(nclasses)
         self._check(self.lib.colibri_b200_shard_unigram_counts(self._h, nclasses, buf.data_ptr()))
@@ -180,7 +185,7 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
     def step():
         eng = CudaShardEngine(corpus, opts, rank, world, local)
         model, passes, head = train_distributed(eng, dist, torch, a.mintokens, a.maxlength)
-        out = (len(model), head, passes, eng.device_ms(), eng.info()["launches"])
+        out = (len(model), head, passes, eng.device_ms(), eng.info()["launches"], eng.phase_ms())
         model.close()
         eng.close()
         return out
@@ -206,6 +211,38 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
     dist.all_reduce(t, op=dist.ReduceOp.MAX)  # the slowest rank defines the step
     npat = torch.tensor([last[0], launches], dtype=torch.int64, device="cuda")
     dist.all_reduce(npat, op=dist.ReduceOp.SUM)
+    # ---- end to end: pinned host shard -> H2D -> distributed train -> this rank's share of the model -> D2H (pinned)
+    host = torch.empty(corpus.nbytes, dtype=torch.uint8, pin_memory=True)
+    host.numpy()[:] = corpus.download()
+    cap_pat = int(last[0] * 1.3) + 1024
+    out_keys = torch.empty(cap_pat * 16, dtype=torch.uint8, pin_memory=True)
+    out_off = torch.empty(cap_pat + 1, dtype=torch.int64, pin_memory=True)
+    out_cnt = torch.empty(cap_pat, dtype=torch.int32, pin_memory=True)
+
+    def e2e_step():
+        c = cb.Corpus.from_host_pointer(host.data_ptr(), host.numel(), device=local)
+        eng = CudaShardEngine(c, opts, rank, world, local)
+        model, _, _ = train_distributed(eng, dist, torch, a.mintokens, a.maxlength)
+        n, kb, _ = model.export_sizes()
+        if n > cap_pat or kb > out_keys.numel():
+            raise RuntimeError("e2e export buffers too small")
+        model.export_into(out_keys.data_ptr(), out_off.data_ptr(), out_cnt.data_ptr())
+        model.close()
+        eng.close()
+        c.close()
+        return kb + 8 * (n + 1) + 4 * n
+
+    e2e_step()
+    barrier()
+    t1 = time.perf_counter()
+    d2h = 0
+    for _ in range(a.steps):
+        d2h = e2e_step()
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    xfer = torch.tensor([corpus.nbytes, d2h], dtype=torch.int64, device="cuda")
+    dist.all_reduce(xfer, op=dist.ReduceOp.SUM)
     if rank == 0:
         clocks = sampler.stop()
         elapsed = float(t[0].item())
@@ -217,12 +254,13 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
             "config": {"workload": workload + " PER GPU (shards of one global stream)", "global_tokens": tokens, "patterns": int(npat[0].item()),
                        "parallelism": "corpus sharded by sentence x%d, model hash-partitioned, NCCL all-to-all of (key,count) records per level" % world,
                        "l2": "inputs exceed L2", "timing": "max over ranks of max(CUDA events, wall clock) around K steps"},
-            "device_ms_per_step_max_rank": 1e3 * float(t[1].item()) / a.steps, "passes": last[2],
+            "device_ms_per_step_max_rank": 1e3 * float(t[1].item()) / a.steps, "passes": last[2], "rank0_phase_ms_last_step": last[5],
             "roofline": {"bound": "hbm", "kernel": "count_ngrams_kernel", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "peak_source": peak_src, "traffic": None,
                          "note": "per-kernel roofline is reported by the 1-GPU run; the N-GPU line reports whole-job throughput",
                          "hbm_read_roofline_frac": (a.maxlength * corpus.nbytes / (elapsed / a.steps) / 1e9) / peak},
             "clocks": clocks, "gpu_launches": int(npat[1].item()),
-            "e2e": None,
+            "e2e": {"value": tokens * a.steps / float(e2e_t.item()), "unit": unit, "h2d_bytes_per_step": int(xfer[0].item()), "d2h_bytes_per_step": int(xfer[1].item()),
+                    "ms_per_step": 1e3 * float(e2e_t.item()) / a.steps, "api": "per rank: colibri_b200_corpus_stage(pinned host shard) + shard phases + NCCL + colibri_b200_model_export (pinned)"},
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

@@ -141,6 +141,8 @@ int    colibri_b200_shard_begin(colibri_b200_corpus* corpus, const colibri_b200_
 /* out[0]=local tokens, out[1]=local maximum class, out[2]=positions, out[3]=kernel launches so far */
 int    colibri_b200_shard_info(const colibri_b200_shard* sh, uint64_t out[4]);
 double colibri_b200_shard_device_ms(const colibri_b200_shard* sh);
+/* device ms by phase: [0] tokenise, [1] unigrams, [2] level_count, [3] level_pack, [4] level_merge, [5] level_finish, [6] export */
+int    colibri_b200_shard_phase_ms(const colibri_b200_shard* sh, double out[8]);
 int    colibri_b200_shard_unigram_counts(colibri_b200_shard* sh, uint32_t nclasses, void* dev_counts /* u32[nclasses] */);
 /* stats[0]=distinct unigrams (global), [1]=kept, [2]=occurrences kept */
 int    colibri_b200_shard_unigram_finish(colibri_b200_shard* sh, const void* dev_global_counts, uint64_t global_tokens, uint64_t stats[3]);

@@ -27,7 +27,11 @@ $(LIBDIR)/shard.o: $(CSRC)/shard.cu $(CSRC)/kernels.h $(CSRC)/engine_common.h in
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/shard.ptxas.log || (cat $(LIBDIR)/shard.ptxas.log; false)
 
-$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o
+$(LIBDIR)/index.o: $(CSRC)/index.cu $(CSRC)/kernels.h $(CSRC)/device_utils.cuh
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/index.ptxas.log || (cat $(LIBDIR)/index.ptxas.log; false)
+
+$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o $(LIBDIR)/index.o
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^
 
 oracle:

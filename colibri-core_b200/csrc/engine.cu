@@ -231,7 +231,8 @@ int colibri::check_options(colibri_b200_options& o) {
         return set_err(COLIBRI_E_INVALID, "Both DOSKIPGRAMS as well as DOSKIPGRAMS_EXHAUSTIVE are set, this shouldn't happen, choose one.");  // :958-963
     if (o.model_type != COLIBRI_UNINDEXEDPATTERNMODEL && o.model_type != COLIBRI_INDEXEDPATTERNMODEL)
         return set_err(COLIBRI_E_UNSUPPORTED, "model type %d (only 10 = unindexed and 20 = indexed run on the device)", o.model_type);
-    if (o.model_type == COLIBRI_INDEXEDPATTERNMODEL) return set_err(COLIBRI_E_UNSUPPORTED, "indexed models are not on the device path yet");
+    if (o.model_type == COLIBRI_INDEXEDPATTERNMODEL && o.DOSKIPGRAMS_EXHAUSTIVE)
+        return set_err(COLIBRI_E_UNSUPPORTED, "exhaustive skipgrams on an indexed model are not on the device path yet");
     if (o.DOSKIPGRAMS) return set_err(COLIBRI_E_UNSUPPORTED, "non-exhaustive skipgrams (IndexedPatternModel::trainskipgrams) are not on the device path yet");
     if (o.DOPATTERNPERLINE) return set_err(COLIBRI_E_UNSUPPORTED, "DOPATTERNPERLINE is not on the device path");
     if (o.PRUNENONSUBSUMED || o.PRUNESUBSUMED) return set_err(COLIBRI_E_UNSUPPORTED, "PRUNE(NON)SUBSUMED is not on the device path");
@@ -272,8 +273,72 @@ struct Trainer {
         if (h_stats.errflags & kErrTableFull) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow");
         return 0;
     }
+    // forward index (indexed models)
+    bool               indexed = false;
+    DevBuf<uint64_t>   sent_before;  // delimiters in tok[0..p)
+    DevBuf<uint32_t>   sent_start;   // first position of sentence k (0-based)
+    int prepare_index(const uint32_t* tok, uint64_t npos);
+    int build_refs(Segment& sg, const uint32_t* ids, const uint32_t* map, bool by_class, uint64_t npos, uint64_t expect);
     int run();
 };
+
+int Trainer::prepare_index(const uint32_t* tok, uint64_t npos) {
+    DevBuf<uint32_t> flags;
+    DevBuf<uint64_t> tmp;
+    TRY(flags.alloc(dev, npos));
+    TRY(tmp.alloc(dev, npos / 2048 + 4));
+    TRY(sent_before.alloc(dev, npos + 1));
+    const uint64_t ndelims = npos - m->totaltokens;
+    TRY(sent_start.alloc(dev, ndelims + 2));
+    launches += launch_delim_flags(s, tok, npos, flags.p);
+    launches += launch_exclusive_scan_u32_u64(s, flags.p, sent_before.p, npos, tmp.p);
+    launches += launch_sent_start(s, tok, sent_before.p, npos, sent_start.p);
+    CUDA_TRY(cudaStreamSynchronize(s));  // the temporaries go back to the pool
+    return 0;
+}
+
+// occurrences of one level -> (sentence, token) lists grouped by survivor, ascending inside each (see index.cu)
+int Trainer::build_refs(Segment& sg, const uint32_t* ids, const uint32_t* map, bool by_class, uint64_t npos, uint64_t expect) {
+    if (sg.count == 0) return 0;
+    const uint64_t   nblk = (npos + 2047) / 2048;
+    DevBuf<uint32_t> blk;
+    DevBuf<uint64_t> blk_off, tmp;
+    TRY(blk.alloc(dev, nblk + 1));
+    TRY(blk_off.alloc(dev, nblk + 2));
+    TRY(tmp.alloc(dev, nblk / 2048 + 4));
+    launches += launch_pair_count(s, ids, map, npos, by_class, blk.p);
+    launches += launch_exclusive_scan_u32_u64(s, blk.p, blk_off.p, nblk, tmp.p);
+    uint64_t R = 0;
+    CUDA_TRY(cudaMemcpyAsync(&R, blk_off.p + nblk, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (R != expect) return set_err(COLIBRI_E_CUDA, "forward index of level %d: %llu occurrences found, %llu expected", sg.n, (unsigned long long)R, (unsigned long long)expect);
+    if (R >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "forward index of level %d has %llu entries", sg.n, (unsigned long long)R);
+    DevBuf<uint32_t> ka, va, kb, vb, hist;
+    DevBuf<uint64_t> hist_off, stmp;
+    const uint64_t   nsort = (R + 4095) / 4096;
+    TRY(ka.alloc(dev, R));
+    TRY(va.alloc(dev, R));
+    TRY(kb.alloc(dev, R));
+    TRY(vb.alloc(dev, R));
+    TRY(hist.alloc(dev, 256 * nsort));
+    TRY(hist_off.alloc(dev, 256 * nsort + 1));
+    TRY(stmp.alloc(dev, 256 * nsort / 2048 + 4));
+    launches += launch_pair_write(s, ids, map, npos, by_class, blk_off.p, ka.p, va.p);
+    uint32_t *kin = ka.p, *vin = va.p, *kout = kb.p, *vout = vb.p;
+    for (int shift = 0; shift < 32 && ((sg.count - 1) >> shift) != 0; shift += 8) {
+        launches += launch_radix_pass(s, kin, vin, R, shift, hist.p, hist_off.p, stmp.p, kout, vout);
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    TRY(sg.ref_sentence.alloc(dev, R));
+    TRY(sg.ref_token.alloc(dev, R));
+    launches += launch_refs_from_positions(s, vin, R, sent_before.p, sent_start.p, sg.ref_sentence.p, sg.ref_token.p, d_stats.p);
+    sg.nrefs = R;
+    TRY(read_stats());
+    if (h_stats.errflags & kErrLongSentence)
+        return set_err(COLIBRI_E_UNSUPPORTED, "indexed model: a sentence has more than 65536 tokens (IndexReference.token is 16 bit; the class encoder splits such lines)");
+    return 0;
+}
 
 int Trainer::run() {
     CUDA_TRY(cudaSetDevice(dev));
@@ -325,6 +390,12 @@ int Trainer::run() {
     m->counters[0] = npos_real;
     m->counters[1] = c->nbytes;
 
+    indexed = o.model_type == COLIBRI_INDEXEDPATTERNMODEL;
+    if (indexed) {
+        int hi = timer.begin(COLIBRI_T_INDEX);
+        TRY(prepare_index(tok.p, npos));
+        timer.end(hi);
+    }
     const uint32_t t  = (uint32_t)o.MINTOKENS;
     const uint32_t t1 = (uint32_t)std::max(o.MINTOKENS, o.MINTOKENS_UNIGRAMS);  // what higher orders require of their unigrams (:1094-1104)
     const uint32_t ts = o.MINSKIPTYPES > 1 ? (uint32_t)o.MINTOKENS_SKIPGRAMS : t;  // PatternModel::pruneskipgrams returns early when minskiptypes <= 1 (:2170-2171)
@@ -343,9 +414,16 @@ int Trainer::run() {
         uint64_t bound = std::min<uint64_t>(nclasses, m->totaltokens / std::max<uint32_t>(t, 1) + 1);
         TRY(sg.pos.alloc(dev, bound));
         TRY(sg.cnt.alloc(dev, bound));
-        launches += launch_unigram_prune(s, count1.p, nclasses, t, sg.pos.p, sg.cnt.p, 0, d_stats.p);
+        DevBuf<uint32_t> class_index;
+        if (indexed) TRY(class_index.alloc(dev, nclasses));
+        launches += launch_unigram_prune(s, count1.p, nclasses, t, sg.pos.p, sg.cnt.p, 0, d_stats.p, 1, 0, indexed ? class_index.p : nullptr);
         TRY(read_stats());
         sg.count = h_stats.kept;
+        if (indexed) {
+            int hi = timer.begin(COLIBRI_T_INDEX);
+            TRY(build_refs(sg, tok.p, class_index.p, true, npos, h_stats.kept_occ));
+            timer.end(hi);
+        }
         segs.push_back(std::move(sg));
     }
     timer.end(h);
@@ -367,6 +445,7 @@ int Trainer::run() {
     DevBuf<NgramSlot>       table;
     DevBuf<uint32_t>        bitmap;  // survivor bit per table slot of the level just pruned
     DevBuf<uint32_t>        filter;  // 2-bit occurrence filter of the level being counted
+    DevBuf<uint32_t>        slot_index;  // indexed models: table slot -> survivor index + 1
     DevBuf<SkipSlot>        sktable;
     DevBuf<const uint32_t*> d_idptrs;
     DevBuf<SkipMask>        d_masks;
@@ -442,12 +521,18 @@ int Trainer::run() {
         TRY(sg.pos.alloc(dev, sv_bound));
         TRY(sg.cnt.alloc(dev, sv_bound));
         if (bitmap.n < cap / 32 + 8) TRY(bitmap.alloc(dev, cap / 32 + 8));
-        launches += launch_prune_ngrams(s, table.p, cap, t, sg.pos.p, sg.cnt.p, bitmap.p, d_stats.p, sms);
+        if (indexed && slot_index.n < cap) TRY(slot_index.alloc(dev, cap));
+        launches += launch_prune_ngrams(s, table.p, cap, t, sg.pos.p, sg.cnt.p, bitmap.p, d_stats.p, sms, indexed ? slot_index.p : nullptr);
         timer.end(hp);
         TRY(read_stats());
         // a window the filter held back is a distinct n-gram with exactly one occurrence: found, and pruned (t >= 2)
         const uint64_t found = h_stats.found + singles, kept = h_stats.kept, occ = h_stats.kept_occ;
         sg.count = kept;
+        if (indexed && kept > 0) {  // IndexedPatternModel::add (:2789-2800) + posttrain sort (:2699-2705)
+            int hi = timer.begin(COLIBRI_T_INDEX);
+            TRY(build_refs(sg, cur.p, slot_index.p, false, npos, occ));
+            timer.end(hi);
+        }
 
         // ---- exhaustive skipgrams of this level (:1163-1171)
         uint64_t foundskip = 0, keptskip = 0;
@@ -624,6 +709,24 @@ int colibri::export_segments(int dev, cudaStream_t s, std::vector<Segment>& segs
     m->keybytes = kb;
     TRY(m->d_keys.alloc(dev, std::max<uint64_t>(kb, 1)));
     launches += launch_export_write(s, tok, pos.p, nm.p, m->d_off.p, total, m->d_keys.p);
+    if (m->model_type == COLIBRI_INDEXEDPATTERNMODEL) {
+        uint64_t nrefs = 0;
+        for (auto& sg : segs) nrefs += sg.nrefs;
+        m->nrefs = nrefs;
+        TRY(m->d_ref_sentence.alloc(dev, std::max<uint64_t>(nrefs, 1)));
+        TRY(m->d_ref_token.alloc(dev, std::max<uint64_t>(nrefs, 1)));
+        TRY(m->d_ref_off.alloc(dev, total + 1));
+        uint64_t rbase = 0;
+        for (auto& sg : segs) {
+            if (sg.nrefs) {
+                CUDA_TRY(cudaMemcpyAsync(m->d_ref_sentence.p + rbase, sg.ref_sentence.p, sg.nrefs * 4, cudaMemcpyDeviceToDevice, s));
+                CUDA_TRY(cudaMemcpyAsync(m->d_ref_token.p + rbase, sg.ref_token.p, sg.nrefs * 2, cudaMemcpyDeviceToDevice, s));
+            }
+            rbase += sg.nrefs;
+        }
+        // a pattern's occurrence list has exactly `count` entries, and lists follow the pattern order
+        launches += launch_exclusive_scan_u32_u64(s, m->d_counts.p, m->d_ref_off.p, total, tmp.p);
+    }
     CUDA_TRY(cudaStreamSynchronize(s));  // the temporaries above go back to the pool when this returns
     segs.clear();
     return 0;
@@ -686,12 +789,17 @@ extern "C" int colibri_b200_model_export_sizes(colibri_b200_model* m, uint64_t* 
     if (nrefs) *nrefs = m->nrefs;
     return 0;
 }
-extern "C" int colibri_b200_model_export(colibri_b200_model* m, uint8_t* keys, uint64_t* key_off, uint32_t* counts, uint32_t*, uint16_t*, uint64_t*) {
+extern "C" int colibri_b200_model_export(colibri_b200_model* m, uint8_t* keys, uint64_t* key_off, uint32_t* counts, uint32_t* ref_sentence, uint16_t* ref_token, uint64_t* ref_off) {
     if (!m || !key_off) return set_err(COLIBRI_E_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(m->device));
     if (m->keybytes && keys) CUDA_TRY(cudaMemcpyAsync(keys, m->d_keys.p, m->keybytes, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaMemcpyAsync(key_off, m->d_off.p, (m->npatterns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, m->stream));
     if (m->npatterns && counts) CUDA_TRY(cudaMemcpyAsync(counts, m->d_counts.p, m->npatterns * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+    if (m->model_type == COLIBRI_INDEXEDPATTERNMODEL && m->d_ref_off.p) {
+        if (ref_off) CUDA_TRY(cudaMemcpyAsync(ref_off, m->d_ref_off.p, (m->npatterns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, m->stream));
+        if (ref_sentence && m->nrefs) CUDA_TRY(cudaMemcpyAsync(ref_sentence, m->d_ref_sentence.p, m->nrefs * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
+        if (ref_token && m->nrefs) CUDA_TRY(cudaMemcpyAsync(ref_token, m->d_ref_token.p, m->nrefs * sizeof(uint16_t), cudaMemcpyDeviceToHost, m->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     return 0;
 }
@@ -700,14 +808,22 @@ static int ensure_host(colibri_b200_model* m) {
     m->h_keys.resize(m->keybytes + 1);
     m->h_off.resize(m->npatterns + 1);
     m->h_counts.resize(m->npatterns + 1);
-    TRY(colibri_b200_model_export(m, m->h_keys.data(), m->h_off.data(), m->h_counts.data(), nullptr, nullptr, nullptr));
+    const bool indexed = m->model_type == COLIBRI_INDEXEDPATTERNMODEL;
+    if (indexed) {
+        m->h_ref_sentence.resize(m->nrefs + 1);
+        m->h_ref_token.resize(m->nrefs + 1);
+        m->h_ref_off.resize(m->npatterns + 1);
+    }
+    TRY(colibri_b200_model_export(m, m->h_keys.data(), m->h_off.data(), m->h_counts.data(), indexed ? m->h_ref_sentence.data() : nullptr, indexed ? m->h_ref_token.data() : nullptr,
+                                  indexed ? m->h_ref_off.data() : nullptr));
     m->host_ready = true;
     return 0;
 }
 extern "C" int colibri_b200_model_write(colibri_b200_model* m, uint8_t* buf, size_t cap, size_t* nbytes) {
     // layout: include/patternmodel.h:1609-1624 + include/patternstore.h:534-542 + src/pattern.cpp:268-277 + include/datatypes.h:216-221
     if (!m || !nbytes) return set_err(COLIBRI_E_INVALID, "NULL argument");
-    size_t need = 3 + 24 + m->keybytes + m->npatterns * 5;
+    const bool indexed = m->model_type == COLIBRI_INDEXEDPATTERNMODEL;  // value = u32 count + count x (u32 sentence, u16 token), include/datatypes.h:263-270, :55-58
+    size_t need = 3 + 24 + m->keybytes + m->npatterns * 5 + (indexed ? m->nrefs * 6 : 0);
     *nbytes     = need;
     if (!buf) return 0;
     if (cap < need) return set_err(COLIBRI_E_INVALID, "buffer too small: need %zu bytes", need);
@@ -726,6 +842,13 @@ extern "C" int colibri_b200_model_write(colibri_b200_model* m, uint8_t* buf, siz
         buf[w++] = 0;
         memcpy(buf + w, &m->h_counts[i], 4);
         w += 4;
+        if (indexed) {
+            for (uint64_t j = m->h_ref_off[i]; j < m->h_ref_off[i + 1]; ++j) {
+                memcpy(buf + w, &m->h_ref_sentence[j], 4);
+                memcpy(buf + w + 4, &m->h_ref_token[j], 2);
+                w += 6;
+            }
+        }
     }
     return 0;
 }

@@ -166,6 +166,10 @@ struct Segment {  // survivors of one (level, category)
     bool             skip = false;
     uint64_t         count = 0;
     DevBuf<uint32_t> pos, cnt, mask;
+    // indexed models: the occurrences of the segment's patterns, grouped by pattern (segment order), ascending inside a pattern
+    uint64_t         nrefs = 0;
+    DevBuf<uint32_t> ref_sentence;
+    DevBuf<uint16_t> ref_token;
 };
 
 int check_options(colibri_b200_options& o);
@@ -203,12 +207,18 @@ struct colibri_b200_model {
     DevBuf<uint8_t>  d_keys;
     DevBuf<uint64_t> d_off;
     DevBuf<uint32_t> d_counts;
+    DevBuf<uint32_t> d_ref_sentence;  // indexed models only
+    DevBuf<uint16_t> d_ref_token;
+    DevBuf<uint64_t> d_ref_off;
     // host copies (filled on first export / lookup)
     bool                  host_ready = false;
     std::vector<uint8_t>  h_keys;
     std::vector<uint64_t> h_off;
     std::vector<uint32_t> h_counts;
     std::vector<uint32_t> h_sorted;  // lookup index
+    std::vector<uint32_t> h_ref_sentence;
+    std::vector<uint16_t> h_ref_token;
+    std::vector<uint64_t> h_ref_off;
     double   ms[COLIBRI_T_NPHASES] = {0};
     uint64_t counters[8] = {0};
     std::map<int, LevelInfo> levels;

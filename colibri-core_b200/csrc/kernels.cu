@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(512) unigram_hist_kernel(const uint32_t* __res
 // prune(MINTOKENS, 1) (patternmodel.h:2107-2128) over the class array + totaltypes (:1199-1201, counted BEFORE pruning)
 // (part_mod, part_rem): in multi-GPU mode every rank sees the same global counts and exports the classes c with c % part_mod == part_rem
 __global__ void __launch_bounds__(256) unigram_prune_kernel(const uint32_t* __restrict__ count1, uint32_t nclasses, uint32_t threshold, uint32_t* __restrict__ sv_pos,
-                                                            uint32_t* __restrict__ sv_count, uint64_t sv_base, DeviceStats* __restrict__ st, uint32_t part_mod, uint32_t part_rem) {
+                                                            uint32_t* __restrict__ sv_count, uint64_t sv_base, DeviceStats* __restrict__ st, uint32_t part_mod, uint32_t part_rem,
+                                                            uint32_t* __restrict__ class_index /* may be NULL: class -> survivor index + 1 */) {
     __shared__ uint64_t scratch[8];
     uint64_t found = 0, kept = 0, occ = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)div_up(nclasses, 32) * 32; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(256) unigram_prune_kernel(const uint32_t* __re
             sv_pos[sv_base + idx]   = (uint32_t)i;  // level 1 survivors carry the class id instead of a position
             sv_count[sv_base + idx] = c;
         }
+        if (class_index != nullptr && i < nclasses) class_index[i] = mine ? (uint32_t)idx + 1 : 0u;
         if (keep) {
             ++kept;
             occ += c;
@@ -219,9 +221,9 @@ int launch_unigram_hist(cudaStream_t s, const uint32_t* tok, uint64_t npos, uint
     return 1;
 }
 int launch_unigram_prune(cudaStream_t s, const uint32_t* count1, uint32_t nclasses, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint64_t sv_base, DeviceStats* st,
-                         uint32_t part_mod, uint32_t part_rem) {
+                         uint32_t part_mod, uint32_t part_rem, uint32_t* class_index) {
     unsigned grid = min(div_up(nclasses, 256), 148u * 8u);
-    unigram_prune_kernel<<<grid, 256, 0, s>>>(count1, nclasses, threshold, sv_pos, sv_count, sv_base, st, part_mod ? part_mod : 1u, part_rem);
+    unigram_prune_kernel<<<grid, 256, 0, s>>>(count1, nclasses, threshold, sv_pos, sv_count, sv_base, st, part_mod ? part_mod : 1u, part_rem, class_index);
     return 1;
 }
 int launch_make_id1(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* count1, uint32_t threshold, uint32_t* id1) {
@@ -390,7 +392,7 @@ __device__ __forceinline__ void load_slot<SkipSlot>(const SkipSlot* table, uint6
 template <class Slot, bool kSkip>
 __global__ void __launch_bounds__(256) prune_table_kernel(const Slot* __restrict__ table, uint64_t cap, uint32_t threshold, uint32_t* __restrict__ sv_pos,
                                                           uint32_t* __restrict__ sv_count, uint32_t* __restrict__ sv_mask, uint32_t* __restrict__ bitmap,
-                                                          DeviceStats* __restrict__ st) {
+                                                          uint32_t* __restrict__ slot_index /* may be NULL: slot -> survivor index + 1 */, DeviceStats* __restrict__ st) {
     __shared__ uint64_t scratch[8];
     __shared__ uint32_t warp_cnt[8];
     __shared__ unsigned long long tile_base;
@@ -439,12 +441,14 @@ __global__ void __launch_bounds__(256) prune_table_kernel(const Slot* __restrict
         uint64_t out = tile_base + warp_cnt[warp];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            if (sv_pos != nullptr && ((keepbits[k] >> lane) & 1u)) {
-                uint64_t idx = out + __popc(keepbits[k] & ((1u << lane) - 1));
+            const bool mine = (keepbits[k] >> lane) & 1u;
+            uint64_t   idx  = out + __popc(keepbits[k] & ((1u << lane) - 1));
+            if (sv_pos != nullptr && mine) {
                 sv_pos[idx]   = pos[k];
                 sv_count[idx] = cnt[k];
                 if (kSkip) sv_mask[idx] = msk[k];
             }
+            if (slot_index != nullptr && base + k * 32 + lane < cap) slot_index[base + k * 32 + lane] = mine ? (uint32_t)idx + 1 : 0u;
             out += __popc(keepbits[k]);
         }
         __syncthreads();  // warp_cnt / tile_base are reused by the next tile
@@ -504,10 +508,11 @@ int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uin
     }
     return 1;
 }
-int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap, DeviceStats* st, int sms) {
+int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap, DeviceStats* st, int sms,
+                        uint32_t* slot_index) {
     static int bps = blocks_per_sm((const void*)prune_table_kernel<NgramSlot, false>, 256, 0);
     unsigned   grid = (unsigned)umin64(div_up(cap, kPruneTile), (uint64_t)sms * bps);
-    prune_table_kernel<NgramSlot, false><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, nullptr, bitmap, st);
+    prune_table_kernel<NgramSlot, false><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, nullptr, bitmap, slot_index, st);
     return 1;
 }
 int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap) {
@@ -593,7 +598,7 @@ int launch_count_skipgrams(cudaStream_t s, const uint32_t* const* ids, int n, co
 int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask, DeviceStats* st, int sms) {
     static int bps  = blocks_per_sm((const void*)prune_table_kernel<SkipSlot, true>, 256, 0);
     unsigned   grid = (unsigned)umin64(div_up(cap, kPruneTile), (uint64_t)sms * bps);
-    prune_table_kernel<SkipSlot, true><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, sv_mask, nullptr, st);
+    prune_table_kernel<SkipSlot, true><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, sv_mask, nullptr, nullptr, st);
     return 1;
 }
 
@@ -909,7 +914,7 @@ int launch_shard_merge(cudaStream_t s, const void* recv, uint64_t nrecv, NgramSl
 }
 int launch_shard_prune_owner(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* bitmap, DeviceStats* st, int sms) {
     unsigned grid = (unsigned)umin64(div_up(cap, kPruneTile), (uint64_t)sms * 4);
-    prune_table_kernel<NgramSlot, false><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, nullptr, nullptr, nullptr, bitmap, st);
+    prune_table_kernel<NgramSlot, false><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, nullptr, nullptr, nullptr, bitmap, nullptr, st);
     return 1;
 }
 int launch_shard_reply(cudaStream_t s, const uint32_t* reply_slot, uint64_t nrecv, const NgramSlot* table, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* reply) {

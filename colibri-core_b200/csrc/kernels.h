@@ -42,6 +42,7 @@ constexpr unsigned kErrTokenTooLong  = 1u;  // varint longer than 5 bytes / clas
 constexpr unsigned kErrNonCanonical  = 2u;  // multi-byte token whose last byte is 0
 constexpr unsigned kErrReservedClass = 4u;  // class 3 (skip) or 4 (flex) in running text
 constexpr unsigned kErrTableFull     = 8u;  // a probe sequence wrapped the whole table
+constexpr unsigned kErrLongSentence  = 16u; // indexed model: a token offset does not fit IndexReference's uint16_t
 
 // gap configuration of one skipgram mask, precomputed on the host (compute_skip_configurations, src/algorithms.cpp:79-94)
 constexpr int kMaxSkipParts = 12;
@@ -64,7 +65,7 @@ int launch_tokenise_write(cudaStream_t s, const uint8_t* corpus, uint64_t nbytes
 // ---- K1: unigram histogram, unigram prune, level-1 ids
 int launch_unigram_hist(cudaStream_t s, const uint32_t* tok, uint64_t npos, uint32_t* count1, uint32_t nclasses, int sms);
 int launch_unigram_prune(cudaStream_t s, const uint32_t* count1, uint32_t nclasses, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint64_t sv_base, DeviceStats* st,
-                         uint32_t part_mod = 1, uint32_t part_rem = 0);
+                         uint32_t part_mod = 1, uint32_t part_rem = 0, uint32_t* class_index = nullptr);
 int launch_make_id1(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* count1, uint32_t threshold, uint32_t* id1);
 
 // ---- K2: n-gram upsert (the dominant kernel), K3: prune/compact, relabel
@@ -74,7 +75,8 @@ int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uin
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms,
                         const uint32_t* filter = nullptr, uint64_t nbuckets = 0);
 // bitmap: (cap+31)/32 words, bit = slot survived (may be NULL)
-int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap, DeviceStats* st, int sms);
+int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap, DeviceStats* st, int sms,
+                        uint32_t* slot_index = nullptr /* slot -> survivor index + 1, for the forward index */);
 int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap);
 
 // ---- skipgrams (config 3)
@@ -93,6 +95,16 @@ int launch_export_write(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_
 // model-file body: per pattern  key bytes, 0x00, u32 count  (unindexed; patternstore.h:534-542 + datatypes.h:216-221)
 int launch_export_write_modelfile(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, const uint32_t* sv_count, const uint64_t* off, uint64_t n,
                                   uint8_t* out);
+
+// ---- forward index of indexed models (index.cu)
+int launch_delim_flags(cudaStream_t s, const uint32_t* tok, uint64_t npos, uint32_t* flags);
+int launch_sent_start(cudaStream_t s, const uint32_t* tok, const uint64_t* sent_before, uint64_t npos, uint32_t* sent_start);
+int launch_pair_count(cudaStream_t s, const uint32_t* ids, const uint32_t* map, uint64_t npos, bool by_class, uint32_t* blk_counts /* one per 2048 positions */);
+int launch_pair_write(cudaStream_t s, const uint32_t* ids, const uint32_t* map, uint64_t npos, bool by_class, const uint64_t* blk_off, uint32_t* keys, uint32_t* vals);
+int launch_radix_pass(cudaStream_t s, const uint32_t* keys_in, const uint32_t* vals_in, uint64_t n, int shift, uint32_t* hist /* 256*ceil(n/4096) */, uint64_t* hist_off,
+                      uint64_t* scan_tmp, uint32_t* keys_out, uint32_t* vals_out);
+int launch_refs_from_positions(cudaStream_t s, const uint32_t* pos, uint64_t n, const uint64_t* sent_before, const uint32_t* sent_start, uint32_t* ref_sentence, uint16_t* ref_token,
+                               DeviceStats* st);
 
 // ---- multi-GPU phases (hash-partitioned model): see shard.cu
 int launch_shard_dest_count(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t world, unsigned long long* dest_counts, int sms);

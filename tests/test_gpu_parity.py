@@ -40,8 +40,6 @@ def gpu_options(case):
 
 def supported(case):
     o = case["options"]
-    if o["indexed"]:
-        return False
     if o.get("mintokens", 2) > 1 and o.get("maxbackofflength", 100) < o.get("maxlength", 100) - 1:
         return False
     return True
@@ -121,6 +119,33 @@ def test_gpu_matches_oracle_on_seeded_synthetic(kw, skip):
     assert (got.tokens, got.types, len(got)) == (want.tokens, want.types, len(want))
     assert got.passes == want.passes
     assert got.same_patterns(want)
+
+
+@pytest.mark.parametrize("kw,maxlength,mintokens", [(dict(ntokens=1500000, vocab=60000, seed=31, mean_sentence=22), 5, 2),
+                                                    (dict(ntokens=800000, vocab=2000, seed=32, mean_sentence=9, phrase_permille=300, nphrases=300), 8, 3),
+                                                    (dict(ntokens=300000, vocab=500, seed=33, mean_sentence=30), 3, 1)])
+def test_indexed_model_matches_oracle(kw, maxlength, mintokens):
+    """Config 4: IndexedPatternModel -- every pattern's sorted (sentence, token) list (datatypes.h:33-89, patternmodel.h:2699-2705, :2789-2800)."""
+    corpus = cb().Corpus.synthetic(**kw)
+    body = corpus.download()
+    m = cb().train(corpus, MINTOKENS=mintokens, MAXLENGTH=maxlength, model_type=20, streamed=0, QUIET=1)
+    want = oracle.train(body, mintokens=mintokens, maxlength=maxlength, indexed=1, streamed=0)
+    got = to_flat(m)
+    assert (got.tokens, got.types, len(got)) == (want.tokens, want.types, len(want))
+    assert got.passes == want.passes
+    assert got.same_patterns(want)  # keys, counts AND reference lists
+    assert oracle.parse_modelfile(m.to_bytes()).same_patterns(want)
+
+
+def test_indexed_sentence_length_limit():
+    """IndexReference.token is a uint16_t (datatypes.h:36).  65 536 tokens in one sentence is the encoder's maximum
+    (src/classencoder.cpp:581-588) and must work; longer ones would wrap in the reference and are refused loudly here."""
+    body = oracle.encode_corpus([[6 + (i % 7) for i in range(65536)], [6, 7, 8]])
+    m = cb().train(body, MINTOKENS=2, MAXLENGTH=2, model_type=20, streamed=0, QUIET=1)
+    assert to_flat(m).same_patterns(oracle.train(body, mintokens=2, maxlength=2, indexed=1, streamed=0))
+    with pytest.raises(cb().ColibriError) as ei:
+        cb().train(oracle.encode_corpus([[6 + (i % 7) for i in range(70000)]]), MINTOKENS=2, MAXLENGTH=2, model_type=20, streamed=0, QUIET=1)
+    assert ei.value.code == 2
 
 
 @pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref (the compiled reference) is not present")

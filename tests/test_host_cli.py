@@ -43,23 +43,23 @@ def test_cli_fails_loudly_without_gpu(cli):
         assert not os.path.exists(os.path.join(td, "m"))
 
 
-CLI_CASES = [c for c in load_cases() if c["corpus"] in ("hamlet", "republic") and c["unindexed"] and c["options"].get("maxbackofflength", 100) >= 100]
+CLI_CASES = [c for c in load_cases() if c["corpus"] in ("hamlet", "republic") and c["options"].get("maxbackofflength", 100) >= 100 and not (c["skipgrams"] and not c["unindexed"])]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", CLI_CASES, ids=["%s-%s%s" % (c["corpus"], "s" if c["skipgrams"] else "", "".join("%s%s" % kv for kv in sorted(c["cli"].items()))) for c in CLI_CASES])
+@pytest.mark.parametrize("case", CLI_CASES, ids=["%s-%s%s%s" % (c["corpus"], "u" if c["unindexed"] else "i", "s" if c["skipgrams"] else "", "".join("%s%s" % kv for kv in sorted(c["cli"].items()))) for c in CLI_CASES])
 def test_cli_model_files_equal_reference(cli, case):
     """colibri-patternmodeller -f X -u [-s] ... -o M  ->  M parses to the same patterns/counts/header as the reference's file."""
     corpus = os.path.join(GOLDEN_DIR, case["corpus"] + ".colibri.dat")
     with tempfile.TemporaryDirectory() as td:
         out = os.path.join(td, "m.colibri.patternmodel")
-        cmd = [cli, "-f", corpus, "-u", "-o", out] + (["-s"] if case["skipgrams"] else [])
+        cmd = [cli, "-f", corpus, "-o", out] + (["-u"] if case["unindexed"] else []) + (["-s"] if case["skipgrams"] else [])
         for k, v in case["cli"].items():
             cmd += ["-" + k, str(v)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         m = oracle.parse_modelfile(open(out, "rb").read())
-        assert (m.tokens, m.types, len(m), m.model_type) == (case["tokens"], case["types"], case["patterns"], 10)
+        assert (m.tokens, m.types, len(m), m.model_type) == (case["tokens"], case["types"], case["patterns"], 10 if case["unindexed"] else 20)
         assert m.digest() == case["digest"]
         # the progress lines are the reference's: " Found X ngrams...pruned Y...total kept: Z"
         assert [(p[0], p[2]) for p in oracle.parse_ref_passes(r.stderr)] == [(p[0], p[2]) for p in case["passes"]]

@@ -53,44 +53,75 @@ def workload_name(a):
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi samples during the timed region (B200_PROFILING.md: the clocks line)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md: the clocks line).
+    Uses NVML directly (two cheap queries per sample); a polling `nvidia-smi -lms` process was measured to stall the
+    driver for milliseconds at a time and to slow the timed step by 2x.  Falls back to one-shot nvidia-smi calls."""
 
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index=0):
-        self.index = index
-        self.rows = []
-        self.proc = None
+    def __init__(self, index=0, period_s=0.05):
+        self.index, self.period = index, period_s
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except Exception:
+                return self.index
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self._nvml = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _sample(self):
+        if self._nvml is not None:
+            n = self._nvml
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)))
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        else:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            r = subprocess.run(["nvidia-smi", "-i", str(self._visible_index()), "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10)
+            f = [x.strip() for x in r.stdout.strip().split(",")]
+            self.sm.append(float(f[0]))
+            self.max_mhz = float(f[1])
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+    def _run(self):
+        while not self._stop.is_set():
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                self._sample()
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+            self._stop.wait(self.period if self._nvml is not None else 1.0)
+
+    def stop(self):
+        if self._thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler not started"]}
+        self._stop.set()
+        self._thread.join(timeout=15)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------- reference / cpu baseline
@@ -219,9 +250,11 @@ def run_ours(a):
         for n in range(2, m.maxlength() + 1):
             lv = m.level(n)
             count_ms += lv["count_ms"]
-            # dominant kernel, per launch: read prev id + write cur id for every position (8 B), one 32 B sector read and one
-            # 32 B write-back for every valid window (DESIGN.md "algorithmic bytes")
-            alg_bytes += 8.0 * (ct["positions"] + 1) + 64.0 * lv["windows"]
+            # dominant kernel family of level n (occurrence filter + count), DESIGN.md "algorithmic bytes": the count launch reads
+            # the previous id and writes the new id of every position (8 B) and moves one 32 B sector in and out of HBM per
+            # window that reaches the table; the filter launch (when used) reads the ids once more (4 B); its 2-bit
+            # counters are sized to stay in L2 and are not counted as HBM traffic.
+            alg_bytes += 8.0 * (ct["positions"] + 1) + 64.0 * (lv["windows"] - lv["singletons"]) + (4.0 * (ct["positions"] + 1) if lv["singletons"] else 0.0)
         if last is not None:
             last.close()
         last = m
@@ -243,7 +276,7 @@ def run_ours(a):
                    "timing": "max(torch CUDA events, wall clock) around K synchronous ABI calls"},
         "device_ms_per_step": sum(dev_ms) / len(dev_ms),
         "phase_ms_per_step": {k: v / a.steps for k, v in phase_ms.items()},
-        "roofline": {"bound": "hbm", "kernel": "count_ngrams_kernel (levels 2..%d, one launch each)" % last.maxlength(), "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "ngram_filter_kernel + count_ngrams_kernel (levels 2..%d)" % last.maxlength(), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "alg_bytes_per_step": alg_bytes / a.steps, "kernel_ms_per_step": count_ms / a.steps,
                      "kernel_share_of_step": (count_ms / a.steps) / (sum(dev_ms) / len(dev_ms)),
                      "traffic": traffic["dram_bytes_per_step"] if traffic else None,

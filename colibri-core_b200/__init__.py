@@ -334,9 +334,9 @@ class Model:
         return {k: int(v) for k, v in zip(names, c)}
 
     def level(self, n):
-        out = (C.c_double * 3)()
+        out = (C.c_double * 4)()
         _check(library().colibri_b200_model_level_counters(self._h, n, out))
-        return {"windows": int(out[0]), "capacity": int(out[1]), "count_ms": float(out[2])}
+        return {"windows": int(out[0]), "capacity": int(out[1]), "count_ms": float(out[2]), "singletons": int(out[3])}
 
     def close(self):
         if self._h:

@@ -169,12 +169,13 @@ extern "C" int colibri_b200_model_counters(const colibri_b200_model* m, uint64_t
     memcpy(out, m->counters, sizeof m->counters);
     return 0;
 }
-extern "C" int colibri_b200_model_level_counters(const colibri_b200_model* m, int n, double out[3]) {
+extern "C" int colibri_b200_model_level_counters(const colibri_b200_model* m, int n, double out[4]) {
     auto it = m->levels.find(n);
     if (it == m->levels.end()) return set_err(COLIBRI_E_INVALID, "level %d was not run", n);
     out[0] = (double)it->second.windows;
     out[1] = (double)it->second.cap;
     out[2] = it->second.ms;
+    out[3] = (double)it->second.singles;
     return 0;
 }
 

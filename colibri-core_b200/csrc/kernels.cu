@@ -812,37 +812,77 @@ __global__ void __launch_bounds__(256) shard_pack_kernel(const NgramSlot* __rest
     }
 }
 
-// owner side: fold the received partial counts into the owner table; reply_slot[i] = slot + 1 of record i
-__global__ void __launch_bounds__(256) shard_merge_kernel(const uint4* __restrict__ recv, uint64_t nrecv, NgramSlot* __restrict__ table, uint64_t cap,
-                                                          uint32_t* __restrict__ reply_slot, DeviceStats* __restrict__ st) {
-    bool full = false;
+// owner side, step 1 (MINTOKENS >= 2): add every record's partial count to a 2-bit saturating counter per hash bucket
+// (L2 resident, same layout as the single-GPU occurrence filter).  A record whose bucket ends at "1" is the only record of
+// its key and has count 1: a global singleton that never needs a table slot.
+__global__ void __launch_bounds__(256) shard_owner_filter_kernel(const uint4* __restrict__ recv, uint64_t nrecv, uint32_t* __restrict__ filter, uint64_t nbuckets_mask) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrecv; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint4              r    = __ldcs(recv + i);
-        unsigned long long key  = ((unsigned long long)r.y << 32) | r.x;
-        uint64_t           slot = fast_range(spooky_hash64_u64(key, 0), cap);
-        uint32_t           out  = 0;
-        for (uint64_t step = 0; step < cap; ++step) {
-            NgramSlot*         s   = table + slot;
-            unsigned long long cur = __ldcg(&s->key);
-            if (cur == 0) {
-                unsigned long long o0, o1;
-                cas128(s, key, (unsigned long long)r.z | ((unsigned long long)(uint32_t)i << 32), o0, o1);  // pos = index of the claiming record
-                if (o0 == 0) {
+        uint4    r = __ldcs(recv + i);
+        uint64_t word;
+        uint32_t shift;
+        filter_locate(spooky_hash64_u64(((unsigned long long)r.y << 32) | r.x, 0), nbuckets_mask, word, shift);
+        if (r.z >= 2) {
+            atomicOr(filter + word, 3u << shift);
+            continue;
+        }
+        uint32_t bits = (__ldcg(filter + word) >> shift) & 3u;
+        if (bits == 3u) continue;
+        if ((bits & 1u) == 0) {
+            uint32_t old = atomicOr(filter + word, 1u << shift);
+            if (((old >> shift) & 1u) == 0) continue;
+        }
+        atomicOr(filter + word, 2u << shift);
+    }
+}
+
+// owner side, step 2: fold the received partial counts into the owner table; reply_slot[i] = slot + 1 of record i (0: singleton)
+__global__ void __launch_bounds__(256) shard_merge_kernel(const uint4* __restrict__ recv, uint64_t nrecv, NgramSlot* __restrict__ table, uint64_t cap,
+                                                          uint32_t* __restrict__ reply_slot, const uint32_t* __restrict__ filter, uint64_t nbuckets_mask,
+                                                          DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    bool     full    = false;
+    uint32_t singles = 0;
+    const uint64_t limit = cap < kMaxProbe ? cap : kMaxProbe;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrecv; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4              r   = __ldcs(recv + i);
+        unsigned long long key = ((unsigned long long)r.y << 32) | r.x;
+        const uint64_t     h   = spooky_hash64_u64(key, 0);
+        uint32_t           out = 0;
+        bool               go  = true;
+        if (filter != nullptr) {
+            uint64_t word;
+            uint32_t shift;
+            filter_locate(h, nbuckets_mask, word, shift);
+            go = ((__ldg(filter + word) >> shift) & 2u) != 0;
+            singles += !go;
+        }
+        if (go) {
+            uint64_t slot = fast_range(h, cap);
+            for (uint64_t step = 0; step < limit; ++step) {
+                NgramSlot*         s   = table + slot;
+                unsigned long long cur = __ldcg(&s->key);
+                if (cur == 0) {
+                    unsigned long long o0, o1;
+                    cas128(s, key, (unsigned long long)r.z | ((unsigned long long)(uint32_t)i << 32), o0, o1);  // pos = index of the claiming record
+                    if (o0 == 0) {
+                        out = (uint32_t)slot + 1;
+                        break;
+                    }
+                    cur = o0;
+                }
+                if (cur == key) {
+                    atomicAdd(&s->count, r.z);
                     out = (uint32_t)slot + 1;
                     break;
                 }
-                cur = o0;
+                slot = slot + 1 == cap ? 0 : slot + 1;
             }
-            if (cur == key) {
-                atomicAdd(&s->count, r.z);
-                out = (uint32_t)slot + 1;
-                break;
-            }
-            slot = slot + 1 == cap ? 0 : slot + 1;
+            if (out == 0) full = true;
         }
-        if (out == 0) full = true;
         reply_slot[i] = out;
     }
+    uint64_t sg = block_reduce_sum(singles, scratch);
+    if (threadIdx.x == 0 && sg) atomicAdd(&st->singletons, (unsigned long long)sg);
     if (full) atomicOr(&st->errflags, kErrTableFull);
 }
 
@@ -906,10 +946,17 @@ int launch_shard_pack(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint
     shard_pack_kernel<<<grid ? grid : 1, 256, 0, s>>>(table, cap, world, dest_base, cursors, (uint4*)send, send_slot);
     return 1;
 }
-int launch_shard_merge(cudaStream_t s, const void* recv, uint64_t nrecv, NgramSlot* table, uint64_t cap, uint32_t* reply_slot, DeviceStats* st, int sms) {
+int launch_shard_owner_filter(cudaStream_t s, const void* recv, uint64_t nrecv, uint32_t* filter, uint64_t nbuckets, int sms) {
     if (!nrecv) return 0;
     unsigned grid = (unsigned)umin64(div_up(nrecv, 256), (uint64_t)sms * 32);
-    shard_merge_kernel<<<grid, 256, 0, s>>>((const uint4*)recv, nrecv, table, cap, reply_slot, st);
+    shard_owner_filter_kernel<<<grid, 256, 0, s>>>((const uint4*)recv, nrecv, filter, nbuckets - 1);
+    return 1;
+}
+int launch_shard_merge(cudaStream_t s, const void* recv, uint64_t nrecv, NgramSlot* table, uint64_t cap, uint32_t* reply_slot, DeviceStats* st, int sms, const uint32_t* filter,
+                       uint64_t nbuckets) {
+    if (!nrecv) return 0;
+    unsigned grid = (unsigned)umin64(div_up(nrecv, 256), (uint64_t)sms * 32);
+    shard_merge_kernel<<<grid, 256, 0, s>>>((const uint4*)recv, nrecv, table, cap, reply_slot, filter, nbuckets ? nbuckets - 1 : 0, st);
     return 1;
 }
 int launch_shard_prune_owner(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* bitmap, DeviceStats* st, int sms) {

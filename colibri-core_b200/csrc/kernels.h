@@ -110,7 +110,9 @@ int launch_refs_from_positions(cudaStream_t s, const uint32_t* pos, uint64_t n, 
 int launch_shard_dest_count(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t world, unsigned long long* dest_counts, int sms);
 int launch_shard_pack(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t world, const unsigned long long* dest_base, unsigned long long* cursors, void* send /*16 B records*/,
                       uint32_t* send_slot, int sms);
-int launch_shard_merge(cudaStream_t s, const void* recv, uint64_t nrecv, NgramSlot* table, uint64_t cap, uint32_t* reply_slot, DeviceStats* st, int sms);
+int launch_shard_owner_filter(cudaStream_t s, const void* recv, uint64_t nrecv, uint32_t* filter /* zeroed */, uint64_t nbuckets, int sms);
+int launch_shard_merge(cudaStream_t s, const void* recv, uint64_t nrecv, NgramSlot* table, uint64_t cap, uint32_t* reply_slot, DeviceStats* st, int sms,
+                       const uint32_t* filter = nullptr, uint64_t nbuckets = 0);
 int launch_shard_prune_owner(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* bitmap, DeviceStats* st, int sms);
 int launch_shard_reply(cudaStream_t s, const uint32_t* reply_slot, uint64_t nrecv, const NgramSlot* table, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* reply /*8 B records*/);
 int launch_shard_apply(cudaStream_t s, const void* reply, const uint32_t* send_slot, uint64_t nsent, const NgramSlot* table, uint32_t* gid_of_slot, uint32_t* sv_pos, uint32_t* sv_count,

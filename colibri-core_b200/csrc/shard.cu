@@ -29,7 +29,7 @@ struct colibri_b200_shard {
     DeviceStats          h_stats;
     uint64_t             npos = 0, local_tokens = 0;
     uint32_t             local_maxclass = 0, nclasses = 0;
-    DevBuf<uint32_t>     tok, count1, prev, cur, bitmap, send_slot, reply_slot, gid_of_slot;
+    DevBuf<uint32_t>     tok, count1, prev, cur, bitmap, send_slot, reply_slot, gid_of_slot, filter;
     DevBuf<NgramSlot>    table, owner_table;
     DevBuf<unsigned long long> d_dest;  // [0..world): counts, [world..2*world): exclusive bases, [2*world..3*world): cursors
     uint64_t             local_cap = 0, owner_cap = 0, nsent = 0, prev_valid = 0;
@@ -261,18 +261,44 @@ extern "C" int colibri_b200_shard_level_merge(colibri_b200_shard* sh, const void
     CUDA_TRY(cudaSetDevice(sh->dev));
     PhaseClock clk(sh, 4);
     cudaStream_t s = sh->s;
+    // owner-side occurrence filter: most received records are global singletons that never need a table slot
+    const bool use_filter = sh->t >= 2 && nrecv >= (1ull << 22) && !getenv("COLIBRI_B200_NO_FILTER");
+    uint64_t   nbuckets = 0;
+    if (use_filter) {
+        nbuckets = 1ull << 20;
+        while (nbuckets < 8 * nrecv && nbuckets < (1ull << 28)) nbuckets <<= 1;
+        if (sh->filter.n < nbuckets / 16) TRY(sh->filter.alloc(sh->dev, nbuckets / 16));
+        CUDA_TRY(cudaMemsetAsync(sh->filter.p, 0, nbuckets / 4, s));
+        sh->launches += launch_shard_owner_filter(s, dev_recv, nrecv, sh->filter.p, nbuckets, sh->sms);
+    }
     uint64_t cap = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);
-    if (cap * sh->world >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner table of %llu slots x %u ranks exceeds the 32-bit id space", (unsigned long long)cap, sh->world);
-    if (sh->owner_table.n < cap) TRY(sh->owner_table.alloc(sh->dev, cap));
-    sh->owner_cap = cap;
+    if (use_filter) cap = std::max<uint64_t>(1024, nrecv / 2 + 1024);  // retried bigger on overflow
     TRY(sh->reply_slot.alloc(sh->dev, nrecv + 1));
+    uint64_t singles = 0;
+    for (int attempt = 0;; ++attempt) {
+        if (cap * sh->world >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner table of %llu slots x %u ranks exceeds the 32-bit id space", (unsigned long long)cap, sh->world);
+        if (sh->owner_table.n < cap) TRY(sh->owner_table.alloc(sh->dev, cap));
+        sh->owner_cap = cap;
+        CUDA_TRY(cudaMemsetAsync(sh->owner_table.p, 0, cap * sizeof(NgramSlot), s));
+        TRY(zero_phase_stats(sh));
+        sh->launches += launch_shard_merge(s, dev_recv, nrecv, sh->owner_table.p, cap, sh->reply_slot.p, sh->d_stats.p, sh->sms, use_filter ? sh->filter.p : nullptr, nbuckets);
+        CUDA_TRY(cudaMemcpyAsync(&sh->h_stats, sh->d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (sh->h_stats.errflags & kErrTableFull) {
+            if (attempt >= 6) return set_err(COLIBRI_E_CAPACITY, "owner hash table overflow");
+            CUDA_TRY(cudaMemsetAsync(&sh->d_stats.p->errflags, 0, sizeof(unsigned int), s));
+            cap *= 2;
+            continue;
+        }
+        singles = sh->h_stats.singletons;
+        break;
+    }
     if (sh->bitmap.n < cap / 32 + 8) TRY(sh->bitmap.alloc(sh->dev, cap / 32 + 8));
-    CUDA_TRY(cudaMemsetAsync(sh->owner_table.p, 0, cap * sizeof(NgramSlot), s));
     TRY(zero_phase_stats(sh));
-    sh->launches += launch_shard_merge(s, dev_recv, nrecv, sh->owner_table.p, cap, sh->reply_slot.p, sh->d_stats.p, sh->sms);
     sh->launches += launch_shard_prune_owner(s, sh->owner_table.p, cap, sh->t, sh->bitmap.p, sh->d_stats.p, sh->sms);
     sh->launches += launch_shard_reply(s, sh->reply_slot.p, nrecv, sh->owner_table.p, sh->bitmap.p, sh->world, sh->rank, dev_reply);
     TRY(read_stats(sh));
+    sh->h_stats.found += singles;  // a filtered record is a distinct n-gram with global count 1: found, and pruned
     stats[0] = sh->h_stats.found;
     stats[1] = sh->h_stats.kept;
     stats[2] = sh->h_stats.kept_occ;

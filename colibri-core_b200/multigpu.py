@@ -121,9 +121,26 @@ def _exchange(dist, torch, engine, send, send_counts, width):
     return recv, recv_counts
 
 
+class _Stopwatch:
+    """Wall-clock split of one distributed train (enabled with COLIBRI_B200_TRACE=1): where the non-kernel time goes."""
+
+    def __init__(self, engine):
+        self.on = bool(os.environ.get("COLIBRI_B200_TRACE"))
+        self.engine, self.acc, self.t = engine, {}, time.perf_counter()
+
+    def lap(self, name):
+        if not self.on:
+            return
+        self.engine.sync()
+        now = time.perf_counter()
+        self.acc[name] = self.acc.get(name, 0.0) + (now - self.t) * 1e3
+        self.t = now
+
+
 def train_distributed(engine, dist, torch, mintokens=2, maxlength=5):
     """Drive one rank through all levels.  Returns (local model share, global passes, global header dict)."""
     world = dist.get_world_size()
+    sw = _Stopwatch(engine)
     info = engine.info()
     dev = engine.new_buffer(1).device
     head = torch.tensor([info["tokens"], 0], dtype=torch.int64, device=dev)
@@ -132,10 +149,14 @@ def train_distributed(engine, dist, torch, mintokens=2, maxlength=5):
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     global_tokens, nclasses = int(head[0].item()), int(mx.item()) + 1
 
+    sw.lap("head_allreduce")
     counts = engine.unigram_counts(nclasses)
+    sw.lap("unigram_counts")
     dist.all_reduce(counts[:nclasses], op=dist.ReduceOp.SUM)  # u32 counts carried as int32 bit patterns: exact below 2^31 occurrences per class
     engine.sync()
+    sw.lap("unigram_allreduce")
     found, kept, kept_occ = engine.unigram_finish(counts, global_tokens)
+    sw.lap("unigram_finish")
     passes, maxn, minn, types = [], 0, 999, found
     if found:
         passes.append((1, found, 0, found - kept))
@@ -144,9 +165,13 @@ def train_distributed(engine, dist, torch, mintokens=2, maxlength=5):
     n = 2
     while found and n <= maxlength and prev_kept > 0:
         dest_counts, _windows, nsend = engine.level_count(n)
+        sw.lap("level_count")
         send = engine.level_pack(nsend)
+        sw.lap("level_pack")
         recv, recv_counts = _exchange(dist, torch, engine, send, dest_counts, 4)
+        sw.lap("a2a_records")
         reply, (f, k, occ) = engine.level_merge(recv, sum(recv_counts))
+        sw.lap("level_merge")
         # replies travel back along the same routes: what I received from rank r goes back to r
         nrep, nback = sum(recv_counts) * 2, nsend * 2
         back = engine.new_buffer(nback)
@@ -154,7 +179,9 @@ def train_distributed(engine, dist, torch, mintokens=2, maxlength=5):
         st = torch.tensor([f, k, occ], dtype=torch.int64, device=dev)
         dist.all_reduce(st, op=dist.ReduceOp.SUM)
         engine.sync()
+        sw.lap("a2a_replies")
         engine.level_finish(back)
+        sw.lap("level_finish")
         gf, gk, _gocc = (int(x) for x in st.tolist())
         if gf == 0:
             break  # "None found" (reference include/patternmodel.h:1189-1194)
@@ -165,6 +192,9 @@ def train_distributed(engine, dist, torch, mintokens=2, maxlength=5):
     if mintokens == 1 and passes:  # the reference reports one pass when every length is extracted in a single scan
         passes = [(1, sum(p[1] for p in passes), 0, sum(p[3] for p in passes))]
     model = engine.finish(passes, types, maxn, minn)
+    sw.lap("export")
+    if sw.on and dist.get_rank() == 0:
+        print("TRACE rank0 ms:", {k: round(v, 2) for k, v in sw.acc.items()}, flush=True)
     return model, passes, {"tokens": global_tokens, "types": types, "maxn": maxn, "minn": minn}
 
 

@@ -127,8 +127,9 @@ int colibri_b200_model_timings(const colibri_b200_model* m, double ms[COLIBRI_T_
  * out[3]=n-gram upserts (valid windows, all n>=2), out[4]=skipgram upserts, out[5]=table slots initialised (sum),
  * out[6]=unigram increments, out[7]=bytes of device memory at the peak */
 int colibri_b200_model_counters(const colibri_b200_model* m, uint64_t out[8]);
-/* per level n>=2: out[0]=valid windows (upserts), out[1]=table capacity in slots, out[2]=count-kernel ms */
-int colibri_b200_model_level_counters(const colibri_b200_model* m, int n, double out[3]);
+/* per level n>=2: out[0]=valid windows, out[1]=table capacity in slots, out[2]=ms of the level's filter + count kernels,
+ * out[3]=windows the occurrence filter proved to be singletons (they never reach the table: upserts = out[0] - out[3]) */
+int colibri_b200_model_level_counters(const colibri_b200_model* m, int n, double out[4]);
 
 /* ---- multi-GPU: one process per GPU drives these per-rank phases and moves the buffers between ranks itself
  * (torch.distributed / NCCL all-to-all); the library does no communication.  Model = hash-partitioned across ranks,

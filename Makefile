@@ -31,7 +31,11 @@ $(LIBDIR)/index.o: $(CSRC)/index.cu $(CSRC)/kernels.h $(CSRC)/device_utils.cuh
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/index.ptxas.log || (cat $(LIBDIR)/index.ptxas.log; false)
 
-$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o $(LIBDIR)/index.o
+$(LIBDIR)/shard_kernels.o: $(CSRC)/shard_kernels.cu $(CSRC)/kernels.h $(CSRC)/device_utils.cuh
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/shard_kernels.ptxas.log || (cat $(LIBDIR)/shard_kernels.ptxas.log; false)
+
+$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o $(LIBDIR)/index.o $(LIBDIR)/shard_kernels.o
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^
 
 oracle:

@@ -102,10 +102,11 @@ def library():
     L.colibri_b200_shard_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.colibri_b200_shard_unigram_counts.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.colibri_b200_shard_unigram_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]
-    L.colibri_b200_shard_level_count.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p]
-    L.colibri_b200_shard_level_pack.argtypes = [C.c_void_p, C.c_void_p]
-    L.colibri_b200_shard_level_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, _u64p]
-    L.colibri_b200_shard_level_finish.argtypes = [C.c_void_p, C.c_void_p, _u64p]
+    L.colibri_b200_shard_level_split_count.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p]
+    L.colibri_b200_shard_level_split_write.argtypes = [C.c_void_p, C.c_void_p]
+    L.colibri_b200_shard_level_owner.argtypes = [C.c_void_p, C.c_void_p, _u64p, C.c_void_p, _u64p, _u64p]
+    L.colibri_b200_shard_level_owner_survivors.argtypes = [C.c_void_p, C.c_void_p]
+    L.colibri_b200_shard_level_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _u64p, _u64p]
     L.colibri_b200_shard_finish.argtypes = [C.c_void_p, _u64p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.colibri_b200_shard_free.argtypes = [C.c_void_p]
     L.colibri_b200_shard_free.restype = None

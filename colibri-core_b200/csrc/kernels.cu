@@ -752,237 +752,6 @@ int launch_export_write_modelfile(cudaStream_t s, const uint32_t* tok, const uin
 }
 
 // =============================================================================================
-// Multi-GPU (hash-partitioned model).  Every rank counts its own sentences into a local table keyed by GLOBAL
-// (n-1)-gram ids; the distinct local entries travel as 16-byte records {key, partial count, source slot} to the owner
-// rank = hash(key) mod G, which merges them, applies the threshold and answers each record with {global id, global count
-// if this record's sender is the one that exports the pattern}.
-__device__ __forceinline__ uint32_t owner_of(unsigned long long key, uint32_t world) {
-    return (uint32_t)fast_range(spooky_hash64_u64(key, 0x5eedull), world);
-}
-
-__global__ void __launch_bounds__(256) shard_dest_count_kernel(const NgramSlot* __restrict__ table, uint64_t cap, uint32_t world, unsigned long long* __restrict__ dest_counts) {
-    __shared__ uint32_t hist[64];
-    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
-    __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        unsigned long long key = __ldcs(&table[i].key);
-        if (key != 0) atomicAdd(&hist[owner_of(key, world)], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < world && hist[threadIdx.x]) atomicAdd(&dest_counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
-}
-
-// records grouped by destination: send[dest_base[d] + k]; send_slot remembers which local slot each record came from.
-// A block handles tiles of 2048 slots and reserves its output ranges with ONE atomicAdd per destination per tile
-// (per-warp cursor atomics on G addresses serialise: 7.9 ms for a 150 M-slot table in the first version).
-__global__ void __launch_bounds__(256) shard_pack_kernel(const NgramSlot* __restrict__ table, uint64_t cap, uint32_t world, const unsigned long long* __restrict__ dest_base,
-                                                         unsigned long long* __restrict__ cursors, uint4* __restrict__ send, uint32_t* __restrict__ send_slot) {
-    __shared__ uint32_t tile_cnt[64];             // per destination: records of this tile, then running offset
-    __shared__ unsigned long long tile_base[64];  // per destination: reserved start in the send buffer
-    const uint64_t ntiles = (cap + kPruneTile - 1) / kPruneTile;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        if (threadIdx.x < 64) tile_cnt[threadIdx.x] = 0;
-        __syncthreads();
-        uint4    raw[8];
-        uint32_t dest[8], rank_in_tile[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            uint64_t i = tile * kPruneTile + (uint64_t)k * 256 + threadIdx.x;
-            raw[k]     = make_uint4(0, 0, 0, 0);
-            if (i < cap) raw[k] = __ldcs(reinterpret_cast<const uint4*>(table) + i);
-            bool used = (raw[k].x | raw[k].y) != 0;
-            dest[k]   = used ? owner_of(((unsigned long long)raw[k].y << 32) | raw[k].x, world) : 0xFFFFFFFFu;
-            if (used) rank_in_tile[k] = atomicAdd(&tile_cnt[dest[k]], 1u);  // shared-memory atomic: order inside a tile is free
-        }
-        __syncthreads();
-        if (threadIdx.x < world) {
-            uint32_t c = tile_cnt[threadIdx.x];
-            tile_base[threadIdx.x] = c ? dest_base[threadIdx.x] + atomicAdd(&cursors[threadIdx.x], (unsigned long long)c) : 0ull;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (dest[k] == 0xFFFFFFFFu) continue;
-            uint64_t i   = tile * kPruneTile + (uint64_t)k * 256 + threadIdx.x;
-            uint64_t idx = tile_base[dest[k]] + rank_in_tile[k];
-            send[idx]      = make_uint4(raw[k].x, raw[k].y, raw[k].z, (uint32_t)i);
-            send_slot[idx] = (uint32_t)i;
-        }
-        __syncthreads();
-    }
-}
-
-// owner side, step 1 (MINTOKENS >= 2): add every record's partial count to a 2-bit saturating counter per hash bucket
-// (L2 resident, same layout as the single-GPU occurrence filter).  A record whose bucket ends at "1" is the only record of
-// its key and has count 1: a global singleton that never needs a table slot.
-__global__ void __launch_bounds__(256) shard_owner_filter_kernel(const uint4* __restrict__ recv, uint64_t nrecv, uint32_t* __restrict__ filter, uint64_t nbuckets_mask) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrecv; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint4    r = __ldcs(recv + i);
-        uint64_t word;
-        uint32_t shift;
-        filter_locate(spooky_hash64_u64(((unsigned long long)r.y << 32) | r.x, 0), nbuckets_mask, word, shift);
-        if (r.z >= 2) {
-            atomicOr(filter + word, 3u << shift);
-            continue;
-        }
-        uint32_t bits = (__ldcg(filter + word) >> shift) & 3u;
-        if (bits == 3u) continue;
-        if ((bits & 1u) == 0) {
-            uint32_t old = atomicOr(filter + word, 1u << shift);
-            if (((old >> shift) & 1u) == 0) continue;
-        }
-        atomicOr(filter + word, 2u << shift);
-    }
-}
-
-// owner side, step 2: fold the received partial counts into the owner table; reply_slot[i] = slot + 1 of record i (0: singleton)
-__global__ void __launch_bounds__(256) shard_merge_kernel(const uint4* __restrict__ recv, uint64_t nrecv, NgramSlot* __restrict__ table, uint64_t cap,
-                                                          uint32_t* __restrict__ reply_slot, const uint32_t* __restrict__ filter, uint64_t nbuckets_mask,
-                                                          DeviceStats* __restrict__ st) {
-    __shared__ uint64_t scratch[8];
-    bool     full    = false;
-    uint32_t singles = 0;
-    const uint64_t limit = cap < kMaxProbe ? cap : kMaxProbe;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrecv; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint4              r   = __ldcs(recv + i);
-        unsigned long long key = ((unsigned long long)r.y << 32) | r.x;
-        const uint64_t     h   = spooky_hash64_u64(key, 0);
-        uint32_t           out = 0;
-        bool               go  = true;
-        if (filter != nullptr) {
-            uint64_t word;
-            uint32_t shift;
-            filter_locate(h, nbuckets_mask, word, shift);
-            go = ((__ldg(filter + word) >> shift) & 2u) != 0;
-            singles += !go;
-        }
-        if (go) {
-            uint64_t slot = fast_range(h, cap);
-            for (uint64_t step = 0; step < limit; ++step) {
-                NgramSlot*         s   = table + slot;
-                unsigned long long cur = __ldcg(&s->key);
-                if (cur == 0) {
-                    unsigned long long o0, o1;
-                    cas128(s, key, (unsigned long long)r.z | ((unsigned long long)(uint32_t)i << 32), o0, o1);  // pos = index of the claiming record
-                    if (o0 == 0) {
-                        out = (uint32_t)slot + 1;
-                        break;
-                    }
-                    cur = o0;
-                }
-                if (cur == key) {
-                    atomicAdd(&s->count, r.z);
-                    out = (uint32_t)slot + 1;
-                    break;
-                }
-                slot = slot + 1 == cap ? 0 : slot + 1;
-            }
-            if (out == 0) full = true;
-        }
-        reply_slot[i] = out;
-    }
-    uint64_t sg = block_reduce_sum(singles, scratch);
-    if (threadIdx.x == 0 && sg) atomicAdd(&st->singletons, (unsigned long long)sg);
-    if (full) atomicOr(&st->errflags, kErrTableFull);
-}
-
-// reply[i] = {global id (0 if pruned), global count if record i is the one that claimed the slot (its sender exports the pattern) else 0}
-__global__ void __launch_bounds__(256) shard_reply_kernel(const uint32_t* __restrict__ reply_slot, uint64_t nrecv, const NgramSlot* __restrict__ table,
-                                                          const uint32_t* __restrict__ bitmap, uint32_t world, uint32_t rank, uint2* __restrict__ reply) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nrecv) return;
-    uint32_t s = reply_slot[i];
-    uint2    r = make_uint2(0, 0);
-    if (s != 0 && ((__ldg(bitmap + ((s - 1) >> 5)) >> ((s - 1) & 31)) & 1u)) {
-        uint4 raw = __ldcg(reinterpret_cast<const uint4*>(table) + (s - 1));
-        r.x       = (s - 1) * world + rank + 1;
-        r.y       = raw.w == (uint32_t)i ? raw.z : 0u;
-    }
-    reply[i] = r;
-}
-
-// sender side: the j-th reply belongs to the j-th record sent
-__global__ void __launch_bounds__(256) shard_apply_kernel(const uint2* __restrict__ reply, const uint32_t* __restrict__ send_slot, uint64_t nsent,
-                                                          const NgramSlot* __restrict__ table, uint32_t* __restrict__ gid_of_slot, uint32_t* __restrict__ sv_pos,
-                                                          uint32_t* __restrict__ sv_count, DeviceStats* __restrict__ st) {
-    const uint64_t rounded = (nsent + 31) / 32 * 32;
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < rounded; j += (uint64_t)gridDim.x * blockDim.x) {
-        uint2    r    = j < nsent ? __ldcs(reply + j) : make_uint2(0, 0);
-        uint32_t slot = j < nsent ? send_slot[j] : 0;
-        if (j < nsent) gid_of_slot[slot] = r.x;
-        bool     mine = r.y != 0;
-        uint64_t idx  = warp_aggregated_inc(&st->cursor, mine);
-        if (mine) {
-            sv_pos[idx]   = __ldcg(&table[slot].pos);
-            sv_count[idx] = r.y;
-        }
-    }
-}
-
-// cur[p]: local slot + 1  ->  global id of the surviving n-gram (0 if pruned); also counts the survivors' positions
-__global__ void __launch_bounds__(256) shard_relabel_kernel(uint32_t* __restrict__ cur, uint64_t npos, const uint32_t* __restrict__ gid_of_slot, DeviceStats* __restrict__ st) {
-    __shared__ uint64_t scratch[8];
-    uint32_t valid = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npos; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t id = cur[i];
-        if (id != 0) {
-            id     = __ldg(gid_of_slot + (id - 1));
-            cur[i] = id;
-            valid += id != 0;
-        }
-    }
-    uint64_t v = block_reduce_sum(valid, scratch);
-    if (threadIdx.x == 0 && v) atomicAdd(&st->kept_occ, (unsigned long long)v);
-}
-
-int launch_shard_dest_count(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t world, unsigned long long* dest_counts, int sms) {
-    unsigned grid = (unsigned)umin64(div_up(cap, 256), (uint64_t)sms * 8);
-    shard_dest_count_kernel<<<grid ? grid : 1, 256, 0, s>>>(table, cap, world, dest_counts);
-    return 1;
-}
-int launch_shard_pack(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t world, const unsigned long long* dest_base, unsigned long long* cursors, void* send,
-                      uint32_t* send_slot, int sms) {
-    unsigned grid = (unsigned)umin64(div_up(cap, kPruneTile), (uint64_t)sms * 4);
-    shard_pack_kernel<<<grid ? grid : 1, 256, 0, s>>>(table, cap, world, dest_base, cursors, (uint4*)send, send_slot);
-    return 1;
-}
-int launch_shard_owner_filter(cudaStream_t s, const void* recv, uint64_t nrecv, uint32_t* filter, uint64_t nbuckets, int sms) {
-    if (!nrecv) return 0;
-    unsigned grid = (unsigned)umin64(div_up(nrecv, 256), (uint64_t)sms * 32);
-    shard_owner_filter_kernel<<<grid, 256, 0, s>>>((const uint4*)recv, nrecv, filter, nbuckets - 1);
-    return 1;
-}
-int launch_shard_merge(cudaStream_t s, const void* recv, uint64_t nrecv, NgramSlot* table, uint64_t cap, uint32_t* reply_slot, DeviceStats* st, int sms, const uint32_t* filter,
-                       uint64_t nbuckets) {
-    if (!nrecv) return 0;
-    unsigned grid = (unsigned)umin64(div_up(nrecv, 256), (uint64_t)sms * 32);
-    shard_merge_kernel<<<grid, 256, 0, s>>>((const uint4*)recv, nrecv, table, cap, reply_slot, filter, nbuckets ? nbuckets - 1 : 0, st);
-    return 1;
-}
-int launch_shard_prune_owner(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* bitmap, DeviceStats* st, int sms) {
-    unsigned grid = (unsigned)umin64(div_up(cap, kPruneTile), (uint64_t)sms * 4);
-    prune_table_kernel<NgramSlot, false><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, nullptr, nullptr, nullptr, bitmap, nullptr, st);
-    return 1;
-}
-int launch_shard_reply(cudaStream_t s, const uint32_t* reply_slot, uint64_t nrecv, const NgramSlot* table, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* reply) {
-    if (!nrecv) return 0;
-    shard_reply_kernel<<<div_up(nrecv, 256), 256, 0, s>>>(reply_slot, nrecv, table, bitmap, world, rank, (uint2*)reply);
-    return 1;
-}
-int launch_shard_apply(cudaStream_t s, const void* reply, const uint32_t* send_slot, uint64_t nsent, const NgramSlot* table, uint32_t* gid_of_slot, uint32_t* sv_pos,
-                       uint32_t* sv_count, DeviceStats* st, int sms) {
-    if (!nsent) return 0;
-    unsigned grid = (unsigned)umin64(div_up(nsent, 256), (uint64_t)sms * 8);
-    shard_apply_kernel<<<grid, 256, 0, s>>>((const uint2*)reply, send_slot, nsent, table, gid_of_slot, sv_pos, sv_count, st);
-    return 1;
-}
-int launch_shard_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* gid_of_slot, DeviceStats* st, int sms) {
-    unsigned grid = (unsigned)umin64(div_up(npos, 256), (uint64_t)sms * 8);
-    shard_relabel_kernel<<<grid ? grid : 1, 256, 0, s>>>(cur, npos, gid_of_slot, st);
-    return 1;
-}
-
-// =============================================================================================
 // Pattern::hash on the device for arbitrary pattern bytes (parity row a5)
 __global__ void __launch_bounds__(256) hash64_batch_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, uint64_t n, uint64_t* __restrict__ out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -106,18 +106,17 @@ int launch_radix_pass(cudaStream_t s, const uint32_t* keys_in, const uint32_t* v
 int launch_refs_from_positions(cudaStream_t s, const uint32_t* pos, uint64_t n, const uint64_t* sent_before, const uint32_t* sent_start, uint32_t* ref_sentence, uint16_t* ref_token,
                                DeviceStats* st);
 
-// ---- multi-GPU phases (hash-partitioned model): see shard.cu
-int launch_shard_dest_count(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t world, unsigned long long* dest_counts, int sms);
-int launch_shard_pack(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t world, const unsigned long long* dest_base, unsigned long long* cursors, void* send /*16 B records*/,
-                      uint32_t* send_slot, int sms);
-int launch_shard_owner_filter(cudaStream_t s, const void* recv, uint64_t nrecv, uint32_t* filter /* zeroed */, uint64_t nbuckets, int sms);
-int launch_shard_merge(cudaStream_t s, const void* recv, uint64_t nrecv, NgramSlot* table, uint64_t cap, uint32_t* reply_slot, DeviceStats* st, int sms,
-                       const uint32_t* filter = nullptr, uint64_t nbuckets = 0);
-int launch_shard_prune_owner(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* bitmap, DeviceStats* st, int sms);
-int launch_shard_reply(cudaStream_t s, const uint32_t* reply_slot, uint64_t nrecv, const NgramSlot* table, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* reply /*8 B records*/);
-int launch_shard_apply(cudaStream_t s, const void* reply, const uint32_t* send_slot, uint64_t nsent, const NgramSlot* table, uint32_t* gid_of_slot, uint32_t* sv_pos, uint32_t* sv_count,
-                       DeviceStats* st, int sms);
-int launch_shard_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* gid_of_slot, DeviceStats* st, int sms);
+// ---- multi-GPU phases (hash-partitioned model): shard_kernels.cu, driven by shard.cu
+int launch_split_count(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, uint32_t* hist /* world x ceil(npos/4096), destination-major */);
+int launch_split_write(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, const uint64_t* hist_off, void* send_keys, uint32_t* pos_of_rec, uint32_t* rec_of_pos);
+int launch_stream_filter(cudaStream_t s, const void* keys, uint64_t n, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms);
+int launch_stream_count(cudaStream_t s, const void* keys, uint64_t n, NgramSlot* table, uint64_t cap, const uint32_t* filter, uint64_t nbuckets, uint32_t* rid, DeviceStats* st, int sms);
+int launch_owner_reply(cudaStream_t s, uint32_t* rid, uint64_t n, const uint32_t* bitmap, uint32_t world, uint32_t rank);
+int launch_owner_survivor_counts(cudaStream_t s, const uint32_t* sv_idx, uint64_t n, uint32_t world, const unsigned long long* src_base, unsigned long long* counts, int sms);
+int launch_owner_survivors(cudaStream_t s, const uint32_t* sv_idx, const uint32_t* sv_count, uint64_t n, uint32_t world, const unsigned long long* src_base,
+                           const unsigned long long* out_base, unsigned long long* cursors, void* out, int sms);
+int launch_sender_relabel(cudaStream_t s, const uint32_t* rec_of_pos, const uint32_t* reply, uint64_t npos, uint32_t* cur, DeviceStats* st, int sms);
+int launch_sender_survivors(cudaStream_t s, const void* recs, uint64_t n, const uint32_t* pos_of_rec, uint64_t send_base, uint32_t* sv_pos, uint32_t* sv_count);
 
 // ---- parity helpers / measurement input
 int launch_hash64_batch(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t n, uint64_t* out);

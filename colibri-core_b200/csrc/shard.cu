@@ -5,14 +5,14 @@
 // by hash: owner(key) = hash(key) mod G.  One process per GPU drives these phases and moves the buffers between ranks
 // with torch.distributed (NCCL all-to-all over NVLink); this file contains no communication and no torch types.
 //
-// Per level n >= 2 and per rank:
-//   level_count   local upsert of every valid window into a local table keyed by GLOBAL (n-1)-gram ids (same kernel as 1 GPU)
-//   level_pack    distinct local entries -> 16-byte records {key, partial count, source slot}, grouped by owner rank
-//   [all-to-all]
-//   level_merge   owner: fold records into the owner table, threshold (prune(), patternmodel.h:2107-2128), reply per record
-//                 {global id | 0, global count if this sender exports the pattern}
-//   [all-to-all back]
-//   level_finish  sender: local slot -> global id, relabel the positions, keep the survivors this rank exports
+// Per level n >= 2 and per rank ("ship the windows to their owners", see shard_kernels.cu):
+//   level_split_count / level_split_write   valid windows -> 8-byte keys grouped by owner rank, corpus order inside a group
+//   [all-to-all of keys]
+//   level_owner            occurrence filter + table upserts over the received keys (the single-GPU kernels on a key stream),
+//                          threshold (prune(), patternmodel.h:2107-2128), reply = global id per received window (4 bytes)
+//   level_owner_survivors  (index in the sender's group, global count) for the window that claimed each surviving slot
+//   [all-to-all back of the replies, all-to-all of the survivor records]
+//   level_finish           id[p] = reply[rec_of_pos[p]] (streaming), survivors -> (position, count) this rank exports
 // Level 1 needs no table: the class histograms are summed with an all-reduce.
 #include "engine_common.h"
 
@@ -29,10 +29,12 @@ struct colibri_b200_shard {
     DeviceStats          h_stats;
     uint64_t             npos = 0, local_tokens = 0;
     uint32_t             local_maxclass = 0, nclasses = 0;
-    DevBuf<uint32_t>     tok, count1, prev, cur, bitmap, send_slot, reply_slot, gid_of_slot, filter;
-    DevBuf<NgramSlot>    table, owner_table;
-    DevBuf<unsigned long long> d_dest;  // [0..world): counts, [world..2*world): exclusive bases, [2*world..3*world): cursors
-    uint64_t             local_cap = 0, owner_cap = 0, nsent = 0, prev_valid = 0;
+    DevBuf<uint32_t>     tok, count1, prev, cur, bitmap, filter, pos_of_rec, rec_of_pos, split_hist, sv_idx, sv_cnt;
+    DevBuf<uint64_t>     split_off, scan_tmp;
+    DevBuf<NgramSlot>    owner_table;
+    DevBuf<unsigned long long> d_aux;   // [0..65): source bases of the receive buffer, [65..130): output bases, [130..195): cursors, [195..260): counts
+    uint64_t             send_base[65] = {0}, nsent = 0, nrecv = 0, nsurv = 0, prev_valid = 0;
+    uint64_t             surv_out_counts[64] = {0};
     int                  level = 1;
     uint32_t             t = 2;
     std::vector<Segment> segs;
@@ -117,7 +119,6 @@ extern "C" int colibri_b200_shard_begin(colibri_b200_corpus* corpus, const colib
         CUDA_TRY(cudaMemcpyAsync(corpus->body() + corpus->nbytes, tail, sizeof tail, cudaMemcpyHostToDevice, s));
         const uint32_t nblocks = (uint32_t)(corpus->padded(staged) / kTokTile);
         TRY(sh->d_stats.alloc(sh->dev, 1));
-        TRY(sh->d_dest.alloc(sh->dev, 3 * 64));
         CUDA_TRY(cudaMemsetAsync(sh->d_stats.p, 0, sizeof(DeviceStats), s));
         DevBuf<uint32_t> blk;
         TRY(blk.alloc(sh->dev, nblocks + 1));
@@ -208,83 +209,86 @@ extern "C" int colibri_b200_shard_unigram_finish(colibri_b200_shard* sh, const v
     return 0;
 }
 
-// local counting of level n; dest_counts[world] = records this rank will send to each owner; stats = {valid windows, distinct local keys}
-extern "C" int colibri_b200_shard_level_count(colibri_b200_shard* sh, int n, uint64_t* dest_counts, uint64_t stats[2]) {
-    if (!sh || !dest_counts || !stats) return set_err(COLIBRI_E_INVALID, "NULL argument");
+// count the valid windows of level n per owner rank.  send_counts[world]; *windows = their sum
+extern "C" int colibri_b200_shard_level_split_count(colibri_b200_shard* sh, int n, uint64_t* send_counts, uint64_t* windows) {
+    if (!sh || !send_counts || !windows) return set_err(COLIBRI_E_INVALID, "NULL argument");
     if (n != sh->level + 1) return set_err(COLIBRI_E_INVALID, "level %d requested after level %d", n, sh->level);
     CUDA_TRY(cudaSetDevice(sh->dev));
     PhaseClock clk(sh, 2);
-    cudaStream_t s = sh->s;
-    uint64_t bound = std::max<uint64_t>(sh->prev_valid, 1);
-    uint64_t cap   = std::max<uint64_t>(64, bound + bound / 2 + 16);
-    if (cap >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "level %d needs %llu local table slots", n, (unsigned long long)cap);
-    if (sh->table.n < cap) TRY(sh->table.alloc(sh->dev, cap));
-    sh->local_cap = cap;
-    CUDA_TRY(cudaMemsetAsync(sh->table.p, 0, cap * sizeof(NgramSlot), s));
-    CUDA_TRY(cudaMemsetAsync(sh->cur.p + sh->npos, 0, 8 * sizeof(uint32_t), s));
-    CUDA_TRY(cudaMemsetAsync(sh->d_dest.p, 0, 3 * 64 * sizeof(unsigned long long), s));
-    TRY(zero_phase_stats(sh));
-    sh->launches += launch_count_ngrams(s, sh->prev.p, sh->cur.p, sh->npos, sh->table.p, cap, sh->d_stats.p, sh->sms);
-    sh->launches += launch_shard_dest_count(s, sh->table.p, cap, sh->world, sh->d_dest.p, sh->sms);
-    unsigned long long h_dest[64];
-    CUDA_TRY(cudaMemcpyAsync(h_dest, sh->d_dest.p, sh->world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    TRY(read_stats(sh));
-    unsigned long long bases[64];
-    uint64_t total = 0;
-    for (uint32_t d = 0; d < sh->world; ++d) {
-        dest_counts[d] = h_dest[d];
-        bases[d]       = total;
-        total += h_dest[d];
-    }
-    CUDA_TRY(cudaMemcpyAsync(sh->d_dest.p + 64, bases, sh->world * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    cudaStream_t   s       = sh->s;
+    const uint64_t nblocks = (sh->npos + 4095) / 4096;
+    const uint64_t nh      = (uint64_t)sh->world * nblocks;
+    if (sh->split_hist.n < nh) TRY(sh->split_hist.alloc(sh->dev, nh));
+    if (sh->split_off.n < nh + 1) TRY(sh->split_off.alloc(sh->dev, nh + 1));
+    if (sh->scan_tmp.n < nh / 2048 + 4) TRY(sh->scan_tmp.alloc(sh->dev, nh / 2048 + 4));
+    sh->launches += launch_split_count(s, sh->prev.p, sh->npos, sh->world, sh->split_hist.p);
+    sh->launches += launch_exclusive_scan_u32_u64(s, sh->split_hist.p, sh->split_off.p, nh, sh->scan_tmp.p);
+    for (uint32_t d = 0; d <= sh->world; ++d)
+        CUDA_TRY(cudaMemcpyAsync(&sh->send_base[d], sh->split_off.p + (uint64_t)d * nblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    sh->nsent = total;
-    stats[0]  = sh->h_stats.valid_windows;
-    stats[1]  = total;
+    for (uint32_t d = 0; d < sh->world; ++d) send_counts[d] = sh->send_base[d + 1] - sh->send_base[d];
+    sh->nsent = sh->send_base[sh->world];
+    *windows  = sh->nsent;
     return 0;
 }
 
-// write the nsent 16-byte records, grouped by destination rank in rank order, into dev_send
-extern "C" int colibri_b200_shard_level_pack(colibri_b200_shard* sh, void* dev_send) {
-    if (!sh || (!dev_send && sh->nsent)) return set_err(COLIBRI_E_INVALID, "NULL argument");
+// write the nsent 8-byte keys, grouped by owner rank in rank order, into dev_send_keys
+extern "C" int colibri_b200_shard_level_split_write(colibri_b200_shard* sh, void* dev_send_keys) {
+    if (!sh || (!dev_send_keys && sh->nsent)) return set_err(COLIBRI_E_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(sh->dev));
     PhaseClock clk(sh, 3);
-    TRY(sh->send_slot.alloc(sh->dev, sh->nsent + 1));
-    if (sh->nsent) sh->launches += launch_shard_pack(sh->s, sh->table.p, sh->local_cap, sh->world, sh->d_dest.p + 64, sh->d_dest.p + 128, dev_send, sh->send_slot.p, sh->sms);
+    if (sh->pos_of_rec.n < sh->nsent + 1) TRY(sh->pos_of_rec.alloc(sh->dev, sh->nsent + 1));
+    if (sh->rec_of_pos.n < sh->npos + 8) TRY(sh->rec_of_pos.alloc(sh->dev, sh->npos + 8));
+    sh->launches += launch_split_write(sh->s, sh->prev.p, sh->npos, sh->world, sh->split_off.p, dev_send_keys, sh->pos_of_rec.p, sh->rec_of_pos.p);
     CUDA_TRY(cudaStreamSynchronize(sh->s));
     return 0;
 }
 
-// owner side: merge nrecv records, prune, write nrecv 8-byte replies; stats = {distinct keys owned, kept, kept occurrences}
-extern "C" int colibri_b200_shard_level_merge(colibri_b200_shard* sh, const void* dev_recv, uint64_t nrecv, void* dev_reply, uint64_t stats[3]) {
-    if (!sh || !stats || (nrecv && (!dev_recv || !dev_reply))) return set_err(COLIBRI_E_INVALID, "NULL argument");
+// owner side.  dev_recv_keys: nrecv = sum(recv_counts) keys grouped by source rank; dev_reply: nrecv u32 (global id | 0 per window).
+// stats = {distinct keys owned, kept, kept occurrences}; surv_counts[world] = survivor records to return to each source.
+extern "C" int colibri_b200_shard_level_owner(colibri_b200_shard* sh, const void* dev_recv_keys, const uint64_t* recv_counts, void* dev_reply, uint64_t stats[3],
+                                              uint64_t* surv_counts) {
+    if (!sh || !recv_counts || !stats || !surv_counts) return set_err(COLIBRI_E_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(sh->dev));
     PhaseClock clk(sh, 4);
     cudaStream_t s = sh->s;
-    // owner-side occurrence filter: most received records are global singletons that never need a table slot
-    const bool use_filter = sh->t >= 2 && nrecv >= (1ull << 22) && !getenv("COLIBRI_B200_NO_FILTER");
-    uint64_t   nbuckets = 0;
+    unsigned long long src_base[65];
+    uint64_t nrecv = 0;
+    for (uint32_t r = 0; r < sh->world; ++r) {
+        src_base[r] = nrecv;
+        nrecv += recv_counts[r];
+    }
+    src_base[sh->world] = nrecv;
+    sh->nrecv = nrecv;
+    if (nrecv && (!dev_recv_keys || !dev_reply)) return set_err(COLIBRI_E_INVALID, "NULL buffer");
+    if (nrecv >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner received %llu windows; the receive index is 32 bit", (unsigned long long)nrecv);
+    if (sh->d_aux.n < 260) TRY(sh->d_aux.alloc(sh->dev, 260));
+    CUDA_TRY(cudaMemsetAsync(sh->d_aux.p, 0, 260 * sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemcpyAsync(sh->d_aux.p, src_base, (sh->world + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+
+    const uint32_t t          = sh->t;
+    const bool     use_filter = t >= 2 && nrecv >= (1ull << 25) && !getenv("COLIBRI_B200_NO_FILTER");
+    uint64_t       nbuckets = 0, cap = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);
     if (use_filter) {
         nbuckets = 1ull << 20;
-        while (nbuckets < 8 * nrecv && nbuckets < (1ull << 28)) nbuckets <<= 1;
+        while (nbuckets < 2 * nrecv && nbuckets < (1ull << 28)) nbuckets <<= 1;
         if (sh->filter.n < nbuckets / 16) TRY(sh->filter.alloc(sh->dev, nbuckets / 16));
         CUDA_TRY(cudaMemsetAsync(sh->filter.p, 0, nbuckets / 4, s));
-        sh->launches += launch_shard_owner_filter(s, dev_recv, nrecv, sh->filter.p, nbuckets, sh->sms);
+        TRY(zero_phase_stats(sh));
+        sh->launches += launch_stream_filter(s, dev_recv_keys, nrecv, sh->filter.p, nbuckets, sh->d_stats.p, sh->sms);
+        TRY(read_stats(sh));
+        cap = std::min(cap, std::max<uint64_t>(1024, 3 * sh->h_stats.found + 1024));
     }
-    uint64_t cap = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);
-    if (use_filter) cap = std::max<uint64_t>(1024, nrecv / 2 + 1024);  // retried bigger on overflow
-    TRY(sh->reply_slot.alloc(sh->dev, nrecv + 1));
     uint64_t singles = 0;
     for (int attempt = 0;; ++attempt) {
         if (cap * sh->world >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner table of %llu slots x %u ranks exceeds the 32-bit id space", (unsigned long long)cap, sh->world);
         if (sh->owner_table.n < cap) TRY(sh->owner_table.alloc(sh->dev, cap));
-        sh->owner_cap = cap;
         CUDA_TRY(cudaMemsetAsync(sh->owner_table.p, 0, cap * sizeof(NgramSlot), s));
         TRY(zero_phase_stats(sh));
-        sh->launches += launch_shard_merge(s, dev_recv, nrecv, sh->owner_table.p, cap, sh->reply_slot.p, sh->d_stats.p, sh->sms, use_filter ? sh->filter.p : nullptr, nbuckets);
+        sh->launches += launch_stream_count(s, dev_recv_keys, nrecv, sh->owner_table.p, cap, use_filter ? sh->filter.p : nullptr, nbuckets, (uint32_t*)dev_reply, sh->d_stats.p, sh->sms);
         CUDA_TRY(cudaMemcpyAsync(&sh->h_stats, sh->d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
-        if (sh->h_stats.errflags & kErrTableFull) {
+        if (sh->h_stats.errflags & kErrTableFull) {  // the estimate was too small: go again with twice the slots
             if (attempt >= 6) return set_err(COLIBRI_E_CAPACITY, "owner hash table overflow");
             CUDA_TRY(cudaMemsetAsync(&sh->d_stats.p->errflags, 0, sizeof(unsigned int), s));
             cap *= 2;
@@ -293,36 +297,73 @@ extern "C" int colibri_b200_shard_level_merge(colibri_b200_shard* sh, const void
         singles = sh->h_stats.singletons;
         break;
     }
+    const uint64_t sv_bound = (nrecv - singles) / std::max<uint32_t>(t, 1) + 1;
+    if (sh->sv_idx.n < sv_bound) TRY(sh->sv_idx.alloc(sh->dev, sv_bound));
+    if (sh->sv_cnt.n < sv_bound) TRY(sh->sv_cnt.alloc(sh->dev, sv_bound));
     if (sh->bitmap.n < cap / 32 + 8) TRY(sh->bitmap.alloc(sh->dev, cap / 32 + 8));
     TRY(zero_phase_stats(sh));
-    sh->launches += launch_shard_prune_owner(s, sh->owner_table.p, cap, sh->t, sh->bitmap.p, sh->d_stats.p, sh->sms);
-    sh->launches += launch_shard_reply(s, sh->reply_slot.p, nrecv, sh->owner_table.p, sh->bitmap.p, sh->world, sh->rank, dev_reply);
+    sh->launches += launch_prune_ngrams(s, sh->owner_table.p, cap, t, sh->sv_idx.p, sh->sv_cnt.p, sh->bitmap.p, sh->d_stats.p, sh->sms);
+    sh->launches += launch_owner_reply(s, (uint32_t*)dev_reply, nrecv, sh->bitmap.p, sh->world, sh->rank);
     TRY(read_stats(sh));
-    sh->h_stats.found += singles;  // a filtered record is a distinct n-gram with global count 1: found, and pruned
-    stats[0] = sh->h_stats.found;
-    stats[1] = sh->h_stats.kept;
-    stats[2] = sh->h_stats.kept_occ;
+    stats[0]  = sh->h_stats.found + singles;  // a filtered window is a distinct n-gram with global count 1: found, and pruned
+    stats[1]  = sh->h_stats.kept;
+    stats[2]  = sh->h_stats.kept_occ;
+    sh->nsurv = sh->h_stats.kept;
+    // how many survivor records go back to each source
+    sh->launches += launch_owner_survivor_counts(s, sh->sv_idx.p, sh->nsurv, sh->world, sh->d_aux.p, sh->d_aux.p + 195, sh->sms);
+    unsigned long long cnt[64];
+    CUDA_TRY(cudaMemcpyAsync(cnt, sh->d_aux.p + 195, sh->world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    unsigned long long obase[65];
+    uint64_t acc = 0;
+    for (uint32_t r = 0; r < sh->world; ++r) {
+        surv_counts[r]          = cnt[r];
+        sh->surv_out_counts[r]  = cnt[r];
+        obase[r]                = acc;
+        acc += cnt[r];
+    }
+    CUDA_TRY(cudaMemcpyAsync(sh->d_aux.p + 65, obase, sh->world * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     return 0;
 }
 
-// sender side: replies (send order) -> global ids per position; keeps the survivors this rank exports. local_valid = positions with a surviving n-gram
-extern "C" int colibri_b200_shard_level_finish(colibri_b200_shard* sh, const void* dev_reply_back, uint64_t* local_valid) {
-    if (!sh || (sh->nsent && !dev_reply_back)) return set_err(COLIBRI_E_INVALID, "NULL argument");
+// the survivor records, grouped by source rank: 8 bytes each {index inside the source's group, global count}
+extern "C" int colibri_b200_shard_level_owner_survivors(colibri_b200_shard* sh, void* dev_out) {
+    if (!sh || (!dev_out && sh->nsurv)) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    PhaseClock clk(sh, 4);
+    sh->launches += launch_owner_survivors(sh->s, sh->sv_idx.p, sh->sv_cnt.p, sh->nsurv, sh->world, sh->d_aux.p, sh->d_aux.p + 65, sh->d_aux.p + 130, dev_out, sh->sms);
+    CUDA_TRY(cudaStreamSynchronize(sh->s));
+    return 0;
+}
+
+// sender side: dev_reply_back = nsent u32 in send order; dev_surv = survivor records grouped by owner rank (surv_counts[world]).
+extern "C" int colibri_b200_shard_level_finish(colibri_b200_shard* sh, const void* dev_reply_back, const void* dev_surv, const uint64_t* surv_counts, uint64_t* local_valid) {
+    if (!sh || !surv_counts || (sh->nsent && !dev_reply_back)) return set_err(COLIBRI_E_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(sh->dev));
     PhaseClock clk(sh, 5);
     cudaStream_t s = sh->s;
     const int n = sh->level + 1;
-    if (sh->gid_of_slot.n < sh->local_cap) TRY(sh->gid_of_slot.alloc(sh->dev, sh->local_cap));
+    TRY(zero_phase_stats(sh));
+    CUDA_TRY(cudaMemsetAsync(sh->cur.p + sh->npos, 0, 8 * sizeof(uint32_t), s));
+    sh->launches += launch_sender_relabel(s, sh->rec_of_pos.p, (const uint32_t*)dev_reply_back, sh->npos, sh->cur.p, sh->d_stats.p, sh->sms);
+    uint64_t total = 0;
+    for (uint32_t g = 0; g < sh->world; ++g) total += surv_counts[g];
     Segment sg;
     sg.n = n;
-    TRY(sg.pos.alloc(sh->dev, sh->nsent + 1));
-    TRY(sg.cnt.alloc(sh->dev, sh->nsent + 1));
-    TRY(zero_phase_stats(sh));
-    sh->launches += launch_shard_apply(s, dev_reply_back, sh->send_slot.p, sh->nsent, sh->table.p, sh->gid_of_slot.p, sg.pos.p, sg.cnt.p, sh->d_stats.p, sh->sms);
-    sh->launches += launch_shard_relabel(s, sh->cur.p, sh->npos, sh->gid_of_slot.p, sh->d_stats.p, sh->sms);
+    if (total) {
+        if (!dev_surv) return set_err(COLIBRI_E_INVALID, "NULL survivor buffer");
+        TRY(sg.pos.alloc(sh->dev, total));
+        TRY(sg.cnt.alloc(sh->dev, total));
+        uint64_t off = 0;
+        for (uint32_t g = 0; g < sh->world; ++g) {
+            sh->launches += launch_sender_survivors(s, (const uint8_t*)dev_surv + off * 8, surv_counts[g], sh->pos_of_rec.p, sh->send_base[g], sg.pos.p + off, sg.cnt.p + off);
+            off += surv_counts[g];
+        }
+    }
     TRY(read_stats(sh));
-    sg.count = sh->h_stats.cursor;
-    if (sg.count) sh->segs.push_back(std::move(sg));
+    sg.count = total;
+    if (total) sh->segs.push_back(std::move(sg));
     sh->prev_valid = sh->h_stats.kept_occ;
     if (local_valid) *local_valid = sh->prev_valid;
     std::swap(sh->prev, sh->cur);

@@ -1,0 +1,347 @@
+// shard_kernels.cu -- device side of the multi-GPU path (nothing in the reference corresponds to this).
+//
+// "Ship the windows to their owners": a rank never aggregates keys it does not own.  Per level n >= 2
+//   sender  split      every valid window's 8-byte key goes into the send buffer of owner(key) = hash(key) mod G, with a STABLE
+//                      multi-split (corpus order inside every destination group).  rec_of_pos[p] remembers where window p went.
+//   [all-to-all of keys]
+//   owner   filter + count   exactly the single-GPU kernels, fed from the received key stream instead of a pair of id arrays:
+//                      occurrence filter in L2, HBM table for the rest, rid[i] = slot + 1 of received window i
+//           prune      threshold scan (the single-GPU kernel); owner_reply turns rid[] into global ids in place
+//   [all-to-all back, 4 bytes per window, same routes]
+//   sender  relabel    id[p] = reply[rec_of_pos[p]] -- G ascending read streams, no random HBM access on the sender at all
+// Survivors travel back as (index inside the sender's group, global count) to the rank whose window claimed the slot; that
+// rank owns the tokens and exports the pattern.  The only random HBM traffic of a level is the owner's table upserts -- the
+// same amount as on one GPU.
+#include "device_utils.cuh"
+#include "kernels.h"
+
+namespace colibri {
+
+static inline unsigned sk_div_up(uint64_t a, uint64_t b) {
+    return (unsigned)((a + b - 1) / b);
+}
+static inline uint64_t sk_min(uint64_t a, uint64_t b) {
+    return a < b ? a : b;
+}
+
+// Which rank owns a key.  Evaluated three times per position per level on the sender, so it is a cheap multiply-xorshift
+// mix (the table slot inside the owner still comes from SpookyV2); only uniformity over G ranks matters here.
+__device__ __forceinline__ uint32_t owner_of_key(unsigned long long key, uint32_t world) {
+    unsigned long long z = key * 0x9E3779B97F4A7C15ull;
+    z ^= z >> 32;
+    z *= 0xD6E8FEB86659FD93ull;
+    return (uint32_t)__umul64hi(z, (unsigned long long)world);
+}
+
+constexpr int      kSplitTile = 4096;  // positions per block: 8 warps x 512, each warp walks its slice in order
+constexpr uint32_t kNoRec     = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t window_dest(const uint32_t* __restrict__ prev, uint64_t p, uint64_t npos, uint32_t world, unsigned long long& key) {
+    if (p >= npos) return 256u;
+    uint32_t a = prev[p], b = prev[p + 1];
+    if (a == 0 || b == 0) return 256u;
+    key = ((unsigned long long)a << 32) | b;
+    return owner_of_key(key, world);
+}
+
+// pass 1: per block, windows per destination (destination-major so that one exclusive scan yields every block's bases)
+__global__ void __launch_bounds__(256) split_count_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t world, uint32_t nblocks, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t h[64];
+    if (threadIdx.x < 64) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * kSplitTile;
+#pragma unroll 4
+    for (int k = 0; k < kSplitTile / 256; ++k) {
+        unsigned long long key;
+        uint32_t           d = window_dest(prev, base + (uint64_t)k * 256 + threadIdx.x, npos, world, key);
+        if (d < 64) atomicAdd(&h[d], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < world) hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// pass 2: stable scatter.  send_keys is laid out [dest 0 | dest 1 | ...]; positions stay ascending inside a group.
+__global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t world, uint32_t nblocks, const uint64_t* __restrict__ hist_off,
+                                                          unsigned long long* __restrict__ send_keys, uint32_t* __restrict__ pos_of_rec, uint32_t* __restrict__ rec_of_pos) {
+    __shared__ uint32_t cnt[8][65];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    for (int i = threadIdx.x; i < 8 * 65; i += 256) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t wbase = (uint64_t)blockIdx.x * kSplitTile + (uint64_t)warp * (kSplitTile / 8);
+    for (int it = 0; it < kSplitTile / 8 / 32; ++it) {
+        unsigned long long key;
+        uint32_t           d = window_dest(prev, wbase + (uint64_t)it * 32 + lane, npos, world, key);
+        if (d > 64) d = 64;
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        if ((int)lane == __ffs(peers) - 1) cnt[warp][d] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        uint32_t run = 0;
+        for (int w = 0; w < 8; ++w) {
+            uint32_t c          = cnt[w][threadIdx.x];
+            cnt[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (int it = 0; it < kSplitTile / 8 / 32; ++it) {
+        const uint64_t     p = wbase + (uint64_t)it * 32 + lane;
+        unsigned long long key = 0;
+        uint32_t           d = window_dest(prev, p, npos, world, key);
+        const bool         act = d < 64;
+        if (d > 64) d = 64;
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t base  = cnt[warp][d];
+        __syncwarp();
+        if ((int)lane == __ffs(peers) - 1) cnt[warp][d] = base + __popc(peers);
+        __syncwarp();
+        if (act) {
+            uint64_t dst    = hist_off[(uint64_t)d * nblocks + blockIdx.x] + base + __popc(peers & ((1u << lane) - 1));
+            send_keys[dst]  = key;
+            pos_of_rec[dst] = (uint32_t)p;
+            rec_of_pos[p]   = (uint32_t)dst;
+        } else if (p < npos) {
+            rec_of_pos[p] = kNoRec;
+        }
+    }
+}
+
+// ---- owner side: the occurrence filter and the counting kernel over a received key stream -------------------------------
+__device__ __forceinline__ void stream_filter_locate(uint64_t h, uint64_t mask, uint64_t& word, uint32_t& shift) {
+    uint64_t bucket = h & mask;
+    word            = bucket >> 4;
+    shift           = (uint32_t)(bucket & 15) * 2;
+}
+
+__global__ void __launch_bounds__(256) stream_filter_kernel(const unsigned long long* __restrict__ keys, uint64_t n, uint32_t* __restrict__ filter, uint64_t nbuckets_mask,
+                                                            DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    uint32_t twice = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t word;
+        uint32_t shift;
+        stream_filter_locate(spooky_hash64_u64(__ldcs(keys + i), 0), nbuckets_mask, word, shift);
+        uint32_t bits = (__ldcg(filter + word) >> shift) & 3u;
+        if (bits == 3u) continue;
+        if ((bits & 1u) == 0) {
+            uint32_t old = atomicOr(filter + word, 1u << shift);
+            if (((old >> shift) & 1u) == 0) continue;
+            bits = (old >> shift) & 3u;
+        }
+        if ((bits & 2u) == 0) {
+            uint32_t old = atomicOr(filter + word, 2u << shift);
+            twice += ((old >> shift) & 2u) == 0;
+        }
+    }
+    uint64_t tw = block_reduce_sum(twice, scratch);
+    if (threadIdx.x == 0 && tw) atomicAdd(&st->found, (unsigned long long)tw);
+}
+
+__device__ __forceinline__ void sk_cas128(void* addr, unsigned long long new0, unsigned long long new1, unsigned long long& old0, unsigned long long& old1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b128 cmp, val, old;\n\t"
+        "mov.b128 cmp, {%3, %3};\n\t"
+        "mov.b128 val, {%4, %5};\n\t"
+        "atom.global.cas.b128 old, [%2], cmp, val;\n\t"
+        "mov.b128 {%0, %1}, old;\n\t"
+        "}"
+        : "=l"(old0), "=l"(old1)
+        : "l"(addr), "l"(0ull), "l"(new0), "l"(new1)
+        : "memory");
+}
+
+// rid[i] = slot + 1 of received window i (0: the filter proved it to be the only window of its key).  slot.pos = i of the claimer.
+__global__ void __launch_bounds__(256) stream_count_kernel(const unsigned long long* __restrict__ keys, uint64_t n, NgramSlot* __restrict__ table, uint64_t cap,
+                                                           const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, uint32_t* __restrict__ rid, DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    uint32_t       singles = 0;
+    bool           full    = false;
+    const uint64_t limit   = cap < 8192 ? cap : 8192;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = __ldcs(keys + i);
+        const uint64_t           h   = spooky_hash64_u64(key, 0);
+        uint32_t                 out = 0;
+        bool                     go  = true;
+        if (filter != nullptr) {
+            uint64_t word;
+            uint32_t shift;
+            stream_filter_locate(h, nbuckets_mask, word, shift);
+            go = ((__ldg(filter + word) >> shift) & 2u) != 0;
+            singles += !go;
+        }
+        if (go) {
+            uint64_t slot = fast_range(h, cap);
+            uint64_t step = 0;
+            for (; step < limit; ++step) {
+                NgramSlot*         s   = table + slot;
+                unsigned long long cur = __ldcg(&s->key);
+                if (cur == 0) {
+                    unsigned long long o0, o1;
+                    sk_cas128(s, key, 1ull | ((unsigned long long)(uint32_t)i << 32), o0, o1);
+                    if (o0 == 0) {
+                        out = (uint32_t)slot + 1;
+                        break;
+                    }
+                    cur = o0;
+                }
+                if (cur == key) {
+                    atomicAdd(&s->count, 1u);
+                    out = (uint32_t)slot + 1;
+                    break;
+                }
+                slot = slot + 1 == cap ? 0 : slot + 1;
+            }
+            if (out == 0) full = true;
+        }
+        __stcs(rid + i, out);
+    }
+    uint64_t sg = block_reduce_sum(singles, scratch);
+    if (threadIdx.x == 0 && sg) atomicAdd(&st->singletons, (unsigned long long)sg);
+    if (full) atomicOr(&st->errflags, kErrTableFull);
+}
+
+// rid[i] (slot + 1) -> global id of the surviving n-gram, 0 if pruned; in place, it becomes the reply buffer
+__global__ void __launch_bounds__(256) owner_reply_kernel(uint32_t* __restrict__ rid, uint64_t n, const uint32_t* __restrict__ bitmap, uint32_t world, uint32_t rank) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = rid[i];
+    if (s == 0) return;
+    rid[i] = ((__ldg(bitmap + ((s - 1) >> 5)) >> ((s - 1) & 31)) & 1u) ? (s - 1) * world + rank + 1 : 0u;
+}
+
+// survivors (claimer's receive index, global count) -> per source rank: (index inside that source's group, count).
+// src_base[r] = first receive index of source r (G+1 entries).  One atomic per destination per 2048-survivor tile.
+__global__ void __launch_bounds__(256) owner_survivors_kernel(const uint32_t* __restrict__ sv_idx, const uint32_t* __restrict__ sv_count, uint64_t n, uint32_t world,
+                                                              const unsigned long long* __restrict__ src_base, const unsigned long long* __restrict__ out_base,
+                                                              unsigned long long* __restrict__ cursors, uint2* __restrict__ out) {
+    __shared__ uint32_t tile_cnt[64];
+    __shared__ unsigned long long tile_base[64];
+    __shared__ unsigned long long sbase[65];
+    if (threadIdx.x <= world) sbase[threadIdx.x] = src_base[threadIdx.x];
+    const uint64_t ntiles = (n + 2047) / 2048;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x < 64) tile_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t idx[8], cnt[8], src[8], rk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint64_t i = tile * 2048 + (uint64_t)k * 256 + threadIdx.x;
+            src[k]     = 0xFFFFFFFFu;
+            if (i < n) {
+                idx[k] = sv_idx[i];
+                cnt[k] = sv_count[i];
+                uint32_t r = 0;
+                while (r + 1 < world && (unsigned long long)idx[k] >= sbase[r + 1]) ++r;
+                src[k] = r;
+                rk[k]  = atomicAdd(&tile_cnt[r], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < world) {
+            uint32_t c = tile_cnt[threadIdx.x];
+            tile_base[threadIdx.x] = c ? out_base[threadIdx.x] + atomicAdd(&cursors[threadIdx.x], (unsigned long long)c) : 0ull;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (src[k] != 0xFFFFFFFFu) out[tile_base[src[k]] + rk[k]] = make_uint2((uint32_t)(idx[k] - sbase[src[k]]), cnt[k]);
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) owner_survivor_counts_kernel(const uint32_t* __restrict__ sv_idx, uint64_t n, uint32_t world, const unsigned long long* __restrict__ src_base,
+                                                                    unsigned long long* __restrict__ counts) {
+    __shared__ uint32_t h[64];
+    __shared__ unsigned long long sbase[65];
+    if (threadIdx.x < 64) h[threadIdx.x] = 0;
+    if (threadIdx.x <= world) sbase[threadIdx.x] = src_base[threadIdx.x];
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t v = sv_idx[i], r = 0;
+        while (r + 1 < world && (unsigned long long)v >= sbase[r + 1]) ++r;
+        atomicAdd(&h[r], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < world && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+// ---- sender side --------------------------------------------------------------------------------------------------------
+// id[p] = reply[rec_of_pos[p]]: inside every destination group the records are in corpus order, so this reads G ascending streams
+__global__ void __launch_bounds__(256) sender_relabel_kernel(const uint32_t* __restrict__ rec_of_pos, const uint32_t* __restrict__ reply, uint64_t npos, uint32_t* __restrict__ cur,
+                                                             DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    uint32_t valid = 0;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t j  = __ldcs(rec_of_pos + p);
+        uint32_t id = j == kNoRec ? 0u : __ldg(reply + j);
+        __stcs(cur + p, id);
+        valid += id != 0;
+    }
+    uint64_t v = block_reduce_sum(valid, scratch);
+    if (threadIdx.x == 0 && v) atomicAdd(&st->kept_occ, (unsigned long long)v);
+}
+// received survivor records of owner group g: (index inside my send group to g, global count) -> (position, count)
+__global__ void __launch_bounds__(256) sender_survivors_kernel(const uint2* __restrict__ recs, uint64_t n, const uint32_t* __restrict__ pos_of_rec, uint64_t send_base,
+                                                               uint32_t* __restrict__ sv_pos, uint32_t* __restrict__ sv_count) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint2 r     = recs[i];
+    sv_pos[i]   = pos_of_rec[send_base + r.x];
+    sv_count[i] = r.y;
+}
+
+// ---- launchers ------------------------------------------------------------------------------------------------------------
+int launch_split_count(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, uint32_t* hist /* world x nblocks */) {
+    uint32_t nblocks = sk_div_up(npos, kSplitTile);
+    split_count_kernel<<<nblocks, 256, 0, s>>>(prev, npos, world, nblocks, hist);
+    return 1;
+}
+int launch_split_write(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, const uint64_t* hist_off, void* send_keys, uint32_t* pos_of_rec, uint32_t* rec_of_pos) {
+    uint32_t nblocks = sk_div_up(npos, kSplitTile);
+    split_write_kernel<<<nblocks, 256, 0, s>>>(prev, npos, world, nblocks, hist_off, (unsigned long long*)send_keys, pos_of_rec, rec_of_pos);
+    return 1;
+}
+int launch_stream_filter(cudaStream_t s, const void* keys, uint64_t n, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms) {
+    if (!n) return 0;
+    unsigned grid = (unsigned)sk_min(sk_div_up(n, 256), (uint64_t)sms * 32);
+    stream_filter_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)keys, n, filter, nbuckets - 1, st);
+    return 1;
+}
+int launch_stream_count(cudaStream_t s, const void* keys, uint64_t n, NgramSlot* table, uint64_t cap, const uint32_t* filter, uint64_t nbuckets, uint32_t* rid, DeviceStats* st, int sms) {
+    if (!n) return 0;
+    unsigned grid = (unsigned)sk_min(sk_div_up(n, 256), (uint64_t)sms * 32);
+    stream_count_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)keys, n, table, cap, filter, nbuckets ? nbuckets - 1 : 0, rid, st);
+    return 1;
+}
+int launch_owner_reply(cudaStream_t s, uint32_t* rid, uint64_t n, const uint32_t* bitmap, uint32_t world, uint32_t rank) {
+    if (!n) return 0;
+    owner_reply_kernel<<<sk_div_up(n, 256), 256, 0, s>>>(rid, n, bitmap, world, rank);
+    return 1;
+}
+int launch_owner_survivor_counts(cudaStream_t s, const uint32_t* sv_idx, uint64_t n, uint32_t world, const unsigned long long* src_base, unsigned long long* counts, int sms) {
+    if (!n) return 0;
+    unsigned grid = (unsigned)sk_min(sk_div_up(n, 256), (uint64_t)sms * 8);
+    owner_survivor_counts_kernel<<<grid, 256, 0, s>>>(sv_idx, n, world, src_base, counts);
+    return 1;
+}
+int launch_owner_survivors(cudaStream_t s, const uint32_t* sv_idx, const uint32_t* sv_count, uint64_t n, uint32_t world, const unsigned long long* src_base,
+                           const unsigned long long* out_base, unsigned long long* cursors, void* out, int sms) {
+    if (!n) return 0;
+    unsigned grid = (unsigned)sk_min(sk_div_up(n, 2048), (uint64_t)sms * 4);
+    owner_survivors_kernel<<<grid, 256, 0, s>>>(sv_idx, sv_count, n, world, src_base, out_base, cursors, (uint2*)out);
+    return 1;
+}
+int launch_sender_relabel(cudaStream_t s, const uint32_t* rec_of_pos, const uint32_t* reply, uint64_t npos, uint32_t* cur, DeviceStats* st, int sms) {
+    unsigned grid = (unsigned)sk_min(sk_div_up(npos, 256), (uint64_t)sms * 16);
+    sender_relabel_kernel<<<grid ? grid : 1, 256, 0, s>>>(rec_of_pos, reply, npos, cur, st);
+    return 1;
+}
+int launch_sender_survivors(cudaStream_t s, const void* recs, uint64_t n, const uint32_t* pos_of_rec, uint64_t send_base, uint32_t* sv_pos, uint32_t* sv_count) {
+    if (!n) return 0;
+    sender_survivors_kernel<<<sk_div_up(n, 256), 256, 0, s>>>((const uint2*)recs, n, pos_of_rec, send_base, sv_pos, sv_count);
+    return 1;
+}
+
+}  // namespace colibri

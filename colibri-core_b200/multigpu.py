@@ -3,10 +3,11 @@
 The library (csrc/shard.cu) exposes each rank's work as phases with plain device pointers; this module is the plumbing
 between them: torch.distributed collectives over NCCL/NVLink (gloo on CPU in the tests, with a stand-in engine).
 
-Per level n >= 2:
-    level_count -> level_pack -> all_to_all(16-byte records) -> level_merge -> all_to_all(8-byte replies) -> level_finish
+Per level n >= 2, "ship the windows to their owners":
+    level_split (count, write) -> all_to_all(8-byte keys) -> level_owner (filter + count + prune on the received stream)
+    -> all_to_all back (4-byte global ids, same routes) + all_to_all(8-byte survivor records) -> level_finish
 Level 1 is an all-reduce of the class histograms.  Every rank ends with its own share of the surviving patterns
-(the rank that first delivered a pattern to its owner exports it, with the global count).
+(the rank whose window claimed a pattern's slot at the owner exports it, with the global count).
 """
 from __future__ import annotations
 
@@ -47,7 +48,7 @@ class CudaShardEngine:
     def phase_ms(self):
         out = (C.c_double * 8)()
         self._check(self.lib.colibri_b200_shard_phase_ms(self._h, out))
-        return dict(zip(["tokenise", "unigrams", "count", "pack", "merge", "finish", "export"], [float(x) for x in out]))
+        return dict(zip(["tokenise", "unigrams", "split_count", "split_write", "owner", "finish", "export"], [float(x) for x in out]))
 
     def unigram_counts(self, nclasses):
         buf = self.new_buffer(nclasses)
@@ -59,26 +60,35 @@ class CudaShardEngine:
         self._check(self.lib.colibri_b200_shard_unigram_finish(self._h, global_counts.data_ptr(), global_tokens, st))
         return tuple(int(x) for x in st)
 
-    def level_count(self, n):
-        dest = (C.c_uint64 * self.world)()
-        st = (C.c_uint64 * 2)()
-        self._check(self.lib.colibri_b200_shard_level_count(self._h, n, dest, st))
-        return [int(x) for x in dest], int(st[0]), int(st[1])
+    def level_split_count(self, n):
+        counts = (C.c_uint64 * self.world)()
+        w = C.c_uint64()
+        self._check(self.lib.colibri_b200_shard_level_split_count(self._h, n, counts, C.byref(w)))
+        return [int(x) for x in counts], int(w.value)
 
-    def level_pack(self, nsend):
-        buf = self.new_buffer(nsend * 4)
-        self._check(self.lib.colibri_b200_shard_level_pack(self._h, buf.data_ptr()))
+    def level_split_write(self, nsend):
+        buf = self.new_buffer(nsend * 2)
+        self._check(self.lib.colibri_b200_shard_level_split_write(self._h, buf.data_ptr()))
         return buf
 
-    def level_merge(self, recv, nrecv):
-        reply = self.new_buffer(nrecv * 2)
+    def level_owner(self, recv, recv_counts):
+        nrecv = sum(recv_counts)
+        reply = self.new_buffer(nrecv)
+        rc = (C.c_uint64 * self.world)(*recv_counts)
         st = (C.c_uint64 * 3)()
-        self._check(self.lib.colibri_b200_shard_level_merge(self._h, recv.data_ptr(), nrecv, reply.data_ptr(), st))
-        return reply, tuple(int(x) for x in st)
+        sc = (C.c_uint64 * self.world)()
+        self._check(self.lib.colibri_b200_shard_level_owner(self._h, recv.data_ptr(), rc, reply.data_ptr(), st, sc))
+        return reply, tuple(int(x) for x in st), [int(x) for x in sc]
 
-    def level_finish(self, reply_back):
+    def level_owner_survivors(self, nsurv):
+        buf = self.new_buffer(nsurv * 2)
+        self._check(self.lib.colibri_b200_shard_level_owner_survivors(self._h, buf.data_ptr()))
+        return buf
+
+    def level_finish(self, reply_back, surv, surv_counts):
         v = C.c_uint64()
-        self._check(self.lib.colibri_b200_shard_level_finish(self._h, reply_back.data_ptr(), C.byref(v)))
+        sc = (C.c_uint64 * self.world)(*surv_counts)
+        self._check(self.lib.colibri_b200_shard_level_finish(self._h, reply_back.data_ptr(), surv.data_ptr(), sc, C.byref(v)))
         return int(v.value)
 
     def finish(self, passes, types, maxn, minn):
@@ -164,23 +174,25 @@ def train_distributed(engine, dist, torch, mintokens=2, maxlength=5):
     prev_kept = kept
     n = 2
     while found and n <= maxlength and prev_kept > 0:
-        dest_counts, _windows, nsend = engine.level_count(n)
-        sw.lap("level_count")
-        send = engine.level_pack(nsend)
-        sw.lap("level_pack")
-        recv, recv_counts = _exchange(dist, torch, engine, send, dest_counts, 4)
-        sw.lap("a2a_records")
-        reply, (f, k, occ) = engine.level_merge(recv, sum(recv_counts))
-        sw.lap("level_merge")
+        send_counts, nsend = engine.level_split_count(n)
+        sw.lap("split_count")
+        send = engine.level_split_write(nsend)
+        sw.lap("split_write")
+        recv, recv_counts = _exchange(dist, torch, engine, send, send_counts, 2)
+        sw.lap("a2a_keys")
+        reply, (f, k, occ), surv_counts = engine.level_owner(recv, recv_counts)
+        surv = engine.level_owner_survivors(sum(surv_counts))
+        sw.lap("owner")
         # replies travel back along the same routes: what I received from rank r goes back to r
-        nrep, nback = sum(recv_counts) * 2, nsend * 2
-        back = engine.new_buffer(nback)
-        dist.all_to_all_single(back[:nback], reply[:nrep], output_split_sizes=[c * 2 for c in dest_counts], input_split_sizes=[c * 2 for c in recv_counts])
+        nrep = sum(recv_counts)
+        back = engine.new_buffer(nsend)
+        dist.all_to_all_single(back[:nsend], reply[:nrep], output_split_sizes=send_counts, input_split_sizes=recv_counts)
+        surv_recv, surv_recv_counts = _exchange(dist, torch, engine, surv, surv_counts, 2)
         st = torch.tensor([f, k, occ], dtype=torch.int64, device=dev)
         dist.all_reduce(st, op=dist.ReduceOp.SUM)
         engine.sync()
         sw.lap("a2a_replies")
-        engine.level_finish(back)
+        engine.level_finish(back, surv_recv, surv_recv_counts)
         sw.lap("level_finish")
         gf, gk, _gocc = (int(x) for x in st.tolist())
         if gf == 0:
@@ -193,8 +205,8 @@ def train_distributed(engine, dist, torch, mintokens=2, maxlength=5):
         passes = [(1, sum(p[1] for p in passes), 0, sum(p[3] for p in passes))]
     model = engine.finish(passes, types, maxn, minn)
     sw.lap("export")
-    if sw.on and dist.get_rank() == 0:
-        print("TRACE rank0 ms:", {k: round(v, 2) for k, v in sw.acc.items()}, flush=True)
+    if sw.on:
+        print("TRACE rank%d ms:" % dist.get_rank(), {k: round(v, 2) for k, v in sw.acc.items()}, "device phases:", {k: round(v, 2) for k, v in engine.phase_ms().items()}, flush=True)
     return model, passes, {"tokens": global_tokens, "types": types, "maxn": maxn, "minn": minn}
 
 

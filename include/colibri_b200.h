@@ -135,8 +135,9 @@ int colibri_b200_model_level_counters(const colibri_b200_model* m, int n, double
  * (torch.distributed / NCCL all-to-all); the library does no communication.  Model = hash-partitioned across ranks,
  * corpus = sharded at sentence boundaries (nothing in the reference corresponds to this).
  * Order per rank: shard_begin, shard_unigram_counts, [all-reduce SUM of the u32 counts], shard_unigram_finish, then for
- * n = 2.. : shard_level_count, shard_level_pack, [all-to-all of 16-byte records], shard_level_merge,
- * [all-to-all back of 8-byte replies], shard_level_finish; finally shard_finish. */
+ * n = 2.. : shard_level_split_count, shard_level_split_write, [all-to-all of 8-byte keys], shard_level_owner,
+ * shard_level_owner_survivors, [all-to-all back of 4-byte replies, all-to-all of 8-byte survivor records],
+ * shard_level_finish; finally shard_finish. */
 typedef struct colibri_b200_shard colibri_b200_shard;
 int    colibri_b200_shard_begin(colibri_b200_corpus* corpus, const colibri_b200_options* opt, int rank, int world, colibri_b200_shard** out);
 /* out[0]=local tokens, out[1]=local maximum class, out[2]=positions, out[3]=kernel launches so far */
@@ -147,12 +148,14 @@ int    colibri_b200_shard_phase_ms(const colibri_b200_shard* sh, double out[8]);
 int    colibri_b200_shard_unigram_counts(colibri_b200_shard* sh, uint32_t nclasses, void* dev_counts /* u32[nclasses] */);
 /* stats[0]=distinct unigrams (global), [1]=kept, [2]=occurrences kept */
 int    colibri_b200_shard_unigram_finish(colibri_b200_shard* sh, const void* dev_global_counts, uint64_t global_tokens, uint64_t stats[3]);
-/* dest_counts[world]: records this rank sends to each owner; stats[0]=valid windows, [1]=distinct local keys */
-int    colibri_b200_shard_level_count(colibri_b200_shard* sh, int n, uint64_t* dest_counts, uint64_t stats[2]);
-int    colibri_b200_shard_level_pack(colibri_b200_shard* sh, void* dev_send /* 16 B per record, grouped by owner */);
-/* stats[0]=distinct keys owned, [1]=kept, [2]=occurrences kept (this owner) */
-int    colibri_b200_shard_level_merge(colibri_b200_shard* sh, const void* dev_recv, uint64_t nrecv, void* dev_reply /* 8 B per record */, uint64_t stats[3]);
-int    colibri_b200_shard_level_finish(colibri_b200_shard* sh, const void* dev_reply_back, uint64_t* local_valid);
+/* send_counts[world]: valid windows of level n whose key is owned by each rank; *windows = their sum */
+int    colibri_b200_shard_level_split_count(colibri_b200_shard* sh, int n, uint64_t* send_counts, uint64_t* windows);
+int    colibri_b200_shard_level_split_write(colibri_b200_shard* sh, void* dev_send_keys /* 8 B per window, grouped by owner */);
+/* recv_counts[world] per source; dev_reply: one u32 per received window; stats[0]=distinct keys owned, [1]=kept, [2]=occurrences kept;
+ * surv_counts[world]: survivor records to return to each source */
+int    colibri_b200_shard_level_owner(colibri_b200_shard* sh, const void* dev_recv_keys, const uint64_t* recv_counts, void* dev_reply, uint64_t stats[3], uint64_t* surv_counts);
+int    colibri_b200_shard_level_owner_survivors(colibri_b200_shard* sh, void* dev_out /* 8 B per record, grouped by source */);
+int    colibri_b200_shard_level_finish(colibri_b200_shard* sh, const void* dev_reply_back, const void* dev_surv, const uint64_t* surv_counts /* per owner */, uint64_t* local_valid);
 /* passes: npasses x {n, found, foundskip, pruned} global numbers; the returned model holds THIS RANK'S share of the patterns */
 int    colibri_b200_shard_finish(colibri_b200_shard* sh, const uint64_t* passes, int npasses, uint64_t global_types, int maxn, int minn, colibri_b200_model** out);
 void   colibri_b200_shard_free(colibri_b200_shard* sh);

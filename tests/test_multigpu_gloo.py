@@ -57,53 +57,72 @@ class NumpyShardEngine:
     def _owner(self, a, b):
         return (a * 1000003 + b * 7919) % self.world
 
-    def level_count(self, n):
-        self.local, self.cur = {}, np.zeros(len(self.tok), dtype=np.int64)
+    def level_split_count(self, n):
+        """valid windows grouped by owner, corpus order inside a group (same contract as the CUDA split kernels)"""
+        groups = [[] for _ in range(self.world)]
         for p in range(len(self.tok) - 1):
             a, b = int(self.prev[p]), int(self.prev[p + 1])
             if a and b:
-                e = self.local.setdefault((a, b), [0, p, len(self.local)])
-                e[0] += 1
-                self.cur[p] = e[2] + 1
-        self.order = sorted(self.local.items(), key=lambda kv: (self._owner(*kv[0]), kv[1][2]))
-        dest = [0] * self.world
-        for (a, b), _ in self.order:
-            dest[self._owner(a, b)] += 1
-        return dest, int((self.cur != 0).sum()), len(self.local)
+                groups[self._owner(a, b)].append(p)
+        self.groups = groups
+        self.send_base = np.concatenate([[0], np.cumsum([len(g) for g in groups])]).astype(np.int64)
+        return [len(g) for g in groups], int(self.send_base[-1])
 
-    def level_pack(self, nsend):
-        rec = np.zeros((max(nsend, 1), 4), dtype=np.uint32)
-        for j, ((a, b), (cnt, _pos, slot)) in enumerate(self.order):
-            rec[j] = (b, a, cnt, slot)  # key = a << 32 | b, little-endian words
+    def level_split_write(self, nsend):
+        rec = np.zeros((max(nsend, 1), 2), dtype=np.uint32)
+        j = 0
+        for g in self.groups:
+            for p in g:
+                rec[j] = (int(self.prev[p + 1]), int(self.prev[p]))  # key = a << 32 | b, little-endian words
+                j += 1
         return torch.from_numpy(rec.view(np.int32).reshape(-1))
 
-    def level_merge(self, recv, nrecv):
-        rec = recv.numpy().view(np.uint32)[: nrecv * 4].reshape(-1, 4)
-        owner = {}
-        slots = []
+    def level_owner(self, recv, recv_counts):
+        nrecv = sum(recv_counts)
+        rec = recv.numpy().view(np.uint32)[: nrecv * 2].reshape(-1, 2)
+        table, rid = {}, []
         for i in range(nrecv):
-            key = (int(rec[i, 1]), int(rec[i, 0]))
-            e = owner.setdefault(key, [0, i, len(owner)])
-            e[0] += int(rec[i, 2])
-            slots.append(e)
-        reply = np.zeros((max(nrecv, 1), 2), dtype=np.uint32)
-        for i, e in enumerate(slots):
+            e = table.setdefault((int(rec[i, 1]), int(rec[i, 0])), [0, i, len(table)])
+            e[0] += 1
+            rid.append(e)
+        reply = np.zeros(max(nrecv, 1), dtype=np.uint32)
+        for i, e in enumerate(rid):
             if e[0] >= self.t:
-                reply[i] = (e[2] * self.world + self.rank + 1, e[0] if e[1] == i else 0)
-        kept = [e for e in owner.values() if e[0] >= self.t]
-        return torch.from_numpy(reply.view(np.int32).reshape(-1)), (len(owner), len(kept), sum(e[0] for e in kept))
+                reply[i] = e[2] * self.world + self.rank + 1
+        kept = [e for e in table.values() if e[0] >= self.t]
+        src_base = np.concatenate([[0], np.cumsum(recv_counts)])
+        self.surv = [[] for _ in range(self.world)]
+        for e in kept:
+            src = int(np.searchsorted(src_base, e[1], side="right") - 1)
+            self.surv[src].append((e[1] - int(src_base[src]), e[0]))
+        return torch.from_numpy(reply.view(np.int32)), (len(table), len(kept), sum(e[0] for e in kept)), [len(x) for x in self.surv]
 
-    def level_finish(self, reply_back):
+    def level_owner_survivors(self, nsurv):
+        rec = np.zeros((max(nsurv, 1), 2), dtype=np.uint32)
+        j = 0
+        for grp in self.surv:
+            for idx, cnt in grp:
+                rec[j] = (idx, cnt)
+                j += 1
+        return torch.from_numpy(rec.view(np.int32).reshape(-1))
+
+    def level_finish(self, reply_back, surv, surv_counts):
         n = self.level + 1
-        rep = reply_back.numpy().view(np.uint32)[: len(self.order) * 2].reshape(-1, 2)
-        gid = np.zeros(len(self.local) + 1, dtype=np.int64)
-        for j, (_key, (_cnt, pos, slot)) in enumerate(self.order):
-            gid[slot] = int(rep[j, 0])
-            if rep[j, 1]:
-                self.segs.append((n, pos, int(rep[j, 1])))
-        self.cur = np.where(self.cur != 0, gid[np.maximum(self.cur - 1, 0)], 0)
-        self.prev, self.level = self.cur, n
-        return int((self.cur != 0).sum())
+        rep = reply_back.numpy().view(np.uint32)
+        cur = np.zeros(len(self.tok), dtype=np.int64)
+        j = 0
+        for g in self.groups:
+            for p in g:
+                cur[p] = int(rep[j])
+                j += 1
+        srec = surv.numpy().view(np.uint32)[: sum(surv_counts) * 2].reshape(-1, 2)
+        k = 0
+        for owner, c in enumerate(surv_counts):
+            for _ in range(c):
+                self.segs.append((n, self.groups[owner][int(srec[k, 0])], int(srec[k, 1])))
+                k += 1
+        self.prev, self.level = cur, n
+        return int((cur != 0).sum())
 
     def finish(self, passes, types, maxn, minn):
         import oracle

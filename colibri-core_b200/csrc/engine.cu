@@ -47,7 +47,7 @@ static int corpus_alloc(colibri_b200_corpus* c, int device, size_t nbytes) {
     if (device < 0 || device >= ndev) return set_err(COLIBRI_E_INVALID, "device %d out of range (have %d)", device, ndev);
     CUDA_TRY(cudaSetDevice(device));
     // the tables are probed one 32-byte sector at a time at random addresses: ask L2 not to fetch the neighbouring sector too
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, getenv("COLIBRI_B200_L2_FETCH") ? (size_t)atoi(getenv("COLIBRI_B200_L2_FETCH")) : 32);
     cudaGetLastError();
     c->device = device;
     c->nbytes = nbytes;
@@ -469,8 +469,9 @@ int Trainer::run() {
         const bool use_filter = t >= 2 && bound >= (1ull << 25) && !getenv("COLIBRI_B200_NO_FILTER");
         uint64_t   nbuckets = 0, cap = 0;
         if (use_filter) {
+            static const int max_log2 = getenv("COLIBRI_B200_FILTER_LOG2") ? atoi(getenv("COLIBRI_B200_FILTER_LOG2")) : 28;
             nbuckets = 1ull << 20;
-            while (nbuckets < 2 * bound && nbuckets < (1ull << 28)) nbuckets <<= 1;  // <= 64 MB of 2-bit counters: L2 resident
+            while (nbuckets < 2 * bound && nbuckets < (1ull << max_log2)) nbuckets <<= 1;  // <= 64 MB of 2-bit counters: L2 resident
             if (filter.n < nbuckets / 16) TRY(filter.alloc(dev, nbuckets / 16));
             int hf = timer.begin(COLIBRI_T_COUNT, n);
             CUDA_TRY(cudaMemsetAsync(filter.p, 0, nbuckets / 4, s));

@@ -107,6 +107,11 @@ def library():
     L.colibri_b200_shard_level_owner.argtypes = [C.c_void_p, C.c_void_p, _u64p, C.c_void_p, _u64p, _u64p]
     L.colibri_b200_shard_level_owner_survivors.argtypes = [C.c_void_p, C.c_void_p]
     L.colibri_b200_shard_level_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _u64p, _u64p]
+    L.colibri_b200_shard_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.colibri_b200_shard_set_peers.argtypes = [C.c_void_p, _u64p, _u64p, _u64p, _u64p, C.c_uint64, C.c_uint64]
+    L.colibri_b200_shard_p2p_split.argtypes = [C.c_void_p, C.c_int, _u64p]
+    L.colibri_b200_shard_p2p_owner.argtypes = [C.c_void_p, _u64p]
+    L.colibri_b200_shard_p2p_finish.argtypes = [C.c_void_p, _u64p, _u64p]
     L.colibri_b200_shard_finish.argtypes = [C.c_void_p, _u64p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.colibri_b200_shard_free.argtypes = [C.c_void_p]
     L.colibri_b200_shard_free.restype = None

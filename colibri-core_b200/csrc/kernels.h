@@ -108,10 +108,18 @@ int launch_refs_from_positions(cudaStream_t s, const uint32_t* pos, uint64_t n, 
 
 // ---- multi-GPU phases (hash-partitioned model): shard_kernels.cu, driven by shard.cu
 int launch_split_count(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, uint32_t* hist /* world x ceil(npos/4096), destination-major */);
-int launch_split_write(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, const uint64_t* hist_off, void* send_keys, uint32_t* pos_of_rec, uint32_t* rec_of_pos);
-int launch_stream_filter(cudaStream_t s, const void* keys, uint64_t n, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms);
-int launch_stream_count(cudaStream_t s, const void* keys, uint64_t n, NgramSlot* table, uint64_t cap, const uint32_t* filter, uint64_t nbuckets, uint32_t* rid, DeviceStats* st, int sms);
-int launch_owner_reply(cudaStream_t s, uint32_t* rid, uint64_t n, const uint32_t* bitmap, uint32_t world, uint32_t rank);
+// peer_* != NULL selects the NVLink peer-store variants (symmetric-memory receive slots of slot_cap entries per source rank)
+int launch_split_write(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, const uint64_t* hist_off, void* send_keys, uint32_t* pos_of_rec, uint32_t* rec_of_pos,
+                       void* const* peer_keys = nullptr, uint32_t my_rank = 0, uint64_t slot_cap = 0);
+int launch_stream_filter(cudaStream_t s, const void* keys, uint64_t n, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms, uint64_t slot_cap = 0,
+                         const unsigned long long* slot_counts = nullptr);
+int launch_stream_count(cudaStream_t s, const void* keys, uint64_t n, NgramSlot* table, uint64_t cap, const uint32_t* filter, uint64_t nbuckets, uint32_t* rid, DeviceStats* st, int sms,
+                        uint64_t slot_cap = 0, const unsigned long long* slot_counts = nullptr);
+int launch_owner_reply(cudaStream_t s, uint32_t* rid, uint64_t n, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* const* peer_reply = nullptr, uint64_t slot_cap = 0,
+                       const unsigned long long* slot_counts = nullptr);
+int launch_owner_survivors_p2p(cudaStream_t s, const uint32_t* sv_idx, const uint32_t* sv_count, uint64_t n, uint32_t world, uint32_t rank, uint64_t slot_cap, uint64_t surv_cap,
+                               unsigned long long* cursors, void* const* peer_surv, DeviceStats* st, int sms);
+int launch_p2p_publish(cudaStream_t s, void* const* peer_hdr, uint32_t world, uint64_t offset, const unsigned long long* vals /* world x nvals */, uint32_t nvals);
 int launch_owner_survivor_counts(cudaStream_t s, const uint32_t* sv_idx, uint64_t n, uint32_t world, const unsigned long long* src_base, unsigned long long* counts, int sms);
 int launch_owner_survivors(cudaStream_t s, const uint32_t* sv_idx, const uint32_t* sv_count, uint64_t n, uint32_t world, const unsigned long long* src_base,
                            const unsigned long long* out_base, unsigned long long* cursors, void* out, int sms);

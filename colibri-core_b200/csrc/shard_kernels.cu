@@ -61,8 +61,11 @@ __global__ void __launch_bounds__(256) split_count_kernel(const uint32_t* __rest
 }
 
 // pass 2: stable scatter.  send_keys is laid out [dest 0 | dest 1 | ...]; positions stay ascending inside a group.
+// P2P mode (peer_keys != NULL): the key is stored straight into the owner's receive slot for this rank over NVLink
+// (peer_keys[d] = base of rank d's receive buffer, slot of source r at r * slot_cap) -- the pack and the all-to-all are one kernel.
 __global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t world, uint32_t nblocks, const uint64_t* __restrict__ hist_off,
-                                                          unsigned long long* __restrict__ send_keys, uint32_t* __restrict__ pos_of_rec, uint32_t* __restrict__ rec_of_pos) {
+                                                          unsigned long long* __restrict__ send_keys, uint32_t* __restrict__ pos_of_rec, uint32_t* __restrict__ rec_of_pos,
+                                                          unsigned long long* const* __restrict__ peer_keys, uint32_t my_rank, uint64_t slot_cap) {
     __shared__ uint32_t cnt[8][65];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     for (int i = threadIdx.x; i < 8 * 65; i += 256) (&cnt[0][0])[i] = 0;
@@ -99,9 +102,15 @@ __global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __rest
         __syncwarp();
         if (act) {
             uint64_t dst    = hist_off[(uint64_t)d * nblocks + blockIdx.x] + base + __popc(peers & ((1u << lane) - 1));
-            send_keys[dst]  = key;
             pos_of_rec[dst] = (uint32_t)p;
-            rec_of_pos[p]   = (uint32_t)dst;
+            if (peer_keys != nullptr) {
+                uint64_t k = dst - hist_off[(uint64_t)d * nblocks];  // index inside the group of owner d
+                peer_keys[d][(uint64_t)my_rank * slot_cap + k] = key;
+                rec_of_pos[p] = (uint32_t)((uint64_t)d * slot_cap + k);  // where the reply will appear in my own reply slots
+            } else {
+                send_keys[dst] = key;
+                rec_of_pos[p]  = (uint32_t)dst;
+            }
         } else if (p < npos) {
             rec_of_pos[p] = kNoRec;
         }
@@ -115,11 +124,19 @@ __device__ __forceinline__ void stream_filter_locate(uint64_t h, uint64_t mask, 
     shift           = (uint32_t)(bucket & 15) * 2;
 }
 
+// slotted input (P2P mode, slot_cap != 0): the buffer is G slots of slot_cap keys, slot r holds slot_counts[r] keys of source r
+__device__ __forceinline__ bool slot_valid(uint64_t i, uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts) {
+    if (slot_cap == 0) return true;
+    uint64_t src = i / slot_cap;
+    return i - src * slot_cap < __ldg(slot_counts + src);
+}
+
 __global__ void __launch_bounds__(256) stream_filter_kernel(const unsigned long long* __restrict__ keys, uint64_t n, uint32_t* __restrict__ filter, uint64_t nbuckets_mask,
-                                                            DeviceStats* __restrict__ st) {
+                                                            DeviceStats* __restrict__ st, uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts) {
     __shared__ uint64_t scratch[8];
     uint32_t twice = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (!slot_valid(i, slot_cap, slot_counts)) continue;
         uint64_t word;
         uint32_t shift;
         stream_filter_locate(spooky_hash64_u64(__ldcs(keys + i), 0), nbuckets_mask, word, shift);
@@ -155,12 +172,17 @@ __device__ __forceinline__ void sk_cas128(void* addr, unsigned long long new0, u
 
 // rid[i] = slot + 1 of received window i (0: the filter proved it to be the only window of its key).  slot.pos = i of the claimer.
 __global__ void __launch_bounds__(256) stream_count_kernel(const unsigned long long* __restrict__ keys, uint64_t n, NgramSlot* __restrict__ table, uint64_t cap,
-                                                           const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, uint32_t* __restrict__ rid, DeviceStats* __restrict__ st) {
+                                                           const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, uint32_t* __restrict__ rid, DeviceStats* __restrict__ st,
+                                                           uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts) {
     __shared__ uint64_t scratch[8];
     uint32_t       singles = 0;
     bool           full    = false;
     const uint64_t limit   = cap < 8192 ? cap : 8192;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (!slot_valid(i, slot_cap, slot_counts)) {
+            rid[i] = 0;
+            continue;
+        }
         const unsigned long long key = __ldcs(keys + i);
         const uint64_t           h   = spooky_hash64_u64(key, 0);
         uint32_t                 out = 0;
@@ -204,12 +226,73 @@ __global__ void __launch_bounds__(256) stream_count_kernel(const unsigned long l
 }
 
 // rid[i] (slot + 1) -> global id of the surviving n-gram, 0 if pruned; in place, it becomes the reply buffer
-__global__ void __launch_bounds__(256) owner_reply_kernel(uint32_t* __restrict__ rid, uint64_t n, const uint32_t* __restrict__ bitmap, uint32_t world, uint32_t rank) {
+// P2P mode (peer_reply != NULL): the global id is stored straight into the sender's reply slot for this owner over NVLink
+__global__ void __launch_bounds__(256) owner_reply_kernel(uint32_t* __restrict__ rid, uint64_t n, const uint32_t* __restrict__ bitmap, uint32_t world, uint32_t rank,
+                                                          uint32_t* const* __restrict__ peer_reply, uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (peer_reply != nullptr) {
+        uint64_t src = i / slot_cap, k = i - src * slot_cap;
+        if (k >= __ldg(slot_counts + src)) return;
+        uint32_t s   = rid[i];
+        uint32_t gid = (s != 0 && ((__ldg(bitmap + ((s - 1) >> 5)) >> ((s - 1) & 31)) & 1u)) ? (s - 1) * world + rank + 1 : 0u;
+        peer_reply[src][(uint64_t)rank * slot_cap + k] = gid;
+        return;
+    }
     uint32_t s = rid[i];
     if (s == 0) return;
     rid[i] = ((__ldg(bitmap + ((s - 1) >> 5)) >> ((s - 1) & 31)) & 1u) ? (s - 1) * world + rank + 1 : 0u;
+}
+
+// P2P survivors: survivor (receive index i, count) -> record (i % slot_cap, count) in the source's survivor slot for this owner;
+// per-source cursors (one atomic per source per 2048-survivor tile); the final cursor values are the counts the host publishes.
+__global__ void __launch_bounds__(256) owner_survivors_p2p_kernel(const uint32_t* __restrict__ sv_idx, const uint32_t* __restrict__ sv_count, uint64_t n, uint32_t world, uint32_t rank,
+                                                                  uint64_t slot_cap, uint64_t surv_cap, unsigned long long* __restrict__ cursors, uint2* const* __restrict__ peer_surv,
+                                                                  DeviceStats* __restrict__ st) {
+    __shared__ uint32_t tile_cnt[64];
+    __shared__ unsigned long long tile_base[64];
+    const uint64_t ntiles = (n + 2047) / 2048;
+    bool overflow = false;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x < 64) tile_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t k_in[8], cnt[8], src[8], rk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint64_t i = tile * 2048 + (uint64_t)k * 256 + threadIdx.x;
+            src[k]     = 0xFFFFFFFFu;
+            if (i < n) {
+                uint32_t v = sv_idx[i];
+                src[k]     = (uint32_t)(v / slot_cap);
+                k_in[k]    = (uint32_t)(v - (uint64_t)src[k] * slot_cap);
+                cnt[k]     = sv_count[i];
+                rk[k]      = atomicAdd(&tile_cnt[src[k]], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < world) {
+            uint32_t c = tile_cnt[threadIdx.x];
+            tile_base[threadIdx.x] = c ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)c) : 0ull;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (src[k] == 0xFFFFFFFFu) continue;
+            uint64_t o = tile_base[src[k]] + rk[k];
+            if (o < surv_cap)
+                peer_surv[src[k]][(uint64_t)rank * surv_cap + o] = make_uint2(k_in[k], cnt[k]);
+            else
+                overflow = true;
+        }
+        __syncthreads();
+    }
+    if (overflow) atomicOr(&st->errflags, kErrTableFull);
+}
+
+// publish up to 8 u64 values per peer: dst[d][offset + j] = vals[d * nvals + j]   (headers of the symmetric buffers)
+__global__ void p2p_publish_kernel(unsigned long long* const* __restrict__ peer_hdr, uint32_t world, uint64_t offset, const unsigned long long* __restrict__ vals, uint32_t nvals) {
+    uint32_t d = threadIdx.x / 8, j = threadIdx.x % 8;
+    if (d < world && j < nvals) peer_hdr[d][offset + j] = vals[d * nvals + j];
 }
 
 // survivors (claimer's receive index, global count) -> per source rank: (index inside that source's group, count).
@@ -298,26 +381,42 @@ int launch_split_count(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint
     split_count_kernel<<<nblocks, 256, 0, s>>>(prev, npos, world, nblocks, hist);
     return 1;
 }
-int launch_split_write(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, const uint64_t* hist_off, void* send_keys, uint32_t* pos_of_rec, uint32_t* rec_of_pos) {
+int launch_split_write(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, const uint64_t* hist_off, void* send_keys, uint32_t* pos_of_rec, uint32_t* rec_of_pos,
+                       void* const* peer_keys, uint32_t my_rank, uint64_t slot_cap) {
     uint32_t nblocks = sk_div_up(npos, kSplitTile);
-    split_write_kernel<<<nblocks, 256, 0, s>>>(prev, npos, world, nblocks, hist_off, (unsigned long long*)send_keys, pos_of_rec, rec_of_pos);
+    split_write_kernel<<<nblocks, 256, 0, s>>>(prev, npos, world, nblocks, hist_off, (unsigned long long*)send_keys, pos_of_rec, rec_of_pos, (unsigned long long* const*)peer_keys,
+                                                my_rank, slot_cap);
     return 1;
 }
-int launch_stream_filter(cudaStream_t s, const void* keys, uint64_t n, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms) {
+int launch_stream_filter(cudaStream_t s, const void* keys, uint64_t n, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms, uint64_t slot_cap,
+                         const unsigned long long* slot_counts) {
     if (!n) return 0;
     unsigned grid = (unsigned)sk_min(sk_div_up(n, 256), (uint64_t)sms * 32);
-    stream_filter_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)keys, n, filter, nbuckets - 1, st);
+    stream_filter_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)keys, n, filter, nbuckets - 1, st, slot_cap, slot_counts);
     return 1;
 }
-int launch_stream_count(cudaStream_t s, const void* keys, uint64_t n, NgramSlot* table, uint64_t cap, const uint32_t* filter, uint64_t nbuckets, uint32_t* rid, DeviceStats* st, int sms) {
+int launch_stream_count(cudaStream_t s, const void* keys, uint64_t n, NgramSlot* table, uint64_t cap, const uint32_t* filter, uint64_t nbuckets, uint32_t* rid, DeviceStats* st, int sms,
+                        uint64_t slot_cap, const unsigned long long* slot_counts) {
     if (!n) return 0;
     unsigned grid = (unsigned)sk_min(sk_div_up(n, 256), (uint64_t)sms * 32);
-    stream_count_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)keys, n, table, cap, filter, nbuckets ? nbuckets - 1 : 0, rid, st);
+    stream_count_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)keys, n, table, cap, filter, nbuckets ? nbuckets - 1 : 0, rid, st, slot_cap, slot_counts);
     return 1;
 }
-int launch_owner_reply(cudaStream_t s, uint32_t* rid, uint64_t n, const uint32_t* bitmap, uint32_t world, uint32_t rank) {
+int launch_owner_reply(cudaStream_t s, uint32_t* rid, uint64_t n, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* const* peer_reply, uint64_t slot_cap,
+                       const unsigned long long* slot_counts) {
     if (!n) return 0;
-    owner_reply_kernel<<<sk_div_up(n, 256), 256, 0, s>>>(rid, n, bitmap, world, rank);
+    owner_reply_kernel<<<sk_div_up(n, 256), 256, 0, s>>>(rid, n, bitmap, world, rank, (uint32_t* const*)peer_reply, slot_cap, slot_counts);
+    return 1;
+}
+int launch_owner_survivors_p2p(cudaStream_t s, const uint32_t* sv_idx, const uint32_t* sv_count, uint64_t n, uint32_t world, uint32_t rank, uint64_t slot_cap, uint64_t surv_cap,
+                               unsigned long long* cursors, void* const* peer_surv, DeviceStats* st, int sms) {
+    if (!n) return 0;
+    unsigned grid = (unsigned)sk_min(sk_div_up(n, 2048), (uint64_t)sms * 4);
+    owner_survivors_p2p_kernel<<<grid, 256, 0, s>>>(sv_idx, sv_count, n, world, rank, slot_cap, surv_cap, cursors, (uint2* const*)peer_surv, st);
+    return 1;
+}
+int launch_p2p_publish(cudaStream_t s, void* const* peer_hdr, uint32_t world, uint64_t offset, const unsigned long long* vals, uint32_t nvals) {
+    p2p_publish_kernel<<<1, 512, 0, s>>>((unsigned long long* const*)peer_hdr, world, offset, vals, nvals);
     return 1;
 }
 int launch_owner_survivor_counts(cudaStream_t s, const uint32_t* sv_idx, uint64_t n, uint32_t world, const unsigned long long* src_base, unsigned long long* counts, int sms) {

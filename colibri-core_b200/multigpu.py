@@ -14,6 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import sys
 import time
 
 import numpy as np
@@ -105,6 +106,29 @@ class CudaShardEngine:
     def sync(self):
         self.torch.cuda.current_stream(self.device).synchronize()
 
+    # ---- NVLink peer-store mode
+    def use_peers(self, peers: "PeerBuffers"):
+        self._check(self.lib.colibri_b200_shard_set_stream(self._h, C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)))
+        arr = [(C.c_uint64 * self.world)(*p) for p in peers.ptrs]
+        self._check(self.lib.colibri_b200_shard_set_peers(self._h, arr[0], arr[1], arr[2], arr[3], peers.slot_cap, peers.surv_cap))
+        self.peers = peers
+
+    def p2p_split(self, n):
+        w = C.c_uint64()
+        self._check(self.lib.colibri_b200_shard_p2p_split(self._h, n, C.byref(w)))
+        return int(w.value)
+
+    def p2p_owner(self):
+        st = (C.c_uint64 * 3)()
+        self._check(self.lib.colibri_b200_shard_p2p_owner(self._h, st))
+        return tuple(int(x) for x in st)
+
+    def p2p_finish(self):
+        st = (C.c_uint64 * 3)()
+        v = C.c_uint64()
+        self._check(self.lib.colibri_b200_shard_p2p_finish(self._h, st, C.byref(v)))
+        return tuple(int(x) for x in st), int(v.value)
+
     def close(self):
         if self._h:
             self.lib.colibri_b200_shard_free(self._h)
@@ -115,6 +139,41 @@ class CudaShardEngine:
             self.close()
         except Exception:
             pass
+
+
+class PeerBuffers:
+    """Symmetric receive buffers of one rank (torch.distributed._symmetric_memory), rendezvoused once and reused by every
+    step: the split / reply kernels of the other ranks store into them over NVLink.  Sized for `positions` per rank."""
+
+    _cache = {}
+
+    def __init__(self, dist, torch, world, positions, device):
+        import torch.distributed._symmetric_memory as symm
+
+        self.world = world
+        self.slot_cap = int(1.3 * positions / world) + 65536
+        self.surv_cap = self.slot_cap // 2 + 4096
+        dev = torch.device("cuda", device)
+        self.keys = symm.empty(world * self.slot_cap * 2, dtype=torch.int32, device=dev)
+        self.reply = symm.empty(world * self.slot_cap, dtype=torch.int32, device=dev)
+        self.surv = symm.empty(world * self.surv_cap * 2, dtype=torch.int32, device=dev)
+        self.hdr = symm.empty(6 * world * 2 + 64, dtype=torch.int32, device=dev)
+        self.hdr.zero_()
+        group = dist.group.WORLD
+        self.handles = [symm.rendezvous(t, group) for t in (self.keys, self.reply, self.surv, self.hdr)]
+        self.ptrs = [[int(p) for p in h.buffer_ptrs] for h in self.handles]
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    @classmethod
+    def get(cls, dist, torch, world, positions, device):
+        key = (world, device, int(positions))
+        if key not in cls._cache:
+            cls._cache[key] = cls(dist, torch, world, positions, device)
+        return cls._cache[key]
+
+    def barrier(self):
+        self.handles[3].barrier(channel=0)  # device-side barrier through the signal pads, enqueued on the current stream
 
 
 def _exchange(dist, torch, engine, send, send_counts, width):
@@ -173,7 +232,26 @@ def train_distributed(engine, dist, torch, mintokens=2, maxlength=5):
         maxn = minn = 1
     prev_kept = kept
     n = 2
-    while found and n <= maxlength and prev_kept > 0:
+    peers = getattr(engine, "peers", None)
+    while peers is not None and found and n <= maxlength and prev_kept > 0:
+        # NVLink peer-store mode: keys and replies are stored into the peers' symmetric buffers by the kernels themselves
+        engine.p2p_split(n)
+        sw.lap("p2p_split")
+        peers.barrier()
+        sw.lap("barrier")
+        engine.p2p_owner()
+        sw.lap("p2p_owner")
+        peers.barrier()
+        sw.lap("barrier")
+        (gf, gk, _gocc), _valid = engine.p2p_finish()
+        sw.lap("p2p_finish")
+        if gf == 0:
+            break
+        passes.append((n, gf, 0, gf - gk))
+        maxn, minn = max(maxn, n), min(minn, n)
+        prev_kept = gk
+        n += 1
+    while peers is None and found and n <= maxlength and prev_kept > 0:
         send_counts, nsend = engine.level_split_count(n)
         sw.lap("split_count")
         send = engine.level_split_write(nsend)
@@ -224,8 +302,18 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
         dist.barrier()
         torch.cuda.synchronize()
 
+    peers = None
+    if not os.environ.get("COLIBRI_B200_NO_P2P"):
+        try:
+            peers = PeerBuffers.get(dist, torch, world, int(ntok * 1.06) + 1024, local)
+        except Exception as e:  # symmetric memory unavailable: the NCCL all-to-all path is used instead (still all on the GPUs)
+            if rank == 0:
+                print("note: symmetric memory unavailable (%r); using NCCL all-to-all" % (e,), file=sys.stderr, flush=True)
+
     def step():
         eng = CudaShardEngine(corpus, opts, rank, world, local)
+        if peers is not None:
+            eng.use_peers(peers)
         model, passes, head = train_distributed(eng, dist, torch, a.mintokens, a.maxlength)
         out = (len(model), head, passes, eng.device_ms(), eng.info()["launches"], eng.phase_ms())
         model.close()
@@ -264,6 +352,8 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
     def e2e_step():
         c = cb.Corpus.from_host_pointer(host.data_ptr(), host.numel(), device=local)
         eng = CudaShardEngine(c, opts, rank, world, local)
+        if peers is not None:
+            eng.use_peers(peers)
         model, _, _ = train_distributed(eng, dist, torch, a.mintokens, a.maxlength)
         n, kb, _ = model.export_sizes()
         if n > cap_pat or kb > out_keys.numel():
@@ -294,7 +384,8 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
             "metric": metric, "value": tokens * a.steps / elapsed, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * elapsed / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 (integer)", "data": "synthetic",
             "config": {"workload": workload + " PER GPU (shards of one global stream)", "global_tokens": tokens, "patterns": int(npat[0].item()),
-                       "parallelism": "corpus sharded by sentence x%d, model hash-partitioned, NCCL all-to-all of (key,count) records per level" % world,
+                       "parallelism": "corpus sharded by sentence x%d, model hash-partitioned; windows shipped to their owners by %s" % (
+                           world, "NVLink peer stores from the split/reply kernels (symmetric memory)" if peers is not None else "NCCL all-to-all"),
                        "l2": "inputs exceed L2", "timing": "max over ranks of max(CUDA events, wall clock) around K steps"},
             "device_ms_per_step_max_rank": 1e3 * float(t[1].item()) / a.steps, "passes": last[2], "rank0_phase_ms_last_step": last[5],
             "roofline": {"bound": "hbm", "kernel": "count_ngrams_kernel", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "peak_source": peak_src, "traffic": None,

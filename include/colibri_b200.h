@@ -156,6 +156,17 @@ int    colibri_b200_shard_level_split_write(colibri_b200_shard* sh, void* dev_se
 int    colibri_b200_shard_level_owner(colibri_b200_shard* sh, const void* dev_recv_keys, const uint64_t* recv_counts, void* dev_reply, uint64_t stats[3], uint64_t* surv_counts);
 int    colibri_b200_shard_level_owner_survivors(colibri_b200_shard* sh, void* dev_out /* 8 B per record, grouped by source */);
 int    colibri_b200_shard_level_finish(colibri_b200_shard* sh, const void* dev_reply_back, const void* dev_surv, const uint64_t* surv_counts /* per owner */, uint64_t* local_valid);
+/* NVLink peer-store mode: the caller allocates symmetric receive buffers on every rank (e.g. torch.distributed._symmetric_memory),
+ * passes every rank's device pointers (keys_rx: G slots x slot_cap x 8 B; reply_rx: G x slot_cap x 4 B; surv_rx: G x surv_cap x 8 B;
+ * hdr: 6*G u64 words) and provides a device-side barrier on the stream given to shard_set_stream.  A level is then
+ * shard_p2p_split, [barrier], shard_p2p_owner, [barrier], shard_p2p_finish: the split kernel stores keys straight into the
+ * owners' slots and the reply kernel stores ids straight into the senders' slots over NVLink; no all-to-all call is made. */
+int    colibri_b200_shard_set_stream(colibri_b200_shard* sh, void* cuda_stream);
+int    colibri_b200_shard_set_peers(colibri_b200_shard* sh, const uint64_t* keys_rx, const uint64_t* reply_rx, const uint64_t* surv_rx, const uint64_t* hdr, uint64_t slot_cap,
+                                    uint64_t surv_cap);
+int    colibri_b200_shard_p2p_split(colibri_b200_shard* sh, int n, uint64_t* windows);
+int    colibri_b200_shard_p2p_owner(colibri_b200_shard* sh, uint64_t stats[3]);
+int    colibri_b200_shard_p2p_finish(colibri_b200_shard* sh, uint64_t global_stats[3], uint64_t* local_valid);
 /* passes: npasses x {n, found, foundskip, pruned} global numbers; the returned model holds THIS RANK'S share of the patterns */
 int    colibri_b200_shard_finish(colibri_b200_shard* sh, const uint64_t* passes, int npasses, uint64_t global_types, int maxn, int minn, colibri_b200_model** out);
 void   colibri_b200_shard_free(colibri_b200_shard* sh);

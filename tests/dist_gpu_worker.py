@@ -22,6 +22,8 @@ def main():
     corpus = cb.Corpus.synthetic(per, device=local, first_token=rank * per, **kw)
     opts = cb.PatternModelOptions(MINTOKENS=mintokens, MAXLENGTH=maxlength, QUIET=1, device=local)
     eng = mg.CudaShardEngine(corpus, opts, rank, world, local)
+    if len(sys.argv) > 6 and sys.argv[6] == "p2p":  # NVLink peer-store mode (symmetric memory)
+        eng.use_peers(mg.PeerBuffers.get(dist, torch, world, per * 2, local))
     model, passes, head = mg.train_distributed(eng, dist, torch, mintokens, maxlength)
     keys, off, counts, _ = model.export()
     share = (keys.tobytes(), off.tolist(), counts.tolist())

@@ -11,9 +11,9 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _run(world, per, vocab, seed, maxlength, mintokens, port):
+def _run(world, per, vocab, seed, maxlength, mintokens, port, mode="nccl"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tests", "dist_gpu_worker.py"), str(per), str(vocab), str(seed), str(maxlength), str(mintokens)]
+           os.path.join(ROOT, "tests", "dist_gpu_worker.py"), str(per), str(vocab), str(seed), str(maxlength), str(mintokens), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_RESULT OK" in r.stdout, r.stdout[-3000:]
@@ -24,9 +24,15 @@ def test_shard_phases_world1(per, vocab, seed, maxlength, mintokens):
     _run(1, per, vocab, seed, maxlength, mintokens, 29711)
 
 
-def test_shard_phases_world2():
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+def test_shard_phases_world2(mode):
     import colibri_core_b200 as cb
 
     if cb.device_count() < 2:
         pytest.skip("needs two GPUs")
-    _run(2, 400000, 30000, 6, 5, 2, 29713)
+    _run(2, 400000, 30000, 6, 5, 2, 29713, mode)
+
+
+def test_shard_phases_world1_peer_stores():
+    """NVLink peer-store mode with a single rank: the kernels store into the rank's own symmetric buffers."""
+    _run(1, 300000, 20000, 4, 5, 2, 29715, "p2p")

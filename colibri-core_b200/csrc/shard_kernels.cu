@@ -61,12 +61,16 @@ __global__ void __launch_bounds__(256) split_count_kernel(const uint32_t* __rest
 }
 
 // pass 2: stable scatter.  send_keys is laid out [dest 0 | dest 1 | ...]; positions stay ascending inside a group.
-// P2P mode (peer_keys != NULL): the key is stored straight into the owner's receive slot for this rank over NVLink
+// P2P mode (peer_keys != NULL): the keys are stored straight into the owner's receive slot for this rank over NVLink
 // (peer_keys[d] = base of rank d's receive buffer, slot of source r at r * slot_cap) -- the pack and the all-to-all are one kernel.
+// The block first gathers its keys per destination in shared memory and then copies each destination's run with consecutive
+// threads: 256-byte warp stores instead of 8-byte ones scattered over G streams (NVLink packets like them long).
 __global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t world, uint32_t nblocks, const uint64_t* __restrict__ hist_off,
                                                           unsigned long long* __restrict__ send_keys, uint32_t* __restrict__ pos_of_rec, uint32_t* __restrict__ rec_of_pos,
                                                           unsigned long long* const* __restrict__ peer_keys, uint32_t my_rank, uint64_t slot_cap) {
     __shared__ uint32_t cnt[8][65];
+    __shared__ uint32_t dpre[66];                       // exclusive prefix of this block's per-destination totals
+    __shared__ unsigned long long stage[kSplitTile];    // keys grouped by destination
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     for (int i = threadIdx.x; i < 8 * 65; i += 256) (&cnt[0][0])[i] = 0;
     __syncthreads();
@@ -87,6 +91,17 @@ __global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __rest
             cnt[w][threadIdx.x] = run;
             run += c;
         }
+        dpre[threadIdx.x + 1] = run;  // totals for now
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        dpre[0]      = 0;
+        for (uint32_t d = 0; d < 64; ++d) {
+            uint32_t c = dpre[d + 1];
+            dpre[d + 1] = acc + c;
+            acc += c;
+        }
     }
     __syncthreads();
     for (int it = 0; it < kSplitTile / 8 / 32; ++it) {
@@ -101,19 +116,28 @@ __global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __rest
         if ((int)lane == __ffs(peers) - 1) cnt[warp][d] = base + __popc(peers);
         __syncwarp();
         if (act) {
-            uint64_t dst    = hist_off[(uint64_t)d * nblocks + blockIdx.x] + base + __popc(peers & ((1u << lane) - 1));
-            pos_of_rec[dst] = (uint32_t)p;
-            if (peer_keys != nullptr) {
-                uint64_t k = dst - hist_off[(uint64_t)d * nblocks];  // index inside the group of owner d
-                peer_keys[d][(uint64_t)my_rank * slot_cap + k] = key;
-                rec_of_pos[p] = (uint32_t)((uint64_t)d * slot_cap + k);  // where the reply will appear in my own reply slots
-            } else {
-                send_keys[dst] = key;
-                rec_of_pos[p]  = (uint32_t)dst;
-            }
+            const uint32_t in_blk = base + __popc(peers & ((1u << lane) - 1));  // rank inside this block's group for owner d
+            const uint64_t dst    = hist_off[(uint64_t)d * nblocks + blockIdx.x] + in_blk;
+            stage[dpre[d] + in_blk] = key;
+            pos_of_rec[dst]         = (uint32_t)p;
+            if (peer_keys != nullptr)
+                rec_of_pos[p] = (uint32_t)((uint64_t)d * slot_cap + (dst - hist_off[(uint64_t)d * nblocks]));  // where the reply will appear in my own reply slots
+            else
+                rec_of_pos[p] = (uint32_t)dst;
         } else if (p < npos) {
             rec_of_pos[p] = kNoRec;
         }
+    }
+    __syncthreads();
+    const uint32_t total = dpre[64];
+    for (uint32_t i = threadIdx.x; i < total; i += 256) {
+        uint32_t d = 0;
+        while (i >= dpre[d + 1]) ++d;
+        const uint64_t dst = hist_off[(uint64_t)d * nblocks + blockIdx.x] + (i - dpre[d]);
+        if (peer_keys != nullptr)
+            peer_keys[d][(uint64_t)my_rank * slot_cap + (dst - hist_off[(uint64_t)d * nblocks])] = stage[i];
+        else
+            send_keys[dst] = stage[i];
     }
 }
 
@@ -171,10 +195,27 @@ __device__ __forceinline__ void sk_cas128(void* addr, unsigned long long new0, u
 }
 
 // rid[i] = slot + 1 of received window i (0: the filter proved it to be the only window of its key).  slot.pos = i of the claimer.
+//
+// Hot keys: an owner receives every occurrence of its keys from all G ranks, so the most frequent n-grams put millions of
+// REDs on one L2 address (they serialise: the owner of "the the" became the straggler of the level).  Each block therefore
+// keeps a small never-evicting cache in shared memory: key -> {table slot, pending count}.  The first window of a key that
+// finds its cache line empty installs it after its normal upsert; later windows of that key in the block only bump the
+// shared-memory counter, which is added to the table once when the block retires.  Lines never change owner, so counts stay exact.
+constexpr uint32_t kHotLines    = 1024;
+constexpr unsigned long long kHotBusy = ~0ull;
+
 __global__ void __launch_bounds__(256) stream_count_kernel(const unsigned long long* __restrict__ keys, uint64_t n, NgramSlot* __restrict__ table, uint64_t cap,
                                                            const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, uint32_t* __restrict__ rid, DeviceStats* __restrict__ st,
                                                            uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts) {
     __shared__ uint64_t scratch[8];
+    __shared__ unsigned long long hot_key[kHotLines];
+    __shared__ uint32_t hot_slot[kHotLines];
+    __shared__ uint32_t hot_pending[kHotLines];
+    for (uint32_t i = threadIdx.x; i < kHotLines; i += blockDim.x) {
+        hot_key[i]     = 0;
+        hot_pending[i] = 0;
+    }
+    __syncthreads();
     uint32_t       singles = 0;
     bool           full    = false;
     const uint64_t limit   = cap < 8192 ? cap : 8192;
@@ -195,37 +236,54 @@ __global__ void __launch_bounds__(256) stream_count_kernel(const unsigned long l
             singles += !go;
         }
         if (go) {
-            uint64_t slot = fast_range(h, cap);
-            uint64_t step = 0;
-            for (; step < limit; ++step) {
-                NgramSlot*         s   = table + slot;
-                unsigned long long cur = __ldcg(&s->key);
-                if (cur == 0) {
-                    unsigned long long o0, o1;
-                    sk_cas128(s, key, 1ull | ((unsigned long long)(uint32_t)i << 32), o0, o1);
-                    if (o0 == 0) {
+            const uint32_t line = (uint32_t)(h >> 20) & (kHotLines - 1);
+            unsigned long long cached = *(volatile unsigned long long*)&hot_key[line];
+            if (cached == key) {  // the slot was published before the key (see below)
+                atomicAdd(&hot_pending[line], 1u);
+                out = *(volatile uint32_t*)&hot_slot[line];
+            } else {
+                uint64_t slot = fast_range(h, cap);
+                uint64_t step = 0;
+                for (; step < limit; ++step) {
+                    NgramSlot*         s   = table + slot;
+                    unsigned long long cur = __ldcg(&s->key);
+                    if (cur == 0) {
+                        unsigned long long o0, o1;
+                        sk_cas128(s, key, 1ull | ((unsigned long long)(uint32_t)i << 32), o0, o1);
+                        if (o0 == 0) {
+                            out = (uint32_t)slot + 1;
+                            break;
+                        }
+                        cur = o0;
+                    }
+                    if (cur == key) {
+                        atomicAdd(&s->count, 1u);
                         out = (uint32_t)slot + 1;
                         break;
                     }
-                    cur = o0;
+                    slot = slot + 1 == cap ? 0 : slot + 1;
                 }
-                if (cur == key) {
-                    atomicAdd(&s->count, 1u);
-                    out = (uint32_t)slot + 1;
-                    break;
+                if (out == 0) {
+                    full = true;
+                } else if (cached == 0 && atomicCAS(&hot_key[line], 0ull, kHotBusy) == 0ull) {
+                    hot_slot[line] = out;          // publish the slot ...
+                    __threadfence_block();
+                    *(volatile unsigned long long*)&hot_key[line] = key;  // ... then the key that makes it visible
                 }
-                slot = slot + 1 == cap ? 0 : slot + 1;
             }
-            if (out == 0) full = true;
         }
         __stcs(rid + i, out);
+    }
+    __syncthreads();
+    for (uint32_t l = threadIdx.x; l < kHotLines; l += blockDim.x) {
+        uint32_t c = hot_pending[l];
+        if (c) atomicAdd(&table[hot_slot[l] - 1].count, c);
     }
     uint64_t sg = block_reduce_sum(singles, scratch);
     if (threadIdx.x == 0 && sg) atomicAdd(&st->singletons, (unsigned long long)sg);
     if (full) atomicOr(&st->errflags, kErrTableFull);
 }
 
-// rid[i] (slot + 1) -> global id of the surviving n-gram, 0 if pruned; in place, it becomes the reply buffer
 // P2P mode (peer_reply != NULL): the global id is stored straight into the sender's reply slot for this owner over NVLink
 __global__ void __launch_bounds__(256) owner_reply_kernel(uint32_t* __restrict__ rid, uint64_t n, const uint32_t* __restrict__ bitmap, uint32_t world, uint32_t rank,
                                                           uint32_t* const* __restrict__ peer_reply, uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts) {

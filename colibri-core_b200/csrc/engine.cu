@@ -496,7 +496,9 @@ int Trainer::run() {
             slots_init += cap;
             TRY(zero_stats());
             int hc = timer.begin(COLIBRI_T_COUNT, n);
-            launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms, use_filter ? filter.p : nullptr, nbuckets);
+            static const int hot_mode = getenv("COLIBRI_B200_HOT") ? atoi(getenv("COLIBRI_B200_HOT")) : 1;  // 0 never, 1 large levels, 2 always
+            const bool hot = hot_mode == 2 || (hot_mode == 1 && bound >= (1ull << 25));
+            launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms, use_filter ? filter.p : nullptr, nbuckets, hot);
             timer.end(hc);
             CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaStreamSynchronize(s));

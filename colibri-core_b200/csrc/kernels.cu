@@ -327,10 +327,29 @@ __global__ void __launch_bounds__(256) ngram_filter_kernel(const uint32_t* __res
     }
 }
 
+// Hot keys: the most frequent n-grams of a corpus put hundreds of thousands to millions of REDs on one L2 address, where
+// they serialise.  Each block keeps a small never-evicting cache in shared memory: key -> {table slot, pending count}.  The
+// first window of a key that finds its line empty installs it after its normal upsert; later windows of that key in the
+// block only bump the shared-memory counter, which is added to the table once when the block retires.  A line never
+// changes owner, so counts stay exact; cold keys pay one shared-memory read.
+constexpr uint32_t           kHotLines = 1024;
+constexpr unsigned long long kHotBusy  = ~0ull;
+
 template <bool kFilter>
-__global__ void __launch_bounds__(256) count_ngrams_kernel(const uint32_t* __restrict__ prev, uint32_t* __restrict__ cur, uint64_t npos, NgramSlot* __restrict__ table,
-                                                           uint64_t cap, const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, DeviceStats* __restrict__ st) {
+__global__ void __launch_bounds__(256, 8) count_ngrams_kernel(const uint32_t* __restrict__ prev, uint32_t* __restrict__ cur, uint64_t npos, NgramSlot* __restrict__ table,
+                                                           uint64_t cap, const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, DeviceStats* __restrict__ st,
+                                                           const bool hot) {
     __shared__ uint64_t scratch[8];
+    __shared__ unsigned long long hot_key[kHotLines];
+    __shared__ uint32_t hot_slot[kHotLines];
+    __shared__ uint32_t hot_pending[kHotLines];
+    if (hot) {
+        for (uint32_t i = threadIdx.x; i < kHotLines; i += blockDim.x) {
+            hot_key[i]     = 0;
+            hot_pending[i] = 0;
+        }
+        __syncthreads();
+    }
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint32_t       valid = 0, probes = 0, singles = 0;
     bool           full = false;
@@ -350,9 +369,31 @@ __global__ void __launch_bounds__(256) count_ngrams_kernel(const uint32_t* __res
                 go = ((__ldg(filter + word) >> shift) & 2u) != 0;
                 singles += !go;
             }
-            if (go) id = upsert_ngram_at(table, cap, fast_range(h, cap), key, (uint32_t)p, probes, full);
+            if (go) {
+                const uint32_t           line   = (uint32_t)(h >> 20) & (kHotLines - 1);
+                unsigned long long cached = ~0ull;
+                if (hot) cached = *(volatile unsigned long long*)&hot_key[line];
+                if (cached == key) {  // its slot was published before the key (below)
+                    atomicAdd(&hot_pending[line], 1u);
+                    id = *(volatile uint32_t*)&hot_slot[line];
+                } else {
+                    id = upsert_ngram_at(table, cap, fast_range(h, cap), key, (uint32_t)p, probes, full);
+                    if (id != 0 && cached == 0 && atomicCAS(&hot_key[line], 0ull, kHotBusy) == 0ull) {
+                        hot_slot[line] = id;  // publish the slot ...
+                        __threadfence_block();
+                        *(volatile unsigned long long*)&hot_key[line] = key;  // ... then the key that makes it visible
+                    }
+                }
+            }
         }
         __stcs(cur + p, id);
+    }
+    if (hot) {
+        __syncthreads();
+        for (uint32_t l = threadIdx.x; l < kHotLines; l += blockDim.x) {
+            uint32_t c = hot_pending[l];
+            if (c) atomicAdd(&table[hot_slot[l] - 1].count, c);
+        }
     }
     uint64_t v  = block_reduce_sum(valid, scratch);
     uint64_t pr = block_reduce_sum(probes, scratch);
@@ -495,16 +536,16 @@ int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uin
     return 1;
 }
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms, const uint32_t* filter,
-                        uint64_t nbuckets) {
+                        uint64_t nbuckets, bool hot) {
     static int bps0 = blocks_per_sm((const void*)count_ngrams_kernel<false>, 256, 0);
     static int bps1 = blocks_per_sm((const void*)count_ngrams_kernel<true>, 256, 0);
     uint64_t   want = div_up(npos, 256);
     if (filter != nullptr) {
         unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bps1 * 4);
-        count_ngrams_kernel<true><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, filter, nbuckets - 1, st);
+        count_ngrams_kernel<true><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, filter, nbuckets - 1, st, hot);
     } else {
         unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bps0 * 4);
-        count_ngrams_kernel<false><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, nullptr, 0, st);
+        count_ngrams_kernel<false><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, nullptr, 0, st, hot);
     }
     return 1;
 }

@@ -73,7 +73,7 @@ int launch_make_id1(cudaStream_t s, const uint32_t* tok, uint64_t npos, const ui
 int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms);
 // filter == NULL: every valid window goes to the table
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms,
-                        const uint32_t* filter = nullptr, uint64_t nbuckets = 0);
+                        const uint32_t* filter = nullptr, uint64_t nbuckets = 0, bool hot = false /* per-block shared-memory cache for frequent keys */);
 // bitmap: (cap+31)/32 words, bit = slot survived (may be NULL)
 int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap, DeviceStats* st, int sms,
                         uint32_t* slot_index = nullptr /* slot -> survivor index + 1, for the forward index */);

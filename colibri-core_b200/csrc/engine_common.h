@@ -46,12 +46,27 @@ struct Pool {
     std::mutex                        mu;
     std::multimap<size_t, void*>      free_blocks;  // size -> ptr
     std::map<void*, size_t>           live;
-    size_t                            in_use = 0, peak = 0, cached = 0;
+    size_t                            in_use = 0, peak = 0, cached = 0, misses = 0;
+    // Requests are rounded up to size classes (powers of two below 1 MB, quarter-octave steps above: <= 25 % slack) and a
+    // free block is reused only by a request of its own class.  The same sequence of requests (every training step makes
+    // one) then always finds its blocks; with "any block up to 25 % larger" a small request could take the block a later,
+    // larger one needed, and the resulting cudaMalloc is millisecond-expensive once peer access is enabled (multi-GPU).
+    static size_t size_class(size_t bytes) {
+        if (bytes <= 256) return 256;
+        if (bytes <= (1u << 20)) {
+            size_t c = 256;
+            while (c < bytes) c <<= 1;
+            return c;
+        }
+        int k = 63 - __builtin_clzll((unsigned long long)bytes);
+        size_t step = (size_t)1 << (k - 2);
+        return (bytes + step - 1) / step * step;
+    }
     int alloc(void** out, size_t bytes) {
-        bytes = std::max<size_t>(256, (bytes + 255) / 256 * 256);
+        bytes = size_class(bytes);
         std::lock_guard<std::mutex> g(mu);
-        auto it = free_blocks.lower_bound(bytes);
-        if (it != free_blocks.end() && it->first <= bytes + bytes / 4 + (1 << 20)) {
+        auto it = free_blocks.find(bytes);
+        if (it != free_blocks.end()) {
             *out = it->second;
             live[*out] = it->first;
             in_use += it->first;
@@ -72,6 +87,7 @@ struct Pool {
             }
             live[*out] = bytes;
             in_use += bytes;
+            ++misses;
         }
         peak = std::max(peak, in_use);
         return 0;
@@ -117,9 +133,10 @@ struct DevBuf {
         reset();
         dev = device;
         void* q = nullptr;
-        TRY(g_pool[device & 15].alloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+        const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        TRY(g_pool[device & 15].alloc(&q, bytes));
         p = (T*)q;
-        n = count;
+        n = Pool::size_class(bytes) / sizeof(T);  // the whole block is usable: grow-only buffers re-allocate less often
         return 0;
     }
     void reset() {

@@ -1,0 +1,89 @@
+// CPU-side checks of the C++ API mirror (colibri-core_b200/host): the value types behave like the reference's
+// (reference include/pattern.h, src/pattern.cpp) and train() refuses loudly without a GPU.  Prints "ok"/"FAILED" lines in
+// the spirit of the reference's own src/test.cpp and exits 2 on the first failure.
+#include <cstdlib>
+#include <iostream>
+#include <sstream>
+#include <string>
+
+#include "patternmodel.h"
+
+static int testnr = 0;
+template <class A, class B>
+static void test(const char* what, const A& value, const B& ref) {
+    ++testnr;
+    if (value == (A)ref) {
+        std::cerr << testnr << " " << what << " ... ok" << std::endl;
+    } else {
+        std::cerr << testnr << " " << what << " ... " << value << " ... FAILED, expected " << ref << std::endl;
+        exit(2);
+    }
+}
+
+int main(int argc, char** argv) {
+    // Pattern basics; hash KATs produced by the reference library
+    Pattern unigram = Pattern::fromclasses({6});
+    Pattern bigram  = Pattern::fromclasses({6, 7});
+    test("unigram n()", unigram.n(), 1u);
+    test("bigram n()", bigram.n(), 2u);
+    test("bigram bytesize()", bigram.bytesize(), 2u);
+    test("Pattern::hash [06]", (unsigned long long)unigram.hash(), 6716366417670780154ull);
+    test("Pattern::hash [06 07]", (unsigned long long)bigram.hash(), 7201352277971678815ull);
+    const unsigned char multibyte[] = {0x86, 0x01, 0x07, 0x80, 0x80, 0x01};
+    Pattern mb(multibyte, 6);
+    test("multibyte n()", mb.n(), 3u);
+    test("Pattern::hash multibyte", (unsigned long long)mb.hash(), 6910059722266967716ull);
+    test("multibyte tovector[0]", mb.tovector()[0], 134u);
+    test("multibyte tovector[2]", mb.tovector()[2], 16384u);
+    test("fromclasses roundtrip", Pattern::fromclasses(mb.tovector()) == mb, true);
+    test("empty hash", (unsigned long long)Pattern().hash(), 0ull);
+    const unsigned char skip[] = {0x0A, 0x03, 0x03, 0x0D, 0x0E};
+    Pattern sg(skip, 5);
+    test("skipgram category", (int)sg.category(), (int)SKIPGRAM);
+    test("skipgram isgap(1)", sg.isgap(1), true);
+    test("skipgram isgap(0)", sg.isgap(0), false);
+    test("skipgram n()", sg.n(), 5u);
+    test("Pattern::hash skipgram", (unsigned long long)sg.hash(), 17915007264098384048ull);
+    test("ngram category", (int)bigram.category(), (int)NGRAM);
+    test("std::hash<Pattern>", (unsigned long long)std::hash<Pattern>()(bigram), 7201352277971678815ull);
+    std::ostringstream os;
+    bigram.write(os);
+    test("write() appends the end marker", os.str().size(), 3u);
+
+    // options defaults (reference include/patternmodel.h:153-180)
+    PatternModelOptions o;
+    test("MINTOKENS default", o.MINTOKENS, -1);
+    test("MAXLENGTH default", o.MAXLENGTH, 100);
+    test("MINSKIPTYPES default", o.MINSKIPTYPES, 2);
+    test("MAXSKIPS default", o.MAXSKIPS, 3);
+    test("DOSKIPGRAMS default", o.DOSKIPGRAMS, false);
+
+    if (argc > 1) {
+        IndexedCorpus corpus{std::string(argv[1])};
+        test("IndexedCorpus sentences (hamlet)", corpus.sentences(), 40u);  // reference src/test.cpp:1549
+        // without a GPU train() must throw InternalError, never compute on the CPU
+        if (colibri_b200_device_count() == 0) {
+            PatternModel<uint32_t> model;
+            bool threw = false;
+            o.QUIET = true;
+            try {
+                model.train(std::string(argv[1]), o);
+            } catch (const InternalError&) {
+                threw = true;
+            }
+            test("train() without a GPU throws InternalError", threw, true);
+            test("model stays empty", model.size(), 0u);
+        }
+        // refusals of the training front end
+        PatternModel<uint32_t> model2;
+        bool threw = false;
+        try {
+            model2.train(std::string(argv[1]), o, nullptr, nullptr, /*continued=*/true);
+        } catch (const InternalError&) {
+            threw = true;
+        }
+        test("continued training is refused", threw, true);
+    }
+    std::cerr << "all " << testnr << " host API tests ok" << std::endl;
+    return 0;
+}

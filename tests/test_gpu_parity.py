@@ -199,3 +199,37 @@ def test_error_paths():
     assert ei.value.code == 4
     with pytest.raises(lib.ColibriError):
         lib.train(bytes([6, 7, 0]), DOSKIPGRAMS=1, DOSKIPGRAMS_EXHAUSTIVE=1)  # patternmodel.h:958-963
+
+
+@pytest.mark.parametrize("seed", range(120))
+def test_gpu_equals_oracle_on_random_input(seed):
+    """Random small corpora (empty/ragged sentences, unknown class, missing final delimiter) x random supported option sets."""
+    import random
+
+    from test_oracle_vs_ref_random import random_case, random_corpus
+
+    rng = random.Random(5000 + seed)
+    body = random_corpus(rng)
+    if not body:
+        pytest.skip("empty corpus")
+    unindexed, skipgrams, cli = random_case(rng)
+    names = {"t": "MINTOKENS", "l": "MAXLENGTH", "m": "MINLENGTH", "y": "MINTOKENS_SKIPGRAMS", "T": "MINSKIPTYPES", "W": "MINTOKENS_UNIGRAMS"}
+    onames = {"t": "mintokens", "l": "maxlength", "m": "minlength", "y": "mintokens_skipgrams", "T": "minskiptypes", "W": "mintokens_unigrams"}
+    streamed = 1 if (unindexed and not skipgrams) else 0
+    okw = {onames[k]: v for k, v in cli.items()}
+    okw.update(indexed=0 if unindexed else 1, doskipgrams_exhaustive=1 if skipgrams else 0, streamed=streamed)
+    try:
+        want = oracle.train(body, **okw)
+    except RuntimeError:
+        with pytest.raises(cb().ColibriError):
+            cb().train(body, QUIET=1, model_type=10 if unindexed else 20, DOSKIPGRAMS_EXHAUSTIVE=int(skipgrams), streamed=streamed, **{names[k]: v for k, v in cli.items()})
+        return
+    try:
+        m = cb().train(body, QUIET=1, model_type=10 if unindexed else 20, DOSKIPGRAMS_EXHAUSTIVE=int(skipgrams), streamed=streamed, **{names[k]: v for k, v in cli.items()})
+    except cb().ColibriError as e:
+        assert e.code == 2, e  # only "outside the accelerated subset" is an acceptable refusal
+        pytest.skip("unsupported on the device path: %s" % e)
+    got = to_flat(m)
+    assert (got.tokens, got.types, len(got), got.maxn, got.minn, got.hasskipgrams) == (want.tokens, want.types, len(want), want.maxn, want.minn, want.hasskipgrams), (cli, unindexed, skipgrams)
+    assert got.passes == want.passes
+    assert got.same_patterns(want)

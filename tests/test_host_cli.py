@@ -63,3 +63,14 @@ def test_cli_model_files_equal_reference(cli, case):
         assert m.digest() == case["digest"]
         # the progress lines are the reference's: " Found X ngrams...pruned Y...total kept: Z"
         assert [(p[0], p[2]) for p in oracle.parse_ref_passes(r.stderr)] == [(p[0], p[2]) for p in case["passes"]]
+
+
+def test_host_api_mirror_cpp(cli, tmp_path):
+    """Compile and run tests/host/test_host_api.cpp against colibri-core_b200/host/*.h (Pattern semantics, hash KATs, refusals)."""
+    exe = str(tmp_path / "test_host_api")
+    libdir = os.path.join(ROOT, "colibri-core_b200", "lib")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "colibri-core_b200", "host"), os.path.join(ROOT, "tests", "host", "test_host_api.cpp"),
+                    "-L" + libdir, "-lcolibri_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    r = subprocess.run([exe, os.path.join(GOLDEN_DIR, "hamlet.colibri.dat")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "host API tests ok" in r.stderr and "FAILED" not in r.stderr

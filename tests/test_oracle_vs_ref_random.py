@@ -1,0 +1,77 @@
+"""Randomised pinning of the oracle: small random corpora x random option sets, oracle.c vs the UNMODIFIED reference binary
+(oracle/_ref/ref_train, compiled from /root/reference by `make -C oracle ref`).  Skipped where the reference build is absent."""
+import os
+import random
+import tempfile
+
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref (the compiled reference) is not present")
+
+CLI2OPT = {"t": "mintokens", "l": "maxlength", "m": "minlength", "y": "mintokens_skipgrams", "T": "minskiptypes", "W": "mintokens_unigrams"}
+
+
+def random_corpus(rng):
+    vocab = rng.choice([3, 5, 12, 40, 300, 20000])
+    sentences = []
+    for _ in range(rng.randint(1, 60)):
+        n = rng.choice([0, 0, 1, 2, 3, 5, 8, 13, 30]) if rng.random() < 0.3 else rng.randint(1, 25)
+        # classes 6.. (never the reserved 0-5); a Zipf-ish skew so that patterns repeat; occasionally the unknown class 2
+        sent = [2 if rng.random() < 0.02 else 6 + min(int(rng.paretovariate(1.1)) - 1, vocab - 1) for _ in range(n)]
+        sentences.append(sent)
+    body = oracle.encode_corpus(sentences)
+    if rng.random() < 0.25 and len(body) > 1 and body[-2] != 0:
+        body = body[:-1]  # drop the final end-of-sentence marker (reader quirk, src/pattern.cpp:483-587)
+    return body
+
+
+def random_case(rng):
+    unindexed = rng.random() < 0.7
+    skipgrams = unindexed and rng.random() < 0.4
+    cli = {"t": rng.choice([1, 2, 2, 2, 3, 4]), "l": rng.choice([1, 2, 3, 4, 5, 6, 8])}
+    if rng.random() < 0.25 and not skipgrams and cli["t"] > 1:
+        cli["m"] = rng.randint(1, min(3, cli["l"]))
+    if skipgrams:
+        if rng.random() < 0.5:
+            cli["y"] = rng.randint(1, 4)
+        if rng.random() < 0.5:
+            cli["T"] = rng.choice([1, 2])
+    if rng.random() < 0.2 and cli["t"] > 1 and cli.get("m", 1) == 1:
+        cli["W"] = rng.randint(1, 4)
+    return unindexed, skipgrams, cli
+
+
+@pytest.mark.parametrize("seed", range(200))
+def test_oracle_equals_reference_on_random_input(seed):
+    rng = random.Random(1000 + seed)
+    body = random_corpus(rng)
+    if not body:
+        pytest.skip("empty corpus")
+    unindexed, skipgrams, cli = random_case(rng)
+    opts = {CLI2OPT[k]: v for k, v in cli.items()}
+    opts["indexed"] = 0 if unindexed else 1
+    opts["doskipgrams_exhaustive"] = 1 if skipgrams else 0
+    opts["streamed"] = 1 if (unindexed and not skipgrams) else 0  # what the CLI does (src/patternmodeller.cpp:721-754)
+    with tempfile.TemporaryDirectory() as td:
+        cpath, mpath = os.path.join(td, "c.colibri.dat"), os.path.join(td, "m")
+        with open(cpath, "wb") as f:
+            f.write(b"\xa2\x02" + body)
+        try:
+            st, err = oracle.ref_train(cpath, mpath, unindexed=unindexed, skipgrams=skipgrams, timeout=60, **cli)
+        except RuntimeError as e:
+            # the reference itself rejects some inputs (e.g. a corpus consisting of one unterminated delimiter); the oracle must refuse too
+            with pytest.raises(RuntimeError):
+                oracle.train(body, **opts)
+            return
+        ref = oracle.parse_modelfile(open(mpath, "rb").read())
+    try:
+        mine = oracle.train(body, **opts)
+    except RuntimeError as e:
+        if "not restated" in str(e):
+            pytest.skip(str(e))
+        raise
+    assert (mine.tokens, mine.types, len(mine), mine.maxn, mine.minn, int(mine.hasskipgrams)) == (st["tokens"], st["types"], st["patterns"], st["maxn"], st["minn"], st["hasskipgrams"]), (cli, unindexed, skipgrams)
+    assert [(p[1], p[3]) for p in mine.passes] == [(p[0], p[2]) for p in oracle.parse_ref_passes(err)]
+    assert mine.same_patterns(ref)

@@ -290,11 +290,11 @@ def run_ours(a):
         host.numpy()[:] = corpus.download()
         npat, kb, _ = last.export_sizes()
         out_keys = torch.empty(int(kb * 1.05) + 64, dtype=torch.uint8, pin_memory=True)
-        out_off = torch.empty(int(npat * 1.05) + 64, dtype=torch.int64, pin_memory=True)
+        out_len = torch.empty(int(npat * 1.05) + 64, dtype=torch.int16, pin_memory=True)
         out_cnt = torch.empty(int(npat * 1.05) + 64, dtype=torch.int32, pin_memory=True)
         for _ in range(max(1, a.warmup)):
             m = cb.train_host_pointer(host.data_ptr(), nbytes, opts)
-            m.export_into(out_keys.data_ptr(), out_off.data_ptr(), out_cnt.data_ptr())
+            m.export_compact_into(out_keys.data_ptr(), out_len.data_ptr(), out_cnt.data_ptr())
             m.close()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -304,14 +304,14 @@ def run_ours(a):
         for _ in range(a.steps):
             m = cb.train_host_pointer(host.data_ptr(), nbytes, opts)
             n2, kb2, _ = m.export_sizes()
-            m.export_into(out_keys.data_ptr(), out_off.data_ptr(), out_cnt.data_ptr())
-            d2h = kb2 + 8 * (n2 + 1) + 4 * n2
+            m.export_compact_into(out_keys.data_ptr(), out_len.data_ptr(), out_cnt.data_ptr())
+            d2h = kb2 + 2 * n2 + 4 * n2
             m.close()
         e1.record()
         barrier()
         e2e_s = max(time.perf_counter() - t0, e0.elapsed_time(e1) / 1e3)
         line["e2e"] = {"value": tokens * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / a.steps,
-                       "api": "colibri_b200_train(host corpus) + colibri_b200_model_export(host keys/offsets/counts), pinned host memory"}
+                       "api": "colibri_b200_train(host corpus) + colibri_b200_model_export_compact(host keys/lengths/counts), pinned host memory"}
 
     # ---- the reference's CPU path beside it (bounded sample)
     if not a.no_cpu_baseline:

@@ -90,6 +90,7 @@ def library():
     L.colibri_b200_model_pass_stats.argtypes = [C.c_void_p, C.c_int, _u64p]
     L.colibri_b200_model_export_sizes.argtypes = [C.c_void_p, _u64p, _u64p, _u64p]
     L.colibri_b200_model_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.colibri_b200_model_export_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.colibri_b200_model_write.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.colibri_b200_model_lookup.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, _u32p]
     L.colibri_b200_model_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -107,6 +108,11 @@ def library():
     L.colibri_b200_shard_level_owner.argtypes = [C.c_void_p, C.c_void_p, _u64p, C.c_void_p, _u64p, _u64p]
     L.colibri_b200_shard_level_owner_survivors.argtypes = [C.c_void_p, C.c_void_p]
     L.colibri_b200_shard_level_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _u64p, _u64p]
+    L.colibri_b200_shard_skip_split_count.argtypes = [C.c_void_p, _u64p, _u64p]
+    L.colibri_b200_shard_skip_split_write.argtypes = [C.c_void_p, C.c_void_p]
+    L.colibri_b200_shard_skip_owner.argtypes = [C.c_void_p, C.c_void_p, _u64p, _u64p, _u64p]
+    L.colibri_b200_shard_skip_owner_survivors.argtypes = [C.c_void_p, C.c_void_p]
+    L.colibri_b200_shard_skip_finish.argtypes = [C.c_void_p, C.c_void_p, _u64p]
     L.colibri_b200_shard_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.colibri_b200_shard_set_peers.argtypes = [C.c_void_p, _u64p, _u64p, _u64p, _u64p, C.c_uint64, C.c_uint64]
     L.colibri_b200_shard_p2p_split.argtypes = [C.c_void_p, C.c_int, _u64p]
@@ -307,6 +313,16 @@ class Model:
     def export_into(self, keys_ptr, off_ptr, counts_ptr):
         """Export into caller-owned (e.g. pinned) host buffers given as raw addresses."""
         _check(library().colibri_b200_model_export(self._h, keys_ptr, off_ptr, counts_ptr, None, None, None))
+
+    def export_compact(self):
+        """(keys blob, key_len uint16[n], counts uint32[n]): the flat model without the 8-byte offsets."""
+        n, kb, _ = self.export_sizes()
+        keys, lens, counts = np.empty(kb, dtype=np.uint8), np.empty(n, dtype=np.uint16), np.empty(n, dtype=np.uint32)
+        _check(library().colibri_b200_model_export_compact(self._h, keys.ctypes.data, lens.ctypes.data, counts.ctypes.data))
+        return keys, lens, counts
+
+    def export_compact_into(self, keys_ptr, len_ptr, counts_ptr):
+        _check(library().colibri_b200_model_export_compact(self._h, keys_ptr, len_ptr, counts_ptr))
 
     def to_bytes(self) -> bytes:
         """The .colibri.patternmodel byte stream (reference include/patternmodel.h:1609-1624)."""

@@ -184,7 +184,8 @@ namespace {
 
 // compute_skip_configurations (reference src/algorithms.cpp:79-94): every non-empty subset of the inner positions
 // 1..n-2, dropped when it has more than maxskips separate gaps (and n-2 >= maxskips)
-int skip_masks(int n, int maxskips, std::vector<SkipMask>& out) {
+}  // namespace
+int colibri::skip_masks(int n, int maxskips, std::vector<SkipMask>& out) {
     out.clear();
     if (n < 3) return 0;
     if (n > 24) return set_err(COLIBRI_E_UNSUPPORTED, "skipgrams of %d tokens: the device key holds masks up to n=24", n);
@@ -221,7 +222,6 @@ int skip_masks(int n, int maxskips, std::vector<SkipMask>& out) {
     return 0;
 }
 
-}  // namespace
 int colibri::check_options(colibri_b200_options& o) {
     // include/patternmodel.h:883-888
     if (o.MINTOKENS == -1) o.MINTOKENS = 2;
@@ -705,7 +705,8 @@ int colibri::export_segments(int dev, cudaStream_t s, std::vector<Segment>& segs
         }
         base += sg.count;
     }
-    launches += launch_export_lengths(s, tok, pos.p, nm.p, total, lens.p);
+    TRY(m->d_len16.alloc(dev, total));
+    launches += launch_export_lengths(s, tok, pos.p, nm.p, total, lens.p, m->d_len16.p);
     launches += launch_exclusive_scan_u32_u64(s, lens.p, m->d_off.p, total, tmp.p);
     uint64_t kb = 0;
     CUDA_TRY(cudaMemcpyAsync(&kb, m->d_off.p + total, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -803,6 +804,18 @@ extern "C" int colibri_b200_model_export(colibri_b200_model* m, uint8_t* keys, u
         if (ref_off) CUDA_TRY(cudaMemcpyAsync(ref_off, m->d_ref_off.p, (m->npatterns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, m->stream));
         if (ref_sentence && m->nrefs) CUDA_TRY(cudaMemcpyAsync(ref_sentence, m->d_ref_sentence.p, m->nrefs * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
         if (ref_token && m->nrefs) CUDA_TRY(cudaMemcpyAsync(ref_token, m->d_ref_token.p, m->nrefs * sizeof(uint16_t), cudaMemcpyDeviceToHost, m->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+// compact flat form: key_len[npatterns] (bytes per key, u16) instead of the u64 offsets -- 2 instead of 8 bytes per pattern over PCIe
+extern "C" int colibri_b200_model_export_compact(colibri_b200_model* m, uint8_t* keys, uint16_t* key_len, uint32_t* counts) {
+    if (!m || !key_len) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    if (m->keybytes && keys) CUDA_TRY(cudaMemcpyAsync(keys, m->d_keys.p, m->keybytes, cudaMemcpyDeviceToHost, m->stream));
+    if (m->npatterns) {
+        CUDA_TRY(cudaMemcpyAsync(key_len, m->d_len16.p, m->npatterns * sizeof(uint16_t), cudaMemcpyDeviceToHost, m->stream));
+        if (counts) CUDA_TRY(cudaMemcpyAsync(counts, m->d_counts.p, m->npatterns * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     return 0;

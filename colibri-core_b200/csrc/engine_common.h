@@ -190,6 +190,8 @@ struct Segment {  // survivors of one (level, category)
 };
 
 int check_options(colibri_b200_options& o);
+// compute_skip_configurations (reference src/algorithms.cpp:79-94) with the run decomposition the kernels need
+int skip_masks(int n, int maxskips, std::vector<SkipMask>& out);
 
 }  // namespace colibri
 
@@ -224,6 +226,7 @@ struct colibri_b200_model {
     DevBuf<uint8_t>  d_keys;
     DevBuf<uint64_t> d_off;
     DevBuf<uint32_t> d_counts;
+    DevBuf<uint16_t> d_len16;         // key length in bytes per pattern (compact export)
     DevBuf<uint32_t> d_ref_sentence;  // indexed models only
     DevBuf<uint16_t> d_ref_token;
     DevBuf<uint64_t> d_ref_off;

@@ -679,9 +679,13 @@ __device__ __forceinline__ uint32_t pattern_bytes(const uint32_t* __restrict__ t
 }
 
 __global__ void __launch_bounds__(256) export_lengths_kernel(const uint32_t* __restrict__ tok, const uint32_t* __restrict__ sv_pos, const uint32_t* __restrict__ sv_nm, uint64_t n,
-                                                             uint32_t* __restrict__ lens) {
+                                                             uint32_t* __restrict__ lens, uint16_t* __restrict__ lens16) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) lens[i] = pattern_bytes(tok, sv_pos[i], sv_nm[i], nullptr);
+    if (i < n) {
+        uint32_t l = pattern_bytes(tok, sv_pos[i], sv_nm[i], nullptr);
+        lens[i]    = l;
+        lens16[i]  = (uint16_t)l;  // <= 255 tokens x 5 bytes
+    }
 }
 __global__ void __launch_bounds__(256) export_write_kernel(const uint32_t* __restrict__ tok, const uint32_t* __restrict__ sv_pos, const uint32_t* __restrict__ sv_nm,
                                                            const uint64_t* __restrict__ off, uint64_t n, uint8_t* __restrict__ keys) {
@@ -768,9 +772,9 @@ int launch_fill_u32(cudaStream_t s, uint32_t* dst, uint64_t n, uint32_t value) {
     fill_u32_kernel<<<div_up(n, 256), 256, 0, s>>>(dst, n, value);
     return 1;
 }
-int launch_export_lengths(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, uint64_t n, uint32_t* lens) {
+int launch_export_lengths(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, uint64_t n, uint32_t* lens, uint16_t* lens16) {
     if (!n) return 0;
-    export_lengths_kernel<<<div_up(n, 256), 256, 0, s>>>(tok, sv_pos, sv_nm, n, lens);
+    export_lengths_kernel<<<div_up(n, 256), 256, 0, s>>>(tok, sv_pos, sv_nm, n, lens, lens16);
     return 1;
 }
 int launch_exclusive_scan_u32_u64(cudaStream_t s, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* tmp) {

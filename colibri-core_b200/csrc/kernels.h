@@ -89,7 +89,7 @@ int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, 
 // sv_nm[i] = n | mask << 8 ; for n == 1 sv_pos holds the class id itself
 int launch_fill_u32(cudaStream_t s, uint32_t* dst, uint64_t n, uint32_t value);
 int launch_pack_nm(cudaStream_t s, uint32_t* nm /*in: gap masks, out: n | mask << 8*/, uint64_t count, uint32_t n);
-int launch_export_lengths(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, uint64_t n, uint32_t* lens);
+int launch_export_lengths(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, uint64_t n, uint32_t* lens, uint16_t* lens16);
 int launch_exclusive_scan_u32_u64(cudaStream_t s, const uint32_t* in, uint64_t* out /*n+1*/, uint64_t n, uint64_t* tmp /*>= n/2048+2*/);
 int launch_export_write(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, const uint64_t* off, uint64_t n, uint8_t* keys);
 // model-file body: per pattern  key bytes, 0x00, u32 count  (unindexed; patternstore.h:534-542 + datatypes.h:216-221)
@@ -125,6 +125,15 @@ int launch_owner_survivors(cudaStream_t s, const uint32_t* sv_idx, const uint32_
                            const unsigned long long* out_base, unsigned long long* cursors, void* out, int sms);
 int launch_sender_relabel(cudaStream_t s, const uint32_t* rec_of_pos, const uint32_t* reply, uint64_t npos, uint32_t* cur, DeviceStats* st, int sms);
 int launch_sender_survivors(cudaStream_t s, const void* recs, uint64_t n, const uint32_t* pos_of_rec, uint64_t send_base, uint32_t* sv_pos, uint32_t* sv_count);
+
+// skipgrams on the multi-GPU path
+int launch_skip_split_count(cudaStream_t s, const uint32_t* const* ids, int n, const SkipMask* masks, int nmasks, uint64_t npos, uint32_t world, unsigned long long* dest_counts, int sms);
+int launch_skip_split_write(cudaStream_t s, const uint32_t* const* ids, int n, const SkipMask* masks, int nmasks, uint64_t npos, uint32_t world, const unsigned long long* dest_base,
+                            unsigned long long* cursors, void* send /* 16 B keys */, uint32_t* pos_of_rec, int sms);
+int launch_skip_stream_count(cudaStream_t s, const void* recv, uint64_t n, SkipSlot* table, uint64_t cap, DeviceStats* st, int sms);
+int launch_skip_owner_survivors(cudaStream_t s, const uint32_t* sv_idx, const uint32_t* sv_count, const uint32_t* sv_mask, uint64_t n, uint32_t world, const unsigned long long* src_base,
+                                const unsigned long long* out_base, unsigned long long* cursors, void* out /* 16 B records */, int sms);
+int launch_skip_sender_survivors(cudaStream_t s, const void* recs, uint64_t n, const uint32_t* pos_of_rec, uint64_t send_base, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask);
 
 // ---- parity helpers / measurement input
 int launch_hash64_batch(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t n, uint64_t* out);

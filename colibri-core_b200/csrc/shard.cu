@@ -45,6 +45,14 @@ struct colibri_b200_shard {
     DevBuf<void*>        d_peer;   // [0..64) keys_rx, [64..128) reply_rx, [128..192) surv_rx, [192..256) hdr
     DevBuf<unsigned long long> d_vals;
     DevBuf<uint32_t>     rid;
+    // skipgrams: every level's (global) ids are kept, the parts of a skipgram are looked up in them
+    std::vector<DevBuf<uint32_t>> ids_keep;
+    DevBuf<const uint32_t*> d_idptrs;
+    DevBuf<SkipMask>     d_masks;
+    DevBuf<SkipSlot>     sktable;
+    DevBuf<uint32_t>     sk_pos_of_rec, sk_sv_idx, sk_sv_cnt, sk_sv_mask;
+    int                  sk_nmasks = 0;
+    uint64_t             sk_send_base[65] = {0}, sk_nsent = 0, sk_nsurv = 0;
     int                  level = 1;
     uint32_t             t = 2;
     std::vector<Segment> segs;
@@ -53,6 +61,15 @@ struct colibri_b200_shard {
     double               device_ms = 0;
     double               phase_ms[8] = {0};  // begin, unigrams, count, pack, merge, finish, export
 };
+
+// skipgram mode: remember the id array of level n (sh->prev after the level's finish)
+static int keep_ids(colibri_b200_shard* sh, int n) {
+    if (!sh->o.DOSKIPGRAMS_EXHAUSTIVE) return 0;
+    if ((int)sh->ids_keep.size() <= n) sh->ids_keep.resize(n + 1);
+    TRY(sh->ids_keep[n].alloc(sh->dev, sh->npos + 8));
+    CUDA_TRY(cudaMemcpyAsync(sh->ids_keep[n].p, sh->prev.p, (sh->npos + 8) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh->s));
+    return 0;
+}
 
 static int zero_phase_stats(colibri_b200_shard* sh) {
     CUDA_TRY(cudaMemsetAsync(&sh->d_stats.p->found, 0, offsetof(DeviceStats, maxclass) - offsetof(DeviceStats, found), sh->s));
@@ -98,7 +115,7 @@ extern "C" int colibri_b200_shard_begin(colibri_b200_corpus* corpus, const colib
     if (world < 1 || world > 64 || rank < 0 || rank >= world) return set_err(COLIBRI_E_INVALID, "rank %d / world %d", rank, world);
     colibri_b200_options o = *opt;
     TRY(check_options(o));
-    if (o.DOSKIPGRAMS_EXHAUSTIVE) return set_err(COLIBRI_E_UNSUPPORTED, "skipgrams are not on the multi-GPU path yet");
+    if (o.model_type == COLIBRI_INDEXEDPATTERNMODEL) return set_err(COLIBRI_E_UNSUPPORTED, "indexed models are not on the multi-GPU path yet");
     if (o.MINLENGTH > 1) return set_err(COLIBRI_E_UNSUPPORTED, "MINLENGTH > 1 is not on the multi-GPU path yet");
     if (corpus->nbytes == 0) return set_err(COLIBRI_E_FORMAT, "Attempting to read pattern from file, but file is empty?");
     CUDA_TRY(cudaSetDevice(corpus->device));
@@ -213,9 +230,11 @@ extern "C" int colibri_b200_shard_unigram_finish(colibri_b200_shard* sh, const v
     TRY(sh->prev.alloc(sh->dev, sh->npos + 8));
     TRY(sh->cur.alloc(sh->dev, sh->npos + 8));
     sh->launches += launch_make_id1(s, sh->tok.p, sh->npos + 1, sh->count1.p, t1, sh->prev.p);
+    CUDA_TRY(cudaMemsetAsync(sh->prev.p + sh->npos, 0, 8 * sizeof(uint32_t), s));
+    sh->level = 1;
+    TRY(keep_ids(sh, 1));
     CUDA_TRY(cudaStreamSynchronize(s));
     sh->prev_valid = sh->local_tokens;
-    sh->level      = 1;
     return 0;
 }
 
@@ -378,6 +397,7 @@ extern "C" int colibri_b200_shard_level_finish(colibri_b200_shard* sh, const voi
     if (local_valid) *local_valid = sh->prev_valid;
     std::swap(sh->prev, sh->cur);
     sh->level = n;
+    TRY(keep_ids(sh, n));
     return 0;
 }
 
@@ -567,6 +587,155 @@ extern "C" int colibri_b200_shard_p2p_finish(colibri_b200_shard* sh, uint64_t gl
     if (local_valid) *local_valid = sh->prev_valid;
     std::swap(sh->prev, sh->cur);
     sh->level = n;
+    TRY(keep_ids(sh, n));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Skipgrams of the level just finished (n = current level >= 3; exhaustive mode).  Every valid window of level n sends one
+// 16-byte key per gap mask to the key's owner; owners count, apply the skipgram threshold and return the survivors to the
+// rank whose record claimed the slot.  Nothing else comes back: skipgrams feed no later level.
+extern "C" int colibri_b200_shard_skip_split_count(colibri_b200_shard* sh, uint64_t* send_counts, uint64_t* nrecords) {
+    if (!sh || !send_counts || !nrecords) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    PhaseClock clk(sh, 2);
+    cudaStream_t s = sh->s;
+    const int    n = sh->level;
+    *nrecords      = 0;
+    for (uint32_t d = 0; d < sh->world; ++d) send_counts[d] = 0;
+    sh->sk_nmasks = 0;
+    sh->sk_nsent  = 0;
+    if (!sh->o.DOSKIPGRAMS_EXHAUSTIVE || n < 3) return 0;
+    std::vector<SkipMask> masks;
+    TRY(skip_masks(n, sh->o.MAXSKIPS, masks));
+    for (auto& m : masks)
+        if (m.nparts > 3) return set_err(COLIBRI_E_UNSUPPORTED, "skipgrams with more than 3 non-gap runs (n >= 7) are not on the multi-GPU path");
+    if (masks.empty()) return 0;
+    sh->sk_nmasks = (int)masks.size();
+    std::vector<const uint32_t*> ptrs(n, nullptr);
+    for (int k = 1; k < n; ++k) ptrs[k] = sh->ids_keep[k].p;
+    TRY(sh->d_idptrs.alloc(sh->dev, n));
+    TRY(sh->d_masks.alloc(sh->dev, masks.size()));
+    if (sh->d_aux.n < 260) TRY(sh->d_aux.alloc(sh->dev, 260));
+    CUDA_TRY(cudaMemcpyAsync(sh->d_idptrs.p, ptrs.data(), n * sizeof(uint32_t*), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(sh->d_masks.p, masks.data(), masks.size() * sizeof(SkipMask), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(sh->d_aux.p, 0, 260 * sizeof(unsigned long long), s));
+    sh->launches += launch_skip_split_count(s, sh->d_idptrs.p, n, sh->d_masks.p, sh->sk_nmasks, sh->npos, sh->world, sh->d_aux.p + 195, sh->sms);
+    unsigned long long cnt[64];
+    CUDA_TRY(cudaMemcpyAsync(cnt, sh->d_aux.p + 195, sh->world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));  // also keeps ptrs/masks alive until the copies are done
+    unsigned long long bases[65];
+    uint64_t acc = 0;
+    for (uint32_t d = 0; d < sh->world; ++d) {
+        send_counts[d]      = cnt[d];
+        bases[d]            = acc;
+        sh->sk_send_base[d] = acc;
+        acc += cnt[d];
+    }
+    sh->sk_send_base[sh->world] = acc;
+    sh->sk_nsent                = acc;
+    *nrecords                   = acc;
+    CUDA_TRY(cudaMemcpyAsync(sh->d_aux.p + 65, bases, sh->world * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+extern "C" int colibri_b200_shard_skip_split_write(colibri_b200_shard* sh, void* dev_send) {
+    if (!sh || (!dev_send && sh->sk_nsent)) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    if (!sh->sk_nsent) return 0;
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    PhaseClock clk(sh, 3);
+    TRY(sh->sk_pos_of_rec.alloc(sh->dev, sh->sk_nsent));
+    sh->launches += launch_skip_split_write(sh->s, sh->d_idptrs.p, sh->level, sh->d_masks.p, sh->sk_nmasks, sh->npos, sh->world, sh->d_aux.p + 65, sh->d_aux.p + 130, dev_send,
+                                            sh->sk_pos_of_rec.p, sh->sms);
+    CUDA_TRY(cudaStreamSynchronize(sh->s));
+    return 0;
+}
+// stats = {distinct skipgrams owned, kept}; surv_counts[world]
+extern "C" int colibri_b200_shard_skip_owner(colibri_b200_shard* sh, const void* dev_recv, const uint64_t* recv_counts, uint64_t stats[2], uint64_t* surv_counts) {
+    if (!sh || !recv_counts || !stats || !surv_counts) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    PhaseClock clk(sh, 4);
+    cudaStream_t s = sh->s;
+    unsigned long long src_base[65];
+    uint64_t nrecv = 0;
+    for (uint32_t r = 0; r < sh->world; ++r) {
+        src_base[r] = nrecv;
+        nrecv += recv_counts[r];
+        surv_counts[r] = 0;
+    }
+    src_base[sh->world] = nrecv;
+    stats[0] = stats[1] = 0;
+    sh->sk_nsurv = 0;
+    if (nrecv == 0) return 0;
+    if (!dev_recv) return set_err(COLIBRI_E_INVALID, "NULL buffer");
+    if (nrecv >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner received %llu skipgram records", (unsigned long long)nrecv);
+    if (sh->d_aux.n < 260) TRY(sh->d_aux.alloc(sh->dev, 260));
+    CUDA_TRY(cudaMemsetAsync(sh->d_aux.p, 0, 260 * sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemcpyAsync(sh->d_aux.p, src_base, (sh->world + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    // PatternModel::pruneskipgrams returns early when minskiptypes <= 1 (reference :2170-2171): then only MINTOKENS applies
+    const uint32_t ts = sh->o.MINSKIPTYPES > 1 ? (uint32_t)sh->o.MINTOKENS_SKIPGRAMS : sh->t;
+    uint64_t cap = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);
+    if (sh->sktable.n < cap) TRY(sh->sktable.alloc(sh->dev, cap));
+    CUDA_TRY(cudaMemsetAsync(sh->sktable.p, 0, cap * sizeof(SkipSlot), s));
+    TRY(zero_phase_stats(sh));
+    sh->launches += launch_skip_stream_count(s, dev_recv, nrecv, sh->sktable.p, cap, sh->d_stats.p, sh->sms);
+    const uint64_t bound = nrecv / std::max<uint32_t>(ts, 1) + 1;
+    if (sh->sk_sv_idx.n < bound) TRY(sh->sk_sv_idx.alloc(sh->dev, bound));
+    if (sh->sk_sv_cnt.n < bound) TRY(sh->sk_sv_cnt.alloc(sh->dev, bound));
+    if (sh->sk_sv_mask.n < bound) TRY(sh->sk_sv_mask.alloc(sh->dev, bound));
+    sh->launches += launch_prune_skipgrams(s, sh->sktable.p, cap, ts, sh->sk_sv_idx.p, sh->sk_sv_cnt.p, sh->sk_sv_mask.p, sh->d_stats.p, sh->sms);
+    TRY(read_stats(sh));
+    stats[0]     = sh->h_stats.found;
+    stats[1]     = sh->h_stats.kept;
+    sh->sk_nsurv = sh->h_stats.kept;
+    sh->launches += launch_owner_survivor_counts(s, sh->sk_sv_idx.p, sh->sk_nsurv, sh->world, sh->d_aux.p, sh->d_aux.p + 195, sh->sms);
+    unsigned long long cnt[64];
+    CUDA_TRY(cudaMemcpyAsync(cnt, sh->d_aux.p + 195, sh->world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    unsigned long long obase[65];
+    uint64_t acc = 0;
+    for (uint32_t r = 0; r < sh->world; ++r) {
+        surv_counts[r] = cnt[r];
+        obase[r]       = acc;
+        acc += cnt[r];
+    }
+    CUDA_TRY(cudaMemcpyAsync(sh->d_aux.p + 65, obase, sh->world * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+extern "C" int colibri_b200_shard_skip_owner_survivors(colibri_b200_shard* sh, void* dev_out) {
+    if (!sh || (!dev_out && sh->sk_nsurv)) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    if (!sh->sk_nsurv) return 0;
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    PhaseClock clk(sh, 4);
+    sh->launches += launch_skip_owner_survivors(sh->s, sh->sk_sv_idx.p, sh->sk_sv_cnt.p, sh->sk_sv_mask.p, sh->sk_nsurv, sh->world, sh->d_aux.p, sh->d_aux.p + 65, sh->d_aux.p + 130, dev_out,
+                                                sh->sms);
+    CUDA_TRY(cudaStreamSynchronize(sh->s));
+    return 0;
+}
+extern "C" int colibri_b200_shard_skip_finish(colibri_b200_shard* sh, const void* dev_surv, const uint64_t* surv_counts) {
+    if (!sh || !surv_counts) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(sh->dev));
+    PhaseClock clk(sh, 5);
+    uint64_t total = 0;
+    for (uint32_t g = 0; g < sh->world; ++g) total += surv_counts[g];
+    if (!total) return 0;
+    if (!dev_surv) return set_err(COLIBRI_E_INVALID, "NULL survivor buffer");
+    Segment sg;
+    sg.n    = sh->level;
+    sg.skip = true;
+    TRY(sg.pos.alloc(sh->dev, total));
+    TRY(sg.cnt.alloc(sh->dev, total));
+    TRY(sg.mask.alloc(sh->dev, total));
+    uint64_t off = 0;
+    for (uint32_t g = 0; g < sh->world; ++g) {
+        sh->launches += launch_skip_sender_survivors(sh->s, (const uint8_t*)dev_surv + off * 16, surv_counts[g], sh->sk_pos_of_rec.p, sh->sk_send_base[g], sg.pos.p + off, sg.cnt.p + off,
+                                                     sg.mask.p + off);
+        off += surv_counts[g];
+    }
+    CUDA_TRY(cudaStreamSynchronize(sh->s));
+    sg.count = total;
+    sh->segs.push_back(std::move(sg));
     return 0;
 }
 
@@ -587,7 +756,10 @@ extern "C" int colibri_b200_shard_finish(colibri_b200_shard* sh, const uint64_t*
     m->totaltypes  = global_types;
     m->maxn        = maxn;
     m->minn        = minn;
-    for (int p = 0; p < npasses; ++p) m->passes.push_back({passes[4 * p], passes[4 * p + 1], passes[4 * p + 2], passes[4 * p + 3]});
+    for (int p = 0; p < npasses; ++p) {
+        m->passes.push_back({passes[4 * p], passes[4 * p + 1], passes[4 * p + 2], passes[4 * p + 3]});
+        if (passes[4 * p + 2]) m->hasskipgrams = 1;
+    }
     int rc;
     {
         PhaseClock clk(sh, 6);

@@ -502,3 +502,183 @@ int launch_sender_survivors(cudaStream_t s, const void* recs, uint64_t n, const 
 }
 
 }  // namespace colibri
+
+// =============================================================================================================================
+// Skipgrams on the multi-GPU path (exhaustive mode, reference include/patternmodel.h:1163-1171).  A skipgram's key is
+// (mask, global ids of its <= 3 contiguous non-gap runs) -- global because every level's ids are global here -- so the same
+// "ship it to its owner" scheme applies, without the way back: skipgrams feed no later level, only the survivors return.
+namespace colibri {
+
+__device__ __forceinline__ uint32_t owner_of_key128(unsigned long long k0, unsigned long long k1, uint32_t world) {
+    unsigned long long z = (k0 ^ ((k1 << 29) | (k1 >> 35))) * 0x9E3779B97F4A7C15ull;
+    z ^= z >> 32;
+    z *= 0xD6E8FEB86659FD93ull;
+    return (uint32_t)__umul64hi(z, (unsigned long long)world);
+}
+
+// item t = (position p, mask m); returns false if the window is not valid at level n
+__device__ __forceinline__ bool skip_item_key(const uint32_t* const* __restrict__ ids, int n, const SkipMask* __restrict__ masks, int nmasks, uint64_t t, uint64_t& p,
+                                              unsigned long long& k0, unsigned long long& k1) {
+    p           = t / nmasks;
+    const int m = (int)(t - p * nmasks);
+    const uint32_t* prev = ids[n - 1];
+    if (__ldg(prev + p) == 0 || __ldg(prev + p + 1) == 0) return false;
+    const SkipMask* sm = masks + m;
+    const uint32_t  np = __ldg(&sm->nparts);
+    k0 = ((unsigned long long)__ldg(&sm->mask) << 32) | __ldg(ids[__ldg(&sm->len[0])] + p + __ldg(&sm->start[0]));
+    k1 = (unsigned long long)__ldg(ids[__ldg(&sm->len[1])] + p + __ldg(&sm->start[1])) << 32;
+    if (np > 2) k1 |= __ldg(ids[__ldg(&sm->len[2])] + p + __ldg(&sm->start[2]));
+    return true;
+}
+
+__global__ void __launch_bounds__(256) skip_split_count_kernel(const uint32_t* const* __restrict__ ids, int n, const SkipMask* __restrict__ masks, int nmasks, uint64_t npos,
+                                                               uint32_t world, unsigned long long* __restrict__ dest_counts) {
+    __shared__ uint32_t h[64];
+    if (threadIdx.x < 64) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t total = npos * (uint64_t)nmasks;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t           p;
+        unsigned long long k0, k1;
+        if (skip_item_key(ids, n, masks, nmasks, t, p, k0, k1)) atomicAdd(&h[owner_of_key128(k0, k1, world)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < world && h[threadIdx.x]) atomicAdd(&dest_counts[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+// 16-byte keys grouped by owner (order inside a group is free: nothing comes back per record), pos_of_rec[j] = window position
+__global__ void __launch_bounds__(256) skip_split_write_kernel(const uint32_t* const* __restrict__ ids, int n, const SkipMask* __restrict__ masks, int nmasks, uint64_t npos,
+                                                               uint32_t world, const unsigned long long* __restrict__ dest_base, unsigned long long* __restrict__ cursors,
+                                                               ulonglong2* __restrict__ send, uint32_t* __restrict__ pos_of_rec) {
+    __shared__ uint32_t tile_cnt[64];
+    __shared__ unsigned long long tile_base[64];
+    const uint64_t total  = npos * (uint64_t)nmasks;
+    const uint64_t ntiles = (total + 2047) / 2048;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x < 64) tile_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        unsigned long long k0[8], k1[8];
+        uint32_t           dest[8], rk[8], pos[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint64_t t = tile * 2048 + (uint64_t)k * 256 + threadIdx.x, p = 0;
+            dest[k]    = 0xFFFFFFFFu;
+            if (t < total && skip_item_key(ids, n, masks, nmasks, t, p, k0[k], k1[k])) {
+                dest[k] = owner_of_key128(k0[k], k1[k], world);
+                pos[k]  = (uint32_t)p;
+                rk[k]   = atomicAdd(&tile_cnt[dest[k]], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < world) {
+            uint32_t c = tile_cnt[threadIdx.x];
+            tile_base[threadIdx.x] = c ? dest_base[threadIdx.x] + atomicAdd(&cursors[threadIdx.x], (unsigned long long)c) : 0ull;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (dest[k] == 0xFFFFFFFFu) continue;
+            uint64_t j    = tile_base[dest[k]] + rk[k];
+            send[j]       = make_ulonglong2(k0[k], k1[k]);
+            pos_of_rec[j] = pos[k];
+        }
+        __syncthreads();
+    }
+}
+
+// owner: count the received skipgram keys; slot.pos = receive index of the claimer
+__global__ void __launch_bounds__(256) skip_stream_count_kernel(const ulonglong2* __restrict__ recv, uint64_t n, SkipSlot* __restrict__ table, uint64_t cap, DeviceStats* __restrict__ st) {
+    bool           full  = false;
+    const uint64_t limit = cap < 8192 ? cap : 8192;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const ulonglong2 key  = __ldcs(recv + i);
+        uint64_t         slot = fast_range(spooky_hash64_u128(key.x, key.y, 0), cap);
+        uint64_t         step = 0;
+        for (; step < limit; ++step) {
+            SkipSlot*          s  = table + slot;
+            ulonglong2         kv = __ldcg(reinterpret_cast<const ulonglong2*>(s));
+            unsigned long long c0 = kv.x, c1 = kv.y;
+            if (c0 == 0 || c1 == 0) {
+                sk_cas128(s, key.x, key.y, c0, c1);  // expects the all-zero key; the result is authoritative
+                if (c0 == 0 && c1 == 0) {
+                    s->pos = (uint32_t)i;
+                    c0     = key.x;
+                    c1     = key.y;
+                }
+            }
+            if (c0 == key.x && c1 == key.y) {
+                atomicAdd(&s->count, 1u);
+                break;
+            }
+            slot = slot + 1 == cap ? 0 : slot + 1;
+        }
+        if (step == limit) full = true;
+    }
+    if (full) atomicOr(&st->errflags, kErrTableFull);
+}
+
+// survivors (receive index, count, mask) -> per source: 16-byte records {index inside the source's group, count, mask, 0}
+__global__ void __launch_bounds__(256) skip_owner_survivors_kernel(const uint32_t* __restrict__ sv_idx, const uint32_t* __restrict__ sv_count, const uint32_t* __restrict__ sv_mask,
+                                                                   uint64_t n, uint32_t world, const unsigned long long* __restrict__ src_base,
+                                                                   const unsigned long long* __restrict__ out_base, unsigned long long* __restrict__ cursors, uint4* __restrict__ out) {
+    __shared__ unsigned long long sbase[65];
+    if (threadIdx.x <= world) sbase[threadIdx.x] = src_base[threadIdx.x];
+    __syncthreads();
+    const uint64_t rounded = (n + 31) / 32 * 32;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t src = 0xFFFFFFFFu, idx = 0;
+        if (i < n) {
+            idx = sv_idx[i];
+            src = 0;
+            while (src + 1 < world && (unsigned long long)idx >= sbase[src + 1]) ++src;
+        }
+        uint32_t peers = __match_any_sync(0xffffffffu, src);
+        if (i >= n) continue;
+        int      leader = __ffs(peers) - 1;
+        uint64_t base   = 0;
+        if ((int)lane_id() == leader) base = atomicAdd(&cursors[src], (unsigned long long)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        out[out_base[src] + base + __popc(peers & ((1u << lane_id()) - 1))] = make_uint4((uint32_t)(idx - sbase[src]), sv_count[i], sv_mask[i], 0u);
+    }
+}
+__global__ void __launch_bounds__(256) skip_sender_survivors_kernel(const uint4* __restrict__ recs, uint64_t n, const uint32_t* __restrict__ pos_of_rec, uint64_t send_base,
+                                                                    uint32_t* __restrict__ sv_pos, uint32_t* __restrict__ sv_count, uint32_t* __restrict__ sv_mask) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 r     = recs[i];
+    sv_pos[i]   = pos_of_rec[send_base + r.x];
+    sv_count[i] = r.y;
+    sv_mask[i]  = r.z;
+}
+
+int launch_skip_split_count(cudaStream_t s, const uint32_t* const* ids, int n, const SkipMask* masks, int nmasks, uint64_t npos, uint32_t world, unsigned long long* dest_counts, int sms) {
+    unsigned grid = (unsigned)sk_min(sk_div_up(npos * nmasks, 256), (uint64_t)sms * 16);
+    skip_split_count_kernel<<<grid ? grid : 1, 256, 0, s>>>(ids, n, masks, nmasks, npos, world, dest_counts);
+    return 1;
+}
+int launch_skip_split_write(cudaStream_t s, const uint32_t* const* ids, int n, const SkipMask* masks, int nmasks, uint64_t npos, uint32_t world, const unsigned long long* dest_base,
+                            unsigned long long* cursors, void* send, uint32_t* pos_of_rec, int sms) {
+    unsigned grid = (unsigned)sk_min(sk_div_up(npos * nmasks, 2048), (uint64_t)sms * 4);
+    skip_split_write_kernel<<<grid ? grid : 1, 256, 0, s>>>(ids, n, masks, nmasks, npos, world, dest_base, cursors, (ulonglong2*)send, pos_of_rec);
+    return 1;
+}
+int launch_skip_stream_count(cudaStream_t s, const void* recv, uint64_t n, SkipSlot* table, uint64_t cap, DeviceStats* st, int sms) {
+    if (!n) return 0;
+    unsigned grid = (unsigned)sk_min(sk_div_up(n, 256), (uint64_t)sms * 32);
+    skip_stream_count_kernel<<<grid, 256, 0, s>>>((const ulonglong2*)recv, n, table, cap, st);
+    return 1;
+}
+int launch_skip_owner_survivors(cudaStream_t s, const uint32_t* sv_idx, const uint32_t* sv_count, const uint32_t* sv_mask, uint64_t n, uint32_t world, const unsigned long long* src_base,
+                                const unsigned long long* out_base, unsigned long long* cursors, void* out, int sms) {
+    if (!n) return 0;
+    unsigned grid = (unsigned)sk_min(sk_div_up(n, 256), (uint64_t)sms * 8);
+    skip_owner_survivors_kernel<<<grid, 256, 0, s>>>(sv_idx, sv_count, sv_mask, n, world, src_base, out_base, cursors, (uint4*)out);
+    return 1;
+}
+int launch_skip_sender_survivors(cudaStream_t s, const void* recs, uint64_t n, const uint32_t* pos_of_rec, uint64_t send_base, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask) {
+    if (!n) return 0;
+    skip_sender_survivors_kernel<<<sk_div_up(n, 256), 256, 0, s>>>((const uint4*)recs, n, pos_of_rec, send_base, sv_pos, sv_count, sv_mask);
+    return 1;
+}
+
+}  // namespace colibri

@@ -106,6 +106,34 @@ class CudaShardEngine:
     def sync(self):
         self.torch.cuda.current_stream(self.device).synchronize()
 
+    # ---- exhaustive skipgrams of the level just finished
+    def skip_split_count(self):
+        counts = (C.c_uint64 * self.world)()
+        n = C.c_uint64()
+        self._check(self.lib.colibri_b200_shard_skip_split_count(self._h, counts, C.byref(n)))
+        return [int(x) for x in counts], int(n.value)
+
+    def skip_split_write(self, nsend):
+        buf = self.new_buffer(nsend * 4)
+        self._check(self.lib.colibri_b200_shard_skip_split_write(self._h, buf.data_ptr()))
+        return buf
+
+    def skip_owner(self, recv, recv_counts):
+        rc = (C.c_uint64 * self.world)(*recv_counts)
+        st = (C.c_uint64 * 2)()
+        sc = (C.c_uint64 * self.world)()
+        self._check(self.lib.colibri_b200_shard_skip_owner(self._h, recv.data_ptr(), rc, st, sc))
+        return tuple(int(x) for x in st), [int(x) for x in sc]
+
+    def skip_owner_survivors(self, nsurv):
+        buf = self.new_buffer(nsurv * 4)
+        self._check(self.lib.colibri_b200_shard_skip_owner_survivors(self._h, buf.data_ptr()))
+        return buf
+
+    def skip_finish(self, surv, surv_counts):
+        sc = (C.c_uint64 * self.world)(*surv_counts)
+        self._check(self.lib.colibri_b200_shard_skip_finish(self._h, surv.data_ptr(), sc))
+
     # ---- NVLink peer-store mode
     def use_peers(self, peers: "PeerBuffers"):
         self._check(self.lib.colibri_b200_shard_set_stream(self._h, C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)))
@@ -206,7 +234,22 @@ class _Stopwatch:
         self.t = now
 
 
-def train_distributed(engine, dist, torch, mintokens=2, maxlength=5):
+def _skipgram_level(engine, dist, torch, dev):
+    """Exhaustive skipgrams of the level the engine just finished: keys to their owners, survivors back.  Returns (found, kept) globally."""
+    send_counts, nsend = engine.skip_split_count()
+    send = engine.skip_split_write(nsend)
+    recv, recv_counts = _exchange(dist, torch, engine, send, send_counts, 4)
+    (f, k), surv_counts = engine.skip_owner(recv, recv_counts)
+    surv = engine.skip_owner_survivors(sum(surv_counts))
+    surv_recv, surv_recv_counts = _exchange(dist, torch, engine, surv, surv_counts, 4)
+    st = torch.tensor([f, k], dtype=torch.int64, device=dev)
+    dist.all_reduce(st, op=dist.ReduceOp.SUM)
+    engine.sync()
+    engine.skip_finish(surv_recv, surv_recv_counts)
+    return int(st[0].item()), int(st[1].item())
+
+
+def train_distributed(engine, dist, torch, mintokens=2, maxlength=5, skipgrams=False):
     """Drive one rank through all levels.  Returns (local model share, global passes, global header dict)."""
     world = dist.get_world_size()
     sw = _Stopwatch(engine)
@@ -247,7 +290,11 @@ def train_distributed(engine, dist, torch, mintokens=2, maxlength=5):
         sw.lap("p2p_finish")
         if gf == 0:
             break
-        passes.append((n, gf, 0, gf - gk))
+        sf = sk = 0
+        if skipgrams and n >= 3:
+            sf, sk = _skipgram_level(engine, dist, torch, dev)
+            sw.lap("skipgrams")
+        passes.append((n, gf, sf, (gf - gk) + (sf - sk)))
         maxn, minn = max(maxn, n), min(minn, n)
         prev_kept = gk
         n += 1
@@ -275,12 +322,16 @@ def train_distributed(engine, dist, torch, mintokens=2, maxlength=5):
         gf, gk, _gocc = (int(x) for x in st.tolist())
         if gf == 0:
             break  # "None found" (reference include/patternmodel.h:1189-1194)
-        passes.append((n, gf, 0, gf - gk))
+        sf = sk = 0
+        if skipgrams and n >= 3:
+            sf, sk = _skipgram_level(engine, dist, torch, dev)
+            sw.lap("skipgrams")
+        passes.append((n, gf, sf, (gf - gk) + (sf - sk)))
         maxn, minn = max(maxn, n), min(minn, n)
         prev_kept = gk
         n += 1
     if mintokens == 1 and passes:  # the reference reports one pass when every length is extracted in a single scan
-        passes = [(1, sum(p[1] for p in passes), 0, sum(p[3] for p in passes))]
+        passes = [(1, sum(p[1] for p in passes), sum(p[2] for p in passes), sum(p[3] for p in passes))]
     model = engine.finish(passes, types, maxn, minn)
     sw.lap("export")
     if sw.on:
@@ -295,7 +346,7 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
     import colibri_core_b200 as cb
 
     ntok = int(a.tokens)
-    opts = cb.PatternModelOptions(MINTOKENS=a.mintokens, MAXLENGTH=a.maxlength, streamed=1, QUIET=1, device=local)
+    opts = cb.PatternModelOptions(MINTOKENS=a.mintokens, MAXLENGTH=a.maxlength, DOSKIPGRAMS_EXHAUSTIVE=a.skipgrams, streamed=0 if a.skipgrams else 1, QUIET=1, device=local)
     corpus = cb.Corpus.synthetic(ntok, vocab=a.vocab, seed=a.seed, device=local, first_token=rank * ntok)
 
     def barrier():
@@ -314,7 +365,7 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
         eng = CudaShardEngine(corpus, opts, rank, world, local)
         if peers is not None:
             eng.use_peers(peers)
-        model, passes, head = train_distributed(eng, dist, torch, a.mintokens, a.maxlength)
+        model, passes, head = train_distributed(eng, dist, torch, a.mintokens, a.maxlength, bool(a.skipgrams))
         out = (len(model), head, passes, eng.device_ms(), eng.info()["launches"], eng.phase_ms())
         model.close()
         eng.close()
@@ -346,7 +397,7 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
     host.numpy()[:] = corpus.download()
     cap_pat = int(last[0] * 1.3) + 1024
     out_keys = torch.empty(cap_pat * 16, dtype=torch.uint8, pin_memory=True)
-    out_off = torch.empty(cap_pat + 1, dtype=torch.int64, pin_memory=True)
+    out_len = torch.empty(cap_pat + 1, dtype=torch.int16, pin_memory=True)
     out_cnt = torch.empty(cap_pat, dtype=torch.int32, pin_memory=True)
 
     def e2e_step():
@@ -354,15 +405,15 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
         eng = CudaShardEngine(c, opts, rank, world, local)
         if peers is not None:
             eng.use_peers(peers)
-        model, _, _ = train_distributed(eng, dist, torch, a.mintokens, a.maxlength)
+        model, _, _ = train_distributed(eng, dist, torch, a.mintokens, a.maxlength, bool(a.skipgrams))
         n, kb, _ = model.export_sizes()
         if n > cap_pat or kb > out_keys.numel():
             raise RuntimeError("e2e export buffers too small")
-        model.export_into(out_keys.data_ptr(), out_off.data_ptr(), out_cnt.data_ptr())
+        model.export_compact_into(out_keys.data_ptr(), out_len.data_ptr(), out_cnt.data_ptr())
         model.close()
         eng.close()
         c.close()
-        return kb + 8 * (n + 1) + 4 * n
+        return kb + 2 * n + 4 * n
 
     e2e_step()
     barrier()
@@ -393,7 +444,7 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
                          "hbm_read_roofline_frac": (a.maxlength * corpus.nbytes / (elapsed / a.steps) / 1e9) / peak},
             "clocks": clocks, "gpu_launches": int(npat[1].item()),
             "e2e": {"value": tokens * a.steps / float(e2e_t.item()), "unit": unit, "h2d_bytes_per_step": int(xfer[0].item()), "d2h_bytes_per_step": int(xfer[1].item()),
-                    "ms_per_step": 1e3 * float(e2e_t.item()) / a.steps, "api": "per rank: colibri_b200_corpus_stage(pinned host shard) + shard phases + NCCL + colibri_b200_model_export (pinned)"},
+                    "ms_per_step": 1e3 * float(e2e_t.item()) / a.steps, "api": "per rank: colibri_b200_corpus_stage(pinned host shard) + shard phases + NCCL + colibri_b200_model_export_compact (pinned)"},
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

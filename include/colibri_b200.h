@@ -106,6 +106,8 @@ int      colibri_b200_model_pass_stats(const colibri_b200_model* m, int pass, ui
  * (IndexReference, include/datatypes.h:33-89).  Pattern order is unspecified (so is the reference's). */
 int colibri_b200_model_export_sizes(colibri_b200_model* m, uint64_t* npatterns, uint64_t* keybytes, uint64_t* nrefs);
 int colibri_b200_model_export(colibri_b200_model* m, uint8_t* keys, uint64_t* key_off, uint32_t* counts, uint32_t* ref_sentence, uint16_t* ref_token, uint64_t* ref_off);
+/* the same without offsets: key_len[npatterns] = bytes of each key, in pattern order (2 instead of 8 bytes per pattern to copy) */
+int colibri_b200_model_export_compact(colibri_b200_model* m, uint8_t* keys, uint16_t* key_len, uint32_t* counts);
 /* the .colibri.patternmodel byte stream (include/patternmodel.h:1609-1624): returns needed size in *nbytes when buf is NULL */
 int colibri_b200_model_write(colibri_b200_model* m, uint8_t* buf, size_t cap, size_t* nbytes);
 /* occurrencecount(pattern) (include/patternmodel.h:1653-1669): key = pattern bytes without terminator; *count = 0 if absent */
@@ -156,6 +158,14 @@ int    colibri_b200_shard_level_split_write(colibri_b200_shard* sh, void* dev_se
 int    colibri_b200_shard_level_owner(colibri_b200_shard* sh, const void* dev_recv_keys, const uint64_t* recv_counts, void* dev_reply, uint64_t stats[3], uint64_t* surv_counts);
 int    colibri_b200_shard_level_owner_survivors(colibri_b200_shard* sh, void* dev_out /* 8 B per record, grouped by source */);
 int    colibri_b200_shard_level_finish(colibri_b200_shard* sh, const void* dev_reply_back, const void* dev_surv, const uint64_t* surv_counts /* per owner */, uint64_t* local_valid);
+/* exhaustive skipgrams of the level just finished (n >= 3): shard_skip_split_count, shard_skip_split_write,
+ * [all-to-all of 16-byte keys], shard_skip_owner, shard_skip_owner_survivors, [all-to-all of 16-byte survivor records],
+ * shard_skip_finish.  stats[0]=distinct skipgrams owned, [1]=kept. */
+int    colibri_b200_shard_skip_split_count(colibri_b200_shard* sh, uint64_t* send_counts, uint64_t* nrecords);
+int    colibri_b200_shard_skip_split_write(colibri_b200_shard* sh, void* dev_send);
+int    colibri_b200_shard_skip_owner(colibri_b200_shard* sh, const void* dev_recv, const uint64_t* recv_counts, uint64_t stats[2], uint64_t* surv_counts);
+int    colibri_b200_shard_skip_owner_survivors(colibri_b200_shard* sh, void* dev_out);
+int    colibri_b200_shard_skip_finish(colibri_b200_shard* sh, const void* dev_surv, const uint64_t* surv_counts);
 /* NVLink peer-store mode: the caller allocates symmetric receive buffers on every rank (e.g. torch.distributed._symmetric_memory),
  * passes every rank's device pointers (keys_rx: G slots x slot_cap x 8 B; reply_rx: G x slot_cap x 4 B; surv_rx: G x surv_cap x 8 B;
  * hdr: 6*G u64 words) and provides a device-side barrier on the stream given to shard_set_stream.  A level is then

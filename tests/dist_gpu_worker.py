@@ -20,11 +20,12 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     kw = dict(vocab=vocab, seed=seed, mean_sentence=15, phrase_permille=150, nphrases=500)
     corpus = cb.Corpus.synthetic(per, device=local, first_token=rank * per, **kw)
-    opts = cb.PatternModelOptions(MINTOKENS=mintokens, MAXLENGTH=maxlength, QUIET=1, device=local)
+    skip = len(sys.argv) > 7 and sys.argv[7] == "skipgrams"
+    opts = cb.PatternModelOptions(MINTOKENS=mintokens, MAXLENGTH=maxlength, DOSKIPGRAMS_EXHAUSTIVE=int(skip), streamed=0 if skip else 1, QUIET=1, device=local)
     eng = mg.CudaShardEngine(corpus, opts, rank, world, local)
     if len(sys.argv) > 6 and sys.argv[6] == "p2p":  # NVLink peer-store mode (symmetric memory)
         eng.use_peers(mg.PeerBuffers.get(dist, torch, world, per * 2, local))
-    model, passes, head = mg.train_distributed(eng, dist, torch, mintokens, maxlength)
+    model, passes, head = mg.train_distributed(eng, dist, torch, mintokens, maxlength, skip)
     keys, off, counts, _ = model.export()
     share = (keys.tobytes(), off.tolist(), counts.tolist())
     gathered = [None] * world if rank == 0 else None
@@ -41,7 +42,7 @@ def main():
                 merged[k] = cn[i]
             assert p == passes and h == head
         body = b"".join(oracle.synth_corpus(per, first_token=r * per, **kw).tobytes() for r in range(world))
-        want = oracle.train(body, mintokens=mintokens, maxlength=maxlength)
+        want = oracle.train(body, mintokens=mintokens, maxlength=maxlength, doskipgrams_exhaustive=int(skip), streamed=0 if skip else 1)
         ok = merged == want.as_dict() and [tuple(p) for p in passes] == want.passes and (head["tokens"], head["types"], head["maxn"], head["minn"]) == (
             want.tokens, want.types, want.maxn, want.minn)
         print("DIST_RESULT", "OK" if ok else "MISMATCH", len(merged), len(want), passes, want.passes, flush=True)

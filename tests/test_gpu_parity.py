@@ -187,6 +187,15 @@ def test_large_corpus_invariants():
     assert all(dd.get(k) == v for k, v in zip(ck[:50000], c.counts.tolist()[:50000]))
 
 
+def test_compact_export_agrees_with_offsets(golden):
+    body = corpus_body(golden, "republic")
+    m = cb().train(body, MINTOKENS=2, MAXLENGTH=5, QUIET=1)
+    keys, off, counts, _ = m.export()
+    ckeys, lens, ccounts = m.export_compact()
+    assert np.array_equal(keys, ckeys) and np.array_equal(counts, ccounts)
+    assert np.array_equal(np.diff(off.astype(np.int64)), lens.astype(np.int64))
+
+
 def test_error_paths():
     lib = cb()
     with pytest.raises(lib.ColibriError):

@@ -29,6 +29,8 @@ class NumpyShardEngine:
         tok.append(0)
         self.tok = np.array(tok, dtype=np.int64)
         self.segs = []  # (n, pos or class, count)
+        self.skipsegs = []  # (n, pos, count, mask)
+        self.ids_keep = {}
         self.level = 1
 
     def new_buffer(self, nwords):
@@ -52,6 +54,7 @@ class NumpyShardEngine:
             if cls % self.world == self.rank and c[cls] > 0:
                 self.segs.append((1, int(cls), int(c[cls])))
         self.prev = np.where((self.tok != 0) & (c[self.tok] >= self.t), self.tok, 0)
+        self.ids_keep[1] = self.prev
         return found, kept, occ
 
     def _owner(self, a, b):
@@ -122,7 +125,80 @@ class NumpyShardEngine:
                 self.segs.append((n, self.groups[owner][int(srec[k, 0])], int(srec[k, 1])))
                 k += 1
         self.prev, self.level = cur, n
+        self.ids_keep[n] = cur
         return int((cur != 0).sum())
+
+    # ---- skipgrams of the level just finished (same record formats as the CUDA phases: 16-byte keys, 16-byte survivor records)
+    def _skip_owner_of(self, k):
+        return (k[0] * 31 + k[1] * 1000003 + k[2] * 7919 + k[3] * 104729) % self.world
+
+    def skip_split_count(self):
+        import oracle
+
+        n = self.level
+        self.ids_keep = getattr(self, "ids_keep", {})
+        masks = oracle.skip_configurations(n, 3) if n >= 3 else []
+        groups = [[] for _ in range(self.world)]
+        prev = self.ids_keep[n - 1] if n >= 2 else None
+        for p in range(len(self.tok) - 1):
+            if not masks or not (prev[p] and prev[p + 1]):
+                continue
+            for mask in masks:
+                parts, j = [], 0
+                while j < n:
+                    if (mask >> j) & 1:
+                        j += 1
+                        continue
+                    k = j
+                    while k < n and not (mask >> k) & 1:
+                        k += 1
+                    parts.append(int(self.ids_keep[k - j][p + j]))
+                    j = k
+                key = (mask, parts[0], parts[1], parts[2] if len(parts) > 2 else 0)
+                groups[self._skip_owner_of(key)].append((key, p))
+        self.sk_groups = groups
+        return [len(g) for g in groups], sum(len(g) for g in groups)
+
+    def skip_split_write(self, nsend):
+        rec = np.zeros((max(nsend, 1), 4), dtype=np.uint32)
+        j = 0
+        for g in self.sk_groups:
+            for (mask, a, b, c), _p in g:
+                rec[j] = (a, mask, c, b)  # k0 = mask << 32 | a ; k1 = b << 32 | c  (little-endian words)
+                j += 1
+        return torch.from_numpy(rec.view(np.int32).reshape(-1))
+
+    def skip_owner(self, recv, recv_counts):
+        nrecv = sum(recv_counts)
+        rec = recv.numpy().view(np.uint32)[: nrecv * 4].reshape(-1, 4)
+        table = {}
+        for i in range(nrecv):
+            e = table.setdefault(tuple(int(x) for x in rec[i]), [0, i])
+            e[0] += 1
+        kept = {k: e for k, e in table.items() if e[0] >= self.t}
+        src_base = np.concatenate([[0], np.cumsum(recv_counts)])
+        self.sk_surv = [[] for _ in range(self.world)]
+        for k, e in kept.items():
+            src = int(np.searchsorted(src_base, e[1], side="right") - 1)
+            self.sk_surv[src].append((e[1] - int(src_base[src]), e[0], k[1]))
+        return (len(table), len(kept)), [len(x) for x in self.sk_surv]
+
+    def skip_owner_survivors(self, nsurv):
+        rec = np.zeros((max(nsurv, 1), 4), dtype=np.uint32)
+        j = 0
+        for grp in self.sk_surv:
+            for idx, cnt, mask in grp:
+                rec[j] = (idx, cnt, mask, 0)
+                j += 1
+        return torch.from_numpy(rec.view(np.int32).reshape(-1))
+
+    def skip_finish(self, surv, surv_counts):
+        srec = surv.numpy().view(np.uint32)[: sum(surv_counts) * 4].reshape(-1, 4)
+        k = 0
+        for owner, c in enumerate(surv_counts):
+            for _ in range(c):
+                self.skipsegs.append((self.level, self.sk_groups[owner][int(srec[k, 0])][1], int(srec[k, 1]), int(srec[k, 2])))
+                k += 1
 
     def finish(self, passes, types, maxn, minn):
         import oracle
@@ -131,16 +207,19 @@ class NumpyShardEngine:
         for n, pos, cnt in self.segs:
             toks = [pos] if n == 1 else self.tok[pos:pos + n].tolist()
             out[b"".join(oracle.inttobytes(int(c)) for c in toks)] = cnt
+        for n, pos, cnt, mask in self.skipsegs:
+            ng = b"".join(oracle.inttobytes(int(c)) for c in self.tok[pos:pos + n].tolist())
+            out[oracle.skipgram_collapse(ng, mask)] = cnt
         return out
 
 
-def _worker(rank, world, port, bodies, mintokens, maxlength, results):
+def _worker(rank, world, port, bodies, mintokens, maxlength, results, skipgrams=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import colibri_core_b200.multigpu as mg
 
     eng = NumpyShardEngine(bodies[rank], mintokens, rank, world)
-    share, passes, head = mg.train_distributed(eng, dist, torch, mintokens, maxlength)
+    share, passes, head = mg.train_distributed(eng, dist, torch, mintokens, maxlength, skipgrams)
     gathered = [None] * world if rank == 0 else None
     dist.gather_object((share, passes, head), gathered, dst=0)
     if rank == 0:
@@ -149,17 +228,18 @@ def _worker(rank, world, port, bodies, mintokens, maxlength, results):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,mintokens,maxlength,seed", [(2, 2, 5, 3), (3, 2, 4, 5), (2, 3, 6, 7), (2, 1, 3, 9)])
-def test_distributed_orchestration_matches_oracle(world, mintokens, maxlength, seed):
+@pytest.mark.parametrize("world,mintokens,maxlength,seed,skipgrams", [(2, 2, 5, 3, False), (3, 2, 4, 5, False), (2, 3, 6, 7, False), (2, 1, 3, 9, False), (2, 2, 5, 11, True),
+                                                                      (3, 2, 6, 13, True)])
+def test_distributed_orchestration_matches_oracle(world, mintokens, maxlength, seed, skipgrams):
     import oracle
 
     per = 4000
     bodies = [oracle.synth_corpus(per, vocab=60, seed=seed, mean_sentence=9, phrase_permille=300, nphrases=20, first_token=r * per).tobytes() for r in range(world)]
-    want = oracle.train(b"".join(bodies), mintokens=mintokens, maxlength=maxlength)
+    want = oracle.train(b"".join(bodies), mintokens=mintokens, maxlength=maxlength, doskipgrams_exhaustive=1 if skipgrams else 0, streamed=0 if skipgrams else 1)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + (os.getpid() + seed) % 300
-    procs = [ctx.Process(target=_worker, args=(r, world, port, bodies, mintokens, maxlength, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, bodies, mintokens, maxlength, q, skipgrams)) for r in range(world)]
     for p in procs:
         p.start()
     gathered = q.get(timeout=240)

@@ -11,9 +11,9 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _run(world, per, vocab, seed, maxlength, mintokens, port, mode="nccl"):
+def _run(world, per, vocab, seed, maxlength, mintokens, port, mode="nccl", extra=""):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tests", "dist_gpu_worker.py"), str(per), str(vocab), str(seed), str(maxlength), str(mintokens), mode]
+           os.path.join(ROOT, "tests", "dist_gpu_worker.py"), str(per), str(vocab), str(seed), str(maxlength), str(mintokens), mode] + ([extra] if extra else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_RESULT OK" in r.stdout, r.stdout[-3000:]
@@ -31,6 +31,20 @@ def test_shard_phases_world2(mode):
     if cb.device_count() < 2:
         pytest.skip("needs two GPUs")
     _run(2, 400000, 30000, 6, 5, 2, 29713, mode)
+
+
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+def test_shard_skipgrams_world1(mode):
+    """Config-3 shape on the sharded path: n-grams + exhaustive skipgrams."""
+    _run(1, 200000, 8000, 14, 5, 2, 29717, mode, "skipgrams")
+
+
+def test_shard_skipgrams_world2():
+    import colibri_core_b200 as cb
+
+    if cb.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run(2, 250000, 8000, 15, 5, 2, 29719, "p2p", "skipgrams")
 
 
 def test_shard_phases_world1_peer_stores():

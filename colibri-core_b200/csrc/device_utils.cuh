@@ -7,8 +7,6 @@
 
 namespace colibri {
 
-constexpr int kWarp = 32;
-
 // map a 64-bit hash onto [0, n) without a modulo (n need not be a power of two)
 __device__ __forceinline__ uint64_t fast_range(uint64_t h, uint64_t n) {
     return __umul64hi(h, n);

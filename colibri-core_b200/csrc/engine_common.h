@@ -102,12 +102,6 @@ struct Pool {
         free_blocks.emplace(it->second, p);
         live.erase(it);
     }
-    void trim() {
-        std::lock_guard<std::mutex> g(mu);
-        for (auto& kv : free_blocks) cudaFree(kv.second);
-        free_blocks.clear();
-        cached = 0;
-    }
 };
 extern Pool g_pool[16];
 

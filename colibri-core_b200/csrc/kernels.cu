@@ -692,22 +692,6 @@ __global__ void __launch_bounds__(256) export_write_kernel(const uint32_t* __res
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) pattern_bytes(tok, sv_pos[i], sv_nm[i], keys + off[i]);
 }
-// record i occupies [off[i] + 5*i, ...): key bytes, 0x00, little-endian u32 count
-__global__ void __launch_bounds__(256) export_write_modelfile_kernel(const uint32_t* __restrict__ tok, const uint32_t* __restrict__ sv_pos, const uint32_t* __restrict__ sv_nm,
-                                                                     const uint32_t* __restrict__ sv_count, const uint64_t* __restrict__ off, uint64_t n,
-                                                                     uint8_t* __restrict__ out) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint8_t* rec = out + off[i] + 5 * i;
-    uint32_t len = pattern_bytes(tok, sv_pos[i], sv_nm[i], rec);
-    uint32_t c   = sv_count[i];
-    rec[len]     = 0;
-    rec[len + 1] = (uint8_t)c;
-    rec[len + 2] = (uint8_t)(c >> 8);
-    rec[len + 3] = (uint8_t)(c >> 16);
-    rec[len + 4] = (uint8_t)(c >> 24);
-}
-
 // exclusive scan u32 -> u64 over n items, out has n+1 entries (out[n] = total).  Three small kernels, 2048 items per block.
 constexpr int kScanItems = 2048;
 __global__ void __launch_bounds__(1024) scan_block_sums_kernel(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ sums) {
@@ -789,13 +773,6 @@ int launch_export_write(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_
     export_write_kernel<<<div_up(n, 256), 256, 0, s>>>(tok, sv_pos, sv_nm, off, n, keys);
     return 1;
 }
-int launch_export_write_modelfile(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, const uint32_t* sv_count, const uint64_t* off, uint64_t n,
-                                  uint8_t* out) {
-    if (!n) return 0;
-    export_write_modelfile_kernel<<<div_up(n, 256), 256, 0, s>>>(tok, sv_pos, sv_nm, sv_count, off, n, out);
-    return 1;
-}
-
 // =============================================================================================
 // Pattern::hash on the device for arbitrary pattern bytes (parity row a5)
 __global__ void __launch_bounds__(256) hash64_batch_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, uint64_t n, uint64_t* __restrict__ out) {

@@ -92,9 +92,6 @@ int launch_pack_nm(cudaStream_t s, uint32_t* nm /*in: gap masks, out: n | mask <
 int launch_export_lengths(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, uint64_t n, uint32_t* lens, uint16_t* lens16);
 int launch_exclusive_scan_u32_u64(cudaStream_t s, const uint32_t* in, uint64_t* out /*n+1*/, uint64_t n, uint64_t* tmp /*>= n/2048+2*/);
 int launch_export_write(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, const uint64_t* off, uint64_t n, uint8_t* keys);
-// model-file body: per pattern  key bytes, 0x00, u32 count  (unindexed; patternstore.h:534-542 + datatypes.h:216-221)
-int launch_export_write_modelfile(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, const uint32_t* sv_count, const uint64_t* off, uint64_t n,
-                                  uint8_t* out);
 
 // ---- forward index of indexed models (index.cu)
 int launch_delim_flags(cudaStream_t s, const uint32_t* tok, uint64_t npos, uint32_t* flags);

@@ -412,4 +412,10 @@ def parse_ref_passes(stderr: str):
         if m:
             found, sk, pr, extra, kept = m.groups()
             out.append((int(found), None if sk is None else int(sk), int(pr) + (int(extra) if extra else 0), int(kept)))
+            continue
+        # IndexedPatternModel::trainskipgrams (:2995-3006): " Found X skipgrams...pruned Y[ plus E extra skipgrams..]...total kept: Z"
+        m = re.search(r"Found (\d+) skipgrams\.\.\.pruned (\d+)(?: plus (\d+) extra skipgrams\.\.)?\.\.\.total kept: (-?\d+)", line)
+        if m:
+            sk, pr, extra, kept = m.groups()
+            out.append((0, int(sk), int(pr) + (int(extra) if extra else 0), int(kept)))
     return out

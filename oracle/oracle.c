@@ -394,6 +394,196 @@ static int model_has(const oracle_model* m, const uint8_t* key, uint32_t len) {
     return store_find(&m->st, key, len, oracle_pattern_hash(key, len)) != NULL;
 }
 
+
+/* ------------------------------------------------------------------------- */
+/* IndexedPatternModel::trainskipgrams (include/patternmodel.h:2969-3010) with computeskipgrams(pattern, ..., multiplerefs)
+ * (:1370-1527) and the indexed pruneskipgrams (:3362-3383) / getskipcontent (:3029-3059), restated with CLEAN iteration
+ * semantics: every surviving n-gram of size n is visited exactly once.  (The reference inserts into the unordered_map it is
+ * iterating over; where a rehash happens mid-loop its own visiting order is undefined.  tests/ pin what agrees.) */
+typedef struct tokindex {
+    span*     toks;      /* every token of the corpus */
+    uint64_t  ntoks;
+    uint64_t* sentfirst; /* sentfirst[s] = index of the first token of sentence s (1-based); nsent+2 entries */
+    uint32_t  nsent;
+} tokindex;
+
+static void tokindex_build(tokindex* ti, const uint8_t* corpus, size_t nbytes) {
+    size_t cap = 1024, scap = 256;
+    ti->toks      = (span*)malloc(cap * sizeof(span));
+    ti->sentfirst = (uint64_t*)malloc(scap * sizeof(uint64_t));
+    ti->ntoks     = 0;
+    ti->nsent     = 0;
+    size_t pos    = 0;
+    while (pos < nbytes) {
+        ++ti->nsent;
+        if (ti->nsent + 2 >= scap) {
+            scap *= 2;
+            ti->sentfirst = (uint64_t*)realloc(ti->sentfirst, scap * sizeof(uint64_t));
+        }
+        ti->sentfirst[ti->nsent] = ti->ntoks;
+        size_t start = pos;
+        int    prevhigh = 0;
+        for (;; ++pos) {
+            uint8_t c = corpus[pos];
+            if (!prevhigh && c == 0) {
+                ++pos;
+                break;
+            }
+            if (c < 128) {
+                if (ti->ntoks == cap) {
+                    cap *= 2;
+                    ti->toks = (span*)realloc(ti->toks, cap * sizeof(span));
+                }
+                ti->toks[ti->ntoks].off = start;
+                ti->toks[ti->ntoks].len = (uint32_t)(pos + 1 - start);
+                ++ti->ntoks;
+                start    = pos + 1;
+                prevhigh = 0;
+            } else {
+                prevhigh = 1;
+            }
+        }
+    }
+    ti->sentfirst[ti->nsent + 1] = ti->ntoks;
+}
+
+static const uint8_t* g_cmp_corpus;
+static int cmp_span(const void* a, const void* b) {
+    const span* x = (const span*)a;
+    const span* y = (const span*)b;
+    uint32_t    l = x->len < y->len ? x->len : y->len;
+    int         c = memcmp(g_cmp_corpus + x->off, g_cmp_corpus + y->off, l);
+    if (c)
+        return c;
+    return x->len < y->len ? -1 : (x->len > y->len);
+}
+
+/* number of distinct raw token spans "first gap .. last gap" over the occurrences of one skipgram (getskipcontent().size()) */
+static uint64_t skip_types(const tokindex* ti, const uint8_t* corpus, const entry* e, uint32_t mask) {
+    int n = e->n, head = 0, tail = 0;
+    while (head < n && !((mask >> head) & 1u))
+        ++head; /* maskheadskip(reversemask(mask)) : leading non-gap tokens */
+    while (tail < n && !((mask >> (n - 1 - tail)) & 1u))
+        ++tail;
+    span* v = (span*)malloc((size_t)(e->count ? e->count : 1) * sizeof(span));
+    for (uint32_t k = 0; k < e->count; ++k) {
+        uint32_t sentence = (uint32_t)(e->refs[k] >> 16), token = (uint32_t)(e->refs[k] & 0xFFFF);
+        uint64_t first = ti->sentfirst[sentence] + token + (uint64_t)head, last = ti->sentfirst[sentence] + token + (uint64_t)(n - tail) - 1;
+        v[k].off = ti->toks[first].off;
+        v[k].len = (uint32_t)(ti->toks[last].off + ti->toks[last].len - ti->toks[first].off);
+    }
+    g_cmp_corpus = corpus;
+    qsort(v, e->count, sizeof(span), cmp_span);
+    uint64_t types = e->count ? 1 : 0;
+    for (uint32_t k = 1; k < e->count; ++k)
+        if (cmp_span(&v[k - 1], &v[k]) != 0)
+            ++types;
+    free(v);
+    return types;
+}
+
+/* gap mask of a stored skipgram key (bytes with 0x03 gap markers): Pattern::getmask, src/pattern.cpp:189-210 */
+static uint32_t key_mask(const uint8_t* key, uint32_t len) {
+    uint32_t mask = 0;
+    int      tok = 0, prevhigh = 0;
+    for (uint32_t i = 0; i < len; ++i) {
+        uint8_t c = key[i];
+        if (c < 128) {
+            if (!prevhigh && c == 3 && tok < 31)
+                mask |= 1u << tok;
+            ++tok;
+            prevhigh = 0;
+        } else {
+            prevhigh = 1;
+        }
+    }
+    return mask;
+}
+
+static int oracle_trainskipgrams(oracle_model* m, const oracle_options* o, const uint8_t* corpus, size_t nbytes) {
+    tokindex ti;
+    tokindex_build(&ti, corpus, nbytes);
+    uint32_t masks[4096];
+    uint8_t  skipkey[1024];
+    int      rc = 0;
+    for (int n = 3; n <= o->maxlength; ++n) {
+        int nmasks = oracle_skip_configurations(n, o->maxskips, masks, 4096);
+        if (nmasks < 0 || nmasks > 4096) {
+            rc = fail("oracle: too many skip configurations");
+            break;
+        }
+        /* snapshot of the surviving n-grams of this size (key bytes + occurrence lists) */
+        uint64_t cnt = 0;
+        for (uint64_t i = 0; i < m->st.cap; ++i)
+            if (m->st.tab[i].used && m->st.tab[i].n == n && !m->st.tab[i].skipgram)
+                ++cnt;
+        uint64_t* idx = (uint64_t*)malloc((cnt + 1) * sizeof(uint64_t));
+        uint64_t  k   = 0;
+        for (uint64_t i = 0; i < m->st.cap; ++i)
+            if (m->st.tab[i].used && m->st.tab[i].n == n && !m->st.tab[i].skipgram)
+                idx[k++] = i;
+        /* copy what is needed: inserting may grow/move the table */
+        typedef struct snap { uint8_t* key; uint32_t len; uint32_t count; uint64_t* refs; } snap;
+        snap* sn = (snap*)malloc((cnt + 1) * sizeof(snap));
+        for (uint64_t q = 0; q < cnt; ++q) {
+            entry* e    = &m->st.tab[idx[q]];
+            sn[q].len   = e->len;
+            sn[q].count = e->count;
+            sn[q].key   = (uint8_t*)malloc(e->len);
+            memcpy(sn[q].key, m->st.arena + e->keyoff, e->len);
+            sn[q].refs = (uint64_t*)malloc((size_t)(e->count ? e->count : 1) * sizeof(uint64_t));
+            memcpy(sn[q].refs, e->refs, (size_t)e->count * sizeof(uint64_t));
+        }
+        free(idx);
+        uint64_t foundskipgrams = 0;
+        for (uint64_t q = 0; q < cnt; ++q) {
+            for (int mi = 0; mi < nmasks; ++mi) {
+                size_t sl = oracle_skipgram_collapse(sn[q].key, sn[q].len, masks[mi], skipkey);
+                if (!model_has(m, skipkey, (uint32_t)sl))
+                    ++foundskipgrams; /* :1504-1505 */
+                for (uint32_t r = 0; r < sn[q].count; ++r)
+                    model_add(m, skipkey, (uint32_t)sl, (uint16_t)n, 1, (uint32_t)(sn[q].refs[r] >> 16), (uint16_t)(sn[q].refs[r] & 0xFFFF)); /* :1508-1512 */
+            }
+        }
+        for (uint64_t q = 0; q < cnt; ++q) {
+            free(sn[q].key);
+            free(sn[q].refs);
+        }
+        free(sn);
+        if (!foundskipgrams)
+            break; /* " None found" :2991-2993 */
+        m->hasskipgrams = 1;
+        prune_rule r      = {n, 0, 0, o->mintokens};
+        uint64_t   pruned = store_prune(&m->st, &r); /* :2999 */
+        uint64_t   extra  = 0;
+        if (o->minskiptypes > 1) { /* :3362-3383 */
+            /* mark, then erase: a skipgram whose gaps were filled by fewer than MINSKIPTYPES distinct contents goes */
+            for (uint64_t i = 0; i < m->st.cap; ++i) {
+                entry* e = &m->st.tab[i];
+                if (e->used && e->skipgram && e->n == n) {
+                    uint32_t mask = key_mask(m->st.arena + e->keyoff, e->len);
+                    if (skip_types(&ti, corpus, e, mask) < (uint64_t)o->minskiptypes) {
+                        e->count = 0; /* below any threshold: picked up by the prune below */
+                        ++extra;
+                    }
+                }
+            }
+            prune_rule z = {n, 0, 2, 1};
+            store_prune(&m->st, &z);
+        }
+        if (m->npasses < 128) { /* recorded as extra "passes": n, 0 n-grams, found skipgrams, pruned */
+            m->pass[m->npasses][0] = (uint64_t)n;
+            m->pass[m->npasses][1] = 0;
+            m->pass[m->npasses][2] = foundskipgrams;
+            m->pass[m->npasses][3] = pruned + extra;
+            ++m->npasses;
+        }
+    }
+    free(ti.toks);
+    free(ti.sentfirst);
+    return rc;
+}
+
 int oracle_train(const uint8_t* corpus_in, size_t nbytes_in, const oracle_options* opt_in, oracle_model** out) {
     oracle_options o = *opt_in;
     *out             = NULL;
@@ -406,8 +596,8 @@ int oracle_train(const uint8_t* corpus_in, size_t nbytes_in, const oracle_option
         o.mintokens_skipgrams = o.mintokens;
     if (o.doskipgrams && o.doskipgrams_exhaustive)
         return fail("Both DOSKIPGRAMS as well as DOSKIPGRAMS_EXHAUSTIVE are set"); /* :958-963 */
-    if (o.doskipgrams)
-        return fail("oracle: non-exhaustive skipgrams (IndexedPatternModel::trainskipgrams) are not restated yet");
+    if (o.doskipgrams && !o.indexed)
+        return fail("Can not compute skipgrams on unindexed model (except exhaustively during train() )"); /* :1554-1561 */
     if (o.maxlength > 127)
         return fail("oracle: MAXLENGTH > 127 not supported");
     if ((o.minlength > 1 || o.mintokens == 1) && o.mintokens_unigrams > o.mintokens)
@@ -633,6 +823,11 @@ int oracle_train(const uint8_t* corpus_in, size_t nbytes_in, const oracle_option
         prevsize = m->st.size; /* :1269 */
     }
 
+    if (o.doskipgrams && !o.doskipgrams_exhaustive) { /* :1271-1273 */
+        rc = oracle_trainskipgrams(m, &o, corpus, nbytes);
+        if (rc)
+            goto done;
+    }
     if (o.mintokens == 1) { /* :1274-1277 postread: maxn/minn/hasskipgrams from the stored patterns */
         for (uint64_t i = 0; i < m->st.cap; ++i) {
             entry* e = &m->st.tab[i];

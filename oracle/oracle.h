@@ -30,7 +30,7 @@ typedef struct oracle_options {
     int32_t maxbackofflength;       /* MAXBACKOFFLENGTH     (default 100) */
     int32_t minskiptypes;           /* MINSKIPTYPES         (default 2) */
     int32_t maxskips;               /* MAXSKIPS             (default 3) */
-    int32_t doskipgrams;            /* DOSKIPGRAMS          (indexed post-pass; not restated yet -> error) */
+    int32_t doskipgrams;            /* DOSKIPGRAMS          (indexed models: trainskipgrams post-pass, patternmodel.h:2969-3010) */
     int32_t doskipgrams_exhaustive; /* DOSKIPGRAMS_EXHAUSTIVE */
     int32_t indexed;                /* 0: PatternModel<uint32_t>, 1: IndexedPatternModel<> */
     int32_t streamed;               /* 1: sentences come from Pattern(std::istream&) (src/pattern.cpp:483-587),

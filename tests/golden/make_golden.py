@@ -87,6 +87,20 @@ CASES = [
     ("zipf300k_phr", False, False, dict(t=2, l=6)),
     ("zipf300k_phr", True, False, dict(t=5, l=7)),
     ("zipf2m", True, False, dict(t=2, l=5)),
+    # indexed models with skipgrams from n-grams (IndexedPatternModel::trainskipgrams, skip-type pruning)
+    ("hamlet", False, True, dict()),               # src/test.cpp:1321-1337, test.py:289-291 (133 patterns)
+    ("hamlet", False, True, dict(l=5, T=1)),
+    ("hamlet", False, True, dict(l=5, T=2)),
+    ("hamlet", False, True, dict(l=6, T=3, t=2)),
+    ("skipkat", False, True, dict(t=2, l=3, T=1)),
+    # NOTE: ("threebyte", indexed, skipgrams) is deliberately NOT a golden case.  trainskipgrams() inserts skipgrams into the
+    # std::unordered_map it is iterating over (patternmodel.h:2986-2990); on that 21-pattern model the insertions of the n=4
+    # loop trigger a rehash (29 buckets), libstdc++ relinks the node list, and the running iterator never reaches one of the
+    # three 4-grams: the reference emits 6 instead of 9 4-skipgrams.  That is undefined behaviour of the reference, not a
+    # semantics to reproduce; the cases below (and the reference's own KAT, 133 patterns) are free of it.
+    ("republic", False, True, dict(t=2, l=4, T=2)),
+    ("republic", False, True, dict(t=3, l=5, T=1)),
+    ("zipf300k_phr", False, True, dict(t=2, l=5, T=2)),
 ]
 
 
@@ -140,6 +154,7 @@ def main():
             opts = {CLI2OPT[k]: v for k, v in cli.items()}
             opts["indexed"] = 0 if unindexed else 1
             opts["doskipgrams_exhaustive"] = 1 if (skipgrams and unindexed) else 0
+            opts["doskipgrams"] = 1 if (skipgrams and not unindexed) else 0
             # the CLI streams the file only for unindexed models without skipgrams (src/patternmodeller.cpp:721-754)
             opts["streamed"] = 1 if (unindexed and not skipgrams) else 0
             case = {

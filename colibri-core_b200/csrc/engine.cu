@@ -234,7 +234,9 @@ int colibri::check_options(colibri_b200_options& o) {
         return set_err(COLIBRI_E_UNSUPPORTED, "model type %d (only 10 = unindexed and 20 = indexed run on the device)", o.model_type);
     if (o.model_type == COLIBRI_INDEXEDPATTERNMODEL && o.DOSKIPGRAMS_EXHAUSTIVE)
         return set_err(COLIBRI_E_UNSUPPORTED, "exhaustive skipgrams on an indexed model are not on the device path yet");
-    if (o.DOSKIPGRAMS) return set_err(COLIBRI_E_UNSUPPORTED, "non-exhaustive skipgrams (IndexedPatternModel::trainskipgrams) are not on the device path yet");
+    if (o.DOSKIPGRAMS && o.model_type != COLIBRI_INDEXEDPATTERNMODEL)
+        return set_err(COLIBRI_E_INVALID, "Can not compute skipgrams on unindexed model (except exhaustively during train() )");  // :1554-1561
+    if (o.DOSKIPGRAMS && o.MINTOKENS == 1) return set_err(COLIBRI_E_UNSUPPORTED, "indexed skipgrams with MINTOKENS=1 are not on the device path");
     if (o.DOPATTERNPERLINE) return set_err(COLIBRI_E_UNSUPPORTED, "DOPATTERNPERLINE is not on the device path");
     if (o.PRUNENONSUBSUMED || o.PRUNESUBSUMED) return set_err(COLIBRI_E_UNSUPPORTED, "PRUNE(NON)SUBSUMED is not on the device path");
     if (o.MAXLENGTH < 1 || o.MAXLENGTH > 255) return set_err(COLIBRI_E_UNSUPPORTED, "MAXLENGTH=%d (device path supports 1..255)", o.MAXLENGTH);
@@ -279,7 +281,9 @@ struct Trainer {
     DevBuf<uint64_t>   sent_before;  // delimiters in tok[0..p)
     DevBuf<uint32_t>   sent_start;   // first position of sentence k (0-based)
     int prepare_index(const uint32_t* tok, uint64_t npos);
-    int build_refs(Segment& sg, const uint32_t* ids, const uint32_t* map, bool by_class, uint64_t npos, uint64_t expect);
+    int build_refs(Segment& sg, const uint32_t* ids, const uint32_t* map, bool by_class, uint64_t npos, uint64_t expect, bool keep_positions = false,
+                   const uint32_t* pos_lookup = nullptr, uint32_t pos_div = 1);
+    int indexed_skipgrams(int n, Segment& ng, const std::vector<DevBuf<uint32_t>>& ids, uint64_t& foundskip, uint64_t& keptskip, Segment& out);
     int run();
 };
 
@@ -299,7 +303,8 @@ int Trainer::prepare_index(const uint32_t* tok, uint64_t npos) {
 }
 
 // occurrences of one level -> (sentence, token) lists grouped by survivor, ascending inside each (see index.cu)
-int Trainer::build_refs(Segment& sg, const uint32_t* ids, const uint32_t* map, bool by_class, uint64_t npos, uint64_t expect) {
+int Trainer::build_refs(Segment& sg, const uint32_t* ids, const uint32_t* map, bool by_class, uint64_t npos, uint64_t expect, bool keep_positions, const uint32_t* pos_lookup,
+                        uint32_t pos_div) {
     if (sg.count == 0) return 0;
     const uint64_t   nblk = (npos + 2047) / 2048;
     DevBuf<uint32_t> blk;
@@ -324,7 +329,11 @@ int Trainer::build_refs(Segment& sg, const uint32_t* ids, const uint32_t* map, b
     TRY(hist.alloc(dev, 256 * nsort));
     TRY(hist_off.alloc(dev, 256 * nsort + 1));
     TRY(stmp.alloc(dev, 256 * nsort / 2048 + 4));
-    launches += launch_pair_write(s, ids, map, npos, by_class, blk_off.p, ka.p, va.p);
+    launches += launch_pair_write(s, ids, map, npos, by_class, blk_off.p, ka.p, va.p, pos_lookup, pos_div);
+    if (keep_positions) {  // corpus-order occurrence positions of this level: the windows of its skipgrams (trainskipgrams)
+        TRY(sg.occ_pos.alloc(dev, R));
+        CUDA_TRY(cudaMemcpyAsync(sg.occ_pos.p, va.p, R * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    }
     uint32_t *kin = ka.p, *vin = va.p, *kout = kb.p, *vout = vb.p;
     for (int shift = 0; shift < 32 && ((sg.count - 1) >> shift) != 0; shift += 8) {
         launches += launch_radix_pass(s, kin, vin, R, shift, hist.p, hist_off.p, stmp.p, kout, vout);
@@ -338,6 +347,75 @@ int Trainer::build_refs(Segment& sg, const uint32_t* ids, const uint32_t* map, b
     TRY(read_stats());
     if (h_stats.errflags & kErrLongSentence)
         return set_err(COLIBRI_E_UNSUPPORTED, "indexed model: a sentence has more than 65536 tokens (IndexReference.token is 16 bit; the class encoder splits such lines)");
+    return 0;
+}
+
+// IndexedPatternModel::trainskipgrams for one n (reference include/patternmodel.h:2969-3010): every occurrence of every surviving
+// n-gram contributes to each of its gap configurations (computeskipgrams with multiplerefs, :1370-1527), then prune(MINTOKENS, n)
+// and the skip-type rule of the indexed pruneskipgrams (:3362-3383).  The skipgrams' occurrence lists come out of the same
+// ordered-pairs + stable radix sort as the n-grams'.
+int Trainer::indexed_skipgrams(int n, Segment& ng, const std::vector<DevBuf<uint32_t>>& ids, uint64_t& foundskip, uint64_t& keptskip, Segment& out) {
+    foundskip = keptskip = 0;
+    std::vector<SkipMask> masks;
+    TRY(skip_masks(n, o.MAXSKIPS, masks));
+    const uint64_t nocc = ng.nrefs;
+    if (masks.empty() || nocc == 0) return 0;
+    const uint64_t items = nocc * masks.size();
+    if (items >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "level %d has %llu skipgram occurrences", n, (unsigned long long)items);
+    uint64_t sbound = 0;
+    for (auto& sm : masks) sbound += nocc * (1 + (sm.nparts > 3 ? (sm.nparts - 2) / 2 : 0));
+    const uint64_t scap = std::max<uint64_t>(64, sbound + sbound / 2 + 16);
+    DevBuf<SkipSlot>        table;
+    DevBuf<const uint32_t*> d_ptrs;
+    DevBuf<SkipMask>        d_m;
+    DevBuf<uint32_t>        item_slot, types, slot_index;
+    DevBuf<NgramSlot>       pairs;
+    TRY(table.alloc(dev, scap));
+    TRY(item_slot.alloc(dev, items));
+    TRY(slot_index.alloc(dev, scap));
+    TRY(d_ptrs.alloc(dev, n + 1));
+    TRY(d_m.alloc(dev, masks.size()));
+    std::vector<const uint32_t*> ptrs(n + 1, nullptr);
+    for (int k = 1; k <= n; ++k) ptrs[k] = ids[k].p;
+    CUDA_TRY(cudaMemcpyAsync(d_ptrs.p, ptrs.data(), (n + 1) * sizeof(uint32_t*), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_m.p, masks.data(), masks.size() * sizeof(SkipMask), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(table.p, 0, scap * sizeof(SkipSlot), s));
+    CUDA_TRY(cudaMemsetAsync(item_slot.p, 0, items * sizeof(uint32_t), s));
+    TRY(zero_stats());
+    int hs = timer.begin(COLIBRI_T_SKIPGRAMS, n);
+    launches += launch_count_skipgrams(s, d_ptrs.p, n, d_m.p, (int)masks.size(), nocc, table.p, scap, d_stats.p, sms, ng.occ_pos.p, item_slot.p);
+    const bool by_types = o.MINSKIPTYPES > 1;
+    if (by_types) {
+        const uint64_t pcap = std::max<uint64_t>(64, items + items / 2 + 16);
+        TRY(types.alloc(dev, scap));
+        TRY(pairs.alloc(dev, pcap));
+        CUDA_TRY(cudaMemsetAsync(types.p, 0, scap * sizeof(uint32_t), s));
+        CUDA_TRY(cudaMemsetAsync(pairs.p, 0, pcap * sizeof(NgramSlot), s));
+        launches += launch_skip_types(s, d_ptrs.p, n, d_m.p, (int)masks.size(), nocc, ng.occ_pos.p, item_slot.p, pairs.p, pcap, types.p, d_stats.p, sms);
+    }
+    timer.end(hs);
+    TRY(read_stats());  // also keeps ptrs/masks alive until the copies are done
+    skip_upserts += h_stats.valid_windows;
+    out.n    = n;
+    out.skip = true;
+    const uint64_t bound = items / std::max<uint32_t>((uint32_t)o.MINTOKENS, 1) + 1;
+    TRY(out.pos.alloc(dev, bound));
+    TRY(out.cnt.alloc(dev, bound));
+    TRY(out.mask.alloc(dev, bound));
+    TRY(zero_stats());
+    int hp = timer.begin(COLIBRI_T_PRUNE);
+    launches += launch_prune_skipgrams(s, table.p, scap, (uint32_t)o.MINTOKENS, out.pos.p, out.cnt.p, out.mask.p, d_stats.p, sms, slot_index.p, by_types ? types.p : nullptr,
+                                       (uint32_t)std::max(o.MINSKIPTYPES, 0));
+    timer.end(hp);
+    TRY(read_stats());
+    foundskip = h_stats.found;
+    keptskip  = h_stats.kept;
+    out.count = keptskip;
+    if (keptskip) {
+        int hi = timer.begin(COLIBRI_T_INDEX);
+        TRY(build_refs(out, item_slot.p, slot_index.p, false, items, h_stats.kept_occ, false, ng.occ_pos.p, (uint32_t)masks.size()));
+        timer.end(hi);
+    }
     return 0;
 }
 
@@ -401,6 +479,8 @@ int Trainer::run() {
     const uint32_t t1 = (uint32_t)std::max(o.MINTOKENS, o.MINTOKENS_UNIGRAMS);  // what higher orders require of their unigrams (:1094-1104)
     const uint32_t ts = o.MINSKIPTYPES > 1 ? (uint32_t)o.MINTOKENS_SKIPGRAMS : t;  // PatternModel::pruneskipgrams returns early when minskiptypes <= 1 (:2170-2171)
     const bool     skipgrams = o.DOSKIPGRAMS_EXHAUSTIVE != 0;
+    const bool     indexed_skip = indexed && o.DOSKIPGRAMS != 0;  // trainskipgrams after the n-gram levels
+    const bool     keep_all_ids = skipgrams || indexed_skip;
 
     // ---- K1 unigrams
     h = timer.begin(COLIBRI_T_UNIGRAMS);
@@ -534,7 +614,7 @@ int Trainer::run() {
         sg.count = kept;
         if (indexed && kept > 0) {  // IndexedPatternModel::add (:2789-2800) + posttrain sort (:2699-2705)
             int hi = timer.begin(COLIBRI_T_INDEX);
-            TRY(build_refs(sg, cur.p, slot_index.p, false, npos, occ));
+            TRY(build_refs(sg, cur.p, slot_index.p, false, npos, occ, indexed_skip && n >= 3));
             timer.end(hi);
         }
 
@@ -595,14 +675,14 @@ int Trainer::run() {
         segs.push_back(std::move(sg));
         if (sk.skip) segs.push_back(std::move(sk));
 
-        if (n < o.MAXLENGTH && kept > 0) {
+        if ((n < o.MAXLENGTH || indexed_skip) && kept > 0) {
             if (t > 1) {
                 hp = timer.begin(COLIBRI_T_PRUNE);
                 launches += launch_relabel(s, cur.p, npos, bitmap.p);
                 timer.end(hp);
             }
         }
-        if (!skipgrams) ids[n - 1].reset();  // ping-pong: only the newest level is needed
+        if (!keep_all_ids) ids[n - 1].reset();  // ping-pong: only the newest level is needed
         prev_kept = kept;
         prev_occ  = occ;
         if (kept == 0) {  // the next pass cannot find anything: it would print "None found" and stop
@@ -610,12 +690,30 @@ int Trainer::run() {
         }
     }
 
+    // ---- indexed models: skipgrams from the surviving n-grams (train() tail, :1271-1273 -> trainskipgrams :2969-3010)
+    if (indexed_skip) {
+        std::vector<Segment> extra;
+        for (int n = 3; n <= o.MAXLENGTH; ++n) {
+            Segment* ng = nullptr;
+            for (auto& sg : segs)
+                if (sg.n == n && !sg.skip) ng = &sg;
+            uint64_t foundskip = 0, keptskip = 0;
+            Segment  sk;
+            if (ng != nullptr && ng->count > 0) TRY(indexed_skipgrams(n, *ng, ids, foundskip, keptskip, sk));
+            if (foundskip == 0) break;  // " None found"
+            m->hasskipgrams = 1;
+            passes.push_back({(uint64_t)n, 0, foundskip, foundskip - keptskip});
+            if (keptskip) extra.push_back(std::move(sk));
+        }
+        for (auto& sk : extra) segs.push_back(std::move(sk));
+    }
+
     // ---- which levels end up in the model
     std::vector<Segment> keep;
     for (auto& sg : segs) {
         bool drop = false;
         if (o.MINTOKENS > 1) {
-            if (!skipgrams) {
+            if (!skipgrams && !o.DOSKIPGRAMS) {
                 // :1221-1229: after pass n, level n-1 is emptied when it is below MINLENGTH
                 int k = sg.n;
                 if (k < o.MINLENGTH && last_pass >= k + 1 && k != o.MAXBACKOFFLENGTH && !(k == 1 && o.MINTOKENS_UNIGRAMS > o.MINTOKENS)) drop = true;

@@ -181,6 +181,7 @@ struct Segment {  // survivors of one (level, category)
     uint64_t         nrefs = 0;
     DevBuf<uint32_t> ref_sentence;
     DevBuf<uint16_t> ref_token;
+    DevBuf<uint32_t> occ_pos;  // indexed + DOSKIPGRAMS: the nrefs occurrence positions of this level in corpus order
 };
 
 int check_options(colibri_b200_options& o);

@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(256) pair_count_kernel(const uint32_t* __restr
 }
 
 __global__ void __launch_bounds__(256) pair_write_kernel(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ map, uint64_t npos, bool by_class,
-                                                         const uint64_t* __restrict__ blk_off, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                         const uint64_t* __restrict__ blk_off, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                         const uint32_t* __restrict__ pos_lookup, uint32_t pos_div) {
     __shared__ uint32_t warp_cnt[8];
     uint64_t base = (uint64_t)blockIdx.x * kPairTile;
     uint64_t out  = blk_off[blockIdx.x];
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256) pair_write_kernel(const uint32_t* __restr
         if (idx != 0) {
             uint64_t dst = out + before + __popc(m & ((1u << lane) - 1));
             keys[dst]    = idx - 1;
-            vals[dst]    = (uint32_t)p;
+            vals[dst]    = pos_lookup != nullptr ? __ldg(pos_lookup + p / pos_div) : (uint32_t)p;
         }
         out += total;
         __syncthreads();
@@ -175,8 +176,9 @@ int launch_pair_count(cudaStream_t s, const uint32_t* ids, const uint32_t* map, 
     pair_count_kernel<<<idx_div_up(npos, kPairTile), 256, 0, s>>>(ids, map, npos, by_class, blk_counts);
     return 1;
 }
-int launch_pair_write(cudaStream_t s, const uint32_t* ids, const uint32_t* map, uint64_t npos, bool by_class, const uint64_t* blk_off, uint32_t* keys, uint32_t* vals) {
-    pair_write_kernel<<<idx_div_up(npos, kPairTile), 256, 0, s>>>(ids, map, npos, by_class, blk_off, keys, vals);
+int launch_pair_write(cudaStream_t s, const uint32_t* ids, const uint32_t* map, uint64_t npos, bool by_class, const uint64_t* blk_off, uint32_t* keys, uint32_t* vals,
+                      const uint32_t* pos_lookup, uint32_t pos_div) {
+    pair_write_kernel<<<idx_div_up(npos, kPairTile), 256, 0, s>>>(ids, map, npos, by_class, blk_off, keys, vals, pos_lookup, pos_div);
     return 1;
 }
 int launch_radix_pass(cudaStream_t s, const uint32_t* keys_in, const uint32_t* vals_in, uint64_t n, int shift, uint32_t* hist, uint64_t* hist_off, uint64_t* scan_tmp,

@@ -433,7 +433,8 @@ __device__ __forceinline__ void load_slot<SkipSlot>(const SkipSlot* table, uint6
 template <class Slot, bool kSkip>
 __global__ void __launch_bounds__(256) prune_table_kernel(const Slot* __restrict__ table, uint64_t cap, uint32_t threshold, uint32_t* __restrict__ sv_pos,
                                                           uint32_t* __restrict__ sv_count, uint32_t* __restrict__ sv_mask, uint32_t* __restrict__ bitmap,
-                                                          uint32_t* __restrict__ slot_index /* may be NULL: slot -> survivor index + 1 */, DeviceStats* __restrict__ st) {
+                                                          uint32_t* __restrict__ slot_index /* may be NULL: slot -> survivor index + 1 */, DeviceStats* __restrict__ st,
+                                                          const uint32_t* __restrict__ types /* may be NULL */, uint32_t mintypes) {
     __shared__ uint64_t scratch[8];
     __shared__ uint32_t warp_cnt[8];
     __shared__ unsigned long long tile_base;
@@ -451,6 +452,7 @@ __global__ void __launch_bounds__(256) prune_table_kernel(const Slot* __restrict
             bool used = (k_lo | k_hi) != 0;
             if (kSkip) used = used && (k_hi & kSkipCombiner) == 0;  // helper entries are ids, not patterns
             bool keep = used && cnt[k] >= threshold;
+            if (types != nullptr && keep) keep = __ldg(types + base + k * 32 + lane) >= mintypes;  // skip-type rule of indexed models
             msk[k]    = k_hi & 0x00FFFFFFu;                         // skipgram: high word of k0 = gap mask (+ round bits, dropped)
             keepbits[k] = __ballot_sync(0xffffffffu, keep);
             found += used;
@@ -553,7 +555,7 @@ int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, ui
                         uint32_t* slot_index) {
     static int bps = blocks_per_sm((const void*)prune_table_kernel<NgramSlot, false>, 256, 0);
     unsigned   grid = (unsigned)umin64(div_up(cap, kPruneTile), (uint64_t)sms * bps);
-    prune_table_kernel<NgramSlot, false><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, nullptr, bitmap, slot_index, st);
+    prune_table_kernel<NgramSlot, false><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, nullptr, bitmap, slot_index, st, nullptr, 0);
     return 1;
 }
 int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap) {
@@ -589,8 +591,12 @@ __device__ __forceinline__ uint32_t upsert_skipkey(SkipSlot* __restrict__ table,
     return 0;
 }
 
+// Two ways to enumerate the windows: every position whose two (n-1)-grams survive (exhaustive mode, occ_pos == NULL), or an
+// explicit list of positions (occ_pos[j], indexed models: the occurrences of the surviving n-grams, trainskipgrams
+// include/patternmodel.h:2969-3010).  item_slot (optional) receives the slot + 1 of every (window, mask) item.
 __global__ void __launch_bounds__(256) count_skipgrams_kernel(const uint32_t* const* __restrict__ ids, int n, const SkipMask* __restrict__ masks, int nmasks, uint64_t npos,
-                                                              SkipSlot* __restrict__ table, uint64_t cap, DeviceStats* __restrict__ st) {
+                                                              SkipSlot* __restrict__ table, uint64_t cap, DeviceStats* __restrict__ st, const uint32_t* __restrict__ occ_pos,
+                                                              uint32_t* __restrict__ item_slot) {
     __shared__ uint64_t scratch[8];
     const uint32_t* prev  = ids[n - 1];
     const uint64_t  total = npos * (uint64_t)nmasks;
@@ -599,7 +605,10 @@ __global__ void __launch_bounds__(256) count_skipgrams_kernel(const uint32_t* co
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t p = t / nmasks;
         int      m = (int)(t - p * nmasks);
-        if (__ldg(prev + p) == 0 || __ldg(prev + p + 1) == 0) continue;
+        if (occ_pos != nullptr)
+            p = __ldg(occ_pos + p);
+        else if (__ldg(prev + p) == 0 || __ldg(prev + p + 1) == 0)
+            continue;
         const SkipMask* sm     = masks + m;
         const uint32_t  mask   = __ldg(&sm->mask);
         const uint32_t  nparts = __ldg(&sm->nparts);
@@ -622,24 +631,73 @@ __global__ void __launch_bounds__(256) count_skipgrams_kernel(const uint32_t* co
         unsigned long long k0 = ((unsigned long long)(mask | (rounds << kSkipRoundShift)) << 32) | part[first];
         unsigned long long k1 = ((unsigned long long)part[first + 1] << 32) | (left > 2 ? part[first + 2] : 0u);
         ++valid;
-        if (upsert_skipkey(table, cap, k0, k1, true, (uint32_t)p) == 0) full = true;
+        const uint32_t slot = upsert_skipkey(table, cap, k0, k1, true, (uint32_t)p);
+        if (slot == 0) full = true;
+        if (item_slot != nullptr) item_slot[t] = slot;
     }
     uint64_t v = block_reduce_sum(valid, scratch);
     if (threadIdx.x == 0 && v) atomicAdd(&st->valid_windows, (unsigned long long)v);
     if (full) atomicOr(&st->errflags, kErrTableFull);
 }
 
+// Skip-type counting of indexed models (IndexedPatternModel::pruneskipgrams :3362-3383, getskipcontent :3029-3059): the
+// "content" of an occurrence is the raw token span from the first to the last gap, i.e. the surviving k-gram starting at
+// p + head; a skipgram survives only if at least MINSKIPTYPES distinct contents occur.  Distinct (skipgram slot, content id)
+// pairs are claimed in a scratch table; the first claim of a pair bumps types[slot].
+__global__ void __launch_bounds__(256) skip_types_kernel(const uint32_t* const* __restrict__ ids, int n, const SkipMask* __restrict__ masks, int nmasks, uint64_t nocc,
+                                                         const uint32_t* __restrict__ occ_pos, const uint32_t* __restrict__ item_slot, NgramSlot* __restrict__ pairs, uint64_t cap,
+                                                         uint32_t* __restrict__ types, DeviceStats* __restrict__ st) {
+    const uint64_t total = nocc * (uint64_t)nmasks;
+    bool           full  = false;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t slot = item_slot[t];
+        if (slot == 0) continue;
+        const uint64_t j    = t / nmasks;
+        const uint32_t mask = __ldg(&masks[t - j * nmasks].mask);
+        const uint32_t p    = __ldg(occ_pos + j);
+        const int      head = __ffs(mask) - 1;                       // leading non-gap tokens
+        const int      tail = n - (32 - __clz(mask));                // trailing non-gap tokens
+        const uint32_t cid  = __ldg(ids[n - head - tail] + p + head);  // id of the content k-gram
+        const unsigned long long key = ((unsigned long long)slot << 32) | cid;
+        uint64_t       at    = fast_range(spooky_hash64_u64(key, 0), cap);
+        const uint64_t limit = cap < kMaxProbe ? cap : kMaxProbe;
+        uint64_t       step  = 0;
+        for (; step < limit; ++step) {
+            unsigned long long cur = __ldcg(&pairs[at].key);
+            if (cur == 0) {
+                cur = atomicCAS(&pairs[at].key, 0ull, key);
+                if (cur == 0) {
+                    atomicAdd(&types[slot - 1], 1u);  // first sighting of this content for this skipgram
+                    break;
+                }
+            }
+            if (cur == key) break;
+            at = at + 1 == cap ? 0 : at + 1;
+        }
+        if (step == limit) full = true;
+    }
+    if (full) atomicOr(&st->errflags, kErrTableFull);
+}
+
 int launch_count_skipgrams(cudaStream_t s, const uint32_t* const* ids, int n, const SkipMask* masks, int nmasks, uint64_t npos, SkipSlot* table, uint64_t cap, DeviceStats* st,
-                           int sms) {
+                           int sms, const uint32_t* occ_pos, uint32_t* item_slot) {
     static int bps  = blocks_per_sm((const void*)count_skipgrams_kernel, 256, 0);
     unsigned   grid = (unsigned)umin64(div_up(npos * nmasks, 256), (uint64_t)sms * bps * 4);
-    count_skipgrams_kernel<<<grid ? grid : 1, 256, 0, s>>>(ids, n, masks, nmasks, npos, table, cap, st);
+    count_skipgrams_kernel<<<grid ? grid : 1, 256, 0, s>>>(ids, n, masks, nmasks, npos, table, cap, st, occ_pos, item_slot);
     return 1;
 }
-int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask, DeviceStats* st, int sms) {
+int launch_skip_types(cudaStream_t s, const uint32_t* const* ids, int n, const SkipMask* masks, int nmasks, uint64_t nocc, const uint32_t* occ_pos, const uint32_t* item_slot,
+                      NgramSlot* pairs, uint64_t cap, uint32_t* types, DeviceStats* st, int sms) {
+    if (!nocc) return 0;
+    unsigned grid = (unsigned)umin64(div_up(nocc * nmasks, 256), (uint64_t)sms * 16);
+    skip_types_kernel<<<grid ? grid : 1, 256, 0, s>>>(ids, n, masks, nmasks, nocc, occ_pos, item_slot, pairs, cap, types, st);
+    return 1;
+}
+int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask, DeviceStats* st, int sms,
+                           uint32_t* slot_index, const uint32_t* types, uint32_t mintypes) {
     static int bps  = blocks_per_sm((const void*)prune_table_kernel<SkipSlot, true>, 256, 0);
     unsigned   grid = (unsigned)umin64(div_up(cap, kPruneTile), (uint64_t)sms * bps);
-    prune_table_kernel<SkipSlot, true><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, sv_mask, nullptr, nullptr, st);
+    prune_table_kernel<SkipSlot, true><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, sv_mask, nullptr, slot_index, st, types, mintypes);
     return 1;
 }
 

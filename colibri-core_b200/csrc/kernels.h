@@ -80,10 +80,13 @@ int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, ui
 int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap);
 
 // ---- skipgrams (config 3)
+// occ_pos != NULL: npos counts entries of occ_pos (explicit window positions) instead of corpus positions; item_slot (optional): slot + 1 per (window, mask)
 int launch_count_skipgrams(cudaStream_t s, const uint32_t* const* ids /*device array, index = level*/, int n, const SkipMask* masks /*device*/, int nmasks, uint64_t npos,
-                           SkipSlot* table, uint64_t cap, DeviceStats* st, int sms);
+                           SkipSlot* table, uint64_t cap, DeviceStats* st, int sms, const uint32_t* occ_pos = nullptr, uint32_t* item_slot = nullptr);
+int launch_skip_types(cudaStream_t s, const uint32_t* const* ids, int n, const SkipMask* masks, int nmasks, uint64_t nocc, const uint32_t* occ_pos, const uint32_t* item_slot,
+                      NgramSlot* pairs /* zeroed scratch */, uint64_t cap, uint32_t* types /* zeroed, one per skip slot */, DeviceStats* st, int sms);
 int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask, DeviceStats* st,
-                           int sms);
+                           int sms, uint32_t* slot_index = nullptr, const uint32_t* types = nullptr, uint32_t mintypes = 0);
 
 // ---- export: survivors -> pattern bytes
 // sv_nm[i] = n | mask << 8 ; for n == 1 sv_pos holds the class id itself
@@ -96,8 +99,10 @@ int launch_export_write(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_
 // ---- forward index of indexed models (index.cu)
 int launch_delim_flags(cudaStream_t s, const uint32_t* tok, uint64_t npos, uint32_t* flags);
 int launch_sent_start(cudaStream_t s, const uint32_t* tok, const uint64_t* sent_before, uint64_t npos, uint32_t* sent_start);
+// pos_lookup != NULL: item i stands for position pos_lookup[i / pos_div] (skipgram items of indexed models)
 int launch_pair_count(cudaStream_t s, const uint32_t* ids, const uint32_t* map, uint64_t npos, bool by_class, uint32_t* blk_counts /* one per 2048 positions */);
-int launch_pair_write(cudaStream_t s, const uint32_t* ids, const uint32_t* map, uint64_t npos, bool by_class, const uint64_t* blk_off, uint32_t* keys, uint32_t* vals);
+int launch_pair_write(cudaStream_t s, const uint32_t* ids, const uint32_t* map, uint64_t npos, bool by_class, const uint64_t* blk_off, uint32_t* keys, uint32_t* vals,
+                      const uint32_t* pos_lookup = nullptr, uint32_t pos_div = 1);
 int launch_radix_pass(cudaStream_t s, const uint32_t* keys_in, const uint32_t* vals_in, uint64_t n, int shift, uint32_t* hist /* 256*ceil(n/4096) */, uint64_t* hist_off,
                       uint64_t* scan_tmp, uint32_t* keys_out, uint32_t* vals_out);
 int launch_refs_from_positions(cudaStream_t s, const uint32_t* pos, uint64_t n, const uint64_t* sent_before, const uint32_t* sent_start, uint32_t* ref_sentence, uint16_t* ref_token,

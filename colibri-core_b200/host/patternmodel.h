@@ -195,9 +195,12 @@ class DevicePatternModel : public PatternModelInterface {
         hasskipgrams = colibri_b200_model_hasskipgrams(mh.h) != 0;
         if (!options.QUIET) {  // the reference's per-pass progress lines (:1005-1019, :1190-1245)
             const int np = colibri_b200_model_passes(mh.h);
+            int ngrampasses = 0;
             for (int p = 0; p < np; ++p) {
                 uint64_t st[4];
                 colibri_b200_model_pass_stats(mh.h, p, st);
+                if (options.DOSKIPGRAMS && st[1] == 0) continue;  // trainskipgrams passes: printed below, after the n-gram passes
+                ++ngrampasses;
                 if (mintokens > 1)
                     std::cerr << "Counting " << st[0] << "-grams" << std::endl;
                 else
@@ -206,10 +209,21 @@ class DevicePatternModel : public PatternModelInterface {
                 if (options.DOSKIPGRAMS_EXHAUSTIVE) std::cerr << st[2] << " skipgram occurrences...";
                 std::cerr << "pruned " << st[3] << "...total kept: " << (st[1] + st[2]) - st[3] << std::endl;
             }
-            if (mintokens > 1 && np > 0 && np < options.MAXLENGTH) {
+            if (mintokens > 1 && ngrampasses > 0 && ngrampasses < options.MAXLENGTH) {
                 uint64_t st[4];
-                colibri_b200_model_pass_stats(mh.h, np - 1, st);
+                colibri_b200_model_pass_stats(mh.h, ngrampasses - 1, st);
                 std::cerr << "Counting " << st[0] + 1 << "-grams" << std::endl << "None found" << std::endl;
+            }
+            if (options.DOSKIPGRAMS) {  // IndexedPatternModel::trainskipgrams, reference :2980-3008
+                int last = 2;
+                for (int p = ngrampasses; p < np; ++p) {
+                    uint64_t st[4];
+                    colibri_b200_model_pass_stats(mh.h, p, st);
+                    last = (int)st[0];
+                    std::cerr << "Counting " << st[0] << "-skipgrams" << std::endl;
+                    std::cerr << " Found " << st[2] << " skipgrams...pruned " << st[3] << "...total kept: " << st[2] - st[3] << std::endl;
+                }
+                if (last < options.MAXLENGTH) std::cerr << "Counting " << last + 1 << "-skipgrams" << std::endl << " None found" << std::endl;
             }
         }
         uint64_t np = 0, kb = 0, nr = 0;

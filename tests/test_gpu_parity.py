@@ -34,7 +34,7 @@ def gpu_options(case):
     o = case["options"]
     return cb().PatternModelOptions(
         MINTOKENS=o.get("mintokens", -1), MINTOKENS_SKIPGRAMS=o.get("mintokens_skipgrams", -1), MINTOKENS_UNIGRAMS=o.get("mintokens_unigrams", 1), MINLENGTH=o.get("minlength", 1),
-        MAXLENGTH=o.get("maxlength", 100), MAXBACKOFFLENGTH=o.get("maxbackofflength", 100), MINSKIPTYPES=o.get("minskiptypes", 2), DOSKIPGRAMS_EXHAUSTIVE=o["doskipgrams_exhaustive"],
+        MAXLENGTH=o.get("maxlength", 100), MAXBACKOFFLENGTH=o.get("maxbackofflength", 100), MINSKIPTYPES=o.get("minskiptypes", 2), DOSKIPGRAMS_EXHAUSTIVE=o["doskipgrams_exhaustive"], DOSKIPGRAMS=o.get("doskipgrams", 0),
         model_type=20 if o["indexed"] else 10, streamed=o["streamed"], QUIET=1)
 
 
@@ -240,5 +240,33 @@ def test_gpu_equals_oracle_on_random_input(seed):
         pytest.skip("unsupported on the device path: %s" % e)
     got = to_flat(m)
     assert (got.tokens, got.types, len(got), got.maxn, got.minn, got.hasskipgrams) == (want.tokens, want.types, len(want), want.maxn, want.minn, want.hasskipgrams), (cli, unindexed, skipgrams)
+    assert got.passes == want.passes
+    assert got.same_patterns(want)
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_gpu_indexed_skipgrams_equal_oracle_on_random_input(seed):
+    """IndexedPatternModel::trainskipgrams (reference :2969-3010) + skip-type pruning on random corpora: patterns, counts, occurrence lists."""
+    import random
+
+    from test_oracle_vs_ref_random import random_corpus
+
+    rng = random.Random(9000 + seed)
+    body = random_corpus(rng)
+    if not body:
+        pytest.skip("empty corpus")
+    kw = dict(MINTOKENS=rng.choice([2, 2, 3]), MAXLENGTH=rng.choice([3, 4, 5, 6, 8]), MINSKIPTYPES=rng.choice([1, 2, 2, 3]))
+    if rng.random() < 0.3:
+        kw["MINLENGTH"] = rng.randint(1, 3)
+    okw = dict(mintokens=kw["MINTOKENS"], maxlength=kw["MAXLENGTH"], minskiptypes=kw["MINSKIPTYPES"], minlength=kw.get("MINLENGTH", 1), indexed=1, doskipgrams=1, streamed=0)
+    try:
+        want = oracle.train(body, **okw)
+    except RuntimeError:
+        with pytest.raises(cb().ColibriError):
+            cb().train(body, QUIET=1, model_type=20, DOSKIPGRAMS=1, streamed=0, **kw)
+        return
+    m = cb().train(body, QUIET=1, model_type=20, DOSKIPGRAMS=1, streamed=0, **kw)
+    got = to_flat(m)
+    assert (got.tokens, got.types, len(got), got.maxn, got.minn, got.hasskipgrams) == (want.tokens, want.types, len(want), want.maxn, want.minn, want.hasskipgrams), kw
     assert got.passes == want.passes
     assert got.same_patterns(want)

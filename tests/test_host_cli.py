@@ -43,7 +43,7 @@ def test_cli_fails_loudly_without_gpu(cli):
         assert not os.path.exists(os.path.join(td, "m"))
 
 
-CLI_CASES = [c for c in load_cases() if c["corpus"] in ("hamlet", "republic") and c["options"].get("maxbackofflength", 100) >= 100 and not (c["skipgrams"] and not c["unindexed"])]
+CLI_CASES = [c for c in load_cases() if c["corpus"] in ("hamlet", "republic") and c["options"].get("maxbackofflength", 100) >= 100]
 
 
 @pytest.mark.gpu

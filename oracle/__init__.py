@@ -48,6 +48,21 @@ class Options(C.Structure):
     ]
 
 
+class LoadOptions(C.Structure):
+    """POD mirror of oracle_load_options: the PatternModelOptions fields load() uses as filters."""
+
+    _fields_ = [
+        ("mintokens", C.c_int32),
+        ("minlength", C.c_int32),
+        ("maxlength", C.c_int32),
+        ("dongrams", C.c_int32),
+        ("doskipgrams", C.c_int32),
+        ("doflexgrams", C.c_int32),
+        ("doreset", C.c_int32),
+        ("load_indexed", C.c_int32),
+    ]
+
+
 class SynthParams(C.Structure):
     _fields_ = [
         ("seed", C.c_uint64),
@@ -108,6 +123,12 @@ def lib():
     L.oracle_model_write.restype = C.c_size_t
     L.oracle_modelfile_scan.argtypes = [_u8p, C.c_size_t, _u64p]
     L.oracle_modelfile_parse.argtypes = [_u8p, C.c_size_t, _u8p, _u64p, _u32p, _u32p, _u16p, _u64p]
+    L.oracle_model_load.argtypes = [_u8p, C.c_size_t, C.POINTER(LoadOptions), C.c_void_p, C.POINTER(C.c_void_p)]
+    L.oracle_model_load.restype = C.c_int
+    L.oracle_model_from_keys.argtypes = [_u8p, _u64p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+    L.oracle_model_from_keys.restype = C.c_int
+    L.oracle_train_constrained.argtypes = [_u8p, C.c_size_t, C.POINTER(Options), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.oracle_train_constrained.restype = C.c_int
     L.oracle_inttobytes.argtypes = [_u8p, C.c_uint32]
     L.oracle_inttobytes.restype = C.c_uint
     L.oracle_bytestoint.argtypes = [_u8p, C.POINTER(C.c_uint)]
@@ -244,6 +265,29 @@ def default_options(**kw) -> Options:
     return o
 
 
+def _flat_from_handle(h, indexed: bool) -> FlatModel:
+    L = lib()
+    np_, kb, nr = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    L.oracle_model_export_sizes(h, C.byref(np_), C.byref(kb), C.byref(nr))
+    keys = np.zeros(kb.value + 1, dtype=np.uint8)
+    key_off = np.zeros(np_.value + 1, dtype=np.uint64)
+    counts = np.zeros(np_.value, dtype=np.uint32)
+    rs = rt = ro = None
+    if indexed:
+        rs = np.zeros(nr.value, dtype=np.uint32)
+        rt = np.zeros(nr.value, dtype=np.uint16)
+        ro = np.zeros(np_.value + 1, dtype=np.uint64)
+    L.oracle_model_export(h, _ptr(keys, _u8p), _ptr(key_off, _u64p), _ptr(counts, _u32p), _ptr(rs, _u32p) if indexed else None, _ptr(rt, _u16p) if indexed else None,
+                          _ptr(ro, _u64p) if indexed else None)
+    passes = []
+    st = (C.c_uint64 * 4)()
+    for p in range(L.oracle_model_passes(h)):
+        L.oracle_model_pass_stats(h, p, st)
+        passes.append(tuple(int(x) for x in st))
+    return FlatModel(keys[: kb.value], key_off, counts, int(L.oracle_model_tokens(h)), int(L.oracle_model_types(h)), L.oracle_model_maxn(h), L.oracle_model_minn(h),
+                     bool(L.oracle_model_hasskipgrams(h)), 20 if indexed else 10, rs, rt, ro, passes)
+
+
 def train(corpus, **kw) -> FlatModel:
     """Run the C restatement on the body of a .colibri.dat (bytes after the 2-byte header)."""
     L = lib()
@@ -254,25 +298,61 @@ def train(corpus, **kw) -> FlatModel:
     if rc != 0:
         raise RuntimeError("oracle_train: " + L.oracle_last_error().decode())
     try:
-        np_, kb, nr = C.c_uint64(), C.c_uint64(), C.c_uint64()
-        L.oracle_model_export_sizes(h, C.byref(np_), C.byref(kb), C.byref(nr))
-        keys = np.zeros(kb.value + 1, dtype=np.uint8)
-        key_off = np.zeros(np_.value + 1, dtype=np.uint64)
-        counts = np.zeros(np_.value, dtype=np.uint32)
-        rs = rt = ro = None
-        if o.indexed:
-            rs = np.zeros(nr.value, dtype=np.uint32)
-            rt = np.zeros(nr.value, dtype=np.uint16)
-            ro = np.zeros(np_.value + 1, dtype=np.uint64)
-        L.oracle_model_export(h, _ptr(keys, _u8p), _ptr(key_off, _u64p), _ptr(counts, _u32p), _ptr(rs, _u32p) if o.indexed else None, _ptr(rt, _u16p) if o.indexed else None,
-                              _ptr(ro, _u64p) if o.indexed else None)
-        passes = []
-        st = (C.c_uint64 * 4)()
-        for p in range(L.oracle_model_passes(h)):
-            L.oracle_model_pass_stats(h, p, st)
-            passes.append(tuple(int(x) for x in st))
-        return FlatModel(keys[: kb.value], key_off, counts, int(L.oracle_model_tokens(h)), int(L.oracle_model_types(h)), L.oracle_model_maxn(h), L.oracle_model_minn(h),
-                         bool(L.oracle_model_hasskipgrams(h)), 20 if o.indexed else 10, rs, rt, ro, passes)
+        return _flat_from_handle(h, bool(o.indexed))
+    finally:
+        L.oracle_model_free(h)
+
+
+class LoadedModel:
+    """A model held inside the oracle library (result of load_model / model_from_flat): the constraint side of train_constrained."""
+
+    def __init__(self, handle, indexed: bool):
+        self.h = handle
+        self.indexed = indexed
+
+    def flat(self) -> FlatModel:
+        return _flat_from_handle(self.h, self.indexed)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_model_free(self.h)
+            self.h = None
+
+
+def load_model(blob, mintokens=-1, minlength=1, maxlength=100, dongrams=1, doskipgrams=1, doflexgrams=1, doreset=0, indexed=0, constrain: "LoadedModel | None" = None) -> LoadedModel:
+    """PatternModel::load with the options as filters (include/patternmodel.h:781-861, include/patternstore.h:555-619)."""
+    L = lib()
+    data = _as_u8(blob)
+    lo = LoadOptions(int(mintokens), int(minlength), int(maxlength), int(dongrams), int(doskipgrams), int(doflexgrams), int(doreset), int(indexed))
+    h = C.c_void_p()
+    if L.oracle_model_load(_ptr(data, _u8p), data.size, C.byref(lo), constrain.h if constrain is not None else None, C.byref(h)) != 0:
+        raise RuntimeError("oracle_model_load: " + L.oracle_last_error().decode())
+    return LoadedModel(h, bool(indexed))
+
+
+def model_from_flat(fm: FlatModel, indexed=0) -> LoadedModel:
+    """A zero-count model holding fm's patterns and totals (constraint side when no file is at hand)."""
+    L = lib()
+    keys = np.ascontiguousarray(fm.keys, dtype=np.uint8)
+    if keys.size == 0:
+        keys = np.zeros(1, dtype=np.uint8)
+    off = np.ascontiguousarray(fm.key_off, dtype=np.uint64)
+    h = C.c_void_p()
+    if L.oracle_model_from_keys(_ptr(keys, _u8p), _ptr(off, _u64p), len(fm), int(fm.tokens), int(fm.types), int(indexed), C.byref(h)) != 0:
+        raise RuntimeError("oracle_model_from_keys: " + L.oracle_last_error().decode())
+    return LoadedModel(h, bool(indexed))
+
+
+def train_constrained(corpus, constrain: LoadedModel, inplace=False, **kw) -> FlatModel:
+    """train() under a constraint model (include/patternmodel.h:880-1345 with constrainbymodel != NULL)."""
+    L = lib()
+    data = _as_u8(corpus)
+    o = default_options(**kw)
+    h = C.c_void_p()
+    if L.oracle_train_constrained(_ptr(data, _u8p), data.size, C.byref(o), constrain.h, int(bool(inplace)), C.byref(h)) != 0:
+        raise RuntimeError("oracle_train_constrained: " + L.oracle_last_error().decode())
+    try:
+        return _flat_from_handle(h, bool(o.indexed))
     finally:
         L.oracle_model_free(h)
 
@@ -399,6 +479,15 @@ def ref_train(corpus_path: str, model_path: str | None = None, unindexed=True, s
     if r.returncode != 0:
         raise RuntimeError("ref_train failed (%d): %s" % (r.returncode, r.stderr[-2000:]))
     return json.loads(r.stdout.strip().splitlines()[-1]), r.stderr
+
+
+REF_CLI = os.path.join(REF_DIR, "colibri-patternmodeller")
+
+
+def ref_cli(args, timeout=None):
+    """Run the unmodified reference CLI (oracle/_ref/colibri-patternmodeller).  Returns (exit code, stderr text)."""
+    r = subprocess.run([REF_CLI] + [str(a) for a in args], capture_output=True, text=True, timeout=timeout)
+    return r.returncode, r.stderr
 
 
 def parse_ref_passes(stderr: str):

@@ -869,6 +869,303 @@ done:
     return 0;
 }
 
+/* ------------------------------------------------------------------------- */
+static int modelfile_walk(const uint8_t* d, size_t n, uint64_t hdr[7], uint8_t* keys, uint64_t* key_off, uint32_t* counts, uint32_t* ref_sentence, uint16_t* ref_token,
+                          uint64_t* ref_off);
+/* Shape of a stored key: tokens (Pattern::n -> datasize, src/pattern.cpp:74-97: one per byte < 128) and category
+ * (datacategory, src/pattern.cpp:23-43: the FIRST skip (3) / flex (4) token decides). */
+static void key_shape(const uint8_t* key, uint32_t len, uint16_t* n_out, uint8_t* cat_out) {
+    uint16_t n = 0;
+    uint8_t  cat = 0;
+    int      tokstart = 1;
+    for (uint32_t i = 0; i < len; ++i) {
+        uint8_t c = key[i];
+        if (c < 128) {
+            if (tokstart && cat == 0 && c == 3)
+                cat = 1;
+            if (tokstart && cat == 0 && c == 4)
+                cat = 2;
+            ++n;
+            tokstart = 1;
+        } else {
+            tokstart = 0;
+        }
+    }
+    *n_out   = n;
+    *cat_out = cat;
+}
+
+/* postread (include/patternmodel.h:572-588): maxn / minn / hasskipgrams from the stored patterns */
+static void model_postread(oracle_model* m) {
+    for (uint64_t i = 0; i < m->st.cap; ++i) {
+        entry* e = &m->st.tab[i];
+        if (!e->used)
+            continue;
+        if (e->n > m->maxn)
+            m->maxn = e->n;
+        if (e->n < m->minn)
+            m->minn = e->n;
+        if (e->skipgram == 1)
+            m->hasskipgrams = 1;
+    }
+}
+
+/* PatternModel::load (include/patternmodel.h:781-861) + PatternMapStore::read (include/patternstore.h:555-619):
+ * read a model file of type 10/20 AS an unindexed (load_indexed=0) or indexed (1) model, applying the options as filters. */
+int oracle_model_load(const uint8_t* file, size_t nbytes, const oracle_load_options* lo, const oracle_model* constrain, oracle_model** out) {
+    *out = NULL;
+    uint64_t hdr[7];
+    if (modelfile_walk(file, nbytes, hdr, NULL, NULL, NULL, NULL, NULL, NULL))
+        return 1;
+    const int filetype = (int)hdr[0];
+    uint64_t  np = hdr[4], kb = hdr[5], nr = hdr[6];
+    uint8_t*  keys = (uint8_t*)malloc(kb + 1);
+    uint64_t* ko   = (uint64_t*)malloc((np + 1) * sizeof(uint64_t));
+    uint32_t* cnt  = (uint32_t*)malloc((np + 1) * sizeof(uint32_t));
+    uint32_t* rs   = (uint32_t*)malloc((nr + 1) * sizeof(uint32_t));
+    uint16_t* rt   = (uint16_t*)malloc((nr + 1) * sizeof(uint16_t));
+    uint64_t* ro   = (uint64_t*)malloc((np + 1) * sizeof(uint64_t));
+    modelfile_walk(file, nbytes, NULL, keys, ko, cnt, rs, rt, ro);
+    oracle_model* m = (oracle_model*)calloc(1, sizeof *m);
+    store_init(&m->st, 1024);
+    m->indexed     = lo->load_indexed;
+    m->maxn        = 0;
+    m->minn        = 999;
+    m->totaltokens = hdr[2]; /* :815-816 */
+    m->totaltypes  = hdr[3];
+    int64_t mintokens = lo->mintokens == -1 ? 0 : lo->mintokens; /* patternstore.h:565-566 */
+    for (uint64_t i = 0; i < np; ++i) {
+        const uint8_t* k = keys + ko[i];
+        uint32_t       l = (uint32_t)(ko[i + 1] - ko[i]);
+        uint16_t       n;
+        uint8_t        cat;
+        key_shape(k, l, &n, &cat);
+        if ((!lo->dongrams && cat == 0) || (!lo->doskipgrams && cat == 1) || (!lo->doflexgrams && cat == 2))
+            continue; /* patternstore.h:574-578 */
+        if ((int)n < lo->minlength || (int)n > lo->maxlength)
+            continue; /* :585 */
+        if ((int64_t)cnt[i] < mintokens)
+            continue; /* :586 */
+        if (constrain && !model_has(constrain, k, l))
+            continue;
+        uint64_t h = oracle_pattern_hash(k, l);
+        if (store_find(&m->st, k, l, h))
+            continue;
+        entry* e = store_insert(&m->st, k, l, h, n, cat);
+        if (lo->doreset)
+            continue; /* :588-589: a fresh value */
+        if (m->indexed) {
+            /* 20 -> 20 keeps the occurrence list; 10 -> 20 "will load the patterns but lose all the counts" (:833-837) */
+            if (filetype == 20)
+                for (uint64_t j = ro[i]; j < ro[i + 1]; ++j)
+                    entry_add(e, 1, rs[j], rt[j]);
+        } else {
+            e->count = cnt[i]; /* 20 -> 10: IndexedDataHandler::convertto -> count (:827-832) */
+        }
+    }
+    model_postread(m); /* :860 */
+    free(keys);
+    free(ko);
+    free(cnt);
+    free(rs);
+    free(rt);
+    free(ro);
+    *out = m;
+    return 0;
+}
+
+/* a model holding the given patterns with zero counts and the given totals: the constraint side of
+ * oracle_train_constrained when the caller has no model file at hand */
+int oracle_model_from_keys(const uint8_t* keys, const uint64_t* key_off, uint64_t npatterns, uint64_t totaltokens, uint64_t totaltypes, int indexed, oracle_model** out) {
+    oracle_model* m = (oracle_model*)calloc(1, sizeof *m);
+    store_init(&m->st, 1024);
+    m->indexed     = indexed;
+    m->maxn        = 0;
+    m->minn        = 999;
+    m->totaltokens = totaltokens;
+    m->totaltypes  = totaltypes;
+    for (uint64_t i = 0; i < npatterns; ++i) {
+        const uint8_t* k = keys + key_off[i];
+        uint32_t       l = (uint32_t)(key_off[i + 1] - key_off[i]);
+        uint16_t       n;
+        uint8_t        cat;
+        key_shape(k, l, &n, &cat);
+        uint64_t h = oracle_pattern_hash(k, l);
+        if (!store_find(&m->st, k, l, h))
+            store_insert(&m->st, k, l, h, n, cat);
+    }
+    model_postread(m);
+    *out = m;
+    return 0;
+}
+
+/* PatternModel::train with constrainbymodel != NULL (include/patternmodel.h:880-1345): ONE scan of the corpus
+ * (:1064-1072 subngrams(MINLENGTH, MAXLENGTH)), a window is counted iff the constraint model has it (:1088-1089),
+ * then prune(MINTOKENS, 0) (:1211-1218) and stop (:1246-1247).
+ *   inplace == 0: `constrain` is another model (the CLI's -j: a PatternSetModel); the result starts empty;
+ *                 totaltypes/totaltokens start from the constraint model's (:892-895) and the corpus tokens are ADDED (:1047-1048).
+ *   inplace == 1: constrainbymodel == this (the CLI's -I / stage 2 of -2): `constrain` is the model itself, loaded with
+ *                 DORESET; totals restart at 0 (:889-891), found = the whole loaded model (prevsize = 0, :970-971),
+ *                 totaltypes = size() for MINTOKENS > 1 (:1199-1201).
+ * The constraint model is not modified; the result is a new model. */
+int oracle_train_constrained(const uint8_t* corpus_in, size_t nbytes_in, const oracle_options* opt_in, const oracle_model* constrain, int inplace, oracle_model** out) {
+    oracle_options o = *opt_in;
+    *out             = NULL;
+    if (o.mintokens == -1)
+        o.mintokens = 2;
+    if (o.mintokens == 0)
+        o.mintokens = 1;
+    if (o.doskipgrams || o.doskipgrams_exhaustive)
+        return fail("oracle: skipgrams under a constraint model are not restated");
+    if (o.mintokens_unigrams > o.mintokens)
+        return fail("oracle: the secondary unigram threshold under a constraint model is not restated");
+    if (o.maxlength > 127)
+        return fail("oracle: MAXLENGTH > 127 not supported");
+    if (nbytes_in == 0)
+        return fail("Attempting to read pattern from file, but file is empty?");
+    size_t   nbytes = nbytes_in;
+    uint8_t* corpus = (uint8_t*)malloc(nbytes_in + 2);
+    memcpy(corpus, corpus_in, nbytes_in);
+    {
+        int ends_with_delim = 0;
+        if (nbytes_in >= 1 && corpus_in[nbytes_in - 1] == 0)
+            ends_with_delim = (nbytes_in == 1) || (corpus_in[nbytes_in - 2] < 128);
+        if (!ends_with_delim) {
+            if (o.streamed)
+                corpus[nbytes++] = corpus_in[nbytes_in - 1];
+            corpus[nbytes++] = 0;
+        }
+    }
+    oracle_model* m = (oracle_model*)calloc(1, sizeof *m);
+    store_init(&m->st, 1024);
+    m->indexed = o.indexed;
+    m->maxn    = 0;
+    m->minn    = 999;
+    if (inplace) {
+        /* the loaded model itself: every pattern present with a reset value; maxn/minn as postread left them */
+        for (uint64_t i = 0; i < constrain->st.cap; ++i) {
+            const entry* e = &constrain->st.tab[i];
+            if (e->used)
+                store_insert(&m->st, constrain->st.arena + e->keyoff, e->len, e->hash, e->n, e->skipgram);
+        }
+        m->maxn         = constrain->maxn;
+        m->minn         = constrain->minn;
+        m->hasskipgrams = constrain->hasskipgrams;
+    } else {
+        m->totaltypes  = constrain->totaltypes; /* :892-895 */
+        m->totaltokens = constrain->totaltokens;
+    }
+    span*    toks    = NULL;
+    size_t   tokscap = 0;
+    uint32_t sentence = 0;
+    size_t   pos      = 0;
+    while (pos < nbytes) {
+        ++sentence;
+        size_t ntok = 0, start = pos;
+        int    prevhigh = 0;
+        for (;; ++pos) {
+            uint8_t c = corpus[pos];
+            if (!prevhigh && c == 0) {
+                ++pos;
+                break;
+            }
+            if (c < 128) {
+                if (ntok == tokscap) {
+                    tokscap = tokscap ? tokscap * 2 : 256;
+                    toks    = (span*)realloc(toks, tokscap * sizeof(span));
+                }
+                toks[ntok].off = start;
+                toks[ntok].len = (uint32_t)(pos + 1 - start);
+                ++ntok;
+                start    = pos + 1;
+                prevhigh = 0;
+            } else {
+                prevhigh = 1;
+            }
+        }
+        if (ntok == 0)
+            continue;
+        m->totaltokens += ntok; /* n == 1 && !continued, :1047-1048 */
+        int lo = o.minlength, hi = o.maxlength < (int)ntok ? o.maxlength : (int)ntok;
+        if (lo > (int)ntok)
+            continue;
+        for (int len = lo; len <= hi; ++len)
+            for (size_t i = 0; i + len <= ntok; ++i) {
+                const uint8_t* key    = corpus + toks[i].off;
+                uint32_t       keylen = (uint32_t)(toks[i + len - 1].off + toks[i + len - 1].len - toks[i].off);
+                if (!model_has(constrain, key, keylen))
+                    continue; /* :1088-1089 */
+                model_add(m, key, keylen, (uint16_t)len, 0, sentence, (uint16_t)i);
+            }
+    }
+    uint64_t foundngrams = m->st.size; /* :1182 with prevsize = 0 (fresh model, or :970-971) */
+    if (foundngrams) {                 /* :1184-1188 with n == 1 */
+        if (1 > m->maxn)
+            m->maxn = 1;
+        if (1 < m->minn)
+            m->minn = 1;
+    }
+    if (inplace) { /* :1199-1209 */
+        if (o.mintokens > 1) {
+            m->totaltypes = m->st.size;
+        } else if (o.minlength == 1) {
+            uint64_t types = 0;
+            for (uint64_t i = 0; i < m->st.cap; ++i)
+                if (m->st.tab[i].used && m->st.tab[i].n == 1 && !m->st.tab[i].skipgram)
+                    ++types;
+            m->totaltypes = types;
+        }
+    }
+    uint64_t pruned = 0;
+    if (foundngrams) { /* "None found" breaks before the prune (:1189-1194) */
+        prune_rule r = {0, 0, 0, o.mintokens};
+        pruned       = store_prune(&m->st, &r); /* :1217 */
+        m->pass[0][0] = 1;
+        m->pass[0][1] = foundngrams;
+        m->pass[0][2] = 0;
+        m->pass[0][3] = pruned;
+        m->npasses    = 1;
+    }
+    if (o.mintokens == 1)
+        model_postread(m); /* :1274-1277 */
+    if (o.maxbackofflength < o.minlength) { /* :1278-1280 */
+        prune_rule r = {o.maxbackofflength, 0, 0, -1};
+        store_prune(&m->st, &r);
+    }
+    if (o.indexed) {
+        for (uint64_t i = 0; i < m->st.cap; ++i)
+            if (m->st.tab[i].used && m->st.tab[i].count > 1)
+                qsort(m->st.tab[i].refs, m->st.tab[i].count, sizeof(uint64_t), cmp_u64);
+    }
+    if (m->totaltypes == 0 && m->st.size > 0 && !(inplace && o.mintokens == 1 && o.minlength == 1)) {
+        /* types() (:1700-1704) falls back to totalwordtypesingroup(0, 0) when totaltypes was never set (in-place rebuild with
+         * MINTOKENS == 1 and MINLENGTH > 1): the distinct word types covered by the patterns left (:1953-1975); write() stores it.
+         * Not after the MINTOKENS == 1 / MINLENGTH == 1 branch above: that call filled the coverage cache, so a zero stays zero. */
+        oracle_model* seen = (oracle_model*)calloc(1, sizeof *seen);
+        store_init(&seen->st, 1024);
+        for (uint64_t i = 0; i < m->st.cap; ++i) {
+            const entry* e = &m->st.tab[i];
+            if (!e->used)
+                continue;
+            const uint8_t* k = m->st.arena + e->keyoff;
+            uint32_t       a = 0;
+            for (uint32_t b = 0; b < e->len; ++b)
+                if (k[b] < 128) {
+                    uint64_t h = oracle_pattern_hash(k + a, b + 1 - a);
+                    if (!store_find(&seen->st, k + a, b + 1 - a, h))
+                        store_insert(&seen->st, k + a, b + 1 - a, h, 1, 0);
+                    a = b + 1;
+                }
+        }
+        m->totaltypes = seen->st.size;
+        oracle_model_free(seen);
+    }
+    free(toks);
+    free(corpus);
+    *out = m;
+    return 0;
+}
+
 void oracle_model_free(oracle_model* m) {
     if (!m)
         return;

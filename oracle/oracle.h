@@ -78,6 +78,24 @@ int         oracle_modelfile_scan(const uint8_t* data, size_t n, uint64_t hdr[7]
 int         oracle_modelfile_parse(const uint8_t* data, size_t n, uint8_t* keys, uint64_t* key_off, uint32_t* counts, uint32_t* ref_sentence, uint16_t* ref_token,
                                    uint64_t* ref_off);
 
+/* Model load with the options acting as filters: PatternModel::load (include/patternmodel.h:781-861) over
+ * PatternMapStore::read (include/patternstore.h:555-619). */
+typedef struct oracle_load_options {
+    int32_t mintokens;    /* MINTOKENS (-1 -> 0 here, patternstore.h:565-566): keep count >= mintokens */
+    int32_t minlength;    /* keep MINLENGTH <= n <= MAXLENGTH */
+    int32_t maxlength;
+    int32_t dongrams;     /* !DOREMOVENGRAMS */
+    int32_t doskipgrams;  /* !DOREMOVESKIPGRAMS */
+    int32_t doflexgrams;  /* !DOREMOVEFLEXGRAMS */
+    int32_t doreset;      /* DORESET: values start empty */
+    int32_t load_indexed; /* 0: read as PatternModel<uint32_t>, 1: as IndexedPatternModel<> */
+} oracle_load_options;
+int         oracle_model_load(const uint8_t* file, size_t nbytes, const oracle_load_options* lo, const oracle_model* constrain, oracle_model** out);
+int         oracle_model_from_keys(const uint8_t* keys, const uint64_t* key_off, uint64_t npatterns, uint64_t totaltokens, uint64_t totaltypes, int indexed,
+                                   oracle_model** out);
+/* train() under a constraint model (include/patternmodel.h:880-1345, constrainbymodel != NULL); inplace = (constrainbymodel == this) */
+int         oracle_train_constrained(const uint8_t* corpus, size_t nbytes, const oracle_options* opt, const oracle_model* constrain, int inplace, oracle_model** out);
+
 /* Codec + hash + masks (the L1 layer). */
 unsigned    oracle_inttobytes(uint8_t* buf, uint32_t cls);               /* src/classencoder.cpp:22-42 */
 uint32_t    oracle_bytestoint(const uint8_t* a, unsigned* length);        /* src/classdecoder.cpp:20-43 */

@@ -49,3 +49,25 @@ def case_id(case) -> str:
 def load_cases():
     with open(os.path.join(GOLDEN_DIR, "golden.json")) as f:
         return json.load(f)["cases"]
+
+
+# ---- constrained training: golden_constrained.json, written by tests/golden/make_golden_constrained.py
+def load_constrained_cases():
+    with open(os.path.join(GOLDEN_DIR, "golden_constrained.json")) as f:
+        return json.load(f)["cases"]
+
+
+def constrained_case_id(case) -> str:
+    return "%s<-%s-%s%s-%s" % (case["corpus"], case["stage1_corpus"], case["mode"], "u" if case["unindexed"] else "i", "".join("%s%s" % kv for kv in sorted(case["cli"].items())))
+
+
+def cli_load_and_train_options(case):
+    """What the reference CLI does with a constrained case before train() runs (src/patternmodeller.cpp:717-737, :777-852):
+    returns (load filter kwargs, train option kwargs without the widened lengths, inplace)."""
+    cli = case["cli"]
+    t, l, m = cli.get("t", -1), cli.get("l", 100), cli.get("m", 1)
+    indexed = 0 if case["unindexed"] else 1
+    if case["mode"] == "I":  # in-place rebuild: model loaded AS the output type with DORESET, corpus preloaded
+        return dict(mintokens=t, minlength=m, maxlength=l, doreset=1, indexed=indexed), dict(mintokens=t, maxlength=l, minlength=m, indexed=indexed, streamed=0), True
+    # -j: PatternSetModel(file, options); an unindexed output model streams the corpus file
+    return dict(mintokens=t, minlength=m, maxlength=l, indexed=0), dict(mintokens=t, maxlength=l, minlength=m, indexed=indexed, streamed=1 if case["unindexed"] else 0), False

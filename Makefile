@@ -35,7 +35,15 @@ $(LIBDIR)/shard_kernels.o: $(CSRC)/shard_kernels.cu $(CSRC)/kernels.h $(CSRC)/de
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/shard_kernels.ptxas.log || (cat $(LIBDIR)/shard_kernels.ptxas.log; false)
 
-$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o $(LIBDIR)/index.o $(LIBDIR)/shard_kernels.o
+$(LIBDIR)/pattern_index.o: $(CSRC)/pattern_index.cu $(CSRC)/kernels.h $(CSRC)/device_utils.cuh $(CSRC)/spooky.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/pattern_index.ptxas.log || (cat $(LIBDIR)/pattern_index.ptxas.log; false)
+
+$(LIBDIR)/model_io.o: $(CSRC)/model_io.cu $(CSRC)/kernels.h $(CSRC)/engine_common.h include/colibri_b200.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/model_io.ptxas.log || (cat $(LIBDIR)/model_io.ptxas.log; false)
+
+$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o $(LIBDIR)/index.o $(LIBDIR)/shard_kernels.o $(LIBDIR)/pattern_index.o $(LIBDIR)/model_io.o
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^
 
 oracle:

@@ -44,7 +44,8 @@ class COptions(C.Structure):
 
     _fields_ = [(n, C.c_int32) for n in (
         "MINTOKENS", "MINTOKENS_SKIPGRAMS", "MINTOKENS_UNIGRAMS", "MINLENGTH", "MAXLENGTH", "MAXBACKOFFLENGTH", "MINSKIPTYPES", "MAXSKIPS",
-        "DOSKIPGRAMS", "DOSKIPGRAMS_EXHAUSTIVE", "DOPATTERNPERLINE", "PRUNENONSUBSUMED", "PRUNESUBSUMED", "QUIET", "DEBUG", "model_type", "streamed", "device")]
+        "DOSKIPGRAMS", "DOSKIPGRAMS_EXHAUSTIVE", "DOPATTERNPERLINE", "PRUNENONSUBSUMED", "PRUNESUBSUMED", "QUIET", "DEBUG", "model_type", "streamed", "device",
+        "DOREMOVEINDEX", "DOREMOVENGRAMS", "DOREMOVESKIPGRAMS", "DOREMOVEFLEXGRAMS", "DORESET")]
 
 
 class CSynthParams(C.Structure):
@@ -93,6 +94,11 @@ def library():
     L.colibri_b200_model_export_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.colibri_b200_model_write.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.colibri_b200_model_lookup.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, _u32p]
+    L.colibri_b200_model_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.colibri_b200_model_from_flat.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
+                                               C.POINTER(C.c_void_p)]
+    L.colibri_b200_model_load.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(COptions), C.c_void_p, C.POINTER(C.c_void_p)]
+    L.colibri_b200_train_constrained.argtypes = [C.c_void_p, C.POINTER(COptions), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     L.colibri_b200_model_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.colibri_b200_model_counters.argtypes = [C.c_void_p, _u64p]
     L.colibri_b200_model_level_counters.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
@@ -342,7 +348,34 @@ class Model:
         return int(c.value)
 
     def has(self, key: bytes) -> bool:
-        return self.occurrencecount(key) > 0
+        return self.lookup_batch([key])[1][0] >= 0
+
+    def lookup_batch(self, keys):
+        """(counts uint32[n], index int64[n]) of n patterns given as byte strings: occurrencecount()/has() on the device.
+        index = position in the export order, -1 when the pattern is not in the model."""
+        blob = np.frombuffer(b"".join(keys), dtype=np.uint8) if keys else np.zeros(0, dtype=np.uint8)
+        off = np.zeros(len(keys) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(k) for k in keys])
+        counts = np.zeros(len(keys), dtype=np.uint32)
+        index = np.full(len(keys), -1, dtype=np.int64)
+        _check(library().colibri_b200_model_lookup_batch(self._h, blob.ctypes.data if blob.size else None, off.ctypes.data, len(keys), counts.ctypes.data, index.ctypes.data))
+        return counts, index
+
+    @classmethod
+    def from_flat(cls, keys, key_off, counts=None, refs=None, tokens=0, types=0, model_type=UNINDEXEDPATTERNMODEL, device=0) -> "Model":
+        """Upload a pattern set given as flat host arrays (the export form)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint8)
+        key_off = np.ascontiguousarray(key_off, dtype=np.uint64)
+        n = len(key_off) - 1
+        counts = None if counts is None else np.ascontiguousarray(counts, dtype=np.uint32)
+        rs = rt = ro = None
+        if refs is not None:
+            rs, rt, ro = (np.ascontiguousarray(refs[0], dtype=np.uint32), np.ascontiguousarray(refs[1], dtype=np.uint16), np.ascontiguousarray(refs[2], dtype=np.uint64))
+        h = C.c_void_p()
+        _check(library().colibri_b200_model_from_flat(keys.ctypes.data if keys.size else None, key_off.ctypes.data, counts.ctypes.data if counts is not None else None, n,
+                                                       rs.ctypes.data if rs is not None and rs.size else None, rt.ctypes.data if rt is not None and rt.size else None,
+                                                       ro.ctypes.data if ro is not None else None, int(tokens), int(types), int(model_type), int(device), C.byref(h)))
+        return cls(h)
 
     def timings(self):
         ms = (C.c_double * T_NPHASES)()
@@ -385,6 +418,38 @@ def train(corpus, options: PatternModelOptions | None = None, **kw) -> Model:
     else:
         a = _as_u8(corpus)
         _check(library().colibri_b200_train(a.ctypes.data if a.size else None, a.size, C.byref(options._c), C.byref(h)))
+    return Model(h)
+
+
+def load_model(blob, options: PatternModelOptions | None = None, constrain: Model | None = None, **kw) -> Model:
+    """PatternModel::load: the bytes of a .colibri.patternmodel file read as options.model_type, the options acting as filters
+    (MINTOKENS, MINLENGTH, MAXLENGTH, DOREMOVE*, DORESET) and `constrain` as the membership constraint."""
+    if options is None:
+        options = PatternModelOptions(**kw)
+    elif kw:
+        raise TypeError("pass either options or keyword fields")
+    a = _as_u8(blob)
+    h = C.c_void_p()
+    _check(library().colibri_b200_model_load(a.ctypes.data if a.size else None, a.size, C.byref(options._c), constrain._h if constrain is not None else None, C.byref(h)))
+    return Model(h)
+
+
+def train_constrained(corpus, constrain: Model, inplace: bool = False, options: PatternModelOptions | None = None, **kw) -> Model:
+    """PatternModel::train(corpus, options, constrainbymodel): only patterns of `constrain` are counted.  inplace=True is the
+    reference's constrainbymodel == this (CLI -I, stage 2 of -2): `constrain` is the model being rebuilt, loaded with DORESET."""
+    if options is None:
+        options = PatternModelOptions(**kw)
+    elif kw:
+        raise TypeError("pass either options or keyword fields")
+    own = None
+    if not isinstance(corpus, Corpus):
+        own = corpus = Corpus.from_bytes(corpus, device=options.device)
+    h = C.c_void_p()
+    try:
+        _check(library().colibri_b200_train_constrained(corpus._h, C.byref(options._c), constrain._h, 1 if inplace else 0, C.byref(h)))
+    finally:
+        if own is not None:
+            own.close()
     return Model(h)
 
 

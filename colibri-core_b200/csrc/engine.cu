@@ -284,7 +284,9 @@ struct Trainer {
     int build_refs(Segment& sg, const uint32_t* ids, const uint32_t* map, bool by_class, uint64_t npos, uint64_t expect, bool keep_positions = false,
                    const uint32_t* pos_lookup = nullptr, uint32_t pos_div = 1);
     int indexed_skipgrams(int n, Segment& ng, const std::vector<DevBuf<uint32_t>>& ids, uint64_t& foundskip, uint64_t& keptskip, Segment& out);
+    int tokenise(DevBuf<uint32_t>& tok, uint64_t& npos, uint32_t& nclasses);
     int run();
+    int run_constrained(colibri_b200_model* cm, bool inplace);
 };
 
 int Trainer::prepare_index(const uint32_t* tok, uint64_t npos) {
@@ -419,12 +421,8 @@ int Trainer::indexed_skipgrams(int n, Segment& ng, const std::vector<DevBuf<uint
     return 0;
 }
 
-int Trainer::run() {
-    CUDA_TRY(cudaSetDevice(dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));  // (cudaGetDeviceProperties costs milliseconds per call)
-    timer.s = s;
-    int h_total = timer.begin(COLIBRI_T_TOTAL);
-
+// K0: stage the sentence-source tail, tokenise, check the encoding.  npos includes one virtual delimiter closing the last sentence.
+int Trainer::tokenise(DevBuf<uint32_t>& tok, uint64_t& npos, uint32_t& nclasses) {
     // ---- the sentence source quirk (see include/colibri_b200.h: streamed)
     if (c->nbytes == 0) return set_err(COLIBRI_E_FORMAT, "Attempting to read pattern from file, but file is empty?");  // src/pattern.cpp:520-523
     size_t staged = c->nbytes;
@@ -453,8 +451,7 @@ int Trainer::run() {
     TRY(read_stats());
     const uint64_t npos_real = h_stats.cursor;  // tokens + delimiters
     if (npos_real >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "corpus has %llu positions; the device index is 32 bit", (unsigned long long)npos_real);
-    const uint64_t npos = npos_real + 1;  // one virtual delimiter closes the last sentence
-    DevBuf<uint32_t> tok;
+    npos = npos_real + 1;  // one virtual delimiter closes the last sentence
     TRY(tok.alloc(dev, npos + 8));
     CUDA_TRY(cudaMemsetAsync(tok.p + npos_real, 0, 8 * sizeof(uint32_t), s));
     launches += launch_tokenise_write(s, c->body(), staged, blk.p, nblocks, tok.p, d_stats.p);
@@ -465,9 +462,22 @@ int Trainer::run() {
     if (h_stats.errflags & kErrReservedClass)
         return set_err(COLIBRI_E_UNSUPPORTED, "corpus contains the reserved skip/flex classes (3, 4) as running text; not on the device path");
     m->totaltokens = h_stats.totaltokens;
-    const uint32_t nclasses = h_stats.maxclass + 1;
+    nclasses       = h_stats.maxclass + 1;
     m->counters[0] = npos_real;
     m->counters[1] = c->nbytes;
+    return 0;
+}
+
+int Trainer::run() {
+    CUDA_TRY(cudaSetDevice(dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));  // (cudaGetDeviceProperties costs milliseconds per call)
+    timer.s = s;
+    int h_total = timer.begin(COLIBRI_T_TOTAL);
+    DevBuf<uint32_t> tok;
+    uint64_t         npos = 0;
+    uint32_t         nclasses = 0;
+    int              h = -1;
+    TRY(tokenise(tok, npos, nclasses));
 
     indexed = o.model_type == COLIBRI_INDEXEDPATTERNMODEL;
     if (indexed) {
@@ -762,6 +772,158 @@ int Trainer::run() {
     return 0;
 }
 
+
+// PatternModel::train with constrainbymodel != NULL (reference include/patternmodel.h:880-1345): ONE scan of the corpus that extracts every
+// window of MINLENGTH..MAXLENGTH tokens (:1064-1072) and counts it iff the constraint model has it (:1088-1089); then prune(MINTOKENS, 0)
+// (:1211-1218) and stop (:1246-1247).  Here: one launch per pattern length that the constraint set actually holds; the window's varint bytes
+// are rebuilt in registers, hashed with SpookyV2 (Pattern::hash) and probed in the set's HBM index (pattern_index.cu); survivors are
+// compacted out of the set's own blob.  Indexed models remember the match of every position and build the occurrence lists with the
+// ordered-pairs + stable radix sort of index.cu, one length at a time (survivors are ordered by length so the lists concatenate).
+int Trainer::run_constrained(colibri_b200_model* cm, bool inplace) {
+    CUDA_TRY(cudaSetDevice(dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    timer.s = s;
+    int h_total = timer.begin(COLIBRI_T_TOTAL);
+    TRY(ensure_index(cm, &launches));
+    DevBuf<uint32_t> tok;
+    uint64_t         npos = 0;
+    uint32_t         nclasses = 0;
+    TRY(tokenise(tok, npos, nclasses));
+    const uint64_t corpus_tokens = m->totaltokens;
+    indexed = o.model_type == COLIBRI_INDEXEDPATTERNMODEL;
+    if (indexed) {
+        int hi = timer.begin(COLIBRI_T_INDEX);
+        TRY(prepare_index(tok.p, npos));
+        timer.end(hi);
+    }
+    const uint64_t np = cm->npatterns;
+    const uint32_t t  = (uint32_t)o.MINTOKENS;
+    std::vector<int> lengths;  // the window lengths worth a scan
+    for (int n = o.MINLENGTH; n <= o.MAXLENGTH && n <= 255; ++n)
+        if (np && cm->meta.nhist[n]) lengths.push_back(n);
+
+    DevBuf<uint32_t> counts, flags, kmap;
+    TRY(counts.alloc(dev, std::max<uint64_t>(np, 1)));
+    TRY(flags.alloc(dev, np + 1));
+    CUDA_TRY(cudaMemsetAsync(counts.p, 0, std::max<uint64_t>(np, 1) * sizeof(uint32_t), s));
+    std::vector<DevBuf<uint32_t>> match(lengths.size());
+    TRY(zero_stats());
+    for (size_t k = 0; k < lengths.size(); ++k) {
+        if (indexed) TRY(match[k].alloc(dev, npos));
+        int hc = timer.begin(COLIBRI_T_COUNT, lengths[k]);
+        launches += launch_constrained_match(s, tok.p, npos, lengths[k], cm->d_keys.p, cm->d_off.p, cm->d_index.p, cm->index_cap, counts.p, indexed ? match[k].p : nullptr,
+                                             d_stats.p, sms);
+        timer.end(hc);
+    }
+    TRY(read_stats());
+    ngram_upserts = h_stats.valid_windows;
+
+    // ---- threshold (prune(MINTOKENS, 0)) and the numbers of the progress line
+    DevBuf<PatternMetaStats> d_pst;
+    PatternMetaStats         pst;
+    memset(&pst, 0, sizeof pst);
+    pst.minn = pst.kept_minn = 0xFFFFFFFFu;
+    TRY(d_pst.alloc(dev, 1));
+    CUDA_TRY(cudaMemcpyAsync(d_pst.p, &pst, sizeof pst, cudaMemcpyHostToDevice, s));
+    TRY(zero_stats());
+    int hp = timer.begin(COLIBRI_T_PRUNE);
+    launches += launch_constrained_stats(s, counts.p, cm->d_pn.p, np, t, flags.p, d_pst.p, d_stats.p);
+    timer.end(hp);
+    CUDA_TRY(cudaMemcpyAsync(&pst, d_pst.p, sizeof pst, cudaMemcpyDeviceToHost, s));
+    TRY(read_stats());
+    const uint64_t found = inplace ? np : h_stats.found;  // :1182 with prevsize = 0 (:970-971): an in-place rebuild "finds" every loaded pattern
+    const uint64_t kept = h_stats.kept, kept_occ = h_stats.kept_occ;
+
+    // ---- survivors -> the flat model (ordered by length for indexed models)
+    int he = timer.begin(COLIBRI_T_EXPORT);
+    if (indexed) TRY(kmap.alloc(dev, std::max<uint64_t>(np, 1)));
+    TRY(compact_patterns(cm, flags.p, counts.p, indexed, false, indexed ? kmap.p : nullptr, m, &launches));
+    timer.end(he);
+    if (m->npatterns != kept) return set_err(COLIBRI_E_CUDA, "constrained training: %llu survivors compacted, %llu counted", (unsigned long long)m->npatterns, (unsigned long long)kept);
+    if (indexed && kept) {
+        int hi = timer.begin(COLIBRI_T_INDEX);
+        DevBuf<uint64_t> tmp;
+        TRY(tmp.alloc(dev, kept / 2048 + 4));
+        launches += launch_exclusive_scan_u32_u64(s, m->d_counts.p, m->d_ref_off.p, kept, tmp.p);
+        m->nrefs = kept_occ;
+        TRY(m->d_ref_sentence.alloc(dev, std::max<uint64_t>(kept_occ, 1)));
+        TRY(m->d_ref_token.alloc(dev, std::max<uint64_t>(kept_occ, 1)));
+        uint64_t base = 0, rbase = 0;
+        for (size_t k = 0; k < lengths.size(); ++k) {
+            const int      n  = lengths[k];
+            const uint64_t kn = pst.kept_n[n], on = pst.kept_occ_n[n];
+            if (kn == 0) continue;
+            Segment sg;
+            sg.n     = n;
+            sg.count = base + kn;  // keys are model-wide survivor indices: this bounds the radix passes
+            TRY(build_refs(sg, match[k].p, kmap.p, false, npos, on));
+            CUDA_TRY(cudaMemcpyAsync(m->d_ref_sentence.p + rbase, sg.ref_sentence.p, on * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(m->d_ref_token.p + rbase, sg.ref_token.p, on * sizeof(uint16_t), cudaMemcpyDeviceToDevice, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            base += kn;
+            rbase += on;
+        }
+        timer.end(hi);
+        if (base != kept || rbase != kept_occ) return set_err(COLIBRI_E_CUDA, "constrained training: occurrence lists cover %llu of %llu patterns", (unsigned long long)base, (unsigned long long)kept);
+    }
+
+    // ---- header numbers (see oracle_train_constrained for the line-by-line account)
+    std::vector<PassStat> passes;
+    int maxn = 0, minn = 999;
+    if (inplace) {
+        maxn            = cm->maxn;
+        minn            = cm->minn;
+        m->hasskipgrams = cm->hasskipgrams;
+        m->totaltokens  = corpus_tokens;  // :889-891, :1047-1048
+        m->totaltypes   = 0;
+        if (t > 1)
+            m->totaltypes = np;  // :1199-1201: size() of the model being rebuilt
+        else if (o.MINLENGTH == 1)
+            m->totaltypes = cm->meta.unigram_ngrams;  // totalwordtypesingroup(NGRAM, 1), :1202-1208
+    } else {
+        m->totaltypes  = cm->totaltypes;  // :892-895
+        m->totaltokens = cm->totaltokens + corpus_tokens;
+    }
+    if (found) {  // :1184-1188 with n == 1
+        maxn = std::max(maxn, 1);
+        minn = std::min(minn, 1);
+        passes.push_back({1, found, 0, found - kept});
+    }
+    if (t == 1 && kept) {  // postread, :1274-1277
+        maxn = std::max(maxn, (int)pst.kept_maxn);
+        minn = std::min(minn, (int)pst.kept_minn);
+    }
+    if (m->totaltypes == 0 && kept && !(inplace && t == 1 && o.MINLENGTH == 1)) {
+        // types() (:1700-1704) computes totalwordtypesingroup(0, 0) on demand when totaltypes was never set, and write() stores that:
+        // the distinct classes occurring in the patterns that are left
+        const uint64_t   words = ((uint64_t)cm->meta.maxclass >> 5) + 1;
+        DevBuf<uint32_t> bitmap;
+        TRY(bitmap.alloc(dev, words));
+        CUDA_TRY(cudaMemsetAsync(bitmap.p, 0, words * sizeof(uint32_t), s));
+        TRY(zero_stats());
+        launches += launch_token_bitmap(s, m->d_keys.p, m->d_off.p, kept, bitmap.p);
+        launches += launch_popcount(s, bitmap.p, words, &d_stats.p->found);
+        TRY(read_stats());
+        m->totaltypes = h_stats.found;
+    }
+    m->maxn   = maxn;
+    m->minn   = minn;
+    m->passes = passes;
+    timer.end(h_total);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    std::map<int, double> level_ms;
+    timer.resolve(m->ms, &level_ms);
+    for (auto& kv : level_ms) {
+        m->levels[kv.first].ms      = kv.second;
+        m->levels[kv.first].windows = 0;
+    }
+    m->counters[2] = launches;
+    m->counters[3] = ngram_upserts;
+    m->counters[6] = corpus_tokens;
+    m->counters[7] = g_pool[dev & 15].peak;
+    return 0;
+}
+
 }  // namespace
 
 // survivors of all levels -> the flat device-resident export (keys blob, offsets, counts) of the model
@@ -870,6 +1032,51 @@ extern "C" int colibri_b200_train_corpus(colibri_b200_corpus* corpus, const coli
     return 0;
 }
 
+// options of a constrained run: the same normalisation as train() (:883-888); what the single constrained scan never consults is not checked
+static int check_constrained_options(colibri_b200_options& o) {
+    if (o.MINTOKENS == -1) o.MINTOKENS = 2;
+    if (o.MINTOKENS == 0) o.MINTOKENS = 1;
+    if (o.MINTOKENS < 1) return set_err(COLIBRI_E_INVALID, "MINTOKENS=%d", o.MINTOKENS);
+    if (o.model_type != COLIBRI_UNINDEXEDPATTERNMODEL && o.model_type != COLIBRI_INDEXEDPATTERNMODEL)
+        return set_err(COLIBRI_E_UNSUPPORTED, "model type %d (only 10 = unindexed and 20 = indexed run on the device)", o.model_type);
+    if (o.DOSKIPGRAMS || o.DOSKIPGRAMS_EXHAUSTIVE) return set_err(COLIBRI_E_UNSUPPORTED, "skipgrams under a constraint model are not on the device path yet");
+    if (o.MINTOKENS_UNIGRAMS > o.MINTOKENS) return set_err(COLIBRI_E_UNSUPPORTED, "MINTOKENS_UNIGRAMS > MINTOKENS under a constraint model is not on the device path");
+    if (o.DOPATTERNPERLINE) return set_err(COLIBRI_E_UNSUPPORTED, "DOPATTERNPERLINE is not on the device path");
+    if (o.PRUNENONSUBSUMED || o.PRUNESUBSUMED) return set_err(COLIBRI_E_UNSUPPORTED, "PRUNE(NON)SUBSUMED is not on the device path");
+    if (o.MAXLENGTH < 1 || o.MAXLENGTH > 255) return set_err(COLIBRI_E_UNSUPPORTED, "MAXLENGTH=%d (device path supports 1..255)", o.MAXLENGTH);
+    if (o.MINLENGTH < 1) o.MINLENGTH = 1;
+    return 0;
+}
+
+extern "C" int colibri_b200_train_constrained(colibri_b200_corpus* corpus, const colibri_b200_options* opt, colibri_b200_model* constrain, int inplace, colibri_b200_model** out) {
+    if (!out) return set_err(COLIBRI_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!corpus || !opt || !constrain) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    colibri_b200_options o = *opt;
+    TRY(check_constrained_options(o));
+    if (o.device != corpus->device) return set_err(COLIBRI_E_INVALID, "options.device=%d but the corpus is staged on device %d", o.device, corpus->device);
+    if (constrain->device != corpus->device) return set_err(COLIBRI_E_INVALID, "the constraint model lives on device %d, the corpus on device %d", constrain->device, corpus->device);
+    colibri_b200_model* m = nullptr;
+    TRY(new_model(corpus->device, o.model_type, &m));
+    int rc;
+    {
+        Trainer tr;
+        tr.c   = corpus;
+        tr.o   = o;
+        tr.m   = m;
+        tr.s   = m->stream;
+        tr.dev = corpus->device;
+        rc     = tr.run_constrained(constrain, inplace != 0);
+        if (rc) cudaStreamSynchronize(m->stream);
+    }
+    if (rc) {
+        colibri_b200_model_free(m);
+        return rc;
+    }
+    *out = m;
+    return 0;
+}
+
 extern "C" int colibri_b200_train(const uint8_t* host_body, size_t nbytes, const colibri_b200_options* opt, colibri_b200_model** out) {
     if (!out) return set_err(COLIBRI_E_INVALID, "out is NULL");
     *out = nullptr;
@@ -967,37 +1174,6 @@ extern "C" int colibri_b200_model_write(colibri_b200_model* m, uint8_t* buf, siz
     }
     return 0;
 }
-extern "C" int colibri_b200_model_lookup(colibri_b200_model* m, const uint8_t* key, uint32_t len, uint32_t* count) {
-    if (!m || !count || (!key && len)) return set_err(COLIBRI_E_INVALID, "NULL argument");
-    TRY(ensure_host(m));
-    auto cmp_key = [&](uint32_t idx, const uint8_t* k, uint32_t l) {  // <0: pattern idx sorts before (k,l)
-        size_t pl = (size_t)(m->h_off[idx + 1] - m->h_off[idx]);
-        int    c  = memcmp(m->h_keys.data() + m->h_off[idx], k, std::min<size_t>(pl, l));
-        if (c) return c;
-        return pl < l ? -1 : (pl > l ? 1 : 0);
-    };
-    if (m->h_sorted.size() != m->npatterns) {
-        m->h_sorted.resize(m->npatterns);
-        for (uint64_t i = 0; i < m->npatterns; ++i) m->h_sorted[i] = (uint32_t)i;
-        std::sort(m->h_sorted.begin(), m->h_sorted.end(), [&](uint32_t a, uint32_t b) {
-            size_t la = (size_t)(m->h_off[a + 1] - m->h_off[a]);
-            return cmp_key(b, m->h_keys.data() + m->h_off[a], (uint32_t)la) > 0;
-        });
-    }
-    *count = 0;
-    size_t lo = 0, hi = m->h_sorted.size();
-    while (lo < hi) {
-        size_t mid = (lo + hi) / 2;
-        int    c   = cmp_key(m->h_sorted[mid], key, len);
-        if (c == 0) {
-            *count = m->h_counts[m->h_sorted[mid]];
-            return 0;
-        }
-        if (c < 0) lo = mid + 1; else hi = mid;
-    }
-    return 0;
-}
-
 // ------------------------------------------------------------------------------------------------ parity helpers
 extern "C" int colibri_b200_hash64_batch(const uint8_t* keys, const uint64_t* key_off, uint64_t n, uint64_t* out, int device) {
     if (colibri_b200_device_count() <= 0) return set_err(COLIBRI_E_CUDA, "no CUDA device available: the B200 path has no CPU fallback");

@@ -234,6 +234,15 @@ struct colibri_b200_model {
     std::vector<uint32_t> h_ref_sentence;
     std::vector<uint16_t> h_ref_token;
     std::vector<uint64_t> h_ref_off;
+    // shape of every pattern (tokens, category) and the hash index over the pattern bytes (pattern_index.cu); built on first
+    // use by constrained training, load filters and lookups
+    DevBuf<uint16_t>           d_pn;
+    DevBuf<uint8_t>            d_pcat;
+    bool                       meta_ready = false;
+    colibri::PatternMetaStats  meta;
+    DevBuf<unsigned long long> d_index;
+    uint64_t                   index_cap = 0;
+    bool                       index_ready = false;
     double   ms[COLIBRI_T_NPHASES] = {0};
     uint64_t counters[8] = {0};
     std::map<int, LevelInfo> levels;
@@ -243,4 +252,14 @@ struct colibri_b200_model {
 namespace colibri {
 // survivors of all levels -> the flat device-resident export of the model (engine.cu)
 int export_segments(int dev, cudaStream_t s, std::vector<Segment>& segs, const uint32_t* tok, colibri_b200_model* m, uint64_t& launches);
+// model_io.cu: a fresh handle with its own stream on `device`
+int new_model(int device, int model_type, colibri_b200_model** out);
+// model_io.cu: per-pattern shape (d_pn, d_pcat, meta) / the hash index over the pattern bytes, built once per model
+int ensure_meta(colibri_b200_model* m, uint64_t* launches);
+int ensure_index(colibri_b200_model* m, uint64_t* launches);
+// model_io.cu: the patterns of `src` whose flag is set become the flat arrays of `dst` (work enqueued on dst->stream, synchronised on return).
+//   d_counts: their counts (NULL: zeros); order_by_length: stable order by token count, so that occurrence lists built per length concatenate;
+//   copy_refs: carry src's occurrence lists over; d_kmap (optional, src->npatterns entries): old index -> new index + 1, 0 = dropped.
+int compact_patterns(const colibri_b200_model* src, const uint32_t* d_flags, const uint32_t* d_counts, bool order_by_length, bool copy_refs, uint32_t* d_kmap, colibri_b200_model* dst,
+                     uint64_t* launches);
 }  // namespace colibri

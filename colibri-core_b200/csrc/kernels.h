@@ -137,6 +137,38 @@ int launch_skip_owner_survivors(cudaStream_t s, const uint32_t* sv_idx, const ui
                                 const unsigned long long* out_base, unsigned long long* cursors, void* out /* 16 B records */, int sms);
 int launch_skip_sender_survivors(cudaStream_t s, const void* recs, uint64_t n, const uint32_t* pos_of_rec, uint64_t send_base, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* sv_mask);
 
+// ---- pattern sets addressed by Pattern::hash of their bytes (pattern_index.cu): constrained training, load filters, queries
+constexpr uint32_t kMaxIndexedKeyBytes = 191;  // SpookyV2 "Short" range; longer patterns are refused
+struct PatternMetaStats {  // zeroed by the host except minn / kept_minn = 0xFFFFFFFF
+    unsigned int       maxn, minn, hasskip, hasflex, maxclass, malformed, duplicates;
+    unsigned int       kept_maxn, kept_minn, kept_hasskip, kept_hasflex;
+    unsigned int       unigram_ngrams;   // patterns of one token that are plain n-grams (totalwordtypesingroup(NGRAM, 1))
+    unsigned long long nhist[256];       // patterns per length (lengths >= 255 share the last bin)
+    unsigned long long kept_n[256];      // survivors per length
+    unsigned long long kept_occ_n[256];  // their occurrences
+};
+int launch_pattern_meta(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, uint16_t* pn, uint8_t* pcat, PatternMetaStats* st);
+// slots: cap_pow2 zeroed 8-byte entries {hash tag << 32 | pattern index + 1}
+int launch_index_build(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, unsigned long long* slots, uint64_t cap_pow2, PatternMetaStats* st);
+int launch_index_lookup(cudaStream_t s, const uint8_t* qkeys, const uint64_t* qoff, uint64_t nq, const uint8_t* keys, const uint64_t* off, const unsigned long long* slots,
+                        uint64_t cap_pow2, uint32_t* out_idx1 /* pattern index + 1, or 0 */);
+int launch_gather_counts(cudaStream_t s, const uint32_t* idx1, uint64_t nq, const uint32_t* counts, uint32_t* out);
+// windows of n tokens that are in the set: counts[pattern] += 1, match[p] = pattern index + 1 or 0 (match may be NULL)
+int launch_constrained_match(cudaStream_t s, const uint32_t* tok, uint64_t npos, int n, const uint8_t* keys, const uint64_t* off, const unsigned long long* slots, uint64_t cap_pow2,
+                             uint32_t* counts, uint32_t* match, DeviceStats* st, int sms);
+int launch_constrained_stats(cudaStream_t s, const uint32_t* counts, const uint16_t* pn, uint64_t np, uint32_t threshold, uint32_t* flags, PatternMetaStats* st, DeviceStats* ds);
+int launch_load_filter(cudaStream_t s, const uint16_t* pn, const uint8_t* pcat, const uint32_t* counts, const uint32_t* constrain_idx1, uint64_t np, uint32_t mintokens,
+                       uint32_t minlength, uint32_t maxlength, int dongrams, int doskipgrams, int doflexgrams, uint32_t* flags, PatternMetaStats* st);
+int launch_select_scatter(cudaStream_t s, const uint32_t* flags, const uint64_t* newpos, const uint16_t* pn, uint64_t np, uint32_t* sel_idx, uint32_t* sel_n);
+int launch_gather_meta(cudaStream_t s, const uint32_t* sel_idx, uint64_t k, const uint64_t* off, const uint32_t* counts, uint32_t* kmap, uint32_t* lens, uint16_t* len16,
+                       uint32_t* counts_out);
+int launch_gather_keys(cudaStream_t s, const uint32_t* sel_idx, uint64_t k, const uint8_t* keys, const uint64_t* off, const uint64_t* new_off, uint8_t* out);
+int launch_gather_refs(cudaStream_t s, const uint32_t* sel_idx, uint64_t k, const uint64_t* ref_off, const uint32_t* rs, const uint16_t* rt, const uint64_t* new_ref_off,
+                       uint32_t* rs_out, uint16_t* rt_out);
+int launch_iota(cudaStream_t s, uint32_t* out, uint64_t n);
+int launch_token_bitmap(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, uint32_t* bitmap /* zeroed, (maxclass >> 5) + 1 words */);
+int launch_popcount(cudaStream_t s, const uint32_t* words, uint64_t n, unsigned long long* total /* zeroed */);
+
 // ---- parity helpers / measurement input
 int launch_hash64_batch(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t n, uint64_t* out);
 int launch_synth_lengths(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint64_t first, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases,

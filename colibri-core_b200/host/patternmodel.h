@@ -13,6 +13,7 @@
 // Errors print a message on std::cerr and throw InternalError (reference include/common.h:41-44).  There is no CPU
 // implementation behind this header: option combinations outside the accelerated subset throw, they do not fall back.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <fstream>
 #include <iostream>
@@ -106,6 +107,15 @@ class IndexedCorpus {
     const unsigned char* beginpointer() const { return body_.data(); }
 };
 
+namespace colibri_b200_detail {
+struct FlatView {  // a model's patterns as the C ABI takes them (colibri_b200_model_from_flat)
+    const uint8_t*  keys = nullptr;
+    const uint64_t* off = nullptr;
+    const uint32_t* counts = nullptr;
+    uint64_t        npatterns = 0;
+};
+}  // namespace colibri_b200_detail
+
 class PatternModelInterface {  // reference include/patternmodel.h:234-287
   public:
     virtual ~PatternModelInterface() {}
@@ -116,6 +126,8 @@ class PatternModelInterface {  // reference include/patternmodel.h:234-287
     virtual int    minlength() const = 0;
     virtual size_t types() = 0;
     virtual size_t tokens() const = 0;
+    /// B200 build: what stands in for getstoreinterface() (reference :286) -- the patterns as flat arrays, to be uploaded as a constraint set
+    virtual colibri_b200_detail::FlatView flatview() const = 0;
 };
 
 /// Placeholder so that the train() signatures match the reference's (filter argument); filters are not on the device path.
@@ -157,13 +169,111 @@ class DevicePatternModel : public PatternModelInterface {
 
     void materialise();
 
+    static colibri_b200_options c_options(const PatternModelOptions& options, bool streamed) {
+        colibri_b200_options o;
+        colibri_b200_options_default(&o);
+        o.MINTOKENS              = options.MINTOKENS;
+        o.MINTOKENS_SKIPGRAMS    = options.MINTOKENS_SKIPGRAMS;
+        o.MINTOKENS_UNIGRAMS     = options.MINTOKENS_UNIGRAMS;
+        o.MINLENGTH              = options.MINLENGTH;
+        o.MAXLENGTH              = options.MAXLENGTH;
+        o.MAXBACKOFFLENGTH       = options.MAXBACKOFFLENGTH;
+        o.MINSKIPTYPES           = options.MINSKIPTYPES;
+        o.MAXSKIPS               = options.MAXSKIPS;
+        o.DOSKIPGRAMS            = options.DOSKIPGRAMS;
+        o.DOSKIPGRAMS_EXHAUSTIVE = options.DOSKIPGRAMS_EXHAUSTIVE;
+        o.DOPATTERNPERLINE       = options.DOPATTERNPERLINE;
+        o.PRUNENONSUBSUMED       = options.PRUNENONSUBSUMED;
+        o.PRUNESUBSUMED          = options.PRUNESUBSUMED;
+        o.DOREMOVEINDEX          = options.DOREMOVEINDEX;
+        o.DOREMOVENGRAMS         = options.DOREMOVENGRAMS;
+        o.DOREMOVESKIPGRAMS      = options.DOREMOVESKIPGRAMS;
+        o.DOREMOVEFLEXGRAMS      = options.DOREMOVEFLEXGRAMS;
+        o.DORESET                = options.DORESET;
+        o.QUIET                  = options.QUIET;
+        o.DEBUG                  = options.DEBUG;
+        o.model_type             = kModelType;
+        o.streamed               = streamed ? 1 : 0;
+        o.device                 = colibri_b200_detail::default_device();
+        return o;
+    }
+
+    /// take over the result of a device call: header numbers + the flat export
+    void adopt(colibri_b200_model* h) {
+        using colibri_b200_detail::fail;
+        totaltokens  = colibri_b200_model_tokens(h);
+        totaltypes   = colibri_b200_model_types(h);
+        maxn         = colibri_b200_model_maxn(h);
+        minn         = colibri_b200_model_minn(h);
+        hasskipgrams = colibri_b200_model_hasskipgrams(h) != 0;
+        uint64_t np = 0, kb = 0, nr = 0;
+        if (colibri_b200_model_export_sizes(h, &np, &kb, &nr) != COLIBRI_OK) fail(colibri_b200_last_error());
+        keys_.assign(kb + 1, 0);
+        off_.assign(np + 1, 0);
+        counts_.assign(np + 1, 0);
+        ref_sentence_.clear();
+        ref_token_.clear();
+        ref_off_.clear();
+        if (kModelType == INDEXEDPATTERNMODEL) {
+            ref_sentence_.assign(nr + 1, 0);
+            ref_token_.assign(nr + 1, 0);
+            ref_off_.assign(np + 1, 0);
+        }
+        if (colibri_b200_model_export(h, keys_.data(), off_.data(), counts_.data(), kModelType == INDEXEDPATTERNMODEL ? ref_sentence_.data() : nullptr,
+                                      kModelType == INDEXEDPATTERNMODEL ? ref_token_.data() : nullptr, kModelType == INDEXEDPATTERNMODEL ? ref_off_.data() : nullptr) != COLIBRI_OK)
+            fail(colibri_b200_last_error());
+        counts_.resize(np);
+        map_.clear();
+        map_ready_ = false;
+    }
+
+    /// train() under a constraint model (reference include/patternmodel.h:880-1345 with constrainbymodel != NULL): one scan, only the
+    /// constraint model's patterns are counted.  constrainbymodel == this is the in-place rebuild of the CLI's -I / -2.
+    void train_constrained_body(const unsigned char* body, size_t nbytes, bool streamed, const PatternModelOptions& options, PatternModelInterface* constrainbymodel) {
+        using colibri_b200_detail::fail;
+        const bool           inplace = constrainbymodel == static_cast<PatternModelInterface*>(this);
+        colibri_b200_options o       = c_options(options, streamed);
+        const int mintokens          = options.MINTOKENS == -1 ? 2 : (options.MINTOKENS == 0 ? 1 : options.MINTOKENS);
+        if (!options.QUIET) std::cerr << "Training patternmodel, constrained by another model, occurrence threshold: " << mintokens << std::endl;  // reference :922-931
+        if (options.DOSKIPGRAMS || options.DOSKIPGRAMS_EXHAUSTIVE) fail("skipgrams under a constraint model are not available in the B200 build");
+        const colibri_b200_detail::FlatView v = constrainbymodel->flatview();
+        colibri_b200_detail::ModelHandle    cm, mh;
+        const uint64_t                      zero = 0;
+        // an in-place rebuild starts from reset values (the caller loaded with DORESET): only the patterns matter
+        if (colibri_b200_model_from_flat(v.keys, v.npatterns ? v.off : &zero, nullptr, v.npatterns, nullptr, nullptr, nullptr, constrainbymodel->tokens(), constrainbymodel->types(),
+                                         UNINDEXEDPATTERNMODEL, o.device, &cm.h) != COLIBRI_OK)
+            fail(colibri_b200_last_error());
+        colibri_b200_corpus* corpus = nullptr;
+        if (colibri_b200_corpus_stage(body, nbytes, o.device, &corpus) != COLIBRI_OK) fail(colibri_b200_last_error());
+        if (!options.QUIET) std::cerr << "Counting n-grams that occur in constraint model" << std::endl;  // reference :1010-1011
+        const int rc = colibri_b200_train_constrained(corpus, &o, cm.h, inplace ? 1 : 0, &mh.h);
+        colibri_b200_corpus_free(corpus);
+        if (rc != COLIBRI_OK) fail(colibri_b200_last_error());
+        if (!options.QUIET) {
+            uint64_t st[4];
+            if (colibri_b200_model_passes(mh.h) > 0 && colibri_b200_model_pass_stats(mh.h, 0, st) == COLIBRI_OK)
+                std::cerr << " Found " << st[1] << " ngrams...pruned " << st[3] << "...total kept: " << st[1] - st[3] << std::endl;  // reference :1195-1245
+            else
+                std::cerr << "None found" << std::endl;
+        }
+        const int keep_maxn = maxn, keep_minn = minn;
+        adopt(mh.h);
+        if (inplace) {  // maxn / minn only ever widen across load() and train() (reference :578-581, :1184-1188)
+            maxn = std::max(maxn, keep_maxn);
+            minn = std::min(minn, keep_minn);
+        }
+    }
+
     void train_body(const unsigned char* body, size_t nbytes, bool streamed, const PatternModelOptions& options, PatternModelInterface* constrainbymodel, PatternSet<>* filter,
                     bool continued, uint32_t firstsentence) {
         using colibri_b200_detail::fail;
-        if (constrainbymodel != nullptr) fail("training constrained by another model is not available in the B200 build");
         if (filter != nullptr && filter->size() > 0) fail("training with a pattern filter is not available in the B200 build");
         if (continued) fail("continued training is not available in the B200 build");
         if (firstsentence != 1) fail("firstsentence != 1 is not available in the B200 build");
+        if (constrainbymodel != nullptr) {
+            train_constrained_body(body, nbytes, streamed, options, constrainbymodel);
+            return;
+        }
         colibri_b200_options o;
         colibri_b200_options_default(&o);
         o.MINTOKENS              = options.MINTOKENS;
@@ -226,22 +336,7 @@ class DevicePatternModel : public PatternModelInterface {
                 if (last < options.MAXLENGTH) std::cerr << "Counting " << last + 1 << "-skipgrams" << std::endl << " None found" << std::endl;
             }
         }
-        uint64_t np = 0, kb = 0, nr = 0;
-        if (colibri_b200_model_export_sizes(mh.h, &np, &kb, &nr) != COLIBRI_OK) fail(colibri_b200_last_error());
-        keys_.assign(kb + 1, 0);
-        off_.assign(np + 1, 0);
-        counts_.assign(np + 1, 0);
-        if (kModelType == INDEXEDPATTERNMODEL) {
-            ref_sentence_.assign(nr + 1, 0);
-            ref_token_.assign(nr + 1, 0);
-            ref_off_.assign(np + 1, 0);
-        }
-        if (colibri_b200_model_export(mh.h, keys_.data(), off_.data(), counts_.data(), kModelType == INDEXEDPATTERNMODEL ? ref_sentence_.data() : nullptr,
-                                      kModelType == INDEXEDPATTERNMODEL ? ref_token_.data() : nullptr, kModelType == INDEXEDPATTERNMODEL ? ref_off_.data() : nullptr) != COLIBRI_OK)
-            fail(colibri_b200_last_error());
-        counts_.resize(np);
-        map_.clear();
-        map_ready_ = false;
+        adopt(mh.h);
     }
 
   public:
@@ -249,7 +344,65 @@ class DevicePatternModel : public PatternModelInterface {
     bool hasflexgrams = false;
 
     DevicePatternModel(IndexedCorpus* corpus = nullptr) : reverseindex(corpus) {}
+    /// Read a pattern model from file (reference include/patternmodel.h:700-726); the options act as filters
+    DevicePatternModel(const std::string& filename, const PatternModelOptions& options, PatternModelInterface* constrainmodel = nullptr, IndexedCorpus* corpus = nullptr)
+        : reverseindex(corpus) {
+        if (!options.QUIET) std::cerr << "Loading " << filename << std::endl;
+        std::ifstream in(filename, std::ios::in | std::ios::binary);
+        if (!in.good()) {
+            std::cerr << "ERROR: Unable to load file " << filename << std::endl;
+            throw InternalError();
+        }
+        this->load(in, options, constrainmodel);
+    }
+    DevicePatternModel(std::istream& f, const PatternModelOptions& options, PatternModelInterface* constrainmodel = nullptr, IndexedCorpus* corpus = nullptr) : reverseindex(corpus) {
+        this->load(f, options, constrainmodel);
+    }
     virtual ~DevicePatternModel() {}
+
+    /// Read a pattern model from a stream (reference include/patternmodel.h:781-861 over PatternMapStore::read, include/patternstore.h:555-619):
+    /// count >= MINTOKENS, MINLENGTH <= n <= MAXLENGTH, DOREMOVE{NGRAMS,SKIPGRAMS,FLEXGRAMS}, membership in constrainmodel, DORESET.
+    /// The record stream is scanned on the host; shapes, filters, the constraint test and the compaction run on the device.
+    virtual void load(std::istream& f, const PatternModelOptions& options, PatternModelInterface* constrainmodel = nullptr) {
+        using colibri_b200_detail::fail;
+        std::vector<unsigned char> all((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        if (all.size() < 3 || all[0] != 0 || (all[1] != UNINDEXEDPATTERNMODEL && all[1] != INDEXEDPATTERNMODEL)) {
+            if (all.size() >= 3 && all[0] == 0 && (all[1] == UNINDEXEDPATTERNPOINTERMODEL || all[1] == INDEXEDPATTERNPOINTERMODEL || all[1] == PATTERNALIGNMENTMODEL))
+                fail("pointer models and alignment models are not read by the B200 build");
+            std::cerr << "File is not a colibri model file (or a very old one)" << std::endl;  // reference :788-793
+            throw InternalError();
+        }
+        colibri_b200_options             o = c_options(options, true);
+        colibri_b200_detail::ModelHandle cm, mh;
+        if (constrainmodel != nullptr) {
+            const colibri_b200_detail::FlatView v    = constrainmodel->flatview();
+            const uint64_t                      zero = 0;
+            if (colibri_b200_model_from_flat(v.keys, v.npatterns ? v.off : &zero, nullptr, v.npatterns, nullptr, nullptr, nullptr, 0, 0, UNINDEXEDPATTERNMODEL, o.device, &cm.h) != COLIBRI_OK)
+                fail(colibri_b200_last_error());
+        }
+        if (colibri_b200_model_load(all.data(), all.size(), &o, cm.h, &mh.h) != COLIBRI_OK) fail(colibri_b200_last_error());
+        adopt(mh.h);
+    }
+    virtual void load(std::string& filename, const PatternModelOptions& options, PatternModelInterface* constrainmodel = nullptr) {
+        if (!options.QUIET) std::cerr << "Loading " << filename << std::endl;
+        std::ifstream in(filename, std::ios::in | std::ios::binary);
+        if (!in.good()) {
+            std::cerr << "ERROR: Unable to load file " << filename << std::endl;
+            throw InternalError();
+        }
+        this->load(in, options, constrainmodel);
+    }
+
+    /// reference include/patternmodel.h:866-868
+    PatternModelInterface* getinterface() { return static_cast<PatternModelInterface*>(this); }
+    colibri_b200_detail::FlatView flatview() const override {
+        colibri_b200_detail::FlatView v;
+        v.keys      = keys_.data();
+        v.off       = off_.data();
+        v.counts    = counts_.data();
+        v.npatterns = counts_.size();
+        return v;
+    }
 
     int getmodeltype() const override { return kModelType; }
     int getmodelversion() const override { return 2; }
@@ -371,6 +524,22 @@ template <class ValueType = uint32_t>
 class PatternModel : public DevicePatternModel<ValueType, UNINDEXEDPATTERNMODEL> {
   public:
     PatternModel(IndexedCorpus* corpus = nullptr) : DevicePatternModel<ValueType, UNINDEXEDPATTERNMODEL>(corpus) {}
+    PatternModel(const std::string& filename, const PatternModelOptions& options, PatternModelInterface* constrainmodel = nullptr, IndexedCorpus* corpus = nullptr)
+        : DevicePatternModel<ValueType, UNINDEXEDPATTERNMODEL>(filename, options, constrainmodel, corpus) {}
+    PatternModel(std::istream& f, const PatternModelOptions& options, PatternModelInterface* constrainmodel = nullptr, IndexedCorpus* corpus = nullptr)
+        : DevicePatternModel<ValueType, UNINDEXEDPATTERNMODEL>(f, options, constrainmodel, corpus) {}
+};
+
+/// PatternSetModel: patterns without values, what the CLI loads as the constraint model of -j (reference include/patternmodel.h:296-470).
+/// Reading an (un)indexed model file as a set applies the same filters (readmap, :421-431); the counts are simply not looked at.
+class PatternSetModel : public DevicePatternModel<uint32_t, UNINDEXEDPATTERNMODEL> {
+  public:
+    PatternSetModel() {}
+    PatternSetModel(const std::string& filename, const PatternModelOptions& options, PatternModelInterface* constrainmodel = nullptr)
+        : DevicePatternModel<uint32_t, UNINDEXEDPATTERNMODEL>(filename, options, constrainmodel, nullptr) {}
+    PatternSetModel(std::istream& f, const PatternModelOptions& options, PatternModelInterface* constrainmodel = nullptr)
+        : DevicePatternModel<uint32_t, UNINDEXEDPATTERNMODEL>(f, options, constrainmodel, nullptr) {}
+    int getmodeltype() const override { return PATTERNSETMODEL; }
 };
 
 /// IndexedPatternModel<>: value = sorted list of positions (reference include/patternmodel.h:2681)
@@ -378,4 +547,8 @@ template <class MapType = void>
 class IndexedPatternModel : public DevicePatternModel<IndexedData, INDEXEDPATTERNMODEL> {
   public:
     IndexedPatternModel(IndexedCorpus* corpus = nullptr) : DevicePatternModel<IndexedData, INDEXEDPATTERNMODEL>(corpus) {}
+    IndexedPatternModel(const std::string& filename, const PatternModelOptions& options, PatternModelInterface* constrainmodel = nullptr, IndexedCorpus* corpus = nullptr)
+        : DevicePatternModel<IndexedData, INDEXEDPATTERNMODEL>(filename, options, constrainmodel, corpus) {}
+    IndexedPatternModel(std::istream& f, const PatternModelOptions& options, PatternModelInterface* constrainmodel = nullptr, IndexedCorpus* corpus = nullptr)
+        : DevicePatternModel<IndexedData, INDEXEDPATTERNMODEL>(f, options, constrainmodel, corpus) {}
 };

@@ -61,6 +61,12 @@ typedef struct colibri_b200_options {
                                        0: from a preloaded IndexedCorpus (src/pattern.cpp:1916-1967).  Only matters when the
                                        last sentence lacks its 0x00 (the stream reader then repeats the last byte). */
     int32_t device;                 /* CUDA device ordinal */
+    /* load-time switches (PatternModel::load, include/patternmodel.h:827-858 -> PatternMapStore::read, include/patternstore.h:555-619) */
+    int32_t DOREMOVEINDEX;          /* accepted for signature parity; choosing model_type = unindexed is what drops the index */
+    int32_t DOREMOVENGRAMS;
+    int32_t DOREMOVESKIPGRAMS;
+    int32_t DOREMOVEFLEXGRAMS;
+    int32_t DORESET;                /* values start empty (counts 0, no references) */
 } colibri_b200_options;
 
 typedef struct colibri_b200_corpus colibri_b200_corpus; /* a corpus body resident in HBM, tokenised lazily */
@@ -110,8 +116,29 @@ int colibri_b200_model_export(colibri_b200_model* m, uint8_t* keys, uint64_t* ke
 int colibri_b200_model_export_compact(colibri_b200_model* m, uint8_t* keys, uint16_t* key_len, uint32_t* counts);
 /* the .colibri.patternmodel byte stream (include/patternmodel.h:1609-1624): returns needed size in *nbytes when buf is NULL */
 int colibri_b200_model_write(colibri_b200_model* m, uint8_t* buf, size_t cap, size_t* nbytes);
-/* occurrencecount(pattern) (include/patternmodel.h:1653-1669): key = pattern bytes without terminator; *count = 0 if absent */
+/* occurrencecount(pattern) (include/patternmodel.h:1653-1669): key = pattern bytes without terminator; *count = 0 if absent.
+ * Runs on the device: SpookyV2 of the key bytes (Pattern::hash, src/pattern.cpp:234-238) into the model's HBM-resident index. */
 int colibri_b200_model_lookup(colibri_b200_model* m, const uint8_t* key, uint32_t len, uint32_t* count);
+/* has() / occurrencecount() for n patterns at once (include/patternmodel.h:751-756, :1653-1669): keys = concatenated pattern bytes,
+ * key_off[n+1]; counts[i] = 0 and index[i] = -1 when pattern i is absent, else its position in the export order.  Either output may be NULL. */
+int colibri_b200_model_lookup_batch(colibri_b200_model* m, const uint8_t* keys, const uint64_t* key_off, uint64_t n, uint32_t* counts, int64_t* index);
+
+/* ---- models that do not come out of train() */
+/* a pattern set given as flat host arrays (the export form) becomes a device-resident model: replaces building a PatternModel /
+ * PatternSetModel by insert() (include/patternstore.h:520, include/patternmodel.h:296-470).  counts and the three ref arrays may be NULL. */
+int colibri_b200_model_from_flat(const uint8_t* keys, const uint64_t* key_off, const uint32_t* counts, uint64_t npatterns, const uint32_t* ref_sentence,
+                                 const uint16_t* ref_token, const uint64_t* ref_off, uint64_t totaltokens, uint64_t totaltypes, int model_type, int device,
+                                 colibri_b200_model** out);
+/* PatternModel::load (include/patternmodel.h:781-861): the bytes of a .colibri.patternmodel file (type 10 or 20, version 2) read AS
+ * opt->model_type, with the options acting as filters exactly like PatternMapStore::read (include/patternstore.h:555-619): count >= MINTOKENS
+ * (-1 -> 0), MINLENGTH <= n <= MAXLENGTH, DOREMOVE{NGRAMS,SKIPGRAMS,FLEXGRAMS}, membership in `constrain` (may be NULL), DORESET.  The record
+ * stream is scanned on the host (its boundaries are sequential), the filters run on the device. */
+int colibri_b200_model_load(const uint8_t* file, size_t nbytes, const colibri_b200_options* opt, colibri_b200_model* constrain, colibri_b200_model** out);
+/* PatternModel::train with constrainbymodel != NULL (include/patternmodel.h:880-1345: one scan :1064-1072, membership :1088-1089, prune :1211-1218):
+ * only patterns of `constrain` are counted.  inplace = 0: constrain is another model (the CLI's -j; totals start from its totals, :892-895);
+ * inplace = 1: constrainbymodel == this, i.e. `constrain` is the model being rebuilt, loaded with DORESET (the CLI's -I and stage 2 of -2;
+ * :889-891, :970-971, :1199-1201).  `constrain` is not modified; the result is a new model. */
+int colibri_b200_train_constrained(colibri_b200_corpus* corpus, const colibri_b200_options* opt, colibri_b200_model* constrain, int inplace, colibri_b200_model** out);
 
 /* ---- measurement hooks (bench.py): device time by phase, from CUDA events on the library's stream */
 #define COLIBRI_T_TOTAL 0     /* whole train_corpus call on the device (tokenise .. survivors ready) */

@@ -61,6 +61,16 @@ def test_compute_fails_loudly_without_a_gpu():
         cb.hash64_batch([b"\x06"])
     with pytest.raises(cb.ColibriError):
         cb.Corpus.synthetic(1000, vocab=100)
+    # models that do not come out of train(): upload, load, constrained training -- no host-side stand-in either
+    import numpy as np
+
+    with pytest.raises(cb.ColibriError) as ei:
+        cb.Model.from_flat(np.array([6, 7], dtype=np.uint8), np.array([0, 1, 2], dtype=np.uint64), np.array([2, 2], dtype=np.uint32))
+    assert ei.value.code == 3
+    blob = bytes([0, 10, 2]) + (3).to_bytes(8, "little") + (2).to_bytes(8, "little") + (1).to_bytes(8, "little") + bytes([6, 0]) + (3).to_bytes(4, "little")
+    with pytest.raises(cb.ColibriError) as ei:
+        cb.load_model(blob)
+    assert ei.value.code == 3
 
 
 def test_invalid_arguments_are_reported():

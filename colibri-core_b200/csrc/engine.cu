@@ -784,7 +784,7 @@ int Trainer::run_constrained(colibri_b200_model* cm, bool inplace) {
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     timer.s = s;
     int h_total = timer.begin(COLIBRI_T_TOTAL);
-    TRY(ensure_index(cm, &launches));
+    TRY(ensure_closure(cm, &launches));
     DevBuf<uint32_t> tok;
     uint64_t         npos = 0;
     uint32_t         nclasses = 0;
@@ -806,13 +806,27 @@ int Trainer::run_constrained(colibri_b200_model* cm, bool inplace) {
     TRY(counts.alloc(dev, std::max<uint64_t>(np, 1)));
     TRY(flags.alloc(dev, np + 1));
     CUDA_TRY(cudaMemsetAsync(counts.p, 0, std::max<uint64_t>(np, 1) * sizeof(uint32_t), s));
-    std::vector<DevBuf<uint32_t>> match(lengths.size());
+    // match[k][p] = pattern (index + 1) of the window of lengths[k] tokens at p.  Indexed models keep every level (the occurrence lists are
+    // built from them); otherwise two buffers alternate: level n only looks at level n-1, to skip windows whose prefix / suffix did not match
+    const bool chain = !getenv("COLIBRI_B200_NO_CHAIN");
+    std::vector<DevBuf<uint32_t>> match(indexed ? lengths.size() : std::min<size_t>(lengths.size(), 2));
+    for (auto& mb : match) {
+        TRY(mb.alloc(dev, npos + 8));
+        CUDA_TRY(cudaMemsetAsync(mb.p + npos, 0, 8 * sizeof(uint32_t), s));
+    }
     TRY(zero_stats());
     for (size_t k = 0; k < lengths.size(); ++k) {
-        if (indexed) TRY(match[k].alloc(dev, npos));
-        int hc = timer.begin(COLIBRI_T_COUNT, lengths[k]);
-        launches += launch_constrained_match(s, tok.p, npos, lengths[k], cm->d_keys.p, cm->d_off.p, cm->d_index.p, cm->index_cap, counts.p, indexed ? match[k].p : nullptr,
-                                             d_stats.p, sms);
+        const int n   = lengths[k];
+        uint32_t* cur = match[indexed ? k : k % 2].p;
+        const uint32_t* prev = (k > 0 && lengths[k - 1] == n - 1 && chain) ? match[indexed ? k - 1 : (k - 1) % 2].p : nullptr;
+        const bool use_prefix = prev && cm->prefix_open[n] == 0, use_suffix = prev && cm->suffix_open[n] == 0;
+        if (!indexed && !(k + 1 < lengths.size() && lengths[k + 1] == n + 1 && chain)) cur = nullptr;  // nobody will read it
+        int hc = timer.begin(COLIBRI_T_COUNT, n);
+        if (n == 1 && cm->uni_classes)
+            launches += launch_constrained_unigrams(s, tok.p, npos, cm->d_uni.p, cm->uni_classes, counts.p, cur, d_stats.p, sms);
+        else
+            launches += launch_constrained_match(s, tok.p, npos, n, cm->d_keys.p, cm->d_off.p, cm->d_index.p, cm->index_cap, cm->d_presence.p, cm->presence_bits, counts.p, cur,
+                                                 prev, use_prefix, use_suffix, d_stats.p, sms);
         timer.end(hc);
     }
     TRY(read_stats());

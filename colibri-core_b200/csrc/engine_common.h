@@ -242,6 +242,13 @@ struct colibri_b200_model {
     colibri::PatternMetaStats  meta;
     DevBuf<unsigned long long> d_index;
     uint64_t                   index_cap = 0;
+    DevBuf<uint32_t>           d_presence;  // one bit per hash bucket (16 per pattern): negative lookups end in L2
+    uint64_t                   presence_bits = 0;
+    // constrained training only: class -> unigram pattern, and per length how many patterns lack their (n-1)-token prefix / suffix
+    DevBuf<uint32_t>           d_uni;
+    uint32_t                   uni_classes = 0;
+    bool                       closure_ready = false;
+    unsigned long long         prefix_open[256] = {0}, suffix_open[256] = {0};
     bool                       index_ready = false;
     double   ms[COLIBRI_T_NPHASES] = {0};
     uint64_t counters[8] = {0};
@@ -257,6 +264,8 @@ int new_model(int device, int model_type, colibri_b200_model** out);
 // model_io.cu: per-pattern shape (d_pn, d_pcat, meta) / the hash index over the pattern bytes, built once per model
 int ensure_meta(colibri_b200_model* m, uint64_t* launches);
 int ensure_index(colibri_b200_model* m, uint64_t* launches);
+// model_io.cu: what constrained training wants to know about its constraint set (unigram table, closure per length), built once per model
+int ensure_closure(colibri_b200_model* m, uint64_t* launches);
 // model_io.cu: the patterns of `src` whose flag is set become the flat arrays of `dst` (work enqueued on dst->stream, synchronised on return).
 //   d_counts: their counts (NULL: zeros); order_by_length: stable order by token count, so that occurrence lists built per length concatenate;
 //   copy_refs: carry src's occurrence lists over; d_kmap (optional, src->npatterns entries): old index -> new index + 1, 0 = dropped.

@@ -406,6 +406,201 @@ __global__ void __launch_bounds__(256, 8) count_ngrams_kernel(const uint32_t* __
     if (full) atomicOr(&st->errflags, kErrTableFull);
 }
 
+// ---- memory-level parallelism (experiment, off by default: COLIBRI_B200_MLP=2|4).  Both kernels above are chains of dependent
+// long-latency operations per window (id load -> filter word -> table sector -> claim); at 98 % occupancy the stall reason is the
+// scoreboard, with HBM at ~37 % and L2 at ~34 % of their byte throughput (profiles/r01_count_ngrams_ncu.md).  The variants below give every
+// thread U windows per iteration and issue each stage for all U before consuming any result, so that U chains are in flight per thread.
+// Same operations, same table contents and statistics (the parity suite passes with U = 4).  MEASURED (B200, 100 M tokens): the count
+// family takes 7.8 ms with U = 1, 11.9 ms with U = 2, 13.9 ms with U = 4 -- more requests in flight make it slower, i.e. the random-sector
+// path is already saturated (queueing, not latency, is what the warps wait on).  Kept as the evidence for that conclusion.
+template <int U>
+__global__ void __launch_bounds__(256) ngram_filter_mlp_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t* __restrict__ filter, uint64_t nbuckets_mask,
+                                                               DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t       valid = 0, twice = 0;
+    for (uint64_t p0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p0 < npos; p0 += stride * U) {
+        uint32_t a[U], b[U], shift[U], bits[U];
+        uint64_t word[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const uint64_t p = p0 + (uint64_t)k * stride;
+            a[k] = p < npos ? __ldcs(prev + p) : 0u;
+            b[k] = p < npos ? __ldg(prev + p + 1) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            bits[k] = 3u;  // 3 = nothing left to do for this window
+            word[k] = 0;
+            shift[k] = 0;
+            if (a[k] != 0 && b[k] != 0) {
+                ++valid;
+                filter_locate(spooky_hash64_u64(((unsigned long long)a[k] << 32) | b[k], 0), nbuckets_mask, word[k], shift[k]);
+                bits[k] = 0x80u;  // marker: load pending
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+            if (bits[k] == 0x80u) bits[k] = (__ldcg(filter + word[k]) >> shift[k]) & 3u;
+        uint32_t old1[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {  // first hit of a bucket
+            old1[k] = 0xFFFFFFFFu;
+            if ((bits[k] & 1u) == 0) old1[k] = atomicOr(filter + word[k], 1u << shift[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+            if ((bits[k] & 1u) == 0) bits[k] = ((old1[k] >> shift[k]) & 1u) == 0 ? 3u /* this window was the first: done */ : ((old1[k] >> shift[k]) & 3u);
+        uint32_t old2[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {  // second hit
+            old2[k] = 0xFFFFFFFFu;
+            if ((bits[k] & 2u) == 0) old2[k] = atomicOr(filter + word[k], 2u << shift[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+            if ((bits[k] & 2u) == 0) twice += ((old2[k] >> shift[k]) & 2u) == 0;  // this thread moved the bucket to "seen twice"
+    }
+    uint64_t v  = block_reduce_sum(valid, scratch);
+    uint64_t tw = block_reduce_sum(twice, scratch);
+    if (threadIdx.x == 0) {
+        if (v) atomicAdd(&st->valid_windows, (unsigned long long)v);
+        if (tw) atomicAdd(&st->found, (unsigned long long)tw);
+    }
+}
+
+// upsert whose first probe was already loaded (`first` = key field of `slot`)
+__device__ __forceinline__ uint32_t upsert_ngram_from(NgramSlot* __restrict__ table, uint64_t cap, uint64_t slot, unsigned long long key, uint32_t pos, unsigned long long first,
+                                                      uint32_t& probes, bool& full) {
+    const uint64_t     limit = cap < kMaxProbe ? cap : kMaxProbe;
+    unsigned long long cur   = first;
+    for (uint64_t step = 0; step < limit; ++step) {
+        NgramSlot* s = table + slot;
+        if (step) cur = __ldcg(&s->key);
+        ++probes;
+        if (cur == 0) {
+            unsigned long long o0, o1;
+            cas128(s, key, 1ull | ((unsigned long long)pos << 32), o0, o1);
+            if (o0 == 0) return (uint32_t)slot + 1;
+            cur = o0;
+        }
+        if (cur == key) {
+            atomicAdd(&s->count, 1u);
+            return (uint32_t)slot + 1;
+        }
+        slot = slot + 1 == cap ? 0 : slot + 1;
+    }
+    full = true;
+    return 0;
+}
+
+template <bool kFilter, int U>
+__global__ void __launch_bounds__(256, 4) count_ngrams_mlp_kernel(const uint32_t* __restrict__ prev, uint32_t* __restrict__ cur, uint64_t npos, NgramSlot* __restrict__ table,
+                                                                  uint64_t cap, const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, DeviceStats* __restrict__ st,
+                                                                  const bool hot) {
+    __shared__ uint64_t scratch[8];
+    __shared__ unsigned long long hot_key[kHotLines];
+    __shared__ uint32_t hot_slot[kHotLines];
+    __shared__ uint32_t hot_pending[kHotLines];
+    if (hot) {
+        for (uint32_t i = threadIdx.x; i < kHotLines; i += blockDim.x) {
+            hot_key[i]     = 0;
+            hot_pending[i] = 0;
+        }
+        __syncthreads();
+    }
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t       valid = 0, probes = 0, singles = 0;
+    bool           full = false;
+    for (uint64_t p0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p0 < npos; p0 += stride * U) {
+        uint32_t           a[U], b[U], id[U], line[U];
+        uint64_t           slot[U];
+        unsigned long long first[U];
+        uint32_t           fw[U], fshift[U];
+        int                state[U];  // 0: no window / filtered / served by the hot cache, 1: goes to the table
+        // stage 1: the ids of the two (n-1)-grams
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const uint64_t p = p0 + (uint64_t)k * stride;
+            a[k] = p < npos ? __ldcs(prev + p) : 0u;
+            b[k] = p < npos ? __ldg(prev + p + 1) : 0u;
+        }
+        // stage 2: hash, filter word
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            id[k]    = 0;
+            state[k] = 0;
+            fw[k]    = 0xFFFFFFFFu;
+            fshift[k] = 0;
+            slot[k]  = 0;
+            line[k]  = 0;
+            if (a[k] != 0 && b[k] != 0) {
+                ++valid;
+                const uint64_t h = spooky_hash64_u64(((unsigned long long)a[k] << 32) | b[k], 0);
+                slot[k]  = fast_range(h, cap);
+                line[k]  = (uint32_t)(h >> 20) & (kHotLines - 1);
+                state[k] = 1;
+                if (kFilter) {
+                    uint64_t word;
+                    filter_locate(h, nbuckets_mask, word, fshift[k]);
+                    fw[k] = __ldg(filter + word);
+                }
+            }
+        }
+        // stage 3: filter verdict, hot cache, first probe of the table
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            first[k] = 0;
+            if (state[k] == 1) {
+                if (kFilter && ((fw[k] >> fshift[k]) & 2u) == 0) {
+                    ++singles;
+                    state[k] = 0;
+                    continue;
+                }
+                const unsigned long long key = ((unsigned long long)a[k] << 32) | b[k];
+                if (hot && *(volatile unsigned long long*)&hot_key[line[k]] == key) {
+                    atomicAdd(&hot_pending[line[k]], 1u);
+                    id[k]    = *(volatile uint32_t*)&hot_slot[line[k]];
+                    state[k] = 0;
+                    continue;
+                }
+                first[k] = __ldcg(&table[slot[k]].key);
+            }
+        }
+        // stage 4: resolve
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const uint64_t p = p0 + (uint64_t)k * stride;
+            if (state[k] == 1) {
+                const unsigned long long key = ((unsigned long long)a[k] << 32) | b[k];
+                id[k] = upsert_ngram_from(table, cap, slot[k], key, (uint32_t)p, first[k], probes, full);
+                if (hot && id[k] != 0 && *(volatile unsigned long long*)&hot_key[line[k]] == 0ull && atomicCAS(&hot_key[line[k]], 0ull, kHotBusy) == 0ull) {
+                    hot_slot[line[k]] = id[k];
+                    __threadfence_block();
+                    *(volatile unsigned long long*)&hot_key[line[k]] = key;
+                }
+            }
+            if (p < npos) __stcs(cur + p, id[k]);
+        }
+    }
+    if (hot) {
+        __syncthreads();
+        for (uint32_t l = threadIdx.x; l < kHotLines; l += blockDim.x) {
+            uint32_t c = hot_pending[l];
+            if (c) atomicAdd(&table[hot_slot[l] - 1].count, c);
+        }
+    }
+    uint64_t v  = block_reduce_sum(valid, scratch);
+    uint64_t pr = block_reduce_sum(probes, scratch);
+    uint64_t sg = block_reduce_sum(singles, scratch);
+    if (threadIdx.x == 0) {
+        if (v) atomicAdd(&st->valid_windows, (unsigned long long)v);
+        if (pr) atomicAdd(&st->probes, (unsigned long long)pr);
+        if (sg) atomicAdd(&st->singletons, (unsigned long long)sg);
+    }
+    if (full) atomicOr(&st->errflags, kErrTableFull);
+}
+
 // K3: prune(MINTOKENS, n) as a table scan: statistics, compaction of the survivors, and a 1-bit-per-slot survivor
 // bitmap (cap/8 bytes: L2 resident) that the relabel step tests instead of going back to the table in HBM.
 // A block handles tiles of 2048 slots: each warp reads 8 x 32 consecutive slots (coalesced 512-byte loads), the block
@@ -531,23 +726,87 @@ static int blocks_per_sm(const void* fn, int threads, size_t smem) {
     return n > 0 ? n : 1;
 }
 
+// experiment knob: cap the resident blocks per SM of a kernel by padding its dynamic shared memory (COLIBRI_B200_COUNT_BPS / _FILTER_BPS)
+static size_t throttle_smem(const void* fn, const char* env, size_t static_smem, int* bps_out) {
+    const char* e = getenv(env);
+    int         want = e ? atoi(e) : 0;
+    if (want <= 0 || want >= 8) return 0;
+    size_t per = (size_t)227 * 1024 / (size_t)want;
+    per        = per > static_smem + 1024 ? per - static_smem - 1024 : 0;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per);
+    if (bps_out) *bps_out = want;
+    return per;
+}
+
+// windows per thread per iteration of the filter / count kernels (COLIBRI_B200_MLP = 1, 2 or 4; 1 = the one-window kernels)
+static int mlp_env(const char* name) {
+    const char* e = getenv(name);
+    if (!e) e = getenv("COLIBRI_B200_MLP");
+    int v = e ? atoi(e) : 1;
+    return v == 1 || v == 2 || v == 4 ? v : 1;
+}
+static int mlp_width_filter() {
+    static int u = mlp_env("COLIBRI_B200_MLP_FILTER");
+    return u;
+}
+static int mlp_width() {
+    static int u = mlp_env("COLIBRI_B200_MLP_COUNT");
+    return u;
+}
 int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms) {
-    static int bps = blocks_per_sm((const void*)ngram_filter_kernel, 256, 0);
-    unsigned   grid = (unsigned)umin64(div_up(npos, 256), (uint64_t)sms * bps * 4);
-    ngram_filter_kernel<<<grid ? grid : 1, 256, 0, s>>>(prev, npos, filter, nbuckets - 1, st);
+    const int u = mlp_width_filter();
+    if (u == 4) {
+        static unsigned per_sm = 0;
+        if (!per_sm) per_sm = blocks_per_sm((const void*)ngram_filter_mlp_kernel<4>, 256, 0);
+        unsigned grid = (unsigned)umin64(div_up(div_up(npos, 4), 256), (uint64_t)sms * per_sm * 4);
+        ngram_filter_mlp_kernel<4><<<grid ? grid : 1, 256, 0, s>>>(prev, npos, filter, nbuckets - 1, st);
+        return 1;
+    }
+    if (u == 2) {
+        static unsigned per_sm = 0;
+        if (!per_sm) per_sm = blocks_per_sm((const void*)ngram_filter_mlp_kernel<2>, 256, 0);
+        unsigned grid = (unsigned)umin64(div_up(div_up(npos, 2), 256), (uint64_t)sms * per_sm * 4);
+        ngram_filter_mlp_kernel<2><<<grid ? grid : 1, 256, 0, s>>>(prev, npos, filter, nbuckets - 1, st);
+        return 1;
+    }
+    static int    bps = blocks_per_sm((const void*)ngram_filter_kernel, 256, 0);
+    static size_t pad = throttle_smem((const void*)ngram_filter_kernel, "COLIBRI_B200_FILTER_BPS", 64, &bps);
+    unsigned      grid = (unsigned)umin64(div_up(npos, 256), (uint64_t)sms * bps * 4);
+    ngram_filter_kernel<<<grid ? grid : 1, 256, pad, s>>>(prev, npos, filter, nbuckets - 1, st);
     return 1;
+}
+template <bool kFilter, int U>
+static void launch_count_mlp(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms, const uint32_t* filter,
+                             uint64_t nbuckets, bool hot) {
+    static unsigned per_sm = 0;
+    if (!per_sm) per_sm = blocks_per_sm((const void*)count_ngrams_mlp_kernel<kFilter, U>, 256, 0);
+    unsigned grid = (unsigned)umin64(div_up(div_up(npos, U), 256), (uint64_t)sms * per_sm * 4);
+    count_ngrams_mlp_kernel<kFilter, U><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, filter, kFilter ? nbuckets - 1 : 0, st, hot);
 }
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms, const uint32_t* filter,
                         uint64_t nbuckets, bool hot) {
-    static int bps0 = blocks_per_sm((const void*)count_ngrams_kernel<false>, 256, 0);
-    static int bps1 = blocks_per_sm((const void*)count_ngrams_kernel<true>, 256, 0);
-    uint64_t   want = div_up(npos, 256);
+    const int u = mlp_width();
+    if (u == 4) {
+        if (filter != nullptr) launch_count_mlp<true, 4>(s, prev, cur, npos, table, cap, st, sms, filter, nbuckets, hot);
+        else launch_count_mlp<false, 4>(s, prev, cur, npos, table, cap, st, sms, nullptr, 0, hot);
+        return 1;
+    }
+    if (u == 2) {
+        if (filter != nullptr) launch_count_mlp<true, 2>(s, prev, cur, npos, table, cap, st, sms, filter, nbuckets, hot);
+        else launch_count_mlp<false, 2>(s, prev, cur, npos, table, cap, st, sms, nullptr, 0, hot);
+        return 1;
+    }
+    static int    bps0 = blocks_per_sm((const void*)count_ngrams_kernel<false>, 256, 0);
+    static int    bps1 = blocks_per_sm((const void*)count_ngrams_kernel<true>, 256, 0);
+    static size_t pad0 = throttle_smem((const void*)count_ngrams_kernel<false>, "COLIBRI_B200_COUNT_BPS", 16448, &bps0);
+    static size_t pad1 = throttle_smem((const void*)count_ngrams_kernel<true>, "COLIBRI_B200_COUNT_BPS", 16448, &bps1);
+    uint64_t      want = div_up(npos, 256);
     if (filter != nullptr) {
         unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bps1 * 4);
-        count_ngrams_kernel<true><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, filter, nbuckets - 1, st, hot);
+        count_ngrams_kernel<true><<<grid ? grid : 1, 256, pad1, s>>>(prev, cur, npos, table, cap, filter, nbuckets - 1, st, hot);
     } else {
         unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bps0 * 4);
-        count_ngrams_kernel<false><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, nullptr, 0, st, hot);
+        count_ngrams_kernel<false><<<grid ? grid : 1, 256, pad0, s>>>(prev, cur, npos, table, cap, nullptr, 0, st, hot);
     }
     return 1;
 }

@@ -148,14 +148,23 @@ struct PatternMetaStats {  // zeroed by the host except minn / kept_minn = 0xFFF
     unsigned long long kept_occ_n[256];  // their occurrences
 };
 int launch_pattern_meta(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, uint16_t* pn, uint8_t* pcat, PatternMetaStats* st);
-// slots: cap_pow2 zeroed 8-byte entries {hash tag << 32 | pattern index + 1}
-int launch_index_build(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, unsigned long long* slots, uint64_t cap_pow2, PatternMetaStats* st);
+// slots: cap_pow2 zeroed 8-byte entries {hash tag << 32 | pattern index + 1}; presence: presence_bits_pow2 zeroed bits, one per hash bucket
+int launch_index_build(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, unsigned long long* slots, uint64_t cap_pow2, uint32_t* presence,
+                       uint64_t presence_bits_pow2, PatternMetaStats* st);
 int launch_index_lookup(cudaStream_t s, const uint8_t* qkeys, const uint64_t* qoff, uint64_t nq, const uint8_t* keys, const uint64_t* off, const unsigned long long* slots,
-                        uint64_t cap_pow2, uint32_t* out_idx1 /* pattern index + 1, or 0 */);
+                        uint64_t cap_pow2, const uint32_t* presence, uint64_t presence_bits_pow2, uint32_t* out_idx1 /* pattern index + 1, or 0 */);
 int launch_gather_counts(cudaStream_t s, const uint32_t* idx1, uint64_t nq, const uint32_t* counts, uint32_t* out);
-// windows of n tokens that are in the set: counts[pattern] += 1, match[p] = pattern index + 1 or 0 (match may be NULL)
+// windows of n tokens that are in the set: counts[pattern] += 1, match[p] = pattern index + 1 or 0 (match may be NULL).
+// prev (may be NULL) = match[] of length n-1 (npos + 1 readable entries); use_prefix / use_suffix: skip windows whose prefix / suffix did not match
 int launch_constrained_match(cudaStream_t s, const uint32_t* tok, uint64_t npos, int n, const uint8_t* keys, const uint64_t* off, const unsigned long long* slots, uint64_t cap_pow2,
-                             uint32_t* counts, uint32_t* match, DeviceStats* st, int sms);
+                             const uint32_t* presence, uint64_t presence_bits_pow2, uint32_t* counts, uint32_t* match, const uint32_t* prev, bool use_prefix, bool use_suffix,
+                             DeviceStats* st, int sms);
+// uni[class] = index + 1 of the unigram pattern of that class (uni zeroed by the caller, nclasses entries)
+int launch_unigram_table(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint16_t* pn, uint64_t np, uint32_t* uni, uint32_t nclasses);
+int launch_constrained_unigrams(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* uni, uint32_t nclasses, uint32_t* counts, uint32_t* match, DeviceStats* st, int sms);
+// per pattern length n (bins of 256, zeroed by the caller): patterns whose (n-1)-token prefix / suffix is not in the set
+int launch_closure_check(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint16_t* pn, uint64_t np, const unsigned long long* slots, uint64_t cap_pow2,
+                         const uint32_t* presence, uint64_t presence_bits_pow2, unsigned long long* prefix_open, unsigned long long* suffix_open);
 int launch_constrained_stats(cudaStream_t s, const uint32_t* counts, const uint16_t* pn, uint64_t np, uint32_t threshold, uint32_t* flags, PatternMetaStats* st, DeviceStats* ds);
 int launch_load_filter(cudaStream_t s, const uint16_t* pn, const uint8_t* pcat, const uint32_t* counts, const uint32_t* constrain_idx1, uint64_t np, uint32_t mintokens,
                        uint32_t minlength, uint32_t maxlength, int dongrams, int doskipgrams, int doflexgrams, uint32_t* flags, PatternMetaStats* st);

@@ -61,14 +61,18 @@ int colibri::ensure_index(colibri_b200_model* m, uint64_t* launches) {
     cudaStream_t s = m->stream;
     uint64_t cap = 1024;
     while (cap < 2 * m->npatterns) cap <<= 1;
+    uint64_t pbits = 1ull << 15;
+    while (pbits < 16 * m->npatterns) pbits <<= 1;
     TRY(m->d_index.alloc(m->device, cap));
+    TRY(m->d_presence.alloc(m->device, pbits / 32));
     CUDA_TRY(cudaMemsetAsync(m->d_index.p, 0, cap * sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemsetAsync(m->d_presence.p, 0, pbits / 8, s));
     uint64_t l = 0;
     if (m->npatterns) {
         DevBuf<PatternMetaStats> st;
         TRY(st.alloc(m->device, 1));
         CUDA_TRY(cudaMemsetAsync(st.p, 0, sizeof(PatternMetaStats), s));
-        l += launch_index_build(s, m->d_keys.p, m->d_off.p, m->npatterns, m->d_index.p, cap, st.p);
+        l += launch_index_build(s, m->d_keys.p, m->d_off.p, m->npatterns, m->d_index.p, cap, m->d_presence.p, pbits, st.p);
         PatternMetaStats h;
         CUDA_TRY(cudaMemcpyAsync(&h, st.p, sizeof h, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
@@ -78,8 +82,37 @@ int colibri::ensure_index(colibri_b200_model* m, uint64_t* launches) {
         CUDA_TRY(cudaStreamSynchronize(s));
     }
     if (launches) *launches += l;
-    m->index_cap   = cap;
-    m->index_ready = true;
+    m->index_cap     = cap;
+    m->presence_bits = pbits;
+    m->index_ready   = true;
+    return 0;
+}
+
+int colibri::ensure_closure(colibri_b200_model* m, uint64_t* launches) {
+    if (m->closure_ready) return 0;
+    TRY(ensure_index(m, launches));
+    cudaStream_t s = m->stream;
+    uint64_t     l = 0;
+    memset(m->prefix_open, 0, sizeof m->prefix_open);
+    memset(m->suffix_open, 0, sizeof m->suffix_open);
+    m->uni_classes = 0;
+    if (m->npatterns) {
+        DevBuf<unsigned long long> open;
+        TRY(open.alloc(m->device, 512));
+        CUDA_TRY(cudaMemsetAsync(open.p, 0, 512 * sizeof(unsigned long long), s));
+        l += launch_closure_check(s, m->d_keys.p, m->d_off.p, m->d_pn.p, m->npatterns, m->d_index.p, m->index_cap, m->d_presence.p, m->presence_bits, open.p, open.p + 256);
+        CUDA_TRY(cudaMemcpyAsync(m->prefix_open, open.p, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(m->suffix_open, open.p + 256, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        if (m->meta.nhist[1] && m->meta.maxclass < (1u << 28)) {
+            m->uni_classes = m->meta.maxclass + 1;
+            TRY(m->d_uni.alloc(m->device, m->uni_classes));
+            CUDA_TRY(cudaMemsetAsync(m->d_uni.p, 0, (size_t)m->uni_classes * sizeof(uint32_t), s));
+            l += launch_unigram_table(s, m->d_keys.p, m->d_off.p, m->d_pn.p, m->npatterns, m->d_uni.p, m->uni_classes);
+        }
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    if (launches) *launches += l;
+    m->closure_ready = true;
     return 0;
 }
 
@@ -362,7 +395,8 @@ extern "C" int colibri_b200_model_load(const uint8_t* file, size_t nbytes, const
             if (constrain && np) {  // constrainstore->has(p), include/patternstore.h:586
                 TRY(ensure_index(constrain, &launches));
                 TRY(cidx.alloc(dev, np));
-                launches += launch_index_lookup(s, all->d_keys.p, all->d_off.p, np, constrain->d_keys.p, constrain->d_off.p, constrain->d_index.p, constrain->index_cap, cidx.p);
+                launches += launch_index_lookup(s, all->d_keys.p, all->d_off.p, np, constrain->d_keys.p, constrain->d_off.p, constrain->d_index.p, constrain->index_cap, constrain->d_presence.p,
+                                                constrain->presence_bits, cidx.p);
             }
             const int64_t mintokens = opt->MINTOKENS == -1 ? 0 : opt->MINTOKENS;  // include/patternstore.h:565-566
             launches += launch_load_filter(s, all->d_pn.p, all->d_pcat.p, all->d_counts.p, (constrain && np) ? cidx.p : nullptr, np, (uint32_t)std::max<int64_t>(mintokens, 0),
@@ -417,7 +451,7 @@ extern "C" int colibri_b200_model_lookup_batch(colibri_b200_model* m, const uint
     TRY(dcnt.alloc(m->device, n));
     if (kb) CUDA_TRY(cudaMemcpyAsync(dk.p, keys, kb, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(doff.p, key_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    launches += launch_index_lookup(s, dk.p, doff.p, n, m->d_keys.p, m->d_off.p, m->d_index.p, m->index_cap, didx.p);
+    launches += launch_index_lookup(s, dk.p, doff.p, n, m->d_keys.p, m->d_off.p, m->d_index.p, m->index_cap, m->d_presence.p, m->presence_bits, didx.p);
     if (counts) {
         launches += launch_gather_counts(s, didx.p, n, m->d_counts.p, dcnt.p);
         CUDA_TRY(cudaMemcpyAsync(counts, dcnt.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

@@ -78,10 +78,19 @@ __device__ __forceinline__ void words_load(uint64_t (&w)[NW], const uint8_t* __r
     for (uint32_t i = 0; i < len; ++i) words_put(w, i, p[i]);
 }
 // probe the index for the key held in w[0..len): pattern index + 1, or 0
+// The presence bitmap: one bit per hash bucket, 16 buckets per pattern, small enough to stay in L2 (11 M patterns: 32 MB).  Most
+// windows of a corpus are NOT in the set; they are turned away here by an L2 hit instead of a random HBM sector.
+__device__ __forceinline__ uint64_t presence_bit(uint64_t h, uint64_t pmask) {
+    return (h >> 13) & pmask;  // bits 13.. : the slot uses the low bits, the tag the high 32
+}
 template <int NW>
 __device__ __forceinline__ uint32_t index_find(const uint64_t (&w)[NW], uint32_t len, const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off,
-                                               const unsigned long long* __restrict__ slots, uint64_t mask) {
-    const uint64_t h   = spooky_words(w, len);
+                                               const unsigned long long* __restrict__ slots, uint64_t mask, const uint32_t* __restrict__ presence, uint64_t pmask) {
+    const uint64_t h = spooky_words(w, len);
+    if (presence != nullptr) {
+        const uint64_t b = presence_bit(h, pmask);
+        if (((__ldg(presence + (b >> 5)) >> (b & 31)) & 1u) == 0) return 0;
+    }
     const uint32_t tag = (uint32_t)(h >> 32);
     uint64_t       s   = h & mask;
     for (uint64_t step = 0; step <= mask; ++step, s = (s + 1) & mask) {
@@ -107,44 +116,63 @@ __device__ __forceinline__ uint32_t index_find(const uint64_t (&w)[NW], uint32_t
 // the first skip (3) / flex (4) token decides); model-wide maxima for postread (include/patternmodel.h:572-588)
 __global__ void __launch_bounds__(256) pattern_meta_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, uint64_t np, uint16_t* __restrict__ pn,
                                                            uint8_t* __restrict__ pcat, PatternMetaStats* __restrict__ st) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= np) return;
-    const uint64_t a = off[i], b = off[i + 1];
-    uint32_t       n = 0, cat = 0;
-    uint64_t       cls = 0, maxcls = 0;
-    uint32_t       shift = 0;
-    bool           start = true, wide = false;
-    for (uint64_t k = a; k < b; ++k) {
-        const uint8_t c = keys[k];
-        if (shift < 35) cls |= (uint64_t)(c & 0x7F) << shift; else wide = true;
-        shift += 7;
-        if (c < 128) {
-            if (start && cat == 0 && c == 3) cat = 1;
-            if (start && cat == 0 && c == 4) cat = 2;
-            ++n;
-            if (cls > maxcls) maxcls = cls;
-            cls   = 0;
-            shift = 0;
-            start = true;
-        } else {
-            start = false;
-        }
+    __shared__ unsigned long long s_nhist[256];
+    __shared__ uint32_t           s_maxn, s_minn, s_skip, s_flex, s_maxclass, s_malformed, s_uni;
+    s_nhist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        s_maxn = s_skip = s_flex = s_maxclass = s_malformed = s_uni = 0;
+        s_minn = 0xFFFFFFFFu;
     }
-    if (maxcls > 0xFFFFFFFFull) wide = true;
-    pn[i]   = (uint16_t)min(n, 65535u);
-    pcat[i] = (uint8_t)cat;
-    atomicMax(&st->maxn, n);
-    atomicMin(&st->minn, n);
-    if (cat == 1) st->hasskip = 1;
-    if (cat == 2) st->hasflex = 1;
-    atomicMax(&st->maxclass, (unsigned)min(maxcls, (uint64_t)0xFFFFFFFFull));
-    if (b - a > kMaxIndexedKeyBytes || b == a || wide || (b > a && keys[b - 1] >= 128)) atomicAdd(&st->malformed, 1u);
-    atomicAdd(&st->nhist[min(n, 255u)], 1ull);
-    if (n == 1 && cat == 0) atomicAdd(&st->unigram_ngrams, 1u);
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t a = off[i], b = off[i + 1];
+        uint32_t       n = 0, cat = 0;
+        uint64_t       cls = 0, maxcls = 0;
+        uint32_t       shift = 0;
+        bool           start = true, wide = false;
+        for (uint64_t k = a; k < b; ++k) {
+            const uint8_t c = keys[k];
+            if (shift < 35) cls |= (uint64_t)(c & 0x7F) << shift; else wide = true;
+            shift += 7;
+            if (c < 128) {
+                if (start && cat == 0 && c == 3) cat = 1;
+                if (start && cat == 0 && c == 4) cat = 2;
+                ++n;
+                if (cls > maxcls) maxcls = cls;
+                cls   = 0;
+                shift = 0;
+                start = true;
+            } else {
+                start = false;
+            }
+        }
+        if (maxcls > 0xFFFFFFFFull) wide = true;
+        pn[i]   = (uint16_t)min(n, 65535u);
+        pcat[i] = (uint8_t)cat;
+        atomicMax(&s_maxn, n);
+        atomicMin(&s_minn, n);
+        if (cat == 1) s_skip = 1;
+        if (cat == 2) s_flex = 1;
+        atomicMax(&s_maxclass, (unsigned)min(maxcls, (uint64_t)0xFFFFFFFFull));
+        if (b - a > kMaxIndexedKeyBytes || b == a || wide || (b > a && keys[b - 1] >= 128)) atomicAdd(&s_malformed, 1u);
+        atomicAdd(&s_nhist[min(n, 255u)], 1ull);
+        if (n == 1 && cat == 0) atomicAdd(&s_uni, 1u);
+    }
+    __syncthreads();
+    if (s_nhist[threadIdx.x]) atomicAdd(&st->nhist[threadIdx.x], s_nhist[threadIdx.x]);
+    if (threadIdx.x == 0 && s_minn != 0xFFFFFFFFu) {
+        atomicMax(&st->maxn, s_maxn);
+        atomicMin(&st->minn, s_minn);
+        if (s_skip) st->hasskip = 1;
+        if (s_flex) st->hasflex = 1;
+        atomicMax(&st->maxclass, s_maxclass);
+        if (s_malformed) atomicAdd(&st->malformed, s_malformed);
+        if (s_uni) atomicAdd(&st->unigram_ngrams, s_uni);
+    }
 }
 
 __global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, uint64_t np, unsigned long long* __restrict__ slots,
-                                                          uint64_t mask, PatternMetaStats* __restrict__ st) {
+                                                          uint64_t mask, uint32_t* __restrict__ presence, uint64_t pmask, PatternMetaStats* __restrict__ st) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
     const uint64_t a   = off[i];
@@ -153,6 +181,10 @@ __global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restr
     words_load(w, keys + a, len);
     const uint64_t           h   = spooky_words(w, len);
     const unsigned long long val = ((unsigned long long)(h >> 32) << 32) | (unsigned long long)(i + 1);
+    {
+        const uint64_t b = presence_bit(h, pmask);
+        atomicOr(presence + (b >> 5), 1u << (b & 31));
+    }
     uint64_t                 s   = h & mask;
     for (uint64_t step = 0; step <= mask; ++step, s = (s + 1) & mask) {
         unsigned long long prev = atomicCAS(&slots[s], 0ull, val);
@@ -180,7 +212,7 @@ __global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restr
 // batch lookup: out_idx1[q] = pattern index + 1, or 0
 __global__ void __launch_bounds__(256) index_lookup_kernel(const uint8_t* __restrict__ qkeys, const uint64_t* __restrict__ qoff, uint64_t nq, const uint8_t* __restrict__ keys,
                                                            const uint64_t* __restrict__ off, const unsigned long long* __restrict__ slots, uint64_t mask,
-                                                           uint32_t* __restrict__ out_idx1) {
+                                                           const uint32_t* __restrict__ presence, uint64_t pmask, uint32_t* __restrict__ out_idx1) {
     uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const uint64_t a = qoff[q], len64 = qoff[q + 1] - a;
@@ -190,7 +222,7 @@ __global__ void __launch_bounds__(256) index_lookup_kernel(const uint8_t* __rest
     }
     uint64_t w[24];
     words_load(w, qkeys + a, (uint32_t)len64);
-    out_idx1[q] = index_find(w, (uint32_t)len64, keys, off, slots, mask);
+    out_idx1[q] = index_find(w, (uint32_t)len64, keys, off, slots, mask, presence, pmask);
 }
 __global__ void __launch_bounds__(256) gather_counts_kernel(const uint32_t* __restrict__ idx1, uint64_t nq, const uint32_t* __restrict__ counts, uint32_t* __restrict__ out) {
     uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,65 +232,291 @@ __global__ void __launch_bounds__(256) gather_counts_kernel(const uint32_t* __re
 // ---------------------------------------------------------------------------------------------
 // constrained training, one window length per launch: window (p, n) is counted iff the constraint set has its bytes
 // (include/patternmodel.h:1064-1072 subngrams, :1088-1089 has(), :1155-1161 add)
+// ---------------------------------------------------------------------------------------------
+// keys of at most 31 bytes (every window of up to 6 tokens) held in four registers: no dynamically indexed array, hence no local memory
+__device__ __forceinline__ void key_append4(uint64_t (&w)[4], uint32_t& len, uint32_t c) {
+    uint64_t v;  // the varint bytes of class c as one little-endian value (src/classencoder.cpp:22-42)
+    uint32_t nb;
+    if (c < (1u << 7)) {
+        v  = c;
+        nb = 1;
+    } else if (c < (1u << 14)) {
+        v  = (uint64_t)((c & 0x7F) | 0x80) | ((uint64_t)(c >> 7) << 8);
+        nb = 2;
+    } else if (c < (1u << 21)) {
+        v  = (uint64_t)((c & 0x7F) | 0x80) | ((uint64_t)(((c >> 7) & 0x7F) | 0x80) << 8) | ((uint64_t)(c >> 14) << 16);
+        nb = 3;
+    } else if (c < (1u << 28)) {
+        v  = (uint64_t)((c & 0x7F) | 0x80) | ((uint64_t)(((c >> 7) & 0x7F) | 0x80) << 8) | ((uint64_t)(((c >> 14) & 0x7F) | 0x80) << 16) | ((uint64_t)(c >> 21) << 24);
+        nb = 4;
+    } else {
+        v = (uint64_t)((c & 0x7F) | 0x80) | ((uint64_t)(((c >> 7) & 0x7F) | 0x80) << 8) | ((uint64_t)(((c >> 14) & 0x7F) | 0x80) << 16) |
+            ((uint64_t)(((c >> 21) & 0x7F) | 0x80) << 24) | ((uint64_t)(c >> 28) << 32);
+        nb = 5;
+    }
+    const uint32_t wi = len >> 3, bo = (len & 7) * 8;
+    const uint64_t lo = v << bo;
+    const uint64_t hi = bo ? (v >> (64 - bo)) : 0ull;  // the bytes that spill into the next word
+    // selects on scalars (written out: an indexed form gets turned back into a local-memory array by the compiler)
+    w[0] |= wi == 0 ? lo : 0ull;
+    w[1] |= wi == 1 ? lo : (wi == 0 ? hi : 0ull);
+    w[2] |= wi == 2 ? lo : (wi == 1 ? hi : 0ull);
+    w[3] |= wi == 3 ? lo : (wi == 2 ? hi : 0ull);
+    len += nb;
+}
+// SpookyHash::Hash64 for len <= 31 over four register words (static indices only)
+__device__ __forceinline__ uint64_t spooky_words4(const uint64_t (&w)[4], uint32_t len) {
+    uint64_t a = 0, b = 0, c = kSpookyConst, d = kSpookyConst;
+    uint32_t rem = len;
+    uint64_t t0 = w[0], t1 = w[1];
+    if (len > 15) {
+        c += w[0];
+        d += w[1];
+        spooky_short_mix(a, b, c, d);
+        rem -= 16;
+        t0 = w[2];
+        t1 = w[3];
+    }
+    d += (uint64_t)len << 56;
+    if (rem == 0) {
+        c += kSpookyConst;
+        d += kSpookyConst;
+    } else {
+        c += t0;
+        if (rem > 8) d += t1;
+    }
+    spooky_short_end(a, b, c, d);
+    return a;
+}
+__device__ __forceinline__ uint32_t index_find4(const uint64_t (&w)[4], uint32_t len, const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off,
+                                                const unsigned long long* __restrict__ slots, uint64_t mask, const uint32_t* __restrict__ presence, uint64_t pmask) {
+    const uint64_t h = spooky_words4(w, len);
+    {
+        const uint64_t b = presence_bit(h, pmask);
+        if (((__ldg(presence + (b >> 5)) >> (b & 31)) & 1u) == 0) return 0;
+    }
+    const uint32_t tag = (uint32_t)(h >> 32);
+    uint64_t       s   = h & mask;
+    for (uint64_t step = 0; step <= mask; ++step, s = (s + 1) & mask) {
+        const unsigned long long v = slots[s];
+        if (v == 0) return 0;
+        if ((uint32_t)(v >> 32) != tag) continue;
+        const uint32_t idx1 = (uint32_t)v;
+        const uint64_t o    = off[idx1 - 1];
+        if (off[idx1] - o != len) continue;
+        bool same = true;
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+            if (8 * i < len) {
+                const uint32_t nb = min(8u, len - 8 * i);
+                uint64_t       pw = 0;
+                for (uint32_t b = 0; b < nb; ++b) pw |= (uint64_t)keys[o + 8 * i + b] << (8 * b);
+                same = same && pw == w[i];
+            }
+        }
+        if (same) return idx1;
+    }
+    return 0;
+}
+
+// Frequent patterns ("the", "of the") would put millions of atomics on one counter, where they serialise.  Each block keeps a small
+// never-evicting cache in shared memory, pattern -> pending count: the first window of a pattern that finds its line empty claims it,
+// later windows of that pattern in the block bump the shared counter, and the block adds the total to the pattern's counter once when it
+// retires.  A line never changes owner, so the counts stay exact; patterns that lose the race for a line go to the global counter.
+constexpr uint32_t kMatchLines = 2048;
+
+// one count for pattern idx1 (> 0) through the block's cache
+__device__ __forceinline__ void count_match(uint32_t idx1, uint32_t* line_key, uint32_t* line_cnt, uint32_t* __restrict__ counts) {
+    const uint32_t line = (idx1 * 2654435761u) >> (32 - 11);  // kMatchLines = 2^11
+    uint32_t       own  = *(volatile uint32_t*)&line_key[line];
+    if (own == 0) {
+        own = atomicCAS(&line_key[line], 0u, idx1);
+        if (own == 0) own = idx1;
+    }
+    if (own == idx1)
+        atomicAdd(&line_cnt[line], 1u);
+    else
+        atomicAdd(&counts[idx1 - 1], 1u);
+}
+
+// prev (optional): match[] of length n-1.  When every pattern of length n has its (n-1)-token prefix in the set (use_prefix), a window
+// whose prefix did not match cannot match either; likewise for the suffix.  This is the back-off rule of unconstrained training
+// (include/patternmodel.h:1139-1152) re-derived for sets that happen to be closed -- every model train() itself produced is.
 template <int NW>
 __global__ void __launch_bounds__(256) constrained_match_kernel(const uint32_t* __restrict__ tok, uint64_t npos, int n, const uint8_t* __restrict__ keys,
                                                                 const uint64_t* __restrict__ off, const unsigned long long* __restrict__ slots, uint64_t mask,
-                                                                uint32_t* __restrict__ counts, uint32_t* __restrict__ match, DeviceStats* __restrict__ st) {
+                                                                const uint32_t* __restrict__ presence, uint64_t pmask, uint32_t* __restrict__ counts,
+                                                                uint32_t* __restrict__ match, const uint32_t* __restrict__ prev, bool use_prefix, bool use_suffix,
+                                                                DeviceStats* __restrict__ st) {
+    __shared__ uint32_t line_key[kMatchLines];
+    __shared__ uint32_t line_cnt[kMatchLines];
+    for (uint32_t i = threadIdx.x; i < kMatchLines; i += blockDim.x) {
+        line_key[i] = 0;
+        line_cnt[i] = 0;
+    }
+    __syncthreads();
     unsigned long long windows = 0;
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t w[NW];
-        words_clear(w);
-        uint32_t len = 0;
-        bool     ok  = true;
-        for (int j = 0; j < n; ++j) {
-            uint32_t t = tok[p + j];  // a delimiter (0) ends the scan, so the read never passes the end of its sentence
-            if (t == 0) {
-                ok = false;
-                break;
-            }
-            do {
-                const uint8_t digit = (uint8_t)(t & 0x7F);
-                t >>= 7;
-                words_put(w, len, t ? (uint8_t)(digit | 0x80) : digit);
-                ++len;
-            } while (t);
-        }
         uint32_t idx1 = 0;
-        if (ok) {
-            ++windows;
-            if (len <= kMaxIndexedKeyBytes && len < 8u * NW) idx1 = index_find(w, len, keys, off, slots, mask);
-            if (idx1) atomicAdd(&counts[idx1 - 1], 1u);
+        bool     candidate = true;
+        if (use_prefix && __ldcs(prev + p) == 0) candidate = false;
+        if (candidate && use_suffix && __ldg(prev + p + 1) == 0) candidate = false;
+        if (candidate) {
+            uint64_t w[NW];
+            words_clear(w);
+            uint32_t len = 0;
+            bool     ok  = true;
+            for (int j = 0; j < n; ++j) {
+                uint32_t t = tok[p + j];  // a delimiter (0) ends the scan, so the read never passes the end of its sentence
+                if (t == 0) {
+                    ok = false;
+                    break;
+                }
+                if constexpr (NW == 4) {
+                    key_append4(w, len, t);
+                } else {
+                    do {
+                        const uint8_t digit = (uint8_t)(t & 0x7F);
+                        t >>= 7;
+                        words_put(w, len, t ? (uint8_t)(digit | 0x80) : digit);
+                        ++len;
+                    } while (t);
+                }
+            }
+            if (ok) {
+                ++windows;
+                if (len <= kMaxIndexedKeyBytes && len < 8u * NW) {
+                    if constexpr (NW == 4)
+                        idx1 = index_find4(w, len, keys, off, slots, mask, presence, pmask);
+                    else
+                        idx1 = index_find(w, len, keys, off, slots, mask, presence, pmask);
+                }
+                if (idx1) count_match(idx1, line_key, line_cnt, counts);
+            }
         }
-        if (match) match[p] = idx1;
+        if (match) __stcs(match + p, idx1);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kMatchLines; i += blockDim.x) {
+        const uint32_t c = line_cnt[i];
+        if (c) atomicAdd(&counts[line_key[i] - 1], c);
     }
     windows = warp_reduce_sum(windows);
     if (lane_id() == 0 && windows) atomicAdd(&st->valid_windows, windows);
 }
 
+// length 1 needs no hashing: classes are dense (src/classencoder.cpp:213-226), so the unigram patterns are a class-indexed array
+// (uni[class] = pattern index + 1), like the level-1 histogram of unconstrained training
+__global__ void __launch_bounds__(256) unigram_table_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, const uint16_t* __restrict__ pn, uint64_t np,
+                                                            uint32_t* __restrict__ uni, uint32_t nclasses) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np || pn[i] != 1) return;
+    const uint64_t a = off[i], l = off[i + 1] - a;
+    if (l == 0 || l > 5) return;
+    uint64_t cls = 0;
+    for (uint64_t k = 0; k < l; ++k) cls |= (uint64_t)(keys[a + k] & 0x7F) << (7 * k);
+    // only the canonical encoding of a class can equal the bytes of a corpus token (the tokeniser refuses the others)
+    if (cls >= nclasses || varint_len((uint32_t)cls) != l) return;
+    uni[cls] = (uint32_t)i + 1;
+}
+__global__ void __launch_bounds__(256) constrained_unigram_kernel(const uint32_t* __restrict__ tok, uint64_t npos, const uint32_t* __restrict__ uni, uint32_t nclasses,
+                                                                  uint32_t* __restrict__ counts, uint32_t* __restrict__ match, DeviceStats* __restrict__ st) {
+    __shared__ uint32_t line_key[kMatchLines];
+    __shared__ uint32_t line_cnt[kMatchLines];
+    for (uint32_t i = threadIdx.x; i < kMatchLines; i += blockDim.x) {
+        line_key[i] = 0;
+        line_cnt[i] = 0;
+    }
+    __syncthreads();
+    unsigned long long windows = 0;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t t = __ldcs(tok + p);
+        uint32_t       idx1 = 0;
+        if (t != 0) {
+            ++windows;
+            if (t < nclasses) idx1 = __ldg(uni + t);
+            if (idx1) count_match(idx1, line_key, line_cnt, counts);
+        }
+        if (match) __stcs(match + p, idx1);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kMatchLines; i += blockDim.x) {
+        const uint32_t c = line_cnt[i];
+        if (c) atomicAdd(&counts[line_key[i] - 1], c);
+    }
+    windows = warp_reduce_sum(windows);
+    if (lane_id() == 0 && windows) atomicAdd(&st->valid_windows, windows);
+}
+
+// closure of the set per pattern length: how many patterns of n tokens lack their (n-1)-token prefix / suffix in the set
+__global__ void __launch_bounds__(256) closure_check_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, const uint16_t* __restrict__ pn, uint64_t np,
+                                                            const unsigned long long* __restrict__ slots, uint64_t mask, const uint32_t* __restrict__ presence, uint64_t pmask,
+                                                            unsigned long long* __restrict__ prefix_open, unsigned long long* __restrict__ suffix_open) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const uint32_t n = pn[i];
+    if (n < 2) return;
+    const uint64_t a = off[i], b = off[i + 1];
+    if (b - a > kMaxIndexedKeyBytes) return;
+    // end of the first token, start of the last token
+    uint64_t first_end = a, last_start = a;
+    {
+        uint64_t k = a;
+        while (k < b && keys[k] >= 128) ++k;
+        first_end = k + 1;
+        uint64_t start = a;
+        for (k = a; k < b; ++k)
+            if (keys[k] < 128 && k + 1 < b) start = k + 1;
+        last_start = start;
+    }
+    uint64_t w[24];
+    words_load(w, keys + a, (uint32_t)(last_start - a));
+    if (index_find(w, (uint32_t)(last_start - a), keys, off, slots, mask, presence, pmask) == 0) atomicAdd(&prefix_open[min(n, 255u)], 1ull);
+    words_load(w, keys + first_end, (uint32_t)(b - first_end));
+    if (index_find(w, (uint32_t)(b - first_end), keys, off, slots, mask, presence, pmask) == 0) atomicAdd(&suffix_open[min(n, 255u)], 1ull);
+}
+
 // after the scan: found = patterns seen at least once, kept = count >= threshold, per-length sums of the kept ones
 __global__ void __launch_bounds__(256) constrained_stats_kernel(const uint32_t* __restrict__ counts, const uint16_t* __restrict__ pn, uint64_t np, uint32_t threshold,
                                                                 uint32_t* __restrict__ flags, PatternMetaStats* __restrict__ st, DeviceStats* __restrict__ ds) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool     seen = false, kept = false;
-    uint32_t c = 0, n = 0;
-    if (i < np) {
-        c        = counts[i];
-        n        = pn[i];
-        seen     = c > 0;
-        kept     = c >= threshold;
+    __shared__ unsigned long long s_kept_n[256], s_occ_n[256];
+    __shared__ unsigned long long s_found, s_kept, s_occ;
+    __shared__ uint32_t           s_maxn, s_minn;
+    s_kept_n[threadIdx.x] = 0;
+    s_occ_n[threadIdx.x]  = 0;
+    if (threadIdx.x == 0) {
+        s_found = s_kept = s_occ = 0;
+        s_maxn = 0;
+        s_minn = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = counts[i], n = pn[i];
+        const bool     kept = c >= threshold;
         flags[i] = kept ? 1u : 0u;
+        if (c > 0) atomicAdd(&s_found, 1ull);
+        if (kept) {
+            atomicAdd(&s_kept, 1ull);
+            atomicAdd(&s_occ, (unsigned long long)c);
+            atomicAdd(&s_kept_n[min(n, 255u)], 1ull);
+            atomicAdd(&s_occ_n[min(n, 255u)], (unsigned long long)c);
+            atomicMax(&s_maxn, n);
+            atomicMin(&s_minn, n);
+        }
     }
-    const uint32_t mseen = __ballot_sync(0xffffffffu, seen), mkept = __ballot_sync(0xffffffffu, kept);
-    if (lane_id() == 0) {
-        if (mseen) atomicAdd(&ds->found, (unsigned long long)__popc(mseen));
-        if (mkept) atomicAdd(&ds->kept, (unsigned long long)__popc(mkept));
+    __syncthreads();
+    if (s_kept_n[threadIdx.x]) {
+        atomicAdd(&st->kept_n[threadIdx.x], s_kept_n[threadIdx.x]);
+        atomicAdd(&st->kept_occ_n[threadIdx.x], s_occ_n[threadIdx.x]);
     }
-    if (kept) {
-        atomicAdd(&ds->kept_occ, (unsigned long long)c);
-        atomicAdd(&st->kept_occ_n[min(n, 255u)], (unsigned long long)c);
-        atomicAdd(&st->kept_n[min(n, 255u)], 1ull);
-        atomicMax(&st->kept_maxn, n);
-        atomicMin(&st->kept_minn, n);
+    if (threadIdx.x == 0) {
+        if (s_found) atomicAdd(&ds->found, s_found);
+        if (s_kept) {
+            atomicAdd(&ds->kept, s_kept);
+            atomicAdd(&ds->kept_occ, s_occ);
+            atomicMax(&st->kept_maxn, s_maxn);
+            atomicMin(&st->kept_minn, s_minn);
+        }
     }
 }
 
@@ -267,19 +525,36 @@ __global__ void __launch_bounds__(256) constrained_stats_kernel(const uint32_t* 
 __global__ void __launch_bounds__(256) load_filter_kernel(const uint16_t* __restrict__ pn, const uint8_t* __restrict__ pcat, const uint32_t* __restrict__ counts,
                                                           const uint32_t* __restrict__ constrain_idx1, uint64_t np, uint32_t mintokens, uint32_t minlength, uint32_t maxlength,
                                                           int dongrams, int doskipgrams, int doflexgrams, uint32_t* __restrict__ flags, PatternMetaStats* __restrict__ st) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= np) return;
-    const uint32_t n = pn[i], cat = pcat[i];
-    bool keep = !((!dongrams && cat == 0) || (!doskipgrams && cat == 1) || (!doflexgrams && cat == 2));
-    keep      = keep && n >= minlength && n <= maxlength && counts[i] >= mintokens;
-    if (keep && constrain_idx1 != nullptr) keep = constrain_idx1[i] != 0;
-    flags[i] = keep ? 1u : 0u;
-    if (keep) {
-        atomicMax(&st->kept_maxn, n);
-        atomicMin(&st->kept_minn, n);
-        if (cat == 1) st->kept_hasskip = 1;
-        if (cat == 2) st->kept_hasflex = 1;
-        atomicAdd(&st->kept_n[min(n, 255u)], 1ull);
+    __shared__ unsigned long long s_kept_n[256];
+    __shared__ uint32_t           s_maxn, s_minn, s_skip, s_flex;
+    s_kept_n[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        s_maxn = 0;
+        s_minn = 0xFFFFFFFFu;
+        s_skip = s_flex = 0;
+    }
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t n = pn[i], cat = pcat[i];
+        bool keep = !((!dongrams && cat == 0) || (!doskipgrams && cat == 1) || (!doflexgrams && cat == 2));
+        keep      = keep && n >= minlength && n <= maxlength && counts[i] >= mintokens;
+        if (keep && constrain_idx1 != nullptr) keep = constrain_idx1[i] != 0;
+        flags[i] = keep ? 1u : 0u;
+        if (keep) {
+            atomicMax(&s_maxn, n);
+            atomicMin(&s_minn, n);
+            if (cat == 1) s_skip = 1;
+            if (cat == 2) s_flex = 1;
+            atomicAdd(&s_kept_n[min(n, 255u)], 1ull);
+        }
+    }
+    __syncthreads();
+    if (s_kept_n[threadIdx.x]) atomicAdd(&st->kept_n[threadIdx.x], s_kept_n[threadIdx.x]);
+    if (threadIdx.x == 0 && s_minn != 0xFFFFFFFFu) {
+        atomicMax(&st->kept_maxn, s_maxn);
+        atomicMin(&st->kept_minn, s_minn);
+        if (s_skip) st->kept_hasskip = 1;
+        if (s_flex) st->kept_hasflex = 1;
     }
 }
 
@@ -357,20 +632,25 @@ __global__ void __launch_bounds__(256) popcount_kernel(const uint32_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// streaming kernels over the patterns: enough blocks to fill the machine, each aggregating its statistics in shared memory first
+static inline unsigned pattern_grid(uint64_t np) {
+    return (unsigned)std::min<uint64_t>(pi_div_up(np, 256), 148 * 16);
+}
 int launch_pattern_meta(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, uint16_t* pn, uint8_t* pcat, PatternMetaStats* st) {
     if (!np) return 0;
-    pattern_meta_kernel<<<pi_div_up(np, 256), 256, 0, s>>>(keys, off, np, pn, pcat, st);
+    pattern_meta_kernel<<<pattern_grid(np), 256, 0, s>>>(keys, off, np, pn, pcat, st);
     return 1;
 }
-int launch_index_build(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, unsigned long long* slots, uint64_t cap_pow2, PatternMetaStats* st) {
+int launch_index_build(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, unsigned long long* slots, uint64_t cap_pow2, uint32_t* presence,
+                       uint64_t presence_bits_pow2, PatternMetaStats* st) {
     if (!np) return 0;
-    index_build_kernel<<<pi_div_up(np, 256), 256, 0, s>>>(keys, off, np, slots, cap_pow2 - 1, st);
+    index_build_kernel<<<pi_div_up(np, 256), 256, 0, s>>>(keys, off, np, slots, cap_pow2 - 1, presence, presence_bits_pow2 - 1, st);
     return 1;
 }
 int launch_index_lookup(cudaStream_t s, const uint8_t* qkeys, const uint64_t* qoff, uint64_t nq, const uint8_t* keys, const uint64_t* off, const unsigned long long* slots,
-                        uint64_t cap_pow2, uint32_t* out_idx1) {
+                        uint64_t cap_pow2, const uint32_t* presence, uint64_t presence_bits_pow2, uint32_t* out_idx1) {
     if (!nq) return 0;
-    index_lookup_kernel<<<pi_div_up(nq, 256), 256, 0, s>>>(qkeys, qoff, nq, keys, off, slots, cap_pow2 - 1, out_idx1);
+    index_lookup_kernel<<<pi_div_up(nq, 256), 256, 0, s>>>(qkeys, qoff, nq, keys, off, slots, cap_pow2 - 1, presence, presence_bits_pow2 - 1, out_idx1);
     return 1;
 }
 int launch_gather_counts(cudaStream_t s, const uint32_t* idx1, uint64_t nq, const uint32_t* counts, uint32_t* out) {
@@ -379,24 +659,43 @@ int launch_gather_counts(cudaStream_t s, const uint32_t* idx1, uint64_t nq, cons
     return 1;
 }
 int launch_constrained_match(cudaStream_t s, const uint32_t* tok, uint64_t npos, int n, const uint8_t* keys, const uint64_t* off, const unsigned long long* slots, uint64_t cap_pow2,
-                             uint32_t* counts, uint32_t* match, DeviceStats* st, int sms) {
+                             const uint32_t* presence, uint64_t presence_bits_pow2, uint32_t* counts, uint32_t* match, const uint32_t* prev, bool use_prefix, bool use_suffix,
+                             DeviceStats* st, int sms) {
     if (!npos) return 0;
-    const unsigned grid = (unsigned)std::min<uint64_t>(pi_div_up(npos, 256), (uint64_t)sms * 8 * 4);
+    const unsigned grid = (unsigned)std::min<uint64_t>(pi_div_up(npos, 256), (uint64_t)sms * 8);  // resident blocks only: each owns one count cache
+    if (prev == nullptr) use_prefix = use_suffix = false;
     if (n * 5 < 8 * 4)  // every window of n tokens fits 31 bytes: registers only
-        constrained_match_kernel<4><<<grid, 256, 0, s>>>(tok, npos, n, keys, off, slots, cap_pow2 - 1, counts, match, st);
+        constrained_match_kernel<4><<<grid, 256, 0, s>>>(tok, npos, n, keys, off, slots, cap_pow2 - 1, presence, presence_bits_pow2 - 1, counts, match, prev, use_prefix, use_suffix, st);
     else
-        constrained_match_kernel<24><<<grid, 256, 0, s>>>(tok, npos, n, keys, off, slots, cap_pow2 - 1, counts, match, st);
+        constrained_match_kernel<24><<<grid, 256, 0, s>>>(tok, npos, n, keys, off, slots, cap_pow2 - 1, presence, presence_bits_pow2 - 1, counts, match, prev, use_prefix, use_suffix, st);
+    return 1;
+}
+int launch_unigram_table(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint16_t* pn, uint64_t np, uint32_t* uni, uint32_t nclasses) {
+    if (!np) return 0;
+    unigram_table_kernel<<<pi_div_up(np, 256), 256, 0, s>>>(keys, off, pn, np, uni, nclasses);
+    return 1;
+}
+int launch_constrained_unigrams(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* uni, uint32_t nclasses, uint32_t* counts, uint32_t* match, DeviceStats* st, int sms) {
+    if (!npos) return 0;
+    const unsigned grid = (unsigned)std::min<uint64_t>(pi_div_up(npos, 256), (uint64_t)sms * 8);
+    constrained_unigram_kernel<<<grid, 256, 0, s>>>(tok, npos, uni, nclasses, counts, match, st);
+    return 1;
+}
+int launch_closure_check(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint16_t* pn, uint64_t np, const unsigned long long* slots, uint64_t cap_pow2,
+                         const uint32_t* presence, uint64_t presence_bits_pow2, unsigned long long* prefix_open, unsigned long long* suffix_open) {
+    if (!np) return 0;
+    closure_check_kernel<<<pi_div_up(np, 256), 256, 0, s>>>(keys, off, pn, np, slots, cap_pow2 - 1, presence, presence_bits_pow2 - 1, prefix_open, suffix_open);
     return 1;
 }
 int launch_constrained_stats(cudaStream_t s, const uint32_t* counts, const uint16_t* pn, uint64_t np, uint32_t threshold, uint32_t* flags, PatternMetaStats* st, DeviceStats* ds) {
     if (!np) return 0;
-    constrained_stats_kernel<<<pi_div_up(np, 256), 256, 0, s>>>(counts, pn, np, threshold, flags, st, ds);
+    constrained_stats_kernel<<<pattern_grid(np), 256, 0, s>>>(counts, pn, np, threshold, flags, st, ds);
     return 1;
 }
 int launch_load_filter(cudaStream_t s, const uint16_t* pn, const uint8_t* pcat, const uint32_t* counts, const uint32_t* constrain_idx1, uint64_t np, uint32_t mintokens,
                        uint32_t minlength, uint32_t maxlength, int dongrams, int doskipgrams, int doflexgrams, uint32_t* flags, PatternMetaStats* st) {
     if (!np) return 0;
-    load_filter_kernel<<<pi_div_up(np, 256), 256, 0, s>>>(pn, pcat, counts, constrain_idx1, np, mintokens, minlength, maxlength, dongrams, doskipgrams, doflexgrams, flags, st);
+    load_filter_kernel<<<pattern_grid(np), 256, 0, s>>>(pn, pcat, counts, constrain_idx1, np, mintokens, minlength, maxlength, dongrams, doskipgrams, doflexgrams, flags, st);
     return 1;
 }
 int launch_select_scatter(cudaStream_t s, const uint32_t* flags, const uint64_t* newpos, const uint16_t* pn, uint64_t np, uint32_t* sel_idx, uint32_t* sel_n) {

@@ -555,6 +555,18 @@ int Trainer::run() {
         if (!cur.p) TRY(cur.alloc(dev, npos + 8));
         CUDA_TRY(cudaMemsetAsync(cur.p + npos, 0, 8 * sizeof(uint32_t), s));
 
+        // ---- dense pairs (level 2 of a large corpus): the ids of level 1 are the class numbers, frequent classes are the small ones
+        uint32_t dense = 0;
+        if (n == 2) {
+            const char*    e_dim = getenv("COLIBRI_B200_DENSE");      // side of the directly addressed square (0 = off)
+            const char*    e_min = getenv("COLIBRI_B200_DENSE_MIN");  // smallest level (upper bound of its windows) that gets one
+            const uint64_t dmin  = e_min ? strtoull(e_min, nullptr, 10) : (1ull << 25);
+            const uint32_t ddim  = e_dim ? (uint32_t)atoi(e_dim) : 2048u;
+            if (bound >= dmin && !getenv("COLIBRI_B200_MLP") && !getenv("COLIBRI_B200_MLP_COUNT") && !getenv("COLIBRI_B200_MLP_FILTER")) dense = std::min<uint32_t>(ddim, nclasses);
+            if (dense > 16384) dense = 16384;
+        }
+        const uint64_t dense_slots = (uint64_t)dense * dense;
+
         // ---- occurrence filter (t >= 2, worth its two extra launches only on large levels)
         const bool use_filter = t >= 2 && bound >= (1ull << 25) && !getenv("COLIBRI_B200_NO_FILTER");
         uint64_t   nbuckets = 0, cap = 0;
@@ -566,7 +578,7 @@ int Trainer::run() {
             int hf = timer.begin(COLIBRI_T_COUNT, n);
             CUDA_TRY(cudaMemsetAsync(filter.p, 0, nbuckets / 4, s));
             TRY(zero_stats());
-            launches += launch_ngram_filter(s, prev.p, npos, filter.p, nbuckets, d_stats.p, sms);
+            launches += launch_ngram_filter(s, prev.p, npos, filter.p, nbuckets, d_stats.p, sms, dense);
             timer.end(hf);
             TRY(read_stats());
             // keys that reach the table live in buckets hit at least twice; there are at most ~2 such keys per bucket
@@ -578,17 +590,18 @@ int Trainer::run() {
         }
         uint64_t windows = 0, singles = 0;
         for (int attempt = 0;; ++attempt) {
-            if (cap >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "level %d needs %llu table slots; slot ids are 32 bit", n, (unsigned long long)cap);
-            if (table.n < cap) TRY(table.alloc(dev, cap));
+            if (cap + dense_slots >= 0xFFFFFFF0ull)
+                return set_err(COLIBRI_E_CAPACITY, "level %d needs %llu table slots; slot ids are 32 bit", n, (unsigned long long)(cap + dense_slots));
+            if (table.n < cap + dense_slots) TRY(table.alloc(dev, cap + dense_slots));
             int hp0 = timer.begin(COLIBRI_T_PRUNE);
-            CUDA_TRY(cudaMemsetAsync(table.p, 0, cap * sizeof(NgramSlot), s));
+            CUDA_TRY(cudaMemsetAsync(table.p, 0, (cap + dense_slots) * sizeof(NgramSlot), s));
             timer.end(hp0);
-            slots_init += cap;
+            slots_init += cap + dense_slots;
             TRY(zero_stats());
             int hc = timer.begin(COLIBRI_T_COUNT, n);
             static const int hot_mode = getenv("COLIBRI_B200_HOT") ? atoi(getenv("COLIBRI_B200_HOT")) : 1;  // 0 never, 1 large levels, 2 always
             const bool hot = hot_mode == 2 || (hot_mode == 1 && bound >= (1ull << 25));
-            launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms, use_filter ? filter.p : nullptr, nbuckets, hot);
+            launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms, use_filter ? filter.p : nullptr, nbuckets, hot, dense);
             timer.end(hc);
             CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaStreamSynchronize(s));
@@ -614,9 +627,10 @@ int Trainer::run() {
         uint64_t sv_bound = windows / std::max<uint32_t>(t, 1) + 1;
         TRY(sg.pos.alloc(dev, sv_bound));
         TRY(sg.cnt.alloc(dev, sv_bound));
-        if (bitmap.n < cap / 32 + 8) TRY(bitmap.alloc(dev, cap / 32 + 8));
-        if (indexed && slot_index.n < cap) TRY(slot_index.alloc(dev, cap));
-        launches += launch_prune_ngrams(s, table.p, cap, t, sg.pos.p, sg.cnt.p, bitmap.p, d_stats.p, sms, indexed ? slot_index.p : nullptr);
+        const uint64_t slots_total = cap + dense_slots;  // the dense square is scanned like the hashed part: its entries are ordinary slots
+        if (bitmap.n < slots_total / 32 + 8) TRY(bitmap.alloc(dev, slots_total / 32 + 8));
+        if (indexed && slot_index.n < slots_total) TRY(slot_index.alloc(dev, slots_total));
+        launches += launch_prune_ngrams(s, table.p, slots_total, t, sg.pos.p, sg.cnt.p, bitmap.p, d_stats.p, sms, indexed ? slot_index.p : nullptr);
         timer.end(hp);
         TRY(read_stats());
         // a window the filter held back is a distinct n-gram with exactly one occurrence: found, and pruned (t >= 2)
@@ -815,6 +829,7 @@ int Trainer::run_constrained(colibri_b200_model* cm, bool inplace) {
         CUDA_TRY(cudaMemsetAsync(mb.p + npos, 0, 8 * sizeof(uint32_t), s));
     }
     TRY(zero_stats());
+    cm->index_counts_dirty = true;  // until the slot counters have been collected (an error in between forces a rebuild of the index)
     for (size_t k = 0; k < lengths.size(); ++k) {
         const int n   = lengths[k];
         uint32_t* cur = match[indexed ? k : k % 2].p;
@@ -829,7 +844,13 @@ int Trainer::run_constrained(colibri_b200_model* cm, bool inplace) {
                                                  prev, use_prefix, use_suffix, d_stats.p, sms);
         timer.end(hc);
     }
+    {
+        int hc = timer.begin(COLIBRI_T_PRUNE);
+        launches += launch_collect_slot_counts(s, cm->d_index.p, cm->index_cap, counts.p);
+        timer.end(hc);
+    }
     TRY(read_stats());
+    cm->index_counts_dirty = false;
     ngram_upserts = h_stats.valid_windows;
 
     // ---- threshold (prune(MINTOKENS, 0)) and the numbers of the progress line
@@ -841,7 +862,7 @@ int Trainer::run_constrained(colibri_b200_model* cm, bool inplace) {
     CUDA_TRY(cudaMemcpyAsync(d_pst.p, &pst, sizeof pst, cudaMemcpyHostToDevice, s));
     TRY(zero_stats());
     int hp = timer.begin(COLIBRI_T_PRUNE);
-    launches += launch_constrained_stats(s, counts.p, cm->d_pn.p, np, t, flags.p, d_pst.p, d_stats.p);
+    launches += launch_constrained_stats(s, counts.p, cm->d_pn.p, np, t, flags.p, d_pst.p, d_stats.p, indexed);
     timer.end(hp);
     CUDA_TRY(cudaMemcpyAsync(&pst, d_pst.p, sizeof pst, cudaMemcpyDeviceToHost, s));
     TRY(read_stats());

@@ -240,7 +240,8 @@ struct colibri_b200_model {
     DevBuf<uint8_t>            d_pcat;
     bool                       meta_ready = false;
     colibri::PatternMetaStats  meta;
-    DevBuf<unsigned long long> d_index;
+    DevBuf<colibri::PatSlot>   d_index;
+    bool                       index_counts_dirty = false;  // a constrained run died between counting in the slots and collecting them
     uint64_t                   index_cap = 0;
     DevBuf<uint32_t>           d_presence;  // one bit per hash bucket (16 per pattern): negative lookups end in L2
     uint64_t                   presence_bits = 0;

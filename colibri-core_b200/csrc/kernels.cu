@@ -295,7 +295,7 @@ __device__ __forceinline__ void filter_locate(uint64_t h, uint64_t nbuckets_mask
 }
 
 __global__ void __launch_bounds__(256) ngram_filter_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t* __restrict__ filter, uint64_t nbuckets_mask,
-                                                           DeviceStats* __restrict__ st) {
+                                                           DeviceStats* __restrict__ st, const uint32_t dense) {
     __shared__ uint64_t scratch[8];
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint32_t       valid = 0, twice = 0;
@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(256) ngram_filter_kernel(const uint32_t* __res
         uint32_t b = __ldg(prev + p + 1);
         if (a == 0 || b == 0) continue;
         ++valid;
+        if (a < dense && b < dense) continue;  // a pair of frequent classes has its own directly addressed slot (see count_ngrams_kernel)
         uint64_t word;
         uint32_t shift;
         filter_locate(spooky_hash64_u64(((unsigned long long)a << 32) | b, 0), nbuckets_mask, word, shift);
@@ -335,10 +336,27 @@ __global__ void __launch_bounds__(256) ngram_filter_kernel(const uint32_t* __res
 constexpr uint32_t           kHotLines = 1024;
 constexpr unsigned long long kHotBusy  = ~0ull;
 
-template <bool kFilter>
-__global__ void __launch_bounds__(256, 8) count_ngrams_kernel(const uint32_t* __restrict__ prev, uint32_t* __restrict__ cur, uint64_t npos, NgramSlot* __restrict__ table,
+// Dense pairs (level 2 only, where the ids ARE the class numbers and classes are ranked by frequency, src/classencoder.cpp:213-226):
+// a bigram of two classes below `dense` owns slot dense_base + a * dense + b of the same table -- no hash, no filter word, no probing.
+// With dense = 2048 that is 46 % of the bigram windows of a Zipf corpus (54 % of those of a 100 k vocabulary fall below 4096), all of
+// them landing in a 64 MB region whose hot part lives in L2.  Such a slot is an ordinary NgramSlot, so the prune scan, the survivor
+// bitmap, the relabel step and the forward index treat it like any other.
+// a directly addressed slot: the key can only be this one, so there is nothing to probe
+__device__ __forceinline__ uint32_t upsert_dense(NgramSlot* __restrict__ table, uint64_t slot, unsigned long long key, uint32_t pos) {
+    NgramSlot* s = table + slot;
+    if (__ldcg(&s->key) == 0) {
+        unsigned long long o0, o1;
+        cas128(s, key, 1ull | ((unsigned long long)pos << 32), o0, o1);
+        if (o0 == 0) return (uint32_t)slot + 1;
+    }
+    atomicAdd(&s->count, 1u);
+    return (uint32_t)slot + 1;
+}
+
+template <bool kFilter, bool kDense>
+__global__ void __launch_bounds__(256, kDense ? 7 : 8) count_ngrams_kernel(const uint32_t* __restrict__ prev, uint32_t* __restrict__ cur, uint64_t npos, NgramSlot* __restrict__ table,
                                                            uint64_t cap, const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, DeviceStats* __restrict__ st,
-                                                           const bool hot) {
+                                                           const bool hot, const uint32_t dense) {
     __shared__ uint64_t scratch[8];
     __shared__ unsigned long long hot_key[kHotLines];
     __shared__ uint32_t hot_slot[kHotLines];
@@ -360,28 +378,46 @@ __global__ void __launch_bounds__(256, 8) count_ngrams_kernel(const uint32_t* __
         if (a != 0 && b != 0) {
             ++valid;
             const unsigned long long key = ((unsigned long long)a << 32) | b;
-            const uint64_t           h   = spooky_hash64_u64(key, 0);
-            bool                     go  = true;
-            if (kFilter) {
-                uint64_t word;
-                uint32_t shift;
-                filter_locate(h, nbuckets_mask, word, shift);
-                go = ((__ldg(filter + word) >> shift) & 2u) != 0;
-                singles += !go;
-            }
-            if (go) {
-                const uint32_t           line   = (uint32_t)(h >> 20) & (kHotLines - 1);
+            if (kDense && a < dense && b < dense) {
+                // the pair owns slot cap + a * dense + b (the dense square follows the hashed part of the table)
+                const uint32_t     line   = (a * 40503u + b) & (kHotLines - 1);
                 unsigned long long cached = ~0ull;
                 if (hot) cached = *(volatile unsigned long long*)&hot_key[line];
-                if (cached == key) {  // its slot was published before the key (below)
+                if (cached == key) {
                     atomicAdd(&hot_pending[line], 1u);
                     id = *(volatile uint32_t*)&hot_slot[line];
                 } else {
-                    id = upsert_ngram_at(table, cap, fast_range(h, cap), key, (uint32_t)p, probes, full);
-                    if (id != 0 && cached == 0 && atomicCAS(&hot_key[line], 0ull, kHotBusy) == 0ull) {
-                        hot_slot[line] = id;  // publish the slot ...
+                    id = upsert_dense(table, cap + (uint64_t)a * dense + b, key, (uint32_t)p);
+                    if (cached == 0 && atomicCAS(&hot_key[line], 0ull, kHotBusy) == 0ull) {
+                        hot_slot[line] = id;
                         __threadfence_block();
-                        *(volatile unsigned long long*)&hot_key[line] = key;  // ... then the key that makes it visible
+                        *(volatile unsigned long long*)&hot_key[line] = key;
+                    }
+                }
+            } else {
+                const uint64_t h  = spooky_hash64_u64(key, 0);
+                bool           go = true;
+                if (kFilter) {
+                    uint64_t word;
+                    uint32_t shift;
+                    filter_locate(h, nbuckets_mask, word, shift);
+                    go = ((__ldg(filter + word) >> shift) & 2u) != 0;
+                    singles += !go;
+                }
+                if (go) {
+                    const uint32_t           line   = (uint32_t)(h >> 20) & (kHotLines - 1);
+                    unsigned long long cached = ~0ull;
+                    if (hot) cached = *(volatile unsigned long long*)&hot_key[line];
+                    if (cached == key) {  // its slot was published before the key (below)
+                        atomicAdd(&hot_pending[line], 1u);
+                        id = *(volatile uint32_t*)&hot_slot[line];
+                    } else {
+                        id = upsert_ngram_at(table, cap, fast_range(h, cap), key, (uint32_t)p, probes, full);
+                        if (id != 0 && cached == 0 && atomicCAS(&hot_key[line], 0ull, kHotBusy) == 0ull) {
+                            hot_slot[line] = id;  // publish the slot ...
+                            __threadfence_block();
+                            *(volatile unsigned long long*)&hot_key[line] = key;  // ... then the key that makes it visible
+                        }
                     }
                 }
             }
@@ -753,8 +789,8 @@ static int mlp_width() {
     static int u = mlp_env("COLIBRI_B200_MLP_COUNT");
     return u;
 }
-int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms) {
-    const int u = mlp_width_filter();
+int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms, uint32_t dense) {
+    const int u = dense ? 1 : mlp_width_filter();
     if (u == 4) {
         static unsigned per_sm = 0;
         if (!per_sm) per_sm = blocks_per_sm((const void*)ngram_filter_mlp_kernel<4>, 256, 0);
@@ -772,7 +808,7 @@ int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uin
     static int    bps = blocks_per_sm((const void*)ngram_filter_kernel, 256, 0);
     static size_t pad = throttle_smem((const void*)ngram_filter_kernel, "COLIBRI_B200_FILTER_BPS", 64, &bps);
     unsigned      grid = (unsigned)umin64(div_up(npos, 256), (uint64_t)sms * bps * 4);
-    ngram_filter_kernel<<<grid ? grid : 1, 256, pad, s>>>(prev, npos, filter, nbuckets - 1, st);
+    ngram_filter_kernel<<<grid ? grid : 1, 256, pad, s>>>(prev, npos, filter, nbuckets - 1, st, dense);
     return 1;
 }
 template <bool kFilter, int U>
@@ -784,8 +820,8 @@ static void launch_count_mlp(cudaStream_t s, const uint32_t* prev, uint32_t* cur
     count_ngrams_mlp_kernel<kFilter, U><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, filter, kFilter ? nbuckets - 1 : 0, st, hot);
 }
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms, const uint32_t* filter,
-                        uint64_t nbuckets, bool hot) {
-    const int u = mlp_width();
+                        uint64_t nbuckets, bool hot, uint32_t dense) {
+    const int u = dense ? 1 : mlp_width();
     if (u == 4) {
         if (filter != nullptr) launch_count_mlp<true, 4>(s, prev, cur, npos, table, cap, st, sms, filter, nbuckets, hot);
         else launch_count_mlp<false, 4>(s, prev, cur, npos, table, cap, st, sms, nullptr, 0, hot);
@@ -796,17 +832,27 @@ int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uin
         else launch_count_mlp<false, 2>(s, prev, cur, npos, table, cap, st, sms, nullptr, 0, hot);
         return 1;
     }
-    static int    bps0 = blocks_per_sm((const void*)count_ngrams_kernel<false>, 256, 0);
-    static int    bps1 = blocks_per_sm((const void*)count_ngrams_kernel<true>, 256, 0);
-    static size_t pad0 = throttle_smem((const void*)count_ngrams_kernel<false>, "COLIBRI_B200_COUNT_BPS", 16448, &bps0);
-    static size_t pad1 = throttle_smem((const void*)count_ngrams_kernel<true>, "COLIBRI_B200_COUNT_BPS", 16448, &bps1);
+    static int    bps0 = blocks_per_sm((const void*)count_ngrams_kernel<false, false>, 256, 0);
+    static int    bps1 = blocks_per_sm((const void*)count_ngrams_kernel<true, false>, 256, 0);
+    static size_t pad0 = throttle_smem((const void*)count_ngrams_kernel<false, false>, "COLIBRI_B200_COUNT_BPS", 16448, &bps0);
+    static size_t pad1 = throttle_smem((const void*)count_ngrams_kernel<true, false>, "COLIBRI_B200_COUNT_BPS", 16448, &bps1);
     uint64_t      want = div_up(npos, 256);
-    if (filter != nullptr) {
+    if (dense) {
+        static int bpsd0 = blocks_per_sm((const void*)count_ngrams_kernel<false, true>, 256, 0);
+        static int bpsd1 = blocks_per_sm((const void*)count_ngrams_kernel<true, true>, 256, 0);
+        if (filter != nullptr) {
+            unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bpsd1 * 4);
+            count_ngrams_kernel<true, true><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, filter, nbuckets - 1, st, hot, dense);
+        } else {
+            unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bpsd0 * 4);
+            count_ngrams_kernel<false, true><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, nullptr, 0, st, hot, dense);
+        }
+    } else if (filter != nullptr) {
         unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bps1 * 4);
-        count_ngrams_kernel<true><<<grid ? grid : 1, 256, pad1, s>>>(prev, cur, npos, table, cap, filter, nbuckets - 1, st, hot);
+        count_ngrams_kernel<true, false><<<grid ? grid : 1, 256, pad1, s>>>(prev, cur, npos, table, cap, filter, nbuckets - 1, st, hot, 0);
     } else {
         unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bps0 * 4);
-        count_ngrams_kernel<false><<<grid ? grid : 1, 256, pad0, s>>>(prev, cur, npos, table, cap, nullptr, 0, st, hot);
+        count_ngrams_kernel<false, false><<<grid ? grid : 1, 256, pad0, s>>>(prev, cur, npos, table, cap, nullptr, 0, st, hot, 0);
     }
     return 1;
 }

@@ -70,10 +70,12 @@ int launch_make_id1(cudaStream_t s, const uint32_t* tok, uint64_t npos, const ui
 
 // ---- K2: n-gram upsert (the dominant kernel), K3: prune/compact, relabel
 // occurrence filter: nbuckets (power of two) 2-bit saturating counters, nbuckets/4 bytes, zeroed by the caller; st->found := buckets hit twice
-int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms);
-// filter == NULL: every valid window goes to the table
+// dense (level 2 only): windows whose two class ids are both below it bypass the filter (they own directly addressed slots, see launch_count_ngrams)
+int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms, uint32_t dense = 0);
+// filter == NULL: every valid window goes to the table.  dense > 0: the table has cap + dense * dense slots; a window (a, b) with a, b < dense is
+// counted in slot cap + a * dense + b (no hash, no filter, no probing), every other window in the hashed part [0, cap)
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms,
-                        const uint32_t* filter = nullptr, uint64_t nbuckets = 0, bool hot = false /* per-block shared-memory cache for frequent keys */);
+                        const uint32_t* filter = nullptr, uint64_t nbuckets = 0, bool hot = false /* per-block shared-memory cache for frequent keys */, uint32_t dense = 0);
 // bitmap: (cap+31)/32 words, bit = slot survived (may be NULL)
 int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap, DeviceStats* st, int sms,
                         uint32_t* slot_index = nullptr /* slot -> survivor index + 1, for the forward index */);
@@ -148,24 +150,36 @@ struct PatternMetaStats {  // zeroed by the host except minn / kept_minn = 0xFFF
     unsigned long long kept_occ_n[256];  // their occurrences
 };
 int launch_pattern_meta(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, uint16_t* pn, uint8_t* pcat, PatternMetaStats* st);
-// slots: cap_pow2 zeroed 8-byte entries {hash tag << 32 | pattern index + 1}; presence: presence_bits_pow2 zeroed bits, one per hash bucket
-int launch_index_build(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, unsigned long long* slots, uint64_t cap_pow2, uint32_t* presence,
+// One slot of the pattern index: 32 bytes = one HBM sector.  idx1 = pattern index + 1 (0 = empty); count = occurrences counted through
+// this slot by constrained training (collected into counts[] and zeroed afterwards); k0, k1 = key bytes 0..15; k2 = key bytes 16..22 with
+// the key length in the top byte, or 0xFF << 56 for keys longer than 23 bytes (their tail is compared in the blob).
+struct alignas(32) PatSlot {
+    uint32_t           idx1;
+    uint32_t           count;
+    unsigned long long k0, k1, k2;
+};
+// slots: cap_pow2 zeroed entries; presence: presence_bits_pow2 zeroed bits, one per hash bucket
+int launch_index_build(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, PatSlot* slots, uint64_t cap_pow2, uint32_t* presence,
                        uint64_t presence_bits_pow2, PatternMetaStats* st);
-int launch_index_lookup(cudaStream_t s, const uint8_t* qkeys, const uint64_t* qoff, uint64_t nq, const uint8_t* keys, const uint64_t* off, const unsigned long long* slots,
+int launch_index_lookup(cudaStream_t s, const uint8_t* qkeys, const uint64_t* qoff, uint64_t nq, const uint8_t* keys, const uint64_t* off, const PatSlot* slots,
                         uint64_t cap_pow2, const uint32_t* presence, uint64_t presence_bits_pow2, uint32_t* out_idx1 /* pattern index + 1, or 0 */);
 int launch_gather_counts(cudaStream_t s, const uint32_t* idx1, uint64_t nq, const uint32_t* counts, uint32_t* out);
 // windows of n tokens that are in the set: counts[pattern] += 1, match[p] = pattern index + 1 or 0 (match may be NULL).
 // prev (may be NULL) = match[] of length n-1 (npos + 1 readable entries); use_prefix / use_suffix: skip windows whose prefix / suffix did not match
-int launch_constrained_match(cudaStream_t s, const uint32_t* tok, uint64_t npos, int n, const uint8_t* keys, const uint64_t* off, const unsigned long long* slots, uint64_t cap_pow2,
+int launch_constrained_match(cudaStream_t s, const uint32_t* tok, uint64_t npos, int n, const uint8_t* keys, const uint64_t* off, PatSlot* slots, uint64_t cap_pow2,
                              const uint32_t* presence, uint64_t presence_bits_pow2, uint32_t* counts, uint32_t* match, const uint32_t* prev, bool use_prefix, bool use_suffix,
                              DeviceStats* st, int sms);
 // uni[class] = index + 1 of the unigram pattern of that class (uni zeroed by the caller, nclasses entries)
 int launch_unigram_table(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint16_t* pn, uint64_t np, uint32_t* uni, uint32_t nclasses);
 int launch_constrained_unigrams(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* uni, uint32_t nclasses, uint32_t* counts, uint32_t* match, DeviceStats* st, int sms);
 // per pattern length n (bins of 256, zeroed by the caller): patterns whose (n-1)-token prefix / suffix is not in the set
-int launch_closure_check(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint16_t* pn, uint64_t np, const unsigned long long* slots, uint64_t cap_pow2,
+// counts[pattern] += the slot counters of a constrained run, which are reset
+int launch_collect_slot_counts(cudaStream_t s, PatSlot* slots, uint64_t cap_pow2, uint32_t* counts);
+int launch_closure_check(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint16_t* pn, uint64_t np, const PatSlot* slots, uint64_t cap_pow2,
                          const uint32_t* presence, uint64_t presence_bits_pow2, unsigned long long* prefix_open, unsigned long long* suffix_open);
-int launch_constrained_stats(cudaStream_t s, const uint32_t* counts, const uint16_t* pn, uint64_t np, uint32_t threshold, uint32_t* flags, PatternMetaStats* st, DeviceStats* ds);
+// per_length: also fill st->kept_n / kept_occ_n (indexed models build their occurrence lists per pattern length)
+int launch_constrained_stats(cudaStream_t s, const uint32_t* counts, const uint16_t* pn, uint64_t np, uint32_t threshold, uint32_t* flags, PatternMetaStats* st, DeviceStats* ds,
+                             bool per_length);
 int launch_load_filter(cudaStream_t s, const uint16_t* pn, const uint8_t* pcat, const uint32_t* counts, const uint32_t* constrain_idx1, uint64_t np, uint32_t mintokens,
                        uint32_t minlength, uint32_t maxlength, int dongrams, int doskipgrams, int doflexgrams, uint32_t* flags, PatternMetaStats* st);
 int launch_select_scatter(cudaStream_t s, const uint32_t* flags, const uint64_t* newpos, const uint16_t* pn, uint64_t np, uint32_t* sel_idx, uint32_t* sel_n);

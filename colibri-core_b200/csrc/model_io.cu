@@ -52,7 +52,10 @@ int colibri::ensure_meta(colibri_b200_model* m, uint64_t* launches) {
 }
 
 int colibri::ensure_index(colibri_b200_model* m, uint64_t* launches) {
-    if (m->index_ready) return 0;
+    if (m->index_ready && !m->index_counts_dirty) return 0;
+    m->index_ready        = false;
+    m->closure_ready      = false;
+    m->index_counts_dirty = false;
     TRY(ensure_meta(m, launches));
     if (m->meta.malformed)
         return set_err(COLIBRI_E_UNSUPPORTED, "%u pattern(s) are empty, longer than %u bytes or not a well-formed class sequence: not indexable on the device", m->meta.malformed,
@@ -65,7 +68,7 @@ int colibri::ensure_index(colibri_b200_model* m, uint64_t* launches) {
     while (pbits < 16 * m->npatterns) pbits <<= 1;
     TRY(m->d_index.alloc(m->device, cap));
     TRY(m->d_presence.alloc(m->device, pbits / 32));
-    CUDA_TRY(cudaMemsetAsync(m->d_index.p, 0, cap * sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemsetAsync(m->d_index.p, 0, cap * sizeof(PatSlot), s));
     CUDA_TRY(cudaMemsetAsync(m->d_presence.p, 0, pbits / 8, s));
     uint64_t l = 0;
     if (m->npatterns) {

@@ -4,8 +4,11 @@
 // (src/pattern.cpp:234-238, include/patternstore.h:954-959): constrainbymodel->has(window) during constrained training
 // (include/patternmodel.h:1088-1089), constrainstore->has(p) while loading (include/patternstore.h:586), has()/occurrencecount()
 // queries (:751-756, :1653-1669).  Here a model's patterns are a flat blob + offsets; the index over them is an open-addressing
-// table of 8-byte slots {hash tag (high 32 bits) | pattern index + 1}, placed by the low bits of SpookyV2 Hash64 of the bytes
-// (the same function as Pattern::hash, csrc/spooky.h).  Keys compare in full (tag first, then the bytes), so it is exact.
+// table of 32-byte slots = one HBM sector {pattern index + 1, counter, the key bytes themselves (up to 23), key length}, placed by
+// the low bits of SpookyV2 Hash64 of the bytes (the same function as Pattern::hash, csrc/spooky.h).  A probe compares the key in
+// full inside the sector it just fetched (longer keys: in the blob), and constrained training counts in that same sector, so a
+// window that matches costs ONE random sector instead of four (slot, two offsets, key bytes, counter: 16.8 GB of DRAM reads for the
+// 68 M matching bigram windows of the 100 M-token corpus before, profiles/r01b).
 //   * constrained_match_kernel: one thread per corpus position and window length n: re-encode the n class ids to their
 //     varint bytes in registers, hash, probe, compare, atomicAdd the pattern's counter; optionally remember the match per
 //     position (the forward index of indexed models is built from those with index.cu's ordered pairs + stable radix sort).
@@ -13,6 +16,7 @@
 //   * compaction kernels: threshold -> survivors, ordered by pattern length so that per-length occurrence lists concatenate.
 // All of it is HBM-bound integer/byte work (random 8-byte probes + short byte compares).
 #include <algorithm>
+#include <cstdlib>
 
 #include "device_utils.cuh"
 #include "kernels.h"
@@ -81,34 +85,55 @@ __device__ __forceinline__ void words_load(uint64_t (&w)[NW], const uint8_t* __r
 // The presence bitmap: one bit per hash bucket, 16 buckets per pattern, small enough to stay in L2 (11 M patterns: 32 MB).  Most
 // windows of a corpus are NOT in the set; they are turned away here by an L2 hit instead of a random HBM sector.
 __device__ __forceinline__ uint64_t presence_bit(uint64_t h, uint64_t pmask) {
-    return (h >> 13) & pmask;  // bits 13.. : the slot uses the low bits, the tag the high 32
+    return (h >> 13) & pmask;  // bits 13.. (the slot uses the low bits)
+}
+// the three key words a slot stores for a key of len bytes held in w: bytes 0..7, 8..15, 16..22 | len << 56 (len <= 23), else a marker
+constexpr uint32_t           kInlineKeyBytes = 23;
+constexpr unsigned long long kLongKey        = 0xFFull << 56;
+template <int NW>
+__device__ __forceinline__ void slot_key(const uint64_t (&w)[NW], uint32_t len, unsigned long long& k0, unsigned long long& k1, unsigned long long& k2) {
+    k0 = w[0];
+    k1 = NW > 1 ? w[1] : 0ull;
+    k2 = len <= kInlineKeyBytes ? ((NW > 2 ? w[2] : 0ull) | ((unsigned long long)len << 56)) : kLongKey;
+}
+// probe for a key whose hash is h: pattern index + 1 (and the slot, for the counter), or 0
+template <int NW>
+__device__ __forceinline__ uint32_t index_probe(uint64_t h, const uint64_t (&w)[NW], uint32_t len, const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off,
+                                                const PatSlot* __restrict__ slots, uint64_t mask, uint64_t& slot_out) {
+    unsigned long long k0, k1, k2;
+    slot_key(w, len, k0, k1, k2);
+    uint64_t s = h & mask;
+    for (uint64_t step = 0; step <= mask; ++step, s = (s + 1) & mask) {
+        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(slots + s));  // {idx1, count, k0}; read-only path: the key words never change after the build
+        if (lo.x == 0) return 0;
+        if ((((unsigned long long)lo.w << 32) | lo.z) != k0) continue;
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(slots + s) + 1);  // {k1, k2}: same sector
+        if ((((unsigned long long)hi.y << 32) | hi.x) != k1 || (((unsigned long long)hi.w << 32) | hi.z) != k2) continue;
+        if (len > kInlineKeyBytes) {  // rare: the rest of a long key lives in the blob
+            const uint64_t o = off[lo.x - 1];
+            if (off[lo.x] - o != len) continue;
+            bool same = true;
+            for (uint32_t i = 16; i < len; ++i)
+                if (keys[o + i] != words_get(w, i)) {
+                    same = false;
+                    break;
+                }
+            if (!same) continue;
+        }
+        slot_out = s;
+        return lo.x;
+    }
+    return 0;
 }
 template <int NW>
 __device__ __forceinline__ uint32_t index_find(const uint64_t (&w)[NW], uint32_t len, const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off,
-                                               const unsigned long long* __restrict__ slots, uint64_t mask, const uint32_t* __restrict__ presence, uint64_t pmask) {
+                                               const PatSlot* __restrict__ slots, uint64_t mask, const uint32_t* __restrict__ presence, uint64_t pmask, uint64_t& slot_out) {
     const uint64_t h = spooky_words(w, len);
     if (presence != nullptr) {
         const uint64_t b = presence_bit(h, pmask);
         if (((__ldg(presence + (b >> 5)) >> (b & 31)) & 1u) == 0) return 0;
     }
-    const uint32_t tag = (uint32_t)(h >> 32);
-    uint64_t       s   = h & mask;
-    for (uint64_t step = 0; step <= mask; ++step, s = (s + 1) & mask) {
-        const unsigned long long v = slots[s];
-        if (v == 0) return 0;
-        if ((uint32_t)(v >> 32) != tag) continue;
-        const uint32_t idx1 = (uint32_t)v;
-        const uint64_t o    = off[idx1 - 1];
-        if (off[idx1] - o != len) continue;
-        bool same = true;
-        for (uint32_t i = 0; i < len; ++i)
-            if (keys[o + i] != words_get(w, i)) {
-                same = false;
-                break;
-            }
-        if (same) return idx1;
-    }
-    return 0;
+    return index_probe(h, w, len, keys, off, slots, mask, slot_out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -171,7 +196,7 @@ __global__ void __launch_bounds__(256) pattern_meta_kernel(const uint8_t* __rest
     }
 }
 
-__global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, uint64_t np, unsigned long long* __restrict__ slots,
+__global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, uint64_t np, PatSlot* __restrict__ slots,
                                                           uint64_t mask, uint32_t* __restrict__ presence, uint64_t pmask, PatternMetaStats* __restrict__ st) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
@@ -179,30 +204,35 @@ __global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restr
     const uint32_t len = (uint32_t)min(off[i + 1] - a, (uint64_t)kMaxIndexedKeyBytes);
     uint64_t       w[24];
     words_load(w, keys + a, len);
-    const uint64_t           h   = spooky_words(w, len);
-    const unsigned long long val = ((unsigned long long)(h >> 32) << 32) | (unsigned long long)(i + 1);
+    const uint64_t h = spooky_words(w, len);
     {
         const uint64_t b = presence_bit(h, pmask);
         atomicOr(presence + (b >> 5), 1u << (b & 31));
     }
-    uint64_t                 s   = h & mask;
+    unsigned long long k0, k1, k2;
+    slot_key(w, len, k0, k1, k2);
+    uint64_t s = h & mask;
     for (uint64_t step = 0; step <= mask; ++step, s = (s + 1) & mask) {
-        unsigned long long prev = atomicCAS(&slots[s], 0ull, val);
-        if (prev == 0) return;
-        if ((prev >> 32) == (val >> 32)) {  // same tag: a second copy of the same pattern?
-            const uint32_t j = (uint32_t)prev - 1;
-            const uint64_t o = off[j];
-            if (off[j + 1] - o == len) {
-                bool same = true;
-                for (uint32_t k = 0; k < len; ++k)
-                    if (keys[o + k] != keys[a + k]) {
-                        same = false;
-                        break;
-                    }
-                if (same) {
-                    atomicAdd(&st->duplicates, 1u);
-                    return;
+        const uint32_t prev = atomicCAS(&slots[s].idx1, 0u, (uint32_t)i + 1);
+        if (prev == 0) {  // claimed: nobody reads the key words before this kernel has finished
+            slots[s].k0 = k0;
+            slots[s].k1 = k1;
+            slots[s].k2 = k2;
+            return;
+        }
+        // a second copy of the same pattern?  (compared in the blob: the other slot's key words may still be in flight)
+        const uint32_t j = prev - 1;
+        const uint64_t o = off[j];
+        if (off[j + 1] - o == len) {
+            bool same = true;
+            for (uint32_t k = 0; k < len; ++k)
+                if (keys[o + k] != keys[a + k]) {
+                    same = false;
+                    break;
                 }
+            if (same) {
+                atomicAdd(&st->duplicates, 1u);
+                return;
             }
         }
     }
@@ -211,7 +241,7 @@ __global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restr
 
 // batch lookup: out_idx1[q] = pattern index + 1, or 0
 __global__ void __launch_bounds__(256) index_lookup_kernel(const uint8_t* __restrict__ qkeys, const uint64_t* __restrict__ qoff, uint64_t nq, const uint8_t* __restrict__ keys,
-                                                           const uint64_t* __restrict__ off, const unsigned long long* __restrict__ slots, uint64_t mask,
+                                                           const uint64_t* __restrict__ off, const PatSlot* __restrict__ slots, uint64_t mask,
                                                            const uint32_t* __restrict__ presence, uint64_t pmask, uint32_t* __restrict__ out_idx1) {
     uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
@@ -222,7 +252,8 @@ __global__ void __launch_bounds__(256) index_lookup_kernel(const uint8_t* __rest
     }
     uint64_t w[24];
     words_load(w, qkeys + a, (uint32_t)len64);
-    out_idx1[q] = index_find(w, (uint32_t)len64, keys, off, slots, mask, presence, pmask);
+    uint64_t slot;
+    out_idx1[q] = index_find(w, (uint32_t)len64, keys, off, slots, mask, presence, pmask, slot);
 }
 __global__ void __launch_bounds__(256) gather_counts_kernel(const uint32_t* __restrict__ idx1, uint64_t nq, const uint32_t* __restrict__ counts, uint32_t* __restrict__ out) {
     uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,32 +320,33 @@ __device__ __forceinline__ uint64_t spooky_words4(const uint64_t (&w)[4], uint32
     return a;
 }
 __device__ __forceinline__ uint32_t index_find4(const uint64_t (&w)[4], uint32_t len, const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off,
-                                                const unsigned long long* __restrict__ slots, uint64_t mask, const uint32_t* __restrict__ presence, uint64_t pmask) {
+                                                const PatSlot* __restrict__ slots, uint64_t mask, const uint32_t* __restrict__ presence, uint64_t pmask, uint64_t& slot_out) {
     const uint64_t h = spooky_words4(w, len);
     {
         const uint64_t b = presence_bit(h, pmask);
         if (((__ldg(presence + (b >> 5)) >> (b & 31)) & 1u) == 0) return 0;
     }
-    const uint32_t tag = (uint32_t)(h >> 32);
-    uint64_t       s   = h & mask;
+    const unsigned long long k0 = w[0], k1 = w[1];
+    const unsigned long long k2 = len <= kInlineKeyBytes ? (w[2] | ((unsigned long long)len << 56)) : kLongKey;
+    uint64_t s = h & mask;
     for (uint64_t step = 0; step <= mask; ++step, s = (s + 1) & mask) {
-        const unsigned long long v = slots[s];
-        if (v == 0) return 0;
-        if ((uint32_t)(v >> 32) != tag) continue;
-        const uint32_t idx1 = (uint32_t)v;
-        const uint64_t o    = off[idx1 - 1];
-        if (off[idx1] - o != len) continue;
-        bool same = true;
-#pragma unroll
-        for (uint32_t i = 0; i < 4; ++i) {
-            if (8 * i < len) {
-                const uint32_t nb = min(8u, len - 8 * i);
-                uint64_t       pw = 0;
-                for (uint32_t b = 0; b < nb; ++b) pw |= (uint64_t)keys[o + 8 * i + b] << (8 * b);
-                same = same && pw == w[i];
+        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(slots + s));
+        if (lo.x == 0) return 0;
+        if ((((unsigned long long)lo.w << 32) | lo.z) != k0) continue;
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(slots + s) + 1);
+        if ((((unsigned long long)hi.y << 32) | hi.x) != k1 || (((unsigned long long)hi.w << 32) | hi.z) != k2) continue;
+        if (len > kInlineKeyBytes) {  // 24..31 bytes: bytes 16.. are compared in the blob (w[2], w[3] hold them)
+            const uint64_t o = off[lo.x - 1];
+            if (off[lo.x] - o != len) continue;
+            uint64_t p2 = 0, p3 = 0;
+            for (uint32_t i = 16; i < len; ++i) {
+                const uint64_t byte = keys[o + i];
+                if (i < 24) p2 |= byte << (8 * (i - 16)); else p3 |= byte << (8 * (i - 24));
             }
+            if (p2 != w[2] || p3 != w[3]) continue;
         }
-        if (same) return idx1;
+        slot_out = s;
+        return lo.x;
     }
     return 0;
 }
@@ -325,8 +357,9 @@ __device__ __forceinline__ uint32_t index_find4(const uint64_t (&w)[4], uint32_t
 // retires.  A line never changes owner, so the counts stay exact; patterns that lose the race for a line go to the global counter.
 constexpr uint32_t kMatchLines = 2048;
 
-// one count for pattern idx1 (> 0) through the block's cache
-__device__ __forceinline__ void count_match(uint32_t idx1, uint32_t* line_key, uint32_t* line_cnt, uint32_t* __restrict__ counts) {
+// one count for pattern idx1 (> 0) through the block's cache; a pattern that lost the race for its cache line counts in `direct`
+// (its own index slot -- the sector the probe just fetched -- or, for unigrams, its entry of counts[])
+__device__ __forceinline__ void count_match(uint32_t idx1, uint32_t* line_key, uint32_t* line_cnt, uint32_t* direct) {
     const uint32_t line = (idx1 * 2654435761u) >> (32 - 11);  // kMatchLines = 2^11
     uint32_t       own  = *(volatile uint32_t*)&line_key[line];
     if (own == 0) {
@@ -336,15 +369,15 @@ __device__ __forceinline__ void count_match(uint32_t idx1, uint32_t* line_key, u
     if (own == idx1)
         atomicAdd(&line_cnt[line], 1u);
     else
-        atomicAdd(&counts[idx1 - 1], 1u);
+        atomicAdd(direct, 1u);
 }
 
 // prev (optional): match[] of length n-1.  When every pattern of length n has its (n-1)-token prefix in the set (use_prefix), a window
 // whose prefix did not match cannot match either; likewise for the suffix.  This is the back-off rule of unconstrained training
 // (include/patternmodel.h:1139-1152) re-derived for sets that happen to be closed -- every model train() itself produced is.
 template <int NW>
-__global__ void __launch_bounds__(256) constrained_match_kernel(const uint32_t* __restrict__ tok, uint64_t npos, int n, const uint8_t* __restrict__ keys,
-                                                                const uint64_t* __restrict__ off, const unsigned long long* __restrict__ slots, uint64_t mask,
+__global__ void __launch_bounds__(256, NW == 4 ? 6 : 1) constrained_match_kernel(const uint32_t* __restrict__ tok, uint64_t npos, int n, const uint8_t* __restrict__ keys,
+                                                                const uint64_t* __restrict__ off, PatSlot* __restrict__ slots, uint64_t mask,
                                                                 const uint32_t* __restrict__ presence, uint64_t pmask, uint32_t* __restrict__ counts,
                                                                 uint32_t* __restrict__ match, const uint32_t* __restrict__ prev, bool use_prefix, bool use_suffix,
                                                                 DeviceStats* __restrict__ st) {
@@ -385,13 +418,14 @@ __global__ void __launch_bounds__(256) constrained_match_kernel(const uint32_t* 
             }
             if (ok) {
                 ++windows;
+                uint64_t slot = 0;
                 if (len <= kMaxIndexedKeyBytes && len < 8u * NW) {
                     if constexpr (NW == 4)
-                        idx1 = index_find4(w, len, keys, off, slots, mask, presence, pmask);
+                        idx1 = index_find4(w, len, keys, off, slots, mask, presence, pmask, slot);
                     else
-                        idx1 = index_find(w, len, keys, off, slots, mask, presence, pmask);
+                        idx1 = index_find(w, len, keys, off, slots, mask, presence, pmask, slot);
                 }
-                if (idx1) count_match(idx1, line_key, line_cnt, counts);
+                if (idx1) count_match(idx1, line_key, line_cnt, &slots[slot].count);
             }
         }
         if (match) __stcs(match + p, idx1);
@@ -435,7 +469,7 @@ __global__ void __launch_bounds__(256) constrained_unigram_kernel(const uint32_t
         if (t != 0) {
             ++windows;
             if (t < nclasses) idx1 = __ldg(uni + t);
-            if (idx1) count_match(idx1, line_key, line_cnt, counts);
+            if (idx1) count_match(idx1, line_key, line_cnt, &counts[idx1 - 1]);
         }
         if (match) __stcs(match + p, idx1);
     }
@@ -450,7 +484,7 @@ __global__ void __launch_bounds__(256) constrained_unigram_kernel(const uint32_t
 
 // closure of the set per pattern length: how many patterns of n tokens lack their (n-1)-token prefix / suffix in the set
 __global__ void __launch_bounds__(256) closure_check_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, const uint16_t* __restrict__ pn, uint64_t np,
-                                                            const unsigned long long* __restrict__ slots, uint64_t mask, const uint32_t* __restrict__ presence, uint64_t pmask,
+                                                            const PatSlot* __restrict__ slots, uint64_t mask, const uint32_t* __restrict__ presence, uint64_t pmask,
                                                             unsigned long long* __restrict__ prefix_open, unsigned long long* __restrict__ suffix_open) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
@@ -471,51 +505,91 @@ __global__ void __launch_bounds__(256) closure_check_kernel(const uint8_t* __res
     }
     uint64_t w[24];
     words_load(w, keys + a, (uint32_t)(last_start - a));
-    if (index_find(w, (uint32_t)(last_start - a), keys, off, slots, mask, presence, pmask) == 0) atomicAdd(&prefix_open[min(n, 255u)], 1ull);
+    uint64_t slot;
+    if (index_find(w, (uint32_t)(last_start - a), keys, off, slots, mask, presence, pmask, slot) == 0) atomicAdd(&prefix_open[min(n, 255u)], 1ull);
     words_load(w, keys + first_end, (uint32_t)(b - first_end));
-    if (index_find(w, (uint32_t)(b - first_end), keys, off, slots, mask, presence, pmask) == 0) atomicAdd(&suffix_open[min(n, 255u)], 1ull);
+    if (index_find(w, (uint32_t)(b - first_end), keys, off, slots, mask, presence, pmask, slot) == 0) atomicAdd(&suffix_open[min(n, 255u)], 1ull);
+}
+
+// the counts taken in the index slots go to counts[] (every pattern has exactly one slot) and the slots are ready for the next run
+__global__ void __launch_bounds__(256) collect_slot_counts_kernel(PatSlot* __restrict__ slots, uint64_t cap, uint32_t* __restrict__ counts) {
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint2 v = __ldcs(reinterpret_cast<const uint2*>(slots + s));  // {idx1, count}
+        if (v.x != 0 && v.y != 0) {
+            counts[v.x - 1] += v.y;
+            slots[s].count = 0;
+        }
+    }
 }
 
 // after the scan: found = patterns seen at least once, kept = count >= threshold, per-length sums of the kept ones
 __global__ void __launch_bounds__(256) constrained_stats_kernel(const uint32_t* __restrict__ counts, const uint16_t* __restrict__ pn, uint64_t np, uint32_t threshold,
-                                                                uint32_t* __restrict__ flags, PatternMetaStats* __restrict__ st, DeviceStats* __restrict__ ds) {
+                                                                uint32_t* __restrict__ flags, PatternMetaStats* __restrict__ st, DeviceStats* __restrict__ ds, bool per_length) {
     __shared__ unsigned long long s_kept_n[256], s_occ_n[256];
-    __shared__ unsigned long long s_found, s_kept, s_occ;
-    __shared__ uint32_t           s_maxn, s_minn;
-    s_kept_n[threadIdx.x] = 0;
-    s_occ_n[threadIdx.x]  = 0;
-    if (threadIdx.x == 0) {
-        s_found = s_kept = s_occ = 0;
-        s_maxn = 0;
-        s_minn = 0xFFFFFFFFu;
+    __shared__ uint64_t           scratch[8];
+    if (per_length) {
+        s_kept_n[threadIdx.x] = 0;
+        s_occ_n[threadIdx.x]  = 0;
+        __syncthreads();
     }
-    __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t c = counts[i], n = pn[i];
-        const bool     kept = c >= threshold;
-        flags[i] = kept ? 1u : 0u;
-        if (c > 0) atomicAdd(&s_found, 1ull);
+    // per-thread registers first, one block reduction at the end; the per-length sums (indexed models only) are aggregated per warp
+    unsigned long long found = 0, kept_c = 0, occ = 0;
+    uint32_t           maxn = 0, minn = 0xFFFFFFFFu;
+    const uint64_t     stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t     rounds = (np + stride - 1) / stride;  // the same trip count for every thread: the warp collectives below stay converged
+    for (uint64_t r = 0; r < rounds; ++r) {
+        const uint64_t i = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        uint32_t       c = 0, n = 0;
+        bool           kept = false;
+        if (i < np) {
+            c        = counts[i];
+            n        = min((uint32_t)pn[i], 255u);
+            kept     = c >= threshold;
+            flags[i] = kept ? 1u : 0u;
+            found += c > 0;
+        }
         if (kept) {
-            atomicAdd(&s_kept, 1ull);
-            atomicAdd(&s_occ, (unsigned long long)c);
-            atomicAdd(&s_kept_n[min(n, 255u)], 1ull);
-            atomicAdd(&s_occ_n[min(n, 255u)], (unsigned long long)c);
-            atomicMax(&s_maxn, n);
-            atomicMin(&s_minn, n);
+            ++kept_c;
+            occ += c;
+            maxn = max(maxn, n);
+            minn = min(minn, n);
+        }
+        if (per_length) {
+            uint32_t todo = __ballot_sync(0xffffffffu, kept);
+            while (todo) {  // one round per distinct length present in the warp (a handful)
+                const uint32_t n0   = __shfl_sync(0xffffffffu, n, __ffs(todo) - 1);
+                const bool     mine = kept && n == n0;
+                const uint32_t grp  = __ballot_sync(0xffffffffu, mine);
+                const uint64_t sum  = warp_reduce_sum(mine ? (uint64_t)c : 0ull);
+                if (lane_id() == 0) {
+                    atomicAdd(&s_kept_n[n0], (unsigned long long)__popc(grp));
+                    atomicAdd(&s_occ_n[n0], (unsigned long long)sum);
+                }
+                todo &= ~grp;
+            }
         }
     }
-    __syncthreads();
-    if (s_kept_n[threadIdx.x]) {
-        atomicAdd(&st->kept_n[threadIdx.x], s_kept_n[threadIdx.x]);
-        atomicAdd(&st->kept_occ_n[threadIdx.x], s_occ_n[threadIdx.x]);
+    const uint64_t f = block_reduce_sum(found, scratch);
+    const uint64_t k = block_reduce_sum(kept_c, scratch);
+    const uint64_t o = block_reduce_sum(occ, scratch);
+    maxn = warp_reduce_max(maxn);
+    minn = ~warp_reduce_max(~minn);
+    if (lane_id() == 0 && minn != 0xFFFFFFFFu) {
+        atomicMax(&st->kept_maxn, maxn);
+        atomicMin(&st->kept_minn, minn);
     }
     if (threadIdx.x == 0) {
-        if (s_found) atomicAdd(&ds->found, s_found);
-        if (s_kept) {
-            atomicAdd(&ds->kept, s_kept);
-            atomicAdd(&ds->kept_occ, s_occ);
-            atomicMax(&st->kept_maxn, s_maxn);
-            atomicMin(&st->kept_minn, s_minn);
+        if (f) atomicAdd(&ds->found, (unsigned long long)f);
+        if (k) {
+            atomicAdd(&ds->kept, (unsigned long long)k);
+            atomicAdd(&ds->kept_occ, (unsigned long long)o);
+        }
+    }
+    if (per_length) {
+        __syncthreads();
+        if (s_kept_n[threadIdx.x]) {
+            atomicAdd(&st->kept_n[threadIdx.x], s_kept_n[threadIdx.x]);
+            atomicAdd(&st->kept_occ_n[threadIdx.x], s_occ_n[threadIdx.x]);
         }
     }
 }
@@ -641,13 +715,13 @@ int launch_pattern_meta(cudaStream_t s, const uint8_t* keys, const uint64_t* off
     pattern_meta_kernel<<<pattern_grid(np), 256, 0, s>>>(keys, off, np, pn, pcat, st);
     return 1;
 }
-int launch_index_build(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, unsigned long long* slots, uint64_t cap_pow2, uint32_t* presence,
+int launch_index_build(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, PatSlot* slots, uint64_t cap_pow2, uint32_t* presence,
                        uint64_t presence_bits_pow2, PatternMetaStats* st) {
     if (!np) return 0;
     index_build_kernel<<<pi_div_up(np, 256), 256, 0, s>>>(keys, off, np, slots, cap_pow2 - 1, presence, presence_bits_pow2 - 1, st);
     return 1;
 }
-int launch_index_lookup(cudaStream_t s, const uint8_t* qkeys, const uint64_t* qoff, uint64_t nq, const uint8_t* keys, const uint64_t* off, const unsigned long long* slots,
+int launch_index_lookup(cudaStream_t s, const uint8_t* qkeys, const uint64_t* qoff, uint64_t nq, const uint8_t* keys, const uint64_t* off, const PatSlot* slots,
                         uint64_t cap_pow2, const uint32_t* presence, uint64_t presence_bits_pow2, uint32_t* out_idx1) {
     if (!nq) return 0;
     index_lookup_kernel<<<pi_div_up(nq, 256), 256, 0, s>>>(qkeys, qoff, nq, keys, off, slots, cap_pow2 - 1, presence, presence_bits_pow2 - 1, out_idx1);
@@ -658,16 +732,31 @@ int launch_gather_counts(cudaStream_t s, const uint32_t* idx1, uint64_t nq, cons
     gather_counts_kernel<<<pi_div_up(nq, 256), 256, 0, s>>>(idx1, nq, counts, out);
     return 1;
 }
-int launch_constrained_match(cudaStream_t s, const uint32_t* tok, uint64_t npos, int n, const uint8_t* keys, const uint64_t* off, const unsigned long long* slots, uint64_t cap_pow2,
+static int match_blocks_per_sm(const void* fn) {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, 256, 0);
+    return n > 0 ? n : 1;
+}
+int launch_constrained_match(cudaStream_t s, const uint32_t* tok, uint64_t npos, int n, const uint8_t* keys, const uint64_t* off, PatSlot* slots, uint64_t cap_pow2,
                              const uint32_t* presence, uint64_t presence_bits_pow2, uint32_t* counts, uint32_t* match, const uint32_t* prev, bool use_prefix, bool use_suffix,
                              DeviceStats* st, int sms) {
     if (!npos) return 0;
-    const unsigned grid = (unsigned)std::min<uint64_t>(pi_div_up(npos, 256), (uint64_t)sms * 8);  // resident blocks only: each owns one count cache
     if (prev == nullptr) use_prefix = use_suffix = false;
-    if (n * 5 < 8 * 4)  // every window of n tokens fits 31 bytes: registers only
+    // resident blocks only (each owns one count cache), exactly as many as fit: a partial second wave would idle half the machine
+    if (n * 5 < 8 * 4) {  // every window of n tokens fits 31 bytes: registers only
+        static int     bps  = getenv("COLIBRI_B200_MATCH_BPS") ? atoi(getenv("COLIBRI_B200_MATCH_BPS")) : match_blocks_per_sm((const void*)constrained_match_kernel<4>);
+        const unsigned grid = (unsigned)std::min<uint64_t>(pi_div_up(npos, 256), (uint64_t)sms * bps);
         constrained_match_kernel<4><<<grid, 256, 0, s>>>(tok, npos, n, keys, off, slots, cap_pow2 - 1, presence, presence_bits_pow2 - 1, counts, match, prev, use_prefix, use_suffix, st);
-    else
+    } else {
+        static int     bps  = match_blocks_per_sm((const void*)constrained_match_kernel<24>);
+        const unsigned grid = (unsigned)std::min<uint64_t>(pi_div_up(npos, 256), (uint64_t)sms * bps);
         constrained_match_kernel<24><<<grid, 256, 0, s>>>(tok, npos, n, keys, off, slots, cap_pow2 - 1, presence, presence_bits_pow2 - 1, counts, match, prev, use_prefix, use_suffix, st);
+    }
+    return 1;
+}
+int launch_collect_slot_counts(cudaStream_t s, PatSlot* slots, uint64_t cap_pow2, uint32_t* counts) {
+    if (!cap_pow2) return 0;
+    collect_slot_counts_kernel<<<(unsigned)std::min<uint64_t>(pi_div_up(cap_pow2, 256), 148 * 16), 256, 0, s>>>(slots, cap_pow2, counts);
     return 1;
 }
 int launch_unigram_table(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint16_t* pn, uint64_t np, uint32_t* uni, uint32_t nclasses) {
@@ -681,15 +770,16 @@ int launch_constrained_unigrams(cudaStream_t s, const uint32_t* tok, uint64_t np
     constrained_unigram_kernel<<<grid, 256, 0, s>>>(tok, npos, uni, nclasses, counts, match, st);
     return 1;
 }
-int launch_closure_check(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint16_t* pn, uint64_t np, const unsigned long long* slots, uint64_t cap_pow2,
+int launch_closure_check(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint16_t* pn, uint64_t np, const PatSlot* slots, uint64_t cap_pow2,
                          const uint32_t* presence, uint64_t presence_bits_pow2, unsigned long long* prefix_open, unsigned long long* suffix_open) {
     if (!np) return 0;
     closure_check_kernel<<<pi_div_up(np, 256), 256, 0, s>>>(keys, off, pn, np, slots, cap_pow2 - 1, presence, presence_bits_pow2 - 1, prefix_open, suffix_open);
     return 1;
 }
-int launch_constrained_stats(cudaStream_t s, const uint32_t* counts, const uint16_t* pn, uint64_t np, uint32_t threshold, uint32_t* flags, PatternMetaStats* st, DeviceStats* ds) {
+int launch_constrained_stats(cudaStream_t s, const uint32_t* counts, const uint16_t* pn, uint64_t np, uint32_t threshold, uint32_t* flags, PatternMetaStats* st, DeviceStats* ds,
+                             bool per_length) {
     if (!np) return 0;
-    constrained_stats_kernel<<<pattern_grid(np), 256, 0, s>>>(counts, pn, np, threshold, flags, st, ds);
+    constrained_stats_kernel<<<pattern_grid(np), 256, 0, s>>>(counts, pn, np, threshold, flags, st, ds, per_length);
     return 1;
 }
 int launch_load_filter(cudaStream_t s, const uint16_t* pn, const uint8_t* pcat, const uint32_t* counts, const uint32_t* constrain_idx1, uint64_t np, uint32_t mintokens,

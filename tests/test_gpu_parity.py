@@ -270,3 +270,32 @@ def test_gpu_indexed_skipgrams_equal_oracle_on_random_input(seed):
     assert (got.tokens, got.types, len(got), got.maxn, got.minn, got.hasskipgrams) == (want.tokens, want.types, len(want), want.maxn, want.minn, want.hasskipgrams), kw
     assert got.passes == want.passes
     assert got.same_patterns(want)
+
+
+@pytest.mark.parametrize("dense", [8, 40, 3000, 100000])
+def test_gpu_dense_pairs_match_oracle(golden, dense, monkeypatch):
+    """Level 2 with directly addressed slots for pairs of frequent classes (count_ngrams_kernel, `dense`): forced on for small corpora and
+    for several sizes of the square, so that windows split between the dense and the hashed part of the table in different ways."""
+    monkeypatch.setenv("COLIBRI_B200_DENSE_MIN", "0")
+    monkeypatch.setenv("COLIBRI_B200_DENSE", str(dense))
+    runs = [
+        ("hamlet", dict(mintokens=2, maxlength=5, streamed=1)),
+        ("hamlet", dict(mintokens=1, maxlength=3, streamed=1)),
+        ("hamlet", dict(mintokens=2, maxlength=4, indexed=1, streamed=0)),
+        ("hamlet", dict(mintokens=2, maxlength=5, doskipgrams_exhaustive=1, streamed=0)),
+        ("hamlet", dict(mintokens=2, maxlength=5, indexed=1, doskipgrams=1, streamed=0)),
+        ("threebyte", dict(mintokens=2, maxlength=5, streamed=1)),
+        ("republic", dict(mintokens=2, maxlength=5, streamed=1)),
+        ("republic", dict(mintokens=3, maxlength=4, indexed=1, streamed=0)),
+        ("zipf300k_phr", dict(mintokens=2, maxlength=5, doskipgrams_exhaustive=1, streamed=0)),
+        ("zipf2m", dict(mintokens=2, maxlength=5, streamed=1)),
+    ]
+    for name, okw in runs:
+        body = corpus_body(golden, name)
+        want = oracle.train(body, **okw)
+        o = cb().PatternModelOptions(MINTOKENS=okw["mintokens"], MAXLENGTH=okw["maxlength"], DOSKIPGRAMS_EXHAUSTIVE=okw.get("doskipgrams_exhaustive", 0),
+                                     DOSKIPGRAMS=okw.get("doskipgrams", 0), model_type=20 if okw.get("indexed") else 10, streamed=okw["streamed"], QUIET=1)
+        m = cb().train(body, o)
+        assert (m.tokens(), m.types(), len(m)) == (want.tokens, want.types, len(want)), (name, okw)
+        assert m.passes() == want.passes, (name, okw)
+        assert to_flat(m).same_patterns(want), (name, okw)

@@ -281,7 +281,7 @@ def run_ours(a):
                    "timing": "max(torch CUDA events, wall clock) around K synchronous ABI calls"},
         "device_ms_per_step": sum(dev_ms) / len(dev_ms),
         "phase_ms_per_step": {k: v / a.steps for k, v in phase_ms.items()},
-        "roofline": {"bound": "hbm", "kernel": "ngram_filter_kernel + count_ngrams_kernel (levels 2..%d)" % last.maxlength(), "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "ngram_filter_kernel + count_ngrams_kernel (levels 2..%d; level 2 with dense pair slots)" % last.maxlength(), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "alg_bytes_per_step": alg_bytes / a.steps, "kernel_ms_per_step": count_ms / a.steps,
                      "kernel_share_of_step": (count_ms / a.steps) / (sum(dev_ms) / len(dev_ms)),
                      "traffic": traffic["dram_bytes_per_step"] if traffic else None,

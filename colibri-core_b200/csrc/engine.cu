@@ -823,6 +823,8 @@ int Trainer::run_constrained(colibri_b200_model* cm, bool inplace) {
     // match[k][p] = pattern (index + 1) of the window of lengths[k] tokens at p.  Indexed models keep every level (the occurrence lists are
     // built from them); otherwise two buffers alternate: level n only looks at level n-1, to skip windows whose prefix / suffix did not match
     const bool chain = !getenv("COLIBRI_B200_NO_CHAIN");
+    DevBuf<uint32_t> count1_scratch;
+    uint64_t         unigram_windows = 0;
     std::vector<DevBuf<uint32_t>> match(indexed ? lengths.size() : std::min<size_t>(lengths.size(), 2));
     for (auto& mb : match) {
         TRY(mb.alloc(dev, npos + 8));
@@ -837,9 +839,16 @@ int Trainer::run_constrained(colibri_b200_model* cm, bool inplace) {
         const bool use_prefix = prev && cm->prefix_open[n] == 0, use_suffix = prev && cm->suffix_open[n] == 0;
         if (!indexed && !(k + 1 < lengths.size() && lengths[k + 1] == n + 1 && chain)) cur = nullptr;  // nobody will read it
         int hc = timer.begin(COLIBRI_T_COUNT, n);
-        if (n == 1 && cm->uni_classes)
-            launches += launch_constrained_unigrams(s, tok.p, npos, cm->d_uni.p, cm->uni_classes, counts.p, cur, d_stats.p, sms);
-        else
+        if (n == 1 && cm->uni_classes) {
+            // the class histogram of unconstrained training, handed to the unigram patterns
+            DevBuf<uint32_t>& hist = count1_scratch;
+            TRY(hist.alloc(dev, nclasses));
+            CUDA_TRY(cudaMemsetAsync(hist.p, 0, (size_t)nclasses * sizeof(uint32_t), s));
+            launches += launch_unigram_hist(s, tok.p, npos, hist.p, nclasses, sms);
+            launches += launch_unigram_apply(s, hist.p, cm->d_uni.p, std::min<uint32_t>(nclasses, cm->uni_classes), counts.p);
+            if (cur) launches += launch_unigram_match(s, tok.p, npos, cm->d_uni.p, cm->uni_classes, cur);
+            unigram_windows = corpus_tokens;
+        } else
             launches += launch_constrained_match(s, tok.p, npos, n, cm->d_keys.p, cm->d_off.p, cm->d_index.p, cm->index_cap, cm->d_presence.p, cm->presence_bits, counts.p, cur,
                                                  prev, use_prefix, use_suffix, d_stats.p, sms);
         timer.end(hc);
@@ -851,7 +860,7 @@ int Trainer::run_constrained(colibri_b200_model* cm, bool inplace) {
     }
     TRY(read_stats());
     cm->index_counts_dirty = false;
-    ngram_upserts = h_stats.valid_windows;
+    ngram_upserts = h_stats.valid_windows + unigram_windows;
 
     // ---- threshold (prune(MINTOKENS, 0)) and the numbers of the progress line
     DevBuf<PatternMetaStats> d_pst;

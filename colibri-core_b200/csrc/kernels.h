@@ -171,7 +171,9 @@ int launch_constrained_match(cudaStream_t s, const uint32_t* tok, uint64_t npos,
                              DeviceStats* st, int sms);
 // uni[class] = index + 1 of the unigram pattern of that class (uni zeroed by the caller, nclasses entries)
 int launch_unigram_table(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint16_t* pn, uint64_t np, uint32_t* uni, uint32_t nclasses);
-int launch_constrained_unigrams(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* uni, uint32_t nclasses, uint32_t* counts, uint32_t* match, DeviceStats* st, int sms);
+// level 1 of a constrained run: counts[uni[c] - 1] += hist[c] for c < nclasses (hist = launch_unigram_hist's class histogram); match[p] = uni[tok[p]]
+int launch_unigram_apply(cudaStream_t s, const uint32_t* hist, const uint32_t* uni, uint32_t nclasses, uint32_t* counts);
+int launch_unigram_match(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* uni, uint32_t nclasses, uint32_t* match);
 // per pattern length n (bins of 256, zeroed by the caller): patterns whose (n-1)-token prefix / suffix is not in the set
 // counts[pattern] += the slot counters of a constrained run, which are reset
 int launch_collect_slot_counts(cudaStream_t s, PatSlot* slots, uint64_t cap_pow2, uint32_t* counts);

@@ -453,33 +453,20 @@ __global__ void __launch_bounds__(256) unigram_table_kernel(const uint8_t* __res
     if (cls >= nclasses || varint_len((uint32_t)cls) != l) return;
     uni[cls] = (uint32_t)i + 1;
 }
-__global__ void __launch_bounds__(256) constrained_unigram_kernel(const uint32_t* __restrict__ tok, uint64_t npos, const uint32_t* __restrict__ uni, uint32_t nclasses,
-                                                                  uint32_t* __restrict__ counts, uint32_t* __restrict__ match, DeviceStats* __restrict__ st) {
-    __shared__ uint32_t line_key[kMatchLines];
-    __shared__ uint32_t line_cnt[kMatchLines];
-    for (uint32_t i = threadIdx.x; i < kMatchLines; i += blockDim.x) {
-        line_key[i] = 0;
-        line_cnt[i] = 0;
-    }
-    __syncthreads();
-    unsigned long long windows = 0;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t t = __ldcs(tok + p);
-        uint32_t       idx1 = 0;
-        if (t != 0) {
-            ++windows;
-            if (t < nclasses) idx1 = __ldg(uni + t);
-            if (idx1) count_match(idx1, line_key, line_cnt, &counts[idx1 - 1]);
-        }
-        if (match) __stcs(match + p, idx1);
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < kMatchLines; i += blockDim.x) {
-        const uint32_t c = line_cnt[i];
-        if (c) atomicAdd(&counts[line_key[i] - 1], c);
-    }
-    windows = warp_reduce_sum(windows);
-    if (lane_id() == 0 && windows) atomicAdd(&st->valid_windows, windows);
+// level 1 of a constrained run = the class histogram of unconstrained training (unigram_hist_kernel, kernels.cu) handed to the unigram
+// patterns: counts[uni[c] - 1] += hist[c]; the per-position matches (only needed when level 2 chains on them) are one streaming pass
+__global__ void __launch_bounds__(256) unigram_apply_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ uni, uint32_t nclasses, uint32_t* __restrict__ counts) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nclasses) return;
+    const uint32_t idx1 = uni[c], h = hist[c];
+    if (idx1 != 0 && h != 0) counts[idx1 - 1] += h;  // a class has at most one unigram pattern
+}
+__global__ void __launch_bounds__(256) unigram_match_kernel(const uint32_t* __restrict__ tok, uint64_t npos, const uint32_t* __restrict__ uni, uint32_t nclasses,
+                                                            uint32_t* __restrict__ match) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npos) return;
+    const uint32_t t = __ldcs(tok + p);
+    __stcs(match + p, (t != 0 && t < nclasses) ? __ldg(uni + t) : 0u);
 }
 
 // closure of the set per pattern length: how many patterns of n tokens lack their (n-1)-token prefix / suffix in the set
@@ -764,10 +751,14 @@ int launch_unigram_table(cudaStream_t s, const uint8_t* keys, const uint64_t* of
     unigram_table_kernel<<<pi_div_up(np, 256), 256, 0, s>>>(keys, off, pn, np, uni, nclasses);
     return 1;
 }
-int launch_constrained_unigrams(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* uni, uint32_t nclasses, uint32_t* counts, uint32_t* match, DeviceStats* st, int sms) {
+int launch_unigram_apply(cudaStream_t s, const uint32_t* hist, const uint32_t* uni, uint32_t nclasses, uint32_t* counts) {
+    if (!nclasses) return 0;
+    unigram_apply_kernel<<<pi_div_up(nclasses, 256), 256, 0, s>>>(hist, uni, nclasses, counts);
+    return 1;
+}
+int launch_unigram_match(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* uni, uint32_t nclasses, uint32_t* match) {
     if (!npos) return 0;
-    const unsigned grid = (unsigned)std::min<uint64_t>(pi_div_up(npos, 256), (uint64_t)sms * 8);
-    constrained_unigram_kernel<<<grid, 256, 0, s>>>(tok, npos, uni, nclasses, counts, match, st);
+    unigram_match_kernel<<<pi_div_up(npos, 256), 256, 0, s>>>(tok, npos, uni, nclasses, match);
     return 1;
 }
 int launch_closure_check(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint16_t* pn, uint64_t np, const PatSlot* slots, uint64_t cap_pow2,

@@ -83,6 +83,32 @@ int main(int argc, char** argv) {
             threw = true;
         }
         test("continued training is refused", threw, true);
+        // loading and constrained training keep the reference's signatures (include/patternmodel.h:700-726, :781-861, :880)
+        threw = false;
+        try {
+            PatternModel<uint32_t> missing(std::string("/nonexistent.colibri.patternmodel"), o);
+        } catch (const InternalError&) {
+            threw = true;
+        }
+        test("loading a missing model file throws InternalError", threw, true);
+        threw = false;
+        try {
+            IndexedPatternModel<> notamodel(std::string(argv[1]), o);  // a corpus file is not a model file (reference :788-793)
+        } catch (const InternalError&) {
+            threw = true;
+        }
+        test("loading a file that is not a model throws InternalError", threw, true);
+        if (colibri_b200_device_count() == 0) {
+            PatternSetModel        constraint;  // an empty set still has to go through the device
+            PatternModel<uint32_t> model3;
+            threw = false;
+            try {
+                model3.train(std::string(argv[1]), o, constraint.getinterface());
+            } catch (const InternalError&) {
+                threw = true;
+            }
+            test("constrained train() without a GPU throws InternalError", threw, true);
+        }
     }
     std::cerr << "all " << testnr << " host API tests ok" << std::endl;
     return 0;

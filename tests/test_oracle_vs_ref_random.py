@@ -75,3 +75,46 @@ def test_oracle_equals_reference_on_random_input(seed):
     assert (mine.tokens, mine.types, len(mine), mine.maxn, mine.minn, int(mine.hasskipgrams)) == (st["tokens"], st["types"], st["patterns"], st["maxn"], st["minn"], st["hasskipgrams"]), (cli, unindexed, skipgrams)
     assert [(p[1], p[3]) for p in mine.passes] == [(p[0], p[2]) for p in oracle.parse_ref_passes(err)]
     assert mine.same_patterns(ref)
+
+
+# ---- training under a constraint model and model loading with the options as filters (8f-3): the oracle against the
+# ---- UNMODIFIED reference CLI (oracle/_ref/colibri-patternmodeller -j / -i -I)
+def _plain_corpus(rng, vocab_choices):
+    sentences = []
+    for _ in range(rng.randint(1, 60)):
+        n = rng.randint(0, rng.choice([4, 12, 30]))
+        sentences.append([6 + min(int(rng.paretovariate(1.1)) - 1, rng.choice(vocab_choices) - 1) if rng.random() < 0.9 else 6 + rng.randrange(max(vocab_choices)) for _ in range(n)])
+    body = oracle.encode_corpus(sentences)
+    return body if body.strip(b"\0") else bytes([6, 7, 0])
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_oracle_constrained_equals_reference_cli_on_random_input(seed):
+    rng = random.Random(5000 + seed)
+    body = _plain_corpus(rng, [5, 30, 200, 20000])
+    body2 = body if rng.random() < 0.5 else _plain_corpus(rng, [5, 30, 200])
+    t1, l1, m1, idx1 = rng.choice([1, 2, 2, 3]), rng.choice([1, 2, 3, 5, 8]), rng.choice([1, 1, 1, 2]), rng.random() < 0.4
+    t, l, m = rng.choice([1, 2, 2, 3]), rng.choice([1, 2, 3, 5, 8, 100]), rng.choice([1, 1, 1, 2, 3])
+    indexed, inplace = rng.random() < 0.5, rng.random() < 0.5
+    with tempfile.TemporaryDirectory() as td:
+        cpath, c2path, s1, out = (os.path.join(td, x) for x in ("c.colibri.dat", "c2.colibri.dat", "s1.model", "out.model"))
+        for path, b in ((cpath, body), (c2path, body2)):
+            with open(path, "wb") as f:
+                f.write(b"\xa2\x02" + b)
+        rc, err = oracle.ref_cli(["-f", c2path, "-t", t1, "-l", l1, "-m", m1, "-o", s1] + ([] if idx1 else ["-u"]), timeout=60)
+        assert rc == 0, err
+        args = ["-f", cpath] + (["-i", s1, "-I"] if inplace else ["-j", s1]) + ["-t", t, "-l", l, "-m", m, "-o", out] + ([] if indexed else ["-u"])
+        rc, err = oracle.ref_cli(args, timeout=60)
+        assert rc == 0, err
+        ref = oracle.parse_modelfile(open(out, "rb").read())
+        stage1 = open(s1, "rb").read()
+    if inplace:  # src/patternmodeller.cpp:804-821: load AS the output type with DORESET, widen the length window, corpus preloaded
+        cm = oracle.load_model(stage1, mintokens=t, minlength=m, maxlength=l, doreset=1, indexed=int(indexed))
+        f = cm.flat()
+        mine = oracle.train_constrained(body, cm, inplace=True, mintokens=t, maxlength=max(l, f.maxn), minlength=min(m, f.minn), indexed=int(indexed), streamed=0)
+    else:  # :713-721 PatternSetModel(file, options); an unindexed output model streams the corpus
+        cm = oracle.load_model(stage1, mintokens=t, minlength=m, maxlength=l, indexed=0)
+        mine = oracle.train_constrained(body, cm, inplace=False, mintokens=t, maxlength=l, minlength=m, indexed=int(indexed), streamed=0 if indexed else 1)
+    assert (mine.tokens, mine.types, len(mine)) == (ref.tokens, ref.types, len(ref)), args
+    assert [(p[1], p[3]) for p in mine.passes] == [(p[0], p[2]) for p in oracle.parse_ref_passes(err)], args
+    assert mine.same_patterns(ref), args

@@ -129,6 +129,8 @@ def lib():
     L.oracle_model_from_keys.restype = C.c_int
     L.oracle_train_constrained.argtypes = [_u8p, C.c_size_t, C.POINTER(Options), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     L.oracle_train_constrained.restype = C.c_int
+    L.oracle_computeflexgrams_fromskipgrams.argtypes = [C.c_void_p]
+    L.oracle_computeflexgrams_fromskipgrams.restype = C.c_int64
     L.oracle_inttobytes.argtypes = [_u8p, C.c_uint32]
     L.oracle_inttobytes.restype = C.c_uint
     L.oracle_bytestoint.argtypes = [_u8p, C.POINTER(C.c_uint)]
@@ -175,6 +177,7 @@ class FlatModel:
     ref_token: np.ndarray | None = None
     ref_off: np.ndarray | None = None
     passes: list = field(default_factory=list)  # [(n, found_ngrams, found_skipgrams, pruned)]
+    flexfound: int = 0  # new flexgrams of computeflexgrams_fromskipgrams (train(..., flexfromskip=1))
 
     def __len__(self):
         return len(self.counts)
@@ -230,6 +233,17 @@ class FlatModel:
                 rs, rt = self.ref_sentence[:0], self.ref_token[:0]
         return FlatModel(new_keys, new_off, self.counts[order], self.tokens, self.types, self.maxn, self.minn, self.hasskipgrams, self.model_type, rs, rt, ro,
                          list(self.passes))
+
+    def sorted_refs(self) -> "FlatModel":
+        """Canonical copy whose occurrence lists are ascending inside every pattern (flexgram lists of the reference are in insertion order)."""
+        c = self.canonical()
+        if c.ref_off is None or len(c) == 0:
+            return c
+        ro = c.ref_off.astype(np.int64)
+        owner = np.repeat(np.arange(len(c)), np.diff(ro))
+        order = np.lexsort((c.ref_token, c.ref_sentence, owner))
+        return FlatModel(c.keys, c.key_off, c.counts, c.tokens, c.types, c.maxn, c.minn, c.hasskipgrams, c.model_type, c.ref_sentence[order], c.ref_token[order], c.ref_off,
+                         list(c.passes), c.flexfound)
 
     def same_patterns(self, other: "FlatModel") -> bool:
         a, b = self.canonical(), other.canonical()
@@ -288,8 +302,9 @@ def _flat_from_handle(h, indexed: bool) -> FlatModel:
                      bool(L.oracle_model_hasskipgrams(h)), 20 if indexed else 10, rs, rt, ro, passes)
 
 
-def train(corpus, **kw) -> FlatModel:
-    """Run the C restatement on the body of a .colibri.dat (bytes after the 2-byte header)."""
+def train(corpus, flexfromskip=0, **kw) -> FlatModel:
+    """Run the C restatement on the body of a .colibri.dat (bytes after the 2-byte header).  flexfromskip: follow up with
+    computeflexgrams_fromskipgrams (include/patternmodel.h:3724-3744), as the CLI's `-F S` does."""
     L = lib()
     data = _as_u8(corpus)
     o = default_options(**kw)
@@ -298,7 +313,14 @@ def train(corpus, **kw) -> FlatModel:
     if rc != 0:
         raise RuntimeError("oracle_train: " + L.oracle_last_error().decode())
     try:
-        return _flat_from_handle(h, bool(o.indexed))
+        found = 0
+        if flexfromskip:
+            found = int(L.oracle_computeflexgrams_fromskipgrams(h))
+            if found < 0:
+                raise RuntimeError("oracle_computeflexgrams_fromskipgrams: " + L.oracle_last_error().decode())
+        fm = _flat_from_handle(h, bool(o.indexed))
+        fm.flexfound = found
+        return fm
     finally:
         L.oracle_model_free(h)
 

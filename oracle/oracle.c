@@ -211,6 +211,7 @@ struct oracle_model {
     int      indexed;
     uint64_t totaltokens, totaltypes;
     int      maxn, minn, hasskipgrams;
+    int      hasflexgrams;
     int      npasses;
     uint64_t pass[128][4];
 };
@@ -997,6 +998,96 @@ int oracle_model_from_keys(const uint8_t* keys, const uint64_t* key_off, uint64_
     model_postread(m);
     *out = m;
     return 0;
+}
+
+/* IndexedPatternModel::computeflexgrams_fromskipgrams (include/patternmodel.h:3724-3744): every skipgram of the model is abstracted to its
+ * flexgram (Pattern::toflexgram, src/pattern.cpp:145-180: each run of gap tokens 0x03 becomes ONE dynamic gap 0x04) and hands all its
+ * occurrences to it; returns the number of flexgrams that were not in the model before.  Restated with CLEAN iteration semantics: the
+ * skipgrams are visited once each (the reference inserts into the unordered_map it iterates over).  The reference appends the
+ * occurrences in iteration order and never sorts them; here every flexgram's list ends up ascending -- compare them as multisets. */
+static uint32_t key_toflexgram(const uint8_t* key, uint32_t len, uint8_t* out) {
+    uint32_t j = 0;
+    int      skipgap = 0, prevhigh = 0;
+    for (uint32_t i = 0; i < len; ++i) {
+        uint8_t c = key[i];
+        if (!prevhigh && c == 3) {
+            if (!skipgap) {
+                out[j++] = 4;
+                skipgap  = 1;
+            }
+        } else {
+            out[j++] = c;
+            skipgap  = 0;
+        }
+        prevhigh = c >= 128;
+    }
+    return j;
+}
+int64_t oracle_computeflexgrams_fromskipgrams(oracle_model* m) {
+    if (!m->indexed) {
+        fail("computeflexgrams_fromskipgrams needs an indexed model");
+        return -1;
+    }
+    /* snapshot of the skipgrams: (key copy, refs copy), since inserting may move the table */
+    uint64_t nsk = 0;
+    for (uint64_t i = 0; i < m->st.cap; ++i)
+        if (m->st.tab[i].used && m->st.tab[i].skipgram == 1)
+            ++nsk;
+    uint8_t** keys  = (uint8_t**)malloc((nsk + 1) * sizeof(uint8_t*));
+    uint32_t* lens  = (uint32_t*)malloc((nsk + 1) * sizeof(uint32_t));
+    uint64_t** refs = (uint64_t**)malloc((nsk + 1) * sizeof(uint64_t*));
+    uint32_t* cnts  = (uint32_t*)malloc((nsk + 1) * sizeof(uint32_t));
+    uint16_t* ns    = (uint16_t*)malloc((nsk + 1) * sizeof(uint16_t));
+    uint64_t  k     = 0;
+    for (uint64_t i = 0; i < m->st.cap; ++i) {
+        entry* e = &m->st.tab[i];
+        if (!e->used || e->skipgram != 1)
+            continue;
+        keys[k] = (uint8_t*)malloc(e->len + 1);
+        memcpy(keys[k], m->st.arena + e->keyoff, e->len);
+        lens[k] = e->len;
+        cnts[k] = e->count;
+        ns[k]   = e->n;
+        refs[k] = (uint64_t*)malloc(((size_t)e->count + 1) * sizeof(uint64_t));
+        memcpy(refs[k], e->refs, (size_t)e->count * sizeof(uint64_t));
+        ++k;
+    }
+    int64_t found = 0;
+    uint8_t flex[1024];
+    for (uint64_t i = 0; i < nsk; ++i) {
+        if (lens[i] > sizeof flex)
+            continue;
+        uint32_t fl = key_toflexgram(keys[i], lens[i], flex);
+        uint64_t h  = oracle_pattern_hash(flex, fl);
+        entry*   e  = store_find(&m->st, flex, fl, h);
+        if (!e) {
+            uint16_t n;
+            uint8_t  cat;
+            key_shape(flex, fl, &n, &cat);
+            e = store_insert(&m->st, flex, fl, h, n, 2);
+            ++found;
+        }
+        for (uint32_t j = 0; j < cnts[i]; ++j)
+            entry_add(e, 1, (uint32_t)(refs[i][j] >> 16), (uint16_t)(refs[i][j] & 0xFFFF));
+    }
+    for (uint64_t i = 0; i < m->st.cap; ++i)
+        if (m->st.tab[i].used && m->st.tab[i].skipgram == 2 && m->st.tab[i].count > 1)
+            qsort(m->st.tab[i].refs, m->st.tab[i].count, sizeof(uint64_t), cmp_u64);
+    if (found)
+        m->hasflexgrams = 1;
+    for (uint64_t i = 0; i < nsk; ++i) {
+        free(keys[i]);
+        free(refs[i]);
+    }
+    free(keys);
+    free(lens);
+    free(refs);
+    free(cnts);
+    free(ns);
+    return found;
+}
+int oracle_model_hasflexgrams(const oracle_model* m) {
+    return m->hasflexgrams;
 }
 
 /* PatternModel::train with constrainbymodel != NULL (include/patternmodel.h:880-1345): ONE scan of the corpus

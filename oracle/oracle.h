@@ -96,6 +96,11 @@ int         oracle_model_from_keys(const uint8_t* keys, const uint64_t* key_off,
 /* train() under a constraint model (include/patternmodel.h:880-1345, constrainbymodel != NULL); inplace = (constrainbymodel == this) */
 int         oracle_train_constrained(const uint8_t* corpus, size_t nbytes, const oracle_options* opt, const oracle_model* constrain, int inplace, oracle_model** out);
 
+/* IndexedPatternModel::computeflexgrams_fromskipgrams (include/patternmodel.h:3724-3744) on an indexed model that holds skipgrams:
+ * returns the number of new flexgrams (-1 on error); every flexgram's occurrence list comes out ascending. */
+int64_t     oracle_computeflexgrams_fromskipgrams(oracle_model* m);
+int         oracle_model_hasflexgrams(const oracle_model* m);
+
 /* Codec + hash + masks (the L1 layer). */
 unsigned    oracle_inttobytes(uint8_t* buf, uint32_t cls);               /* src/classencoder.cpp:22-42 */
 uint32_t    oracle_bytestoint(const uint8_t* a, unsigned* length);        /* src/classdecoder.cpp:20-43 */

@@ -73,3 +73,20 @@ def test_load_filters(golden):
     assert oracle.load_model(iblob, indexed=1).flat().same_patterns(oracle.train(body, mintokens=2, maxlength=3, indexed=1, streamed=0))
     lost = oracle.load_model(oracle.train_to_modelfile(body, mintokens=2, maxlength=3), indexed=1).flat()
     assert len(lost) == 81 and int(lost.counts.sum()) == 0
+
+
+# ---- flexgrams abstracted from skipgrams (first piece): tests/golden/golden_flex.json, written by make_golden_flex.py
+import json  # noqa: E402
+import os  # noqa: E402
+
+from conftest import GOLDEN_DIR  # noqa: E402
+
+FLEX_CASES = json.load(open(os.path.join(GOLDEN_DIR, "golden_flex.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", FLEX_CASES, ids=["%s-%s" % (c["corpus"], "".join("%s%s" % kv for kv in sorted(c["cli"].items())) or "default") for c in FLEX_CASES])
+def test_oracle_flexgrams_fromskipgrams_match_reference_cli(golden, case):
+    """computeflexgrams_fromskipgrams (include/patternmodel.h:3724-3744); reference KAT src/test.cpp:1440-1443: 22 found, 155 patterns."""
+    m = oracle.train(corpus_body(golden, case["corpus"]), flexfromskip=1, **case["options"])
+    assert (m.flexfound, len(m), m.tokens, m.types, int(m.counts.sum())) == (case["flexfound"], case["patterns"], case["tokens"], case["types"], case["occurrences"])
+    assert m.sorted_refs().digest() == case["digest_sorted_refs"]

@@ -39,11 +39,15 @@ $(LIBDIR)/pattern_index.o: $(CSRC)/pattern_index.cu $(CSRC)/kernels.h $(CSRC)/de
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/pattern_index.ptxas.log || (cat $(LIBDIR)/pattern_index.ptxas.log; false)
 
+$(LIBDIR)/flexgrams.o: $(CSRC)/flexgrams.cu $(CSRC)/kernels.h $(CSRC)/engine_common.h $(CSRC)/device_utils.cuh include/colibri_b200.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/flexgrams.ptxas.log || (cat $(LIBDIR)/flexgrams.ptxas.log; false)
+
 $(LIBDIR)/model_io.o: $(CSRC)/model_io.cu $(CSRC)/kernels.h $(CSRC)/engine_common.h include/colibri_b200.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/model_io.ptxas.log || (cat $(LIBDIR)/model_io.ptxas.log; false)
 
-$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o $(LIBDIR)/index.o $(LIBDIR)/shard_kernels.o $(LIBDIR)/pattern_index.o $(LIBDIR)/model_io.o
+$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o $(LIBDIR)/index.o $(LIBDIR)/shard_kernels.o $(LIBDIR)/pattern_index.o $(LIBDIR)/model_io.o $(LIBDIR)/flexgrams.o
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^
 
 oracle:

@@ -99,6 +99,9 @@ def library():
                                                C.POINTER(C.c_void_p)]
     L.colibri_b200_model_load.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(COptions), C.c_void_p, C.POINTER(C.c_void_p)]
     L.colibri_b200_train_constrained.argtypes = [C.c_void_p, C.POINTER(COptions), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.colibri_b200_model_flexgrams_fromskipgrams.argtypes = [C.c_void_p, _u64p, C.POINTER(C.c_void_p)]
+    L.colibri_b200_model_hasflexgrams.argtypes = [C.c_void_p]
+    L.colibri_b200_model_hasflexgrams.restype = C.c_int
     L.colibri_b200_model_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.colibri_b200_model_counters.argtypes = [C.c_void_p, _u64p]
     L.colibri_b200_model_level_counters.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
@@ -273,6 +276,17 @@ class Model:
     @property
     def hasskipgrams(self):
         return bool(library().colibri_b200_model_hasskipgrams(self._h))
+
+    @property
+    def hasflexgrams(self):
+        return bool(library().colibri_b200_model_hasflexgrams(self._h))
+
+    def flexgrams_fromskipgrams(self):
+        """IndexedPatternModel::computeflexgrams_fromskipgrams: (number of new flexgrams, a new Model = this one + the flexgrams)."""
+        found = C.c_uint64()
+        h = C.c_void_p()
+        _check(library().colibri_b200_model_flexgrams_fromskipgrams(self._h, C.byref(found), C.byref(h)))
+        return int(found.value), Model(h)
 
     @property
     def model_type(self):

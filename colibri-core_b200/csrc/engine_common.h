@@ -215,7 +215,7 @@ struct colibri_b200_model {
     int      model_type = COLIBRI_UNINDEXEDPATTERNMODEL;
     uint64_t npatterns = 0, keybytes = 0, nrefs = 0;
     uint64_t totaltokens = 0, totaltypes = 0;
-    int      maxn = 0, minn = 999, hasskipgrams = 0;
+    int      maxn = 0, minn = 999, hasskipgrams = 0, hasflexgrams = 0;
     std::vector<PassStat> passes;
     // device-resident flat export
     DevBuf<uint8_t>  d_keys;

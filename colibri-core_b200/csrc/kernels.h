@@ -159,8 +159,9 @@ struct alignas(32) PatSlot {
     unsigned long long k0, k1, k2;
 };
 // slots: cap_pow2 zeroed entries; presence: presence_bits_pow2 zeroed bits, one per hash bucket
+// rep == NULL: equal keys are an error (st->duplicates); rep != NULL: group-by mode, rep[i] = index of the copy of key i that claimed the slot
 int launch_index_build(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, PatSlot* slots, uint64_t cap_pow2, uint32_t* presence,
-                       uint64_t presence_bits_pow2, PatternMetaStats* st);
+                       uint64_t presence_bits_pow2, PatternMetaStats* st, uint32_t* rep = nullptr);
 int launch_index_lookup(cudaStream_t s, const uint8_t* qkeys, const uint64_t* qoff, uint64_t nq, const uint8_t* keys, const uint64_t* off, const PatSlot* slots,
                         uint64_t cap_pow2, const uint32_t* presence, uint64_t presence_bits_pow2, uint32_t* out_idx1 /* pattern index + 1, or 0 */);
 int launch_gather_counts(cudaStream_t s, const uint32_t* idx1, uint64_t nq, const uint32_t* counts, uint32_t* out);

@@ -196,8 +196,10 @@ __global__ void __launch_bounds__(256) pattern_meta_kernel(const uint8_t* __rest
     }
 }
 
+// rep (optional): group-by mode -- equal keys are expected; rep[i] = the index of the copy that claimed the slot (rep[i] == i for that one)
 __global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, uint64_t np, PatSlot* __restrict__ slots,
-                                                          uint64_t mask, uint32_t* __restrict__ presence, uint64_t pmask, PatternMetaStats* __restrict__ st) {
+                                                          uint64_t mask, uint32_t* __restrict__ presence, uint64_t pmask, PatternMetaStats* __restrict__ st,
+                                                          uint32_t* __restrict__ rep) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
     const uint64_t a   = off[i];
@@ -218,6 +220,7 @@ __global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restr
             slots[s].k0 = k0;
             slots[s].k1 = k1;
             slots[s].k2 = k2;
+            if (rep) rep[i] = (uint32_t)i;
             return;
         }
         // a second copy of the same pattern?  (compared in the blob: the other slot's key words may still be in flight)
@@ -231,7 +234,10 @@ __global__ void __launch_bounds__(256) index_build_kernel(const uint8_t* __restr
                     break;
                 }
             if (same) {
-                atomicAdd(&st->duplicates, 1u);
+                if (rep)
+                    rep[i] = j;
+                else
+                    atomicAdd(&st->duplicates, 1u);
                 return;
             }
         }
@@ -703,9 +709,9 @@ int launch_pattern_meta(cudaStream_t s, const uint8_t* keys, const uint64_t* off
     return 1;
 }
 int launch_index_build(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, PatSlot* slots, uint64_t cap_pow2, uint32_t* presence,
-                       uint64_t presence_bits_pow2, PatternMetaStats* st) {
+                       uint64_t presence_bits_pow2, PatternMetaStats* st, uint32_t* rep) {
     if (!np) return 0;
-    index_build_kernel<<<pi_div_up(np, 256), 256, 0, s>>>(keys, off, np, slots, cap_pow2 - 1, presence, presence_bits_pow2 - 1, st);
+    index_build_kernel<<<pi_div_up(np, 256), 256, 0, s>>>(keys, off, np, slots, cap_pow2 - 1, presence, presence_bits_pow2 - 1, st, rep);
     return 1;
 }
 int launch_index_lookup(cudaStream_t s, const uint8_t* qkeys, const uint64_t* qoff, uint64_t nq, const uint8_t* keys, const uint64_t* off, const PatSlot* slots,

@@ -393,6 +393,29 @@ class DevicePatternModel : public PatternModelInterface {
         this->load(in, options, constrainmodel);
     }
 
+    /// Compute flexgrams by abstracting from the skipgrams in the model (reference include/patternmodel.h:3724-3744, IndexedPatternModel only):
+    /// returns the number of flexgrams found.  The model goes to the device as it is, comes back with the flexgrams appended.
+    int computeflexgrams_fromskipgrams() {
+        using colibri_b200_detail::fail;
+        if (kModelType != INDEXEDPATTERNMODEL) fail("computeflexgrams_fromskipgrams is defined for indexed models only");
+        colibri_b200_detail::ModelHandle cur, res;
+        const uint64_t                   zero = 0;
+        const bool                       any  = !counts_.empty();
+        if (colibri_b200_model_from_flat(keys_.data(), any ? off_.data() : &zero, counts_.data(), counts_.size(), ref_sentence_.data(), ref_token_.data(), any ? ref_off_.data() : &zero,
+                                         totaltokens, totaltypes, INDEXEDPATTERNMODEL, colibri_b200_detail::default_device(), &cur.h) != COLIBRI_OK)
+            fail(colibri_b200_last_error());
+        uint64_t found = 0;
+        if (colibri_b200_model_flexgrams_fromskipgrams(cur.h, &found, &res.h) != COLIBRI_OK) fail(colibri_b200_last_error());
+        const int keep_maxn = maxn, keep_minn = minn;
+        const bool keep_skip = hasskipgrams;
+        adopt(res.h);
+        maxn         = keep_maxn;  // the reference leaves maxn / minn alone here
+        minn         = keep_minn;
+        hasskipgrams = keep_skip;
+        if (found) hasflexgrams = true;
+        return (int)found;
+    }
+
     /// reference include/patternmodel.h:866-868
     PatternModelInterface* getinterface() { return static_cast<PatternModelInterface*>(this); }
     colibri_b200_detail::FlatView flatview() const override {

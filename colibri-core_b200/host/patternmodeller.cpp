@@ -27,6 +27,7 @@ static void usage() {
                  "  -y N      occurrence threshold for skipgrams (default: same as -t)\n"
                  "  -T N      skip type threshold (default 2)\n"
                  "  -W N      word occurrence threshold\n"
+                 "  -F S      compute flexgrams by abstracting from the skipgrams (implies -s; indexed models)\n"
                  "  -i FILE   input model (with -I: the model to rebuild on the corpus; alone with -o: load, filter by the options, write)\n"
                  "  -j FILE   constraint model: only patterns that occur in it are counted\n"
                  "  -I        constrained in-place rebuild of the input model (-i) on the corpus (-f)\n"
@@ -34,6 +35,8 @@ static void usage() {
                  "  -q        quiet\n"
                  "  -d N      CUDA device ordinal (default 0)\n";
 }
+
+static bool g_flexfromskip = false;  // -F S / -S S: abstract flexgrams from the skipgrams after training (reference src/patternmodeller.cpp:330-337)
 
 template <class ModelType>
 static int run(const std::string& corpusfile, const std::string& outputmodelfile, IndexedCorpus* corpus, const PatternModelOptions& options, const std::string& qualifier) {
@@ -45,6 +48,15 @@ static int run(const std::string& corpusfile, const std::string& outputmodelfile
     if (!options.QUIET)
         std::cerr << "Trained in " << sec << " s: " << model.size() << " patterns, " << model.types() << " types, " << model.tokens() << " tokens (" << model.tokens() / sec / 1e6
                   << " M tokens/s)" << std::endl;
+    if (g_flexfromskip) {
+        if (model.getmodeltype() != INDEXEDPATTERNMODEL) {
+            std::cerr << "WARNING: Can't compute flexgrams from skipgrams on unindexed model" << std::endl;  // reference :327-329
+        } else {
+            std::cerr << "Computing flexgrams from skipgrams" << corpusfile << std::endl;  // reference :333-336 (sic)
+            int found = model.computeflexgrams_fromskipgrams();
+            std::cerr << found << " flexgrams found" << corpusfile << std::endl;
+        }
+    }
     if (!outputmodelfile.empty()) {
         std::cerr << "Writing model to " << outputmodelfile << std::endl;  // reference :389
         model.write(outputmodelfile);
@@ -123,6 +135,16 @@ int main(int argc, char** argv) {
             case 'd': device = atoi(optarg); break;
             case 'i': inputmodelfile = optarg; break;
             case 'j': inputmodelfile2 = optarg; break;
+            case 'S':
+            case 'F':
+                if (std::string(optarg) == "S") {  // reference src/patternmodeller.cpp:550-554
+                    g_flexfromskip      = true;
+                    options.DOSKIPGRAMS = true;
+                } else {
+                    std::cerr << "ERROR: flexgrams from co-occurrence (-F <threshold>) are not part of the B200 training front end" << std::endl;
+                    return 2;
+                }
+                break;
             case 'I': inplace = true; break;
             case '2': twostage = true; break;
             case 'h': usage(); return 0;

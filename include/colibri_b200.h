@@ -140,6 +140,14 @@ int colibri_b200_model_load(const uint8_t* file, size_t nbytes, const colibri_b2
  * :889-891, :970-971, :1199-1201).  `constrain` is not modified; the result is a new model. */
 int colibri_b200_train_constrained(colibri_b200_corpus* corpus, const colibri_b200_options* opt, colibri_b200_model* constrain, int inplace, colibri_b200_model** out);
 
+/* ---- flexgrams (first piece)
+ * IndexedPatternModel::computeflexgrams_fromskipgrams (include/patternmodel.h:3724-3744; CLI `-F S`, src/patternmodeller.cpp:330-337): every
+ * skipgram of an indexed model is abstracted to its flexgram (Pattern::toflexgram, src/pattern.cpp:145-180) and hands it all its occurrences.
+ * *found = the new flexgrams (the reference's return value); *out = a new model = m's patterns + the flexgrams, each flexgram's occurrence
+ * list ascending.  m is not modified. */
+int colibri_b200_model_flexgrams_fromskipgrams(colibri_b200_model* m, uint64_t* found, colibri_b200_model** out);
+int colibri_b200_model_hasflexgrams(const colibri_b200_model* m);
+
 /* ---- measurement hooks (bench.py): device time by phase, from CUDA events on the library's stream */
 #define COLIBRI_T_TOTAL 0     /* whole train_corpus call on the device (tokenise .. survivors ready) */
 #define COLIBRI_T_TOKENISE 1  /* K0 */

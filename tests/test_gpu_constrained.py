@@ -174,3 +174,73 @@ def test_gpu_constrained_refusals():
         assert ei.value.code == 2
     with pytest.raises(cb().ColibriError):  # duplicate patterns are not a set
         cb().Model.from_flat(np.array([6, 6], dtype=np.uint8), np.array([0, 1, 2], dtype=np.uint64)).lookup_batch([b"\x06"])
+
+
+# ---- flexgrams abstracted from skipgrams (first piece)
+import json  # noqa: E402
+import os  # noqa: E402
+
+from conftest import GOLDEN_DIR  # noqa: E402
+
+FLEX_CASES = json.load(open(os.path.join(GOLDEN_DIR, "golden_flex.json")))["cases"]
+
+
+def gpu_train_indexed_skipgrams(body, o):
+    opts = cb().PatternModelOptions(MINTOKENS=o.get("mintokens", -1), MAXLENGTH=o.get("maxlength", 100), MINSKIPTYPES=o.get("minskiptypes", 2),
+                                    MINTOKENS_SKIPGRAMS=o.get("mintokens_skipgrams", -1), DOSKIPGRAMS=1, model_type=20, streamed=0, QUIET=1)
+    return cb().train(body, opts)
+
+
+@pytest.mark.parametrize("case", FLEX_CASES, ids=["%s-%s" % (c["corpus"], "".join("%s%s" % kv for kv in sorted(c["cli"].items())) or "default") for c in FLEX_CASES])
+def test_gpu_flexgrams_fromskipgrams_match_reference_golden(golden, case):
+    """computeflexgrams_fromskipgrams on the device against the reference CLI's `-s -F S` files (reference KAT: 22 found, 155 patterns)."""
+    body = corpus_body(golden, case["corpus"])
+    m = gpu_train_indexed_skipgrams(body, case["options"])
+    found, fm = m.flexgrams_fromskipgrams()
+    assert (found, len(fm), fm.tokens(), fm.types()) == (case["flexfound"], case["patterns"], case["tokens"], case["types"])
+    assert fm.hasflexgrams == (found > 0) and fm.hasskipgrams == m.hasskipgrams
+    flat = to_flat(fm)
+    assert int(flat.counts.sum()) == case["occurrences"]
+    assert flat.sorted_refs().digest() == case["digest_sorted_refs"]
+    want = oracle.train(body, flexfromskip=1, **case["options"])
+    assert flat.same_patterns(want)  # both emit every occurrence list ascending
+    assert oracle.parse_modelfile(fm.to_bytes()).sorted_refs().digest() == case["digest_sorted_refs"]
+    assert len(m) == case["patterns"] - case["flexfound"]  # the source model is untouched
+
+
+@pytest.mark.parametrize("seed", range(25))
+def test_gpu_flexgrams_random_vs_oracle(seed):
+    """Random corpora: the clean iteration (every skipgram once), which is what the oracle restates; the reference itself is only
+    comparable where its insert-while-iterating does not rehash (tests/golden/make_golden_flex.py)."""
+    rng = random.Random(7000 + seed)
+    body = _rand_corpus(rng, rng.randint(1, 60), rng.choice([5, 30, 200]), rng.choice([6, 12, 30]))
+    if not body.strip(b"\0"):
+        body = bytes([6, 7, 8, 0, 6, 9, 8, 0])
+    o = dict(mintokens=rng.choice([2, 2, 3]), maxlength=rng.choice([3, 4, 5, 6]), minskiptypes=rng.choice([1, 2]), indexed=1, doskipgrams=1, streamed=0)
+    want = oracle.train(body, flexfromskip=1, **o)
+    found, fm = gpu_train_indexed_skipgrams(body, o).flexgrams_fromskipgrams()
+    assert found == want.flexfound and len(fm) == len(want)
+    assert to_flat(fm).same_patterns(want)
+
+
+def test_gpu_flexgrams_refusals_and_cli(tmp_path):
+    body = open(os.path.join(GOLDEN_DIR, "hamlet.colibri.dat"), "rb").read()[2:]
+    with pytest.raises(cb().ColibriError) as ei:
+        cb().train(body, MINTOKENS=2, MAXLENGTH=3, QUIET=1).flexgrams_fromskipgrams()  # unindexed
+    assert ei.value.code == 1
+    found, fm = gpu_train_indexed_skipgrams(body, {}).flexgrams_fromskipgrams()
+    with pytest.raises(cb().ColibriError) as ei:
+        fm.flexgrams_fromskipgrams()  # already holds flexgrams
+    assert ei.value.code == 2
+    import subprocess
+
+    from conftest import ROOT
+
+    cli = os.path.join(ROOT, "colibri-core_b200", "bin", "colibri-patternmodeller")
+    subprocess.run(["make", "-s", "-C", ROOT, "host"], check=True)
+    out = str(tmp_path / "flex.colibri.patternmodel")
+    r = subprocess.run([cli, "-f", os.path.join(GOLDEN_DIR, "hamlet.colibri.dat"), "-F", "S", "-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "22 flexgrams found" in r.stderr
+    got = oracle.parse_modelfile(open(out, "rb").read())
+    assert len(got) == 155 and got.sorted_refs().digest() == FLEX_CASES[0]["digest_sorted_refs"]

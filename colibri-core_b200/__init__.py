@@ -99,6 +99,8 @@ def library():
                                                C.POINTER(C.c_void_p)]
     L.colibri_b200_model_load.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(COptions), C.c_void_p, C.POINTER(C.c_void_p)]
     L.colibri_b200_train_constrained.argtypes = [C.c_void_p, C.POINTER(COptions), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.colibri_b200_constrained_count.argtypes = [C.c_void_p, C.POINTER(COptions), C.c_void_p, C.c_void_p, _u64p, _u64p]
+    L.colibri_b200_constrained_finish.argtypes = [C.POINTER(COptions), C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
     L.colibri_b200_model_flexgrams_fromskipgrams.argtypes = [C.c_void_p, _u64p, C.POINTER(C.c_void_p)]
     L.colibri_b200_model_hasflexgrams.argtypes = [C.c_void_p]
     L.colibri_b200_model_hasflexgrams.restype = C.c_int
@@ -464,6 +466,21 @@ def train_constrained(corpus, constrain: Model, inplace: bool = False, options: 
     finally:
         if own is not None:
             own.close()
+    return Model(h)
+
+
+def constrained_count(shard: Corpus, constrain: Model, options: PatternModelOptions, counts_ptr):
+    """One rank's share of a sharded constrained run: add this shard's occurrences of every pattern of `constrain` to the device array
+    at counts_ptr (uint32[len(constrain)], zeroed by the caller).  Returns (tokens of the shard, kernel launches)."""
+    tokens, launches = C.c_uint64(), C.c_uint64()
+    _check(library().colibri_b200_constrained_count(shard._h, C.byref(options._c), constrain._h, counts_ptr, C.byref(tokens), C.byref(launches)))
+    return int(tokens.value), int(launches.value)
+
+
+def constrained_finish(constrain: Model, options: PatternModelOptions, counts_ptr, corpus_tokens: int, inplace: bool = False) -> Model:
+    """Threshold + compaction of the counters summed over all shards (see constrained_count)."""
+    h = C.c_void_p()
+    _check(library().colibri_b200_constrained_finish(C.byref(options._c), constrain._h, counts_ptr, int(corpus_tokens), 1 if inplace else 0, C.byref(h)))
     return Model(h)
 
 

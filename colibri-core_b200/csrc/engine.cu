@@ -286,7 +286,9 @@ struct Trainer {
     int indexed_skipgrams(int n, Segment& ng, const std::vector<DevBuf<uint32_t>>& ids, uint64_t& foundskip, uint64_t& keptskip, Segment& out);
     int tokenise(DevBuf<uint32_t>& tok, uint64_t& npos, uint32_t& nclasses);
     int run();
-    int run_constrained(colibri_b200_model* cm, bool inplace);
+    // phase 0: the whole call; 1: count this corpus into ext_counts only (a shard of a multi-GPU run); 2: threshold + compaction of
+    // ext_counts (summed over the shards by the caller), corpus_tokens = ext_tokens.  Phases 1 and 2 are for unindexed models.
+    int run_constrained(colibri_b200_model* cm, bool inplace, int phase = 0, uint32_t* ext_counts = nullptr, uint64_t ext_tokens = 0);
 };
 
 int Trainer::prepare_index(const uint32_t* tok, uint64_t npos) {
@@ -793,18 +795,25 @@ int Trainer::run() {
 // are rebuilt in registers, hashed with SpookyV2 (Pattern::hash) and probed in the set's HBM index (pattern_index.cu); survivors are
 // compacted out of the set's own blob.  Indexed models remember the match of every position and build the occurrence lists with the
 // ordered-pairs + stable radix sort of index.cu, one length at a time (survivors are ordered by length so the lists concatenate).
-int Trainer::run_constrained(colibri_b200_model* cm, bool inplace) {
+int Trainer::run_constrained(colibri_b200_model* cm, bool inplace, int phase, uint32_t* ext_counts, uint64_t ext_tokens) {
     CUDA_TRY(cudaSetDevice(dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     timer.s = s;
     int h_total = timer.begin(COLIBRI_T_TOTAL);
+    indexed = o.model_type == COLIBRI_INDEXEDPATTERNMODEL;
+    if (phase != 0 && (indexed || ext_counts == nullptr)) return set_err(COLIBRI_E_UNSUPPORTED, "sharded constrained training is for unindexed models");
     TRY(ensure_closure(cm, &launches));
     DevBuf<uint32_t> tok;
     uint64_t         npos = 0;
     uint32_t         nclasses = 0;
-    TRY(tokenise(tok, npos, nclasses));
+    if (phase != 2) {
+        TRY(tokenise(tok, npos, nclasses));
+    } else {
+        TRY(d_stats.alloc(dev, 1));
+        CUDA_TRY(cudaMemsetAsync(d_stats.p, 0, sizeof(DeviceStats), s));
+        m->totaltokens = ext_tokens;
+    }
     const uint64_t corpus_tokens = m->totaltokens;
-    indexed = o.model_type == COLIBRI_INDEXEDPATTERNMODEL;
     if (indexed) {
         int hi = timer.begin(COLIBRI_T_INDEX);
         TRY(prepare_index(tok.p, npos));
@@ -816,23 +825,27 @@ int Trainer::run_constrained(colibri_b200_model* cm, bool inplace) {
     for (int n = o.MINLENGTH; n <= o.MAXLENGTH && n <= 255; ++n)
         if (np && cm->meta.nhist[n]) lengths.push_back(n);
 
-    DevBuf<uint32_t> counts, flags, kmap;
-    TRY(counts.alloc(dev, std::max<uint64_t>(np, 1)));
+    DevBuf<uint32_t> counts_own, flags, kmap;
+    if (ext_counts == nullptr) {
+        TRY(counts_own.alloc(dev, std::max<uint64_t>(np, 1)));
+        CUDA_TRY(cudaMemsetAsync(counts_own.p, 0, std::max<uint64_t>(np, 1) * sizeof(uint32_t), s));
+        ext_counts = counts_own.p;
+    }
+    struct { uint32_t* p; } counts{ext_counts};  // this call's counter array: its own, or the caller's (sharded run)
     TRY(flags.alloc(dev, np + 1));
-    CUDA_TRY(cudaMemsetAsync(counts.p, 0, std::max<uint64_t>(np, 1) * sizeof(uint32_t), s));
     // match[k][p] = pattern (index + 1) of the window of lengths[k] tokens at p.  Indexed models keep every level (the occurrence lists are
     // built from them); otherwise two buffers alternate: level n only looks at level n-1, to skip windows whose prefix / suffix did not match
     const bool chain = !getenv("COLIBRI_B200_NO_CHAIN");
     DevBuf<uint32_t> count1_scratch;
     uint64_t         unigram_windows = 0;
-    std::vector<DevBuf<uint32_t>> match(indexed ? lengths.size() : std::min<size_t>(lengths.size(), 2));
+    std::vector<DevBuf<uint32_t>> match(phase == 2 ? 0 : (indexed ? lengths.size() : std::min<size_t>(lengths.size(), 2)));
     for (auto& mb : match) {
         TRY(mb.alloc(dev, npos + 8));
         CUDA_TRY(cudaMemsetAsync(mb.p + npos, 0, 8 * sizeof(uint32_t), s));
     }
     TRY(zero_stats());
-    cm->index_counts_dirty = true;  // until the slot counters have been collected (an error in between forces a rebuild of the index)
-    for (size_t k = 0; k < lengths.size(); ++k) {
+    if (phase != 2) cm->index_counts_dirty = true;  // until the slot counters have been collected (an error in between forces a rebuild of the index)
+    for (size_t k = 0; k < lengths.size() && phase != 2; ++k) {
         const int n   = lengths[k];
         uint32_t* cur = match[indexed ? k : k % 2].p;
         const uint32_t* prev = (k > 0 && lengths[k - 1] == n - 1 && chain) ? match[indexed ? k - 1 : (k - 1) % 2].p : nullptr;
@@ -853,14 +866,22 @@ int Trainer::run_constrained(colibri_b200_model* cm, bool inplace) {
                                                  prev, use_prefix, use_suffix, d_stats.p, sms);
         timer.end(hc);
     }
-    {
+    if (phase != 2) {
         int hc = timer.begin(COLIBRI_T_PRUNE);
         launches += launch_collect_slot_counts(s, cm->d_index.p, cm->index_cap, counts.p);
         timer.end(hc);
     }
     TRY(read_stats());
-    cm->index_counts_dirty = false;
+    if (phase != 2) cm->index_counts_dirty = false;
     ngram_upserts = h_stats.valid_windows + unigram_windows;
+    if (phase == 1) {  // a shard: the caller sums the counters over the ranks and runs phase 2
+        timer.end(h_total);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        timer.resolve(m->ms, nullptr);
+        m->counters[2] = launches;
+        m->counters[3] = ngram_upserts;
+        return 0;
+    }
 
     // ---- threshold (prune(MINTOKENS, 0)) and the numbers of the progress line
     DevBuf<PatternMetaStats> d_pst;
@@ -1111,6 +1132,64 @@ extern "C" int colibri_b200_train_constrained(colibri_b200_corpus* corpus, const
         tr.s   = m->stream;
         tr.dev = corpus->device;
         rc     = tr.run_constrained(constrain, inplace != 0);
+        if (rc) cudaStreamSynchronize(m->stream);
+    }
+    if (rc) {
+        colibri_b200_model_free(m);
+        return rc;
+    }
+    *out = m;
+    return 0;
+}
+
+// ---- constrained training over a sharded corpus: the constraint set is replicated, every rank counts its shard (no communication), the
+// caller sums the counter arrays (one all-reduce), then every rank thresholds the same sums
+extern "C" int colibri_b200_constrained_count(colibri_b200_corpus* shard, const colibri_b200_options* opt, colibri_b200_model* constrain, void* dev_counts, uint64_t* shard_tokens,
+                                              uint64_t* kernel_launches) {
+    if (!shard || !opt || !constrain || !dev_counts) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    colibri_b200_options o = *opt;
+    TRY(check_constrained_options(o));
+    if (o.device != shard->device || constrain->device != shard->device) return set_err(COLIBRI_E_INVALID, "corpus, constraint model and options must name the same device");
+    colibri_b200_model* scratch = nullptr;
+    TRY(new_model(shard->device, o.model_type, &scratch));
+    int rc;
+    {
+        Trainer tr;
+        tr.c   = shard;
+        tr.o   = o;
+        tr.m   = scratch;
+        tr.s   = scratch->stream;
+        tr.dev = shard->device;
+        rc     = tr.run_constrained(constrain, false, 1, (uint32_t*)dev_counts, 0);
+        if (rc) cudaStreamSynchronize(scratch->stream);
+    }
+    if (rc == 0) {
+        if (shard_tokens) *shard_tokens = scratch->totaltokens;
+        if (kernel_launches) *kernel_launches = scratch->counters[2];
+    }
+    colibri_b200_model_free(scratch);
+    return rc;
+}
+
+extern "C" int colibri_b200_constrained_finish(const colibri_b200_options* opt, colibri_b200_model* constrain, void* dev_counts, uint64_t corpus_tokens, int inplace,
+                                               colibri_b200_model** out) {
+    if (!out) return set_err(COLIBRI_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!opt || !constrain || !dev_counts) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    colibri_b200_options o = *opt;
+    TRY(check_constrained_options(o));
+    if (o.device != constrain->device) return set_err(COLIBRI_E_INVALID, "options.device=%d but the constraint model lives on device %d", o.device, constrain->device);
+    colibri_b200_model* m = nullptr;
+    TRY(new_model(constrain->device, o.model_type, &m));
+    int rc;
+    {
+        Trainer tr;
+        tr.c   = nullptr;
+        tr.o   = o;
+        tr.m   = m;
+        tr.s   = m->stream;
+        tr.dev = constrain->device;
+        rc     = tr.run_constrained(constrain, inplace != 0, 2, (uint32_t*)dev_counts, corpus_tokens);
         if (rc) cudaStreamSynchronize(m->stream);
     }
     if (rc) {

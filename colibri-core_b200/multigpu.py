@@ -339,6 +339,42 @@ def train_distributed(engine, dist, torch, mintokens=2, maxlength=5, skipgrams=F
     return model, passes, {"tokens": global_tokens, "types": types, "maxn": maxn, "minn": minn}
 
 
+# --------------------------------------------------------------------------------------------- constrained training, sharded
+class CudaConstrainedEngine:
+    """Per-rank side of a sharded constrained run (PatternModel::train with constrainbymodel, SURVEY 8f-2 x 8e): the constraint set is
+    replicated, the corpus is cut at sentence boundaries, one shard per rank.  Counting needs no communication at all."""
+
+    def __init__(self, shard, constrain, options, local, torch):
+        self.shard, self.constrain, self.options, self.local, self.torch = shard, constrain, options, local, torch
+
+    def count(self):
+        counts = self.torch.zeros(max(len(self.constrain), 1), dtype=self.torch.int32, device="cuda:%d" % self.local)
+        self.torch.cuda.synchronize(self.local)
+        tokens, self.launches = _cb().constrained_count(self.shard, self.constrain, self.options, counts.data_ptr())
+        return counts, tokens
+
+    def finish(self, counts, tokens, inplace):
+        self.torch.cuda.synchronize(self.local)
+        return _cb().constrained_finish(self.constrain, self.options, counts.data_ptr(), tokens, inplace)
+
+
+def _cb():
+    import colibri_core_b200 as cb
+
+    return cb
+
+
+def train_constrained_distributed(engine, dist, torch, inplace=False):
+    """count (local) -> all-reduce SUM of the per-pattern counters and of the token counts -> finish (the same model on every rank).
+    The counters are uint32 carried in int32 tensors: two's-complement sums wrap the same way."""
+    counts, tokens = engine.count()
+    tok = torch.tensor([tokens], dtype=torch.int64, device=counts.device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(counts)
+        dist.all_reduce(tok)
+    return engine.finish(counts, int(tok.item()), inplace)
+
+
 def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, measured_peaks):
     """bench.py --gpus N under torchrun: weak scaling, every rank trains its own `--tokens` shard of one global stream."""
     import torch

@@ -140,6 +140,14 @@ int colibri_b200_model_load(const uint8_t* file, size_t nbytes, const colibri_b2
  * :889-891, :970-971, :1199-1201).  `constrain` is not modified; the result is a new model. */
 int colibri_b200_train_constrained(colibri_b200_corpus* corpus, const colibri_b200_options* opt, colibri_b200_model* constrain, int inplace, colibri_b200_model** out);
 
+/* The same over a corpus sharded at sentence boundaries, one shard per rank (SURVEY.md 8e applied to 8f-2; unindexed models): the constraint set is
+ * replicated on every rank; _count adds this shard's occurrences of every pattern to dev_counts (device u32[size of constrain], zeroed by the
+ * caller) -- no communication; the caller sums dev_counts and the token counts over the ranks (one all-reduce each); _finish thresholds the sums
+ * and returns the model (identical on every rank).  colibri_b200_train_constrained == _count + _finish on one rank. */
+int colibri_b200_constrained_count(colibri_b200_corpus* shard, const colibri_b200_options* opt, colibri_b200_model* constrain, void* dev_counts, uint64_t* shard_tokens,
+                                   uint64_t* kernel_launches);
+int colibri_b200_constrained_finish(const colibri_b200_options* opt, colibri_b200_model* constrain, void* dev_counts, uint64_t corpus_tokens, int inplace, colibri_b200_model** out);
+
 /* ---- flexgrams (first piece)
  * IndexedPatternModel::computeflexgrams_fromskipgrams (include/patternmodel.h:3724-3744; CLI `-F S`, src/patternmodeller.cpp:330-337): every
  * skipgram of an indexed model is abstracted to its flexgram (Pattern::toflexgram, src/pattern.cpp:145-180) and hands it all its occurrences.

@@ -20,6 +20,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     kw = dict(vocab=vocab, seed=seed, mean_sentence=15, phrase_permille=150, nphrases=500)
     corpus = cb.Corpus.synthetic(per, device=local, first_token=rank * per, **kw)
+    if len(sys.argv) > 6 and sys.argv[6] == "constrained":
+        return constrained(per, kw, maxlength, mintokens, rank, world, local, corpus)
     skip = len(sys.argv) > 7 and sys.argv[7] == "skipgrams"
     opts = cb.PatternModelOptions(MINTOKENS=mintokens, MAXLENGTH=maxlength, DOSKIPGRAMS_EXHAUSTIVE=int(skip), streamed=0 if skip else 1, QUIET=1, device=local)
     eng = mg.CudaShardEngine(corpus, opts, rank, world, local)
@@ -46,6 +48,33 @@ def main():
         ok = merged == want.as_dict() and [tuple(p) for p in passes] == want.passes and (head["tokens"], head["types"], head["maxn"], head["minn"]) == (
             want.tokens, want.types, want.maxn, want.minn)
         print("DIST_RESULT", "OK" if ok else "MISMATCH", len(merged), len(want), passes, want.passes, flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+def constrained(per, kw, maxlength, mintokens, rank, world, local, corpus):
+    """Sharded constrained training (SURVEY 8f-2 x 8e): the stage-1 model of another corpus, replicated; local counting; one all-reduce."""
+    kw1 = dict(kw, seed=kw["seed"] + 1)
+    stage1 = cb.train(cb.Corpus.synthetic(per, device=local, **kw1), MINTOKENS=2, MAXLENGTH=maxlength, QUIET=1, device=local)
+    blob = stage1.to_bytes()
+    constrain = cb.load_model(blob, MINTOKENS=mintokens, MAXLENGTH=maxlength, QUIET=1, device=local)
+    opts = cb.PatternModelOptions(MINTOKENS=mintokens, MAXLENGTH=maxlength, streamed=1, QUIET=1, device=local)
+    eng = mg.CudaConstrainedEngine(corpus, constrain, opts, local, torch)
+    model = mg.train_constrained_distributed(eng, dist, torch, inplace=False)
+    keys, off, counts, _ = model.export()
+    mine = {keys[int(off[i]):int(off[i + 1])].tobytes(): int(counts[i]) for i in range(len(counts))}
+    head = (model.tokens(), model.types(), model.passes())
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object((mine, head), gathered, dst=0)
+    ok = True
+    if rank == 0:
+        import oracle
+
+        body = b"".join(oracle.synth_corpus(per, first_token=r * per, **kw).tobytes() for r in range(world))
+        want = oracle.train_constrained(body, oracle.load_model(blob, mintokens=mintokens, maxlength=maxlength), inplace=False, mintokens=mintokens, maxlength=maxlength, streamed=1)
+        ok = all(g[0] == want.as_dict() and g[1] == (want.tokens, want.types, want.passes) for g in gathered)
+        print("DIST_RESULT", "OK" if ok else "MISMATCH", len(mine), len(want), head, (want.tokens, want.types, want.passes), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

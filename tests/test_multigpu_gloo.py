@@ -255,3 +255,69 @@ def test_distributed_orchestration_matches_oracle(world, mintokens, maxlength, s
     _, passes, head = gathered[0]
     assert [tuple(p) for p in passes] == want.passes
     assert (head["tokens"], head["types"], head["maxn"], head["minn"]) == (want.tokens, want.types, want.maxn, want.minn)
+
+
+# ---- constrained training, sharded (SURVEY 8f-2 x 8e): replicated constraint set, local counting, one all-reduce
+class NumpyConstrainedEngine:
+    """Test double with the interface of multigpu.CudaConstrainedEngine, backed by the oracle on this rank's shard."""
+
+    def __init__(self, body, stage1_blob, load_kw, train_kw):
+        import oracle
+
+        self.body, self.train_kw = body, train_kw
+        self.cm = oracle.load_model(stage1_blob, **load_kw)
+        self.flat = self.cm.flat()  # canonical order = the pattern numbering all ranks share
+
+    def count(self):
+        import oracle
+
+        kw = dict(self.train_kw, mintokens=1)
+        local = oracle.train_constrained(self.body, self.cm, inplace=False, **kw)
+        d = local.as_dict()
+        counts = np.array([d.get(self.flat.key(i), 0) for i in range(len(self.flat))], dtype=np.int32)
+        return torch.from_numpy(counts if len(counts) else np.zeros(1, dtype=np.int32)), local.tokens - self.flat.tokens
+
+    def finish(self, counts, tokens, inplace):
+        t = self.train_kw["mintokens"]
+        c = counts.numpy()
+        return {self.flat.key(i): int(c[i]) for i in range(len(self.flat)) if c[i] >= t}, tokens
+
+
+def _constrained_worker(rank, world, port, bodies, stage1, load_kw, train_kw, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import colibri_core_b200.multigpu as mg
+
+    eng = NumpyConstrainedEngine(bodies[rank], stage1, load_kw, train_kw)
+    model, tokens = mg.train_constrained_distributed(eng, dist, torch, inplace=False)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object((model, tokens), gathered, dst=0)
+    if rank == 0:
+        results.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,mintokens,maxlength,seed", [(2, 2, 5, 3), (3, 3, 4, 5), (2, 1, 3, 7)])
+def test_distributed_constrained_orchestration_matches_oracle(world, mintokens, maxlength, seed):
+    import oracle
+
+    per = 4000
+    bodies = [oracle.synth_corpus(per, vocab=60, seed=seed, mean_sentence=9, phrase_permille=300, nphrases=20, first_token=r * per).tobytes() for r in range(world)]
+    stage1 = oracle.train_to_modelfile(oracle.synth_corpus(6000, vocab=60, seed=seed + 1, mean_sentence=9, phrase_permille=300, nphrases=20).tobytes(), mintokens=2, maxlength=maxlength)
+    load_kw = dict(mintokens=mintokens, maxlength=maxlength)
+    train_kw = dict(mintokens=mintokens, maxlength=maxlength, streamed=1)
+    want = oracle.train_constrained(b"".join(bodies), oracle.load_model(stage1, **load_kw), inplace=False, **train_kw)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() + seed) % 90
+    procs = [ctx.Process(target=_constrained_worker, args=(r, world, port, bodies, stage1, load_kw, train_kw, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for model, tokens in gathered:  # every rank holds the same model
+        assert model == want.as_dict()
+        assert tokens == per * world

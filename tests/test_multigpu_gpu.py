@@ -50,3 +50,16 @@ def test_shard_skipgrams_world2():
 def test_shard_phases_world1_peer_stores():
     """NVLink peer-store mode with a single rank: the kernels store into the rank's own symmetric buffers."""
     _run(1, 300000, 20000, 4, 5, 2, 29715, "p2p")
+
+
+def test_constrained_sharded_world1():
+    """Sharded constrained training (count / all-reduce / finish) with a single rank."""
+    _run(1, 300000, 20000, 21, 5, 2, 29721, "constrained")
+
+
+def test_constrained_sharded_world2():
+    import colibri_core_b200 as cb
+
+    if cb.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run(2, 300000, 20000, 23, 5, 2, 29723, "constrained")

@@ -143,7 +143,8 @@ int colibri_b200_train_constrained(colibri_b200_corpus* corpus, const colibri_b2
 /* The same over a corpus sharded at sentence boundaries, one shard per rank (SURVEY.md 8e applied to 8f-2; unindexed models): the constraint set is
  * replicated on every rank; _count adds this shard's occurrences of every pattern to dev_counts (device u32[size of constrain], zeroed by the
  * caller) -- no communication; the caller sums dev_counts and the token counts over the ranks (one all-reduce each); _finish thresholds the sums
- * and returns the model (identical on every rank).  colibri_b200_train_constrained == _count + _finish on one rank. */
+ * and returns the model (identical on every rank).  Every rank must hold the SAME pattern numbering, i.e. load the same model file / upload the
+ * same flat arrays (the export order of a freshly trained model is not deterministic).  colibri_b200_train_constrained == _count + _finish on one rank. */
 int colibri_b200_constrained_count(colibri_b200_corpus* shard, const colibri_b200_options* opt, colibri_b200_model* constrain, void* dev_counts, uint64_t* shard_tokens,
                                    uint64_t* kernel_launches);
 int colibri_b200_constrained_finish(const colibri_b200_options* opt, colibri_b200_model* constrain, void* dev_counts, uint64_t corpus_tokens, int inplace, colibri_b200_model** out);

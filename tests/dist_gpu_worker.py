@@ -57,7 +57,11 @@ def constrained(per, kw, maxlength, mintokens, rank, world, local, corpus):
     """Sharded constrained training (SURVEY 8f-2 x 8e): the stage-1 model of another corpus, replicated; local counting; one all-reduce."""
     kw1 = dict(kw, seed=kw["seed"] + 1)
     stage1 = cb.train(cb.Corpus.synthetic(per, device=local, **kw1), MINTOKENS=2, MAXLENGTH=maxlength, QUIET=1, device=local)
-    blob = stage1.to_bytes()
+    # every rank must number the patterns identically: in practice they all read the same model file; here rank 0's bytes are broadcast
+    # (the export order of a trained model depends on which thread claimed which table slot, so two ranks' files differ in order)
+    box = [stage1.to_bytes() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    blob = box[0]
     constrain = cb.load_model(blob, MINTOKENS=mintokens, MAXLENGTH=maxlength, QUIET=1, device=local)
     opts = cb.PatternModelOptions(MINTOKENS=mintokens, MAXLENGTH=maxlength, streamed=1, QUIET=1, device=local)
     eng = mg.CudaConstrainedEngine(corpus, constrain, opts, local, torch)

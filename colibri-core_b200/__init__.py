@@ -107,6 +107,7 @@ def library():
     L.colibri_b200_model_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.colibri_b200_model_counters.argtypes = [C.c_void_p, _u64p]
     L.colibri_b200_model_level_counters.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    L.colibri_b200_model_level_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.colibri_b200_shard_begin.argtypes = [C.c_void_p, C.POINTER(COptions), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.colibri_b200_shard_info.argtypes = [C.c_void_p, _u64p]
     L.colibri_b200_shard_device_ms.argtypes = [C.c_void_p]
@@ -405,9 +406,9 @@ class Model:
         return {k: int(v) for k, v in zip(names, c)}
 
     def level(self, n):
-        out = (C.c_double * 4)()
-        _check(library().colibri_b200_model_level_counters(self._h, n, out))
-        return {"windows": int(out[0]), "capacity": int(out[1]), "count_ms": float(out[2]), "singletons": int(out[3])}
+        out = (C.c_double * 8)()
+        _check(library().colibri_b200_model_level_info(self._h, n, out))
+        return {"windows": int(out[0]), "capacity": int(out[1]), "count_ms": float(out[2]), "singletons": int(out[3]), "items": int(out[4])}
 
     def close(self):
         if self._h:

@@ -13,6 +13,37 @@ __device__ __forceinline__ uint64_t fast_range(uint64_t h, uint64_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Placement hash of the fixed-width id keys (the (prefix-id, suffix-id) pair of an n-gram, the 16-byte skipgram key).  Its value is
+// not observable in any result (only iteration order depends on the hash), so it only has to spread keys evenly.
+// Round 1 used SpookyV2 Hash64 here as well: ~75 integer instructions per key, executed by whole warps even when only a few lanes
+// hold a valid window -- the filter and the sparse levels 4/5 were ALU-bound on it (profiles/r02_ncu.md: 140 warp instructions per
+// position in ngram_filter_kernel, ALU pipe 52 %).  This is the 64-bit finaliser of MurmurHash3 (public domain): two multiplies,
+// three xor-shifts, ~18 instructions.  SpookyV2 stays where the key IS the pattern's bytes (pattern_index.cu: constrained training,
+// load, lookups -- the hash the reference computes, Pattern::hash).  Build with -DCOLIBRI_TABLE_HASH_SPOOKY to get round 1's choice back.
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xFF51AFD7ED558CCDull;
+    x ^= x >> 33;
+    x *= 0xC4CEB9FE1A85EC53ull;
+    x ^= x >> 33;
+    return x;
+}
+__host__ __device__ __forceinline__ uint64_t table_hash_u64(uint64_t key) {
+#ifdef COLIBRI_TABLE_HASH_SPOOKY
+    return spooky_hash64_u64(key, 0);
+#else
+    return fmix64(key);
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t table_hash_u128(uint64_t k0, uint64_t k1) {
+#ifdef COLIBRI_TABLE_HASH_SPOOKY
+    return spooky_hash64_u128(k0, k1, 0);
+#else
+    return fmix64(k0 + 0x9E3779B97F4A7C15ull * fmix64(k1 ^ 0xD6E8FEB86659FD93ull));
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
 // warp / block primitives
 __device__ __forceinline__ uint32_t lane_id() {
     return threadIdx.x & 31;

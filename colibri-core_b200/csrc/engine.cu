@@ -178,6 +178,17 @@ extern "C" int colibri_b200_model_level_counters(const colibri_b200_model* m, in
     out[3] = (double)it->second.singles;
     return 0;
 }
+extern "C" int colibri_b200_model_level_info(const colibri_b200_model* m, int n, double out[8]) {
+    auto it = m->levels.find(n);
+    if (it == m->levels.end()) return set_err(COLIBRI_E_INVALID, "level %d was not run", n);
+    memset(out, 0, 8 * sizeof(double));
+    out[0] = (double)it->second.windows;
+    out[1] = (double)it->second.cap;
+    out[2] = it->second.ms;
+    out[3] = (double)it->second.singles;
+    out[4] = (double)it->second.items;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------ training
 namespace {
@@ -263,6 +274,7 @@ struct Trainer {
     DeviceStats                h_stats;
     std::vector<Segment>       segs;
     uint64_t                   slots_init = 0, ngram_upserts = 0, skip_upserts = 0, filtered_windows = 0;
+    Tuning                     tune = Tuning::from_env();
 
     int zero_stats(bool keep_global = true) {
         // found/kept/kept_occ/cursor/valid_windows/probes are per-phase; totaltokens/maxclass/errflags live for the whole train
@@ -271,6 +283,7 @@ struct Trainer {
         return 0;
     }
     int read_stats() {
+        CUDA_TRY(cudaGetLastError());  // a kernel of this phase that failed to launch (bad configuration, missing opt-in) must not read as "nothing found"
         CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (h_stats.errflags & kErrTableFull) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow");
@@ -539,6 +552,9 @@ int Trainer::run() {
     DevBuf<uint32_t>        bitmap;  // survivor bit per table slot of the level just pruned
     DevBuf<uint32_t>        filter;  // 2-bit occurrence filter of the level being counted
     DevBuf<uint32_t>        slot_index;  // indexed models: table slot -> survivor index + 1
+    DevBuf<uint32_t>        list_cur, list_next;  // list mode: positions whose newest id is non-zero (see kernels.cu: load_window)
+    uint64_t                nlist = 0;
+    bool                    list_valid = false;
     DevBuf<SkipSlot>        sktable;
     DevBuf<const uint32_t*> d_idptrs;
     DevBuf<SkipMask>        d_masks;
@@ -557,30 +573,26 @@ int Trainer::run() {
         if (!cur.p) TRY(cur.alloc(dev, npos + 8));
         CUDA_TRY(cudaMemsetAsync(cur.p + npos, 0, 8 * sizeof(uint32_t), s));
 
+        // ---- list mode: the previous level's relabel step left the positions whose (n-1)-gram survived
+        const bool      use_list = list_valid;
+        const uint32_t* list     = use_list ? list_cur.p : nullptr;
+        if (use_list) CUDA_TRY(cudaMemsetAsync(cur.p, 0, npos * sizeof(uint32_t), s));  // only the windows that exist are written
+
         // ---- dense pairs (level 2 of a large corpus): the ids of level 1 are the class numbers, frequent classes are the small ones
         uint32_t dense = 0;
-        if (n == 2) {
-            const char*    e_dim = getenv("COLIBRI_B200_DENSE");      // side of the directly addressed square (0 = off)
-            const char*    e_min = getenv("COLIBRI_B200_DENSE_MIN");  // smallest level (upper bound of its windows) that gets one
-            const uint64_t dmin  = e_min ? strtoull(e_min, nullptr, 10) : (1ull << 25);
-            const uint32_t ddim  = e_dim ? (uint32_t)atoi(e_dim) : 2048u;
-            if (bound >= dmin && !getenv("COLIBRI_B200_MLP") && !getenv("COLIBRI_B200_MLP_COUNT") && !getenv("COLIBRI_B200_MLP_FILTER")) dense = std::min<uint32_t>(ddim, nclasses);
-            if (dense > 16384) dense = 16384;
-        }
+        if (n == 2 && !use_list && bound >= tune.dense_min) dense = std::min<uint32_t>(tune.dense_dim, nclasses);
         const uint64_t dense_slots = (uint64_t)dense * dense;
 
         // ---- occurrence filter (t >= 2, worth its two extra launches only on large levels)
-        const bool use_filter = t >= 2 && bound >= (1ull << 25) && !getenv("COLIBRI_B200_NO_FILTER");
+        const bool use_filter = tune.use_filter(t, bound);
         uint64_t   nbuckets = 0, cap = 0;
         if (use_filter) {
-            static const int max_log2 = getenv("COLIBRI_B200_FILTER_LOG2") ? atoi(getenv("COLIBRI_B200_FILTER_LOG2")) : 28;
-            nbuckets = 1ull << 20;
-            while (nbuckets < 2 * bound && nbuckets < (1ull << max_log2)) nbuckets <<= 1;  // <= 64 MB of 2-bit counters: L2 resident
+            nbuckets = tune.filter_buckets(bound);  // <= 64 MB of 2-bit counters: L2 resident
             if (filter.n < nbuckets / 16) TRY(filter.alloc(dev, nbuckets / 16));
             int hf = timer.begin(COLIBRI_T_COUNT, n);
             CUDA_TRY(cudaMemsetAsync(filter.p, 0, nbuckets / 4, s));
             TRY(zero_stats());
-            launches += launch_ngram_filter(s, prev.p, npos, filter.p, nbuckets, d_stats.p, sms, dense);
+            launches += launch_ngram_filter(s, prev.p, npos, filter.p, nbuckets, d_stats.p, sms, dense, list, nlist);
             timer.end(hf);
             TRY(read_stats());
             // keys that reach the table live in buckets hit at least twice; there are at most ~2 such keys per bucket
@@ -601,15 +613,16 @@ int Trainer::run() {
             slots_init += cap + dense_slots;
             TRY(zero_stats());
             int hc = timer.begin(COLIBRI_T_COUNT, n);
-            static const int hot_mode = getenv("COLIBRI_B200_HOT") ? atoi(getenv("COLIBRI_B200_HOT")) : 1;  // 0 never, 1 large levels, 2 always
-            const bool hot = hot_mode == 2 || (hot_mode == 1 && bound >= (1ull << 25));
-            launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms, use_filter ? filter.p : nullptr, nbuckets, hot, dense);
+            const bool hot = tune.use_hot(bound);
+            launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms, use_filter ? filter.p : nullptr, nbuckets, hot, dense, list, nlist);
             timer.end(hc);
+            CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaStreamSynchronize(s));
             if (h_stats.errflags & kErrTableFull) {  // the estimate was too small: clear the flag and go again with twice the slots
                 if (attempt >= 6) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow at level %d", n);
                 CUDA_TRY(cudaMemsetAsync(&d_stats.p->errflags, 0, sizeof(unsigned int), s));
+                if (use_list) CUDA_TRY(cudaMemsetAsync(cur.p, 0, npos * sizeof(uint32_t), s));
                 cap *= 2;
                 continue;
             }
@@ -622,6 +635,7 @@ int Trainer::run() {
         m->levels[n].windows = windows;
         m->levels[n].cap     = cap;
         m->levels[n].singles = singles;
+        m->levels[n].items   = use_list ? nlist : npos;
 
         int hp = timer.begin(COLIBRI_T_PRUNE);
         Segment sg;
@@ -701,13 +715,28 @@ int Trainer::run() {
         segs.push_back(std::move(sg));
         if (sk.skip) segs.push_back(std::move(sk));
 
+        bool next_list = false;
         if ((n < o.MAXLENGTH || indexed_skip) && kept > 0) {
             if (t > 1) {
+                // the next level runs from a position list when this level's survivors cover a small part of the corpus
+                next_list = n < o.MAXLENGTH && tune.sparse_div > 0 && occ * tune.sparse_div <= npos && occ < 0xFFFFFFF0ull;
                 hp = timer.begin(COLIBRI_T_PRUNE);
-                launches += launch_relabel(s, cur.p, npos, bitmap.p);
+                if (next_list) {
+                    if (list_next.n < occ + 8) TRY(list_next.alloc(dev, occ + 8));
+                    CUDA_TRY(cudaMemsetAsync(&d_stats.p->cursor, 0, sizeof(unsigned long long), s));
+                }
+                launches += launch_relabel(s, cur.p, npos, bitmap.p, list, nlist, next_list ? list_next.p : nullptr, &d_stats.p->cursor, sms);
                 timer.end(hp);
+                if (next_list) {
+                    TRY(read_stats());
+                    if (h_stats.cursor != occ)
+                        return set_err(COLIBRI_E_CUDA, "level %d: %llu surviving positions listed, %llu occurrences kept", n, (unsigned long long)h_stats.cursor, (unsigned long long)occ);
+                    std::swap(list_cur, list_next);
+                    nlist = occ;
+                }
             }
         }
+        list_valid = next_list;
         if (!keep_all_ids) ids[n - 1].reset();  // ping-pong: only the newest level is needed
         prev_kept = kept;
         prev_occ  = occ;
@@ -743,6 +772,8 @@ int Trainer::run() {
                 // :1221-1229: after pass n, level n-1 is emptied when it is below MINLENGTH
                 int k = sg.n;
                 if (k < o.MINLENGTH && last_pass >= k + 1 && k != o.MAXBACKOFFLENGTH && !(k == 1 && o.MINTOKENS_UNIGRAMS > o.MINTOKENS)) drop = true;
+                // :1278-1280: the level the back-off rule needed until the end goes last, `prune(-1, MAXBACKOFFLENGTH)` when it is below MINLENGTH
+                if (k == o.MAXBACKOFFLENGTH && o.MAXBACKOFFLENGTH < o.MINLENGTH) drop = true;
             } else if (o.MINLENGTH > 1 && sg.n <= o.MINLENGTH - 1) {
                 drop = true;  // :1337-1341 prunebylength
             }

@@ -184,6 +184,48 @@ struct Segment {  // survivors of one (level, category)
     DevBuf<uint32_t> occ_pos;  // indexed + DOSKIPGRAMS: the nrefs occurrence positions of this level in corpus order
 };
 
+// ------------------------------------------------------------------------------------------------ tuning knobs
+// When the large-corpus machinery switches on.  Read from the environment at every train call (not cached), so that the parity
+// suite can force every path -- occurrence filter with a crowded bucket array, hot-key cache, dense pair slots, list mode --
+// on corpora small enough for the oracle, and so that A/B measurements need no rebuild.
+struct Tuning {
+    uint64_t filter_min      = 1ull << 25;  // COLIBRI_B200_FILTER_MIN: smallest level (upper bound of its windows) that gets the occurrence filter
+    int      filter_log2_min = 20;          // COLIBRI_B200_FILTER_LOG2_MIN / _LOG2: the filter has 2^min .. 2^max buckets (>= 2 per window where that fits)
+    int      filter_log2_max = 28;
+    bool     no_filter       = false;       // COLIBRI_B200_NO_FILTER
+    int      hot_mode        = 1;           // COLIBRI_B200_HOT: per-block hot-key cache 0 never, 1 levels >= hot_min, 2 always
+    uint64_t hot_min         = 1ull << 25;  // COLIBRI_B200_HOT_MIN
+    uint32_t dense_dim       = 2048;        // COLIBRI_B200_DENSE: side of the directly addressed square of level 2 (0 = off)
+    uint64_t dense_min       = 1ull << 25;  // COLIBRI_B200_DENSE_MIN
+    uint32_t sparse_div      = 4;           // COLIBRI_B200_SPARSE_DIV: level n+1 runs from a position list when occurrences(n) * div <= positions (0 = never)
+    static uint64_t env_u64(const char* name, uint64_t dflt) {
+        const char* e = getenv(name);
+        return e && *e ? strtoull(e, nullptr, 10) : dflt;
+    }
+    static Tuning from_env() {
+        Tuning t;
+        t.filter_min      = env_u64("COLIBRI_B200_FILTER_MIN", t.filter_min);
+        t.filter_log2_min = (int)env_u64("COLIBRI_B200_FILTER_LOG2_MIN", t.filter_log2_min);
+        t.filter_log2_max = (int)env_u64("COLIBRI_B200_FILTER_LOG2", t.filter_log2_max);
+        t.filter_log2_min = std::max(6, std::min(t.filter_log2_min, 32));
+        t.filter_log2_max = std::max(t.filter_log2_min, std::min(t.filter_log2_max, 32));
+        t.no_filter       = getenv("COLIBRI_B200_NO_FILTER") != nullptr;
+        t.hot_mode        = (int)env_u64("COLIBRI_B200_HOT", t.hot_mode);
+        t.hot_min         = env_u64("COLIBRI_B200_HOT_MIN", t.hot_min);
+        t.dense_dim       = (uint32_t)std::min<uint64_t>(env_u64("COLIBRI_B200_DENSE", t.dense_dim), 16384);
+        t.dense_min       = env_u64("COLIBRI_B200_DENSE_MIN", t.dense_min);
+        t.sparse_div      = (uint32_t)env_u64("COLIBRI_B200_SPARSE_DIV", t.sparse_div);
+        return t;
+    }
+    bool     use_filter(uint32_t mintokens, uint64_t bound) const { return mintokens >= 2 && !no_filter && bound >= filter_min; }
+    bool     use_hot(uint64_t bound) const { return hot_mode == 2 || (hot_mode == 1 && bound >= hot_min); }
+    uint64_t filter_buckets(uint64_t bound) const {
+        uint64_t nb = 1ull << filter_log2_min;
+        while (nb < 2 * bound && nb < (1ull << filter_log2_max)) nb <<= 1;
+        return nb;
+    }
+};
+
 int check_options(colibri_b200_options& o);
 // compute_skip_configurations (reference src/algorithms.cpp:79-94) with the run decomposition the kernels need
 int skip_masks(int n, int maxskips, std::vector<SkipMask>& out);
@@ -209,7 +251,7 @@ struct colibri_b200_corpus {
 
 
 struct PassStat { uint64_t n, found, foundskip, pruned; };
-struct LevelInfo { uint64_t windows = 0, cap = 0, singles = 0; double ms = 0; };
+struct LevelInfo { uint64_t windows = 0, cap = 0, singles = 0, items = 0; double ms = 0; };
 struct colibri_b200_model {
     int      device = 0;
     int      model_type = COLIBRI_UNINDEXEDPATTERNMODEL;

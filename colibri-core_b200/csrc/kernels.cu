@@ -212,11 +212,8 @@ __global__ void __launch_bounds__(256) make_id1_kernel(const uint32_t* __restric
 }
 
 int launch_unigram_hist(cudaStream_t s, const uint32_t* tok, uint64_t npos, uint32_t* count1, uint32_t, int sms) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(unigram_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHotClasses * 4);
-        configured = true;
-    }
+    // the opt-in is per device (a process may train on several): set it on every call, it costs nothing next to the launch
+    cudaFuncSetAttribute(unigram_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHotClasses * 4);
     unigram_hist_kernel<<<sms * 3, 512, kHotClasses * 4, s>>>(tok, npos, count1);
     return 1;
 }
@@ -278,7 +275,7 @@ __device__ __forceinline__ uint32_t upsert_ngram_at(NgramSlot* __restrict__ tabl
     return 0;
 }
 __device__ __forceinline__ uint32_t upsert_ngram(NgramSlot* __restrict__ table, uint64_t cap, unsigned long long key, uint32_t pos, uint32_t& probes, bool& full) {
-    return upsert_ngram_at(table, cap, fast_range(spooky_hash64_u64(key, 0), cap), key, pos, probes, full);
+    return upsert_ngram_at(table, cap, fast_range(table_hash_u64(key), cap), key, pos, probes, full);
 }
 
 // ---- the occurrence filter (MINTOKENS >= 2 only).  Most distinct n-grams of a corpus occur once and are pruned right
@@ -294,20 +291,40 @@ __device__ __forceinline__ void filter_locate(uint64_t h, uint64_t nbuckets_mask
     shift           = (uint32_t)(bucket & 15) * 2;
 }
 
-__global__ void __launch_bounds__(256) ngram_filter_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t* __restrict__ filter, uint64_t nbuckets_mask,
-                                                           DeviceStats* __restrict__ st, const uint32_t dense) {
+// Two ways to enumerate the windows of a level (template parameter kList):
+//   dense   item j IS position j; prev[] is streamed (levels whose (n-1)-grams cover most of the corpus)
+//   list    item j is position list[j]: the positions whose (n-1)-gram survived, written by the previous level's relabel step.
+//           Higher levels of a natural corpus are sparse (Zipf 100 M tokens: 18 % of the positions carry a surviving trigram, 4 % a
+//           4-gram), and a dense pass still pays the id stream, the hash of every warp that holds one valid lane, and the id write
+//           for ALL positions.  In list mode cur[] is zeroed by a memset and written only where a window exists.
+template <bool kList>
+__device__ __forceinline__ bool load_window(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ list, uint64_t j, uint64_t& p, uint32_t& a, uint32_t& b) {
+    if (kList) {
+        p = __ldcs(list + j);
+        a = __ldg(prev + p);  // non-zero by construction, but read anyway: it is half of the key
+    } else {
+        p = j;
+        a = __ldcs(prev + p);
+    }
+    b = __ldg(prev + p + 1);  // prev has npos + 1 readable entries, the last one 0
+    return a != 0 && b != 0;
+}
+
+template <bool kList>
+__global__ void __launch_bounds__(256) ngram_filter_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ list, uint64_t nitems, uint32_t* __restrict__ filter,
+                                                           uint64_t nbuckets_mask, DeviceStats* __restrict__ st, const uint32_t dense) {
     __shared__ uint64_t scratch[8];
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint32_t       valid = 0, twice = 0;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += stride) {
-        uint32_t a = __ldcs(prev + p);
-        uint32_t b = __ldg(prev + p + 1);
-        if (a == 0 || b == 0) continue;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nitems; j += stride) {
+        uint64_t p;
+        uint32_t a, b;
+        if (!load_window<kList>(prev, list, j, p, a, b)) continue;
         ++valid;
         if (a < dense && b < dense) continue;  // a pair of frequent classes has its own directly addressed slot (see count_ngrams_kernel)
         uint64_t word;
         uint32_t shift;
-        filter_locate(spooky_hash64_u64(((unsigned long long)a << 32) | b, 0), nbuckets_mask, word, shift);
+        filter_locate(table_hash_u64(((unsigned long long)a << 32) | b), nbuckets_mask, word, shift);
         uint32_t bits = (__ldcg(filter + word) >> shift) & 3u;
         if (bits == 3u) continue;  // already saturated: hot keys stop here with a plain L2 read
         if ((bits & 1u) == 0) {
@@ -353,10 +370,11 @@ __device__ __forceinline__ uint32_t upsert_dense(NgramSlot* __restrict__ table, 
     return (uint32_t)slot + 1;
 }
 
-template <bool kFilter, bool kDense>
-__global__ void __launch_bounds__(256, kDense ? 7 : 8) count_ngrams_kernel(const uint32_t* __restrict__ prev, uint32_t* __restrict__ cur, uint64_t npos, NgramSlot* __restrict__ table,
-                                                           uint64_t cap, const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, DeviceStats* __restrict__ st,
-                                                           const bool hot, const uint32_t dense) {
+template <bool kFilter, bool kDense, bool kList>
+__global__ void __launch_bounds__(256, kDense ? 7 : 8) count_ngrams_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ list, uint64_t nitems,
+                                                                           uint32_t* __restrict__ cur, NgramSlot* __restrict__ table, uint64_t cap,
+                                                                           const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, DeviceStats* __restrict__ st, const bool hot,
+                                                                           const uint32_t dense) {
     __shared__ uint64_t scratch[8];
     __shared__ unsigned long long hot_key[kHotLines];
     __shared__ uint32_t hot_slot[kHotLines];
@@ -371,11 +389,10 @@ __global__ void __launch_bounds__(256, kDense ? 7 : 8) count_ngrams_kernel(const
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint32_t       valid = 0, probes = 0, singles = 0;
     bool           full = false;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += stride) {
-        uint32_t a  = __ldcs(prev + p);
-        uint32_t b  = __ldg(prev + p + 1);  // prev has npos+1 entries, the last one 0
-        uint32_t id = 0;
-        if (a != 0 && b != 0) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nitems; j += stride) {
+        uint64_t p;
+        uint32_t a, b, id = 0;
+        if (load_window<kList>(prev, list, j, p, a, b)) {
             ++valid;
             const unsigned long long key = ((unsigned long long)a << 32) | b;
             if (kDense && a < dense && b < dense) {
@@ -395,7 +412,7 @@ __global__ void __launch_bounds__(256, kDense ? 7 : 8) count_ngrams_kernel(const
                     }
                 }
             } else {
-                const uint64_t h  = spooky_hash64_u64(key, 0);
+                const uint64_t h  = table_hash_u64(key);
                 bool           go = true;
                 if (kFilter) {
                     uint64_t word;
@@ -405,7 +422,7 @@ __global__ void __launch_bounds__(256, kDense ? 7 : 8) count_ngrams_kernel(const
                     singles += !go;
                 }
                 if (go) {
-                    const uint32_t           line   = (uint32_t)(h >> 20) & (kHotLines - 1);
+                    const uint32_t     line   = (uint32_t)(h >> 20) & (kHotLines - 1);
                     unsigned long long cached = ~0ull;
                     if (hot) cached = *(volatile unsigned long long*)&hot_key[line];
                     if (cached == key) {  // its slot was published before the key (below)
@@ -422,202 +439,10 @@ __global__ void __launch_bounds__(256, kDense ? 7 : 8) count_ngrams_kernel(const
                 }
             }
         }
-        __stcs(cur + p, id);
-    }
-    if (hot) {
-        __syncthreads();
-        for (uint32_t l = threadIdx.x; l < kHotLines; l += blockDim.x) {
-            uint32_t c = hot_pending[l];
-            if (c) atomicAdd(&table[hot_slot[l] - 1].count, c);
-        }
-    }
-    uint64_t v  = block_reduce_sum(valid, scratch);
-    uint64_t pr = block_reduce_sum(probes, scratch);
-    uint64_t sg = block_reduce_sum(singles, scratch);
-    if (threadIdx.x == 0) {
-        if (v) atomicAdd(&st->valid_windows, (unsigned long long)v);
-        if (pr) atomicAdd(&st->probes, (unsigned long long)pr);
-        if (sg) atomicAdd(&st->singletons, (unsigned long long)sg);
-    }
-    if (full) atomicOr(&st->errflags, kErrTableFull);
-}
-
-// ---- memory-level parallelism (experiment, off by default: COLIBRI_B200_MLP=2|4).  Both kernels above are chains of dependent
-// long-latency operations per window (id load -> filter word -> table sector -> claim); at 98 % occupancy the stall reason is the
-// scoreboard, with HBM at ~37 % and L2 at ~34 % of their byte throughput (profiles/r01_count_ngrams_ncu.md).  The variants below give every
-// thread U windows per iteration and issue each stage for all U before consuming any result, so that U chains are in flight per thread.
-// Same operations, same table contents and statistics (the parity suite passes with U = 4).  MEASURED (B200, 100 M tokens): the count
-// family takes 7.8 ms with U = 1, 11.9 ms with U = 2, 13.9 ms with U = 4 -- more requests in flight make it slower, i.e. the random-sector
-// path is already saturated (queueing, not latency, is what the warps wait on).  Kept as the evidence for that conclusion.
-template <int U>
-__global__ void __launch_bounds__(256) ngram_filter_mlp_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t* __restrict__ filter, uint64_t nbuckets_mask,
-                                                               DeviceStats* __restrict__ st) {
-    __shared__ uint64_t scratch[8];
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint32_t       valid = 0, twice = 0;
-    for (uint64_t p0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p0 < npos; p0 += stride * U) {
-        uint32_t a[U], b[U], shift[U], bits[U];
-        uint64_t word[U];
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const uint64_t p = p0 + (uint64_t)k * stride;
-            a[k] = p < npos ? __ldcs(prev + p) : 0u;
-            b[k] = p < npos ? __ldg(prev + p + 1) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            bits[k] = 3u;  // 3 = nothing left to do for this window
-            word[k] = 0;
-            shift[k] = 0;
-            if (a[k] != 0 && b[k] != 0) {
-                ++valid;
-                filter_locate(spooky_hash64_u64(((unsigned long long)a[k] << 32) | b[k], 0), nbuckets_mask, word[k], shift[k]);
-                bits[k] = 0x80u;  // marker: load pending
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < U; ++k)
-            if (bits[k] == 0x80u) bits[k] = (__ldcg(filter + word[k]) >> shift[k]) & 3u;
-        uint32_t old1[U];
-#pragma unroll
-        for (int k = 0; k < U; ++k) {  // first hit of a bucket
-            old1[k] = 0xFFFFFFFFu;
-            if ((bits[k] & 1u) == 0) old1[k] = atomicOr(filter + word[k], 1u << shift[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < U; ++k)
-            if ((bits[k] & 1u) == 0) bits[k] = ((old1[k] >> shift[k]) & 1u) == 0 ? 3u /* this window was the first: done */ : ((old1[k] >> shift[k]) & 3u);
-        uint32_t old2[U];
-#pragma unroll
-        for (int k = 0; k < U; ++k) {  // second hit
-            old2[k] = 0xFFFFFFFFu;
-            if ((bits[k] & 2u) == 0) old2[k] = atomicOr(filter + word[k], 2u << shift[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < U; ++k)
-            if ((bits[k] & 2u) == 0) twice += ((old2[k] >> shift[k]) & 2u) == 0;  // this thread moved the bucket to "seen twice"
-    }
-    uint64_t v  = block_reduce_sum(valid, scratch);
-    uint64_t tw = block_reduce_sum(twice, scratch);
-    if (threadIdx.x == 0) {
-        if (v) atomicAdd(&st->valid_windows, (unsigned long long)v);
-        if (tw) atomicAdd(&st->found, (unsigned long long)tw);
-    }
-}
-
-// upsert whose first probe was already loaded (`first` = key field of `slot`)
-__device__ __forceinline__ uint32_t upsert_ngram_from(NgramSlot* __restrict__ table, uint64_t cap, uint64_t slot, unsigned long long key, uint32_t pos, unsigned long long first,
-                                                      uint32_t& probes, bool& full) {
-    const uint64_t     limit = cap < kMaxProbe ? cap : kMaxProbe;
-    unsigned long long cur   = first;
-    for (uint64_t step = 0; step < limit; ++step) {
-        NgramSlot* s = table + slot;
-        if (step) cur = __ldcg(&s->key);
-        ++probes;
-        if (cur == 0) {
-            unsigned long long o0, o1;
-            cas128(s, key, 1ull | ((unsigned long long)pos << 32), o0, o1);
-            if (o0 == 0) return (uint32_t)slot + 1;
-            cur = o0;
-        }
-        if (cur == key) {
-            atomicAdd(&s->count, 1u);
-            return (uint32_t)slot + 1;
-        }
-        slot = slot + 1 == cap ? 0 : slot + 1;
-    }
-    full = true;
-    return 0;
-}
-
-template <bool kFilter, int U>
-__global__ void __launch_bounds__(256, 4) count_ngrams_mlp_kernel(const uint32_t* __restrict__ prev, uint32_t* __restrict__ cur, uint64_t npos, NgramSlot* __restrict__ table,
-                                                                  uint64_t cap, const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, DeviceStats* __restrict__ st,
-                                                                  const bool hot) {
-    __shared__ uint64_t scratch[8];
-    __shared__ unsigned long long hot_key[kHotLines];
-    __shared__ uint32_t hot_slot[kHotLines];
-    __shared__ uint32_t hot_pending[kHotLines];
-    if (hot) {
-        for (uint32_t i = threadIdx.x; i < kHotLines; i += blockDim.x) {
-            hot_key[i]     = 0;
-            hot_pending[i] = 0;
-        }
-        __syncthreads();
-    }
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint32_t       valid = 0, probes = 0, singles = 0;
-    bool           full = false;
-    for (uint64_t p0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p0 < npos; p0 += stride * U) {
-        uint32_t           a[U], b[U], id[U], line[U];
-        uint64_t           slot[U];
-        unsigned long long first[U];
-        uint32_t           fw[U], fshift[U];
-        int                state[U];  // 0: no window / filtered / served by the hot cache, 1: goes to the table
-        // stage 1: the ids of the two (n-1)-grams
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const uint64_t p = p0 + (uint64_t)k * stride;
-            a[k] = p < npos ? __ldcs(prev + p) : 0u;
-            b[k] = p < npos ? __ldg(prev + p + 1) : 0u;
-        }
-        // stage 2: hash, filter word
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            id[k]    = 0;
-            state[k] = 0;
-            fw[k]    = 0xFFFFFFFFu;
-            fshift[k] = 0;
-            slot[k]  = 0;
-            line[k]  = 0;
-            if (a[k] != 0 && b[k] != 0) {
-                ++valid;
-                const uint64_t h = spooky_hash64_u64(((unsigned long long)a[k] << 32) | b[k], 0);
-                slot[k]  = fast_range(h, cap);
-                line[k]  = (uint32_t)(h >> 20) & (kHotLines - 1);
-                state[k] = 1;
-                if (kFilter) {
-                    uint64_t word;
-                    filter_locate(h, nbuckets_mask, word, fshift[k]);
-                    fw[k] = __ldg(filter + word);
-                }
-            }
-        }
-        // stage 3: filter verdict, hot cache, first probe of the table
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            first[k] = 0;
-            if (state[k] == 1) {
-                if (kFilter && ((fw[k] >> fshift[k]) & 2u) == 0) {
-                    ++singles;
-                    state[k] = 0;
-                    continue;
-                }
-                const unsigned long long key = ((unsigned long long)a[k] << 32) | b[k];
-                if (hot && *(volatile unsigned long long*)&hot_key[line[k]] == key) {
-                    atomicAdd(&hot_pending[line[k]], 1u);
-                    id[k]    = *(volatile uint32_t*)&hot_slot[line[k]];
-                    state[k] = 0;
-                    continue;
-                }
-                first[k] = __ldcg(&table[slot[k]].key);
-            }
-        }
-        // stage 4: resolve
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const uint64_t p = p0 + (uint64_t)k * stride;
-            if (state[k] == 1) {
-                const unsigned long long key = ((unsigned long long)a[k] << 32) | b[k];
-                id[k] = upsert_ngram_from(table, cap, slot[k], key, (uint32_t)p, first[k], probes, full);
-                if (hot && id[k] != 0 && *(volatile unsigned long long*)&hot_key[line[k]] == 0ull && atomicCAS(&hot_key[line[k]], 0ull, kHotBusy) == 0ull) {
-                    hot_slot[line[k]] = id[k];
-                    __threadfence_block();
-                    *(volatile unsigned long long*)&hot_key[line[k]] = key;
-                }
-            }
-            if (p < npos) __stcs(cur + p, id[k]);
-        }
+        if (!kList)
+            __stcs(cur + p, id);
+        else if (id != 0)
+            cur[p] = id;  // cur was zeroed by the host
     }
     if (hot) {
         __syncthreads();
@@ -737,21 +562,86 @@ __global__ void __launch_bounds__(256) prune_table_kernel(const Slot* __restrict
     }
 }
 
-// after pruning: a position keeps its id only if its n-gram survived (bit test in the L2-resident survivor bitmap)
-__global__ void __launch_bounds__(256) relabel_kernel(uint32_t* __restrict__ cur, uint64_t npos, const uint32_t* __restrict__ bitmap) {
+// ---- relabel: after pruning a position keeps its id only if its n-gram survived (bit test in the L2-resident survivor bitmap).
+// Three shapes: dense -> dense (in place), dense -> dense + the list of surviving positions (when the next level will run in
+// list mode), list -> dense + list.  A block compacts its survivors with one atomicAdd on the list cursor (a per-warp cursor atomic
+// serialises on a single L2 address); inside a block the positions stay ascending, so the list is sorted in runs of <= 1024.
+__device__ __forceinline__ bool id_survives(uint32_t id, const uint32_t* __restrict__ bitmap) {
+    return id != 0 && ((__ldg(bitmap + ((id - 1) >> 5)) >> ((id - 1) & 31)) & 1u) != 0;
+}
+// every thread contributes `c` (0..4) values; returns the thread's first output index in list_out
+__device__ __forceinline__ uint64_t block_reserve(uint32_t c, unsigned long long* __restrict__ cursor, uint32_t* warp_tot, unsigned long long* base_smem) {
+    uint32_t incl = warp_inclusive_scan(c);
+    if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) {
+            uint32_t t  = warp_tot[w];
+            warp_tot[w] = tot;
+            tot += t;
+        }
+        *base_smem = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    uint64_t out = *base_smem + warp_tot[threadIdx.x >> 5] + (incl - c);
+    __syncthreads();  // warp_tot / base_smem are reused by the caller's next round
+    return out;
+}
+
+template <bool kEmit>
+__global__ void __launch_bounds__(256) relabel_kernel(uint32_t* __restrict__ cur, uint64_t npos, const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ list_out,
+                                                      unsigned long long* __restrict__ cursor) {
+    __shared__ uint32_t warp_tot[8];
+    __shared__ unsigned long long base_smem;
     uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i >= npos) return;
+    uint32_t c[4] = {0, 0, 0, 0};
+    uint32_t n = 0;
     if (i + 4 <= npos) {
-        uint4    v    = *reinterpret_cast<uint4*>(cur + i);
-        uint32_t c[4] = {v.x, v.y, v.z, v.w};
+        uint4 v = *reinterpret_cast<uint4*>(cur + i);
+        c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+        bool changed = false;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (c[k] != 0 && ((__ldg(bitmap + ((c[k] - 1) >> 5)) >> ((c[k] - 1) & 31)) & 1u) == 0) c[k] = 0;
-        *reinterpret_cast<uint4*>(cur + i) = make_uint4(c[0], c[1], c[2], c[3]);
-    } else {
-        for (; i < npos; ++i) {
-            uint32_t id = cur[i];
-            if (id != 0 && ((__ldg(bitmap + ((id - 1) >> 5)) >> ((id - 1) & 31)) & 1u) == 0) cur[i] = 0;
+            if (c[k] != 0) {
+                if (id_survives(c[k], bitmap)) ++n;
+                else { c[k] = 0; changed = true; }
+            }
+        if (changed) *reinterpret_cast<uint4*>(cur + i) = make_uint4(c[0], c[1], c[2], c[3]);
+    } else if (i < npos) {
+        for (int k = 0; k < 4 && i + k < npos; ++k) {
+            uint32_t id = cur[i + k];
+            if (id_survives(id, bitmap)) { c[k] = id; ++n; }
+            else if (id != 0) cur[i + k] = 0;
+        }
+    }
+    if (kEmit) {
+        uint64_t out = block_reserve(n, cursor, warp_tot, &base_smem);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c[k] != 0) list_out[out++] = (uint32_t)(i + k);
+    }
+}
+
+__global__ void __launch_bounds__(256) relabel_list_kernel(uint32_t* __restrict__ cur, const uint32_t* __restrict__ list_in, uint64_t nitems, const uint32_t* __restrict__ bitmap,
+                                                           uint32_t* __restrict__ list_out, unsigned long long* __restrict__ cursor) {
+    __shared__ uint32_t warp_tot[8];
+    __shared__ unsigned long long base_smem;
+    const uint64_t rounds = (nitems + (uint64_t)gridDim.x * blockDim.x - 1) / ((uint64_t)gridDim.x * blockDim.x);
+    for (uint64_t r = 0; r < rounds; ++r) {
+        // consecutive blocks take consecutive 256-item tiles of a round, so the output keeps the input's rough order
+        const uint64_t j = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        uint32_t p = 0;
+        bool     keep = false;
+        if (j < nitems) {
+            p = __ldcs(list_in + j);
+            const uint32_t id = cur[p];
+            keep = id_survives(id, bitmap);
+            if (id != 0 && !keep) cur[p] = 0;
+        }
+        if (list_out != nullptr) {  // uniform
+            uint64_t out = block_reserve(keep ? 1u : 0u, cursor, warp_tot, &base_smem);
+            if (keep) list_out[out] = p;
         }
     }
 }
@@ -762,97 +652,39 @@ static int blocks_per_sm(const void* fn, int threads, size_t smem) {
     return n > 0 ? n : 1;
 }
 
-// experiment knob: cap the resident blocks per SM of a kernel by padding its dynamic shared memory (COLIBRI_B200_COUNT_BPS / _FILTER_BPS)
-static size_t throttle_smem(const void* fn, const char* env, size_t static_smem, int* bps_out) {
-    const char* e = getenv(env);
-    int         want = e ? atoi(e) : 0;
-    if (want <= 0 || want >= 8) return 0;
-    size_t per = (size_t)227 * 1024 / (size_t)want;
-    per        = per > static_smem + 1024 ? per - static_smem - 1024 : 0;
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per);
-    if (bps_out) *bps_out = want;
-    return per;
-}
-
-// windows per thread per iteration of the filter / count kernels (COLIBRI_B200_MLP = 1, 2 or 4; 1 = the one-window kernels)
-static int mlp_env(const char* name) {
-    const char* e = getenv(name);
-    if (!e) e = getenv("COLIBRI_B200_MLP");
-    int v = e ? atoi(e) : 1;
-    return v == 1 || v == 2 || v == 4 ? v : 1;
-}
-static int mlp_width_filter() {
-    static int u = mlp_env("COLIBRI_B200_MLP_FILTER");
-    return u;
-}
-static int mlp_width() {
-    static int u = mlp_env("COLIBRI_B200_MLP_COUNT");
-    return u;
-}
-int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms, uint32_t dense) {
-    const int u = dense ? 1 : mlp_width_filter();
-    if (u == 4) {
-        static unsigned per_sm = 0;
-        if (!per_sm) per_sm = blocks_per_sm((const void*)ngram_filter_mlp_kernel<4>, 256, 0);
-        unsigned grid = (unsigned)umin64(div_up(div_up(npos, 4), 256), (uint64_t)sms * per_sm * 4);
-        ngram_filter_mlp_kernel<4><<<grid ? grid : 1, 256, 0, s>>>(prev, npos, filter, nbuckets - 1, st);
-        return 1;
-    }
-    if (u == 2) {
-        static unsigned per_sm = 0;
-        if (!per_sm) per_sm = blocks_per_sm((const void*)ngram_filter_mlp_kernel<2>, 256, 0);
-        unsigned grid = (unsigned)umin64(div_up(div_up(npos, 2), 256), (uint64_t)sms * per_sm * 4);
-        ngram_filter_mlp_kernel<2><<<grid ? grid : 1, 256, 0, s>>>(prev, npos, filter, nbuckets - 1, st);
-        return 1;
-    }
-    static int    bps = blocks_per_sm((const void*)ngram_filter_kernel, 256, 0);
-    static size_t pad = throttle_smem((const void*)ngram_filter_kernel, "COLIBRI_B200_FILTER_BPS", 64, &bps);
-    unsigned      grid = (unsigned)umin64(div_up(npos, 256), (uint64_t)sms * bps * 4);
-    ngram_filter_kernel<<<grid ? grid : 1, 256, pad, s>>>(prev, npos, filter, nbuckets - 1, st, dense);
+int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms, uint32_t dense, const uint32_t* list,
+                        uint64_t nlist) {
+    const uint64_t nitems = list ? nlist : npos;
+    if (!nitems) return 0;
+    static int bps  = blocks_per_sm((const void*)ngram_filter_kernel<false>, 256, 0);
+    unsigned   grid = (unsigned)umin64(div_up(nitems, 256), (uint64_t)sms * bps * 4);
+    if (list)
+        ngram_filter_kernel<true><<<grid, 256, 0, s>>>(prev, list, nitems, filter, nbuckets - 1, st, dense);
+    else
+        ngram_filter_kernel<false><<<grid, 256, 0, s>>>(prev, nullptr, nitems, filter, nbuckets - 1, st, dense);
     return 1;
 }
-template <bool kFilter, int U>
-static void launch_count_mlp(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms, const uint32_t* filter,
-                             uint64_t nbuckets, bool hot) {
-    static unsigned per_sm = 0;
-    if (!per_sm) per_sm = blocks_per_sm((const void*)count_ngrams_mlp_kernel<kFilter, U>, 256, 0);
-    unsigned grid = (unsigned)umin64(div_up(div_up(npos, U), 256), (uint64_t)sms * per_sm * 4);
-    count_ngrams_mlp_kernel<kFilter, U><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, filter, kFilter ? nbuckets - 1 : 0, st, hot);
+template <bool kFilter, bool kDense, bool kList>
+static void launch_count_variant(cudaStream_t s, const uint32_t* prev, const uint32_t* list, uint64_t nitems, uint32_t* cur, NgramSlot* table, uint64_t cap, const uint32_t* filter,
+                                 uint64_t nbuckets, DeviceStats* st, int sms, bool hot, uint32_t dense) {
+    static int bps  = blocks_per_sm((const void*)count_ngrams_kernel<kFilter, kDense, kList>, 256, 0);
+    unsigned   grid = (unsigned)umin64(div_up(nitems, 256), (uint64_t)sms * bps * 4);
+    count_ngrams_kernel<kFilter, kDense, kList><<<grid, 256, 0, s>>>(prev, list, nitems, cur, table, cap, filter, kFilter ? nbuckets - 1 : 0, st, hot, dense);
 }
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms, const uint32_t* filter,
-                        uint64_t nbuckets, bool hot, uint32_t dense) {
-    const int u = dense ? 1 : mlp_width();
-    if (u == 4) {
-        if (filter != nullptr) launch_count_mlp<true, 4>(s, prev, cur, npos, table, cap, st, sms, filter, nbuckets, hot);
-        else launch_count_mlp<false, 4>(s, prev, cur, npos, table, cap, st, sms, nullptr, 0, hot);
-        return 1;
-    }
-    if (u == 2) {
-        if (filter != nullptr) launch_count_mlp<true, 2>(s, prev, cur, npos, table, cap, st, sms, filter, nbuckets, hot);
-        else launch_count_mlp<false, 2>(s, prev, cur, npos, table, cap, st, sms, nullptr, 0, hot);
-        return 1;
-    }
-    static int    bps0 = blocks_per_sm((const void*)count_ngrams_kernel<false, false>, 256, 0);
-    static int    bps1 = blocks_per_sm((const void*)count_ngrams_kernel<true, false>, 256, 0);
-    static size_t pad0 = throttle_smem((const void*)count_ngrams_kernel<false, false>, "COLIBRI_B200_COUNT_BPS", 16448, &bps0);
-    static size_t pad1 = throttle_smem((const void*)count_ngrams_kernel<true, false>, "COLIBRI_B200_COUNT_BPS", 16448, &bps1);
-    uint64_t      want = div_up(npos, 256);
-    if (dense) {
-        static int bpsd0 = blocks_per_sm((const void*)count_ngrams_kernel<false, true>, 256, 0);
-        static int bpsd1 = blocks_per_sm((const void*)count_ngrams_kernel<true, true>, 256, 0);
-        if (filter != nullptr) {
-            unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bpsd1 * 4);
-            count_ngrams_kernel<true, true><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, filter, nbuckets - 1, st, hot, dense);
-        } else {
-            unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bpsd0 * 4);
-            count_ngrams_kernel<false, true><<<grid ? grid : 1, 256, 0, s>>>(prev, cur, npos, table, cap, nullptr, 0, st, hot, dense);
-        }
-    } else if (filter != nullptr) {
-        unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bps1 * 4);
-        count_ngrams_kernel<true, false><<<grid ? grid : 1, 256, pad1, s>>>(prev, cur, npos, table, cap, filter, nbuckets - 1, st, hot, 0);
+                        uint64_t nbuckets, bool hot, uint32_t dense, const uint32_t* list, uint64_t nlist) {
+    const uint64_t nitems = list ? nlist : npos;
+    if (!nitems) return 0;
+    const bool f = filter != nullptr;
+    if (list) {  // (the dense square belongs to level 2, which never runs from a list: its input is the class ids themselves)
+        if (f) launch_count_variant<true, false, true>(s, prev, list, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, 0);
+        else launch_count_variant<false, false, true>(s, prev, list, nitems, cur, table, cap, nullptr, 0, st, sms, hot, 0);
+    } else if (dense) {
+        if (f) launch_count_variant<true, true, false>(s, prev, nullptr, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, dense);
+        else launch_count_variant<false, true, false>(s, prev, nullptr, nitems, cur, table, cap, nullptr, 0, st, sms, hot, dense);
     } else {
-        unsigned grid = (unsigned)umin64(want, (uint64_t)sms * bps0 * 4);
-        count_ngrams_kernel<false, false><<<grid ? grid : 1, 256, pad0, s>>>(prev, cur, npos, table, cap, nullptr, 0, st, hot, 0);
+        if (f) launch_count_variant<true, false, false>(s, prev, nullptr, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, 0);
+        else launch_count_variant<false, false, false>(s, prev, nullptr, nitems, cur, table, cap, nullptr, 0, st, sms, hot, 0);
     }
     return 1;
 }
@@ -863,8 +695,17 @@ int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, ui
     prune_table_kernel<NgramSlot, false><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, nullptr, bitmap, slot_index, st, nullptr, 0);
     return 1;
 }
-int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap) {
-    relabel_kernel<<<div_up(div_up(npos, 4), 256), 256, 0, s>>>(cur, npos, bitmap);
+int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap, const uint32_t* list_in, uint64_t nlist_in, uint32_t* list_out, unsigned long long* cursor,
+                   int sms) {
+    if (list_in != nullptr) {
+        if (!nlist_in) return 0;
+        unsigned grid = (unsigned)umin64(div_up(nlist_in, 256), (uint64_t)sms * 8);
+        relabel_list_kernel<<<grid, 256, 0, s>>>(cur, list_in, nlist_in, bitmap, list_out, cursor);
+    } else if (list_out != nullptr) {
+        relabel_kernel<true><<<div_up(div_up(npos, 4), 256), 256, 0, s>>>(cur, npos, bitmap, list_out, cursor);
+    } else {
+        relabel_kernel<false><<<div_up(div_up(npos, 4), 256), 256, 0, s>>>(cur, npos, bitmap, nullptr, nullptr);
+    }
     return 1;
 }
 
@@ -874,7 +715,7 @@ int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t*
 // contiguous non-gap runs, each of which is a surviving k-gram (k < n) whose id sits in ids[k][p + start].
 // find-or-claim the slot of a 128-bit key; returns slot index + 1 (0 when the table is full)
 __device__ __forceinline__ uint32_t upsert_skipkey(SkipSlot* __restrict__ table, uint64_t cap, unsigned long long k0, unsigned long long k1, bool count, uint32_t pos) {
-    uint64_t slot = fast_range(spooky_hash64_u128(k0, k1, 0), cap);
+    uint64_t slot = fast_range(table_hash_u128(k0, k1), cap);
     for (uint64_t step = 0; step < cap; ++step) {
         SkipSlot*          s  = table + slot;
         ulonglong2         kv = __ldcg(reinterpret_cast<const ulonglong2*>(s));
@@ -964,7 +805,7 @@ __global__ void __launch_bounds__(256) skip_types_kernel(const uint32_t* const* 
         const int      tail = n - (32 - __clz(mask));                // trailing non-gap tokens
         const uint32_t cid  = __ldg(ids[n - head - tail] + p + head);  // id of the content k-gram
         const unsigned long long key = ((unsigned long long)slot << 32) | cid;
-        uint64_t       at    = fast_range(spooky_hash64_u64(key, 0), cap);
+        uint64_t       at    = fast_range(table_hash_u64(key), cap);
         const uint64_t limit = cap < kMaxProbe ? cap : kMaxProbe;
         uint64_t       step  = 0;
         for (; step < limit; ++step) {

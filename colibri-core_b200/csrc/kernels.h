@@ -71,15 +71,21 @@ int launch_make_id1(cudaStream_t s, const uint32_t* tok, uint64_t npos, const ui
 // ---- K2: n-gram upsert (the dominant kernel), K3: prune/compact, relabel
 // occurrence filter: nbuckets (power of two) 2-bit saturating counters, nbuckets/4 bytes, zeroed by the caller; st->found := buckets hit twice
 // dense (level 2 only): windows whose two class ids are both below it bypass the filter (they own directly addressed slots, see launch_count_ngrams)
-int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms, uint32_t dense = 0);
+// list != NULL: the windows are the nlist positions list[j] (positions whose (n-1)-gram survived) instead of every position 0..npos
+int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms, uint32_t dense = 0,
+                        const uint32_t* list = nullptr, uint64_t nlist = 0);
 // filter == NULL: every valid window goes to the table.  dense > 0: the table has cap + dense * dense slots; a window (a, b) with a, b < dense is
 // counted in slot cap + a * dense + b (no hash, no filter, no probing), every other window in the hashed part [0, cap)
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms,
-                        const uint32_t* filter = nullptr, uint64_t nbuckets = 0, bool hot = false /* per-block shared-memory cache for frequent keys */, uint32_t dense = 0);
+                        const uint32_t* filter = nullptr, uint64_t nbuckets = 0, bool hot = false /* per-block shared-memory cache for frequent keys */, uint32_t dense = 0,
+                        const uint32_t* list = nullptr /* list mode: cur must have been zeroed by the caller */, uint64_t nlist = 0);
 // bitmap: (cap+31)/32 words, bit = slot survived (may be NULL)
 int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap, DeviceStats* st, int sms,
                         uint32_t* slot_index = nullptr /* slot -> survivor index + 1, for the forward index */);
-int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap);
+// cur[p] := 0 where the n-gram of p was pruned.  list_in != NULL: only the nlist_in positions list_in[j] are visited (everything else in cur
+// is zero already).  list_out != NULL: the surviving positions are appended to it through *cursor (zeroed by the caller; rough corpus order).
+int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap, const uint32_t* list_in = nullptr, uint64_t nlist_in = 0, uint32_t* list_out = nullptr,
+                   unsigned long long* cursor = nullptr, int sms = 148);
 
 // ---- skipgrams (config 3)
 // occ_pos != NULL: npos counts entries of occ_pos (explicit window positions) instead of corpus positions; item_slot (optional): slot + 1 per (window, mask)

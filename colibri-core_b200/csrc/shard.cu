@@ -296,11 +296,11 @@ extern "C" int colibri_b200_shard_level_owner(colibri_b200_shard* sh, const void
     CUDA_TRY(cudaMemcpyAsync(sh->d_aux.p, src_base, (sh->world + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
 
     const uint32_t t          = sh->t;
-    const bool     use_filter = t >= 2 && nrecv >= (1ull << 25) && !getenv("COLIBRI_B200_NO_FILTER");
+    const Tuning   tune       = Tuning::from_env();
+    const bool     use_filter = tune.use_filter(t, nrecv);
     uint64_t       nbuckets = 0, cap = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);
     if (use_filter) {
-        nbuckets = 1ull << 20;
-        while (nbuckets < 2 * nrecv && nbuckets < (1ull << 28)) nbuckets <<= 1;
+        nbuckets = tune.filter_buckets(nrecv);
         if (sh->filter.n < nbuckets / 16) TRY(sh->filter.alloc(sh->dev, nbuckets / 16));
         CUDA_TRY(cudaMemsetAsync(sh->filter.p, 0, nbuckets / 4, s));
         TRY(zero_phase_stats(sh));
@@ -485,11 +485,11 @@ extern "C" int colibri_b200_shard_p2p_owner(colibri_b200_shard* sh, uint64_t sta
     if (sh->rid.n < phys) TRY(sh->rid.alloc(sh->dev, phys));
 
     const uint32_t t          = sh->t;
-    const bool     use_filter = t >= 2 && nrecv >= (1ull << 25) && !getenv("COLIBRI_B200_NO_FILTER");
+    const Tuning   tune       = Tuning::from_env();
+    const bool     use_filter = tune.use_filter(t, nrecv);
     uint64_t       nbuckets = 0, cap = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);
     if (use_filter) {
-        nbuckets = 1ull << 20;
-        while (nbuckets < 2 * nrecv && nbuckets < (1ull << 28)) nbuckets <<= 1;
+        nbuckets = tune.filter_buckets(nrecv);
         if (sh->filter.n < nbuckets / 16) TRY(sh->filter.alloc(sh->dev, nbuckets / 16));
         CUDA_TRY(cudaMemsetAsync(sh->filter.p, 0, nbuckets / 4, s));
         TRY(zero_phase_stats(sh));

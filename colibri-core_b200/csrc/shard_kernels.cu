@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) stream_filter_kernel(const unsigned long 
         if (!slot_valid(i, slot_cap, slot_counts)) continue;
         uint64_t word;
         uint32_t shift;
-        stream_filter_locate(spooky_hash64_u64(__ldcs(keys + i), 0), nbuckets_mask, word, shift);
+        stream_filter_locate(table_hash_u64(__ldcs(keys + i)), nbuckets_mask, word, shift);
         uint32_t bits = (__ldcg(filter + word) >> shift) & 3u;
         if (bits == 3u) continue;
         if ((bits & 1u) == 0) {
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256) stream_count_kernel(const unsigned long l
             continue;
         }
         const unsigned long long key = __ldcs(keys + i);
-        const uint64_t           h   = spooky_hash64_u64(key, 0);
+        const uint64_t           h   = table_hash_u64(key);
         uint32_t                 out = 0;
         bool                     go  = true;
         if (filter != nullptr) {
@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(256) skip_stream_count_kernel(const ulonglong2
     const uint64_t limit = cap < 8192 ? cap : 8192;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const ulonglong2 key  = __ldcs(recv + i);
-        uint64_t         slot = fast_range(spooky_hash64_u128(key.x, key.y, 0), cap);
+        uint64_t         slot = fast_range(table_hash_u128(key.x, key.y), cap);
         uint64_t         step = 0;
         for (; step < limit; ++step) {
             SkipSlot*          s  = table + slot;

@@ -133,6 +133,10 @@ int main(int argc, char** argv) {
             case 'W': options.MINTOKENS_UNIGRAMS = atoi(optarg); break;
             case 'q': options.QUIET = true; break;
             case 'd': device = atoi(optarg); break;
+            case 'c':  // the class file only matters to the views (decoding patterns for print/report); training never opens it (reference :506, :857-865)
+                if (!options.QUIET) std::cerr << "Note: class file " << optarg << " is not needed to build a model; ignored" << std::endl;
+                break;
+            case 'D': options.DEBUG = true; break;  // reference :511
             case 'i': inputmodelfile = optarg; break;
             case 'j': inputmodelfile2 = optarg; break;
             case 'S':

@@ -176,6 +176,9 @@ int colibri_b200_model_counters(const colibri_b200_model* m, uint64_t out[8]);
 /* per level n>=2: out[0]=valid windows, out[1]=table capacity in slots, out[2]=ms of the level's filter + count kernels,
  * out[3]=windows the occurrence filter proved to be singletons (they never reach the table: upserts = out[0] - out[3]) */
 int colibri_b200_model_level_counters(const colibri_b200_model* m, int n, double out[4]);
+/* same plus out[4]=items the level's kernels enumerated: every position (dense mode), or the length of the position list the previous
+ * level left behind (list mode: only positions whose (n-1)-gram survived are visited); out[5..7] reserved (0) */
+int colibri_b200_model_level_info(const colibri_b200_model* m, int n, double out[8]);
 
 /* ---- multi-GPU: one process per GPU drives these per-rank phases and moves the buffers between ranks itself
  * (torch.distributed / NCCL all-to-all); the library does no communication.  Model = hash-partitioned across ranks,

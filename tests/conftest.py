@@ -71,3 +71,27 @@ def cli_load_and_train_options(case):
         return dict(mintokens=t, minlength=m, maxlength=l, doreset=1, indexed=indexed), dict(mintokens=t, maxlength=l, minlength=m, indexed=indexed, streamed=0), True
     # -j: PatternSetModel(file, options); an unindexed output model streams the corpus file
     return dict(mintokens=t, minlength=m, maxlength=l, indexed=0), dict(mintokens=t, maxlength=l, minlength=m, indexed=indexed, streamed=1 if case["unindexed"] else 0), False
+
+
+# ---- the large-corpus machinery of the device path, forced onto small inputs (csrc/engine_common.h: Tuning).
+# bench.py runs 100 M tokens per GPU, where the occurrence filter, the per-block hot-key cache, the dense pair slots of level 2 and the
+# list mode of the sparse levels are all on; the oracle cannot follow there in seconds, so the parity suite switches each of them on by
+# environment knob on corpora it can check, with a filter so small (2^8 .. 2^12 buckets) that buckets collide all the time.
+FORCED_PATHS = {
+    "default": {},
+    "filter": {"COLIBRI_B200_FILTER_MIN": "0", "COLIBRI_B200_FILTER_LOG2_MIN": "8", "COLIBRI_B200_FILTER_LOG2": "12", "COLIBRI_B200_HOT": "0", "COLIBRI_B200_SPARSE_DIV": "0",
+               "COLIBRI_B200_DENSE": "0"},
+    "filter+hot+dense": {"COLIBRI_B200_FILTER_MIN": "0", "COLIBRI_B200_FILTER_LOG2_MIN": "10", "COLIBRI_B200_FILTER_LOG2": "16", "COLIBRI_B200_HOT": "2", "COLIBRI_B200_DENSE_MIN": "0",
+                         "COLIBRI_B200_DENSE": "48", "COLIBRI_B200_SPARSE_DIV": "0"},
+    "list": {"COLIBRI_B200_SPARSE_DIV": "1", "COLIBRI_B200_HOT": "0"},
+    "bench": {"COLIBRI_B200_FILTER_MIN": "0", "COLIBRI_B200_FILTER_LOG2_MIN": "12", "COLIBRI_B200_FILTER_LOG2": "20", "COLIBRI_B200_HOT": "2", "COLIBRI_B200_DENSE_MIN": "0",
+              "COLIBRI_B200_DENSE": "2048", "COLIBRI_B200_SPARSE_DIV": "1"},
+}
+
+
+def force_path(monkeypatch, name):
+    for k in ("COLIBRI_B200_FILTER_MIN", "COLIBRI_B200_FILTER_LOG2_MIN", "COLIBRI_B200_FILTER_LOG2", "COLIBRI_B200_HOT", "COLIBRI_B200_HOT_MIN", "COLIBRI_B200_DENSE",
+              "COLIBRI_B200_DENSE_MIN", "COLIBRI_B200_SPARSE_DIV", "COLIBRI_B200_NO_FILTER"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in FORCED_PATHS[name].items():
+        monkeypatch.setenv(k, v)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import case_id, corpus_body, load_cases
+from conftest import FORCED_PATHS, case_id, corpus_body, force_path, load_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -45,8 +45,12 @@ def supported(case):
     return True
 
 
+@pytest.mark.parametrize("path", list(FORCED_PATHS))
 @pytest.mark.parametrize("case", CASES, ids=[case_id(c) for c in CASES])
-def test_gpu_matches_reference_golden(golden, case):
+def test_gpu_matches_reference_golden(golden, case, path, monkeypatch):
+    """Every golden case of the unmodified reference, through every code path of the level loop (conftest.FORCED_PATHS: the occurrence
+    filter with colliding buckets, the hot-key cache, the dense pair slots, the list mode -- what bench.py runs at 100 M tokens)."""
+    force_path(monkeypatch, path)
     body = corpus_body(golden, case["corpus"])
     if not supported(case):
         with pytest.raises(cb().ColibriError) as ei:
@@ -110,7 +114,9 @@ def test_modelfile_written_by_gpu_is_reference_layout(golden):
 
 @pytest.mark.parametrize("kw", [dict(ntokens=3000000, vocab=100000, seed=11, mean_sentence=22), dict(ntokens=2000000, vocab=50000, seed=12, mean_sentence=18, phrase_permille=200, nphrases=5000)])
 @pytest.mark.parametrize("skip", [0, 1])
-def test_gpu_matches_oracle_on_seeded_synthetic(kw, skip):
+@pytest.mark.parametrize("path", list(FORCED_PATHS))
+def test_gpu_matches_oracle_on_seeded_synthetic(kw, skip, path, monkeypatch):
+    force_path(monkeypatch, path)
     corpus = cb().Corpus.synthetic(**kw)
     body = corpus.download()
     m = cb().train(corpus, MINTOKENS=2, MAXLENGTH=5, DOSKIPGRAMS_EXHAUSTIVE=skip, streamed=0 if skip else 1, QUIET=1)
@@ -124,7 +130,13 @@ def test_gpu_matches_oracle_on_seeded_synthetic(kw, skip):
 @pytest.mark.parametrize("kw,maxlength,mintokens", [(dict(ntokens=1500000, vocab=60000, seed=31, mean_sentence=22), 5, 2),
                                                     (dict(ntokens=800000, vocab=2000, seed=32, mean_sentence=9, phrase_permille=300, nphrases=300), 8, 3),
                                                     (dict(ntokens=300000, vocab=500, seed=33, mean_sentence=30), 3, 1)])
-def test_indexed_model_matches_oracle(kw, maxlength, mintokens):
+@pytest.mark.parametrize("path", ["default", "bench"])
+def test_indexed_model_matches_oracle(kw, maxlength, mintokens, path, monkeypatch):
+    force_path(monkeypatch, path)
+    _indexed_model_matches_oracle(kw, maxlength, mintokens)
+
+
+def _indexed_model_matches_oracle(kw, maxlength, mintokens):
     """Config 4: IndexedPatternModel -- every pattern's sorted (sentence, token) list (datatypes.h:33-89, patternmodel.h:2699-2705, :2789-2800)."""
     corpus = cb().Corpus.synthetic(**kw)
     body = corpus.download()
@@ -210,14 +222,16 @@ def test_error_paths():
         lib.train(bytes([6, 7, 0]), DOSKIPGRAMS=1, DOSKIPGRAMS_EXHAUSTIVE=1)  # patternmodel.h:958-963
 
 
-@pytest.mark.parametrize("seed", range(120))
-def test_gpu_equals_oracle_on_random_input(seed):
-    """Random small corpora (empty/ragged sentences, unknown class, missing final delimiter) x random supported option sets."""
+@pytest.mark.parametrize("seed", range(240))
+def test_gpu_equals_oracle_on_random_input(seed, monkeypatch):
+    """Random small corpora (empty/ragged sentences, unknown class, missing final delimiter) x random supported option sets; the forced
+    code paths of conftest.FORCED_PATHS take turns (seed 0..119: default knobs, as in round 1)."""
     import random
 
     from test_oracle_vs_ref_random import random_case, random_corpus
 
-    rng = random.Random(5000 + seed)
+    force_path(monkeypatch, "default" if seed < 120 else list(FORCED_PATHS)[1 + seed % (len(FORCED_PATHS) - 1)])
+    rng = random.Random(5000 + seed % 120 + (7000 if seed >= 120 else 0))
     body = random_corpus(rng)
     if not body:
         pytest.skip("empty corpus")
@@ -245,12 +259,13 @@ def test_gpu_equals_oracle_on_random_input(seed):
 
 
 @pytest.mark.parametrize("seed", range(60))
-def test_gpu_indexed_skipgrams_equal_oracle_on_random_input(seed):
+def test_gpu_indexed_skipgrams_equal_oracle_on_random_input(seed, monkeypatch):
     """IndexedPatternModel::trainskipgrams (reference :2969-3010) + skip-type pruning on random corpora: patterns, counts, occurrence lists."""
     import random
 
     from test_oracle_vs_ref_random import random_corpus
 
+    force_path(monkeypatch, list(FORCED_PATHS)[seed % len(FORCED_PATHS)])
     rng = random.Random(9000 + seed)
     body = random_corpus(rng)
     if not body:
@@ -299,3 +314,55 @@ def test_gpu_dense_pairs_match_oracle(golden, dense, monkeypatch):
         assert (m.tokens(), m.types(), len(m)) == (want.tokens, want.types, len(want)), (name, okw)
         assert m.passes() == want.passes, (name, okw)
         assert to_flat(m).same_patterns(want), (name, okw)
+
+
+# ---- the benchmark corpus itself, pinned to the unmodified reference (tests/golden/golden_bench.json, written by make_golden_bench.py)
+def _bench_golden():
+    import json
+
+    from conftest import GOLDEN_DIR
+
+    with open(os.path.join(GOLDEN_DIR, "golden_bench.json")) as f:
+        return json.load(f)
+
+
+def _check_against_bench_fixture(name, skip, monkeypatch, path):
+    if name not in _bench_golden():
+        pytest.skip("tests/golden/golden_bench.json has no case %s yet (make_golden_bench.py)" % name)
+    g = _bench_golden()[name]
+    force_path(monkeypatch, path)
+    gen = g["generator"]
+    corpus = cb().Corpus.synthetic(gen["ntokens"], vocab=gen["vocab"], seed=gen["seed"], mean_sentence=gen["mean_sentence"])
+    assert corpus.nbytes == g["corpus_bytes"]  # the device generator produced the bytes the reference was run on
+    m = cb().train(corpus, MINTOKENS=2, MAXLENGTH=5, DOSKIPGRAMS_EXHAUSTIVE=int(skip), streamed=0 if skip else 1, QUIET=1)
+    assert (m.tokens(), m.types(), len(m)) == (g["tokens"], g["types"], g["patterns"])
+    # the reference's progress lines: (found n-grams, found skipgram occurrences, pruned, kept) per pass
+    assert [(p[1], p[3]) for p in m.passes()] == [(p[0], p[2]) for p in g["passes_found_skip_pruned_kept"]]
+    got = to_flat(m)
+    n_of = np.add.reduceat((got.keys < 128).astype(np.int64), got.key_off[:-1].astype(np.int64))
+    per_len = {int(n): [int((n_of == n).sum()), int(got.counts[n_of == n].astype(np.int64).sum())] for n in np.unique(n_of)}
+    assert per_len == {int(k): v for k, v in g["per_length_patterns_occurrences"].items()}
+    assert len(m.to_bytes()) == g["modelfile_bytes"]
+    assert got.digest() == g["digest"]  # every pattern and every count, canonical order
+    return m
+
+
+@pytest.mark.parametrize("path", ["default", "bench"])
+def test_bench_corpus_10m_prefix_matches_reference_fixture(path, monkeypatch):
+    """10 M-token prefix of the benchmark stream, -u -t 2 -l 5, against the unmodified reference's model (digest, passes, file size);
+    `bench` forces filter + hot-key cache + dense pairs + list mode, which a 10 M-token corpus does not reach on its own."""
+    _check_against_bench_fixture("zipf10m", False, monkeypatch, path)
+
+
+def test_bench_corpus_10m_prefix_with_skipgrams_matches_reference_fixture(monkeypatch):
+    """BASELINE.json configs[2] shape (exhaustive skipgrams) on the 10 M-token prefix against the unmodified reference."""
+    _check_against_bench_fixture("zipf10m_skip", True, monkeypatch, "bench")
+
+
+@pytest.mark.slow
+def test_bench_corpus_100m_matches_reference_fixture(monkeypatch):
+    """BASELINE.json configs[1]: the corpus bench.py times (100 M tokens, V = 100 000, seed 1), default knobs -- i.e. exactly the kernels and
+    thresholds the benchmark runs -- bit-exact against the model the unmodified reference wrote for the same bytes (12 CPU-minutes, once)."""
+    m = _check_against_bench_fixture("zipf100m", False, monkeypatch, "default")
+    assert m.level(2)["singletons"] > 0  # the occurrence filter was on ...
+    assert m.level(5)["items"] < m.counters()["positions"] // 4  # ... and the sparse levels ran from a position list

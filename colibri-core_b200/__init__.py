@@ -108,6 +108,7 @@ def library():
     L.colibri_b200_model_counters.argtypes = [C.c_void_p, _u64p]
     L.colibri_b200_model_level_counters.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.colibri_b200_model_level_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    L.colibri_b200_model_checksum.argtypes = [C.c_void_p, _u64p]
     L.colibri_b200_shard_begin.argtypes = [C.c_void_p, C.POINTER(COptions), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.colibri_b200_shard_info.argtypes = [C.c_void_p, _u64p]
     L.colibri_b200_shard_device_ms.argtypes = [C.c_void_p]
@@ -404,6 +405,12 @@ class Model:
         _check(library().colibri_b200_model_counters(self._h, c))
         names = ["positions", "corpus_bytes", "kernel_launches", "ngram_upserts", "skipgram_upserts", "slots_initialised", "unigram_increments", "peak_device_bytes"]
         return {k: int(v) for k, v in zip(names, c)}
+
+    def checksum(self):
+        """Order-independent checksum of the model content (see include/colibri_b200.h): dict of sum, xor, occurrences, patterns, refsum, refs."""
+        out = (C.c_uint64 * 6)()
+        _check(library().colibri_b200_model_checksum(self._h, out))
+        return dict(zip(("sum", "xor", "occurrences", "patterns", "refsum", "refs"), (int(x) for x in out)))
 
     def level(self, n):
         out = (C.c_double * 8)()

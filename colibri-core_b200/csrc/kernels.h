@@ -201,6 +201,10 @@ int launch_iota(cudaStream_t s, uint32_t* out, uint64_t n);
 int launch_token_bitmap(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t np, uint32_t* bitmap /* zeroed, (maxclass >> 5) + 1 words */);
 int launch_popcount(cudaStream_t s, const uint32_t* words, uint64_t n, unsigned long long* total /* zeroed */);
 
+// order-independent checksum: out[0] += sum, out[1] ^= xor of the per-pattern values, out[2] += occurrences, out[4] += per-reference values (out zeroed by the caller)
+int launch_model_checksum(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint32_t* counts, uint64_t np, uint64_t* keyhash /* may be NULL */, unsigned long long* out);
+int launch_refs_checksum(cudaStream_t s, const uint64_t* keyhash, const uint64_t* ref_off, uint64_t np, const uint32_t* rs, const uint16_t* rt, uint64_t nrefs, unsigned long long* out);
+
 // ---- parity helpers / measurement input
 int launch_hash64_batch(cudaStream_t s, const uint8_t* keys, const uint64_t* off, uint64_t n, uint64_t* out);
 int launch_synth_lengths(cudaStream_t s, uint64_t seed, uint64_t ntokens, uint64_t first, uint32_t vocab, uint32_t mean_sentence, uint32_t phrase_permille, uint32_t nphrases,

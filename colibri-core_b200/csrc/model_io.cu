@@ -435,6 +435,34 @@ extern "C" int colibri_b200_model_load(const uint8_t* file, size_t nbytes, const
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ checksum
+// out[0] = sum and out[1] = xor over the patterns of fmix64(FNV1a64(key bytes) ^ count * K), out[2] = total occurrences, out[3] = patterns,
+// out[4] = sum over the stored references of fmix64(FNV1a64(key) ^ (sentence << 16 | token) * K') (indexed models, else 0), out[5] = references.
+// Order-independent: shares of a sharded model add up (out[1]: xor) to the checksum of the whole.
+extern "C" int colibri_b200_model_checksum(colibri_b200_model* m, uint64_t out[6]) {
+    if (!m || !out) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    memset(out, 0, 6 * sizeof(uint64_t));
+    out[3] = m->npatterns;
+    if (m->npatterns == 0) return 0;
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    const bool   refs = m->model_type == COLIBRI_INDEXEDPATTERNMODEL && m->d_ref_off.p && m->nrefs;
+    DevBuf<unsigned long long> d;
+    DevBuf<uint64_t>           kh;
+    TRY(d.alloc(m->device, 8));
+    if (refs) TRY(kh.alloc(m->device, m->npatterns));
+    CUDA_TRY(cudaMemsetAsync(d.p, 0, 8 * sizeof(unsigned long long), s));
+    launch_model_checksum(s, m->d_keys.p, m->d_off.p, m->d_counts.p, m->npatterns, refs ? kh.p : nullptr, d.p);
+    if (refs) launch_refs_checksum(s, kh.p, m->d_ref_off.p, m->npatterns, m->d_ref_sentence.p, m->d_ref_token.p, m->nrefs, d.p);
+    unsigned long long h[8];
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h, d.p, sizeof h, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[4] = h[4];
+    out[5] = refs ? m->nrefs : 0;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ queries
 extern "C" int colibri_b200_model_lookup_batch(colibri_b200_model* m, const uint8_t* keys, const uint64_t* key_off, uint64_t n, uint32_t* counts, int64_t* index) {
     if (!m || !key_off || (!counts && !index)) return set_err(COLIBRI_E_INVALID, "NULL argument");

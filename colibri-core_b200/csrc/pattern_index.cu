@@ -823,4 +823,61 @@ int launch_popcount(cudaStream_t s, const uint32_t* words, uint64_t n, unsigned 
     return 1;
 }
 
+// ---- order-independent checksum of a model (measurement / parity aid: equal models give equal sums whatever order the table scans,
+// the ranks or the reference's unordered_map put the patterns in).  Per pattern: FNV-1a 64 of the key bytes, mixed with the count;
+// per occurrence of an indexed model: the same key hash mixed with (sentence, token).  Sums wrap modulo 2^64.
+__device__ __forceinline__ uint64_t fnv1a64(const uint8_t* __restrict__ p, uint64_t len) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint64_t i = 0; i < len; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+    return h;
+}
+__global__ void __launch_bounds__(256) model_checksum_kernel(const uint8_t* __restrict__ keys, const uint64_t* __restrict__ off, const uint32_t* __restrict__ counts, uint64_t np,
+                                                             uint64_t* __restrict__ keyhash /* may be NULL */, unsigned long long* __restrict__ out) {
+    __shared__ uint64_t scratch[8];
+    uint64_t sum = 0, x = 0, occ = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t b = off[i], e = off[i + 1];
+        const uint64_t h = fnv1a64(keys + b, e - b);
+        if (keyhash) keyhash[i] = h;
+        const uint64_t v = fmix64(h ^ ((uint64_t)counts[i] * 0x9E3779B97F4A7C15ull));
+        sum += v;
+        x ^= v;
+        occ += counts[i];
+    }
+    sum = block_reduce_sum(sum, scratch);
+    occ = block_reduce_sum(occ, scratch);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x ^= __shfl_xor_sync(0xffffffffu, x, d);
+    if (threadIdx.x == 0) {
+        atomicAdd(&out[0], (unsigned long long)sum);
+        atomicAdd(&out[2], (unsigned long long)occ);
+    }
+    if (lane_id() == 0) atomicXor(&out[1], (unsigned long long)x);
+}
+__global__ void __launch_bounds__(256) refs_checksum_kernel(const uint64_t* __restrict__ keyhash, const uint64_t* __restrict__ ref_off, uint64_t np, const uint32_t* __restrict__ rs,
+                                                            const uint16_t* __restrict__ rt, uint64_t nrefs, unsigned long long* __restrict__ out) {
+    __shared__ uint64_t scratch[8];
+    uint64_t sum = 0;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nrefs; j += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t lo = 0, hi = np;  // the pattern whose list holds reference j: last i with ref_off[i] <= j
+        while (hi - lo > 1) {
+            uint64_t mid = (lo + hi) / 2;
+            if (__ldg(ref_off + mid) <= j) lo = mid; else hi = mid;
+        }
+        sum += fmix64(keyhash[lo] ^ ((((uint64_t)rs[j] << 16) | rt[j]) * 0xD6E8FEB86659FD93ull));
+    }
+    sum = block_reduce_sum(sum, scratch);
+    if (threadIdx.x == 0) atomicAdd(&out[4], (unsigned long long)sum);
+}
+int launch_model_checksum(cudaStream_t s, const uint8_t* keys, const uint64_t* off, const uint32_t* counts, uint64_t np, uint64_t* keyhash, unsigned long long* out) {
+    if (!np) return 0;
+    model_checksum_kernel<<<(unsigned)std::min<uint64_t>(pi_div_up(np, 256), 148 * 16), 256, 0, s>>>(keys, off, counts, np, keyhash, out);
+    return 1;
+}
+int launch_refs_checksum(cudaStream_t s, const uint64_t* keyhash, const uint64_t* ref_off, uint64_t np, const uint32_t* rs, const uint16_t* rt, uint64_t nrefs, unsigned long long* out) {
+    if (!nrefs || !np) return 0;
+    refs_checksum_kernel<<<(unsigned)std::min<uint64_t>(pi_div_up(nrefs, 256), 148 * 16), 256, 0, s>>>(keyhash, ref_off, np, rs, rt, nrefs, out);
+    return 1;
+}
+
 }  // namespace colibri

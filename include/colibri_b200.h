@@ -175,6 +175,12 @@ int colibri_b200_model_timings(const colibri_b200_model* m, double ms[COLIBRI_T_
 int colibri_b200_model_counters(const colibri_b200_model* m, uint64_t out[8]);
 /* per level n>=2: out[0]=valid windows, out[1]=table capacity in slots, out[2]=ms of the level's filter + count kernels,
  * out[3]=windows the occurrence filter proved to be singletons (they never reach the table: upserts = out[0] - out[3]) */
+/* order-independent checksum of the model's (pattern bytes, count[, occurrence list]) content: out[0] = sum and out[1] = xor over the patterns of
+ * fmix64(FNV1a64(key bytes) ^ count * 0x9E3779B97F4A7C15), out[2] = total occurrences, out[3] = patterns, out[4] = sum over the stored references
+ * of fmix64(FNV1a64(key) ^ (sentence << 16 | token) * 0xD6E8FEB86659FD93) (indexed models), out[5] = references.  The shares of a sharded model
+ * combine (add / xor) to the checksum of the whole; the reference's model file yields the same numbers (tests/checksum.py).  Measurement aid: lets
+ * bench.py compare 10^8-pattern models across GPU counts and against committed fixtures without shipping and sorting them. */
+int colibri_b200_model_checksum(colibri_b200_model* m, uint64_t out[6]);
 int colibri_b200_model_level_counters(const colibri_b200_model* m, int n, double out[4]);
 /* same plus out[4]=items the level's kernels enumerated: every position (dense mode), or the length of the position list the previous
  * level left behind (list mode: only positions whose (n-1)-gram survived are visited); out[5..7] reserved (0) */

@@ -9,7 +9,8 @@ container and its output is committed.  Also pins two shorter prefixes of the sa
 too) and the exhaustive-skipgram variant (config 3 shape) on the 10 M prefix.
 
 What is recorded per case: tokens, types, pattern count, per-pass (found, pruned), per-length (patterns, sum of counts), the size of
-the written model file and the canonical digest (oracle.FlatModel.digest: sha256 over the bytewise-sorted (key, count) stream).
+the written model file, the canonical digest (oracle.FlatModel.digest: sha256 over the bytewise-sorted (key, count) stream) and the
+order-independent checksum (tests/checksum.py = colibri_b200_model_checksum) that bench.py compares at every GPU count.
 """
 import json
 import os
@@ -21,7 +22,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
 import oracle  # noqa: E402
+from checksum import flat_checksum  # noqa: E402
 
 CASES = [
     # name, ntokens, vocab, seed, skipgrams
@@ -71,7 +74,7 @@ def main():
             "generator": {"ntokens": ntok, "vocab": vocab, "seed": seed, "mean_sentence": 22}, "corpus_bytes": int(body.size),
             "cli": "-u -t 2 -l 5" + (" -s" if skip else ""), "tokens": int(fm.tokens), "types": int(fm.types), "patterns": len(fm),
             "passes_found_skip_pruned_kept": passes, "per_length_patterns_occurrences": per_length(fm), "modelfile_bytes": len(blob),
-            "digest": fm.digest(), "reference_train_seconds": st.get("train_seconds"), "reference_wall_seconds": round(wall, 1),
+            "digest": fm.digest(), "checksum": flat_checksum(fm), "reference_train_seconds": st.get("train_seconds"), "reference_wall_seconds": round(wall, 1),
             "host": "development container, 1 core (the reference is single-threaded)",
         }
         print(name, json.dumps(result[name])[:400], flush=True)

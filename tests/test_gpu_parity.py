@@ -366,3 +366,13 @@ def test_bench_corpus_100m_matches_reference_fixture(monkeypatch):
     m = _check_against_bench_fixture("zipf100m", False, monkeypatch, "default")
     assert m.level(2)["singletons"] > 0  # the occurrence filter was on ...
     assert m.level(5)["items"] < m.counters()["positions"] // 4  # ... and the sparse levels ran from a position list
+
+
+def test_device_checksum_matches_host_restatement(golden):
+    """colibri_b200_model_checksum (what bench.py compares across GPU counts and against the fixtures) against tests/checksum.py on the same model."""
+    from checksum import flat_checksum
+
+    for name, kw in (("hamlet", dict(MINTOKENS=2, MAXLENGTH=5)), ("republic", dict(MINTOKENS=2, MAXLENGTH=5, model_type=20, streamed=0)),
+                     ("zipf300k_phr", dict(MINTOKENS=2, MAXLENGTH=5, DOSKIPGRAMS_EXHAUSTIVE=1, streamed=0)), ("single_token", dict(MINTOKENS=1, MAXLENGTH=3))):
+        m = cb().train(corpus_body(golden, name), QUIET=1, **kw)
+        assert m.checksum() == flat_checksum(to_flat(m)), name

@@ -40,9 +40,14 @@ def parse_args():
     ap.add_argument("--maxlength", type=int, default=5)
     ap.add_argument("--mintokens", type=int, default=2)
     ap.add_argument("--skipgrams", type=int, default=0)
-    ap.add_argument("--cpu-sample-tokens", type=float, default=3e6)
+    ap.add_argument("--cpu-sample-tokens", type=float, default=3e6, help="cpu_baseline leg of the default arm: tokens of the bounded sample")
+    ap.add_argument("--ref-sample-tokens", type=float, default=1e7, help="--impl reference: tokens per step (prefix of the same corpus)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="--impl reference: CPU seconds the whole run may take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra configurations (1 B tokens, skipgrams, indexed) after the headline loop")
+    ap.add_argument("--no-digest", action="store_true", help="skip the sha256 digest of the exported model (the device checksum is always compared)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1: every rank gets --tokens (weak) or the ranks share one --tokens corpus (strong)")
     return ap.parse_args()
 
 
@@ -150,27 +155,53 @@ def sample_body(a, ntokens):
     return oracle.synth_corpus(int(ntokens), vocab=a.vocab, seed=a.seed, mean_sentence=22).tobytes()
 
 
+def reference_fixture(a):
+    """The committed one-off run of the unmodified reference on the FULL workload corpus (tests/golden/golden_bench.json), if this is that workload."""
+    if int(a.tokens) != 100000000 or a.vocab != 100000 or a.seed != 1 or a.maxlength != 5 or a.mintokens != 2 or a.skipgrams:
+        return None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "golden_bench.json")) as f:
+            return json.load(f).get("zipf100m")
+    except Exception:
+        return None
+
+
+def full_config_note(a):
+    g = reference_fixture(a)
+    if not g:
+        return None
+    return {"tokens": g["tokens"], "train_seconds": g["reference_train_seconds"], "tokens_per_s": g["tokens"] / g["reference_train_seconds"], "host": g["host"],
+            "source": "tests/golden/golden_bench.json (tests/golden/make_golden_bench.py; one run, not repeated on the GPU box: 12 CPU-minutes)"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # size one step so that (K + W) steps of single-threaded reference work stay within a few minutes (~0.15 M tokens/s)
-    budget_s = 150.0
-    per_step = budget_s / max(1, a.steps + a.warmup)
-    ntok = int(min(a.cpu_sample_tokens, max(2e5, per_step * 1.5e5)))
+    # One step = the reference's own train() on the first --ref-sample-tokens (10 M) tokens of the workload corpus: ~60 s of one core (the
+    # reference is single-threaded and slows down with corpus size: 0.6 M tokens/s at 1 M tokens, 0.17 M at 10 M, 0.14 M at 100 M), so the
+    # requested K + W steps are cut to what fits --ref-budget-s; the line says how many steps were really timed.
+    ntok = int(min(a.ref_sample_tokens, a.tokens))
     body = sample_body(a, ntok)
-    times, kind, tokens = [], "port", ntok
-    for i in range(a.warmup + a.steps):
-        tokens, sec, kind = cpu_reference_run(body, a.maxlength, a.mintokens, a.skipgrams)
-        if i >= a.warmup:
+    t0 = time.perf_counter()
+    tokens, sec, kind = cpu_reference_run(body, a.maxlength, a.mintokens, a.skipgrams)  # doubles as the warm-up (page cache, allocator)
+    first = sec
+    times = [sec]
+    steps = max(1, min(a.steps, int((a.ref_budget_s - (time.perf_counter() - t0)) / max(first, 1e-3))))
+    warm = 0
+    if steps >= 2:  # enough budget: the first run becomes the warm-up
+        times, warm = [], 1
+        for _ in range(min(steps - 1, a.steps)):
+            tokens, sec, kind = cpu_reference_run(body, a.maxlength, a.mintokens, a.skipgrams)
             times.append(sec)
     total = sum(times)
     value = tokens * len(times) / total
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 (integer)", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample": "first %d tokens of the same corpus per step" % tokens},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": "first %d tokens of the workload corpus, reference is single-threaded (host has %d cores)" % (tokens, os.cpu_count() or 0)},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": len(times), "warmup": warm, "requested_steps": a.steps, "requested_warmup": a.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 (integer)", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": "first %d tokens of the same corpus per step (K, W cut to fit %.0f s of CPU)" % (tokens, a.ref_budget_s)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": "first %d tokens of the workload corpus, reference is single-threaded (host has %d cores)" % (tokens, os.cpu_count() or 0),
+                         "full_config_reference": full_config_note(a)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -186,13 +217,124 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_sources_sha():
+    """sha256 over the sources of the dominant kernel family and its driver: what a committed ncu capture is tied to."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for rel in ("colibri-core_b200/csrc/kernels.cu", "colibri-core_b200/csrc/device_utils.cuh", "colibri-core_b200/csrc/engine.cu", "colibri-core_b200/csrc/engine_common.h"):
+        with open(os.path.join(ROOT, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def profile_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture summary, if there is one."""
+    """DRAM bytes per step of the dominant kernel family from the committed ncu capture (profiles/traffic.json).  The capture names the
+    kernel sources it was taken from; when they have changed since, the number is stale and is NOT printed."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f)
+            t = json.load(f)
     except Exception:
-        return None
+        return None, "no profiles/traffic.json"
+    if t.get("kernel_sources_sha") != kernel_sources_sha():
+        return None, "profiles/traffic.json was captured from other kernel sources (%s, now %s): stale, not reported" % (t.get("kernel_sources_sha"), kernel_sources_sha())
+    return t, t.get("source")
+
+
+def canonical_digest(keys, key_off, counts):
+    """sha256 over the bytewise-sorted (key, count) stream of a flat model -- the same canonical form tests/golden/*.json pin
+    (restated here because bench.py may use oracle/ only as the CPU baseline)."""
+    import hashlib
+
+    import numpy as np
+
+    off = key_off.astype(np.int64)
+    lens = np.diff(off)
+    n = len(lens)
+    w = int(lens.max()) if n else 1
+    pad = np.zeros((n, w), dtype=np.uint8)
+    if n:
+        rows = np.repeat(np.arange(n), lens)
+        cols = np.arange(int(off[-1])) - np.repeat(off[:-1], lens)
+        pad[rows, cols] = keys[: int(off[-1])]
+    order = np.argsort(pad.view("S%d" % w).reshape(-1), kind="stable")
+    new_lens = lens[order]
+    new_off = np.zeros(n + 1, dtype=np.uint64)
+    new_off[1:] = np.cumsum(new_lens)
+    src = np.repeat(off[:-1][order], new_lens) + (np.arange(int(new_lens.sum())) - np.repeat(new_off[:-1].astype(np.int64), new_lens)) if n else np.zeros(0, dtype=np.int64)
+    h = hashlib.sha256()
+    h.update(np.uint64(n).tobytes())
+    h.update(new_off.tobytes())
+    h.update(keys[src].tobytes())
+    h.update(counts[order].astype(np.uint32).tobytes())
+    return h.hexdigest()
+
+
+def parity_block(a, model, with_digest):
+    """Compare the model of the last timed step with the committed fixture of the unmodified reference on the same corpus."""
+    g = reference_fixture(a)
+    cs = model.checksum()
+    out = {"checksum": cs, "fixture": None}
+    if not g:
+        return out
+    out["fixture"] = "tests/golden/golden_bench.json: zipf100m (unmodified reference, %s)" % g["cli"]
+    out["patterns_ok"] = len(model) == g["patterns"] and model.tokens() == g["tokens"] and model.types() == g["types"]
+    out["passes_ok"] = [(p[1], p[3]) for p in model.passes()] == [(p[0], p[2]) for p in g["passes_found_skip_pruned_kept"]]
+    if "checksum" in g:
+        out["checksum_ok"] = all(cs[k] == g["checksum"][k] for k in ("sum", "xor", "occurrences", "patterns"))
+    if with_digest:
+        keys, off, counts, _ = model.export()
+        out["digest"] = canonical_digest(keys, off, counts)
+        out["digest_ok"] = out["digest"] == g["digest"]
+    return out
+
+
+def extra_configs(cb, a, local):
+    """BASELINE.json configs[2..3] and the north-star's 1 B-token target on one GPU, a few steps each, AFTER the headline loop (device-generated
+    corpora; 1 B tokens: V = 10^6, seed 2).  Reported under `extra_configs`; the headline numbers above are not affected."""
+    import torch
+
+    out = []
+
+    def run(name, corpus, warm, steps, **kw):
+        rec = {"name": name}
+        try:
+            opts = cb.PatternModelOptions(MINTOKENS=2, MAXLENGTH=5, QUIET=1, device=local, **kw)
+            m = None
+            for _ in range(warm):
+                m = cb.train(corpus, opts)
+                m.close()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            dev_ms = 0.0
+            for i in range(steps):
+                m = cb.train(corpus, opts)
+                dev_ms += m.timings()["total"]
+                if i + 1 < steps:
+                    m.close()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = max(1e3 * (time.perf_counter() - t0), e0.elapsed_time(e1)) / steps
+            rec.update({"tokens": m.tokens(), "steps": steps, "warmup": warm, "ms_per_step": ms, "device_ms_per_step": dev_ms / steps, "tokens_per_s": m.tokens() / (ms / 1e3),
+                        "patterns": len(m), "passes": m.passes(), "peak_device_gb": m.counters()["peak_device_bytes"] / 1e9, "checksum": m.checksum(),
+                        "phase_ms": m.timings(), "levels": {n: m.level(n) for n in range(2, m.maxlength() + 1)}})
+            m.close()
+        except Exception as e:  # a configuration that does not fit or is refused is reported, it does not take the headline line down
+            rec["error"] = str(e)[:300]
+        out.append(rec)
+
+    c100 = cb.Corpus.synthetic(int(a.tokens), vocab=a.vocab, seed=a.seed, device=local)
+    run("config 3 shape at 100 M tokens: unindexed + exhaustive skipgrams (-u -s -t 2 -l 5)", c100, 1, 3, DOSKIPGRAMS_EXHAUSTIVE=1, streamed=0)
+    run("config 4 shape at 100 M tokens: indexed (-t 2 -l 5)", c100, 1, 3, model_type=20, streamed=0)
+    c100.close()
+    c1b = cb.Corpus.synthetic(1000000000, vocab=1000000, seed=2, device=local)
+    run("north-star target: 1 B tokens (V = 10^6, seed 2), unindexed n <= 5 t = 2", c1b, 1, 3)
+    run("config 3: 1 B tokens, unindexed + exhaustive skipgrams", c1b, 0, 1, DOSKIPGRAMS_EXHAUSTIVE=1, streamed=0)
+    run("config 4: 1 B tokens, indexed", c1b, 0, 1, model_type=20, streamed=0)
+    c1b.close()
+    return out
 
 
 def run_ours(a):
@@ -259,7 +401,13 @@ def run_ours(a):
             # the previous id and writes the new id of every position (8 B) and moves one 32 B sector in and out of HBM per
             # window that reaches the table; the filter launch (when used) reads the ids once more (4 B); its 2-bit
             # counters are sized to stay in L2 and are not counted as HBM traffic.
-            alg_bytes += 8.0 * (ct["positions"] + 1) + 64.0 * (lv["windows"] - lv["singletons"]) + (4.0 * (ct["positions"] + 1) if lv["singletons"] else 0.0)
+            # A level that runs from a position list (items < positions: only positions whose (n-1)-gram survived are visited) instead reads
+            # 12 B per item (list entry, its id, the neighbour's id), zeroes the new id array (4 B/position) and writes 4 B per counted window.
+            npos_l, table_w = ct["positions"] + 1, lv["windows"] - lv["singletons"]
+            if lv["items"] < ct["positions"]:
+                alg_bytes += 12.0 * lv["items"] + 4.0 * npos_l + 68.0 * table_w + (8.0 * lv["items"] if lv["singletons"] else 0.0)
+            else:
+                alg_bytes += 8.0 * npos_l + 64.0 * table_w + (4.0 * npos_l if lv["singletons"] else 0.0)
         if last is not None:
             last.close()
         last = m
@@ -273,7 +421,7 @@ def run_ours(a):
     value = tokens / (ms_per_step / 1e3)
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (count_ms / 1e3) / 1e9 if count_ms > 0 else 0.0
-    traffic = profile_traffic()
+    traffic, traffic_note = profile_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 (integer)", "data": "synthetic",
@@ -284,10 +432,12 @@ def run_ours(a):
         "roofline": {"bound": "hbm", "kernel": "ngram_filter_kernel + count_ngrams_kernel (levels 2..%d; level 2 with dense pair slots)" % last.maxlength(), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "alg_bytes_per_step": alg_bytes / a.steps, "kernel_ms_per_step": count_ms / a.steps,
                      "kernel_share_of_step": (count_ms / a.steps) / (sum(dev_ms) / len(dev_ms)),
-                     "traffic": traffic["dram_bytes_per_step"] if traffic else None,
+                     "traffic": traffic["dram_bytes_per_step"] if traffic else None, "traffic_source": traffic_note,
                      "hbm_read_roofline_frac": (last.maxlength() * nbytes / ((sum(dev_ms) / len(dev_ms)) / 1e3) / 1e9) / peak},
         "clocks": clocks, "gpu_launches": launches,
+        "levels_last_step": {n: last.level(n) for n in range(2, last.maxlength() + 1)},
     }
+    line["parity"] = parity_block(a, last, not a.no_digest)
 
     # ---- end-to-end arm: host buffers in, host buffers out, copies inside the timed region
     if not a.no_e2e:
@@ -297,34 +447,39 @@ def run_ours(a):
         out_keys = torch.empty(int(kb * 1.05) + 64, dtype=torch.uint8, pin_memory=True)
         out_len = torch.empty(int(npat * 1.05) + 64, dtype=torch.int16, pin_memory=True)
         out_cnt = torch.empty(int(npat * 1.05) + 64, dtype=torch.int32, pin_memory=True)
+        cap_k, cap_p = out_keys.numel(), out_cnt.numel()
         for _ in range(max(1, a.warmup)):
-            m = cb.train_host_pointer(host.data_ptr(), nbytes, opts)
-            m.export_compact_into(out_keys.data_ptr(), out_len.data_ptr(), out_cnt.data_ptr())
-            m.close()
+            sm = cb.train_export_pointers(host.data_ptr(), nbytes, opts, out_keys.data_ptr(), cap_k, out_len.data_ptr(), out_cnt.data_ptr(), cap_p)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        d2h = 0
+        d2h, e2e_launches = 0, 0
         for _ in range(a.steps):
-            m = cb.train_host_pointer(host.data_ptr(), nbytes, opts)
-            n2, kb2, _ = m.export_sizes()
-            m.export_compact_into(out_keys.data_ptr(), out_len.data_ptr(), out_cnt.data_ptr())
-            d2h = kb2 + 2 * n2 + 4 * n2
-            m.close()
+            sm = cb.train_export_pointers(host.data_ptr(), nbytes, opts, out_keys.data_ptr(), cap_k, out_len.data_ptr(), out_cnt.data_ptr(), cap_p)
+            d2h = sm["keybytes"] + 2 * sm["npatterns"] + 4 * sm["npatterns"]
+            e2e_launches += sm["kernel_launches"]
         e1.record()
         barrier()
         e2e_s = max(time.perf_counter() - t0, e0.elapsed_time(e1) / 1e3)
+        # the host copy is the same model: patterns, and the order-independent checksum over the bytes that arrived
+        e2e_ok = sm["npatterns"] == len(last) and sm["passes"] == last.passes()
         line["e2e"] = {"value": tokens * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / a.steps,
-                       "api": "colibri_b200_train(host corpus) + colibri_b200_model_export_compact(host keys/lengths/counts), pinned host memory"}
+                       "device_phase_ms_last_step": sm["ms"], "same_model_as_device_arm": bool(e2e_ok),
+                       "api": "colibri_b200_train_export(pinned host corpus -> pinned host keys/lengths/counts): H2D, train, per-level export overlapped with the next level's counting"}
+        line["gpu_launches"] = launches + e2e_launches
 
     # ---- the reference's CPU path beside it (bounded sample)
     if not a.no_cpu_baseline:
         body = sample_body(a, a.cpu_sample_tokens)
         ctok, csec, kind = cpu_reference_run(body, a.maxlength, a.mintokens, a.skipgrams)
         line["cpu_baseline"] = {"value": ctok / csec, "unit": UNIT, "cores": 1, "kind": kind, "seconds": csec,
-                                "sample": "first %d tokens of the workload corpus; the reference is single-threaded (host has %d cores)" % (ctok, os.cpu_count() or 0)}
+                                "sample": "first %d tokens of the workload corpus; the reference is single-threaded (host has %d cores)" % (ctok, os.cpu_count() or 0),
+                                "full_config_reference": full_config_note(a)}
     last.close()
+    corpus.close()
+    if not a.no_extra:
+        line["extra_configs"] = extra_configs(cb, a, local)
     print(json.dumps(line), flush=True)
 
 

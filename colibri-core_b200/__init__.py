@@ -48,6 +48,13 @@ class COptions(C.Structure):
         "DOREMOVEINDEX", "DOREMOVENGRAMS", "DOREMOVESKIPGRAMS", "DOREMOVEFLEXGRAMS", "DORESET")]
 
 
+class CTrainSummary(C.Structure):
+    """struct colibri_b200_train_summary (include/colibri_b200.h)."""
+
+    _fields_ = [("npatterns", C.c_uint64), ("keybytes", C.c_uint64), ("totaltokens", C.c_uint64), ("totaltypes", C.c_uint64), ("maxn", C.c_int32), ("minn", C.c_int32),
+                ("hasskipgrams", C.c_int32), ("npasses", C.c_int32), ("passes", (C.c_uint64 * 4) * 32), ("ms", C.c_double * 16), ("counters", C.c_uint64 * 8)]
+
+
 class CSynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("ntokens", C.c_uint64), ("vocab", C.c_uint32), ("mean_sentence", C.c_uint32), ("phrase_permille", C.c_uint32), ("nphrases", C.c_uint32),
                 ("first_token", C.c_uint64)]
@@ -78,6 +85,7 @@ def library():
     L.colibri_b200_corpus_tokens.argtypes = [C.c_void_p, _u32p, C.c_uint64, _u64p]
     L.colibri_b200_train.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(COptions), C.POINTER(C.c_void_p)]
     L.colibri_b200_train_corpus.argtypes = [C.c_void_p, C.POINTER(COptions), C.POINTER(C.c_void_p)]
+    L.colibri_b200_train_export.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(COptions), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(CTrainSummary)]
     L.colibri_b200_model_free.argtypes = [C.c_void_p]
     L.colibri_b200_model_free.restype = None
     for f in ("size", "tokens", "types"):
@@ -497,6 +505,35 @@ def train_host_pointer(ptr, nbytes, options: PatternModelOptions) -> Model:
     h = C.c_void_p()
     _check(library().colibri_b200_train(ptr, nbytes, C.byref(options._c), C.byref(h)))
     return Model(h)
+
+
+def train_export_pointers(ptr, nbytes, options: PatternModelOptions, keys_ptr, keys_cap, len_ptr, counts_ptr, patterns_cap) -> dict:
+    """colibri_b200_train_export on raw host addresses: corpus in, compact flat model out (keys blob, u16 key lengths, u32 counts), with the
+    copies of finished levels overlapped with the counting of the next.  Returns the summary as a dict."""
+    sm = CTrainSummary()
+    _check(library().colibri_b200_train_export(ptr, nbytes, C.byref(options._c), keys_ptr, keys_cap, len_ptr, counts_ptr, patterns_cap, C.byref(sm)))
+    return {"npatterns": int(sm.npatterns), "keybytes": int(sm.keybytes), "tokens": int(sm.totaltokens), "types": int(sm.totaltypes), "maxn": sm.maxn, "minn": sm.minn,
+            "hasskipgrams": bool(sm.hasskipgrams), "passes": [tuple(int(x) for x in sm.passes[i]) for i in range(min(sm.npasses, 32))],
+            "ms": {PHASE_NAMES[i]: float(sm.ms[i]) for i in range(T_NPHASES)}, "kernel_launches": int(sm.counters[2])}
+
+
+def train_export(body, options: PatternModelOptions | None = None, **kw):
+    """train + compact export in one call (numpy in / numpy out).  Returns (keys, key_len, counts, summary)."""
+    o = options if options is not None else PatternModelOptions(**kw)
+    a = np.ascontiguousarray(np.frombuffer(bytes(body), dtype=np.uint8) if not isinstance(body, np.ndarray) else body, dtype=np.uint8)
+    cap_p, cap_k = 1 << 16, 1 << 20
+    while True:
+        keys, lens, counts = np.empty(cap_k, dtype=np.uint8), np.empty(cap_p, dtype=np.uint16), np.empty(cap_p, dtype=np.uint32)
+        sm = CTrainSummary()
+        rc = library().colibri_b200_train_export(a.ctypes.data if a.size else None, a.size, C.byref(o._c), keys.ctypes.data, cap_k, lens.ctypes.data, counts.ctypes.data, cap_p, C.byref(sm))
+        if rc == 5 and (sm.npatterns > cap_p or sm.keybytes > cap_k):  # COLIBRI_E_CAPACITY: the summary says what is needed
+            cap_p, cap_k = max(cap_p, int(sm.npatterns) + 16), max(cap_k, int(sm.keybytes) + 16)
+            continue
+        _check(rc)
+        n, kb = int(sm.npatterns), int(sm.keybytes)
+        summary = {"tokens": int(sm.totaltokens), "types": int(sm.totaltypes), "maxn": sm.maxn, "minn": sm.minn, "hasskipgrams": bool(sm.hasskipgrams),
+                   "passes": [tuple(int(x) for x in sm.passes[i]) for i in range(min(sm.npasses, 32))]}
+        return keys[:kb], lens[:n], counts[:n], summary
 
 
 def hash64_batch(keys, device=0) -> np.ndarray:

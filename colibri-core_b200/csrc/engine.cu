@@ -6,6 +6,7 @@
 // (:1233-1243), MINLENGTH clean-up (:1221-1229, :1337-1341).  No CPU implementation of the counting exists here:
 // without a CUDA device every entry point fails with COLIBRI_E_CUDA.
 #include "engine_common.h"
+#include "spooky.h"
 
 using namespace colibri;
 
@@ -262,6 +263,38 @@ int colibri::check_options(colibri_b200_options& o) {
 }
 
 namespace {
+// colibri_b200_train_export: the caller's host buffers and the second stream the finished levels leave on
+struct ExportSink {
+    uint8_t*     keys = nullptr;
+    uint16_t*    len16 = nullptr;
+    uint32_t*    counts = nullptr;
+    uint64_t     keys_cap = 0, pat_cap = 0;
+    uint64_t     npat = 0, nbytes = 0;  // what has been handed to the copy stream so far (also: what is needed, on overflow)
+    bool         overflow = false;
+    cudaStream_t xs = nullptr;
+    struct Pending {
+        uint64_t           count = 0;
+        DevBuf<uint32_t>   nm, lens, cnt;
+        DevBuf<uint64_t>   off, tmp;
+        DevBuf<uint16_t>   len16;
+        DevBuf<uint8_t>    keys;
+        unsigned long long* h_kb = nullptr;  // pinned: total key bytes of the segment, written by an async copy on the main stream
+        cudaEvent_t        ready = nullptr;
+    };
+    std::vector<Pending> pending, inflight;
+    unsigned long long*  h_scalars = nullptr;  // pinned, one per segment
+    int                  nscalars = 0;
+    ~ExportSink() {
+        if (xs) {
+            cudaStreamSynchronize(xs);
+            cudaStreamDestroy(xs);
+        }
+        for (auto& p : pending) if (p.ready) cudaEventDestroy(p.ready);
+        for (auto& p : inflight) if (p.ready) cudaEventDestroy(p.ready);
+        if (h_scalars) cudaFreeHost(h_scalars);
+    }
+};
+
 struct Trainer {
     colibri_b200_corpus*       c;
     colibri_b200_options       o;
@@ -275,6 +308,15 @@ struct Trainer {
     std::vector<Segment>       segs;
     uint64_t                   slots_init = 0, ngram_upserts = 0, skip_upserts = 0, filtered_windows = 0;
     Tuning                     tune = Tuning::from_env();
+    ExportSink*                sink = nullptr;
+    uint64_t                   tok_ext_cells = 0;  // the token array has room for this many (class, class) pairs behind position npos + 8
+    size_t                     l2_persist_max = 0, l2_window_max = 0;
+    int  l2_pin(const void* base, size_t bytes);
+    void l2_unpin();
+    const uint32_t*            tok_for_sink = nullptr;
+    uint32_t                   sink_maxclass = 0;
+    int emit_segment(Segment& sg);
+    int flush_sink(bool final);
 
     int zero_stats(bool keep_global = true) {
         // found/kept/kept_occ/cursor/valid_windows/probes are per-phase; totaltokens/maxclass/errflags live for the whole train
@@ -287,6 +329,7 @@ struct Trainer {
         CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (h_stats.errflags & kErrTableFull) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow");
+        if (sink) TRY(flush_sink(false));  // every host sync of the level loop is a chance to hand finished segments to the copy stream
         return 0;
     }
     // forward index (indexed models)
@@ -436,6 +479,103 @@ int Trainer::indexed_skipgrams(int n, Segment& ng, const std::vector<DevBuf<uint
     return 0;
 }
 
+// ---- L2 residency for the small random-access structures of a level (occurrence filter + dense square, <= ~50 MB): without it the
+// table's HBM traffic keeps evicting them and the count launch re-fetches filter lines from DRAM (profiles/r02_ncu.md: 4.4 GB of the
+// 6.3 GB the level-2 count launch read).  A stream access-policy window marks the buffer persisting; the set-aside is released after the level.
+int Trainer::l2_pin(const void* base, size_t bytes) {
+    if (getenv("COLIBRI_B200_NO_L2_PIN") || bytes == 0) return 0;
+    if (l2_persist_max == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        l2_persist_max = (size_t)std::max(v, 0);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        l2_window_max = (size_t)std::max(v, 0);
+        if (l2_persist_max == 0 || l2_window_max == 0) {
+            l2_persist_max = l2_window_max = 1;  // not supported: stay quiet
+            return 0;
+        }
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist_max);
+    }
+    if (l2_persist_max <= 1) return 0;
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    av.accessPolicyWindow.base_ptr  = const_cast<void*>(base);
+    av.accessPolicyWindow.num_bytes = std::min(bytes, l2_window_max);
+    av.accessPolicyWindow.hitRatio  = (float)std::min(1.0, (double)l2_persist_max / (double)av.accessPolicyWindow.num_bytes);
+    av.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    return 0;
+}
+void Trainer::l2_unpin() {
+    if (l2_persist_max <= 1) return;
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    av.accessPolicyWindow.num_bytes = 0;
+    av.accessPolicyWindow.hitProp   = cudaAccessPropertyNormal;
+    av.accessPolicyWindow.missProp  = cudaAccessPropertyNormal;
+    if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
+}
+
+// ---- streamed export (colibri_b200_train_export).  A level's survivors are final once its prune scan ran, so their pattern bytes are
+// produced right away (the same kernels export_segments runs at the end, on the main stream: small, and their inputs are hot) into a
+// staging block sized by an upper bound; the total lands in pinned memory with the next statistics read, and from then on the host knows
+// how many bytes to copy: keys, lengths and counts leave on the second stream while the next level counts.
+int Trainer::emit_segment(Segment& sg) {
+    if (sg.count == 0) return 0;
+    if (sink->nscalars >= 1024) return set_err(COLIBRI_E_CAPACITY, "streamed export: more than 1024 segments");
+    ExportSink::Pending p;
+    p.count = sg.count;
+    const uint32_t vmax = varint_len(sink_maxclass);
+    uint64_t       bound = 0;  // bytes of the segment's keys at most
+    if (sg.n == 1) bound = sg.count * vmax;
+    else bound = sg.count * (uint64_t)sg.n * vmax;
+    TRY(p.nm.alloc(dev, sg.count));
+    TRY(p.lens.alloc(dev, sg.count));
+    TRY(p.off.alloc(dev, sg.count + 1));
+    TRY(p.tmp.alloc(dev, sg.count / 2048 + 4));
+    TRY(p.len16.alloc(dev, sg.count));
+    TRY(p.keys.alloc(dev, bound + 16));
+    if (sg.skip) {
+        CUDA_TRY(cudaMemcpyAsync(p.nm.p, sg.mask.p, sg.count * 4, cudaMemcpyDeviceToDevice, s));
+        launches += launch_pack_nm(s, p.nm.p, sg.count, (uint32_t)sg.n);
+    } else {
+        launches += launch_fill_u32(s, p.nm.p, sg.count, (uint32_t)sg.n);
+    }
+    launches += launch_export_lengths(s, tok_for_sink, sg.pos.p, p.nm.p, sg.count, p.lens.p, p.len16.p);
+    launches += launch_exclusive_scan_u32_u64(s, p.lens.p, p.off.p, sg.count, p.tmp.p);
+    launches += launch_export_write(s, tok_for_sink, sg.pos.p, p.nm.p, p.off.p, sg.count, p.keys.p);
+    p.h_kb = sink->h_scalars + sink->nscalars++;
+    CUDA_TRY(cudaMemcpyAsync(p.h_kb, p.off.p + sg.count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    // the counts travel from the segment's own array; it stays alive (segs) until the end of the call
+    p.cnt = std::move(sg.cnt);
+    CUDA_TRY(cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(p.ready, s));
+    sink->pending.push_back(std::move(p));
+    return 0;
+}
+
+// called right after a synchronise of the main stream: every pending segment's byte total is known now
+int Trainer::flush_sink(bool final) {
+    for (auto& p : sink->pending) {
+        const uint64_t kb = *p.h_kb;
+        if (sink->npat + p.count > sink->pat_cap || sink->nbytes + kb > sink->keys_cap) sink->overflow = true;
+        if (!sink->overflow) {
+            CUDA_TRY(cudaStreamWaitEvent(sink->xs, p.ready, 0));
+            if (kb) CUDA_TRY(cudaMemcpyAsync(sink->keys + sink->nbytes, p.keys.p, kb, cudaMemcpyDeviceToHost, sink->xs));
+            CUDA_TRY(cudaMemcpyAsync(sink->len16 + sink->npat, p.len16.p, p.count * sizeof(uint16_t), cudaMemcpyDeviceToHost, sink->xs));
+            CUDA_TRY(cudaMemcpyAsync(sink->counts + sink->npat, p.cnt.p, p.count * sizeof(uint32_t), cudaMemcpyDeviceToHost, sink->xs));
+        }
+        sink->npat += p.count;
+        sink->nbytes += kb;
+        sink->inflight.push_back(std::move(p));  // its blocks go back to the pool when the sink dies, after the copy stream drained
+    }
+    sink->pending.clear();
+    if (final) CUDA_TRY(cudaStreamSynchronize(sink->xs));
+    return 0;
+}
+
 // K0: stage the sentence-source tail, tokenise, check the encoding.  npos includes one virtual delimiter closing the last sentence.
 int Trainer::tokenise(DevBuf<uint32_t>& tok, uint64_t& npos, uint32_t& nclasses) {
     // ---- the sentence source quirk (see include/colibri_b200.h: streamed)
@@ -467,7 +607,10 @@ int Trainer::tokenise(DevBuf<uint32_t>& tok, uint64_t& npos, uint32_t& nclasses)
     const uint64_t npos_real = h_stats.cursor;  // tokens + delimiters
     if (npos_real >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "corpus has %llu positions; the device index is 32 bit", (unsigned long long)npos_real);
     npos = npos_real + 1;  // one virtual delimiter closes the last sentence
-    TRY(tok.alloc(dev, npos + 8));
+    // spare room behind the tokens: the class pairs of the surviving dense bigrams (kernels.cu: prune_dense_kernel)
+    tok_ext_cells = (tune.dense_dim && npos >= tune.dense_min) ? (uint64_t)tune.dense_dim * tune.dense_dim : 0;
+    if (npos + 8 + 2 * tok_ext_cells >= 0xFFFFFFF0ull) tok_ext_cells = 0;
+    TRY(tok.alloc(dev, npos + 8 + 2 * tok_ext_cells));
     CUDA_TRY(cudaMemsetAsync(tok.p + npos_real, 0, 8 * sizeof(uint32_t), s));
     launches += launch_tokenise_write(s, c->body(), staged, blk.p, nblocks, tok.p, d_stats.p);
     timer.end(h);
@@ -493,6 +636,10 @@ int Trainer::run() {
     uint32_t         nclasses = 0;
     int              h = -1;
     TRY(tokenise(tok, npos, nclasses));
+    tok_for_sink  = tok.p;
+    sink_maxclass = nclasses ? nclasses - 1 : 0;
+    // a level can be handed to the caller as soon as it is pruned unless a later rule may still drop it (MINLENGTH clean-up, :1221-1229, :1337-1341)
+    const bool stream_levels = sink != nullptr && o.MINLENGTH <= 1 && o.MINTOKENS > 1;
 
     indexed = o.model_type == COLIBRI_INDEXEDPATTERNMODEL;
     if (indexed) {
@@ -530,21 +677,36 @@ int Trainer::run() {
             TRY(build_refs(sg, tok.p, class_index.p, true, npos, h_stats.kept_occ));
             timer.end(hi);
         }
+        if (h_stats.found == 0) sg.count = 0;
         segs.push_back(std::move(sg));
+        if (stream_levels) {
+            int he = timer.begin(COLIBRI_T_EXPORT);
+            TRY(emit_segment(segs.back()));
+            timer.end(he);
+        }
     }
     timer.end(h);
     m->counters[6] = m->totaltokens;
+    const DeviceStats uni = h_stats;  // found / kept / kept occurrences of the unigram level
+    // tokens of the classes the dense square covers (sizes the occurrence filter of level 2)
+    uint64_t dense_tokens = 0;
+    if (tok_ext_cells && nclasses) {
+        TRY(zero_stats());
+        launches += launch_sum_u32(s, count1.p, std::min<uint32_t>(tune.dense_dim, nclasses), &d_stats.p->found);
+        TRY(read_stats());
+        dense_tokens = h_stats.found;
+    }
     std::vector<PassStat> passes;
-    uint64_t prev_kept = h_stats.kept, prev_occ = h_stats.kept_occ;
-    if (h_stats.found == 0) {  // nothing at all ("None found", :1189-1194): an empty model
+    uint64_t prev_kept = uni.kept, prev_occ = uni.kept_occ;
+    if (uni.found == 0) {  // nothing at all ("None found", :1189-1194): an empty model
         segs.clear();
     } else {
-        passes.push_back({1, h_stats.found, 0, h_stats.found - h_stats.kept});
+        passes.push_back({1, uni.found, 0, uni.found - uni.kept});
         m->maxn = 1;
         m->minn = 1;
-        m->totaltypes = h_stats.found;  // :1199-1201 (t > 1) and totalwordtypesingroup(NGRAM,1) (t == 1, :1202-1208)
+        m->totaltypes = uni.found;  // :1199-1201 (t > 1) and totalwordtypesingroup(NGRAM,1) (t == 1, :1202-1208)
     }
-    int last_pass = h_stats.found ? 1 : 0;
+    int last_pass = uni.found ? 1 : 0;
 
     // ---- levels n >= 2
     std::vector<DevBuf<uint32_t>> ids(2);  // ids[k] = id array of level k (all kept when skipgrams need their parts, else ping-pong)
@@ -580,17 +742,28 @@ int Trainer::run() {
 
         // ---- dense pairs (level 2 of a large corpus): the ids of level 1 are the class numbers, frequent classes are the small ones
         uint32_t dense = 0;
-        if (n == 2 && !use_list && bound >= tune.dense_min) dense = std::min<uint32_t>(tune.dense_dim, nclasses);
-        const uint64_t dense_slots = (uint64_t)dense * dense;
+        if (n == 2 && !use_list && bound >= tune.dense_min && tok_ext_cells) dense = std::min<uint32_t>(tune.dense_dim, nclasses);
+        const uint64_t dense_cells = (uint64_t)dense * dense;
 
-        // ---- occurrence filter (t >= 2, worth its two extra launches only on large levels)
+        // ---- occurrence filter (t >= 2): the 2-bit counters and the dense square share one buffer, pinned in L2 for the level
         const bool use_filter = tune.use_filter(t, bound);
         uint64_t   nbuckets = 0, cap = 0;
         if (use_filter) {
-            nbuckets = tune.filter_buckets(bound);  // <= 64 MB of 2-bit counters: L2 resident
-            if (filter.n < nbuckets / 16) TRY(filter.alloc(dev, nbuckets / 16));
+            // windows of two dense classes never look at the filter: size it for the rest (share estimated from the class histogram)
+            uint64_t fbound = bound;
+            if (dense && m->totaltokens) {
+                const double f = (double)dense_tokens / (double)m->totaltokens;
+                fbound = (uint64_t)((double)bound * std::min(1.0, 1.05 * (1.0 - f * f))) + 1024;
+            }
+            nbuckets = tune.filter_buckets(fbound);
+        }
+        const uint64_t filter_words = nbuckets / 16;
+        if (filter.n < filter_words + dense_cells + 8) TRY(filter.alloc(dev, filter_words + dense_cells + 8));
+        uint32_t* dense_cnt = filter.p + filter_words;
+        if (use_filter || dense) TRY(l2_pin(filter.p, (filter_words + dense_cells) * sizeof(uint32_t)));
+        if (use_filter) {
             int hf = timer.begin(COLIBRI_T_COUNT, n);
-            CUDA_TRY(cudaMemsetAsync(filter.p, 0, nbuckets / 4, s));
+            CUDA_TRY(cudaMemsetAsync(filter.p, 0, filter_words * sizeof(uint32_t), s));
             TRY(zero_stats());
             launches += launch_ngram_filter(s, prev.p, npos, filter.p, nbuckets, d_stats.p, sms, dense, list, nlist);
             timer.end(hf);
@@ -598,32 +771,36 @@ int Trainer::run() {
             // keys that reach the table live in buckets hit at least twice; there are at most ~2 such keys per bucket
             // when the filter is crowded with singletons, ~1 otherwise.  Overflow is detected and retried.
             cap = std::max<uint64_t>(1024, 3 * h_stats.found + 1024);
+            if (h_stats.found * 8 > nbuckets) cap = bound + bound / 2 + 16;  // a saturated filter says nothing about the number of keys
             cap = std::min(cap, std::max<uint64_t>(64, bound + bound / 2 + 16));
         } else {
             cap = std::max<uint64_t>(64, bound + bound / 2 + 16);  // load factor <= 2/3
         }
+        const uint64_t cap_max = std::max<uint64_t>(64, bound + bound / 2 + 16);  // windows <= bound: a table this large cannot fill up
         uint64_t windows = 0, singles = 0;
-        for (int attempt = 0;; ++attempt) {
-            if (cap + dense_slots >= 0xFFFFFFF0ull)
-                return set_err(COLIBRI_E_CAPACITY, "level %d needs %llu table slots; slot ids are 32 bit", n, (unsigned long long)(cap + dense_slots));
-            if (table.n < cap + dense_slots) TRY(table.alloc(dev, cap + dense_slots));
+        for (;;) {
+            cap = (cap + 31) / 32 * 32;  // the dense cells' survivor bits start on a bitmap word
+            if (cap + dense_cells >= 0xFFFFFFF0ull)
+                return set_err(COLIBRI_E_CAPACITY, "level %d needs %llu table slots; slot ids are 32 bit", n, (unsigned long long)(cap + dense_cells));
+            if (table.n < cap) TRY(table.alloc(dev, cap));
             int hp0 = timer.begin(COLIBRI_T_PRUNE);
-            CUDA_TRY(cudaMemsetAsync(table.p, 0, (cap + dense_slots) * sizeof(NgramSlot), s));
+            CUDA_TRY(cudaMemsetAsync(table.p, 0, cap * sizeof(NgramSlot), s));
+            if (dense) CUDA_TRY(cudaMemsetAsync(dense_cnt, 0, dense_cells * sizeof(uint32_t), s));
             timer.end(hp0);
-            slots_init += cap + dense_slots;
+            slots_init += cap + dense_cells / 4;
             TRY(zero_stats());
             int hc = timer.begin(COLIBRI_T_COUNT, n);
             const bool hot = tune.use_hot(bound);
-            launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms, use_filter ? filter.p : nullptr, nbuckets, hot, dense, list, nlist);
+            launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms, use_filter ? filter.p : nullptr, nbuckets, hot, dense, list, nlist, dense_cnt);
             timer.end(hc);
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaStreamSynchronize(s));
-            if (h_stats.errflags & kErrTableFull) {  // the estimate was too small: clear the flag and go again with twice the slots
-                if (attempt >= 6) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow at level %d", n);
+            if (h_stats.errflags & kErrTableFull) {  // the estimate was too small: clear the flag and go again with more slots
+                if (cap >= cap_max) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow at level %d", n);
                 CUDA_TRY(cudaMemsetAsync(&d_stats.p->errflags, 0, sizeof(unsigned int), s));
                 if (use_list) CUDA_TRY(cudaMemsetAsync(cur.p, 0, npos * sizeof(uint32_t), s));
-                cap *= 2;
+                cap = std::min(cap_max, cap * 4);
                 continue;
             }
             windows = h_stats.valid_windows;
@@ -643,12 +820,15 @@ int Trainer::run() {
         uint64_t sv_bound = windows / std::max<uint32_t>(t, 1) + 1;
         TRY(sg.pos.alloc(dev, sv_bound));
         TRY(sg.cnt.alloc(dev, sv_bound));
-        const uint64_t slots_total = cap + dense_slots;  // the dense square is scanned like the hashed part: its entries are ordinary slots
+        const uint64_t slots_total = cap + dense_cells;  // ids cap + 1 .. cap + dense^2 name the cells of the dense square
         if (bitmap.n < slots_total / 32 + 8) TRY(bitmap.alloc(dev, slots_total / 32 + 8));
         if (indexed && slot_index.n < slots_total) TRY(slot_index.alloc(dev, slots_total));
-        launches += launch_prune_ngrams(s, table.p, slots_total, t, sg.pos.p, sg.cnt.p, bitmap.p, d_stats.p, sms, indexed ? slot_index.p : nullptr);
+        launches += launch_prune_ngrams(s, table.p, cap, t, sg.pos.p, sg.cnt.p, bitmap.p, d_stats.p, sms, indexed ? slot_index.p : nullptr);
+        if (dense)
+            launches += launch_prune_dense(s, dense_cnt, dense, cap, t, sg.pos.p, sg.cnt.p, bitmap.p, indexed ? slot_index.p : nullptr, tok.p + npos + 8, (uint32_t)(npos + 8), d_stats.p, sms);
         timer.end(hp);
         TRY(read_stats());
+        if (use_filter || dense) l2_unpin();
         // a window the filter held back is a distinct n-gram with exactly one occurrence: found, and pruned (t >= 2)
         const uint64_t found = h_stats.found + singles, kept = h_stats.kept, occ = h_stats.kept_occ;
         sg.count = kept;
@@ -713,7 +893,19 @@ int Trainer::run() {
         if (foundskip) m->hasskipgrams = 1;
         passes.push_back({(uint64_t)n, found, foundskip, (found - kept) + (foundskip - keptskip)});
         segs.push_back(std::move(sg));
-        if (sk.skip) segs.push_back(std::move(sk));
+        if (stream_levels) {
+            int he = timer.begin(COLIBRI_T_EXPORT);
+            TRY(emit_segment(segs.back()));
+            timer.end(he);
+        }
+        if (sk.skip) {
+            segs.push_back(std::move(sk));
+            if (stream_levels) {
+                int he = timer.begin(COLIBRI_T_EXPORT);
+                TRY(emit_segment(segs.back()));
+                timer.end(he);
+            }
+        }
 
         bool next_list = false;
         if ((n < o.MAXLENGTH || indexed_skip) && kept > 0) {
@@ -802,10 +994,21 @@ int Trainer::run() {
     m->passes = passes;
 
     h = timer.begin(COLIBRI_T_EXPORT);
-    TRY(colibri::export_segments(dev, s, segs, tok.p, m, launches));
-    timer.end(h);
-    timer.end(h_total);
-    CUDA_TRY(cudaStreamSynchronize(s));
+    if (sink != nullptr) {
+        if (!stream_levels)
+            for (auto& sg : segs) TRY(emit_segment(sg));
+        timer.end(h);
+        timer.end(h_total);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        TRY(flush_sink(true));
+        m->npatterns = sink->npat;
+        m->keybytes  = sink->nbytes;
+    } else {
+        TRY(colibri::export_segments(dev, s, segs, tok.p, m, launches));
+        timer.end(h);
+        timer.end(h_total);
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
     {
         std::map<int, double> lvl;
         timer.resolve(m->ms, &lvl);
@@ -1241,6 +1444,52 @@ extern "C" int colibri_b200_train(const uint8_t* host_body, size_t nbytes, const
     TRY(colibri_b200_corpus_stage(host_body, nbytes, o.device, &c));
     int rc = colibri_b200_train_corpus(c, opt, out);
     if (rc == 0) (*out)->ms[COLIBRI_T_H2D] = c->h2d_ms;
+    colibri_b200_corpus_free(c);
+    return rc;
+}
+
+extern "C" int colibri_b200_train_export(const uint8_t* host_body, size_t nbytes, const colibri_b200_options* opt, uint8_t* keys, uint64_t keys_cap, uint16_t* key_len,
+                                         uint32_t* counts, uint64_t patterns_cap, colibri_b200_train_summary* summary) {
+    if (!opt || !summary) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    memset(summary, 0, sizeof *summary);
+    if ((keys_cap && !keys) || (patterns_cap && (!key_len || !counts))) return set_err(COLIBRI_E_INVALID, "NULL output buffer");
+    colibri_b200_options o = *opt;
+    TRY(check_options(o));
+    if (o.model_type != COLIBRI_UNINDEXEDPATTERNMODEL) return set_err(COLIBRI_E_UNSUPPORTED, "colibri_b200_train_export streams unindexed models; use colibri_b200_train + colibri_b200_model_export for indexed ones");
+    colibri_b200_corpus* c = nullptr;
+    TRY(colibri_b200_corpus_stage(host_body, nbytes, o.device, &c));
+    colibri_b200_model* m = nullptr;
+    int rc = new_model(o.device, o.model_type, &m);
+    if (rc == 0) {
+        ExportSink sink;
+        sink.keys = keys; sink.len16 = key_len; sink.counts = counts; sink.keys_cap = keys_cap; sink.pat_cap = patterns_cap;
+        cudaError_t e = cudaStreamCreateWithFlags(&sink.xs, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&sink.h_scalars, 1024 * sizeof(unsigned long long), cudaHostAllocDefault);
+        if (e != cudaSuccess) rc = set_err(COLIBRI_E_CUDA, "streamed export set-up: %s", cudaGetErrorString(e));
+        if (rc == 0) {
+            Trainer tr;
+            tr.c = c; tr.o = o; tr.m = m; tr.s = m->stream; tr.dev = c->device;
+            tr.sink = &sink;
+            rc = tr.run();
+            if (rc) cudaStreamSynchronize(m->stream);
+        }
+        if (rc == 0) {
+            summary->npatterns = sink.npat; summary->keybytes = sink.nbytes;
+            summary->totaltokens = m->totaltokens; summary->totaltypes = m->totaltypes;
+            summary->maxn = m->maxn; summary->minn = m->minn; summary->hasskipgrams = m->hasskipgrams;
+            summary->npasses = (int32_t)m->passes.size();
+            for (size_t i = 0; i < m->passes.size() && i < 32; ++i) {
+                summary->passes[i][0] = m->passes[i].n; summary->passes[i][1] = m->passes[i].found;
+                summary->passes[i][2] = m->passes[i].foundskip; summary->passes[i][3] = m->passes[i].pruned;
+            }
+            m->ms[COLIBRI_T_H2D] = c->h2d_ms;
+            for (int i = 0; i < COLIBRI_T_NPHASES && i < 16; ++i) summary->ms[i] = m->ms[i];
+            memcpy(summary->counters, m->counters, sizeof m->counters);
+            if (sink.overflow)
+                rc = set_err(COLIBRI_E_CAPACITY, "output buffers too small: %llu patterns / %llu key bytes needed", (unsigned long long)sink.npat, (unsigned long long)sink.nbytes);
+        }
+    }
+    if (m) colibri_b200_model_free(m);
     colibri_b200_corpus_free(c);
     return rc;
 }

@@ -189,7 +189,7 @@ struct Segment {  // survivors of one (level, category)
 // suite can force every path -- occurrence filter with a crowded bucket array, hot-key cache, dense pair slots, list mode --
 // on corpora small enough for the oracle, and so that A/B measurements need no rebuild.
 struct Tuning {
-    uint64_t filter_min      = 1ull << 25;  // COLIBRI_B200_FILTER_MIN: smallest level (upper bound of its windows) that gets the occurrence filter
+    uint64_t filter_min      = 1ull << 20;  // COLIBRI_B200_FILTER_MIN: smallest level (upper bound of its windows) that gets the occurrence filter
     int      filter_log2_min = 20;          // COLIBRI_B200_FILTER_LOG2_MIN / _LOG2: the filter has 2^min .. 2^max buckets (>= 2 per window where that fits)
     int      filter_log2_max = 28;
     bool     no_filter       = false;       // COLIBRI_B200_NO_FILTER

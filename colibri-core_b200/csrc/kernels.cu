@@ -285,6 +285,11 @@ __device__ __forceinline__ uint32_t upsert_ngram(NgramSlot* __restrict__ table, 
 // bucket was hit once is the ONLY window of its key, so it is a distinct n-gram with count 1: it is counted as "found"
 // and as "pruned" without ever touching the table.  Keys that reach the table are counted exactly as before, so the
 // surviving patterns, their counts and the found/pruned statistics are unchanged.
+__device__ __forceinline__ uint32_t ld_cached(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void filter_locate(uint64_t h, uint64_t nbuckets_mask, uint64_t& word, uint32_t& shift) {
     uint64_t bucket = h & nbuckets_mask;  // low hash bits; the table slot uses the high bits (fast_range)
     word            = bucket >> 4;
@@ -325,8 +330,11 @@ __global__ void __launch_bounds__(256) ngram_filter_kernel(const uint32_t* __res
         uint64_t word;
         uint32_t shift;
         filter_locate(table_hash_u64(((unsigned long long)a << 32) | b), nbuckets_mask, word, shift);
-        uint32_t bits = (__ldcg(filter + word) >> shift) & 3u;
-        if (bits == 3u) continue;  // already saturated: hot keys stop here with a plain L2 read
+        // Look before touching: filter bits only ever go from 0 to 1 during this launch, so a copy cached in L1 can be stale in one
+        // direction only (it may miss bits that are set by now) and then the atomics below fetch the truth.  The frequent keys of a
+        // Zipf corpus therefore stop at an L1 hit instead of an L2 round trip.
+        uint32_t bits = (ld_cached(filter + word) >> shift) & 3u;
+        if (bits == 3u) continue;  // already saturated
         if ((bits & 1u) == 0) {
             uint32_t old = atomicOr(filter + word, 1u << shift);
             if (((old >> shift) & 1u) == 0) continue;  // first hit of this bucket
@@ -354,27 +362,18 @@ constexpr uint32_t           kHotLines = 1024;
 constexpr unsigned long long kHotBusy  = ~0ull;
 
 // Dense pairs (level 2 only, where the ids ARE the class numbers and classes are ranked by frequency, src/classencoder.cpp:213-226):
-// a bigram of two classes below `dense` owns slot dense_base + a * dense + b of the same table -- no hash, no filter word, no probing.
-// With dense = 2048 that is 46 % of the bigram windows of a Zipf corpus (54 % of those of a 100 k vocabulary fall below 4096), all of
-// them landing in a 64 MB region whose hot part lives in L2.  Such a slot is an ordinary NgramSlot, so the prune scan, the survivor
-// bitmap, the relabel step and the forward index treat it like any other.
-// a directly addressed slot: the key can only be this one, so there is nothing to probe
-__device__ __forceinline__ uint32_t upsert_dense(NgramSlot* __restrict__ table, uint64_t slot, unsigned long long key, uint32_t pos) {
-    NgramSlot* s = table + slot;
-    if (__ldcg(&s->key) == 0) {
-        unsigned long long o0, o1;
-        cas128(s, key, 1ull | ((unsigned long long)pos << 32), o0, o1);
-        if (o0 == 0) return (uint32_t)slot + 1;
-    }
-    atomicAdd(&s->count, 1u);
-    return (uint32_t)slot + 1;
-}
+// a bigram of two classes below `dense` is counted in dense_cnt[a * dense + b], a plain u32 square that follows the occurrence filter
+// in one buffer (2048^2 x 4 B = 16 MB; round 1 used full 16-byte slots: 64 MB of random L2 traffic that pushed the filter out).  No
+// hash, no filter word, no key to compare, no probing: one RED.  With dense = 2048 that is 46 % of the bigram windows of a Zipf corpus.
+// Its id is cap + a * dense + b + 1, as if the square were appended to the hashed table: the survivor bitmap, the relabel step and the
+// forward index see nothing special.  A surviving pair needs "a position where it occurs" for the export: prune_dense_kernel writes the
+// two class ids into the spare room behind the token array and hands out that position.
 
 template <bool kFilter, bool kDense, bool kList>
 __global__ void __launch_bounds__(256, kDense ? 7 : 8) count_ngrams_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ list, uint64_t nitems,
                                                                            uint32_t* __restrict__ cur, NgramSlot* __restrict__ table, uint64_t cap,
                                                                            const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, DeviceStats* __restrict__ st, const bool hot,
-                                                                           const uint32_t dense) {
+                                                                           const uint32_t dense, uint32_t* __restrict__ dense_cnt) {
     __shared__ uint64_t scratch[8];
     __shared__ unsigned long long hot_key[kHotLines];
     __shared__ uint32_t hot_slot[kHotLines];
@@ -404,7 +403,9 @@ __global__ void __launch_bounds__(256, kDense ? 7 : 8) count_ngrams_kernel(const
                     atomicAdd(&hot_pending[line], 1u);
                     id = *(volatile uint32_t*)&hot_slot[line];
                 } else {
-                    id = upsert_dense(table, cap + (uint64_t)a * dense + b, key, (uint32_t)p);
+                    const uint32_t cell = a * dense + b;
+                    atomicAdd(dense_cnt + cell, 1u);  // result unused -> RED
+                    id = (uint32_t)cap + cell + 1;
                     if (cached == 0 && atomicCAS(&hot_key[line], 0ull, kHotBusy) == 0ull) {
                         hot_slot[line] = id;
                         __threadfence_block();
@@ -448,7 +449,11 @@ __global__ void __launch_bounds__(256, kDense ? 7 : 8) count_ngrams_kernel(const
         __syncthreads();
         for (uint32_t l = threadIdx.x; l < kHotLines; l += blockDim.x) {
             uint32_t c = hot_pending[l];
-            if (c) atomicAdd(&table[hot_slot[l] - 1].count, c);
+            if (c) {
+                const uint64_t slot = hot_slot[l] - 1;
+                if (kDense && slot >= cap) atomicAdd(dense_cnt + (slot - cap), c);
+                else atomicAdd(&table[slot].count, c);
+            }
         }
     }
     uint64_t v  = block_reduce_sum(valid, scratch);
@@ -551,6 +556,47 @@ __global__ void __launch_bounds__(256) prune_table_kernel(const Slot* __restrict
             out += __popc(keepbits[k]);
         }
         __syncthreads();  // warp_cnt / tile_base are reused by the next tile
+    }
+    found = block_reduce_sum(found, scratch);
+    kept  = block_reduce_sum(kept, scratch);
+    occ   = block_reduce_sum(occ, scratch);
+    if (threadIdx.x == 0) {
+        if (found) atomicAdd(&st->found, (unsigned long long)found);
+        if (kept) atomicAdd(&st->kept, (unsigned long long)kept);
+        if (occ) atomicAdd(&st->kept_occ, (unsigned long long)occ);
+    }
+}
+
+__device__ __forceinline__ uint64_t block_reserve(uint32_t c, unsigned long long* __restrict__ cursor, uint32_t* warp_tot, unsigned long long* base_smem);
+// prune(MINTOKENS, 2) over the dense square: the same outputs as prune_table_kernel (statistics, survivors, survivor bitmap at bit
+// cap + cell, slot -> survivor index) for the cells of dense_cnt.  A survivor's two class ids go to tok_ext[2 * cell ..] (the spare room
+// behind the token array) and its "position" is where they were put, so the export re-encodes it like any other bigram.
+__global__ void __launch_bounds__(256) prune_dense_kernel(const uint32_t* __restrict__ dense_cnt, uint32_t dense, uint64_t cap, uint32_t threshold, uint32_t* __restrict__ sv_pos,
+                                                          uint32_t* __restrict__ sv_count, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ slot_index,
+                                                          uint32_t* __restrict__ tok_ext, uint32_t ext_pos0, DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    __shared__ uint32_t warp_tot[8];
+    __shared__ unsigned long long base_smem;
+    const uint64_t cells  = (uint64_t)dense * dense;
+    const uint64_t rounds = (cells + (uint64_t)gridDim.x * 256 - 1) / ((uint64_t)gridDim.x * 256);
+    uint64_t found = 0, kept = 0, occ = 0;
+    for (uint64_t r = 0; r < rounds; ++r) {
+        const uint64_t i = (r * gridDim.x + blockIdx.x) * 256 + threadIdx.x;  // cap and the cell count are multiples of 32: a warp covers one bitmap word
+        const uint32_t c = i < cells ? __ldcs(dense_cnt + i) : 0u;
+        const bool keep  = c != 0 && c >= threshold;
+        found += c != 0;
+        const uint32_t bits = __ballot_sync(0xffffffffu, keep);
+        if (lane_id() == 0 && i < cells) bitmap[(cap + i) >> 5] = bits;
+        const uint64_t out = block_reserve(keep ? 1u : 0u, &st->cursor, warp_tot, &base_smem);
+        if (keep) {
+            ++kept;
+            occ += c;
+            sv_pos[out]        = ext_pos0 + 2u * (uint32_t)i;
+            sv_count[out]      = c;
+            tok_ext[2 * i]     = (uint32_t)(i / dense);
+            tok_ext[2 * i + 1] = (uint32_t)(i % dense);
+        }
+        if (slot_index != nullptr && i < cells) slot_index[cap + i] = keep ? (uint32_t)out + 1 : 0u;
     }
     found = block_reduce_sum(found, scratch);
     kept  = block_reduce_sum(kept, scratch);
@@ -666,13 +712,13 @@ int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uin
 }
 template <bool kFilter, bool kDense, bool kList>
 static void launch_count_variant(cudaStream_t s, const uint32_t* prev, const uint32_t* list, uint64_t nitems, uint32_t* cur, NgramSlot* table, uint64_t cap, const uint32_t* filter,
-                                 uint64_t nbuckets, DeviceStats* st, int sms, bool hot, uint32_t dense) {
+                                 uint64_t nbuckets, DeviceStats* st, int sms, bool hot, uint32_t dense, uint32_t* dense_cnt = nullptr) {
     static int bps  = blocks_per_sm((const void*)count_ngrams_kernel<kFilter, kDense, kList>, 256, 0);
     unsigned   grid = (unsigned)umin64(div_up(nitems, 256), (uint64_t)sms * bps * 4);
-    count_ngrams_kernel<kFilter, kDense, kList><<<grid, 256, 0, s>>>(prev, list, nitems, cur, table, cap, filter, kFilter ? nbuckets - 1 : 0, st, hot, dense);
+    count_ngrams_kernel<kFilter, kDense, kList><<<grid, 256, 0, s>>>(prev, list, nitems, cur, table, cap, filter, kFilter ? nbuckets - 1 : 0, st, hot, dense, dense_cnt);
 }
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms, const uint32_t* filter,
-                        uint64_t nbuckets, bool hot, uint32_t dense, const uint32_t* list, uint64_t nlist) {
+                        uint64_t nbuckets, bool hot, uint32_t dense, const uint32_t* list, uint64_t nlist, uint32_t* dense_cnt) {
     const uint64_t nitems = list ? nlist : npos;
     if (!nitems) return 0;
     const bool f = filter != nullptr;
@@ -680,8 +726,8 @@ int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uin
         if (f) launch_count_variant<true, false, true>(s, prev, list, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, 0);
         else launch_count_variant<false, false, true>(s, prev, list, nitems, cur, table, cap, nullptr, 0, st, sms, hot, 0);
     } else if (dense) {
-        if (f) launch_count_variant<true, true, false>(s, prev, nullptr, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, dense);
-        else launch_count_variant<false, true, false>(s, prev, nullptr, nitems, cur, table, cap, nullptr, 0, st, sms, hot, dense);
+        if (f) launch_count_variant<true, true, false>(s, prev, nullptr, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, dense, dense_cnt);
+        else launch_count_variant<false, true, false>(s, prev, nullptr, nitems, cur, table, cap, nullptr, 0, st, sms, hot, dense, dense_cnt);
     } else {
         if (f) launch_count_variant<true, false, false>(s, prev, nullptr, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, 0);
         else launch_count_variant<false, false, false>(s, prev, nullptr, nitems, cur, table, cap, nullptr, 0, st, sms, hot, 0);
@@ -693,6 +739,13 @@ int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, ui
     static int bps = blocks_per_sm((const void*)prune_table_kernel<NgramSlot, false>, 256, 0);
     unsigned   grid = (unsigned)umin64(div_up(cap, kPruneTile), (uint64_t)sms * bps);
     prune_table_kernel<NgramSlot, false><<<grid ? grid : 1, 256, 0, s>>>(table, cap, threshold, sv_pos, sv_count, nullptr, bitmap, slot_index, st, nullptr, 0);
+    return 1;
+}
+int launch_prune_dense(cudaStream_t s, const uint32_t* dense_cnt, uint32_t dense, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap,
+                       uint32_t* slot_index, uint32_t* tok_ext, uint32_t ext_pos0, DeviceStats* st, int sms) {
+    if (!dense) return 0;
+    unsigned grid = (unsigned)umin64(div_up((uint64_t)dense * dense, 256), (uint64_t)sms * 8);
+    prune_dense_kernel<<<grid, 256, 0, s>>>(dense_cnt, dense, cap, threshold, sv_pos, sv_count, bitmap, slot_index, tok_ext, ext_pos0, st);
     return 1;
 }
 int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap, const uint32_t* list_in, uint64_t nlist_in, uint32_t* list_out, unsigned long long* cursor,
@@ -955,6 +1008,18 @@ __global__ void __launch_bounds__(1024) scan_apply_kernel(const uint32_t* __rest
     if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = sums[nb];
 }
 
+__global__ void __launch_bounds__(256) sum_u32_kernel(const uint32_t* __restrict__ v, uint64_t n, unsigned long long* __restrict__ total) {
+    __shared__ uint64_t scratch[8];
+    uint64_t acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc += v[i];
+    acc = block_reduce_sum(acc, scratch);
+    if (threadIdx.x == 0 && acc) atomicAdd(total, (unsigned long long)acc);
+}
+int launch_sum_u32(cudaStream_t s, const uint32_t* v, uint64_t n, unsigned long long* total) {
+    if (!n) return 0;
+    sum_u32_kernel<<<(unsigned)umin64(div_up(n, 256), 148), 256, 0, s>>>(v, n, total);
+    return 1;
+}
 int launch_fill_u32(cudaStream_t s, uint32_t* dst, uint64_t n, uint32_t value) {
     if (!n) return 0;
     fill_u32_kernel<<<div_up(n, 256), 256, 0, s>>>(dst, n, value);

@@ -78,7 +78,12 @@ int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uin
 // counted in slot cap + a * dense + b (no hash, no filter, no probing), every other window in the hashed part [0, cap)
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms,
                         const uint32_t* filter = nullptr, uint64_t nbuckets = 0, bool hot = false /* per-block shared-memory cache for frequent keys */, uint32_t dense = 0,
-                        const uint32_t* list = nullptr /* list mode: cur must have been zeroed by the caller */, uint64_t nlist = 0);
+                        const uint32_t* list = nullptr /* list mode: cur must have been zeroed by the caller */, uint64_t nlist = 0,
+                        uint32_t* dense_cnt = nullptr /* dense > 0: the zeroed u32 square dense x dense */);
+// prune() over the dense square (cells = ids cap + 1 .. cap + dense^2); cap must be a multiple of 32.  Survivors get tok_ext[2 * cell ..] = their two class
+// ids and the position ext_pos0 + 2 * cell (tok_ext = token array + ext_pos0)
+int launch_prune_dense(cudaStream_t s, const uint32_t* dense_cnt, uint32_t dense, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap,
+                       uint32_t* slot_index, uint32_t* tok_ext, uint32_t ext_pos0, DeviceStats* st, int sms);
 // bitmap: (cap+31)/32 words, bit = slot survived (may be NULL)
 int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap, DeviceStats* st, int sms,
                         uint32_t* slot_index = nullptr /* slot -> survivor index + 1, for the forward index */);
@@ -99,6 +104,7 @@ int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, 
 // ---- export: survivors -> pattern bytes
 // sv_nm[i] = n | mask << 8 ; for n == 1 sv_pos holds the class id itself
 int launch_fill_u32(cudaStream_t s, uint32_t* dst, uint64_t n, uint32_t value);
+int launch_sum_u32(cudaStream_t s, const uint32_t* v, uint64_t n, unsigned long long* total /* += sum */);
 int launch_pack_nm(cudaStream_t s, uint32_t* nm /*in: gap masks, out: n | mask << 8*/, uint64_t count, uint32_t n);
 int launch_export_lengths(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, uint64_t n, uint32_t* lens, uint16_t* lens16);
 int launch_exclusive_scan_u32_u64(cudaStream_t s, const uint32_t* in, uint64_t* out /*n+1*/, uint64_t n, uint64_t* tmp /*>= n/2048+2*/);

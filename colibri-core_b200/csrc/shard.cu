@@ -306,10 +306,11 @@ extern "C" int colibri_b200_shard_level_owner(colibri_b200_shard* sh, const void
         TRY(zero_phase_stats(sh));
         sh->launches += launch_stream_filter(s, dev_recv_keys, nrecv, sh->filter.p, nbuckets, sh->d_stats.p, sh->sms);
         TRY(read_stats(sh));
-        cap = std::min(cap, std::max<uint64_t>(1024, 3 * sh->h_stats.found + 1024));
+        if (sh->h_stats.found * 8 <= nbuckets) cap = std::min(cap, std::max<uint64_t>(1024, 3 * sh->h_stats.found + 1024));  // (a saturated filter says nothing about the number of keys)
     }
+    const uint64_t cap_max = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);  // a table this large cannot fill up
     uint64_t singles = 0;
-    for (int attempt = 0;; ++attempt) {
+    for (;;) {
         if (cap * sh->world >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner table of %llu slots x %u ranks exceeds the 32-bit id space", (unsigned long long)cap, sh->world);
         if (sh->owner_table.n < cap) TRY(sh->owner_table.alloc(sh->dev, cap));
         CUDA_TRY(cudaMemsetAsync(sh->owner_table.p, 0, cap * sizeof(NgramSlot), s));
@@ -318,9 +319,9 @@ extern "C" int colibri_b200_shard_level_owner(colibri_b200_shard* sh, const void
         CUDA_TRY(cudaMemcpyAsync(&sh->h_stats, sh->d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (sh->h_stats.errflags & kErrTableFull) {  // the estimate was too small: go again with twice the slots
-            if (attempt >= 6) return set_err(COLIBRI_E_CAPACITY, "owner hash table overflow");
+            if (cap >= cap_max) return set_err(COLIBRI_E_CAPACITY, "owner hash table overflow");
             CUDA_TRY(cudaMemsetAsync(&sh->d_stats.p->errflags, 0, sizeof(unsigned int), s));
-            cap *= 2;
+            cap = std::min(cap_max, cap * 4);
             continue;
         }
         singles = sh->h_stats.singletons;
@@ -495,10 +496,11 @@ extern "C" int colibri_b200_shard_p2p_owner(colibri_b200_shard* sh, uint64_t sta
         TRY(zero_phase_stats(sh));
         sh->launches += launch_stream_filter(s, keys, phys, sh->filter.p, nbuckets, sh->d_stats.p, sh->sms, sh->slot_cap, my_hdr);
         TRY(read_stats(sh));
-        cap = std::min(cap, std::max<uint64_t>(1024, 3 * sh->h_stats.found + 1024));
+        if (sh->h_stats.found * 8 <= nbuckets) cap = std::min(cap, std::max<uint64_t>(1024, 3 * sh->h_stats.found + 1024));  // (a saturated filter says nothing about the number of keys)
     }
+    const uint64_t cap_max = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);  // a table this large cannot fill up
     uint64_t singles = 0;
-    for (int attempt = 0;; ++attempt) {
+    for (;;) {
         if (cap * G >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner table of %llu slots x %u ranks exceeds the 32-bit id space", (unsigned long long)cap, G);
         if (sh->owner_table.n < cap) TRY(sh->owner_table.alloc(sh->dev, cap));
         CUDA_TRY(cudaMemsetAsync(sh->owner_table.p, 0, cap * sizeof(NgramSlot), s));
@@ -507,9 +509,9 @@ extern "C" int colibri_b200_shard_p2p_owner(colibri_b200_shard* sh, uint64_t sta
         CUDA_TRY(cudaMemcpyAsync(&sh->h_stats, sh->d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (sh->h_stats.errflags & kErrTableFull) {
-            if (attempt >= 6) return set_err(COLIBRI_E_CAPACITY, "owner hash table overflow");
+            if (cap >= cap_max) return set_err(COLIBRI_E_CAPACITY, "owner hash table overflow");
             CUDA_TRY(cudaMemsetAsync(&sh->d_stats.p->errflags, 0, sizeof(unsigned int), s));
-            cap *= 2;
+            cap = std::min(cap_max, cap * 4);
             continue;
         }
         singles = sh->h_stats.singletons;

@@ -89,6 +89,20 @@ void colibri_b200_corpus_free(colibri_b200_corpus* c);
 /* ---- training (replaces PatternModel::train, include/patternmodel.h:880-1345, for the subset documented in DESIGN.md) */
 /* end to end from host memory: stage + train + leave the result ready for export */
 int  colibri_b200_train(const uint8_t* host_body, size_t nbytes, const colibri_b200_options* opt, colibri_b200_model** out);
+/* end to end into caller-owned host buffers, with the PCIe legs overlapped: the survivors of level n are turned into pattern bytes and copied
+ * to the host (second stream, asynchronous when the buffers are pinned) while level n+1 counts.  Output = the compact flat form of
+ * colibri_b200_model_export_compact (keys blob, key_len[], counts[]; unindexed models).  No device-resident model is left behind; what a
+ * caller reads after train() comes back in the summary.  If a buffer is too small the call returns COLIBRI_E_CAPACITY and the summary
+ * holds the sizes needed.  Replaces train() + iteration for callers that materialise the map on the host (host/patternmodel.h: adopt()). */
+typedef struct colibri_b200_train_summary {
+    uint64_t npatterns, keybytes, totaltokens, totaltypes;
+    int32_t  maxn, minn, hasskipgrams, npasses;
+    uint64_t passes[32][4];          /* n, found n-grams, found skipgrams, pruned (first 32 passes) */
+    double   ms[16];                 /* COLIBRI_T_* phase times of the device work */
+    uint64_t counters[8];            /* as colibri_b200_model_counters */
+} colibri_b200_train_summary;
+int  colibri_b200_train_export(const uint8_t* host_body, size_t nbytes, const colibri_b200_options* opt, uint8_t* keys, uint64_t keys_cap, uint16_t* key_len,
+                               uint32_t* counts, uint64_t patterns_cap, colibri_b200_train_summary* summary);
 /* from a staged corpus (device resident input); the corpus can be trained repeatedly with different options */
 int  colibri_b200_train_corpus(colibri_b200_corpus* corpus, const colibri_b200_options* opt, colibri_b200_model** out);
 void colibri_b200_model_free(colibri_b200_model* m);

@@ -376,3 +376,28 @@ def test_device_checksum_matches_host_restatement(golden):
                      ("zipf300k_phr", dict(MINTOKENS=2, MAXLENGTH=5, DOSKIPGRAMS_EXHAUSTIVE=1, streamed=0)), ("single_token", dict(MINTOKENS=1, MAXLENGTH=3))):
         m = cb().train(corpus_body(golden, name), QUIET=1, **kw)
         assert m.checksum() == flat_checksum(to_flat(m)), name
+
+
+@pytest.mark.parametrize("path", ["default", "bench"])
+def test_streamed_train_export_equals_train_then_export(golden, path, monkeypatch):
+    """colibri_b200_train_export (levels copied to the host while the next one counts) delivers the same model as train() + export, for
+    streamable option sets, for those where a level may still be dropped at the end (MINLENGTH > 1: exported after the last level),
+    with skipgram segments, and through the grow-and-retry path of too small buffers."""
+    force_path(monkeypatch, path)
+    runs = [("hamlet", dict(MINTOKENS=2, MAXLENGTH=5)), ("hamlet", dict(MINTOKENS=1, MAXLENGTH=3)), ("hamlet", dict(MINTOKENS=2, MAXLENGTH=6, MINLENGTH=3)),
+            ("republic", dict(MINTOKENS=2, MAXLENGTH=5)), ("zipf300k_phr", dict(MINTOKENS=2, MAXLENGTH=5, DOSKIPGRAMS_EXHAUSTIVE=1, streamed=0)),
+            ("zipf2m", dict(MINTOKENS=2, MAXLENGTH=5)), ("single_token", dict(MINTOKENS=2, MAXLENGTH=3)), ("noeos", dict(MINTOKENS=1, MAXLENGTH=3))]
+    for name, kw in runs:
+        body = corpus_body(golden, name)
+        m = cb().train(body, QUIET=1, **kw)
+        want = to_flat(m)
+        keys, lens, counts, sm = cb().train_export(body, QUIET=1, **kw)
+        off = np.zeros(len(lens) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens.astype(np.uint64))
+        got = oracle.FlatModel(keys, off, counts, sm["tokens"], sm["types"], sm["maxn"], sm["minn"], sm["hasskipgrams"])
+        assert (got.tokens, got.types, len(got), got.maxn, got.minn, got.hasskipgrams) == (want.tokens, want.types, len(want), want.maxn, want.minn, want.hasskipgrams), (name, kw)
+        assert sm["passes"] == m.passes(), (name, kw)
+        assert got.same_patterns(want), (name, kw)
+    with pytest.raises(cb().ColibriError) as ei:
+        cb().train_export(corpus_body(golden, "hamlet"), MINTOKENS=2, MAXLENGTH=3, model_type=20, streamed=0, QUIET=1)
+    assert ei.value.code == 2

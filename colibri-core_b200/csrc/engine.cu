@@ -483,7 +483,9 @@ int Trainer::indexed_skipgrams(int n, Segment& ng, const std::vector<DevBuf<uint
 // table's HBM traffic keeps evicting them and the count launch re-fetches filter lines from DRAM (profiles/r02_ncu.md: 4.4 GB of the
 // 6.3 GB the level-2 count launch read).  A stream access-policy window marks the buffer persisting; the set-aside is released after the level.
 int Trainer::l2_pin(const void* base, size_t bytes) {
-    if (getenv("COLIBRI_B200_NO_L2_PIN") || bytes == 0) return 0;
+    // MEASURED (B200, 100 M tokens, profiles/r02_ncu.md): with the window on, the whole step went 10.9 -> 15.2 ms (every kernel slower, the
+    // tokeniser included: the set-aside shrinks the L2 everything else lives in).  Off unless asked for; kept as the evidence.
+    if (!getenv("COLIBRI_B200_L2_PIN") || bytes == 0) return 0;
     if (l2_persist_max == 0) {
         int v = 0;
         cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev);
@@ -751,7 +753,7 @@ int Trainer::run() {
         if (use_filter) {
             // windows of two dense classes never look at the filter: size it for the rest (share estimated from the class histogram)
             uint64_t fbound = bound;
-            if (dense && m->totaltokens) {
+            if (dense && m->totaltokens && getenv("COLIBRI_B200_FILTER_SHRINK")) {
                 const double f = (double)dense_tokens / (double)m->totaltokens;
                 fbound = (uint64_t)((double)bound * std::min(1.0, 1.05 * (1.0 - f * f))) + 1024;
             }

@@ -1,0 +1,85 @@
+// shard.h -- the per-rank state of a multi-GPU run (shard.cu: phases driven through NCCL all-to-alls; shard_p2p.cu: the fused
+// NVLink peer-store levels) and the small helpers both files use.
+#pragma once
+#include "engine_common.h"
+
+using namespace colibri;
+
+struct colibri_b200_shard {
+    colibri_b200_corpus* corpus = nullptr;
+    colibri_b200_options o;
+    int                  dev = 0, sms = 148;
+    uint32_t             rank = 0, world = 1;
+    cudaStream_t         s = nullptr;
+    uint64_t             launches = 0;
+    DevBuf<DeviceStats>  d_stats;
+    DeviceStats          h_stats;
+    uint64_t             npos = 0, local_tokens = 0;
+    uint32_t             local_maxclass = 0, nclasses = 0;
+    DevBuf<uint32_t>     tok, count1, prev, cur, bitmap, filter, pos_of_rec, rec_of_pos, split_hist, sv_idx, sv_cnt;
+    DevBuf<uint64_t>     split_off, scan_tmp;
+    DevBuf<NgramSlot>    owner_table;
+    DevBuf<unsigned long long> d_aux;   // [0..65): source bases of the receive buffer, [65..130): output bases, [130..195): cursors, [195..260): counts
+    uint64_t             send_base[65] = {0}, nsent = 0, nrecv = 0, nsurv = 0, prev_valid = 0;
+    uint64_t             surv_out_counts[64] = {0};
+    // NVLink peer-store mode: symmetric receive buffers of every rank (device pointers valid in this process)
+    bool                 p2p = false, own_stream = true;
+    uint64_t             slot_cap = 0, surv_cap = 0;
+    void*                h_keys_rx[64] = {nullptr};
+    void*                h_reply_rx[64] = {nullptr};
+    void*                h_surv_rx[64] = {nullptr};
+    void*                h_hdr[64] = {nullptr};
+    DevBuf<void*>        d_peer;   // [0..64) keys_rx, [64..128) reply_rx, [128..192) surv_rx, [192..256) hdr
+    DevBuf<unsigned long long> d_vals;
+    DevBuf<uint32_t>     rid;
+    // skipgrams: every level's (global) ids are kept, the parts of a skipgram are looked up in them
+    std::vector<DevBuf<uint32_t>> ids_keep;
+    DevBuf<const uint32_t*> d_idptrs;
+    DevBuf<SkipMask>     d_masks;
+    DevBuf<SkipSlot>     sktable;
+    DevBuf<uint32_t>     sk_pos_of_rec, sk_sv_idx, sk_sv_cnt, sk_sv_mask;
+    int                  sk_nmasks = 0;
+    uint64_t             sk_send_base[65] = {0}, sk_nsent = 0, sk_nsurv = 0;
+    int                  level = 1;
+    uint32_t             t = 2;
+    std::vector<Segment> segs;
+    uint64_t             global_tokens = 0, global_types = 0;
+    cudaEvent_t          ev0 = nullptr, ev1 = nullptr;
+    double               device_ms = 0;
+    double               phase_ms[8] = {0};  // begin, unigrams, count, pack, merge, finish, export
+};
+
+// skipgram mode: remember the id array of level n (sh->prev after the level's finish)
+inline int shard_keep_ids(colibri_b200_shard* sh, int n) {
+    if (!sh->o.DOSKIPGRAMS_EXHAUSTIVE) return 0;
+    if ((int)sh->ids_keep.size() <= n) sh->ids_keep.resize(n + 1);
+    TRY(sh->ids_keep[n].alloc(sh->dev, sh->npos + 8));
+    CUDA_TRY(cudaMemcpyAsync(sh->ids_keep[n].p, sh->prev.p, (sh->npos + 8) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh->s));
+    return 0;
+}
+
+inline int shard_zero_stats(colibri_b200_shard* sh) {
+    CUDA_TRY(cudaMemsetAsync(&sh->d_stats.p->found, 0, offsetof(DeviceStats, maxclass) - offsetof(DeviceStats, found), sh->s));
+    return 0;
+}
+inline int shard_read_stats(colibri_b200_shard* sh) {
+    CUDA_TRY(cudaMemcpyAsync(&sh->h_stats, sh->d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, sh->s));
+    CUDA_TRY(cudaStreamSynchronize(sh->s));
+    if (sh->h_stats.errflags & kErrTableFull) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow");
+    return 0;
+}
+struct PhaseClock {  // accumulates device time of one ABI call into shard->device_ms / phase_ms[phase]
+    colibri_b200_shard* sh;
+    int                 phase;
+    explicit PhaseClock(colibri_b200_shard* s, int ph) : sh(s), phase(ph) { cudaEventRecord(sh->ev0, sh->s); }
+    ~PhaseClock() {
+        cudaEventRecord(sh->ev1, sh->s);
+        cudaEventSynchronize(sh->ev1);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sh->ev0, sh->ev1) == cudaSuccess) {
+            sh->device_ms += ms;
+            sh->phase_ms[phase] += ms;
+        }
+    }
+};
+

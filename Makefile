@@ -19,7 +19,7 @@ $(LIBDIR)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.h $(CSRC)/device_utils.c
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/kernels.ptxas.log || (cat $(LIBDIR)/kernels.ptxas.log; false)
 
-$(LIBDIR)/engine.o: $(CSRC)/engine.cu $(CSRC)/kernels.h $(CSRC)/engine_common.h include/colibri_b200.h
+$(LIBDIR)/engine.o: $(CSRC)/engine.cu $(CSRC)/kernels.h $(CSRC)/shard.h $(CSRC)/engine_common.h include/colibri_b200.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/engine.ptxas.log || (cat $(LIBDIR)/engine.ptxas.log; false)
 
@@ -30,6 +30,10 @@ $(LIBDIR)/shard.o: $(CSRC)/shard.cu $(CSRC)/shard.h $(CSRC)/kernels.h $(CSRC)/en
 $(LIBDIR)/shard_p2p.o: $(CSRC)/shard_p2p.cu $(CSRC)/shard.h $(CSRC)/kernels.h $(CSRC)/engine_common.h include/colibri_b200.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/shard_p2p.ptxas.log || (cat $(LIBDIR)/shard_p2p.ptxas.log; false)
+
+$(LIBDIR)/partition.o: $(CSRC)/partition.cu $(CSRC)/kernels.h $(CSRC)/device_utils.cuh $(CSRC)/spooky.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/partition.ptxas.log || (cat $(LIBDIR)/partition.ptxas.log; false)
 
 $(LIBDIR)/index.o: $(CSRC)/index.cu $(CSRC)/kernels.h $(CSRC)/device_utils.cuh
 	@mkdir -p $(LIBDIR)
@@ -51,7 +55,7 @@ $(LIBDIR)/model_io.o: $(CSRC)/model_io.cu $(CSRC)/kernels.h $(CSRC)/engine_commo
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/model_io.ptxas.log || (cat $(LIBDIR)/model_io.ptxas.log; false)
 
-$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o $(LIBDIR)/shard_p2p.o $(LIBDIR)/index.o $(LIBDIR)/shard_kernels.o $(LIBDIR)/pattern_index.o $(LIBDIR)/model_io.o $(LIBDIR)/flexgrams.o
+$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o $(LIBDIR)/shard_p2p.o $(LIBDIR)/partition.o $(LIBDIR)/index.o $(LIBDIR)/shard_kernels.o $(LIBDIR)/pattern_index.o $(LIBDIR)/model_io.o $(LIBDIR)/flexgrams.o
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^
 
 oracle:

@@ -311,6 +311,11 @@ struct Trainer {
     ExportSink*                sink = nullptr;
     uint64_t                   tok_ext_cells = 0;  // the token array has room for this many (class, class) pairs behind position npos + 8
     size_t                     l2_persist_max = 0, l2_window_max = 0;
+    // partitioned counting path (partition.cu): record buffers of the two splits and the small per-partition arrays, reused across levels
+    DevBuf<unsigned long long> part_rk1, part_rk2;
+    DevBuf<uint32_t>           part_rp1, part_rp2, part_small, part_dense_id, part_dense_bits;
+    int  level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint64_t npos, const uint32_t* list, uint64_t nlist, uint64_t wbound, uint32_t dense, uint32_t* dense_cnt,
+                           uint32_t t, uint32_t* tok_ext, Segment& sg, bool& overflow);
     int  l2_pin(const void* base, size_t bytes);
     void l2_unpin();
     const uint32_t*            tok_for_sink = nullptr;
@@ -578,6 +583,63 @@ int Trainer::flush_sink(bool final) {
     return 0;
 }
 
+// One level on the partitioned path (partition.cu).  On return h_stats holds the level's device statistics (valid_windows, found, kept,
+// kept_occ, singletons = keys that occur once); sg.pos / sg.cnt hold the survivors, cur[] the final ids (survivor index + 1, 0 = pruned or no
+// window).  overflow: a partition did not fit its shared-memory table -- nothing of the level is usable, the caller reruns it on the HBM table.
+int Trainer::level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint64_t npos, const uint32_t* list, uint64_t nlist, uint64_t wbound, uint32_t dense,
+                               uint32_t* dense_cnt, uint32_t t, uint32_t* tok_ext, Segment& sg, bool& overflow) {
+    overflow = false;
+    const PartPlan pl  = part_plan(wbound);
+    const uint32_t p1n = 1u << pl.b1;
+    // hist | off (+1) | cursor2 | cursor1 | tstart (+1) | work
+    const uint64_t small_words = 3ull * pl.nparts + 2ull * p1n + 8;
+    if (part_small.n < small_words) TRY(part_small.alloc(dev, small_words));
+    uint32_t* hist    = part_small.p;
+    uint32_t* off     = hist + pl.nparts;
+    uint32_t* cursor2 = off + pl.nparts + 1;
+    uint32_t* cursor1 = cursor2 + pl.nparts;
+    uint32_t* tstart  = cursor1 + p1n;
+    uint32_t* work    = tstart + p1n + 1;
+    if (part_rk1.n < wbound + 1) TRY(part_rk1.alloc(dev, wbound + 1));
+    if (part_rp1.n < wbound + 1) TRY(part_rp1.alloc(dev, wbound + 1));
+    if (part_rk2.n < wbound + 1) TRY(part_rk2.alloc(dev, wbound + 1));
+    if (part_rp2.n < wbound + 1) TRY(part_rp2.alloc(dev, wbound + 1));
+    const uint64_t dense_cells = (uint64_t)dense * dense;
+    if (dense) {
+        if (part_dense_id.n < dense_cells) TRY(part_dense_id.alloc(dev, dense_cells));
+        if (part_dense_bits.n < dense_cells / 32 + 8) TRY(part_dense_bits.alloc(dev, dense_cells / 32 + 8));
+    }
+    const uint64_t sv_bound = wbound / std::max<uint32_t>(t, 1) + 1;
+    TRY(sg.pos.alloc(dev, sv_bound));
+    TRY(sg.cnt.alloc(dev, sv_bound));
+    const uint64_t nitems = list ? nlist : npos;
+
+    int hc = timer.begin(COLIBRI_T_COUNT, n);
+    CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)pl.nparts * sizeof(uint32_t), s));
+    CUDA_TRY(cudaMemsetAsync(work, 0, sizeof(uint32_t), s));
+    if (dense) CUDA_TRY(cudaMemsetAsync(dense_cnt, 0, dense_cells * sizeof(uint32_t), s));
+    TRY(zero_stats());
+    launches += launch_part_hist(s, prev, list, nitems, dense, dense_cnt, hist, pl, d_stats.p, sms);
+    if (dense)  // prune(MINTOKENS, 2) of the dense square first: its survivors open the segment, dense_id[cell] = survivor index + 1
+        launches += launch_prune_dense(s, dense_cnt, dense, 0, t, sg.pos.p, sg.cnt.p, part_dense_bits.p, part_dense_id.p, tok_ext, (uint32_t)(npos + 8), d_stats.p, sms);
+    launches += launch_part_scan(s, hist, pl, off, cursor2, cursor1, tstart);
+    launches += launch_part_split1(s, prev, list, nitems, dense, part_dense_id.p, cur, pl, cursor1, part_rk1.p, part_rp1.p);
+    launches += launch_part_split2(s, part_rk1.p, part_rp1.p, off, tstart, pl, wbound, cursor2, part_rk2.p, part_rp2.p);
+    launches += launch_part_count(s, part_rk2.p, part_rp2.p, off, pl, t, cur, 1, 1, sg.pos.p, sg.cnt.p, d_stats.p, work, sms);
+    timer.end(hc);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (h_stats.errflags & kErrTableFull) {
+        CUDA_TRY(cudaMemsetAsync(&d_stats.p->errflags, 0, sizeof(unsigned int), s));
+        overflow = true;
+        return 0;
+    }
+    if (sink) TRY(flush_sink(false));
+    m->levels[n].cap = pl.nparts;
+    return 0;
+}
+
 // K0: stage the sentence-source tail, tokenise, check the encoding.  npos includes one virtual delimiter closing the last sentence.
 int Trainer::tokenise(DevBuf<uint32_t>& tok, uint64_t& npos, uint32_t& nclasses) {
     // ---- the sentence source quirk (see include/colibri_b200.h: streamed)
@@ -747,6 +809,36 @@ int Trainer::run() {
         if (n == 2 && !use_list && bound >= tune.dense_min && tok_ext_cells) dense = std::min<uint32_t>(tune.dense_dim, nclasses);
         const uint64_t dense_cells = (uint64_t)dense * dense;
 
+        // ---- large levels: radix-partitioned counting in shared memory (partition.cu); the HBM-table path below serves the small ones
+        const uint64_t wbound = use_list ? nlist : std::min<uint64_t>(prev_occ, npos);  // valid windows start where the (n-1)-gram survived
+        bool     parted = false;
+        uint64_t windows = 0, singles = 0;
+        Segment  sg;
+        sg.n = n;
+        if (tune.use_partition(wbound) && wbound < 0xFFFFFFF0ull) {
+            if (filter.n < dense_cells + 8) TRY(filter.alloc(dev, dense_cells + 8));
+            bool overflow = false;
+            TRY(level_partitioned(n, prev.p, cur.p, npos, list, nlist, wbound, dense, filter.p, t, tok.p + npos + 8, sg, overflow));
+            parted = !overflow;
+            if (parted) {
+                windows = h_stats.valid_windows;
+                singles = h_stats.singletons;
+                ngram_upserts += windows;
+                m->levels[n].windows = windows;
+                m->levels[n].singles = singles;
+                m->levels[n].items   = use_list ? nlist : npos;
+            } else if (use_list) {
+                CUDA_TRY(cudaMemsetAsync(cur.p, 0, npos * sizeof(uint32_t), s));
+            }
+        }
+        uint64_t found = 0, kept = 0, occ = 0;
+        if (parted) {
+            found = h_stats.found; kept = h_stats.kept; occ = h_stats.kept_occ;
+            if (indexed) {
+                if (slot_index.n < kept + 8) TRY(slot_index.alloc(dev, kept + 8));
+                launches += launch_iota_plus1(s, slot_index.p, kept);  // the ids are survivor indices already
+            }
+        } else {
         // ---- occurrence filter (t >= 2): the 2-bit counters and the dense square share one buffer, pinned in L2 for the level
         const bool use_filter = tune.use_filter(t, bound);
         uint64_t   nbuckets = 0, cap = 0;
@@ -779,7 +871,6 @@ int Trainer::run() {
             cap = std::max<uint64_t>(64, bound + bound / 2 + 16);  // load factor <= 2/3
         }
         const uint64_t cap_max = std::max<uint64_t>(64, bound + bound / 2 + 16);  // windows <= bound: a table this large cannot fill up
-        uint64_t windows = 0, singles = 0;
         for (;;) {
             cap = (cap + 31) / 32 * 32;  // the dense cells' survivor bits start on a bitmap word
             if (cap + dense_cells >= 0xFFFFFFF0ull)
@@ -817,8 +908,6 @@ int Trainer::run() {
         m->levels[n].items   = use_list ? nlist : npos;
 
         int hp = timer.begin(COLIBRI_T_PRUNE);
-        Segment sg;
-        sg.n = n;
         uint64_t sv_bound = windows / std::max<uint32_t>(t, 1) + 1;
         TRY(sg.pos.alloc(dev, sv_bound));
         TRY(sg.cnt.alloc(dev, sv_bound));
@@ -832,8 +921,10 @@ int Trainer::run() {
         TRY(read_stats());
         if (use_filter || dense) l2_unpin();
         // a window the filter held back is a distinct n-gram with exactly one occurrence: found, and pruned (t >= 2)
-        const uint64_t found = h_stats.found + singles, kept = h_stats.kept, occ = h_stats.kept_occ;
+        found = h_stats.found + singles; kept = h_stats.kept; occ = h_stats.kept_occ;
+        }  // HBM-table path
         sg.count = kept;
+        int hp = -1;
         if (indexed && kept > 0) {  // IndexedPatternModel::add (:2789-2800) + posttrain sort (:2699-2705)
             int hi = timer.begin(COLIBRI_T_INDEX);
             TRY(build_refs(sg, cur.p, slot_index.p, false, npos, occ, indexed_skip && n >= 3));
@@ -919,7 +1010,8 @@ int Trainer::run() {
                     if (list_next.n < occ + 8) TRY(list_next.alloc(dev, occ + 8));
                     CUDA_TRY(cudaMemsetAsync(&d_stats.p->cursor, 0, sizeof(unsigned long long), s));
                 }
-                launches += launch_relabel(s, cur.p, npos, bitmap.p, list, nlist, next_list ? list_next.p : nullptr, &d_stats.p->cursor, sms);
+                if (!parted) launches += launch_relabel(s, cur.p, npos, bitmap.p, list, nlist, next_list ? list_next.p : nullptr, &d_stats.p->cursor, sms);
+                else if (next_list) launches += launch_compact_nonzero(s, cur.p, npos, list_next.p, &d_stats.p->cursor);  // the ids are final already
                 timer.end(hp);
                 if (next_list) {
                     TRY(read_stats());

@@ -197,6 +197,7 @@ struct Tuning {
     uint64_t hot_min         = 1ull << 25;  // COLIBRI_B200_HOT_MIN
     uint32_t dense_dim       = 2048;        // COLIBRI_B200_DENSE: side of the directly addressed square of level 2 (0 = off)
     uint64_t dense_min       = 1ull << 25;  // COLIBRI_B200_DENSE_MIN
+    uint64_t part_min        = 1ull << 22;  // COLIBRI_B200_PART_MIN: smallest level (upper bound of its windows) counted on the partitioned path (partition.cu)
     uint32_t sparse_div      = 4;           // COLIBRI_B200_SPARSE_DIV: level n+1 runs from a position list when occurrences(n) * div <= positions (0 = never)
     static uint64_t env_u64(const char* name, uint64_t dflt) {
         const char* e = getenv(name);
@@ -215,9 +216,11 @@ struct Tuning {
         t.dense_dim       = (uint32_t)std::min<uint64_t>(env_u64("COLIBRI_B200_DENSE", t.dense_dim), 16384);
         t.dense_min       = env_u64("COLIBRI_B200_DENSE_MIN", t.dense_min);
         t.sparse_div      = (uint32_t)env_u64("COLIBRI_B200_SPARSE_DIV", t.sparse_div);
+        t.part_min        = env_u64("COLIBRI_B200_PART_MIN", t.part_min);
         return t;
     }
     bool     use_filter(uint32_t mintokens, uint64_t bound) const { return mintokens >= 2 && !no_filter && bound >= filter_min; }
+    bool     use_partition(uint64_t windows) const { return windows >= part_min; }
     bool     use_hot(uint64_t bound) const { return hot_mode == 2 || (hot_mode == 1 && bound >= hot_min); }
     uint64_t filter_buckets(uint64_t bound) const {
         uint64_t nb = 1ull << filter_log2_min;

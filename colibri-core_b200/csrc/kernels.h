@@ -92,6 +92,32 @@ int launch_prune_ngrams(cudaStream_t s, const NgramSlot* table, uint64_t cap, ui
 int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t* bitmap, const uint32_t* list_in = nullptr, uint64_t nlist_in = 0, uint32_t* list_out = nullptr,
                    unsigned long long* cursor = nullptr, int sms = 148);
 
+// ---- partitioned counting path of a level (partition.cu): radix partition of the windows by key hash, counting in shared memory
+struct PartPlan {
+    int      b1 = 4, b2 = 4;  // bits of the first / second split
+    uint32_t nparts = 256;    // 1 << (b1 + b2)
+};
+PartPlan part_plan(uint64_t window_bound);  // <= 512 windows per partition on average
+// pass A: hist[partition] += 1 per hashed window (hist zeroed by the caller, nparts entries); level 2 (dense > 0): windows of two classes below `dense`
+// are counted in dense_cnt[a * dense + b] (zeroed) instead; st->valid_windows += valid windows
+int launch_part_hist(cudaStream_t s, const uint32_t* prev, const uint32_t* list, uint64_t nitems, uint32_t dense, uint32_t* dense_cnt, uint32_t* hist, const PartPlan& pl,
+                     DeviceStats* st, int sms);
+// off[nparts + 1] = exclusive scan of hist, cursor2[nparts] = off, cursor1[1 << b1] = first record of every b1-partition, tstart[(1 << b1) + 1] = tiles of pass D
+int launch_part_scan(cudaStream_t s, const uint32_t* hist, const PartPlan& pl, uint32_t* off, uint32_t* cursor2, uint32_t* cursor1, uint32_t* tstart);
+// pass B: records (key, position) of the hashed windows grouped by their b1 bits; dense mode (list == NULL) also writes cur[p] = dense_id[a * dense + b] or 0 for
+// every position (list mode: cur zeroed by the caller)
+int launch_part_split1(cudaStream_t s, const uint32_t* prev, const uint32_t* list, uint64_t nitems, uint32_t dense, const uint32_t* dense_id, uint32_t* cur, const PartPlan& pl,
+                       uint32_t* cursor1, void* rk /* u64 */, uint32_t* rp);
+// pass D: every b1-partition split by the next b2 bits (max_records: host-side upper bound of the record count, sizes the grid)
+int launch_part_split2(cudaStream_t s, const void* rk_in, const uint32_t* rp_in, const uint32_t* off, const uint32_t* tstart, const PartPlan& pl, uint64_t max_records,
+                       uint32_t* cursor2, void* rk_out, uint32_t* rp_out);
+// pass E: per partition count in shared memory, threshold, survivors appended through st->cursor to sv_pos / sv_cnt, out[rp[i]] = survivor index * id_mul + id_add
+// for the records of surviving keys; st->found / kept / kept_occ / singletons (keys counted once) are added to; kErrTableFull if a partition does not fit
+int launch_part_count(cudaStream_t s, const void* rk, const uint32_t* rp, const uint32_t* off, const PartPlan& pl, uint32_t threshold, uint32_t* out, uint32_t id_mul,
+                      uint32_t id_add, uint32_t* sv_pos, uint32_t* sv_cnt, DeviceStats* st, unsigned int* work /* zeroed */, int sms);
+int launch_compact_nonzero(cudaStream_t s, const uint32_t* cur, uint64_t npos, uint32_t* list_out, unsigned long long* cursor /* zeroed */);
+int launch_iota_plus1(cudaStream_t s, uint32_t* out, uint64_t n);
+
 // ---- skipgrams (config 3)
 // occ_pos != NULL: npos counts entries of occ_pos (explicit window positions) instead of corpus positions; item_slot (optional): slot + 1 per (window, mask)
 int launch_count_skipgrams(cudaStream_t s, const uint32_t* const* ids /*device array, index = level*/, int n, const SkipMask* masks /*device*/, int nmasks, uint64_t npos,

@@ -130,7 +130,7 @@ def test_gpu_matches_oracle_on_seeded_synthetic(kw, skip, path, monkeypatch):
 @pytest.mark.parametrize("kw,maxlength,mintokens", [(dict(ntokens=1500000, vocab=60000, seed=31, mean_sentence=22), 5, 2),
                                                     (dict(ntokens=800000, vocab=2000, seed=32, mean_sentence=9, phrase_permille=300, nphrases=300), 8, 3),
                                                     (dict(ntokens=300000, vocab=500, seed=33, mean_sentence=30), 3, 1)])
-@pytest.mark.parametrize("path", ["default", "bench"])
+@pytest.mark.parametrize("path", ["default", "bench", "part", "part+dense+list"])
 def test_indexed_model_matches_oracle(kw, maxlength, mintokens, path, monkeypatch):
     force_path(monkeypatch, path)
     _indexed_model_matches_oracle(kw, maxlength, mintokens)

@@ -222,7 +222,7 @@ def kernel_sources_sha():
     import hashlib
 
     h = hashlib.sha256()
-    for rel in ("colibri-core_b200/csrc/kernels.cu", "colibri-core_b200/csrc/device_utils.cuh", "colibri-core_b200/csrc/engine.cu", "colibri-core_b200/csrc/engine_common.h"):
+    for rel in ("colibri-core_b200/csrc/kernels.cu", "colibri-core_b200/csrc/partition.cu", "colibri-core_b200/csrc/device_utils.cuh", "colibri-core_b200/csrc/engine_common.h"):
         with open(os.path.join(ROOT, rel), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]
@@ -397,17 +397,17 @@ def run_ours(a):
         for n in range(2, m.maxlength() + 1):
             lv = m.level(n)
             count_ms += lv["count_ms"]
-            # dominant kernel family of level n (occurrence filter + count), DESIGN.md "algorithmic bytes": the count launch reads
-            # the previous id and writes the new id of every position (8 B) and moves one 32 B sector in and out of HBM per
-            # window that reaches the table; the filter launch (when used) reads the ids once more (4 B); its 2-bit
-            # counters are sized to stay in L2 and are not counted as HBM traffic.
+            # dominant kernel family of level n, DESIGN.md "algorithmic bytes" -- the unit of work, the same whichever path a level runs on: the
+            # previous id of every position is read and its new id written (8 B) and one 32 B sector moves in and out of HBM per window whose
+            # n-gram is not proven a singleton beforehand; the occurrence filter (HBM-table path) reads the ids once more (4 B); its 2-bit
+            # counters are sized to stay in L2 and are not counted.  On the partitioned path "singletons" are the n-grams that occur exactly once.
             # A level that runs from a position list (items < positions: only positions whose (n-1)-gram survived are visited) instead reads
             # 12 B per item (list entry, its id, the neighbour's id), zeroes the new id array (4 B/position) and writes 4 B per counted window.
             npos_l, table_w = ct["positions"] + 1, lv["windows"] - lv["singletons"]
             if lv["items"] < ct["positions"]:
-                alg_bytes += 12.0 * lv["items"] + 4.0 * npos_l + 68.0 * table_w + (8.0 * lv["items"] if lv["singletons"] else 0.0)
+                alg_bytes += 12.0 * lv["items"] + 4.0 * npos_l + 68.0 * table_w + (8.0 * lv["items"] if lv["filtered"] else 0.0)
             else:
-                alg_bytes += 8.0 * npos_l + 64.0 * table_w + (4.0 * npos_l if lv["singletons"] else 0.0)
+                alg_bytes += 8.0 * npos_l + 64.0 * table_w + (4.0 * npos_l if lv["filtered"] else 0.0)
         if last is not None:
             last.close()
         last = m
@@ -429,7 +429,7 @@ def run_ours(a):
                    "timing": "max(torch CUDA events, wall clock) around K synchronous ABI calls"},
         "device_ms_per_step": sum(dev_ms) / len(dev_ms),
         "phase_ms_per_step": {k: v / a.steps for k, v in phase_ms.items()},
-        "roofline": {"bound": "hbm", "kernel": "ngram_filter_kernel + count_ngrams_kernel (levels 2..%d; level 2 with dense pair slots)" % last.maxlength(), "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "count family, levels 2..%d: part_hist/split1/split2/count (level 2, partitioned, dense pair square) + ngram_filter_kernel + count_ngrams_kernel (HBM table)" % last.maxlength(), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "alg_bytes_per_step": alg_bytes / a.steps, "kernel_ms_per_step": count_ms / a.steps,
                      "kernel_share_of_step": (count_ms / a.steps) / (sum(dev_ms) / len(dev_ms)),
                      "traffic": traffic["dram_bytes_per_step"] if traffic else None, "traffic_source": traffic_note,

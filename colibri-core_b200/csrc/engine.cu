@@ -188,6 +188,8 @@ extern "C" int colibri_b200_model_level_info(const colibri_b200_model* m, int n,
     out[2] = it->second.ms;
     out[3] = (double)it->second.singles;
     out[4] = (double)it->second.items;
+    out[5] = (double)it->second.path;
+    out[6] = (double)it->second.filtered;
     return 0;
 }
 
@@ -315,7 +317,7 @@ struct Trainer {
     DevBuf<unsigned long long> part_rk1, part_rk2;
     DevBuf<uint32_t>           part_rp1, part_rp2, part_small, part_dense_id, part_dense_bits;
     int  level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint64_t npos, const uint32_t* list, uint64_t nlist, uint64_t wbound, uint32_t dense, uint32_t* dense_cnt,
-                           uint32_t t, uint32_t* tok_ext, Segment& sg, bool& overflow);
+                           uint32_t t, uint32_t* tok_ext, Segment& sg, bool& overflow, double hashed_share, DevBuf<uint32_t>* slot_index);
     int  l2_pin(const void* base, size_t bytes);
     void l2_unpin();
     const uint32_t*            tok_for_sink = nullptr;
@@ -587,24 +589,28 @@ int Trainer::flush_sink(bool final) {
 // kept_occ, singletons = keys that occur once); sg.pos / sg.cnt hold the survivors, cur[] the final ids (survivor index + 1, 0 = pruned or no
 // window).  overflow: a partition did not fit its shared-memory table -- nothing of the level is usable, the caller reruns it on the HBM table.
 int Trainer::level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint64_t npos, const uint32_t* list, uint64_t nlist, uint64_t wbound, uint32_t dense,
-                               uint32_t* dense_cnt, uint32_t t, uint32_t* tok_ext, Segment& sg, bool& overflow) {
+                               uint32_t* dense_cnt, uint32_t t, uint32_t* tok_ext, Segment& sg, bool& overflow, double hashed_share, DevBuf<uint32_t>* slot_index) {
     overflow = false;
-    const PartPlan pl  = part_plan(wbound);
+    // partitions are sized for the windows expected to become records (an estimate that is too low shows up as an overflow, not as a wrong count)
+    const PartPlan pl  = part_plan((uint64_t)((double)wbound * std::min(1.0, hashed_share)) + 1024);
     const uint32_t p1n = 1u << pl.b1;
-    // hist | off (+1) | cursor2 | cursor1 | tstart (+1) | work
-    const uint64_t small_words = 3ull * pl.nparts + 2ull * p1n + 8;
+    // hist1 | off1 (+1) | cursor1 | group_tot | group_base (+1) | off (+1) | kept_of (first: hist2) | dst_off (+1)
+    const uint64_t small_words = 5ull * p1n + 3ull * pl.nparts + 16;
     if (part_small.n < small_words) TRY(part_small.alloc(dev, small_words));
-    uint32_t* hist    = part_small.p;
-    uint32_t* off     = hist + pl.nparts;
-    uint32_t* cursor2 = off + pl.nparts + 1;
-    uint32_t* cursor1 = cursor2 + pl.nparts;
-    uint32_t* tstart  = cursor1 + p1n;
-    uint32_t* work    = tstart + p1n + 1;
+    uint32_t* hist1      = part_small.p;
+    uint32_t* off1       = hist1 + p1n;
+    uint32_t* cursor1    = off1 + p1n + 1;
+    uint32_t* group_tot  = cursor1 + p1n;
+    uint32_t* group_base = group_tot + p1n;
+    uint32_t* off        = group_base + p1n + 1;
+    uint32_t* kept_of    = off + pl.nparts + 1;
+    uint32_t* dst_off    = kept_of + pl.nparts;
     if (part_rk1.n < wbound + 1) TRY(part_rk1.alloc(dev, wbound + 1));
     if (part_rp1.n < wbound + 1) TRY(part_rp1.alloc(dev, wbound + 1));
     if (part_rk2.n < wbound + 1) TRY(part_rk2.alloc(dev, wbound + 1));
     if (part_rp2.n < wbound + 1) TRY(part_rp2.alloc(dev, wbound + 1));
     const uint64_t dense_cells = (uint64_t)dense * dense;
+    if (dense_cells + wbound + 2 >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "level %d: %llu windows; ids are 32 bit", n, (unsigned long long)wbound);
     if (dense) {
         if (part_dense_id.n < dense_cells) TRY(part_dense_id.alloc(dev, dense_cells));
         if (part_dense_bits.n < dense_cells / 32 + 8) TRY(part_dense_bits.alloc(dev, dense_cells / 32 + 8));
@@ -612,20 +618,31 @@ int Trainer::level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint6
     const uint64_t sv_bound = wbound / std::max<uint32_t>(t, 1) + 1;
     TRY(sg.pos.alloc(dev, sv_bound));
     TRY(sg.cnt.alloc(dev, sv_bound));
+    if (slot_index) {  // indexed models: id - 1 -> survivor index + 1 (the dense survivors' ids are their indices already)
+        if (slot_index->n < dense_cells + wbound + 8) TRY(slot_index->alloc(dev, dense_cells + wbound + 8));
+        launches += launch_iota_plus1(s, slot_index->p, dense_cells);
+    }
     const uint64_t nitems = list ? nlist : npos;
+    // the survivors wait inside their partition's record range until part_gather compacts them: the first split's buffers are free by then
+    uint32_t* tmp_pos = reinterpret_cast<uint32_t*>(part_rk1.p);
+    uint32_t* tmp_cnt = part_rp1.p;
 
     int hc = timer.begin(COLIBRI_T_COUNT, n);
-    CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)pl.nparts * sizeof(uint32_t), s));
-    CUDA_TRY(cudaMemsetAsync(work, 0, sizeof(uint32_t), s));
+    uint32_t* hist2 = kept_of;  // the final partitions' sizes (pass B) are consumed by the scan before pass E writes the survivor counts there
+    CUDA_TRY(cudaMemsetAsync(hist1, 0, (size_t)p1n * sizeof(uint32_t), s));
+    CUDA_TRY(cudaMemsetAsync(hist2, 0, (size_t)pl.nparts * sizeof(uint32_t), s));
     if (dense) CUDA_TRY(cudaMemsetAsync(dense_cnt, 0, dense_cells * sizeof(uint32_t), s));
     TRY(zero_stats());
-    launches += launch_part_hist(s, prev, list, nitems, dense, dense_cnt, hist, pl, d_stats.p, sms);
+    launches += launch_part_hist(s, prev, list, nitems, dense, dense_cnt, hist1, pl, d_stats.p, sms);
     if (dense)  // prune(MINTOKENS, 2) of the dense square first: its survivors open the segment, dense_id[cell] = survivor index + 1
         launches += launch_prune_dense(s, dense_cnt, dense, 0, t, sg.pos.p, sg.cnt.p, part_dense_bits.p, part_dense_id.p, tok_ext, (uint32_t)(npos + 8), d_stats.p, sms);
-    launches += launch_part_scan(s, hist, pl, off, cursor2, cursor1, tstart);
-    launches += launch_part_split1(s, prev, list, nitems, dense, part_dense_id.p, cur, pl, cursor1, part_rk1.p, part_rp1.p);
-    launches += launch_part_split2(s, part_rk1.p, part_rp1.p, off, tstart, pl, wbound, cursor2, part_rk2.p, part_rp2.p);
-    launches += launch_part_count(s, part_rk2.p, part_rp2.p, off, pl, t, cur, 1, 1, sg.pos.p, sg.cnt.p, d_stats.p, work, sms);
+    launches += launch_part_bases(s, hist1, p1n, off1, cursor1, nullptr);
+    launches += launch_part_split1(s, prev, list, nitems, dense, part_dense_id.p, cur, pl, cursor1, hist2, part_rk1.p, part_rp1.p);
+    launches += launch_part_scan(s, hist2, pl, group_tot, group_base, off, nullptr);
+    launches += launch_part_split2(s, part_rk1.p, part_rp1.p, off, pl, part_rk2.p, part_rp2.p);
+    launches += launch_part_count(s, part_rk2.p, part_rp2.p, off, pl, t, cur, (uint32_t)dense_cells, 1, 1, tmp_pos, tmp_cnt, kept_of, d_stats.p, sms);
+    launches += launch_part_gather(s, tmp_pos, tmp_cnt, off, kept_of, pl, group_tot, group_base, dst_off, &d_stats.p->cursor, sg.pos.p, sg.cnt.p,
+                                   slot_index ? slot_index->p : nullptr, (uint32_t)dense_cells);
     timer.end(hc);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
@@ -636,7 +653,8 @@ int Trainer::level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint6
         return 0;
     }
     if (sink) TRY(flush_sink(false));
-    m->levels[n].cap = pl.nparts;
+    m->levels[n].cap  = pl.nparts;
+    m->levels[n].path = 1;
     return 0;
 }
 
@@ -815,10 +833,15 @@ int Trainer::run() {
         uint64_t windows = 0, singles = 0;
         Segment  sg;
         sg.n = n;
-        if (tune.use_partition(wbound) && wbound < 0xFFFFFFF0ull) {
+        if (tune.use_partition(wbound, dense != 0) && wbound < 0xFFFFFFF0ull) {
             if (filter.n < dense_cells + 8) TRY(filter.alloc(dev, dense_cells + 8));
             bool overflow = false;
-            TRY(level_partitioned(n, prev.p, cur.p, npos, list, nlist, wbound, dense, filter.p, t, tok.p + npos + 8, sg, overflow));
+            double share = 1.0;  // windows of two dense classes never become records: their share follows from the class histogram
+            if (dense && m->totaltokens) {
+                const double f = (double)dense_tokens / (double)m->totaltokens;
+                share = 1.1 * (1.0 - f * f);
+            }
+            TRY(level_partitioned(n, prev.p, cur.p, npos, list, nlist, wbound, dense, filter.p, t, tok.p + npos + 8, sg, overflow, share, indexed ? &slot_index : nullptr));
             parted = !overflow;
             if (parted) {
                 windows = h_stats.valid_windows;
@@ -834,10 +857,6 @@ int Trainer::run() {
         uint64_t found = 0, kept = 0, occ = 0;
         if (parted) {
             found = h_stats.found; kept = h_stats.kept; occ = h_stats.kept_occ;
-            if (indexed) {
-                if (slot_index.n < kept + 8) TRY(slot_index.alloc(dev, kept + 8));
-                launches += launch_iota_plus1(s, slot_index.p, kept);  // the ids are survivor indices already
-            }
         } else {
         // ---- occurrence filter (t >= 2): the 2-bit counters and the dense square share one buffer, pinned in L2 for the level
         const bool use_filter = tune.use_filter(t, bound);
@@ -904,6 +923,8 @@ int Trainer::run() {
         filtered_windows += singles;
         m->levels[n].windows = windows;
         m->levels[n].cap     = cap;
+        m->levels[n].path    = 0;
+        m->levels[n].filtered = use_filter ? 1 : 0;
         m->levels[n].singles = singles;
         m->levels[n].items   = use_list ? nlist : npos;
 

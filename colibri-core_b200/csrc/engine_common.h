@@ -197,7 +197,9 @@ struct Tuning {
     uint64_t hot_min         = 1ull << 25;  // COLIBRI_B200_HOT_MIN
     uint32_t dense_dim       = 2048;        // COLIBRI_B200_DENSE: side of the directly addressed square of level 2 (0 = off)
     uint64_t dense_min       = 1ull << 25;  // COLIBRI_B200_DENSE_MIN
-    uint64_t part_min        = 1ull << 22;  // COLIBRI_B200_PART_MIN: smallest level (upper bound of its windows) counted on the partitioned path (partition.cu)
+    uint64_t part_min        = 1ull << 26;  // COLIBRI_B200_PART_MIN: smallest level (upper bound of its windows) counted on the partitioned path (partition.cu)
+    bool     part_all        = false;       // COLIBRI_B200_PART_ALL: every level >= part_min, not only level 2 with its dense square (measured: the later
+                                            // levels are faster on the HBM table -- their frequent keys make partitions only one warp works through)
     uint32_t sparse_div      = 4;           // COLIBRI_B200_SPARSE_DIV: level n+1 runs from a position list when occurrences(n) * div <= positions (0 = never)
     static uint64_t env_u64(const char* name, uint64_t dflt) {
         const char* e = getenv(name);
@@ -217,10 +219,11 @@ struct Tuning {
         t.dense_min       = env_u64("COLIBRI_B200_DENSE_MIN", t.dense_min);
         t.sparse_div      = (uint32_t)env_u64("COLIBRI_B200_SPARSE_DIV", t.sparse_div);
         t.part_min        = env_u64("COLIBRI_B200_PART_MIN", t.part_min);
+        t.part_all        = env_u64("COLIBRI_B200_PART_ALL", 0) != 0;
         return t;
     }
     bool     use_filter(uint32_t mintokens, uint64_t bound) const { return mintokens >= 2 && !no_filter && bound >= filter_min; }
-    bool     use_partition(uint64_t windows) const { return windows >= part_min; }
+    bool     use_partition(uint64_t windows, bool dense_level) const { return windows >= part_min && (dense_level || part_all); }
     bool     use_hot(uint64_t bound) const { return hot_mode == 2 || (hot_mode == 1 && bound >= hot_min); }
     uint64_t filter_buckets(uint64_t bound) const {
         uint64_t nb = 1ull << filter_log2_min;
@@ -254,7 +257,7 @@ struct colibri_b200_corpus {
 
 
 struct PassStat { uint64_t n, found, foundskip, pruned; };
-struct LevelInfo { uint64_t windows = 0, cap = 0, singles = 0, items = 0; double ms = 0; };
+struct LevelInfo { uint64_t windows = 0, cap = 0, singles = 0, items = 0; double ms = 0; int path = 0 /* 0 HBM table, 1 partitioned */; int filtered = 0; };
 struct colibri_b200_model {
     int      device = 0;
     int      model_type = COLIBRI_UNINDEXEDPATTERNMODEL;

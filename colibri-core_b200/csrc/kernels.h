@@ -94,27 +94,33 @@ int launch_relabel(cudaStream_t s, uint32_t* cur, uint64_t npos, const uint32_t*
 
 // ---- partitioned counting path of a level (partition.cu): radix partition of the windows by key hash, counting in shared memory
 struct PartPlan {
-    int      b1 = 4, b2 = 4;  // bits of the first / second split
+    int      b1 = 4, b2 = 4;  // bits of the first / second split (<= 11 each)
     uint32_t nparts = 256;    // 1 << (b1 + b2)
 };
-PartPlan part_plan(uint64_t window_bound);  // <= 512 windows per partition on average
-// pass A: hist[partition] += 1 per hashed window (hist zeroed by the caller, nparts entries); level 2 (dense > 0): windows of two classes below `dense`
-// are counted in dense_cnt[a * dense + b] (zeroed) instead; st->valid_windows += valid windows
-int launch_part_hist(cudaStream_t s, const uint32_t* prev, const uint32_t* list, uint64_t nitems, uint32_t dense, uint32_t* dense_cnt, uint32_t* hist, const PartPlan& pl,
+PartPlan part_plan(uint64_t window_bound);  // <= 256 windows per partition on average
+// pass A: hist1[b1 bits of the key hash] += 1 per hashed window (hist1 zeroed by the caller, 1 << b1 entries); level 2 (dense > 0): windows of two classes
+// below `dense` are counted in dense_cnt[a * dense + b] (zeroed) instead; st->valid_windows += valid windows
+int launch_part_hist(cudaStream_t s, const uint32_t* prev, const uint32_t* list, uint64_t nitems, uint32_t dense, uint32_t* dense_cnt, uint32_t* hist1, const PartPlan& pl,
                      DeviceStats* st, int sms);
-// off[nparts + 1] = exclusive scan of hist, cursor2[nparts] = off, cursor1[1 << b1] = first record of every b1-partition, tstart[(1 << b1) + 1] = tiles of pass D
-int launch_part_scan(cudaStream_t s, const uint32_t* hist, const PartPlan& pl, uint32_t* off, uint32_t* cursor2, uint32_t* cursor1, uint32_t* tstart);
-// pass B: records (key, position) of the hashed windows grouped by their b1 bits; dense mode (list == NULL) also writes cur[p] = dense_id[a * dense + b] or 0 for
-// every position (list mode: cur zeroed by the caller)
+// out[0..n] = exclusive scan of counts[0..n) (+ *base_ptr if given), out2 (may be NULL) = a second copy of out[0..n); n <= 2048 is cheap, larger n works
+int launch_part_bases(cudaStream_t s, const uint32_t* counts, uint32_t n, uint32_t* out, uint32_t* out2, const unsigned long long* base_ptr);
+// pass B: records (key, position) of the hashed windows grouped by their b1 bits (cursor1 = a copy of the partition offsets, advanced by the kernel);
+// dense mode (list == NULL) also writes cur[p] = dense_id[a * dense + b] or 0 for every position (list mode: cur zeroed by the caller)
 int launch_part_split1(cudaStream_t s, const uint32_t* prev, const uint32_t* list, uint64_t nitems, uint32_t dense, const uint32_t* dense_id, uint32_t* cur, const PartPlan& pl,
-                       uint32_t* cursor1, void* rk /* u64 */, uint32_t* rp);
-// pass D: every b1-partition split by the next b2 bits (max_records: host-side upper bound of the record count, sizes the grid)
-int launch_part_split2(cudaStream_t s, const void* rk_in, const uint32_t* rp_in, const uint32_t* off, const uint32_t* tstart, const PartPlan& pl, uint64_t max_records,
-                       uint32_t* cursor2, void* rk_out, uint32_t* rp_out);
-// pass E: per partition count in shared memory, threshold, survivors appended through st->cursor to sv_pos / sv_cnt, out[rp[i]] = survivor index * id_mul + id_add
-// for the records of surviving keys; st->found / kept / kept_occ / singletons (keys counted once) are added to; kErrTableFull if a partition does not fit
-int launch_part_count(cudaStream_t s, const void* rk, const uint32_t* rp, const uint32_t* off, const PartPlan& pl, uint32_t threshold, uint32_t* out, uint32_t id_mul,
-                      uint32_t id_add, uint32_t* sv_pos, uint32_t* sv_cnt, DeviceStats* st, unsigned int* work /* zeroed */, int sms);
+                       uint32_t* cursor1, uint32_t* hist2 /* zeroed, nparts: += records per final partition */, void* rk /* u64 */, uint32_t* rp);
+// off[0 .. nparts] = exclusive scan of counts[0 .. nparts) (+ *base_ptr if given); scratch: group_tot 1 << b1, group_base (1 << b1) + 1
+int launch_part_scan(cudaStream_t s, const uint32_t* counts, const PartPlan& pl, uint32_t* group_tot, uint32_t* group_base, uint32_t* off, const unsigned long long* base_ptr);
+// pass D: every b1-partition split by the next b2 bits; off[nparts + 1] = the final partition offsets
+int launch_part_split2(cudaStream_t s, const void* rk_in, const uint32_t* rp_in, const uint32_t* off, const PartPlan& pl, void* rk_out, uint32_t* rp_out);
+// pass E: per partition count in shared memory and threshold; survivors of partition q -> tmp_pos / tmp_cnt [off[q] ..], kept_of[q] of them;
+// out[rp[i]] = (id_base + index in tmp) * id_mul + id_add for the records of surviving keys; st->found / kept / kept_occ / singletons (keys counted
+// once) are added to; kErrTableFull if a partition does not fit its table
+int launch_part_count(cudaStream_t s, const void* rk, const uint32_t* rp, const uint32_t* off, const PartPlan& pl, uint32_t threshold, uint32_t* out, uint32_t id_base,
+                      uint32_t id_mul, uint32_t id_add, uint32_t* tmp_pos, uint32_t* tmp_cnt, uint32_t* kept_of, DeviceStats* st, int sms);
+// survivors out of the partitions' ranges -> sv_pos / sv_cnt [*first ..], compacted (scratch: group_tot 1 << b1, group_base (1 << b1) + 1, dst_off nparts + 1);
+// slot_index (may be NULL): slot_index[id_base + index in tmp] = survivor index + 1
+int launch_part_gather(cudaStream_t s, const uint32_t* tmp_pos, const uint32_t* tmp_cnt, const uint32_t* off, const uint32_t* kept_of, const PartPlan& pl, uint32_t* group_tot,
+                       uint32_t* group_base, uint32_t* dst_off, const unsigned long long* first, uint32_t* sv_pos, uint32_t* sv_cnt, uint32_t* slot_index, uint32_t id_base);
 int launch_compact_nonzero(cudaStream_t s, const uint32_t* cur, uint64_t npos, uint32_t* list_out, unsigned long long* cursor /* zeroed */);
 int launch_iota_plus1(cudaStream_t s, uint32_t* out, uint64_t n);
 

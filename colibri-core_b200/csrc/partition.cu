@@ -4,21 +4,24 @@
 // (:2107-2128).  Round 1 counted every window with one random 32-byte-sector access into a table in HBM; ncu showed the level-2 launch
 // moving 130 B of DRAM per table window at 38 % of the HBM peak (profiles/r02_ncu.md) -- random sectors are what HBM is worst at.  Here
 // the windows of a level are radix-partitioned by the high bits of their key hash, twice (b1 + b2 bits), with streaming passes only, until
-// a partition holds a few hundred windows; one thread block then counts a partition in a SHARED-MEMORY table, applies the threshold there
-// and hands every window of a surviving n-gram its id.  Nothing in HBM is ever probed:
-//   A  part_hist      stream prev[] (or the position list): histogram of the b1+b2 partition bits (REDs on an L2-resident array);
+// a partition holds a few hundred windows; one WARP then counts a partition in a shared-memory table, applies the threshold there
+// and hands every window of a surviving n-gram its id.  No table in HBM is ever probed, and no pass takes a global atomic per window:
+//   A  part_hist      stream prev[] (or the position list): histogram of the b1 bits, privatised in shared memory;
 //                     level 2: pairs of frequent classes are counted in the dense square instead and never become records
 //   -  prune_dense    (kernels.cu) dense square -> survivors, dense_id[cell] = survivor index + 1
-//   -  part_scan      exclusive scan of the histogram: partition offsets, cursors, tile starts of pass D
+//   -  part_bases     exclusive scan of the 2^b1 counts (one small block)
 //   B  part_split1    stream prev[] again: record (key, position) of every hashed window -> its b1-partition (block-staged in shared
 //                     memory, one cursor reservation per bin per tile); writes cur[] = dense id or 0 for every position on the way
-//   D  part_split2    every b1-partition -> its 2^b2 sub-partitions, same scheme
-//   E  part_count     one block per final partition: shared-memory open addressing (64-bit CAS), threshold, survivor compaction
-//                     (one global cursor reservation per partition), then cur[position] = survivor index + 1 for the windows that stay
-// ids are survivor indices + 1 (dense, no table slots), a pruned window keeps id 0: no survivor bitmap, no relabel pass, no table memset,
+//   -  scan of the b1+b2-bit histogram pass B took on the way (REDs on an L2-resident array): the final partition offsets
+//   D  part_split2    one block per b1-partition: its records go to their sub-partition in staged chunks through shared-memory cursors
+//   E  part_count     one warp per final partition: shared-memory open addressing (64-bit CAS), threshold; the survivors stay in the
+//                     partition's own range for now and name the ids: id = id_base + (offset of the partition) + (rank in it) + 1;
+//                     cur[position] = id for the windows that stay
+//   -  scan of the per-partition survivor counts, part_gather: survivors -> the level's segment, compacted
+// ids are unique non-zero numbers (not table slots), a pruned window keeps id 0: no survivor bitmap, no relabel pass, no table memset,
 // no table scan.  Exactness: keys are compared in full, partitions are exhaustive and disjoint (a key has one hash), counts are exact.
 // A partition with more distinct keys than the shared-memory table holds raises kErrTableFull and the host reruns the level on the HBM-table
-// path (never seen on hashed keys; partitions are sized for <= 512 windows on average, the table holds 2048 keys).
+// path (never seen on hashed keys; partitions are sized for <= 384 windows on average (usually half of that), a table holds 512 keys).
 #include <algorithm>
 
 #include "device_utils.cuh"
@@ -28,48 +31,62 @@ namespace colibri {
 
 namespace {
 
-constexpr int      kTile1      = 4096;  // items per block of pass B (16 per thread, four 16-byte loads)
-constexpr int      kTile2      = 2048;  // records per block of pass D
-constexpr uint32_t kPartSlots  = 2048;  // shared-memory table of pass E
-constexpr uint32_t kHotSide    = 64;    // pass A counts the pairs of the 64 most frequent classes in shared memory first
+constexpr int      kTile1   = 4096;  // items per block of pass B (16 per thread, four 16-byte loads)
+constexpr int      kTile2   = 4096;  // records per chunk of pass D (512 threads, 8 per thread)
+constexpr uint32_t kHotSide = 64;    // pass A counts the pairs of the 64 most frequent classes in shared memory first
 
 __device__ __forceinline__ uint32_t part_of(uint64_t h, int shift) {
     return (uint32_t)(h >> shift);
 }
 
 // ---- pass A ---------------------------------------------------------------------------------------------------------------------
+// dynamic shared memory: hist1 u32[nbins] (| hot u32[64 * 64] when kDense)
 template <bool kList, bool kDense>
 __global__ void __launch_bounds__(256) part_hist_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ list, uint64_t nitems, uint32_t dense,
-                                                        uint32_t* __restrict__ dense_cnt, uint32_t* __restrict__ hist, int shift, DeviceStats* __restrict__ st) {
+                                                        uint32_t* __restrict__ dense_cnt, uint32_t* __restrict__ hist, uint32_t nbins, int shift1, DeviceStats* __restrict__ st) {
+    extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t scratch[8];
-    __shared__ uint32_t hot[kDense ? kHotSide * kHotSide : 1];
-    if (kDense) {
-        for (uint32_t i = threadIdx.x; i < kHotSide * kHotSide; i += blockDim.x) hot[i] = 0;
-        __syncthreads();
-    }
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint32_t       valid  = 0;
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nitems; j += stride) {
-        uint64_t p = j;
-        uint32_t a;
-        if (kList) {
-            p = __ldcs(list + j);
-            a = __ldg(prev + p);
-        } else {
-            a = __ldcs(prev + p);
-        }
-        const uint32_t b = __ldg(prev + p + 1);
-        if (a == 0 || b == 0) continue;
+    uint32_t* h1  = reinterpret_cast<uint32_t*>(smem);
+    uint32_t* hot = h1 + nbins;
+    for (uint32_t i = threadIdx.x; i < nbins + (kDense ? kHotSide * kHotSide : 0); i += blockDim.x) h1[i] = 0;
+    __syncthreads();
+    uint32_t valid = 0;
+    auto     one   = [&](uint32_t a, uint32_t b) {
+        if (a == 0 || b == 0) return;
         ++valid;
         if (kDense && a < dense && b < dense) {
             if (a < kHotSide && b < kHotSide) atomicAdd(&hot[a * kHotSide + b], 1u);
             else atomicAdd(dense_cnt + a * dense + b, 1u);
-            continue;
+            return;
         }
-        atomicAdd(hist + part_of(table_hash_u64(((unsigned long long)a << 32) | b), shift), 1u);
+        atomicAdd(&h1[part_of(table_hash_u64(((unsigned long long)a << 32) | b), shift1)], 1u);
+    };
+    if (kList) {
+        const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+        for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nitems; j += stride) {
+            const uint32_t p = __ldcs(list + j);
+            one(__ldg(prev + p), __ldg(prev + p + 1));
+        }
+    } else {
+        // four positions per thread and iteration (one 16-byte load); the right neighbour of the fourth comes from the next lane.
+        // A warp leaves the loop as a whole (its first lane's position decides), so the shuffle always sees 32 lanes.
+        const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+        for (uint64_t p0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;; p0 += stride) {
+            if (p0 - (uint64_t)lane_id() * 4 >= nitems) break;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (p0 < nitems) v = __ldcs(reinterpret_cast<const uint4*>(prev + p0));  // prev has nitems + 8 entries
+            uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (lane_id() == 31) nxt = p0 + 4 <= nitems ? __ldg(prev + p0 + 4) : 0u;
+            if (p0 < nitems) one(v.x, v.y);
+            if (p0 + 1 < nitems) one(v.y, v.z);
+            if (p0 + 2 < nitems) one(v.z, v.w);
+            if (p0 + 3 < nitems) one(v.w, nxt);
+        }
     }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nbins; i += blockDim.x)
+        if (h1[i]) atomicAdd(hist + i, h1[i]);
     if (kDense) {
-        __syncthreads();
         for (uint32_t i = threadIdx.x; i < kHotSide * kHotSide; i += blockDim.x) {
             const uint32_t c = hot[i], a = i / kHotSide, b = i % kHotSide;
             if (c && a < dense && b < dense) atomicAdd(dense_cnt + a * dense + b, c);
@@ -79,70 +96,81 @@ __global__ void __launch_bounds__(256) part_hist_kernel(const uint32_t* __restri
     if (threadIdx.x == 0 && v) atomicAdd(&st->valid_windows, (unsigned long long)v);
 }
 
-// ---- scan: off[i] = sum of hist[0..i), cursor2 = off, cursor1[p1] = off[p1 << b2], tstart[p1] = tiles of pass D before partition p1 -----------
-__global__ void __launch_bounds__(1024) part_scan_kernel(const uint32_t* __restrict__ hist, uint32_t nparts, int b2, uint32_t* off, uint32_t* __restrict__ cursor2,
-                                                         uint32_t* __restrict__ cursor1, uint32_t* __restrict__ tstart) {
+// ---- exclusive scan of up to 2048 counts in one block: out[i] = base + sum of in[0..i), out[n] = base + total ------------------------------
+// base_ptr (may be NULL): a device-side value added to everything (the survivors the dense square already produced)
+__global__ void __launch_bounds__(1024) part_bases_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out, uint32_t* __restrict__ out2,
+                                                          const unsigned long long* __restrict__ base_ptr) {
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
+    if (threadIdx.x == 0) carry = base_ptr ? (uint32_t)*base_ptr : 0u;
     __syncthreads();
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < nparts; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < nparts ? hist[i] : 0u;
-        uint32_t incl = warp_inclusive_scan(v);
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_tot[lane];
-            uint32_t s = warp_inclusive_scan(w);
-            warp_tot[lane] = s - w;
-        }
-        __syncthreads();
-        const uint32_t excl = carry + warp_tot[warp] + incl - v;
-        if (i < nparts) {
-            off[i]     = excl;
-            cursor2[i] = excl;
-            if ((i & ((1u << b2) - 1)) == 0) cursor1[i >> b2] = excl;
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) off[nparts] = carry;
-    __syncthreads();
-    // tiles of pass D per b1-partition: tstart[q] = tiles before partition q (<= 2048 partitions: two rounds of the same block scan)
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const uint32_t p1n = nparts >> b2, total = off[nparts];
-    for (uint32_t base = 0; base <= p1n; base += 1024) {
+    for (uint32_t base = 0; base < n; base += 1024) {
         const uint32_t q = base + threadIdx.x;
-        uint32_t       v = 0;
-        if (q < p1n) {
-            const uint32_t beg = off[q << b2], end = (q + 1 == p1n) ? total : off[(q + 1) << b2];
-            v                  = (end - beg + kTile2 - 1) / kTile2;
-        }
+        const uint32_t v = q < n ? in[q] : 0u;
         uint32_t incl = warp_inclusive_scan(v);
         if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            uint32_t w = warp_tot[lane];
-            uint32_t s = warp_inclusive_scan(w);
-            warp_tot[lane] = s - w;
+            uint32_t a = warp_tot[lane], s1 = warp_inclusive_scan(a);
+            warp_tot[lane] = s1 - a;
         }
         __syncthreads();
         const uint32_t excl = carry + warp_tot[warp] + incl - v;
-        if (q <= p1n) tstart[q] = excl;
+        if (q < n) {
+            out[q] = excl;
+            if (out2) out2[q] = excl;
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
+    if (threadIdx.x == 0) out[n] = carry;
 }
 
-// ---- the block-level multi-split both passes share: nbins counters, exclusive prefix, one cursor reservation per non-empty bin -------------
-// bins[0..nbins) = per-bin record count of the tile on entry; on exit bins[b] = first staging index of bin b, gdelta[b] = (global index of
-// the bin's run) - (staging index), returns the tile's record total
-__device__ __forceinline__ uint32_t split_reserve(uint32_t* bins, uint32_t* gdelta, uint32_t nbins, uint32_t* __restrict__ cursor, uint32_t* warp_tot) {
+// ---- scan of nparts per-partition counts in three small launches (totals per group of 2^b2, scan of the group totals, scan inside each group)
+__global__ void __launch_bounds__(256) part_totals_kernel(const uint32_t* __restrict__ cnt, int b2, uint32_t* __restrict__ totals) {
+    __shared__ uint64_t scratch[8];
+    const uint32_t n = 1u << b2;
+    uint32_t       v = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += 256) v += cnt[((uint64_t)blockIdx.x << b2) + i];
+    uint64_t t = block_reduce_sum(v, scratch);
+    if (threadIdx.x == 0) totals[blockIdx.x] = (uint32_t)t;
+}
+__global__ void __launch_bounds__(256) part_offsets_kernel(const uint32_t* __restrict__ cnt, int b2, const uint32_t* __restrict__ group_base, uint32_t* __restrict__ off) {
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = group_base[blockIdx.x];
+    __syncthreads();
+    const uint32_t n = 1u << b2, lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint64_t first = (uint64_t)blockIdx.x << b2;
+    for (uint32_t base = 0; base < n; base += 256) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? cnt[first + i] : 0u;
+        uint32_t incl = warp_inclusive_scan(v);
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < 8; ++w) {
+            const uint32_t c = warp_tot[w];
+            if (w < warp) before += c;
+            total += c;
+        }
+        const uint32_t excl = carry + before + incl - v;
+        if (i < n) off[first + i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (blockIdx.x + 1 == gridDim.x && threadIdx.x == 0) off[first + n] = carry;  // off[nparts] = grand total
+}
+
+// ---- block-level multi-split: bins[0..nbins) = per-bin record count of the tile on entry; on exit bins[b] = first staging index of bin b,
+// gdelta[b] = (global index of the bin's run) - (staging index); returns the tile's record total.  The run is reserved with one atomicAdd per
+// non-empty bin on cursor[] (global memory, pass B) or, kLocal, by advancing the block's own shared-memory cursors (pass D).
+template <bool kLocal>
+__device__ __forceinline__ uint32_t split_reserve(uint32_t* bins, uint32_t* gdelta, uint32_t nbins, uint32_t* cursor, uint32_t* warp_tot) {
     // nbins <= 2048, 256 threads: thread t owns bins [t * per, (t + 1) * per)
     const uint32_t per = (nbins + 255) / 256;
     uint32_t       local[8];
@@ -169,7 +197,14 @@ __device__ __forceinline__ uint32_t split_reserve(uint32_t* bins, uint32_t* gdel
         const uint32_t b = threadIdx.x * per + k;
         if (k < per && b < nbins) {
             bins[b] = run;
-            if (local[k]) gdelta[b] = atomicAdd(cursor + b, local[k]) - run;
+            if (local[k]) {
+                if (kLocal) {
+                    gdelta[b] = cursor[b] - run;
+                    cursor[b] += local[k];
+                } else {
+                    gdelta[b] = atomicAdd(cursor + b, local[k]) - run;
+                }
+            }
             run += local[k];
         }
     }
@@ -180,9 +215,10 @@ __device__ __forceinline__ uint32_t split_reserve(uint32_t* bins, uint32_t* gdel
 // ---- pass B ---------------------------------------------------------------------------------------------------------------------
 // dynamic shared memory: stage_key u64[kTile1] | stage_pos u32[kTile1] | stage_bin u16[kTile1] | bins u32[nbins] | gdelta u32[nbins]
 template <bool kList, bool kDense>
-__global__ void __launch_bounds__(256) part_split1_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ list, uint64_t nitems, uint32_t dense,
-                                                          const uint32_t* __restrict__ dense_id, uint32_t* __restrict__ cur, int shift1, uint32_t nbins,
-                                                          uint32_t* __restrict__ cursor1, unsigned long long* __restrict__ rk, uint32_t* __restrict__ rp) {
+__global__ void __launch_bounds__(256, 3) part_split1_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ list, uint64_t nitems, uint32_t dense,
+                                                             const uint32_t* __restrict__ dense_id, uint32_t* __restrict__ cur, int shift1, int b2, uint32_t nbins,
+                                                             uint32_t* __restrict__ cursor1, uint32_t* __restrict__ hist2, unsigned long long* __restrict__ rk,
+                                                             uint32_t* __restrict__ rp) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned long long* stage_key = reinterpret_cast<unsigned long long*>(smem);
     uint32_t*           stage_pos = reinterpret_cast<uint32_t*>(stage_key + kTile1);
@@ -195,10 +231,10 @@ __global__ void __launch_bounds__(256) part_split1_kernel(const uint32_t* __rest
     __syncthreads();
 
     const uint64_t tile = (uint64_t)blockIdx.x * kTile1;
-    uint32_t       a[16], b[16], pos[16];
-    uint32_t       binrank[16];  // bin << 16 | rank inside (tile, bin); 0xFFFFFFFF = no record
+    uint32_t       binrank[16];  // bin << 16 | rank inside (tile, bin); 0xFFFFFFFF = no record (<= 4096 records per tile: the rank fits 16 bits)
     if (!kList) {
         // four 16-byte loads per thread: positions tile + k * 1024 + 4 * tid .. + 3; the right neighbour of the fourth comes from the next lane
+        uint32_t a[16], nx[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint64_t p0 = tile + (uint64_t)k * 1024 + 4u * threadIdx.x;
@@ -207,47 +243,76 @@ __global__ void __launch_bounds__(256) part_split1_kernel(const uint32_t* __rest
             uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
             if (lane_id() == 31) nxt = p0 + 4 <= nitems ? __ldg(prev + p0 + 4) : 0u;
             a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
-            b[4 * k] = v.y; b[4 * k + 1] = v.z; b[4 * k + 2] = v.w; b[4 * k + 3] = nxt;
+            nx[k] = nxt;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                pos[4 * k + e] = (uint32_t)(p0 + e);
+            for (int e = 0; e < 4; ++e)
                 if (p0 + e >= nitems) a[4 * k + e] = 0;
-            }
         }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const uint64_t j = tile + (uint64_t)k * 256 + threadIdx.x;
-            a[k] = 0; b[k] = 0; pos[k] = 0;
-            if (j < nitems) {
-                pos[k] = __ldcs(list + j);
-                a[k]   = __ldg(prev + pos[k]);
-                b[k]   = __ldg(prev + pos[k] + 1);
-            }
-        }
-    }
-    uint32_t dense_out[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        binrank[k]   = 0xFFFFFFFFu;
-        dense_out[k] = 0;
-        if (a[k] == 0 || b[k] == 0) continue;
-        if (kDense && a[k] < dense && b[k] < dense) {
-            dense_out[k] = __ldg(dense_id + a[k] * dense + b[k]);
-            continue;
-        }
-        const uint32_t bin = part_of(table_hash_u64(((unsigned long long)a[k] << 32) | b[k]), shift1);
-        binrank[k]         = (bin << 16) | atomicAdd(&bins[bin], 1u);  // <= 4096 records per tile: the rank fits 16 bits (4095 at most)
-    }
-    if (!kList) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+            uint32_t dense_out[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t x = a[4 * k + e], y = e < 3 ? a[4 * k + e + 1] : nx[k];
+                binrank[4 * k + e] = 0xFFFFFFFFu;
+                dense_out[e]       = 0;
+                if (x == 0 || y == 0) continue;
+                if (kDense && x < dense && y < dense) {
+                    dense_out[e] = __ldg(dense_id + x * dense + y);
+                    continue;
+                }
+                const uint32_t part = part_of(table_hash_u64(((unsigned long long)x << 32) | y), shift1 - b2), bin = part >> b2;
+                atomicAdd(hist2 + part, 1u);  // result unused -> RED: the final partitions' sizes, for pass D
+                binrank[4 * k + e] = (bin << 16) | atomicAdd(&bins[bin], 1u);
+            }
             const uint64_t p0 = tile + (uint64_t)k * 1024 + 4u * threadIdx.x;
-            if (p0 < nitems) __stcs(reinterpret_cast<uint4*>(cur + p0), make_uint4(dense_out[4 * k], dense_out[4 * k + 1], dense_out[4 * k + 2], dense_out[4 * k + 3]));
+            if (p0 < nitems) __stcs(reinterpret_cast<uint4*>(cur + p0), make_uint4(dense_out[0], dense_out[1], dense_out[2], dense_out[3]));
+        }
+        __syncthreads();
+        const uint32_t total = split_reserve<false>(bins, gdelta, nbins, cursor1, warp_tot);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t br = binrank[4 * k + e];
+                if (br == 0xFFFFFFFFu) continue;
+                const uint32_t x = a[4 * k + e], y = e < 3 ? a[4 * k + e + 1] : nx[k];
+                const uint32_t bin = br >> 16, idx = bins[bin] + (br & 0xFFFFu);
+                stage_key[idx]     = ((unsigned long long)x << 32) | y;
+                stage_pos[idx]     = (uint32_t)(tile + (uint64_t)k * 1024 + 4u * threadIdx.x + e);
+                stage_bin[idx]     = (uint16_t)bin;
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < total; i += 256) {
+            const uint32_t dst = gdelta[stage_bin[i]] + i;
+            rk[dst]            = stage_key[i];
+            rp[dst]            = stage_pos[i];
+        }
+        return;
+    }
+    // list mode: item j is position list[j]; cur was zeroed by the host
+    uint32_t a[16], b[16], pos[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint64_t j = tile + (uint64_t)k * 256 + threadIdx.x;
+        a[k] = 0; b[k] = 0; pos[k] = 0;
+        if (j < nitems) {
+            pos[k] = __ldcs(list + j);
+            a[k]   = __ldg(prev + pos[k]);
+            b[k]   = __ldg(prev + pos[k] + 1);
         }
     }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        binrank[k] = 0xFFFFFFFFu;
+        if (a[k] == 0 || b[k] == 0) continue;
+        const uint32_t part = part_of(table_hash_u64(((unsigned long long)a[k] << 32) | b[k]), shift1 - b2), bin = part >> b2;
+        atomicAdd(hist2 + part, 1u);
+        binrank[k]         = (bin << 16) | atomicAdd(&bins[bin], 1u);
+    }
     __syncthreads();
-    const uint32_t total = split_reserve(bins, gdelta, nbins, cursor1, warp_tot);
+    const uint32_t total = split_reserve<false>(bins, gdelta, nbins, cursor1, warp_tot);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         if (binrank[k] == 0xFFFFFFFFu) continue;
@@ -265,74 +330,119 @@ __global__ void __launch_bounds__(256) part_split1_kernel(const uint32_t* __rest
 }
 
 // ---- pass D ---------------------------------------------------------------------------------------------------------------------
-// dynamic shared memory: stage_key u64[kTile2] | stage_pos u32[kTile2] | stage_bin u16[kTile2] | bins u32[nbins] | gdelta u32[nbins]
-__global__ void __launch_bounds__(256) part_split2_kernel(const unsigned long long* __restrict__ rk_in, const uint32_t* __restrict__ rp_in, const uint32_t* __restrict__ off,
-                                                          const uint32_t* __restrict__ tstart, uint32_t p1n, int b2, int shift2, uint32_t* __restrict__ cursor2,
-                                                          unsigned long long* __restrict__ rk_out, uint32_t* __restrict__ rp_out) {
+// One block per b1-partition q (records off[q << b2] .. off[(q + 1) << b2]): chunks of kTile2 records are ranked by their next b2 hash bits,
+// grouped per bin in shared memory and copied to their sub-partition through the block's own cursors (= the final partition offsets, from the
+// scan of the histogram pass B took).  No global atomic.
+// dynamic shared memory: stage_key u64[kTile2] | stage_pos u32[kTile2] | stage_bin u16[kTile2] | cursors u32[nbins] | bins u32[nbins] | gdelta u32[nbins]
+__global__ void __launch_bounds__(512, 2) part_split2_kernel(const unsigned long long* __restrict__ rk_in, const uint32_t* __restrict__ rp_in, const uint32_t* __restrict__ off,
+                                                             int b2, int shift2, unsigned long long* __restrict__ rk_out, uint32_t* __restrict__ rp_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t      nbins     = 1u << b2;
     unsigned long long* stage_key = reinterpret_cast<unsigned long long*>(smem);
     uint32_t*           stage_pos = reinterpret_cast<uint32_t*>(stage_key + kTile2);
     uint16_t*           stage_bin = reinterpret_cast<uint16_t*>(stage_pos + kTile2);
-    uint32_t*           bins      = reinterpret_cast<uint32_t*>(stage_bin + kTile2);
+    uint32_t*           cursors   = reinterpret_cast<uint32_t*>(stage_bin + kTile2);
+    uint32_t*           bins      = cursors + nbins;
     uint32_t*           gdelta    = bins + nbins;
-    __shared__ uint32_t warp_tot[8];
-    if (blockIdx.x >= __ldg(tstart + p1n)) return;
-    // which b1-partition this tile belongs to: last q with tstart[q] <= blockIdx.x
-    uint32_t lo = 0, hi = p1n;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(tstart + mid) <= blockIdx.x) lo = mid;
-        else hi = mid;
-    }
-    const uint32_t q    = lo;
-    const uint32_t beg  = __ldg(off + ((uint64_t)q << b2)) + (blockIdx.x - __ldg(tstart + q)) * kTile2;
-    const uint32_t pend = __ldg(off + ((uint64_t)(q + 1) << b2));  // off has nparts + 1 entries: the last partition ends at the total
-    const uint32_t end  = beg + kTile2 < pend ? beg + kTile2 : pend;
-
-    for (uint32_t i = threadIdx.x; i < nbins; i += 256) bins[i] = 0;
-    __syncthreads();
-    unsigned long long key[8];
-    uint32_t           pos[8], binrank[8];
+    __shared__ uint32_t warp_tot[16];
+    const uint64_t first = (uint64_t)blockIdx.x << b2;
+    const uint32_t beg = __ldg(off + first), end = __ldg(off + first + nbins);
+    for (uint32_t i = threadIdx.x; i < nbins; i += 512) cursors[i] = __ldg(off + first + i);
+    for (uint32_t c0 = beg; c0 < end; c0 += kTile2) {
+        for (uint32_t i = threadIdx.x; i < nbins; i += 512) bins[i] = 0;
+        __syncthreads();
+        unsigned long long key[8];
+        uint32_t           pos[8], binrank[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint32_t i = beg + k * 256 + threadIdx.x;
-        binrank[k]       = 0xFFFFFFFFu;
-        if (i < end) {
-            key[k] = __ldcs(rk_in + i);
-            pos[k] = __ldcs(rp_in + i);
-            const uint32_t bin = part_of(table_hash_u64(key[k]), shift2) & (nbins - 1);
-            binrank[k]         = (bin << 16) | atomicAdd(&bins[bin], 1u);
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t i = c0 + k * 512 + threadIdx.x;
+            key[k]           = 0;
+            pos[k]           = 0;
+            if (i < end) {
+                key[k] = __ldcs(rk_in + i);
+                pos[k] = __ldcs(rp_in + i);
+            }
         }
-    }
-    __syncthreads();
-    const uint32_t total = split_reserve(bins, gdelta, nbins, cursor2 + ((uint64_t)q << b2), warp_tot);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (binrank[k] == 0xFFFFFFFFu) continue;
-        const uint32_t bin = binrank[k] >> 16, idx = bins[bin] + (binrank[k] & 0xFFFFu);
-        stage_key[idx]     = key[k];
-        stage_pos[idx]     = pos[k];
-        stage_bin[idx]     = (uint16_t)bin;
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < total; i += 256) {
-        const uint32_t dst = gdelta[stage_bin[i]] + i;
-        rk_out[dst]        = stage_key[i];
-        rp_out[dst]        = stage_pos[i];
+        for (int k = 0; k < 8; ++k) {
+            binrank[k] = 0xFFFFFFFFu;
+            if (key[k]) {
+                const uint32_t bin = part_of(table_hash_u64(key[k]), shift2) & (nbins - 1);
+                binrank[k]         = (bin << 16) | atomicAdd(&bins[bin], 1u);
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the chunk's bin counts (512 threads, <= 4 bins each); the runs go where the block's cursors point
+        uint32_t total;
+        {
+            const uint32_t per = (nbins + 511) / 512;
+            uint32_t       local[4], sum = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                const uint32_t b = threadIdx.x * per + k;
+                local[k]         = (k < per && b < nbins) ? bins[b] : 0u;
+                sum += local[k];
+            }
+            uint32_t incl = warp_inclusive_scan(sum);
+            if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            uint32_t before = 0;
+            total           = 0;
+#pragma unroll
+            for (uint32_t w = 0; w < 16; ++w) {
+                const uint32_t c = warp_tot[w];
+                if (w < (threadIdx.x >> 5)) before += c;
+                total += c;
+            }
+            uint32_t run = before + incl - sum;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                const uint32_t b = threadIdx.x * per + k;
+                if (k < per && b < nbins) {
+                    bins[b] = run;
+                    if (local[k]) {
+                        gdelta[b] = cursors[b] - run;
+                        cursors[b] += local[k];
+                    }
+                    run += local[k];
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (binrank[k] == 0xFFFFFFFFu) continue;
+            const uint32_t bin = binrank[k] >> 16, idx = bins[bin] + (binrank[k] & 0xFFFFu);
+            stage_key[idx]     = key[k];
+            stage_pos[idx]     = pos[k];
+            stage_bin[idx]     = (uint16_t)bin;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < total; i += 512) {
+            const uint32_t dst = gdelta[stage_bin[i]] + i;
+            rk_out[dst]        = stage_key[i];
+            rp_out[dst]        = stage_pos[i];
+        }
+        __syncthreads();
     }
 }
 
 // ---- pass E ---------------------------------------------------------------------------------------------------------------------
-// One block per partition (persistent blocks take partitions from a work counter).  out[rp[i]] = (survivor index) * id_mul + id_add for the
-// records of surviving keys (single GPU: id_mul = id_add = 1, out = cur; owner of a sharded run: out = the reply array, global ids).
-constexpr int kHeld = 4;  // records per thread kept in registers between the two phases (partitions of <= 1024 records never re-read)
+// One WARP per partition (a partition is a few hundred records: a block would spend its time in barriers and in the latency of one
+// partition's loads; 24 independent warps per SM overlap them).  Each warp owns a 512-slot table in shared memory.  The survivors of
+// partition q stay inside the partition's own record range for now -- tmp_pos / tmp_cnt [off[q] + r], r = 0 .. kept[q] -- and that place names
+// the n-gram: id = (id_base + off[q] + r) * id_mul + id_add.  No global atomic at all (one compaction cursor for all partitions costs ~5 ns per
+// partition, serialised: 1.4 of this kernel's 1.6 ms when it had one).  out[rp[i]] = id for the records of surviving keys (single GPU:
+// id_mul = id_add = 1, out = cur; owner of a sharded run: out = the reply array, global ids).
+constexpr int      kHeld      = 8;    // records per lane kept in registers between the two phases (partitions of <= 256 records never re-read)
+constexpr uint32_t kWarpSlots = 512;  // per-warp table: keys u64 | counts u32 = 6 KB
 
-__device__ __forceinline__ uint32_t smem_upsert(unsigned long long* tk, uint32_t* tc, uint32_t* tp, uint32_t mask, unsigned long long key, uint32_t pos, bool& full) {
+__device__ __forceinline__ uint32_t smem_upsert(unsigned long long* tk, uint32_t* tc, uint32_t mask, unsigned long long key, bool& claimed, bool& full) {
     uint32_t slot = (uint32_t)table_hash_u64(key) & mask;
+    claimed       = false;
     for (uint32_t step = 0; step <= mask; ++step) {
         const unsigned long long old = atomicCAS(tk + slot, 0ull, key);
-        if (old == 0ull) tp[slot] = pos;  // the claimer's position names the n-gram (any occurrence does)
+        if (old == 0ull) claimed = true;
         if (old == 0ull || old == key) {
             atomicAdd(tc + slot, 1u);
             return slot;
@@ -352,117 +462,214 @@ __device__ __forceinline__ uint32_t smem_find(const unsigned long long* tk, uint
 }
 
 __global__ void __launch_bounds__(256) part_count_kernel(const unsigned long long* __restrict__ rk, const uint32_t* __restrict__ rp, const uint32_t* __restrict__ off,
-                                                         uint32_t nparts, uint32_t threshold, uint32_t* __restrict__ out, uint32_t id_mul, uint32_t id_add,
-                                                         uint32_t* __restrict__ sv_pos, uint32_t* __restrict__ sv_cnt, DeviceStats* __restrict__ st,
-                                                         unsigned int* __restrict__ work) {
-    __shared__ unsigned long long tk[kPartSlots];
-    __shared__ uint32_t           tc[kPartSlots];
-    __shared__ uint32_t           tp[kPartSlots];
-    __shared__ uint64_t           scratch[8];
-    __shared__ uint32_t           warp_tot[8];
-    __shared__ uint32_t           s_part;
-    __shared__ unsigned long long s_base;
-    uint64_t found = 0, kept = 0, occ = 0, singles = 0;
+                                                         uint32_t nparts, uint32_t threshold, uint32_t* __restrict__ out, uint32_t id_base, uint32_t id_mul, uint32_t id_add,
+                                                         uint32_t* __restrict__ tmp_pos, uint32_t* __restrict__ tmp_cnt, uint32_t* __restrict__ kept_of, DeviceStats* __restrict__ st) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint64_t scratch[8];
+    const uint32_t      warp = threadIdx.x >> 5, lane = lane_id();
+    unsigned long long* tk = reinterpret_cast<unsigned long long*>(smem) + (size_t)warp * kWarpSlots;
+    uint32_t*           tc = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned long long*>(smem) + 8 * kWarpSlots) + (size_t)warp * kWarpSlots;
+    uint32_t found = 0, kept = 0, singles = 0;
+    uint64_t occ = 0;
     bool     full = false;
-    for (;;) {
-        __syncthreads();  // the previous partition's tables are done with
-        if (threadIdx.x == 0) s_part = atomicAdd(work, 1u);
-        __syncthreads();
-        const uint32_t q = s_part;
-        if (q >= nparts) break;
-        const uint32_t beg = __ldg(off + q), end = __ldg(off + q + 1), n = end - beg;
-        if (n == 0) continue;
+    const uint32_t nwarps = gridDim.x * 8, lt = (1u << lane) - 1;
+    uint32_t q = blockIdx.x * 8 + warp;
+    uint32_t beg = 0, end = 0;
+    if (q < nparts) {
+        beg = __ldg(off + q);
+        end = __ldg(off + q + 1);
+    }
+    for (; q < nparts; q += nwarps) {
+        const uint32_t n = end - beg, cbeg = beg, cend = end;
+        // the next partition's bounds are on their way while this one is counted
+        if (q + nwarps < nparts) {
+            beg = __ldg(off + q + nwarps);
+            end = __ldg(off + q + nwarps + 1);
+        }
+        if (n == 0) {
+            if (lane == 0) kept_of[q] = 0;
+            continue;
+        }
         uint32_t size = 64;
-        while (size < 2 * n && size < kPartSlots) size <<= 1;
+        while (size < 2 * n && size < kWarpSlots) size <<= 1;
         const uint32_t mask = size - 1;
-        for (uint32_t i = threadIdx.x; i < size; i += 256) {
+        if (n <= kHeld * 32) {
+            // ---- the usual case: every record stays in a register.  All loads are issued before the first table access (one memory latency per
+            // partition, not one per 32 records).  The record whose CAS claimed a slot stands for its key afterwards: the claimers enumerate
+            // the distinct keys, so the threshold and the compaction walk the records, not the table.
+            unsigned long long key[kHeld];
+            uint32_t           held_pos[kHeld], held_slot[kHeld], claims = 0;
+#pragma unroll
+            for (int k = 0; k < kHeld; ++k) {
+                const uint32_t i = cbeg + k * 32 + lane;
+                key[k]           = 0ull;
+                held_pos[k]      = 0;
+                if (i < cend) {
+                    key[k]      = __ldcs(rk + i);
+                    held_pos[k] = __ldcs(rp + i);
+                }
+            }
+            for (uint32_t i = lane; i < size; i += 32) {
+                tk[i] = 0ull;
+                tc[i] = 0u;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < kHeld; ++k) {
+                held_slot[k] = 0xFFFFFFFFu;
+                if (key[k] != 0ull) {
+                    bool claimed;
+                    held_slot[k] = smem_upsert(tk, tc, mask, key[k], claimed, full);
+                    if (claimed) claims |= 1u << k;
+                }
+            }
+            __syncwarp();
+            uint32_t run = cbeg;  // the survivors fit the partition's own range: kept <= distinct keys <= records
+#pragma unroll
+            for (int k = 0; k < kHeld; ++k) {
+                if (k * 32 < (int)n) {
+                    const bool     cl   = (claims >> k) & 1u;
+                    const uint32_t c    = cl ? tc[held_slot[k]] : 0u;
+                    const bool     keep = cl && c >= threshold;
+                    const uint32_t m    = __ballot_sync(0xffffffffu, keep);
+                    if (cl) {
+                        ++found;
+                        singles += c == 1;
+                        uint32_t id = 0;
+                        if (keep) {
+                            const uint32_t o = run + __popc(m & lt);
+                            tmp_pos[o]       = held_pos[k];
+                            tmp_cnt[o]       = c;
+                            id               = (id_base + o) * id_mul + id_add;
+                            occ += c;
+                            ++kept;
+                        }
+                        tc[held_slot[k]] = id;  // the slot now answers "which id", 0 = pruned
+                    }
+                    run += __popc(m);
+                }
+            }
+            if (lane == 0) kept_of[q] = run - cbeg;
+            __syncwarp();
+            if (run != cbeg) {
+#pragma unroll
+                for (int k = 0; k < kHeld; ++k) {
+                    if (held_slot[k] == 0xFFFFFFFFu) continue;
+                    const uint32_t id = tc[held_slot[k]];
+                    if (id) out[held_pos[k]] = id;
+                }
+            }
+            __syncwarp();  // the table is cleared for the next partition
+            continue;
+        }
+        // ---- a partition with more records than the registers hold (a frequent key landed here): records are read twice, the table is scanned
+        for (uint32_t i = lane; i < size; i += 32) {
             tk[i] = 0ull;
             tc[i] = 0u;
         }
-        __syncthreads();
-        // phase 1: count
-        uint32_t held_slot[kHeld], held_pos[kHeld];
+        __syncwarp();
+        for (uint32_t c0 = cbeg; c0 < cend; c0 += kHeld * 32) {  // loads in batches of eight, as above: one memory latency per 256 records
+            unsigned long long key[kHeld];
 #pragma unroll
-        for (int k = 0; k < kHeld; ++k) {
-            const uint32_t i = beg + k * 256 + threadIdx.x;
-            held_slot[k]     = 0xFFFFFFFFu;
-            held_pos[k]      = 0;
-            if (i < end) {
-                const unsigned long long key = __ldcs(rk + i);
-                held_pos[k]                  = __ldcs(rp + i);
-                held_slot[k]                 = smem_upsert(tk, tc, tp, mask, key, held_pos[k], full);
+            for (int k = 0; k < kHeld; ++k) {
+                const uint32_t i = c0 + k * 32 + lane;
+                key[k]           = i < cend ? __ldg(rk + i) : 0ull;
+            }
+#pragma unroll
+            for (int k = 0; k < kHeld; ++k) {
+                if (key[k] == 0ull) continue;
+                // a frequent key fills whole warps: one lane per distinct key of the warp does the table work for all of them
+                const uint32_t peers = __match_any_sync(__activemask(), key[k]);
+                if ((int)lane == __ffs(peers) - 1) {
+                    bool           claimed;
+                    const uint32_t sl = smem_upsert(tk, tc, mask, key[k], claimed, full);
+                    if (sl != 0xFFFFFFFFu && __popc(peers) > 1) atomicAdd(tc + sl, (uint32_t)__popc(peers) - 1);
+                }
             }
         }
-        for (uint32_t i = beg + kHeld * 256 + threadIdx.x; i < end; i += 256) smem_upsert(tk, tc, tp, mask, __ldg(rk + i), __ldg(rp + i), full);
-        __syncthreads();
-        // threshold + compaction: thread t owns slots t, t + 256, ...
+        __syncwarp();
         uint32_t nkeep = 0;
-        for (uint32_t sl = threadIdx.x; sl < size; sl += 256) {
+        for (uint32_t sl = lane; sl < size; sl += 32) {
             if (tk[sl] != 0ull) {
                 const uint32_t c = tc[sl];
                 ++found;
                 singles += c == 1;
                 if (c >= threshold) {
                     ++nkeep;
-                    ++kept;
                     occ += c;
                 }
             }
         }
-        uint32_t incl = warp_inclusive_scan(nkeep);
-        if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t tot = 0;
-            for (int w = 0; w < 8; ++w) {
-                const uint32_t c = warp_tot[w];
-                warp_tot[w]      = tot;
-                tot += c;
-            }
-            s_base = tot ? atomicAdd(&st->cursor, (unsigned long long)tot) : 0ull;
-        }
-        __syncthreads();
-        uint64_t o = s_base + warp_tot[threadIdx.x >> 5] + incl - nkeep;
-        for (uint32_t sl = threadIdx.x; sl < size; sl += 256) {
-            uint32_t id = 0;
+        kept += nkeep;
+        const uint32_t incl  = warp_inclusive_scan(nkeep);
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) kept_of[q] = total;
+        uint32_t o = cbeg + incl - nkeep;
+        for (uint32_t sl = lane; sl < size; sl += 32) {
+            uint32_t v = 0;
             if (tk[sl] != 0ull) {
                 const uint32_t c = tc[sl];
                 if (c >= threshold) {
-                    sv_pos[o] = tp[sl];
-                    sv_cnt[o] = c;
-                    id        = (uint32_t)o * id_mul + id_add;
+                    tmp_cnt[o] = c;
+                    v          = o + 1;  // where the survivor lives; its position is filled in by any of its records below
                     ++o;
                 }
             }
-            tc[sl] = id;  // the slot now answers "which id", 0 = pruned
+            tc[sl] = v;
         }
-        __syncthreads();
-        // phase 2: ids to the windows that stay
+        __syncwarp();
+        if (total) {
+            for (uint32_t c0 = cbeg; c0 < cend; c0 += kHeld * 32) {
+                unsigned long long key[kHeld];
+                uint32_t           pos[kHeld];
 #pragma unroll
-        for (int k = 0; k < kHeld; ++k) {
-            if (held_slot[k] == 0xFFFFFFFFu) continue;
-            const uint32_t id = tc[held_slot[k]];
-            if (id) out[held_pos[k]] = id;
-        }
-        for (uint32_t i = beg + kHeld * 256 + threadIdx.x; i < end; i += 256) {
-            const uint32_t sl = smem_find(tk, mask, __ldg(rk + i));
-            if (sl != 0xFFFFFFFFu) {
-                const uint32_t id = tc[sl];
-                if (id) out[__ldg(rp + i)] = id;
+                for (int k = 0; k < kHeld; ++k) {
+                    const uint32_t i = c0 + k * 32 + lane;
+                    key[k]           = i < cend ? __ldg(rk + i) : 0ull;
+                    pos[k]           = i < cend ? __ldg(rp + i) : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < kHeld; ++k) {
+                    if (key[k] == 0ull) continue;
+                    const uint32_t sl = smem_find(tk, mask, key[k]);
+                    if (sl != 0xFFFFFFFFu) {
+                        const uint32_t v = tc[sl];
+                        if (v) {
+                            tmp_pos[v - 1] = pos[k];  // every occurrence names the n-gram equally well: whichever store lands last stays
+                            out[pos[k]]    = (id_base + v - 1) * id_mul + id_add;
+                        }
+                    }
+                }
             }
         }
+        __syncwarp();
     }
-    found   = block_reduce_sum(found, scratch);
-    kept    = block_reduce_sum(kept, scratch);
-    occ     = block_reduce_sum(occ, scratch);
-    singles = block_reduce_sum(singles, scratch);
+    uint64_t f = block_reduce_sum(found, scratch);
+    uint64_t k = block_reduce_sum(kept, scratch);
+    uint64_t c = block_reduce_sum(occ, scratch);
+    uint64_t g = block_reduce_sum(singles, scratch);
     if (threadIdx.x == 0) {
-        if (found) atomicAdd(&st->found, (unsigned long long)found);
-        if (kept) atomicAdd(&st->kept, (unsigned long long)kept);
-        if (occ) atomicAdd(&st->kept_occ, (unsigned long long)occ);
-        if (singles) atomicAdd(&st->singletons, (unsigned long long)singles);
+        if (f) atomicAdd(&st->found, (unsigned long long)f);
+        if (k) atomicAdd(&st->kept, (unsigned long long)k);
+        if (c) atomicAdd(&st->kept_occ, (unsigned long long)c);
+        if (g) atomicAdd(&st->singletons, (unsigned long long)g);
     }
     if (full) atomicOr(&st->errflags, kErrTableFull);
+}
+
+// survivors of partition q: tmp[off[q] .. + kept_of[q]) -> sv[dst_off[q] ..); slot_index (indexed models): id - 1 -> survivor index + 1
+__global__ void __launch_bounds__(256) part_gather_kernel(const uint32_t* __restrict__ tmp_pos, const uint32_t* __restrict__ tmp_cnt, const uint32_t* __restrict__ off,
+                                                          const uint32_t* __restrict__ kept_of, const uint32_t* __restrict__ dst_off, uint32_t nparts, uint32_t* __restrict__ sv_pos,
+                                                          uint32_t* __restrict__ sv_cnt, uint32_t* __restrict__ slot_index, uint32_t id_base) {
+    const uint32_t lane = lane_id();
+    const uint32_t q    = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= nparts) return;
+    const uint32_t n = __ldg(kept_of + q), src = __ldg(off + q), dst = __ldg(dst_off + q);
+    for (uint32_t r = lane; r < n; r += 32) {
+        sv_pos[dst + r] = tmp_pos[src + r];
+        sv_cnt[dst + r] = tmp_cnt[src + r];
+        if (slot_index) slot_index[id_base + src + r] = dst + r + 1;
+    }
 }
 
 // ---- the positions whose id is non-zero, in corpus order inside 1024-position tiles (the next level's list mode) -------------------------
@@ -503,8 +710,8 @@ __global__ void __launch_bounds__(256) iota_plus1_kernel(uint32_t* __restrict__ 
     if (i < n) out[i] = (uint32_t)i + 1;
 }
 
-size_t split_smem(int tile, uint32_t nbins) {
-    return (size_t)tile * (8 + 4 + 2) + (size_t)nbins * 8;
+size_t split_smem(int tile, uint32_t nbins, int bin_arrays) {
+    return (size_t)tile * (8 + 4 + 2) + (size_t)nbins * 4 * bin_arrays;
 }
 
 template <class K>
@@ -517,7 +724,7 @@ void opt_in_smem(K kernel, size_t bytes) {
 
 PartPlan part_plan(uint64_t bound) {
     PartPlan pl;
-    uint64_t want = bound / 512 + 1;
+    uint64_t want = bound / 384 + 1;
     int      b    = 8;
     while ((1ull << b) < want && b < 22) ++b;
     pl.b1     = (b + 1) / 2;
@@ -526,65 +733,81 @@ PartPlan part_plan(uint64_t bound) {
     return pl;
 }
 
-int launch_part_hist(cudaStream_t s, const uint32_t* prev, const uint32_t* list, uint64_t nitems, uint32_t dense, uint32_t* dense_cnt, uint32_t* hist, const PartPlan& pl,
+int launch_part_hist(cudaStream_t s, const uint32_t* prev, const uint32_t* list, uint64_t nitems, uint32_t dense, uint32_t* dense_cnt, uint32_t* hist1, const PartPlan& pl,
                      DeviceStats* st, int sms) {
     if (!nitems) return 0;
-    const int      shift = 64 - pl.b1 - pl.b2;
-    const unsigned grid  = (unsigned)std::min<uint64_t>((nitems + 255) / 256, (uint64_t)sms * 32);
-    if (list) part_hist_kernel<true, false><<<grid, 256, 0, s>>>(prev, list, nitems, 0, nullptr, hist, shift, st);
-    else if (dense) part_hist_kernel<false, true><<<grid, 256, 0, s>>>(prev, nullptr, nitems, dense, dense_cnt, hist, shift, st);
-    else part_hist_kernel<false, false><<<grid, 256, 0, s>>>(prev, nullptr, nitems, 0, nullptr, hist, shift, st);
+    const uint32_t nbins  = 1u << pl.b1;
+    const int      shift1 = 64 - pl.b1;
+    const size_t   smem   = (size_t)nbins * 4 + (dense && !list ? kHotSide * kHotSide * 4 : 0);
+    const uint64_t per    = list ? 256 : 1024;
+    const unsigned grid   = (unsigned)std::min<uint64_t>((nitems + per - 1) / per, (uint64_t)sms * 8);
+    if (list) part_hist_kernel<true, false><<<grid, 256, smem, s>>>(prev, list, nitems, 0, nullptr, hist1, nbins, shift1, st);
+    else if (dense) part_hist_kernel<false, true><<<grid, 256, smem, s>>>(prev, nullptr, nitems, dense, dense_cnt, hist1, nbins, shift1, st);
+    else part_hist_kernel<false, false><<<grid, 256, smem, s>>>(prev, nullptr, nitems, 0, nullptr, hist1, nbins, shift1, st);
     return 1;
 }
 
-int launch_part_scan(cudaStream_t s, const uint32_t* hist, const PartPlan& pl, uint32_t* off, uint32_t* cursor2, uint32_t* cursor1, uint32_t* tstart) {
-    part_scan_kernel<<<1, 1024, 0, s>>>(hist, pl.nparts, pl.b2, off, cursor2, cursor1, tstart);
+int launch_part_bases(cudaStream_t s, const uint32_t* counts, uint32_t n, uint32_t* out, uint32_t* out2, const unsigned long long* base_ptr) {
+    part_bases_kernel<<<1, 1024, 0, s>>>(counts, n, out, out2, base_ptr);
     return 1;
 }
 
 int launch_part_split1(cudaStream_t s, const uint32_t* prev, const uint32_t* list, uint64_t nitems, uint32_t dense, const uint32_t* dense_id, uint32_t* cur, const PartPlan& pl,
-                       uint32_t* cursor1, void* rk, uint32_t* rp) {
+                       uint32_t* cursor1, uint32_t* hist2, void* rk, uint32_t* rp) {
     if (!nitems) return 0;
     const uint32_t nbins  = 1u << pl.b1;
     const int      shift1 = 64 - pl.b1;
-    const size_t   smem   = split_smem(kTile1, nbins);
+    const size_t   smem   = split_smem(kTile1, nbins, 2);
     const unsigned grid   = (unsigned)((nitems + kTile1 - 1) / kTile1);
     auto*          keys   = static_cast<unsigned long long*>(rk);
     if (list) {
         opt_in_smem(part_split1_kernel<true, false>, smem);
-        part_split1_kernel<true, false><<<grid, 256, smem, s>>>(prev, list, nitems, 0, nullptr, cur, shift1, nbins, cursor1, keys, rp);
+        part_split1_kernel<true, false><<<grid, 256, smem, s>>>(prev, list, nitems, 0, nullptr, cur, shift1, pl.b2, nbins, cursor1, hist2, keys, rp);
     } else if (dense) {
         opt_in_smem(part_split1_kernel<false, true>, smem);
-        part_split1_kernel<false, true><<<grid, 256, smem, s>>>(prev, nullptr, nitems, dense, dense_id, cur, shift1, nbins, cursor1, keys, rp);
+        part_split1_kernel<false, true><<<grid, 256, smem, s>>>(prev, nullptr, nitems, dense, dense_id, cur, shift1, pl.b2, nbins, cursor1, hist2, keys, rp);
     } else {
         opt_in_smem(part_split1_kernel<false, false>, smem);
-        part_split1_kernel<false, false><<<grid, 256, smem, s>>>(prev, nullptr, nitems, 0, nullptr, cur, shift1, nbins, cursor1, keys, rp);
+        part_split1_kernel<false, false><<<grid, 256, smem, s>>>(prev, nullptr, nitems, 0, nullptr, cur, shift1, pl.b2, nbins, cursor1, hist2, keys, rp);
     }
     return 1;
 }
 
-int launch_part_split2(cudaStream_t s, const void* rk_in, const uint32_t* rp_in, const uint32_t* off, const uint32_t* tstart, const PartPlan& pl, uint64_t max_records,
-                       uint32_t* cursor2, void* rk_out, uint32_t* rp_out) {
+int launch_part_scan(cudaStream_t s, const uint32_t* counts, const PartPlan& pl, uint32_t* group_tot, uint32_t* group_base, uint32_t* off, const unsigned long long* base_ptr) {
+    const uint32_t p1n = 1u << pl.b1;
+    part_totals_kernel<<<p1n, 256, 0, s>>>(counts, pl.b2, group_tot);
+    part_bases_kernel<<<1, 1024, 0, s>>>(group_tot, p1n, group_base, nullptr, base_ptr);
+    part_offsets_kernel<<<p1n, 256, 0, s>>>(counts, pl.b2, group_base, off);
+    return 3;
+}
+
+int launch_part_split2(cudaStream_t s, const void* rk_in, const uint32_t* rp_in, const uint32_t* off, const PartPlan& pl, void* rk_out, uint32_t* rp_out) {
     const uint32_t p1n    = 1u << pl.b1;
     const int      shift2 = 64 - pl.b1 - pl.b2;
-    const size_t   smem   = split_smem(kTile2, 1u << pl.b2);
-    const unsigned grid   = (unsigned)(max_records / kTile2 + p1n + 1);  // every b1-partition rounds its tile count up
+    const size_t   smem   = split_smem(kTile2, 1u << pl.b2, 3);
     opt_in_smem(part_split2_kernel, smem);
-    part_split2_kernel<<<grid, 256, smem, s>>>(static_cast<const unsigned long long*>(rk_in), rp_in, off, tstart, p1n, pl.b2, shift2, cursor2,
-                                                static_cast<unsigned long long*>(rk_out), rp_out);
+    part_split2_kernel<<<p1n, 512, smem, s>>>(static_cast<const unsigned long long*>(rk_in), rp_in, off, pl.b2, shift2, static_cast<unsigned long long*>(rk_out), rp_out);
     return 1;
 }
 
-int launch_part_count(cudaStream_t s, const void* rk, const uint32_t* rp, const uint32_t* off, const PartPlan& pl, uint32_t threshold, uint32_t* out, uint32_t id_mul,
-                      uint32_t id_add, uint32_t* sv_pos, uint32_t* sv_cnt, DeviceStats* st, unsigned int* work /* zeroed */, int sms) {
-    static int bps = 0;
-    if (!bps) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, part_count_kernel, 256, 0);
-        if (bps < 1) bps = 1;
-    }
-    const unsigned grid = (unsigned)std::min<uint64_t>(pl.nparts, (uint64_t)sms * bps);
-    part_count_kernel<<<grid, 256, 0, s>>>(static_cast<const unsigned long long*>(rk), rp, off, pl.nparts, threshold, out, id_mul, id_add, sv_pos, sv_cnt, st, work);
+int launch_part_count(cudaStream_t s, const void* rk, const uint32_t* rp, const uint32_t* off, const PartPlan& pl, uint32_t threshold, uint32_t* out, uint32_t id_base,
+                      uint32_t id_mul, uint32_t id_add, uint32_t* tmp_pos, uint32_t* tmp_cnt, uint32_t* kept_of, DeviceStats* st, int sms) {
+    const size_t smem = (size_t)8 * kWarpSlots * 12;
+    opt_in_smem(part_count_kernel, smem);
+    int bps = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, part_count_kernel, 256, smem);
+    if (bps < 1) bps = 1;
+    const unsigned grid = (unsigned)std::min<uint64_t>((pl.nparts + 7) / 8, (uint64_t)sms * bps);
+    part_count_kernel<<<grid, 256, smem, s>>>(static_cast<const unsigned long long*>(rk), rp, off, pl.nparts, threshold, out, id_base, id_mul, id_add, tmp_pos, tmp_cnt, kept_of, st);
     return 1;
+}
+
+int launch_part_gather(cudaStream_t s, const uint32_t* tmp_pos, const uint32_t* tmp_cnt, const uint32_t* off, const uint32_t* kept_of, const PartPlan& pl, uint32_t* group_tot,
+                       uint32_t* group_base, uint32_t* dst_off, const unsigned long long* first /* device: survivors already in the segment */, uint32_t* sv_pos, uint32_t* sv_cnt,
+                       uint32_t* slot_index, uint32_t id_base) {
+    launch_part_scan(s, kept_of, pl, group_tot, group_base, dst_off, first);
+    part_gather_kernel<<<(pl.nparts + 7) / 8, 256, 0, s>>>(tmp_pos, tmp_cnt, off, kept_of, dst_off, pl.nparts, sv_pos, sv_cnt, slot_index, id_base);
+    return 4;
 }
 
 int launch_compact_nonzero(cudaStream_t s, const uint32_t* cur, uint64_t npos, uint32_t* list_out, unsigned long long* cursor) {

@@ -197,7 +197,9 @@ int colibri_b200_model_counters(const colibri_b200_model* m, uint64_t out[8]);
 int colibri_b200_model_checksum(colibri_b200_model* m, uint64_t out[6]);
 int colibri_b200_model_level_counters(const colibri_b200_model* m, int n, double out[4]);
 /* same plus out[4]=items the level's kernels enumerated: every position (dense mode), or the length of the position list the previous
- * level left behind (list mode: only positions whose (n-1)-gram survived are visited); out[5..7] reserved (0) */
+ * level left behind (list mode: only positions whose (n-1)-gram survived are visited); out[5]=1 if the level ran on the partitioned path
+ * (shared-memory counting, out[1] = partitions, out[3] = n-grams that occur once) else 0 (HBM table, out[3] = windows the occurrence filter held
+ * back); out[6]=1 if the occurrence filter ran; out[7] reserved (0) */
 int colibri_b200_model_level_info(const colibri_b200_model* m, int n, double out[8]);
 
 /* ---- multi-GPU: one process per GPU drives these per-rank phases and moves the buffers between ranks itself

@@ -12,6 +12,62 @@ using namespace colibri;
 
 thread_local char colibri::g_err[1024] = "";
 colibri::Pool colibri::g_pool[16];
+colibri::EventCache colibri::g_events;
+thread_local colibri::HostTrace colibri::g_trace;
+
+namespace {
+// Per-call CUDA objects that are expensive to make are kept: streams (a create/destroy pair costs tens of microseconds and the destroy
+// waits for the stream), and one small pinned block per device for the scalars the export stream reads back (cudaHostAlloc / cudaFreeHost
+// cost up to a millisecond each and the free synchronises the whole device).
+struct StreamCache {
+    std::mutex                mu;
+    std::vector<cudaStream_t> free_streams[16];
+    int get(int dev, cudaStream_t* out) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto& v = free_streams[dev & 15];
+            if (!v.empty()) {
+                *out = v.back();
+                v.pop_back();
+                return 0;
+            }
+        }
+        CUDA_TRY(cudaStreamCreateWithFlags(out, cudaStreamNonBlocking));
+        return 0;
+    }
+    void put(int dev, cudaStream_t s) {  // the stream must be idle
+        if (!s) return;
+        std::lock_guard<std::mutex> g(mu);
+        free_streams[dev & 15].push_back(s);
+    }
+} g_streams;
+struct PinnedScalars {
+    std::mutex                       mu;
+    std::vector<unsigned long long*> free_blocks;
+    unsigned long long* get() {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (!free_blocks.empty()) {
+                auto* p = free_blocks.back();
+                free_blocks.pop_back();
+                return p;
+            }
+        }
+        unsigned long long* p = nullptr;
+        if (cudaHostAlloc((void**)&p, 1024 * sizeof(unsigned long long), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return p;
+    }
+    void put(unsigned long long* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu);
+        free_blocks.push_back(p);
+    }
+} g_pinned;
+}  // namespace
+
 
 extern "C" const char* colibri_b200_last_error(void) {
     return g_err;
@@ -47,14 +103,18 @@ static int corpus_alloc(colibri_b200_corpus* c, int device, size_t nbytes) {
     if (ndev <= 0) return set_err(COLIBRI_E_CUDA, "no CUDA device available: the B200 path has no CPU fallback");
     if (device < 0 || device >= ndev) return set_err(COLIBRI_E_INVALID, "device %d out of range (have %d)", device, ndev);
     CUDA_TRY(cudaSetDevice(device));
-    // the tables are probed one 32-byte sector at a time at random addresses: ask L2 not to fetch the neighbouring sector too
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, getenv("COLIBRI_B200_L2_FETCH") ? (size_t)atoi(getenv("COLIBRI_B200_L2_FETCH")) : 32);
-    cudaGetLastError();
+    // the tables are probed one 32-byte sector at a time at random addresses: ask L2 not to fetch the neighbouring sector too (once per device)
+    static bool limit_set[16] = {false};
+    if (!limit_set[device & 15]) {
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, getenv("COLIBRI_B200_L2_FETCH") ? (size_t)atoi(getenv("COLIBRI_B200_L2_FETCH")) : 32);
+        cudaGetLastError();
+        limit_set[device & 15] = true;
+    }
     c->device = device;
     c->nbytes = nbytes;
     size_t total = kHalo + c->padded(nbytes + 2) + kTokTile;
     TRY(c->buf.alloc(device, total));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    TRY(g_streams.get(device, &c->stream));
     CUDA_TRY(cudaMemsetAsync(c->buf.p, 0, kHalo, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->buf.p + kHalo + nbytes, 0x80, total - kHalo - nbytes, c->stream));
     return 0;
@@ -70,33 +130,70 @@ static int corpus_finish(colibri_b200_corpus* c) {
     return 0;
 }
 
-extern "C" int colibri_b200_corpus_stage(const uint8_t* host_body, size_t nbytes, int device, colibri_b200_corpus** out) {
-    if (!out) return set_err(COLIBRI_E_INVALID, "out is NULL");
+// Staging without a host synchronise: whether the last sentence is terminated is read from the caller's bytes, the copy is left running on
+// the corpus stream and ev_h2d1 tells other streams when the body is in HBM.  host_body must stay valid until that event has passed
+// (colibri_b200_train / _train_export synchronise before they return; the public colibri_b200_corpus_stage waits right away).
+static int corpus_stage_async(const uint8_t* host_body, size_t nbytes, int device, colibri_b200_corpus** out) {
     *out = nullptr;
     if (!host_body && nbytes) return set_err(COLIBRI_E_INVALID, "host_body is NULL");
     auto* c = new colibri_b200_corpus();
     int   rc = corpus_alloc(c, device, nbytes);
-    if (rc == 0 && nbytes) {
-        cudaEvent_t a, b;
-        cudaEventCreate(&a);
-        cudaEventCreate(&b);
-        cudaEventRecord(a, c->stream);
-        cudaError_t e = cudaMemcpyAsync(c->body(), host_body, nbytes, cudaMemcpyHostToDevice, c->stream);
-        cudaEventRecord(b, c->stream);
-        if (e != cudaSuccess) rc = set_err(COLIBRI_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
-        if (rc == 0) rc = corpus_finish(c);
-        float ms = 0;
-        if (rc == 0 && cudaEventElapsedTime(&ms, a, b) == cudaSuccess) c->h2d_ms = ms;
-        cudaEventDestroy(a);
-        cudaEventDestroy(b);
-    } else if (rc == 0) {
-        rc = corpus_finish(c);
+    if (rc == 0) {
+        c->ev_h2d0 = g_events.get(device);
+        c->ev_h2d1 = g_events.get(device);
+        if (!c->ev_h2d0 || !c->ev_h2d1) rc = set_err(COLIBRI_E_CUDA, "cudaEventCreate failed");
+    }
+    if (rc == 0) {
+        cudaEventRecord(c->ev_h2d0, c->stream);
+        // a large body goes in chunks with an event behind each, so that the tokeniser can start on chunk k while chunk k + 1 is on the bus
+        size_t chunk = Tuning::env_u64("COLIBRI_B200_H2D_CHUNK", 16u << 20) / kTokTile * kTokTile;
+        if (chunk == 0 || nbytes < 4 * chunk) chunk = 0;
+        if (chunk) {
+            c->chunk_bytes = chunk;
+            for (size_t o0 = 0; o0 < nbytes && rc == 0; o0 += chunk) {
+                cudaError_t e = cudaMemcpyAsync(c->body() + o0, host_body + o0, std::min(chunk, nbytes - o0), cudaMemcpyHostToDevice, c->stream);
+                if (e != cudaSuccess) rc = set_err(COLIBRI_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+                cudaEvent_t ev = g_events.get(device);
+                if (!ev) rc = set_err(COLIBRI_E_CUDA, "cudaEventCreate failed");
+                else {
+                    cudaEventRecord(ev, c->stream);
+                    c->chunk_ev.push_back(ev);
+                }
+            }
+        } else if (nbytes) {
+            cudaError_t e = cudaMemcpyAsync(c->body(), host_body, nbytes, cudaMemcpyHostToDevice, c->stream);
+            if (e != cudaSuccess) rc = set_err(COLIBRI_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+        }
+        cudaEventRecord(c->ev_h2d1, c->stream);
+        c->h2d_pending = true;
+        // the last two body bytes decide whether the final sentence is terminated (delimiter = 0x00 not preceded by a continuation byte)
+        c->last_byte       = nbytes ? host_body[nbytes - 1] : 0;
+        c->ends_with_delim = nbytes >= 1 && host_body[nbytes - 1] == 0 && (nbytes == 1 || host_body[nbytes - 2] < 128);
     }
     if (rc) {
         colibri_b200_corpus_free(c);
         return rc;
     }
     *out = c;
+    return 0;
+}
+static void corpus_resolve_h2d(colibri_b200_corpus* c) {  // after a synchronise that covers ev_h2d1
+    if (!c->h2d_pending) return;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev_h2d0, c->ev_h2d1) == cudaSuccess) c->h2d_ms = ms;
+    else cudaGetLastError();
+    c->h2d_pending = false;
+}
+extern "C" int colibri_b200_corpus_stage(const uint8_t* host_body, size_t nbytes, int device, colibri_b200_corpus** out) {
+    if (!out) return set_err(COLIBRI_E_INVALID, "out is NULL");
+    TRY(corpus_stage_async(host_body, nbytes, device, out));
+    cudaError_t e = cudaStreamSynchronize((*out)->stream);
+    if (e != cudaSuccess) {
+        colibri_b200_corpus_free(*out);
+        *out = nullptr;
+        return set_err(COLIBRI_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+    }
+    corpus_resolve_h2d(*out);
     return 0;
 }
 extern "C" int colibri_b200_corpus_from_device(const void* dev_body, size_t nbytes, int device, colibri_b200_corpus** out) {
@@ -124,8 +221,11 @@ extern "C" void colibri_b200_corpus_free(colibri_b200_corpus* c) {
     cudaSetDevice(c->device);
     if (c->stream) {
         cudaStreamSynchronize(c->stream);
-        cudaStreamDestroy(c->stream);
+        g_streams.put(c->device, c->stream);
     }
+    g_events.put(c->device, c->ev_h2d0);
+    g_events.put(c->device, c->ev_h2d1);
+    for (auto ev : c->chunk_ev) g_events.put(c->device, ev);
     delete c;
 }
 extern "C" int colibri_b200_corpus_download(const colibri_b200_corpus* c, uint8_t* host, size_t cap) {
@@ -286,14 +386,15 @@ struct ExportSink {
     std::vector<Pending> pending, inflight;
     unsigned long long*  h_scalars = nullptr;  // pinned, one per segment
     int                  nscalars = 0;
+    int                  dev = 0;
     ~ExportSink() {
         if (xs) {
             cudaStreamSynchronize(xs);
-            cudaStreamDestroy(xs);
+            g_streams.put(dev, xs);
         }
-        for (auto& p : pending) if (p.ready) cudaEventDestroy(p.ready);
-        for (auto& p : inflight) if (p.ready) cudaEventDestroy(p.ready);
-        if (h_scalars) cudaFreeHost(h_scalars);
+        for (auto& p : pending) g_events.put(dev, p.ready);
+        for (auto& p : inflight) g_events.put(dev, p.ready);
+        g_pinned.put(h_scalars);
     }
 };
 
@@ -307,6 +408,18 @@ struct Trainer {
     uint64_t                   launches = 0;
     DevBuf<DeviceStats>        d_stats;
     DeviceStats                h_stats;
+    unsigned long long*        h_pinned = nullptr;  // mapped pinned block: the statistics arrive here by kernel stores, not through the copy engine
+    ~Trainer() { g_pinned.put(h_pinned); }
+    int fetch_stats() {  // d_stats -> h_stats, synchronising the stream
+        if (!h_pinned) {
+            h_pinned = g_pinned.get();
+            if (!h_pinned) return set_err(COLIBRI_E_CUDA, "no pinned memory for the statistics block");
+        }
+        launches += launch_copy_words_to_host(s, d_stats.p, h_pinned, (uint32_t)sizeof(DeviceStats));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        memcpy(&h_stats, h_pinned, sizeof(DeviceStats));
+        return 0;
+    }
     std::vector<Segment>       segs;
     uint64_t                   slots_init = 0, ngram_upserts = 0, skip_upserts = 0, filtered_windows = 0;
     Tuning                     tune = Tuning::from_env();
@@ -333,10 +446,13 @@ struct Trainer {
     }
     int read_stats() {
         CUDA_TRY(cudaGetLastError());  // a kernel of this phase that failed to launch (bad configuration, missing opt-in) must not read as "nothing found"
-        CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
+        TRY(fetch_stats());
         if (h_stats.errflags & kErrTableFull) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow");
-        if (sink) TRY(flush_sink(false));  // every host sync of the level loop is a chance to hand finished segments to the copy stream
+        if (sink && !sink->pending.empty()) {  // every host sync of the level loop is a chance to hand finished segments to the copy stream
+            g_trace.mark("(");
+            TRY(flush_sink(false));
+            g_trace.mark("flush)");
+        }
         return 0;
     }
     // forward index (indexed models)
@@ -556,10 +672,11 @@ int Trainer::emit_segment(Segment& sg) {
     launches += launch_exclusive_scan_u32_u64(s, p.lens.p, p.off.p, sg.count, p.tmp.p);
     launches += launch_export_write(s, tok_for_sink, sg.pos.p, p.nm.p, p.off.p, sg.count, p.keys.p);
     p.h_kb = sink->h_scalars + sink->nscalars++;
-    CUDA_TRY(cudaMemcpyAsync(p.h_kb, p.off.p + sg.count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    launches += launch_copy_words_to_host(s, p.off.p + sg.count, p.h_kb, (uint32_t)sizeof(unsigned long long));  // (not the copy engine: it is busy with the previous level)
     // the counts travel from the segment's own array; it stays alive (segs) until the end of the call
     p.cnt = std::move(sg.cnt);
-    CUDA_TRY(cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming));
+    p.ready = g_events.get(dev);
+    if (!p.ready) return set_err(COLIBRI_E_CUDA, "cudaEventCreate failed");
     CUDA_TRY(cudaEventRecord(p.ready, s));
     sink->pending.push_back(std::move(p));
     return 0;
@@ -645,8 +762,7 @@ int Trainer::level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint6
                                    slot_index ? slot_index->p : nullptr, (uint32_t)dense_cells);
     timer.end(hc);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    TRY(fetch_stats());
     if (h_stats.errflags & kErrTableFull) {
         CUDA_TRY(cudaMemsetAsync(&d_stats.p->errflags, 0, sizeof(unsigned int), s));
         overflow = true;
@@ -662,6 +778,10 @@ int Trainer::level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint6
 int Trainer::tokenise(DevBuf<uint32_t>& tok, uint64_t& npos, uint32_t& nclasses) {
     // ---- the sentence source quirk (see include/colibri_b200.h: streamed)
     if (c->nbytes == 0) return set_err(COLIBRI_E_FORMAT, "Attempting to read pattern from file, but file is empty?");  // src/pattern.cpp:520-523
+    // a corpus staged asynchronously is still on its way: chunk by chunk (below) or as a whole
+    const bool piped = c->h2d_pending && c->chunk_bytes && !c->chunk_ev.empty();
+    if (piped) CUDA_TRY(cudaStreamWaitEvent(s, c->chunk_ev[0], 0));  // (also orders the tail below after the padding memset of the corpus stream)
+    else if (c->ev_h2d1) CUDA_TRY(cudaStreamWaitEvent(s, c->ev_h2d1, 0));
     size_t staged = c->nbytes;
     {
         uint8_t tail[16];
@@ -683,20 +803,50 @@ int Trainer::tokenise(DevBuf<uint32_t>& tok, uint64_t& npos, uint32_t& nclasses)
     int h = timer.begin(COLIBRI_T_TOKENISE);
     DevBuf<uint32_t> blk;
     TRY(blk.alloc(dev, nblocks + 1));
-    launches += launch_tokenise_count(s, c->body(), staged, blk.p, nblocks);
-    launches += launch_scan_block_counts(s, blk.p, nblocks, &d_stats.p->cursor);
-    TRY(read_stats());
-    const uint64_t npos_real = h_stats.cursor;  // tokens + delimiters
-    if (npos_real >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "corpus has %llu positions; the device index is 32 bit", (unsigned long long)npos_real);
-    npos = npos_real + 1;  // one virtual delimiter closes the last sentence
-    // spare room behind the tokens: the class pairs of the surviving dense bigrams (kernels.cu: prune_dense_kernel)
-    tok_ext_cells = (tune.dense_dim && npos >= tune.dense_min) ? (uint64_t)tune.dense_dim * tune.dense_dim : 0;
-    if (npos + 8 + 2 * tok_ext_cells >= 0xFFFFFFF0ull) tok_ext_cells = 0;
-    TRY(tok.alloc(dev, npos + 8 + 2 * tok_ext_cells));
-    CUDA_TRY(cudaMemsetAsync(tok.p + npos_real, 0, 8 * sizeof(uint32_t), s));
-    launches += launch_tokenise_write(s, c->body(), staged, blk.p, nblocks, tok.p, d_stats.p);
-    timer.end(h);
-    TRY(read_stats());
+    uint64_t npos_real = 0;
+    if (piped) {
+        // The tokeniser follows the copy: a token belongs to the tile in which it ENDS and is decoded backwards, so the tiles of chunk k need
+        // nothing of chunk k + 1.  The token array is sized by its upper bound (a token has at least one byte) because the count is not known yet.
+        const uint64_t pos_bound = staged;
+        tok_ext_cells = (tune.dense_dim && pos_bound >= tune.dense_min) ? (uint64_t)tune.dense_dim * tune.dense_dim : 0;
+        if (pos_bound + 9 + 2 * tok_ext_cells >= 0xFFFFFFF0ull) {
+            tok_ext_cells = 0;
+            if (pos_bound + 9 >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "corpus of %llu bytes; the device index is 32 bit", (unsigned long long)pos_bound);
+        }
+        TRY(tok.alloc(dev, pos_bound + 9 + 2 * tok_ext_cells));
+        const uint32_t tiles_per_chunk = (uint32_t)(c->chunk_bytes / kTokTile);
+        for (size_t k = 0; k < c->chunk_ev.size(); ++k) {
+            const uint32_t t0 = (uint32_t)k * tiles_per_chunk;
+            const uint32_t t1 = k + 1 == c->chunk_ev.size() ? nblocks : std::min<uint32_t>(nblocks, t0 + tiles_per_chunk);  // the last chunk takes the tail and the padding along
+            if (t0 >= t1) break;
+            if (k) CUDA_TRY(cudaStreamWaitEvent(s, c->chunk_ev[k], 0));
+            const uint8_t* base = c->body() + (uint64_t)t0 * kTokTile;
+            launches += launch_tokenise_count(s, base, 0, blk.p + t0, t1 - t0);
+            launches += launch_scan_block_counts(s, blk.p + t0, t1 - t0, &d_stats.p->cursor, true);
+            launches += launch_tokenise_write(s, base, 0, blk.p + t0, t1 - t0, tok.p, d_stats.p);
+        }
+        timer.end(h);
+        TRY(read_stats());
+        npos_real = h_stats.cursor;  // tokens + delimiters
+        npos      = npos_real + 1;   // one virtual delimiter closes the last sentence
+        if (!(tune.dense_dim && npos >= tune.dense_min)) tok_ext_cells = 0;
+        CUDA_TRY(cudaMemsetAsync(tok.p + npos_real, 0, 8 * sizeof(uint32_t), s));
+    } else {
+        launches += launch_tokenise_count(s, c->body(), staged, blk.p, nblocks);
+        launches += launch_scan_block_counts(s, blk.p, nblocks, &d_stats.p->cursor);
+        TRY(read_stats());
+        npos_real = h_stats.cursor;  // tokens + delimiters
+        if (npos_real >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "corpus has %llu positions; the device index is 32 bit", (unsigned long long)npos_real);
+        npos = npos_real + 1;  // one virtual delimiter closes the last sentence
+        // spare room behind the tokens: the class pairs of the surviving dense bigrams (kernels.cu: prune_dense_kernel)
+        tok_ext_cells = (tune.dense_dim && npos >= tune.dense_min) ? (uint64_t)tune.dense_dim * tune.dense_dim : 0;
+        if (npos + 8 + 2 * tok_ext_cells >= 0xFFFFFFF0ull) tok_ext_cells = 0;
+        TRY(tok.alloc(dev, npos + 8 + 2 * tok_ext_cells));
+        CUDA_TRY(cudaMemsetAsync(tok.p + npos_real, 0, 8 * sizeof(uint32_t), s));
+        launches += launch_tokenise_write(s, c->body(), staged, blk.p, nblocks, tok.p, d_stats.p);
+        timer.end(h);
+        TRY(read_stats());
+    }
     if (h_stats.errflags & kErrTokenTooLong) return set_err(COLIBRI_E_FORMAT, "corpus contains a class wider than 32 bits / 5 bytes");
     if (h_stats.errflags & kErrNonCanonical) return set_err(COLIBRI_E_FORMAT, "corpus contains a non-canonical class encoding (multi-byte token ending in 0x00)");
     if (h_stats.errflags & kErrReservedClass)
@@ -711,13 +861,15 @@ int Trainer::tokenise(DevBuf<uint32_t>& tok, uint64_t& npos, uint32_t& nclasses)
 int Trainer::run() {
     CUDA_TRY(cudaSetDevice(dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));  // (cudaGetDeviceProperties costs milliseconds per call)
-    timer.s = s;
+    timer.s   = s;
+    timer.dev = dev;
     int h_total = timer.begin(COLIBRI_T_TOTAL);
     DevBuf<uint32_t> tok;
     uint64_t         npos = 0;
     uint32_t         nclasses = 0;
     int              h = -1;
     TRY(tokenise(tok, npos, nclasses));
+    g_trace.mark("tokenise");
     tok_for_sink  = tok.p;
     sink_maxclass = nclasses ? nclasses - 1 : 0;
     // a level can be handed to the caller as soon as it is pruned unless a later rule may still drop it (MINLENGTH clean-up, :1221-1229, :1337-1341)
@@ -769,6 +921,7 @@ int Trainer::run() {
     }
     timer.end(h);
     m->counters[6] = m->totaltokens;
+    g_trace.mark("unigrams");
     const DeviceStats uni = h_stats;  // found / kept / kept occurrences of the unigram level
     // tokens of the classes the dense square covers (sizes the occurrence filter of level 2)
     uint64_t dense_tokens = 0;
@@ -906,8 +1059,7 @@ int Trainer::run() {
             launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms, use_filter ? filter.p : nullptr, nbuckets, hot, dense, list, nlist, dense_cnt);
             timer.end(hc);
             CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaMemcpyAsync(&h_stats, d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
+            TRY(fetch_stats());
             if (h_stats.errflags & kErrTableFull) {  // the estimate was too small: clear the flag and go again with more slots
                 if (cap >= cap_max) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow at level %d", n);
                 CUDA_TRY(cudaMemsetAsync(&d_stats.p->errflags, 0, sizeof(unsigned int), s));
@@ -1008,9 +1160,11 @@ int Trainer::run() {
         passes.push_back({(uint64_t)n, found, foundskip, (found - kept) + (foundskip - keptskip)});
         segs.push_back(std::move(sg));
         if (stream_levels) {
+            g_trace.mark("(");
             int he = timer.begin(COLIBRI_T_EXPORT);
             TRY(emit_segment(segs.back()));
             timer.end(he);
+            g_trace.mark("emit)");
         }
         if (sk.skip) {
             segs.push_back(std::move(sk));
@@ -1044,6 +1198,10 @@ int Trainer::run() {
             }
         }
         list_valid = next_list;
+        {
+            static const char* const kLevelNames[] = {"L0", "L1", "L2", "L3", "L4", "L5", "L6", "L7", "L8", "L9+"};
+            g_trace.mark(kLevelNames[std::min(n, 9)]);
+        }
         if (!keep_all_ids) ids[n - 1].reset();  // ping-pong: only the newest level is needed
         prev_kept = kept;
         prev_occ  = occ;
@@ -1114,8 +1272,11 @@ int Trainer::run() {
             for (auto& sg : segs) TRY(emit_segment(sg));
         timer.end(h);
         timer.end(h_total);
+        g_trace.mark("emit-last");
         CUDA_TRY(cudaStreamSynchronize(s));
+        g_trace.mark("sync-main");
         TRY(flush_sink(true));
+        g_trace.mark("sync-copy");
         m->npatterns = sink->npat;
         m->keybytes  = sink->nbytes;
     } else {
@@ -1147,7 +1308,8 @@ int Trainer::run() {
 int Trainer::run_constrained(colibri_b200_model* cm, bool inplace, int phase, uint32_t* ext_counts, uint64_t ext_tokens) {
     CUDA_TRY(cudaSetDevice(dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    timer.s = s;
+    timer.s   = s;
+    timer.dev = dev;
     int h_total = timer.begin(COLIBRI_T_TOTAL);
     indexed = o.model_type == COLIBRI_INDEXEDPATTERNMODEL;
     if (phase != 0 && (indexed || ext_counts == nullptr)) return set_err(COLIBRI_E_UNSUPPORTED, "sharded constrained training is for unindexed models");
@@ -1556,8 +1718,10 @@ extern "C" int colibri_b200_train(const uint8_t* host_body, size_t nbytes, const
     colibri_b200_options o = *opt;
     TRY(check_options(o));
     colibri_b200_corpus* c = nullptr;
-    TRY(colibri_b200_corpus_stage(host_body, nbytes, o.device, &c));
+    TRY(corpus_stage_async(host_body, nbytes, o.device, &c));  // the copy runs while the host sets the training up
     int rc = colibri_b200_train_corpus(c, opt, out);
+    cudaStreamSynchronize(c->stream);  // host_body must not be in use after this call returns, whatever happened
+    corpus_resolve_h2d(c);
     if (rc == 0) (*out)->ms[COLIBRI_T_H2D] = c->h2d_ms;
     colibri_b200_corpus_free(c);
     return rc;
@@ -1571,23 +1735,32 @@ extern "C" int colibri_b200_train_export(const uint8_t* host_body, size_t nbytes
     colibri_b200_options o = *opt;
     TRY(check_options(o));
     if (o.model_type != COLIBRI_UNINDEXEDPATTERNMODEL) return set_err(COLIBRI_E_UNSUPPORTED, "colibri_b200_train_export streams unindexed models; use colibri_b200_train + colibri_b200_model_export for indexed ones");
+    g_trace.begin();
     colibri_b200_corpus* c = nullptr;
-    TRY(colibri_b200_corpus_stage(host_body, nbytes, o.device, &c));
+    TRY(corpus_stage_async(host_body, nbytes, o.device, &c));
+    g_trace.mark("stage");
     colibri_b200_model* m = nullptr;
     int rc = new_model(o.device, o.model_type, &m);
     if (rc == 0) {
         ExportSink sink;
+        sink.dev = c->device;
         sink.keys = keys; sink.len16 = key_len; sink.counts = counts; sink.keys_cap = keys_cap; sink.pat_cap = patterns_cap;
-        cudaError_t e = cudaStreamCreateWithFlags(&sink.xs, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaHostAlloc((void**)&sink.h_scalars, 1024 * sizeof(unsigned long long), cudaHostAllocDefault);
-        if (e != cudaSuccess) rc = set_err(COLIBRI_E_CUDA, "streamed export set-up: %s", cudaGetErrorString(e));
+        rc = g_streams.get(c->device, &sink.xs);
+        if (rc == 0) {
+            sink.h_scalars = g_pinned.get();
+            if (!sink.h_scalars) rc = set_err(COLIBRI_E_CUDA, "streamed export set-up: no pinned memory");
+        }
+        g_trace.mark("setup");
         if (rc == 0) {
             Trainer tr;
             tr.c = c; tr.o = o; tr.m = m; tr.s = m->stream; tr.dev = c->device;
             tr.sink = &sink;
             rc = tr.run();
             if (rc) cudaStreamSynchronize(m->stream);
+            g_trace.mark("run");
         }
+        cudaStreamSynchronize(c->stream);  // host_body is the caller's again
+        corpus_resolve_h2d(c);
         if (rc == 0) {
             summary->npatterns = sink.npat; summary->keybytes = sink.nbytes;
             summary->totaltokens = m->totaltokens; summary->totaltypes = m->totaltypes;
@@ -1604,8 +1777,11 @@ extern "C" int colibri_b200_train_export(const uint8_t* host_body, size_t nbytes
                 rc = set_err(COLIBRI_E_CAPACITY, "output buffers too small: %llu patterns / %llu key bytes needed", (unsigned long long)sink.npat, (unsigned long long)sink.nbytes);
         }
     }
+    g_trace.mark("teardown-sink");
     if (m) colibri_b200_model_free(m);
     colibri_b200_corpus_free(c);
+    g_trace.mark("free");
+    g_trace.dump("train_export");
     return rc;
 }
 

@@ -140,13 +140,68 @@ struct DevBuf {
     }
 };
 
+// Timing events are reused across calls: cudaEventCreate / Destroy cost microseconds each and a train call takes dozens of spans.
+struct EventCache {
+    std::mutex               mu;
+    std::vector<cudaEvent_t> free_events[16];
+    cudaEvent_t get(int dev) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto& v = free_events[dev & 15];
+            if (!v.empty()) {
+                cudaEvent_t e = v.back();
+                v.pop_back();
+                return e;
+            }
+        }
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        return e;
+    }
+    void put(int dev, cudaEvent_t e) {
+        if (!e) return;
+        std::lock_guard<std::mutex> g(mu);
+        free_events[dev & 15].push_back(e);
+    }
+};
+extern EventCache g_events;
+
+// Host-side trace of one ABI call (COLIBRI_B200_TRACE=1): wall-clock marks, printed to stderr when the call returns.  The aux "tracing"
+// subsystem of this path: it answers where the time between the device phases goes (allocation, synchronisation, copies).
+struct HostTrace {
+    bool                                        on = false;
+    std::vector<std::pair<const char*, double>> marks;
+    static double now_ms() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+    }
+    void begin() {
+        on = getenv("COLIBRI_B200_TRACE") != nullptr;
+        marks.clear();
+        mark("begin");
+    }
+    void mark(const char* what) {
+        if (on) marks.emplace_back(what, now_ms());
+    }
+    void dump(const char* call) {
+        if (!on || marks.empty()) return;
+        fprintf(stderr, "[colibri_b200 trace] %s:", call);
+        for (size_t i = 1; i < marks.size(); ++i) fprintf(stderr, " %s +%.3f", marks[i].first, marks[i].second - marks[i - 1].second);
+        fprintf(stderr, " | total %.3f ms\n", marks.back().second - marks.front().second);
+        marks.clear();
+    }
+};
+extern thread_local HostTrace g_trace;
+
 struct PhaseTimer {  // CUDA events on the library's stream, resolved after the final synchronise
     struct Span { int phase; cudaEvent_t a, b; int level; };
     std::vector<Span> spans;
     cudaStream_t      s = nullptr;
+    int               dev = 0;
     int begin(int phase, int level = 0) {
-        Span sp{phase, nullptr, nullptr, level};
-        if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return -1;
+        Span sp{phase, g_events.get(dev), g_events.get(dev), level};
+        if (!sp.a || !sp.b) return -1;
         cudaEventRecord(sp.a, s);
         spans.push_back(sp);
         return (int)spans.size() - 1;
@@ -154,8 +209,8 @@ struct PhaseTimer {  // CUDA events on the library's stream, resolved after the 
     void end(int h) { if (h >= 0) cudaEventRecord(spans[h].b, s); }
     ~PhaseTimer() {
         for (auto& sp : spans) {
-            cudaEventDestroy(sp.a);
-            cudaEventDestroy(sp.b);
+            g_events.put(dev, sp.a);
+            g_events.put(dev, sp.b);
         }
     }
     void resolve(double ms[COLIBRI_T_NPHASES], std::map<int, double>* level_ms) {
@@ -165,8 +220,8 @@ struct PhaseTimer {  // CUDA events on the library's stream, resolved after the 
                 ms[sp.phase] += t;
                 if (level_ms && sp.phase == COLIBRI_T_COUNT) (*level_ms)[sp.level] += t;
             }
-            cudaEventDestroy(sp.a);
-            cudaEventDestroy(sp.b);
+            g_events.put(dev, sp.a);
+            g_events.put(dev, sp.b);
         }
         spans.clear();
     }
@@ -251,6 +306,10 @@ struct colibri_b200_corpus {
     uint8_t          last_byte = 0;
     cudaStream_t     stream = nullptr;
     double           h2d_ms = 0;
+    cudaEvent_t      ev_h2d0 = nullptr, ev_h2d1 = nullptr;  // around the staging copy; ev_h2d1 doubles as "the body is in HBM" for other streams
+    bool             h2d_pending = false;                   // staged asynchronously: h2d_ms is resolved after the caller's final synchronise
+    size_t           chunk_bytes = 0;                       // > 0: the body was copied in chunks of this many bytes (a multiple of the tokeniser's tile),
+    std::vector<cudaEvent_t> chunk_ev;                      //      chunk_ev[k] fires when chunk k is in HBM: the tokeniser follows the copy chunk by chunk
     uint8_t*         body() const { return buf.p + kHalo; }
     size_t           padded(size_t staged) const { return (staged + kTokTile - 1) / kTokTile * kTokTile; }
 };

@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(256) tokenise_count_kernel(const uint8_t* __re
 }
 
 // exclusive scan of the per-tile counts, in place, by one block (at most a few hundred thousand entries)
-__global__ void __launch_bounds__(1024) scan_block_counts_kernel(uint32_t* __restrict__ counts, uint32_t n, unsigned long long* __restrict__ total) {
+// accumulate: the scan starts at *total (the tiles of one chunk of a corpus that is still being copied; *total carries over to the next chunk)
+__global__ void __launch_bounds__(1024) scan_block_counts_kernel(uint32_t* __restrict__ counts, uint32_t n, unsigned long long* __restrict__ total, bool accumulate) {
     __shared__ uint64_t part[1024];
     uint32_t            chunk = (n + blockDim.x - 1) / blockDim.x;
     uint32_t            lo = threadIdx.x * chunk, hi = min(n, lo + chunk);
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(1024) scan_block_counts_kernel(uint32_t* __res
     part[threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint64_t acc = 0;
+        uint64_t acc = accumulate ? *total : 0;
         for (uint32_t i = 0; i < blockDim.x; ++i) {
             uint64_t t = part[i];
             part[i]    = acc;
@@ -127,8 +128,8 @@ int launch_tokenise_count(cudaStream_t s, const uint8_t* corpus, uint64_t, uint3
     tokenise_count_kernel<<<nblocks, 256, 0, s>>>(corpus, blk_counts);
     return 1;
 }
-int launch_scan_block_counts(cudaStream_t s, uint32_t* blk_counts, uint32_t nblocks, unsigned long long* total) {
-    scan_block_counts_kernel<<<1, 1024, 0, s>>>(blk_counts, nblocks, total);
+int launch_scan_block_counts(cudaStream_t s, uint32_t* blk_counts, uint32_t nblocks, unsigned long long* total, bool accumulate) {
+    scan_block_counts_kernel<<<1, 1024, 0, s>>>(blk_counts, nblocks, total, accumulate);
     return 1;
 }
 int launch_tokenise_write(cudaStream_t s, const uint8_t* corpus, uint64_t, const uint32_t* blk_offsets, uint32_t nblocks, uint32_t* tok, DeviceStats* st) {
@@ -904,6 +905,17 @@ int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, 
 // K5: export.  A survivor is (position | class, count, n | mask << 8); its key bytes are re-encoded from the token
 // array in the reference's pattern format: varint per token, gap tokens collapsed to the single byte 0x03
 // (Pattern(const PatternPointer&), src/pattern.cpp:873-909).
+// A few words device -> mapped pinned host memory by plain stores over PCIe.  A cudaMemcpyAsync of the same bytes would queue on the D2H copy
+// engine behind whatever the export stream is copying (a finished level: tens of MB) and stall the stream that is waiting for a statistics block.
+__global__ void copy_words_to_host_kernel(const uint32_t* __restrict__ src, volatile uint32_t* __restrict__ dst, uint32_t nwords) {
+    for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+int launch_copy_words_to_host(cudaStream_t s, const void* src, void* dst_mapped, uint32_t nbytes) {
+    copy_words_to_host_kernel<<<1, 32, 0, s>>>(static_cast<const uint32_t*>(src), static_cast<volatile uint32_t*>(dst_mapped), (nbytes + 3) / 4);
+    return 1;
+}
+
 __global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t* __restrict__ dst, uint64_t n, uint32_t value) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = value;

@@ -59,7 +59,7 @@ constexpr uint32_t kSkipRoundShift = 24;           // mask-field bits 24..30: nu
 // ---- K0: corpus bytes -> class ids (0 = sentence delimiter)
 constexpr int kTokTile = 4096;  // bytes per block
 int launch_tokenise_count(cudaStream_t s, const uint8_t* corpus, uint64_t nbytes, uint32_t* blk_counts, uint32_t nblocks);
-int launch_scan_block_counts(cudaStream_t s, uint32_t* blk_counts, uint32_t nblocks, unsigned long long* total);
+int launch_scan_block_counts(cudaStream_t s, uint32_t* blk_counts, uint32_t nblocks, unsigned long long* total, bool accumulate = false /* start at *total */);
 int launch_tokenise_write(cudaStream_t s, const uint8_t* corpus, uint64_t nbytes, const uint32_t* blk_offsets, uint32_t nblocks, uint32_t* tok, DeviceStats* st);
 
 // ---- K1: unigram histogram, unigram prune, level-1 ids
@@ -136,6 +136,8 @@ int launch_prune_skipgrams(cudaStream_t s, const SkipSlot* table, uint64_t cap, 
 // ---- export: survivors -> pattern bytes
 // sv_nm[i] = n | mask << 8 ; for n == 1 sv_pos holds the class id itself
 int launch_fill_u32(cudaStream_t s, uint32_t* dst, uint64_t n, uint32_t value);
+// nbytes (multiple of 4, 4-byte aligned) from device memory to MAPPED pinned host memory with a one-warp kernel instead of the copy engine
+int launch_copy_words_to_host(cudaStream_t s, const void* src, void* dst_mapped, uint32_t nbytes);
 int launch_sum_u32(cudaStream_t s, const uint32_t* v, uint64_t n, unsigned long long* total /* += sum */);
 int launch_pack_nm(cudaStream_t s, uint32_t* nm /*in: gap masks, out: n | mask << 8*/, uint64_t count, uint32_t n);
 int launch_export_lengths(cudaStream_t s, const uint32_t* tok, const uint32_t* sv_pos, const uint32_t* sv_nm, uint64_t n, uint32_t* lens, uint16_t* lens16);

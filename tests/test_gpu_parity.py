@@ -401,3 +401,29 @@ def test_streamed_train_export_equals_train_then_export(golden, path, monkeypatc
     with pytest.raises(cb().ColibriError) as ei:
         cb().train_export(corpus_body(golden, "hamlet"), MINTOKENS=2, MAXLENGTH=3, model_type=20, streamed=0, QUIET=1)
     assert ei.value.code == 2
+
+
+@pytest.mark.parametrize("chunk", [4096, 8192, 65536])
+def test_tokeniser_following_a_chunked_copy_matches_oracle(golden, chunk, monkeypatch):
+    """Host corpora above four chunks are copied in chunks and tokenised chunk by chunk behind the copy (engine.cu: Trainer::tokenise, `piped`);
+    forced here with tiny chunks: tokens that straddle a chunk border, a corpus without its final delimiter (streamed and preloaded), the
+    dense square's spare room behind an over-sized token array."""
+    monkeypatch.setenv("COLIBRI_B200_H2D_CHUNK", str(chunk))
+    runs = [("republic", dict(mintokens=2, maxlength=5), {}), ("zipf300k_phr", dict(mintokens=2, maxlength=4), {}),
+            ("zipf2m", dict(mintokens=2, maxlength=3), {"COLIBRI_B200_DENSE_MIN": "0", "COLIBRI_B200_DENSE": "64", "COLIBRI_B200_PART_MIN": "0"}),
+            ("noeos", dict(mintokens=1, maxlength=3, streamed=1), {}), ("noeos", dict(mintokens=1, maxlength=3, streamed=0), {})]
+    for name, okw, env in runs:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        body = corpus_body(golden, name)
+        if name == "noeos":
+            body = body * 4000  # long enough to be chunked; still without the final delimiter
+        want = oracle.train(body, **okw)
+        m = cb().train(body, QUIET=1, MINTOKENS=okw["mintokens"], MAXLENGTH=okw["maxlength"], streamed=okw.get("streamed", 1))
+        got = to_flat(m)
+        assert (got.tokens, got.types, len(got)) == (want.tokens, want.types, len(want)), (name, chunk)
+        assert got.passes == want.passes and got.same_patterns(want), (name, chunk)
+        keys, lens, counts, sm = cb().train_export(body, QUIET=1, MINTOKENS=okw["mintokens"], MAXLENGTH=okw["maxlength"], streamed=okw.get("streamed", 1))
+        assert len(lens) == len(want) and sm["passes"] == want.passes, (name, chunk)
+        for k in env:
+            monkeypatch.delenv(k)

@@ -134,6 +134,7 @@ def library():
     L.colibri_b200_shard_skip_owner.argtypes = [C.c_void_p, C.c_void_p, _u64p, _u64p, _u64p]
     L.colibri_b200_shard_skip_owner_survivors.argtypes = [C.c_void_p, C.c_void_p]
     L.colibri_b200_shard_skip_finish.argtypes = [C.c_void_p, C.c_void_p, _u64p]
+    L.colibri_b200_shard_set_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.colibri_b200_shard_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.colibri_b200_shard_set_peers.argtypes = [C.c_void_p, _u64p, _u64p, _u64p, _u64p, C.c_uint64, C.c_uint64]
     L.colibri_b200_shard_p2p_split.argtypes = [C.c_void_p, C.c_int, _u64p]

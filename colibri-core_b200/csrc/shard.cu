@@ -77,7 +77,12 @@ extern "C" int colibri_b200_shard_begin(colibri_b200_corpus* corpus, const colib
         const uint64_t npos_real = sh->h_stats.cursor;
         if (npos_real >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "shard has %llu positions; the device index is 32 bit", (unsigned long long)npos_real);
         sh->npos = npos_real + 1;
-        TRY(sh->tok.alloc(sh->dev, sh->npos + 8));
+        {   // spare room behind the tokens for the class pairs of dense survivors (shard_set_dense; 32 MB at the default side)
+            const Tuning tune = Tuning::from_env();
+            sh->tok_ext_cells = (uint64_t)tune.dense_dim * tune.dense_dim;
+            if (sh->npos + 8 + 2 * sh->tok_ext_cells >= 0xFFFFFFF0ull) sh->tok_ext_cells = 0;
+        }
+        TRY(sh->tok.alloc(sh->dev, sh->npos + 8 + 2 * sh->tok_ext_cells));
         CUDA_TRY(cudaMemsetAsync(sh->tok.p + npos_real, 0, 8 * sizeof(uint32_t), s));
         sh->launches += launch_tokenise_write(s, corpus->body(), staged, blk.p, nblocks, sh->tok.p, sh->d_stats.p);
         TRY(shard_read_stats(sh));
@@ -160,6 +165,24 @@ extern "C" int colibri_b200_shard_unigram_finish(colibri_b200_shard* sh, const v
     return 0;
 }
 
+// Dense pairs of level 2.  dev_square: the caller's zeroed u32[dim * dim]; level_split_count / p2p_split count this rank's dense windows
+// into it, the CALLER sums the squares of all ranks (one all-reduce) before level_owner / p2p_owner, and every rank then reads the same verdicts
+// from it.  All ranks must make the same call (same dim) or none: the ids of level 2 depend on it.
+extern "C" int colibri_b200_shard_set_dense(colibri_b200_shard* sh, void* dev_square, uint32_t dim) {
+    if (!sh) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    if (sh->level != 1) return set_err(COLIBRI_E_INVALID, "shard_set_dense comes before level 2");
+    if (dim == 0 || !dev_square) {
+        sh->dense     = 0;
+        sh->dense_cnt = nullptr;
+        return 0;
+    }
+    if ((uint64_t)dim * dim > sh->tok_ext_cells) return set_err(COLIBRI_E_INVALID, "dense side %u: the shard keeps room for %llu cells (COLIBRI_B200_DENSE at shard_begin)", dim, (unsigned long long)sh->tok_ext_cells);
+    if (sh->p2p && sh->slot_cap * sh->world >= 0x80000000ull) return set_err(COLIBRI_E_CAPACITY, "receive slots of %llu x %u: the record index has 31 bits beside the dense square", (unsigned long long)sh->slot_cap, sh->world);
+    sh->dense     = dim;
+    sh->dense_cnt = static_cast<uint32_t*>(dev_square);
+    return 0;
+}
+
 // count the valid windows of level n per owner rank.  send_counts[world]; *windows = their sum
 extern "C" int colibri_b200_shard_level_split_count(colibri_b200_shard* sh, int n, uint64_t* send_counts, uint64_t* windows) {
     if (!sh || !send_counts || !windows) return set_err(COLIBRI_E_INVALID, "NULL argument");
@@ -172,7 +195,7 @@ extern "C" int colibri_b200_shard_level_split_count(colibri_b200_shard* sh, int 
     if (sh->split_hist.n < nh) TRY(sh->split_hist.alloc(sh->dev, nh));
     if (sh->split_off.n < nh + 1) TRY(sh->split_off.alloc(sh->dev, nh + 1));
     if (sh->scan_tmp.n < nh / 2048 + 4) TRY(sh->scan_tmp.alloc(sh->dev, nh / 2048 + 4));
-    sh->launches += launch_split_count(s, sh->prev.p, sh->npos, sh->world, sh->split_hist.p);
+    sh->launches += launch_split_count(s, sh->prev.p, sh->npos, sh->world, sh->split_hist.p, shard_dense_now(sh), sh->dense_cnt);
     sh->launches += launch_exclusive_scan_u32_u64(s, sh->split_hist.p, sh->split_off.p, nh, sh->scan_tmp.p);
     for (uint32_t d = 0; d <= sh->world; ++d)
         CUDA_TRY(cudaMemcpyAsync(&sh->send_base[d], sh->split_off.p + (uint64_t)d * nblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -190,7 +213,8 @@ extern "C" int colibri_b200_shard_level_split_write(colibri_b200_shard* sh, void
     PhaseClock clk(sh, 3);
     if (sh->pos_of_rec.n < sh->nsent + 1) TRY(sh->pos_of_rec.alloc(sh->dev, sh->nsent + 1));
     if (sh->rec_of_pos.n < sh->npos + 8) TRY(sh->rec_of_pos.alloc(sh->dev, sh->npos + 8));
-    sh->launches += launch_split_write(sh->s, sh->prev.p, sh->npos, sh->world, sh->split_off.p, dev_send_keys, sh->pos_of_rec.p, sh->rec_of_pos.p);
+    if (shard_dense_now(sh) && sh->nsent >= 0x80000000ull) return set_err(COLIBRI_E_CAPACITY, "%llu windows to ship; the record index has 31 bits beside the dense square", (unsigned long long)sh->nsent);
+    sh->launches += launch_split_write(sh->s, sh->prev.p, sh->npos, sh->world, sh->split_off.p, dev_send_keys, sh->pos_of_rec.p, sh->rec_of_pos.p, nullptr, 0, 0, shard_dense_now(sh));
     CUDA_TRY(cudaStreamSynchronize(sh->s));
     return 0;
 }
@@ -213,6 +237,7 @@ extern "C" int colibri_b200_shard_level_owner(colibri_b200_shard* sh, const void
     sh->nrecv = nrecv;
     if (nrecv && (!dev_recv_keys || !dev_reply)) return set_err(COLIBRI_E_INVALID, "NULL buffer");
     if (nrecv >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner received %llu windows; the receive index is 32 bit", (unsigned long long)nrecv);
+    TRY(shard_dense_owner(sh));  // (the caller has summed the dense squares by now)
     if (sh->d_aux.n < 260) TRY(sh->d_aux.alloc(sh->dev, 260));
     CUDA_TRY(cudaMemsetAsync(sh->d_aux.p, 0, 260 * sizeof(unsigned long long), s));
     CUDA_TRY(cudaMemcpyAsync(sh->d_aux.p, src_base, (sh->world + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
@@ -233,7 +258,7 @@ extern "C" int colibri_b200_shard_level_owner(colibri_b200_shard* sh, const void
     const uint64_t cap_max = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);  // a table this large cannot fill up
     uint64_t singles = 0;
     for (;;) {
-        if (cap * sh->world >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner table of %llu slots x %u ranks exceeds the 32-bit id space", (unsigned long long)cap, sh->world);
+        if (cap * sh->world + shard_id_off(sh) >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner table of %llu slots x %u ranks exceeds the 32-bit id space", (unsigned long long)cap, sh->world);
         if (sh->owner_table.n < cap) TRY(sh->owner_table.alloc(sh->dev, cap));
         CUDA_TRY(cudaMemsetAsync(sh->owner_table.p, 0, cap * sizeof(NgramSlot), s));
         TRY(shard_zero_stats(sh));
@@ -255,11 +280,11 @@ extern "C" int colibri_b200_shard_level_owner(colibri_b200_shard* sh, const void
     if (sh->bitmap.n < cap / 32 + 8) TRY(sh->bitmap.alloc(sh->dev, cap / 32 + 8));
     TRY(shard_zero_stats(sh));
     sh->launches += launch_prune_ngrams(s, sh->owner_table.p, cap, t, sh->sv_idx.p, sh->sv_cnt.p, sh->bitmap.p, sh->d_stats.p, sh->sms);
-    sh->launches += launch_owner_reply(s, (uint32_t*)dev_reply, nrecv, sh->bitmap.p, sh->world, sh->rank);
+    sh->launches += launch_owner_reply(s, (uint32_t*)dev_reply, nrecv, sh->bitmap.p, sh->world, sh->rank, nullptr, 0, nullptr, shard_id_off(sh));
     TRY(shard_read_stats(sh));
-    stats[0]  = sh->h_stats.found + singles;  // a filtered window is a distinct n-gram with global count 1: found, and pruned
-    stats[1]  = sh->h_stats.kept;
-    stats[2]  = sh->h_stats.kept_occ;
+    stats[0]  = sh->h_stats.found + singles + sh->dense_stats[0];  // a filtered window is a distinct n-gram with global count 1: found, and pruned
+    stats[1]  = sh->h_stats.kept + sh->dense_stats[1];
+    stats[2]  = sh->h_stats.kept_occ + sh->dense_stats[2];
     sh->nsurv = sh->h_stats.kept;
     // how many survivor records go back to each source
     sh->launches += launch_owner_survivor_counts(s, sh->sv_idx.p, sh->nsurv, sh->world, sh->d_aux.p, sh->d_aux.p + 195, sh->sms);
@@ -298,24 +323,29 @@ extern "C" int colibri_b200_shard_level_finish(colibri_b200_shard* sh, const voi
     const int n = sh->level + 1;
     TRY(shard_zero_stats(sh));
     CUDA_TRY(cudaMemsetAsync(sh->cur.p + sh->npos, 0, 8 * sizeof(uint32_t), s));
-    sh->launches += launch_sender_relabel(s, sh->rec_of_pos.p, (const uint32_t*)dev_reply_back, sh->npos, sh->cur.p, sh->d_stats.p, sh->sms);
+    sh->launches += launch_sender_relabel(s, sh->rec_of_pos.p, (const uint32_t*)dev_reply_back, sh->npos, sh->cur.p, sh->d_stats.p, sh->sms, shard_dense_now(sh) ? sh->dense_cnt : nullptr, sh->t);
     uint64_t total = 0;
     for (uint32_t g = 0; g < sh->world; ++g) total += surv_counts[g];
     Segment sg;
     sg.n = n;
-    if (total) {
-        if (!dev_surv) return set_err(COLIBRI_E_INVALID, "NULL survivor buffer");
-        TRY(sg.pos.alloc(sh->dev, total));
-        TRY(sg.cnt.alloc(sh->dev, total));
+    const uint64_t nd = shard_dense_now(sh) ? sh->dense_nsurv : 0;  // this rank's share of the dense square's survivors goes into the same segment
+    if (total + nd) {
+        if (total && !dev_surv) return set_err(COLIBRI_E_INVALID, "NULL survivor buffer");
+        TRY(sg.pos.alloc(sh->dev, total + nd));
+        TRY(sg.cnt.alloc(sh->dev, total + nd));
         uint64_t off = 0;
         for (uint32_t g = 0; g < sh->world; ++g) {
             sh->launches += launch_sender_survivors(s, (const uint8_t*)dev_surv + off * 8, surv_counts[g], sh->pos_of_rec.p, sh->send_base[g], sg.pos.p + off, sg.cnt.p + off);
             off += surv_counts[g];
         }
+        if (nd) {
+            CUDA_TRY(cudaMemcpyAsync(sg.pos.p + total, sh->dense_sv_pos.p, nd * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(sg.cnt.p + total, sh->dense_sv_cnt.p, nd * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        }
     }
     TRY(shard_read_stats(sh));
-    sg.count = total;
-    if (total) sh->segs.push_back(std::move(sg));
+    sg.count = total + nd;
+    if (total + nd) sh->segs.push_back(std::move(sg));
     sh->prev_valid = sh->h_stats.kept_occ;
     if (local_valid) *local_valid = sh->prev_valid;
     std::swap(sh->prev, sh->cur);

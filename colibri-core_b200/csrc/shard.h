@@ -40,6 +40,12 @@ struct colibri_b200_shard {
     DevBuf<uint32_t>     sk_pos_of_rec, sk_sv_idx, sk_sv_cnt, sk_sv_mask;
     int                  sk_nmasks = 0;
     uint64_t             sk_send_base[65] = {0}, sk_nsent = 0, sk_nsurv = 0;
+    // dense pairs of level 2 (shard_set_dense): the caller's zeroed square, summed over the ranks by the caller between split and owner
+    uint32_t             dense = 0;
+    uint32_t*            dense_cnt = nullptr;
+    uint64_t             tok_ext_cells = 0;  // room behind the tokens for the class pairs of this rank's dense survivors
+    DevBuf<uint32_t>     dense_sv_pos, dense_sv_cnt;
+    uint64_t             dense_stats[3] = {0, 0, 0}, dense_nsurv = 0;
     int                  level = 1;
     uint32_t             t = 2;
     std::vector<Segment> segs;
@@ -68,6 +74,31 @@ inline int shard_read_stats(colibri_b200_shard* sh) {
     if (sh->h_stats.errflags & kErrTableFull) return set_err(COLIBRI_E_CAPACITY, "device hash table overflow");
     return 0;
 }
+// level 2 with a dense square: this rank's share of the (already summed) square -> statistics + survivors, kept until the level's finish
+inline int shard_dense_owner(colibri_b200_shard* sh) {
+    sh->dense_stats[0] = sh->dense_stats[1] = sh->dense_stats[2] = 0;
+    sh->dense_nsurv = 0;
+    if (!sh->dense || sh->level != 1) return 0;
+    const uint64_t mine = ((uint64_t)sh->dense * sh->dense + sh->world - 1) / sh->world;
+    if (sh->dense_sv_pos.n < mine + 1) TRY(sh->dense_sv_pos.alloc(sh->dev, mine + 1));
+    if (sh->dense_sv_cnt.n < mine + 1) TRY(sh->dense_sv_cnt.alloc(sh->dev, mine + 1));
+    TRY(shard_zero_stats(sh));
+    sh->launches += launch_dense_share(sh->s, sh->dense_cnt, sh->dense, sh->world, sh->rank, sh->t, sh->dense_sv_pos.p, sh->dense_sv_cnt.p, sh->tok.p + sh->npos + 8,
+                                       (uint32_t)(sh->npos + 8), sh->d_stats.p, sh->sms);
+    TRY(shard_read_stats(sh));
+    sh->dense_stats[0] = sh->h_stats.found;
+    sh->dense_stats[1] = sh->h_stats.kept;
+    sh->dense_stats[2] = sh->h_stats.kept_occ;
+    sh->dense_nsurv    = sh->h_stats.kept;
+    return 0;
+}
+inline uint32_t shard_dense_now(const colibri_b200_shard* sh) {  // the dense side of the level being built (level + 1)
+    return sh->level == 1 ? sh->dense : 0u;
+}
+inline uint32_t shard_id_off(const colibri_b200_shard* sh) {
+    return sh->level == 1 ? sh->dense * sh->dense : 0u;
+}
+
 struct PhaseClock {  // accumulates device time of one ABI call into shard->device_ms / phase_ms[phase]
     colibri_b200_shard* sh;
     int                 phase;

@@ -35,29 +35,53 @@ __device__ __forceinline__ uint32_t owner_of_key(unsigned long long key, uint32_
 
 constexpr int      kSplitTile = 4096;  // positions per block: 8 warps x 512, each warp walks its slice in order
 constexpr uint32_t kNoRec     = 0xFFFFFFFFu;
+constexpr uint32_t kDenseRec  = 0x80000000u;  // rec_of_pos: the window is a pair of frequent classes, low bits = its cell of the dense square
+constexpr uint32_t kDenseDest = 255u;
+constexpr uint32_t kHotSide   = 64;           // the pairs of the 64 most frequent classes are counted in shared memory first
 
-__device__ __forceinline__ uint32_t window_dest(const uint32_t* __restrict__ prev, uint64_t p, uint64_t npos, uint32_t world, unsigned long long& key) {
+// Dense pairs (level 2, as on one GPU -- kernels.cu): a window of two classes below `dense` is never shipped.  Every rank counts such pairs
+// in its own dense square, the squares are summed by one all-reduce, and every rank derives the same verdict from the global square:
+// id = cell + 1 if the global count reaches the threshold, else 0.  The ids of the hashed n-grams start above dense^2.
+__device__ __forceinline__ uint32_t window_dest(const uint32_t* __restrict__ prev, uint64_t p, uint64_t npos, uint32_t world, unsigned long long& key, uint32_t dense = 0) {
     if (p >= npos) return 256u;
     uint32_t a = prev[p], b = prev[p + 1];
     if (a == 0 || b == 0) return 256u;
+    if (a < dense && b < dense) {
+        key = (unsigned long long)a * dense + b;
+        return kDenseDest;
+    }
     key = ((unsigned long long)a << 32) | b;
     return owner_of_key(key, world);
 }
 
 // pass 1: per block, windows per destination (destination-major so that one exclusive scan yields every block's bases)
-__global__ void __launch_bounds__(256) split_count_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t world, uint32_t nblocks, uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(256) split_count_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t world, uint32_t nblocks, uint32_t* __restrict__ hist,
+                                                          uint32_t dense, uint32_t* __restrict__ dense_cnt) {
     __shared__ uint32_t h[64];
+    __shared__ uint32_t hot[kHotSide * kHotSide];
     if (threadIdx.x < 64) h[threadIdx.x] = 0;
+    if (dense)
+        for (uint32_t i = threadIdx.x; i < kHotSide * kHotSide; i += 256) hot[i] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * kSplitTile;
 #pragma unroll 4
     for (int k = 0; k < kSplitTile / 256; ++k) {
         unsigned long long key;
-        uint32_t           d = window_dest(prev, base + (uint64_t)k * 256 + threadIdx.x, npos, world, key);
+        uint32_t           d = window_dest(prev, base + (uint64_t)k * 256 + threadIdx.x, npos, world, key, dense);
         if (d < 64) atomicAdd(&h[d], 1u);
+        else if (d == kDenseDest) {
+            const uint32_t cell = (uint32_t)key, a = cell / dense, b = cell % dense;
+            if (a < kHotSide && b < kHotSide) atomicAdd(&hot[a * kHotSide + b], 1u);
+            else atomicAdd(dense_cnt + cell, 1u);
+        }
     }
     __syncthreads();
     if (threadIdx.x < world) hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+    if (dense)
+        for (uint32_t i = threadIdx.x; i < kHotSide * kHotSide; i += 256) {
+            const uint32_t c = hot[i], a = i / kHotSide, b = i % kHotSide;
+            if (c && a < dense && b < dense) atomicAdd(dense_cnt + a * dense + b, c);
+        }
 }
 
 // pass 2: stable scatter.  send_keys is laid out [dest 0 | dest 1 | ...]; positions stay ascending inside a group.
@@ -67,7 +91,7 @@ __global__ void __launch_bounds__(256) split_count_kernel(const uint32_t* __rest
 // threads: 256-byte warp stores instead of 8-byte ones scattered over G streams (NVLink packets like them long).
 __global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t world, uint32_t nblocks, const uint64_t* __restrict__ hist_off,
                                                           unsigned long long* __restrict__ send_keys, uint32_t* __restrict__ pos_of_rec, uint32_t* __restrict__ rec_of_pos,
-                                                          unsigned long long* const* __restrict__ peer_keys, uint32_t my_rank, uint64_t slot_cap) {
+                                                          unsigned long long* const* __restrict__ peer_keys, uint32_t my_rank, uint64_t slot_cap, uint32_t dense) {
     __shared__ uint32_t cnt[8][65];
     __shared__ uint32_t dpre[66];                       // exclusive prefix of this block's per-destination totals
     __shared__ unsigned long long stage[kSplitTile];    // keys grouped by destination
@@ -77,7 +101,7 @@ __global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __rest
     const uint64_t wbase = (uint64_t)blockIdx.x * kSplitTile + (uint64_t)warp * (kSplitTile / 8);
     for (int it = 0; it < kSplitTile / 8 / 32; ++it) {
         unsigned long long key;
-        uint32_t           d = window_dest(prev, wbase + (uint64_t)it * 32 + lane, npos, world, key);
+        uint32_t           d = window_dest(prev, wbase + (uint64_t)it * 32 + lane, npos, world, key, dense);
         if (d > 64) d = 64;
         uint32_t peers = __match_any_sync(0xffffffffu, d);
         if ((int)lane == __ffs(peers) - 1) cnt[warp][d] += __popc(peers);
@@ -107,8 +131,8 @@ __global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __rest
     for (int it = 0; it < kSplitTile / 8 / 32; ++it) {
         const uint64_t     p = wbase + (uint64_t)it * 32 + lane;
         unsigned long long key = 0;
-        uint32_t           d = window_dest(prev, p, npos, world, key);
-        const bool         act = d < 64;
+        uint32_t           d = window_dest(prev, p, npos, world, key, dense);
+        const bool         act = d < 64, is_dense = d == kDenseDest;
         if (d > 64) d = 64;
         uint32_t peers = __match_any_sync(0xffffffffu, d);
         uint32_t base  = cnt[warp][d];
@@ -125,7 +149,7 @@ __global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __rest
             else
                 rec_of_pos[p] = (uint32_t)dst;
         } else if (p < npos) {
-            rec_of_pos[p] = kNoRec;
+            rec_of_pos[p] = is_dense ? (kDenseRec | (uint32_t)key) : kNoRec;
         }
     }
     __syncthreads();
@@ -286,20 +310,21 @@ __global__ void __launch_bounds__(256) stream_count_kernel(const unsigned long l
 
 // P2P mode (peer_reply != NULL): the global id is stored straight into the sender's reply slot for this owner over NVLink
 __global__ void __launch_bounds__(256) owner_reply_kernel(uint32_t* __restrict__ rid, uint64_t n, const uint32_t* __restrict__ bitmap, uint32_t world, uint32_t rank,
-                                                          uint32_t* const* __restrict__ peer_reply, uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts) {
+                                                          uint32_t* const* __restrict__ peer_reply, uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts,
+                                                          uint32_t id_off) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (peer_reply != nullptr) {
         uint64_t src = i / slot_cap, k = i - src * slot_cap;
         if (k >= __ldg(slot_counts + src)) return;
         uint32_t s   = rid[i];
-        uint32_t gid = (s != 0 && ((__ldg(bitmap + ((s - 1) >> 5)) >> ((s - 1) & 31)) & 1u)) ? (s - 1) * world + rank + 1 : 0u;
+        uint32_t gid = (s != 0 && ((__ldg(bitmap + ((s - 1) >> 5)) >> ((s - 1) & 31)) & 1u)) ? id_off + (s - 1) * world + rank + 1 : 0u;
         peer_reply[src][(uint64_t)rank * slot_cap + k] = gid;
         return;
     }
     uint32_t s = rid[i];
     if (s == 0) return;
-    rid[i] = ((__ldg(bitmap + ((s - 1) >> 5)) >> ((s - 1) & 31)) & 1u) ? (s - 1) * world + rank + 1 : 0u;
+    rid[i] = ((__ldg(bitmap + ((s - 1) >> 5)) >> ((s - 1) & 31)) & 1u) ? id_off + (s - 1) * world + rank + 1 : 0u;
 }
 
 // P2P survivors: survivor (receive index i, count) -> record (i % slot_cap, count) in the source's survivor slot for this owner;
@@ -411,18 +436,56 @@ __global__ void __launch_bounds__(256) owner_survivor_counts_kernel(const uint32
 // ---- sender side --------------------------------------------------------------------------------------------------------
 // id[p] = reply[rec_of_pos[p]]: inside every destination group the records are in corpus order, so this reads G ascending streams
 __global__ void __launch_bounds__(256) sender_relabel_kernel(const uint32_t* __restrict__ rec_of_pos, const uint32_t* __restrict__ reply, uint64_t npos, uint32_t* __restrict__ cur,
-                                                             DeviceStats* __restrict__ st) {
+                                                             DeviceStats* __restrict__ st, const uint32_t* __restrict__ dense_global, uint32_t threshold) {
     __shared__ uint64_t scratch[8];
     uint32_t valid = 0;
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t j  = __ldcs(rec_of_pos + p);
-        uint32_t id = j == kNoRec ? 0u : __ldg(reply + j);
+        uint32_t id;
+        if (j == kNoRec) id = 0u;
+        else if (j & kDenseRec) id = __ldg(dense_global + (j & ~kDenseRec)) >= threshold ? (j & ~kDenseRec) + 1u : 0u;  // the same verdict on every rank
+        else id = __ldg(reply + j);
         __stcs(cur + p, id);
         valid += id != 0;
     }
     uint64_t v = block_reduce_sum(valid, scratch);
     if (threadIdx.x == 0 && v) atomicAdd(&st->kept_occ, (unsigned long long)v);
 }
+// prune(MINTOKENS, 2) over this rank's share of the GLOBAL dense square (cells = rank mod world): statistics, and the survivors as
+// (position of the class pair in the spare room behind the tokens, global count) -- the rank exports them like any other bigram.
+__global__ void __launch_bounds__(256) dense_share_kernel(const uint32_t* __restrict__ dense_global, uint32_t dense, uint32_t world, uint32_t rank, uint32_t threshold,
+                                                          uint32_t* __restrict__ sv_pos, uint32_t* __restrict__ sv_cnt, uint32_t* __restrict__ tok_ext, uint32_t ext_pos0,
+                                                          DeviceStats* __restrict__ st) {
+    __shared__ uint64_t scratch[8];
+    const uint64_t cells = (uint64_t)dense * dense;
+    uint64_t found = 0, kept = 0, occ = 0;
+    const uint64_t mine = (cells + world - 1 - rank) / world;  // cells rank, rank + world, ...
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < mine; base += (uint64_t)gridDim.x * blockDim.x) {  // (whole warps iterate together: the cursor is warp-aggregated)
+        const uint64_t i    = base + threadIdx.x;
+        const uint64_t cell = i * world + rank;
+        const uint32_t c    = i < mine ? __ldg(dense_global + cell) : 0u;
+        const bool     keep = c != 0 && c >= threshold;
+        found += c != 0;
+        const uint64_t o = warp_aggregated_inc(&st->cursor, keep);
+        if (keep) {
+            ++kept;
+            occ += c;
+            sv_pos[o]          = ext_pos0 + 2u * (uint32_t)i;
+            sv_cnt[o]          = c;
+            tok_ext[2 * i]     = (uint32_t)(cell / dense);
+            tok_ext[2 * i + 1] = (uint32_t)(cell % dense);
+        }
+    }
+    found = block_reduce_sum(found, scratch);
+    kept  = block_reduce_sum(kept, scratch);
+    occ   = block_reduce_sum(occ, scratch);
+    if (threadIdx.x == 0) {
+        if (found) atomicAdd(&st->found, (unsigned long long)found);
+        if (kept) atomicAdd(&st->kept, (unsigned long long)kept);
+        if (occ) atomicAdd(&st->kept_occ, (unsigned long long)occ);
+    }
+}
+
 // received survivor records of owner group g: (index inside my send group to g, global count) -> (position, count)
 __global__ void __launch_bounds__(256) sender_survivors_kernel(const uint2* __restrict__ recs, uint64_t n, const uint32_t* __restrict__ pos_of_rec, uint64_t send_base,
                                                                uint32_t* __restrict__ sv_pos, uint32_t* __restrict__ sv_count) {
@@ -434,16 +497,16 @@ __global__ void __launch_bounds__(256) sender_survivors_kernel(const uint2* __re
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------------------------
-int launch_split_count(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, uint32_t* hist /* world x nblocks */) {
+int launch_split_count(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, uint32_t* hist /* world x nblocks */, uint32_t dense, uint32_t* dense_cnt) {
     uint32_t nblocks = sk_div_up(npos, kSplitTile);
-    split_count_kernel<<<nblocks, 256, 0, s>>>(prev, npos, world, nblocks, hist);
+    split_count_kernel<<<nblocks, 256, 0, s>>>(prev, npos, world, nblocks, hist, dense, dense_cnt);
     return 1;
 }
 int launch_split_write(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, const uint64_t* hist_off, void* send_keys, uint32_t* pos_of_rec, uint32_t* rec_of_pos,
-                       void* const* peer_keys, uint32_t my_rank, uint64_t slot_cap) {
+                       void* const* peer_keys, uint32_t my_rank, uint64_t slot_cap, uint32_t dense) {
     uint32_t nblocks = sk_div_up(npos, kSplitTile);
     split_write_kernel<<<nblocks, 256, 0, s>>>(prev, npos, world, nblocks, hist_off, (unsigned long long*)send_keys, pos_of_rec, rec_of_pos, (unsigned long long* const*)peer_keys,
-                                                my_rank, slot_cap);
+                                                my_rank, slot_cap, dense);
     return 1;
 }
 int launch_stream_filter(cudaStream_t s, const void* keys, uint64_t n, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms, uint64_t slot_cap,
@@ -461,9 +524,9 @@ int launch_stream_count(cudaStream_t s, const void* keys, uint64_t n, NgramSlot*
     return 1;
 }
 int launch_owner_reply(cudaStream_t s, uint32_t* rid, uint64_t n, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* const* peer_reply, uint64_t slot_cap,
-                       const unsigned long long* slot_counts) {
+                       const unsigned long long* slot_counts, uint32_t id_off) {
     if (!n) return 0;
-    owner_reply_kernel<<<sk_div_up(n, 256), 256, 0, s>>>(rid, n, bitmap, world, rank, (uint32_t* const*)peer_reply, slot_cap, slot_counts);
+    owner_reply_kernel<<<sk_div_up(n, 256), 256, 0, s>>>(rid, n, bitmap, world, rank, (uint32_t* const*)peer_reply, slot_cap, slot_counts, id_off);
     return 1;
 }
 int launch_owner_survivors_p2p(cudaStream_t s, const uint32_t* sv_idx, const uint32_t* sv_count, uint64_t n, uint32_t world, uint32_t rank, uint64_t slot_cap, uint64_t surv_cap,
@@ -490,9 +553,17 @@ int launch_owner_survivors(cudaStream_t s, const uint32_t* sv_idx, const uint32_
     owner_survivors_kernel<<<grid, 256, 0, s>>>(sv_idx, sv_count, n, world, src_base, out_base, cursors, (uint2*)out);
     return 1;
 }
-int launch_sender_relabel(cudaStream_t s, const uint32_t* rec_of_pos, const uint32_t* reply, uint64_t npos, uint32_t* cur, DeviceStats* st, int sms) {
+int launch_sender_relabel(cudaStream_t s, const uint32_t* rec_of_pos, const uint32_t* reply, uint64_t npos, uint32_t* cur, DeviceStats* st, int sms, const uint32_t* dense_global,
+                          uint32_t threshold) {
     unsigned grid = (unsigned)sk_min(sk_div_up(npos, 256), (uint64_t)sms * 16);
-    sender_relabel_kernel<<<grid ? grid : 1, 256, 0, s>>>(rec_of_pos, reply, npos, cur, st);
+    sender_relabel_kernel<<<grid ? grid : 1, 256, 0, s>>>(rec_of_pos, reply, npos, cur, st, dense_global, threshold);
+    return 1;
+}
+int launch_dense_share(cudaStream_t s, const uint32_t* dense_global, uint32_t dense, uint32_t world, uint32_t rank, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_cnt,
+                       uint32_t* tok_ext, uint32_t ext_pos0, DeviceStats* st, int sms) {
+    const uint64_t mine = ((uint64_t)dense * dense + world - 1) / world;
+    unsigned       grid = (unsigned)sk_min(sk_div_up(mine, 256), (uint64_t)sms * 8);
+    dense_share_kernel<<<grid ? grid : 1, 256, 0, s>>>(dense_global, dense, world, rank, threshold, sv_pos, sv_cnt, tok_ext, ext_pos0, st);
     return 1;
 }
 int launch_sender_survivors(cudaStream_t s, const void* recs, uint64_t n, const uint32_t* pos_of_rec, uint64_t send_base, uint32_t* sv_pos, uint32_t* sv_count) {

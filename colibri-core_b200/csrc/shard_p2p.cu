@@ -54,7 +54,7 @@ extern "C" int colibri_b200_shard_p2p_split(colibri_b200_shard* sh, int n, uint6
     cudaStream_t s = sh->s;
     if (sh->pos_of_rec.n < sh->nsent + 1) TRY(sh->pos_of_rec.alloc(sh->dev, sh->nsent + 1));
     if (sh->rec_of_pos.n < sh->npos + 8) TRY(sh->rec_of_pos.alloc(sh->dev, sh->npos + 8));
-    sh->launches += launch_split_write(s, sh->prev.p, sh->npos, sh->world, sh->split_off.p, nullptr, sh->pos_of_rec.p, sh->rec_of_pos.p, sh->d_peer.p, sh->rank, sh->slot_cap);
+    sh->launches += launch_split_write(s, sh->prev.p, sh->npos, sh->world, sh->split_off.p, nullptr, sh->pos_of_rec.p, sh->rec_of_pos.p, sh->d_peer.p, sh->rank, sh->slot_cap, shard_dense_now(sh));
     unsigned long long vals[64];
     for (uint32_t d = 0; d < sh->world; ++d) vals[d] = counts[d];
     CUDA_TRY(cudaMemcpyAsync(sh->d_vals.p, vals, sh->world * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
@@ -80,6 +80,7 @@ extern "C" int colibri_b200_shard_p2p_owner(colibri_b200_shard* sh, uint64_t sta
         nrecv += counts[r];
     }
     sh->nrecv = nrecv;
+    TRY(shard_dense_owner(sh));  // (the caller has summed the dense squares by now)
     const uint64_t phys = (uint64_t)G * sh->slot_cap;  // slots are scanned whole; entries past a slot's count are skipped
     const void*    keys = sh->h_keys_rx[sh->rank];
     if (sh->rid.n < phys) TRY(sh->rid.alloc(sh->dev, phys));
@@ -100,7 +101,7 @@ extern "C" int colibri_b200_shard_p2p_owner(colibri_b200_shard* sh, uint64_t sta
     const uint64_t cap_max = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);  // a table this large cannot fill up
     uint64_t singles = 0;
     for (;;) {
-        if (cap * G >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner table of %llu slots x %u ranks exceeds the 32-bit id space", (unsigned long long)cap, G);
+        if (cap * G + shard_id_off(sh) >= 0xFFFFFFF0ull) return set_err(COLIBRI_E_CAPACITY, "owner table of %llu slots x %u ranks exceeds the 32-bit id space", (unsigned long long)cap, G);
         if (sh->owner_table.n < cap) TRY(sh->owner_table.alloc(sh->dev, cap));
         CUDA_TRY(cudaMemsetAsync(sh->owner_table.p, 0, cap * sizeof(NgramSlot), s));
         TRY(shard_zero_stats(sh));
@@ -122,11 +123,11 @@ extern "C" int colibri_b200_shard_p2p_owner(colibri_b200_shard* sh, uint64_t sta
     if (sh->bitmap.n < cap / 32 + 8) TRY(sh->bitmap.alloc(sh->dev, cap / 32 + 8));
     TRY(shard_zero_stats(sh));
     sh->launches += launch_prune_ngrams(s, sh->owner_table.p, cap, t, sh->sv_idx.p, sh->sv_cnt.p, sh->bitmap.p, sh->d_stats.p, sh->sms);
-    sh->launches += launch_owner_reply(s, sh->rid.p, phys, sh->bitmap.p, G, sh->rank, sh->d_peer.p + 64, sh->slot_cap, my_hdr);  // ids -> the senders' reply slots
+    sh->launches += launch_owner_reply(s, sh->rid.p, phys, sh->bitmap.p, G, sh->rank, sh->d_peer.p + 64, sh->slot_cap, my_hdr, shard_id_off(sh));  // ids -> the senders' reply slots
     TRY(shard_read_stats(sh));
-    stats[0]  = sh->h_stats.found + singles;
-    stats[1]  = sh->h_stats.kept;
-    stats[2]  = sh->h_stats.kept_occ;
+    stats[0]  = sh->h_stats.found + singles + sh->dense_stats[0];
+    stats[1]  = sh->h_stats.kept + sh->dense_stats[1];
+    stats[2]  = sh->h_stats.kept_occ + sh->dense_stats[2];
     sh->nsurv = sh->h_stats.kept;
     // survivors -> the claimers' survivor slots; the cursors become the counts the sources read from their headers
     if (sh->d_aux.n < 260) TRY(sh->d_aux.alloc(sh->dev, 260));
@@ -166,24 +167,30 @@ extern "C" int colibri_b200_shard_p2p_finish(colibri_b200_shard* sh, uint64_t gl
     const int n = sh->level + 1;
     TRY(shard_zero_stats(sh));
     CUDA_TRY(cudaMemsetAsync(sh->cur.p + sh->npos, 0, 8 * sizeof(uint32_t), s));
-    sh->launches += launch_sender_relabel(s, sh->rec_of_pos.p, (const uint32_t*)sh->h_reply_rx[sh->rank], sh->npos, sh->cur.p, sh->d_stats.p, sh->sms);
+    sh->launches += launch_sender_relabel(s, sh->rec_of_pos.p, (const uint32_t*)sh->h_reply_rx[sh->rank], sh->npos, sh->cur.p, sh->d_stats.p, sh->sms,
+                                          shard_dense_now(sh) ? sh->dense_cnt : nullptr, sh->t);
     uint64_t total = 0;
     for (uint32_t g = 0; g < G; ++g) total += surv_counts[g];
     Segment sg;
     sg.n = n;
-    if (total) {
-        TRY(sg.pos.alloc(sh->dev, total));
-        TRY(sg.cnt.alloc(sh->dev, total));
+    const uint64_t nd = shard_dense_now(sh) ? sh->dense_nsurv : 0;  // this rank's share of the dense square's survivors goes into the same segment
+    if (total + nd) {
+        TRY(sg.pos.alloc(sh->dev, total + nd));
+        TRY(sg.cnt.alloc(sh->dev, total + nd));
         uint64_t off = 0;
         for (uint32_t g = 0; g < G; ++g) {
             const uint8_t* recs = (const uint8_t*)sh->h_surv_rx[sh->rank] + (uint64_t)g * sh->surv_cap * 8;
             sh->launches += launch_sender_survivors(s, recs, surv_counts[g], sh->pos_of_rec.p, sh->send_base[g], sg.pos.p + off, sg.cnt.p + off);
             off += surv_counts[g];
         }
+        if (nd) {
+            CUDA_TRY(cudaMemcpyAsync(sg.pos.p + total, sh->dense_sv_pos.p, nd * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(sg.cnt.p + total, sh->dense_sv_cnt.p, nd * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        }
     }
     TRY(shard_read_stats(sh));
-    sg.count = total;
-    if (total) sh->segs.push_back(std::move(sg));
+    sg.count = total + nd;
+    if (total + nd) sh->segs.push_back(std::move(sg));
     sh->prev_valid = sh->h_stats.kept_occ;
     if (local_valid) *local_valid = sh->prev_valid;
     std::swap(sh->prev, sh->cur);

@@ -134,6 +134,12 @@ class CudaShardEngine:
         sc = (C.c_uint64 * self.world)(*surv_counts)
         self._check(self.lib.colibri_b200_shard_skip_finish(self._h, surv.data_ptr(), sc))
 
+    def enable_dense(self, dim):
+        """Level 2: pairs of classes below `dim` are counted in a square on every rank and summed by ONE all-reduce instead of being shipped."""
+        self.dense_t = self.torch.zeros(dim * dim, dtype=self.torch.int32, device=self.device)
+        self._check(self.lib.colibri_b200_shard_set_dense(self._h, self.dense_t.data_ptr(), dim))
+        return self.dense_t
+
     # ---- NVLink peer-store mode
     def use_peers(self, peers: "PeerBuffers"):
         self._check(self.lib.colibri_b200_shard_set_stream(self._h, C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)))
@@ -276,9 +282,16 @@ def train_distributed(engine, dist, torch, mintokens=2, maxlength=5, skipgrams=F
     prev_kept = kept
     n = 2
     peers = getattr(engine, "peers", None)
+    # dense pairs of level 2: decided from global quantities only, so that every rank decides alike (the ids of level 2 depend on it)
+    dense_t = None
+    dense_dim = min(int(os.environ.get("COLIBRI_B200_DENSE", "2048")), nclasses, 16384)
+    if hasattr(engine, "enable_dense") and dense_dim >= 2 and global_tokens // world >= int(os.environ.get("COLIBRI_B200_DENSE_MIN", str(1 << 25))):
+        dense_t = engine.enable_dense(dense_dim)
     while peers is not None and found and n <= maxlength and prev_kept > 0:
         # NVLink peer-store mode: keys and replies are stored into the peers' symmetric buffers by the kernels themselves
         engine.p2p_split(n)
+        if n == 2 and dense_t is not None:
+            dist.all_reduce(dense_t)  # same stream as the phases: summed before the owner phase reads it
         sw.lap("p2p_split")
         peers.barrier()
         sw.lap("barrier")
@@ -300,6 +313,8 @@ def train_distributed(engine, dist, torch, mintokens=2, maxlength=5, skipgrams=F
         n += 1
     while peers is None and found and n <= maxlength and prev_kept > 0:
         send_counts, nsend = engine.level_split_count(n)
+        if n == 2 and dense_t is not None:
+            dist.all_reduce(dense_t)  # (the engine.sync() of the key exchange below covers it)
         sw.lap("split_count")
         send = engine.level_split_write(nsend)
         sw.lap("split_write")
@@ -373,6 +388,65 @@ def train_constrained_distributed(engine, dist, torch, inplace=False):
         dist.all_reduce(counts)
         dist.all_reduce(tok)
     return engine.finish(counts, int(tok.item()), inplace)
+
+
+def cut_at_sentences(body: np.ndarray, world: int):
+    """Byte offsets that cut a class-encoded corpus into `world` shards of about equal size at sentence boundaries (a delimiter is a 0x00 byte
+    that is not the last byte of a multi-byte class: the byte before it is below 128)."""
+    cuts = [0]
+    for r in range(1, world):
+        j = max(len(body) * r // world, cuts[-1])
+        while j < len(body) and not (body[j] == 0 and (j == 0 or body[j - 1] < 128)):
+            j += 1
+        cuts.append(min(j + 1, len(body)))
+    cuts.append(len(body))
+    return cuts
+
+
+def strong_scaling_parity(a, dist, torch, cb, rank, world, local, opts, peers):
+    """One untimed STRONG-scaling step: the 1-GPU benchmark corpus (the one tests/golden/golden_bench.json pins to the unmodified reference) cut
+    into `world` shards at sentence boundaries and trained through the same sharded path; the order-independent checksums of the ranks' shares are
+    combined (sum, xor, occurrences, patterns) and compared with the reference model's -- the same model from 1, 2, 4 or 8 GPUs."""
+    if (int(a.tokens), a.vocab, a.seed, a.maxlength, a.mintokens, int(a.skipgrams)) != (100000000, 100000, 1, 5, 2, 0):
+        return {"checked": False, "why": "the committed fixture pins the default workload only"}
+    try:
+        with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "golden_bench.json")) as f:
+            g = json.load(f)["zipf100m"]
+    except Exception as e:
+        return {"checked": False, "why": "no fixture: %r" % (e,)}
+    full = cb.Corpus.synthetic(int(a.tokens), vocab=a.vocab, seed=a.seed, device=local)
+    body = full.download()
+    full.close()
+    cuts = cut_at_sentences(body, world)
+    shard = np.ascontiguousarray(body[cuts[rank]:cuts[rank + 1]])
+    c = cb.Corpus.from_host_pointer(shard.ctypes.data, shard.size, device=local)
+    eng = CudaShardEngine(c, opts, rank, world, local)
+    if peers is not None:
+        eng.use_peers(peers)
+    model, passes, head = train_distributed(eng, dist, torch, a.mintokens, a.maxlength, False)
+    cs = model.checksum()
+    n_local = len(model)
+    model.close()
+    eng.close()
+    c.close()
+
+    def i64(x):  # u64 bit pattern as a signed value: two's-complement sums wrap the same way
+        return x - (1 << 64) if x >= (1 << 63) else x
+
+    tot = torch.tensor([i64(cs["sum"]), cs["occurrences"], cs["patterns"]], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    xors = [None] * world
+    dist.all_gather_object(xors, cs["xor"])
+    x = 0
+    for v in xors:
+        x ^= v
+    got = {"sum": int(tot[0].item()) & ((1 << 64) - 1), "xor": x, "occurrences": int(tot[1].item()), "patterns": int(tot[2].item())}
+    want = g["checksum"]
+    return {"checked": True, "what": "strong scaling: the 100 M-token benchmark corpus cut into %d shards at sentence boundaries, trained on %d GPUs" % (world, world),
+            "fixture": "tests/golden/golden_bench.json: zipf100m (unmodified reference, %s)" % g["cli"], "shard_bytes": [cuts[i + 1] - cuts[i] for i in range(world)],
+            "checksum": got, "checksum_ok": all(got[k] == want[k] for k in ("sum", "xor", "occurrences", "patterns")),
+            "passes_ok": [(p[1], p[3]) for p in passes] == [(p[0], p[2]) for p in g["passes_found_skip_pruned_kept"]],
+            "header_ok": (head["tokens"], head["types"]) == (g["tokens"], g["types"]), "patterns_on_rank0": n_local}
 
 
 def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, measured_peaks):
@@ -462,6 +536,7 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
     dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     xfer = torch.tensor([corpus.nbytes, d2h], dtype=torch.int64, device="cuda")
     dist.all_reduce(xfer, op=dist.ReduceOp.SUM)
+    parity = strong_scaling_parity(a, dist, torch, cb, rank, world, local, opts, peers)
     if rank == 0:
         clocks = sampler.stop()
         elapsed = float(t[0].item())
@@ -478,7 +553,7 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
             "roofline": {"bound": "hbm", "kernel": "count_ngrams_kernel", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "peak_source": peak_src, "traffic": None,
                          "note": "per-kernel roofline is reported by the 1-GPU run; the N-GPU line reports whole-job throughput",
                          "hbm_read_roofline_frac": (a.maxlength * corpus.nbytes / (elapsed / a.steps) / 1e9) / peak},
-            "clocks": clocks, "gpu_launches": int(npat[1].item()),
+            "clocks": clocks, "gpu_launches": int(npat[1].item()), "parity": parity,
             "e2e": {"value": tokens * a.steps / float(e2e_t.item()), "unit": unit, "h2d_bytes_per_step": int(xfer[0].item()), "d2h_bytes_per_step": int(xfer[1].item()),
                     "ms_per_step": 1e3 * float(e2e_t.item()) / a.steps, "api": "per rank: colibri_b200_corpus_stage(pinned host shard) + shard phases + NCCL + colibri_b200_model_export_compact (pinned)"},
         }

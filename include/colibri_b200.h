@@ -219,6 +219,10 @@ int    colibri_b200_shard_phase_ms(const colibri_b200_shard* sh, double out[8]);
 int    colibri_b200_shard_unigram_counts(colibri_b200_shard* sh, uint32_t nclasses, void* dev_counts /* u32[nclasses] */);
 /* stats[0]=distinct unigrams (global), [1]=kept, [2]=occurrences kept */
 int    colibri_b200_shard_unigram_finish(colibri_b200_shard* sh, const void* dev_global_counts, uint64_t global_tokens, uint64_t stats[3]);
+/* Dense pairs of level 2 (optional, before level 2; all ranks alike): dev_square = the caller's zeroed u32[dim * dim] on this rank's device.  The split
+ * of level 2 counts this rank's windows of two classes below dim into it instead of shipping them; the CALLER sums the squares of all ranks
+ * (one all-reduce) before shard_level_owner / shard_p2p_owner.  dim = 0 switches it off. */
+int    colibri_b200_shard_set_dense(colibri_b200_shard* sh, void* dev_square, uint32_t dim);
 /* send_counts[world]: valid windows of level n whose key is owned by each rank; *windows = their sum */
 int    colibri_b200_shard_level_split_count(colibri_b200_shard* sh, int n, uint64_t* send_counts, uint64_t* windows);
 int    colibri_b200_shard_level_split_write(colibri_b200_shard* sh, void* dev_send_keys /* 8 B per window, grouped by owner */);

@@ -11,10 +11,13 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _run(world, per, vocab, seed, maxlength, mintokens, port, mode="nccl", extra=""):
+DENSE = {"COLIBRI_B200_DENSE_MIN": "0", "COLIBRI_B200_DENSE": "64"}  # the dense square of level 2 forced onto small shards (bench.py has it at 100 M tokens per GPU)
+
+
+def _run(world, per, vocab, seed, maxlength, mintokens, port, mode="nccl", extra="", env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "dist_gpu_worker.py"), str(per), str(vocab), str(seed), str(maxlength), str(mintokens), mode] + ([extra] if extra else [])
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_RESULT OK" in r.stdout, r.stdout[-3000:]
 
@@ -24,13 +27,21 @@ def test_shard_phases_world1(per, vocab, seed, maxlength, mintokens):
     _run(1, per, vocab, seed, maxlength, mintokens, 29711)
 
 
+@pytest.mark.parametrize("dense", [False, True])
 @pytest.mark.parametrize("mode", ["nccl", "p2p"])
-def test_shard_phases_world2(mode):
+def test_shard_phases_world2(mode, dense):
     import colibri_core_b200 as cb
 
     if cb.device_count() < 2:
         pytest.skip("needs two GPUs")
-    _run(2, 400000, 30000, 6, 5, 2, 29713, mode)
+    _run(2, 400000, 30000, 6, 5, 2, 29713, mode, env=DENSE if dense else None)
+
+
+@pytest.mark.parametrize("mode,extra", [("nccl", ""), ("p2p", ""), ("p2p", "skipgrams")])
+def test_shard_dense_pairs_world1(mode, extra):
+    """Level 2 with the dense square on the sharded path: pairs of frequent classes are counted locally and summed by one all-reduce instead of
+    being shipped; their ids (cell + 1) live below the ids of the hashed n-grams and feed level 3 and the skipgrams."""
+    _run(1, 300000, 20000, 4, 5, 2, 29725, mode, extra, env=DENSE)
 
 
 @pytest.mark.parametrize("mode", ["nccl", "p2p"])

@@ -159,14 +159,16 @@ int launch_refs_from_positions(cudaStream_t s, const uint32_t* pos, uint64_t n, 
 // ---- multi-GPU phases (hash-partitioned model): shard_kernels.cu, driven by shard.cu
 // dense > 0 (level 2): windows of two classes below `dense` are counted in dense_cnt[a * dense + b] and get no destination
 int launch_split_count(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, uint32_t* hist /* world x ceil(npos/4096), destination-major */, uint32_t dense = 0,
-                       uint32_t* dense_cnt = nullptr);
+                       uint32_t* dense_cnt = nullptr, const uint32_t* list = nullptr /* list mode: npos items, item j = position list[j] */);
 // peer_* != NULL selects the NVLink peer-store variants (symmetric-memory receive slots of slot_cap entries per source rank)
 int launch_split_write(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, const uint64_t* hist_off, void* send_keys, uint32_t* pos_of_rec, uint32_t* rec_of_pos,
-                       void* const* peer_keys = nullptr, uint32_t my_rank = 0, uint64_t slot_cap = 0, uint32_t dense = 0 /* rec_of_pos = 0x80000000 | cell for dense windows */);
+                       void* const* peer_keys = nullptr, uint32_t my_rank = 0, uint64_t slot_cap = 0, uint32_t dense = 0 /* rec_of_pos = 0x80000000 | cell for dense windows */,
+                       const uint32_t* list = nullptr /* list mode: rec_of_pos is indexed by item */);
+// n = keys received; slot_cap != 0: they sit in `world` slots of slot_cap entries, slot_counts[r] of them in slot r (rid[] is indexed like the buffer)
 int launch_stream_filter(cudaStream_t s, const void* keys, uint64_t n, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms, uint64_t slot_cap = 0,
-                         const unsigned long long* slot_counts = nullptr);
+                         const unsigned long long* slot_counts = nullptr, uint32_t world = 0);
 int launch_stream_count(cudaStream_t s, const void* keys, uint64_t n, NgramSlot* table, uint64_t cap, const uint32_t* filter, uint64_t nbuckets, uint32_t* rid, DeviceStats* st, int sms,
-                        uint64_t slot_cap = 0, const unsigned long long* slot_counts = nullptr);
+                        uint64_t slot_cap = 0, const unsigned long long* slot_counts = nullptr, uint32_t world = 0);
 int launch_owner_reply(cudaStream_t s, uint32_t* rid, uint64_t n, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* const* peer_reply = nullptr, uint64_t slot_cap = 0,
                        const unsigned long long* slot_counts = nullptr, uint32_t id_off = 0 /* global ids start above the dense square's */);
 int launch_owner_survivors_p2p(cudaStream_t s, const uint32_t* sv_idx, const uint32_t* sv_count, uint64_t n, uint32_t world, uint32_t rank, uint64_t slot_cap, uint64_t surv_cap,
@@ -176,7 +178,7 @@ int launch_owner_survivor_counts(cudaStream_t s, const uint32_t* sv_idx, uint64_
 int launch_owner_survivors(cudaStream_t s, const uint32_t* sv_idx, const uint32_t* sv_count, uint64_t n, uint32_t world, const unsigned long long* src_base,
                            const unsigned long long* out_base, unsigned long long* cursors, void* out, int sms);
 int launch_sender_relabel(cudaStream_t s, const uint32_t* rec_of_pos, const uint32_t* reply, uint64_t npos, uint32_t* cur, DeviceStats* st, int sms,
-                          const uint32_t* dense_global = nullptr, uint32_t threshold = 0);
+                          const uint32_t* dense_global = nullptr, uint32_t threshold = 0, const uint32_t* list = nullptr /* list mode: cur zeroed by the caller */);
 // this rank's share (cells = rank mod world) of the globally summed dense square: found / kept / kept_occ into st, survivors appended through st->cursor
 int launch_dense_share(cudaStream_t s, const uint32_t* dense_global, uint32_t dense, uint32_t world, uint32_t rank, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_cnt,
                        uint32_t* tok_ext, uint32_t ext_pos0, DeviceStats* st, int sms);

@@ -190,12 +190,12 @@ extern "C" int colibri_b200_shard_level_split_count(colibri_b200_shard* sh, int 
     CUDA_TRY(cudaSetDevice(sh->dev));
     PhaseClock clk(sh, 2);
     cudaStream_t   s       = sh->s;
-    const uint64_t nblocks = (sh->npos + 4095) / 4096;
+    const uint64_t nblocks = (shard_items(sh) + 4095) / 4096;
     const uint64_t nh      = (uint64_t)sh->world * nblocks;
     if (sh->split_hist.n < nh) TRY(sh->split_hist.alloc(sh->dev, nh));
     if (sh->split_off.n < nh + 1) TRY(sh->split_off.alloc(sh->dev, nh + 1));
     if (sh->scan_tmp.n < nh / 2048 + 4) TRY(sh->scan_tmp.alloc(sh->dev, nh / 2048 + 4));
-    sh->launches += launch_split_count(s, sh->prev.p, sh->npos, sh->world, sh->split_hist.p, shard_dense_now(sh), sh->dense_cnt);
+    sh->launches += launch_split_count(s, sh->prev.p, shard_items(sh), sh->world, sh->split_hist.p, shard_dense_now(sh), sh->dense_cnt, shard_list(sh));
     sh->launches += launch_exclusive_scan_u32_u64(s, sh->split_hist.p, sh->split_off.p, nh, sh->scan_tmp.p);
     for (uint32_t d = 0; d <= sh->world; ++d)
         CUDA_TRY(cudaMemcpyAsync(&sh->send_base[d], sh->split_off.p + (uint64_t)d * nblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -212,9 +212,9 @@ extern "C" int colibri_b200_shard_level_split_write(colibri_b200_shard* sh, void
     CUDA_TRY(cudaSetDevice(sh->dev));
     PhaseClock clk(sh, 3);
     if (sh->pos_of_rec.n < sh->nsent + 1) TRY(sh->pos_of_rec.alloc(sh->dev, sh->nsent + 1));
-    if (sh->rec_of_pos.n < sh->npos + 8) TRY(sh->rec_of_pos.alloc(sh->dev, sh->npos + 8));
+    if (sh->rec_of_pos.n < shard_items(sh) + 8) TRY(sh->rec_of_pos.alloc(sh->dev, shard_items(sh) + 8));
     if (shard_dense_now(sh) && sh->nsent >= 0x80000000ull) return set_err(COLIBRI_E_CAPACITY, "%llu windows to ship; the record index has 31 bits beside the dense square", (unsigned long long)sh->nsent);
-    sh->launches += launch_split_write(sh->s, sh->prev.p, sh->npos, sh->world, sh->split_off.p, dev_send_keys, sh->pos_of_rec.p, sh->rec_of_pos.p, nullptr, 0, 0, shard_dense_now(sh));
+    sh->launches += launch_split_write(sh->s, sh->prev.p, shard_items(sh), sh->world, sh->split_off.p, dev_send_keys, sh->pos_of_rec.p, sh->rec_of_pos.p, nullptr, 0, 0, shard_dense_now(sh), shard_list(sh));
     CUDA_TRY(cudaStreamSynchronize(sh->s));
     return 0;
 }
@@ -323,7 +323,9 @@ extern "C" int colibri_b200_shard_level_finish(colibri_b200_shard* sh, const voi
     const int n = sh->level + 1;
     TRY(shard_zero_stats(sh));
     CUDA_TRY(cudaMemsetAsync(sh->cur.p + sh->npos, 0, 8 * sizeof(uint32_t), s));
-    sh->launches += launch_sender_relabel(s, sh->rec_of_pos.p, (const uint32_t*)dev_reply_back, sh->npos, sh->cur.p, sh->d_stats.p, sh->sms, shard_dense_now(sh) ? sh->dense_cnt : nullptr, sh->t);
+    if (sh->list_valid) CUDA_TRY(cudaMemsetAsync(sh->cur.p, 0, sh->npos * sizeof(uint32_t), s));  // list mode writes only the positions that keep an id
+    sh->launches += launch_sender_relabel(s, sh->rec_of_pos.p, (const uint32_t*)dev_reply_back, shard_items(sh), sh->cur.p, sh->d_stats.p, sh->sms,
+                                          shard_dense_now(sh) ? sh->dense_cnt : nullptr, sh->t, shard_list(sh));
     uint64_t total = 0;
     for (uint32_t g = 0; g < sh->world; ++g) total += surv_counts[g];
     Segment sg;
@@ -351,6 +353,7 @@ extern "C" int colibri_b200_shard_level_finish(colibri_b200_shard* sh, const voi
     std::swap(sh->prev, sh->cur);
     sh->level = n;
     TRY(shard_keep_ids(sh, n));
+    TRY(shard_next_list(sh));
     return 0;
 }
 

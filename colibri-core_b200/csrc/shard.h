@@ -46,6 +46,10 @@ struct colibri_b200_shard {
     uint64_t             tok_ext_cells = 0;  // room behind the tokens for the class pairs of this rank's dense survivors
     DevBuf<uint32_t>     dense_sv_pos, dense_sv_cnt;
     uint64_t             dense_stats[3] = {0, 0, 0}, dense_nsurv = 0;
+    // list mode of the sparse later levels: the positions whose newest id is non-zero (see kernels.cu: load_window; shard_kernels.cu: window_dest)
+    DevBuf<uint32_t>     list;
+    uint64_t             nlist = 0;
+    bool                 list_valid = false;
     int                  level = 1;
     uint32_t             t = 2;
     std::vector<Segment> segs;
@@ -90,6 +94,20 @@ inline int shard_dense_owner(colibri_b200_shard* sh) {
     sh->dense_stats[1] = sh->h_stats.kept;
     sh->dense_stats[2] = sh->h_stats.kept_occ;
     sh->dense_nsurv    = sh->h_stats.kept;
+    return 0;
+}
+inline uint64_t shard_items(const colibri_b200_shard* sh) { return sh->list_valid ? sh->nlist : sh->npos; }
+inline const uint32_t* shard_list(const colibri_b200_shard* sh) { return sh->list_valid ? sh->list.p : nullptr; }
+// after a level's finish (sh->prev = the new ids, sh->prev_valid of them non-zero): the next level runs from a position list when few positions are left
+inline int shard_next_list(colibri_b200_shard* sh) {
+    const Tuning tune = Tuning::from_env();
+    sh->list_valid    = false;
+    if (sh->level >= sh->o.MAXLENGTH || tune.sparse_div == 0 || sh->prev_valid == 0 || sh->prev_valid * tune.sparse_div > sh->npos) return 0;
+    if (sh->list.n < sh->prev_valid + 8) TRY(sh->list.alloc(sh->dev, sh->prev_valid + 8));
+    CUDA_TRY(cudaMemsetAsync(&sh->d_stats.p->cursor, 0, sizeof(unsigned long long), sh->s));
+    sh->launches += launch_compact_nonzero(sh->s, sh->prev.p, sh->npos, sh->list.p, &sh->d_stats.p->cursor);
+    sh->nlist      = sh->prev_valid;
+    sh->list_valid = true;
     return 0;
 }
 inline uint32_t shard_dense_now(const colibri_b200_shard* sh) {  // the dense side of the level being built (level + 1)

@@ -42,8 +42,12 @@ constexpr uint32_t kHotSide   = 64;           // the pairs of the 64 most freque
 // Dense pairs (level 2, as on one GPU -- kernels.cu): a window of two classes below `dense` is never shipped.  Every rank counts such pairs
 // in its own dense square, the squares are summed by one all-reduce, and every rank derives the same verdict from the global square:
 // id = cell + 1 if the global count reaches the threshold, else 0.  The ids of the hashed n-grams start above dense^2.
-__device__ __forceinline__ uint32_t window_dest(const uint32_t* __restrict__ prev, uint64_t p, uint64_t npos, uint32_t world, unsigned long long& key, uint32_t dense = 0) {
-    if (p >= npos) return 256u;
+// item j of a level: position j, or -- list mode, the sparse later levels -- position list[j] (the positions whose (n-1)-gram survived, left behind
+// by the previous level's finish).  In list mode the per-position arrays (rec_of_pos) are indexed by ITEM.
+__device__ __forceinline__ uint32_t window_dest(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ list, uint64_t j, uint64_t nitems, uint32_t world,
+                                                unsigned long long& key, uint32_t dense, uint32_t& p) {
+    if (j >= nitems) return 256u;
+    p = list ? __ldg(list + j) : (uint32_t)j;
     uint32_t a = prev[p], b = prev[p + 1];
     if (a == 0 || b == 0) return 256u;
     if (a < dense && b < dense) {
@@ -55,8 +59,8 @@ __device__ __forceinline__ uint32_t window_dest(const uint32_t* __restrict__ pre
 }
 
 // pass 1: per block, windows per destination (destination-major so that one exclusive scan yields every block's bases)
-__global__ void __launch_bounds__(256) split_count_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t world, uint32_t nblocks, uint32_t* __restrict__ hist,
-                                                          uint32_t dense, uint32_t* __restrict__ dense_cnt) {
+__global__ void __launch_bounds__(256) split_count_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ list, uint64_t npos /* items */, uint32_t world,
+                                                          uint32_t nblocks, uint32_t* __restrict__ hist, uint32_t dense, uint32_t* __restrict__ dense_cnt) {
     __shared__ uint32_t h[64];
     __shared__ uint32_t hot[kHotSide * kHotSide];
     if (threadIdx.x < 64) h[threadIdx.x] = 0;
@@ -67,7 +71,8 @@ __global__ void __launch_bounds__(256) split_count_kernel(const uint32_t* __rest
 #pragma unroll 4
     for (int k = 0; k < kSplitTile / 256; ++k) {
         unsigned long long key;
-        uint32_t           d = window_dest(prev, base + (uint64_t)k * 256 + threadIdx.x, npos, world, key, dense);
+        uint32_t           p;
+        uint32_t           d = window_dest(prev, list, base + (uint64_t)k * 256 + threadIdx.x, npos, world, key, dense, p);
         if (d < 64) atomicAdd(&h[d], 1u);
         else if (d == kDenseDest) {
             const uint32_t cell = (uint32_t)key, a = cell / dense, b = cell % dense;
@@ -89,7 +94,8 @@ __global__ void __launch_bounds__(256) split_count_kernel(const uint32_t* __rest
 // (peer_keys[d] = base of rank d's receive buffer, slot of source r at r * slot_cap) -- the pack and the all-to-all are one kernel.
 // The block first gathers its keys per destination in shared memory and then copies each destination's run with consecutive
 // threads: 256-byte warp stores instead of 8-byte ones scattered over G streams (NVLink packets like them long).
-__global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __restrict__ prev, uint64_t npos, uint32_t world, uint32_t nblocks, const uint64_t* __restrict__ hist_off,
+__global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ list, uint64_t npos /* items */, uint32_t world,
+                                                          uint32_t nblocks, const uint64_t* __restrict__ hist_off,
                                                           unsigned long long* __restrict__ send_keys, uint32_t* __restrict__ pos_of_rec, uint32_t* __restrict__ rec_of_pos,
                                                           unsigned long long* const* __restrict__ peer_keys, uint32_t my_rank, uint64_t slot_cap, uint32_t dense) {
     __shared__ uint32_t cnt[8][65];
@@ -101,7 +107,8 @@ __global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __rest
     const uint64_t wbase = (uint64_t)blockIdx.x * kSplitTile + (uint64_t)warp * (kSplitTile / 8);
     for (int it = 0; it < kSplitTile / 8 / 32; ++it) {
         unsigned long long key;
-        uint32_t           d = window_dest(prev, wbase + (uint64_t)it * 32 + lane, npos, world, key, dense);
+        uint32_t           p;
+        uint32_t           d = window_dest(prev, list, wbase + (uint64_t)it * 32 + lane, npos, world, key, dense, p);
         if (d > 64) d = 64;
         uint32_t peers = __match_any_sync(0xffffffffu, d);
         if ((int)lane == __ffs(peers) - 1) cnt[warp][d] += __popc(peers);
@@ -129,9 +136,10 @@ __global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __rest
     }
     __syncthreads();
     for (int it = 0; it < kSplitTile / 8 / 32; ++it) {
-        const uint64_t     p = wbase + (uint64_t)it * 32 + lane;
+        const uint64_t     j = wbase + (uint64_t)it * 32 + lane;  // the item; rec_of_pos is indexed by item
         unsigned long long key = 0;
-        uint32_t           d = window_dest(prev, p, npos, world, key, dense);
+        uint32_t           p = 0;
+        uint32_t           d = window_dest(prev, list, j, npos, world, key, dense, p);
         const bool         act = d < 64, is_dense = d == kDenseDest;
         if (d > 64) d = 64;
         uint32_t peers = __match_any_sync(0xffffffffu, d);
@@ -143,13 +151,13 @@ __global__ void __launch_bounds__(256) split_write_kernel(const uint32_t* __rest
             const uint32_t in_blk = base + __popc(peers & ((1u << lane) - 1));  // rank inside this block's group for owner d
             const uint64_t dst    = hist_off[(uint64_t)d * nblocks + blockIdx.x] + in_blk;
             stage[dpre[d] + in_blk] = key;
-            pos_of_rec[dst]         = (uint32_t)p;
+            pos_of_rec[dst]         = p;
             if (peer_keys != nullptr)
-                rec_of_pos[p] = (uint32_t)((uint64_t)d * slot_cap + (dst - hist_off[(uint64_t)d * nblocks]));  // where the reply will appear in my own reply slots
+                rec_of_pos[j] = (uint32_t)((uint64_t)d * slot_cap + (dst - hist_off[(uint64_t)d * nblocks]));  // where the reply will appear in my own reply slots
             else
-                rec_of_pos[p] = (uint32_t)dst;
-        } else if (p < npos) {
-            rec_of_pos[p] = is_dense ? (kDenseRec | (uint32_t)key) : kNoRec;
+                rec_of_pos[j] = (uint32_t)dst;
+        } else if (j < npos) {
+            rec_of_pos[j] = is_dense ? (kDenseRec | (uint32_t)key) : kNoRec;
         }
     }
     __syncthreads();
@@ -172,19 +180,50 @@ __device__ __forceinline__ void stream_filter_locate(uint64_t h, uint64_t mask, 
     shift           = (uint32_t)(bucket & 15) * 2;
 }
 
-// slotted input (P2P mode, slot_cap != 0): the buffer is G slots of slot_cap keys, slot r holds slot_counts[r] keys of source r
-__device__ __forceinline__ bool slot_valid(uint64_t i, uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts) {
-    if (slot_cap == 0) return true;
-    uint64_t src = i / slot_cap;
-    return i - src * slot_cap < __ldg(slot_counts + src);
-}
+// slotted input (P2P mode, slot_cap != 0): the buffer is G slots of slot_cap keys, slot r holds slot_counts[r] keys of source r.  The owner's
+// kernels enumerate the nrecv keys that are there (c = 0 .. nrecv), not the slots' capacity: SlotMap turns c into the buffer index
+// src * slot_cap + k through the prefix sums of the counts (G <= 64, built once per block in shared memory).
+struct SlotMap {
+    unsigned long long pre[65];
+    uint32_t           world;
+    uint64_t           slot_cap;
+    __device__ __forceinline__ void init(uint32_t G, uint64_t cap, const unsigned long long* __restrict__ slot_counts) {  // by the whole block; ends with a barrier
+        if (threadIdx.x == 0) {
+            world    = cap ? G : 0;
+            slot_cap = cap;
+            pre[0]   = 0;
+            for (uint32_t r = 0; r < world; ++r) pre[r + 1] = pre[r] + slot_counts[r];
+        }
+        __syncthreads();
+    }
+    __device__ __forceinline__ uint64_t index_of(uint64_t c, uint32_t& src, uint64_t& k) const {
+        if (world == 0) {
+            src = 0;
+            k   = c;
+            return c;
+        }
+        uint32_t lo = 0, hi = world;  // pre[lo] <= c < pre[hi]
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (pre[mid] <= c) lo = mid;
+            else hi = mid;
+        }
+        src = lo;
+        k   = c - pre[lo];
+        return (uint64_t)lo * slot_cap + k;
+    }
+};
 
 __global__ void __launch_bounds__(256) stream_filter_kernel(const unsigned long long* __restrict__ keys, uint64_t n, uint32_t* __restrict__ filter, uint64_t nbuckets_mask,
-                                                            DeviceStats* __restrict__ st, uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts) {
+                                                            DeviceStats* __restrict__ st, uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts, uint32_t world) {
     __shared__ uint64_t scratch[8];
+    __shared__ SlotMap  map;
+    map.init(world, slot_cap, slot_counts);
     uint32_t twice = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        if (!slot_valid(i, slot_cap, slot_counts)) continue;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t       src;
+        uint64_t       k;
+        const uint64_t i = map.index_of(c, src, k);
         uint64_t word;
         uint32_t shift;
         stream_filter_locate(table_hash_u64(__ldcs(keys + i)), nbuckets_mask, word, shift);
@@ -230,8 +269,9 @@ constexpr unsigned long long kHotBusy = ~0ull;
 
 __global__ void __launch_bounds__(256) stream_count_kernel(const unsigned long long* __restrict__ keys, uint64_t n, NgramSlot* __restrict__ table, uint64_t cap,
                                                            const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, uint32_t* __restrict__ rid, DeviceStats* __restrict__ st,
-                                                           uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts) {
+                                                           uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts, uint32_t world) {
     __shared__ uint64_t scratch[8];
+    __shared__ SlotMap  map;
     __shared__ unsigned long long hot_key[kHotLines];
     __shared__ uint32_t hot_slot[kHotLines];
     __shared__ uint32_t hot_pending[kHotLines];
@@ -243,11 +283,11 @@ __global__ void __launch_bounds__(256) stream_count_kernel(const unsigned long l
     uint32_t       singles = 0;
     bool           full    = false;
     const uint64_t limit   = cap < 8192 ? cap : 8192;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        if (!slot_valid(i, slot_cap, slot_counts)) {
-            rid[i] = 0;
-            continue;
-        }
+    map.init(world, slot_cap, slot_counts);
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t       src;
+        uint64_t       kk;
+        const uint64_t i = map.index_of(c, src, kk);  // rid[] and the claimer's index stay in buffer coordinates
         const unsigned long long key = __ldcs(keys + i);
         const uint64_t           h   = table_hash_u64(key);
         uint32_t                 out = 0;
@@ -312,11 +352,14 @@ __global__ void __launch_bounds__(256) stream_count_kernel(const unsigned long l
 __global__ void __launch_bounds__(256) owner_reply_kernel(uint32_t* __restrict__ rid, uint64_t n, const uint32_t* __restrict__ bitmap, uint32_t world, uint32_t rank,
                                                           uint32_t* const* __restrict__ peer_reply, uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts,
                                                           uint32_t id_off) {
+    __shared__ SlotMap map;
+    map.init(world, peer_reply != nullptr ? slot_cap : 0, slot_counts);
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (peer_reply != nullptr) {
-        uint64_t src = i / slot_cap, k = i - src * slot_cap;
-        if (k >= __ldg(slot_counts + src)) return;
+        uint32_t src;
+        uint64_t k;
+        i            = map.index_of(i, src, k);
         uint32_t s   = rid[i];
         uint32_t gid = (s != 0 && ((__ldg(bitmap + ((s - 1) >> 5)) >> ((s - 1) & 31)) & 1u)) ? id_off + (s - 1) * world + rank + 1 : 0u;
         peer_reply[src][(uint64_t)rank * slot_cap + k] = gid;
@@ -435,8 +478,10 @@ __global__ void __launch_bounds__(256) owner_survivor_counts_kernel(const uint32
 
 // ---- sender side --------------------------------------------------------------------------------------------------------
 // id[p] = reply[rec_of_pos[p]]: inside every destination group the records are in corpus order, so this reads G ascending streams
-__global__ void __launch_bounds__(256) sender_relabel_kernel(const uint32_t* __restrict__ rec_of_pos, const uint32_t* __restrict__ reply, uint64_t npos, uint32_t* __restrict__ cur,
-                                                             DeviceStats* __restrict__ st, const uint32_t* __restrict__ dense_global, uint32_t threshold) {
+// list != NULL: item i is position list[i] and cur was zeroed by the host; only the positions with a surviving n-gram are written
+__global__ void __launch_bounds__(256) sender_relabel_kernel(const uint32_t* __restrict__ rec_of_pos, const uint32_t* __restrict__ reply, uint64_t npos /* items */,
+                                                             uint32_t* __restrict__ cur, DeviceStats* __restrict__ st, const uint32_t* __restrict__ dense_global, uint32_t threshold,
+                                                             const uint32_t* __restrict__ list) {
     __shared__ uint64_t scratch[8];
     uint32_t valid = 0;
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += (uint64_t)gridDim.x * blockDim.x) {
@@ -445,7 +490,8 @@ __global__ void __launch_bounds__(256) sender_relabel_kernel(const uint32_t* __r
         if (j == kNoRec) id = 0u;
         else if (j & kDenseRec) id = __ldg(dense_global + (j & ~kDenseRec)) >= threshold ? (j & ~kDenseRec) + 1u : 0u;  // the same verdict on every rank
         else id = __ldg(reply + j);
-        __stcs(cur + p, id);
+        if (list == nullptr) __stcs(cur + p, id);
+        else if (id != 0) cur[__ldg(list + p)] = id;
         valid += id != 0;
     }
     uint64_t v = block_reduce_sum(valid, scratch);
@@ -497,30 +543,33 @@ __global__ void __launch_bounds__(256) sender_survivors_kernel(const uint2* __re
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------------------------
-int launch_split_count(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, uint32_t* hist /* world x nblocks */, uint32_t dense, uint32_t* dense_cnt) {
+int launch_split_count(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, uint32_t* hist /* world x nblocks */, uint32_t dense, uint32_t* dense_cnt,
+                       const uint32_t* list) {
     uint32_t nblocks = sk_div_up(npos, kSplitTile);
-    split_count_kernel<<<nblocks, 256, 0, s>>>(prev, npos, world, nblocks, hist, dense, dense_cnt);
+    if (!nblocks) return 0;
+    split_count_kernel<<<nblocks, 256, 0, s>>>(prev, list, npos, world, nblocks, hist, dense, dense_cnt);
     return 1;
 }
 int launch_split_write(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint32_t world, const uint64_t* hist_off, void* send_keys, uint32_t* pos_of_rec, uint32_t* rec_of_pos,
-                       void* const* peer_keys, uint32_t my_rank, uint64_t slot_cap, uint32_t dense) {
+                       void* const* peer_keys, uint32_t my_rank, uint64_t slot_cap, uint32_t dense, const uint32_t* list) {
     uint32_t nblocks = sk_div_up(npos, kSplitTile);
-    split_write_kernel<<<nblocks, 256, 0, s>>>(prev, npos, world, nblocks, hist_off, (unsigned long long*)send_keys, pos_of_rec, rec_of_pos, (unsigned long long* const*)peer_keys,
+    if (!nblocks) return 0;
+    split_write_kernel<<<nblocks, 256, 0, s>>>(prev, list, npos, world, nblocks, hist_off, (unsigned long long*)send_keys, pos_of_rec, rec_of_pos, (unsigned long long* const*)peer_keys,
                                                 my_rank, slot_cap, dense);
     return 1;
 }
 int launch_stream_filter(cudaStream_t s, const void* keys, uint64_t n, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms, uint64_t slot_cap,
-                         const unsigned long long* slot_counts) {
+                         const unsigned long long* slot_counts, uint32_t world) {
     if (!n) return 0;
     unsigned grid = (unsigned)sk_min(sk_div_up(n, 256), (uint64_t)sms * 32);
-    stream_filter_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)keys, n, filter, nbuckets - 1, st, slot_cap, slot_counts);
+    stream_filter_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)keys, n, filter, nbuckets - 1, st, slot_cap, slot_counts, world);
     return 1;
 }
 int launch_stream_count(cudaStream_t s, const void* keys, uint64_t n, NgramSlot* table, uint64_t cap, const uint32_t* filter, uint64_t nbuckets, uint32_t* rid, DeviceStats* st, int sms,
-                        uint64_t slot_cap, const unsigned long long* slot_counts) {
+                        uint64_t slot_cap, const unsigned long long* slot_counts, uint32_t world) {
     if (!n) return 0;
     unsigned grid = (unsigned)sk_min(sk_div_up(n, 256), (uint64_t)sms * 32);
-    stream_count_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)keys, n, table, cap, filter, nbuckets ? nbuckets - 1 : 0, rid, st, slot_cap, slot_counts);
+    stream_count_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)keys, n, table, cap, filter, nbuckets ? nbuckets - 1 : 0, rid, st, slot_cap, slot_counts, world);
     return 1;
 }
 int launch_owner_reply(cudaStream_t s, uint32_t* rid, uint64_t n, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* const* peer_reply, uint64_t slot_cap,
@@ -554,9 +603,9 @@ int launch_owner_survivors(cudaStream_t s, const uint32_t* sv_idx, const uint32_
     return 1;
 }
 int launch_sender_relabel(cudaStream_t s, const uint32_t* rec_of_pos, const uint32_t* reply, uint64_t npos, uint32_t* cur, DeviceStats* st, int sms, const uint32_t* dense_global,
-                          uint32_t threshold) {
+                          uint32_t threshold, const uint32_t* list) {
     unsigned grid = (unsigned)sk_min(sk_div_up(npos, 256), (uint64_t)sms * 16);
-    sender_relabel_kernel<<<grid ? grid : 1, 256, 0, s>>>(rec_of_pos, reply, npos, cur, st, dense_global, threshold);
+    sender_relabel_kernel<<<grid ? grid : 1, 256, 0, s>>>(rec_of_pos, reply, npos, cur, st, dense_global, threshold, list);
     return 1;
 }
 int launch_dense_share(cudaStream_t s, const uint32_t* dense_global, uint32_t dense, uint32_t world, uint32_t rank, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_cnt,

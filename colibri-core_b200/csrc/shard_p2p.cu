@@ -53,8 +53,9 @@ extern "C" int colibri_b200_shard_p2p_split(colibri_b200_shard* sh, int n, uint6
     PhaseClock clk(sh, 3);
     cudaStream_t s = sh->s;
     if (sh->pos_of_rec.n < sh->nsent + 1) TRY(sh->pos_of_rec.alloc(sh->dev, sh->nsent + 1));
-    if (sh->rec_of_pos.n < sh->npos + 8) TRY(sh->rec_of_pos.alloc(sh->dev, sh->npos + 8));
-    sh->launches += launch_split_write(s, sh->prev.p, sh->npos, sh->world, sh->split_off.p, nullptr, sh->pos_of_rec.p, sh->rec_of_pos.p, sh->d_peer.p, sh->rank, sh->slot_cap, shard_dense_now(sh));
+    if (sh->rec_of_pos.n < shard_items(sh) + 8) TRY(sh->rec_of_pos.alloc(sh->dev, shard_items(sh) + 8));
+    sh->launches += launch_split_write(s, sh->prev.p, shard_items(sh), sh->world, sh->split_off.p, nullptr, sh->pos_of_rec.p, sh->rec_of_pos.p, sh->d_peer.p, sh->rank, sh->slot_cap, shard_dense_now(sh),
+                                       shard_list(sh));
     unsigned long long vals[64];
     for (uint32_t d = 0; d < sh->world; ++d) vals[d] = counts[d];
     CUDA_TRY(cudaMemcpyAsync(sh->d_vals.p, vals, sh->world * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
@@ -94,7 +95,7 @@ extern "C" int colibri_b200_shard_p2p_owner(colibri_b200_shard* sh, uint64_t sta
         if (sh->filter.n < nbuckets / 16) TRY(sh->filter.alloc(sh->dev, nbuckets / 16));
         CUDA_TRY(cudaMemsetAsync(sh->filter.p, 0, nbuckets / 4, s));
         TRY(shard_zero_stats(sh));
-        sh->launches += launch_stream_filter(s, keys, phys, sh->filter.p, nbuckets, sh->d_stats.p, sh->sms, sh->slot_cap, my_hdr);
+        sh->launches += launch_stream_filter(s, keys, nrecv, sh->filter.p, nbuckets, sh->d_stats.p, sh->sms, sh->slot_cap, my_hdr, G);
         TRY(shard_read_stats(sh));
         if (sh->h_stats.found * 8 <= nbuckets) cap = std::min(cap, std::max<uint64_t>(1024, 3 * sh->h_stats.found + 1024));  // (a saturated filter says nothing about the number of keys)
     }
@@ -105,7 +106,7 @@ extern "C" int colibri_b200_shard_p2p_owner(colibri_b200_shard* sh, uint64_t sta
         if (sh->owner_table.n < cap) TRY(sh->owner_table.alloc(sh->dev, cap));
         CUDA_TRY(cudaMemsetAsync(sh->owner_table.p, 0, cap * sizeof(NgramSlot), s));
         TRY(shard_zero_stats(sh));
-        sh->launches += launch_stream_count(s, keys, phys, sh->owner_table.p, cap, use_filter ? sh->filter.p : nullptr, nbuckets, sh->rid.p, sh->d_stats.p, sh->sms, sh->slot_cap, my_hdr);
+        sh->launches += launch_stream_count(s, keys, nrecv, sh->owner_table.p, cap, use_filter ? sh->filter.p : nullptr, nbuckets, sh->rid.p, sh->d_stats.p, sh->sms, sh->slot_cap, my_hdr, G);
         CUDA_TRY(cudaMemcpyAsync(&sh->h_stats, sh->d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (sh->h_stats.errflags & kErrTableFull) {
@@ -123,7 +124,7 @@ extern "C" int colibri_b200_shard_p2p_owner(colibri_b200_shard* sh, uint64_t sta
     if (sh->bitmap.n < cap / 32 + 8) TRY(sh->bitmap.alloc(sh->dev, cap / 32 + 8));
     TRY(shard_zero_stats(sh));
     sh->launches += launch_prune_ngrams(s, sh->owner_table.p, cap, t, sh->sv_idx.p, sh->sv_cnt.p, sh->bitmap.p, sh->d_stats.p, sh->sms);
-    sh->launches += launch_owner_reply(s, sh->rid.p, phys, sh->bitmap.p, G, sh->rank, sh->d_peer.p + 64, sh->slot_cap, my_hdr, shard_id_off(sh));  // ids -> the senders' reply slots
+    sh->launches += launch_owner_reply(s, sh->rid.p, nrecv, sh->bitmap.p, G, sh->rank, sh->d_peer.p + 64, sh->slot_cap, my_hdr, shard_id_off(sh));  // ids -> the senders' reply slots
     TRY(shard_read_stats(sh));
     stats[0]  = sh->h_stats.found + singles + sh->dense_stats[0];
     stats[1]  = sh->h_stats.kept + sh->dense_stats[1];
@@ -167,8 +168,9 @@ extern "C" int colibri_b200_shard_p2p_finish(colibri_b200_shard* sh, uint64_t gl
     const int n = sh->level + 1;
     TRY(shard_zero_stats(sh));
     CUDA_TRY(cudaMemsetAsync(sh->cur.p + sh->npos, 0, 8 * sizeof(uint32_t), s));
-    sh->launches += launch_sender_relabel(s, sh->rec_of_pos.p, (const uint32_t*)sh->h_reply_rx[sh->rank], sh->npos, sh->cur.p, sh->d_stats.p, sh->sms,
-                                          shard_dense_now(sh) ? sh->dense_cnt : nullptr, sh->t);
+    if (sh->list_valid) CUDA_TRY(cudaMemsetAsync(sh->cur.p, 0, sh->npos * sizeof(uint32_t), s));  // list mode writes only the positions that keep an id
+    sh->launches += launch_sender_relabel(s, sh->rec_of_pos.p, (const uint32_t*)sh->h_reply_rx[sh->rank], shard_items(sh), sh->cur.p, sh->d_stats.p, sh->sms,
+                                          shard_dense_now(sh) ? sh->dense_cnt : nullptr, sh->t, shard_list(sh));
     uint64_t total = 0;
     for (uint32_t g = 0; g < G; ++g) total += surv_counts[g];
     Segment sg;
@@ -196,6 +198,7 @@ extern "C" int colibri_b200_shard_p2p_finish(colibri_b200_shard* sh, uint64_t gl
     std::swap(sh->prev, sh->cur);
     sh->level = n;
     TRY(shard_keep_ids(sh, n));
+    TRY(shard_next_list(sh));
     return 0;
 }
 

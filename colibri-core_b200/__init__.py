@@ -143,6 +143,14 @@ def library():
     L.colibri_b200_shard_finish.argtypes = [C.c_void_p, _u64p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.colibri_b200_shard_free.argtypes = [C.c_void_p]
     L.colibri_b200_shard_free.restype = None
+    L.colibri_b200_rindex_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.colibri_b200_rindex_free.argtypes = [C.c_void_p]
+    L.colibri_b200_rindex_free.restype = None
+    L.colibri_b200_rindex_info.argtypes = [C.c_void_p, _u64p]
+    L.colibri_b200_rindex_lengths.argtypes = [C.c_void_p, _u32p, C.c_uint32, _u32p]
+    L.colibri_b200_rindex_sentence_starts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.colibri_b200_rindex_query.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.colibri_b200_rindex_cooc.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, _u64p]
     L.colibri_b200_hash64_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
     L.colibri_b200_synth_corpus.argtypes = [C.POINTER(CSynthParams), C.c_int, C.POINTER(C.c_void_p)]
     _lib = L
@@ -430,6 +438,58 @@ class Model:
     def close(self):
         if self._h:
             library().colibri_b200_model_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ReverseIndex:
+    """colibri_b200_rindex: a model's n-grams matched against every position of a corpus once; answers getreverseindex in batches and the
+    co-occurrence relations of all patterns (reference include/patternmodel.h:1746-1824, :3460-3531)."""
+
+    def __init__(self, model: Model, corpus: "Corpus", streamed: int = 0):
+        self._h = C.c_void_p()
+        self.model, self.corpus = model, corpus  # keep them alive
+        _check(library().colibri_b200_rindex_build(model._h, corpus._h, int(streamed), C.byref(self._h)))
+        out = (C.c_uint64 * 4)()
+        _check(library().colibri_b200_rindex_info(self._h, out))
+        self.sentences, self.positions = int(out[0]), int(out[1])
+        n = C.c_uint32()
+        buf = (C.c_uint32 * 256)()
+        _check(library().colibri_b200_rindex_lengths(self._h, buf, 256, C.byref(n)))
+        self.lengths = [int(buf[i]) for i in range(n.value)]
+
+    def sentence_starts(self) -> np.ndarray:
+        out = np.empty(self.sentences + 1, dtype=np.uint32)
+        _check(library().colibri_b200_rindex_sentence_starts(self._h, out.ctypes.data, out.size))
+        return out
+
+    def query(self, refs) -> np.ndarray:
+        """refs: iterable of (sentence, token), sentences from 1.  Returns u32[len(refs), len(self.lengths)]: pattern index + 1 in the model's export order, 0 = none."""
+        refs = list(refs)
+        s = np.ascontiguousarray([r[0] for r in refs], dtype=np.uint32)
+        t = np.ascontiguousarray([r[1] for r in refs], dtype=np.uint16)
+        out = np.zeros((len(refs), max(len(self.lengths), 1)), dtype=np.uint32)
+        if len(refs) and self.lengths:
+            _check(library().colibri_b200_rindex_query(self._h, s.ctypes.data, t.ctypes.data, len(refs), out.ctypes.data))
+        return out[:, :len(self.lengths)]
+
+    def cooc(self, left: bool = False):
+        """(index of P, index of Q, joint) of every getrightcooc / getleftcooc relation, as three arrays."""
+        n = C.c_uint64()
+        _check(library().colibri_b200_rindex_cooc(self._h, 1 if left else 0, None, None, None, 0, C.byref(n)))
+        p, q, j = np.empty(n.value, dtype=np.uint32), np.empty(n.value, dtype=np.uint32), np.empty(n.value, dtype=np.uint64)
+        if n.value:
+            _check(library().colibri_b200_rindex_cooc(self._h, 1 if left else 0, p.ctypes.data, q.ctypes.data, j.ctypes.data, n.value, C.byref(n)))
+        return p[:n.value], q[:n.value], j[:n.value]
+
+    def close(self):
+        if self._h:
+            library().colibri_b200_rindex_free(self._h)
             self._h = None
 
     def __del__(self):

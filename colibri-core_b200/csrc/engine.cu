@@ -468,6 +468,7 @@ struct Trainer {
     // phase 0: the whole call; 1: count this corpus into ext_counts only (a shard of a multi-GPU run); 2: threshold + compaction of
     // ext_counts (summed over the shards by the caller), corpus_tokens = ext_tokens.  Phases 1 and 2 are for unindexed models.
     int run_constrained(colibri_b200_model* cm, bool inplace, int phase = 0, uint32_t* ext_counts = nullptr, uint64_t ext_tokens = 0);
+    int build_rindex(colibri_b200_model* cm, colibri_b200_rindex* r);
 };
 
 int Trainer::prepare_index(const uint32_t* tok, uint64_t npos) {
@@ -1299,6 +1300,70 @@ int Trainer::run() {
 }
 
 
+// The reverse index of a model over a corpus (colibri_b200_rindex_build): the matching half of constrained training -- every window of every
+// length the model holds is looked up in the model's pattern index -- with all match arrays kept, plus the sentence tables of indexed models.
+int Trainer::build_rindex(colibri_b200_model* cm, colibri_b200_rindex* r) {
+    CUDA_TRY(cudaSetDevice(dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    timer.s   = s;
+    timer.dev = dev;
+    TRY(ensure_closure(cm, &launches));
+    uint64_t npos = 0;
+    uint32_t nclasses = 0;
+    TRY(tokenise(r->tok, npos, nclasses));
+    TRY(prepare_index(r->tok.p, npos));
+    r->npos        = npos;
+    r->nsentences  = npos - m->totaltokens;  // delimiters, the virtual one closing the last sentence included
+    r->sent_before = std::move(sent_before);
+    r->sent_start  = std::move(sent_start);
+    r->minn        = cm->minn;
+    r->maxn        = cm->maxn;
+    const uint64_t np = cm->npatterns;
+    for (int n = 1; n <= cm->maxn && n <= 255; ++n)
+        if (np && cm->meta.nhist[n]) r->lengths.push_back(n);
+    DevBuf<uint32_t> counts;  // the matching kernels count as they go; the counts are not wanted here
+    TRY(counts.alloc(dev, std::max<uint64_t>(np, 1)));
+    CUDA_TRY(cudaMemsetAsync(counts.p, 0, std::max<uint64_t>(np, 1) * sizeof(uint32_t), s));
+    r->match.resize(r->lengths.size());
+    for (auto& mb : r->match) {
+        TRY(mb.alloc(dev, npos + 8));
+        CUDA_TRY(cudaMemsetAsync(mb.p + npos, 0, 8 * sizeof(uint32_t), s));
+    }
+    TRY(zero_stats());
+    cm->index_counts_dirty = true;
+    const bool chain = !getenv("COLIBRI_B200_NO_CHAIN");
+    DevBuf<uint32_t> hist;
+    for (size_t k = 0; k < r->lengths.size(); ++k) {
+        const int       n    = r->lengths[k];
+        uint32_t*       cur  = r->match[k].p;
+        const uint32_t* prev = (k > 0 && r->lengths[k - 1] == n - 1 && chain) ? r->match[k - 1].p : nullptr;
+        const bool use_prefix = prev && cm->prefix_open[n] == 0, use_suffix = prev && cm->suffix_open[n] == 0;
+        if (n == 1 && cm->uni_classes) {
+            launches += launch_unigram_match(s, r->tok.p, npos, cm->d_uni.p, cm->uni_classes, cur);
+        } else {
+            launches += launch_constrained_match(s, r->tok.p, npos, n, cm->d_keys.p, cm->d_off.p, cm->d_index.p, cm->index_cap, cm->d_presence.p, cm->presence_bits, counts.p, cur, prev,
+                                                 use_prefix, use_suffix, d_stats.p, sms);
+        }
+    }
+    launches += launch_collect_slot_counts(s, cm->d_index.p, cm->index_cap, counts.p);
+    TRY(read_stats());
+    cm->index_counts_dirty = false;
+    std::vector<const uint32_t*> ptrs;
+    std::vector<uint32_t>        lens;
+    for (size_t k = 0; k < r->lengths.size(); ++k) {
+        ptrs.push_back(r->match[k].p);
+        lens.push_back((uint32_t)r->lengths[k]);
+    }
+    TRY(r->d_match_ptrs.alloc(dev, std::max<size_t>(ptrs.size(), 1)));
+    TRY(r->d_lengths.alloc(dev, std::max<size_t>(lens.size(), 1)));
+    if (!ptrs.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(r->d_match_ptrs.p, ptrs.data(), ptrs.size() * sizeof(uint32_t*), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(r->d_lengths.p, lens.data(), lens.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
 // PatternModel::train with constrainbymodel != NULL (reference include/patternmodel.h:880-1345): ONE scan of the corpus that extracts every
 // window of MINLENGTH..MAXLENGTH tokens (:1064-1072) and counts it iff the constraint model has it (:1088-1089); then prune(MINTOKENS, 0)
 // (:1211-1218) and stop (:1246-1247).  Here: one launch per pattern length that the constraint set actually holds; the window's varint bytes
@@ -1783,6 +1848,55 @@ extern "C" int colibri_b200_train_export(const uint8_t* host_body, size_t nbytes
     g_trace.mark("free");
     g_trace.dump("train_export");
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ reverse index (queries: relations.cu)
+extern "C" int colibri_b200_rindex_build(colibri_b200_model* model, colibri_b200_corpus* corpus, int streamed, colibri_b200_rindex** out) {
+    if (!out) return set_err(COLIBRI_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!model || !corpus) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    if (model->device != corpus->device) return set_err(COLIBRI_E_INVALID, "model on device %d, corpus on device %d", model->device, corpus->device);
+    colibri_b200_options o;
+    colibri_b200_options_default(&o);
+    o.MINTOKENS = 1;
+    o.MAXLENGTH = std::max(model->maxn, 1);
+    o.streamed  = streamed;
+    o.device    = model->device;
+    o.model_type = COLIBRI_INDEXEDPATTERNMODEL;
+    colibri_b200_model* scratch = nullptr;  // the tokeniser reports into a model handle
+    TRY(new_model(model->device, COLIBRI_INDEXEDPATTERNMODEL, &scratch));
+    auto* r   = new colibri_b200_rindex();
+    r->device = model->device;
+    r->model  = model;
+    r->stream = model->stream;
+    int rc;
+    {
+        Trainer tr;
+        tr.c = corpus; tr.o = o; tr.m = scratch; tr.s = model->stream; tr.dev = model->device;
+        rc = tr.build_rindex(model, r);
+        if (rc) cudaStreamSynchronize(model->stream);
+    }
+    colibri_b200_model_free(scratch);
+    if (rc) {
+        delete r;
+        return rc;
+    }
+    *out = r;
+    return 0;
+}
+extern "C" void colibri_b200_rindex_free(colibri_b200_rindex* r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    cudaStreamSynchronize(r->stream);
+    delete r;
+}
+extern "C" int colibri_b200_rindex_info(const colibri_b200_rindex* r, uint64_t out[4]) {
+    if (!r || !out) return set_err(COLIBRI_E_INVALID, "NULL argument");
+    out[0] = r->nsentences;
+    out[1] = r->npos;
+    out[2] = r->lengths.empty() ? 0 : (uint64_t)r->lengths.front();
+    out[3] = r->lengths.empty() ? 0 : (uint64_t)r->lengths.back();
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ export / lookup

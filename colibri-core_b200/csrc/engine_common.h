@@ -364,6 +364,24 @@ struct colibri_b200_model {
     cudaStream_t stream = nullptr;
 };
 
+// ------------------------------------------------------------------------------------------------ reverse index of a model over a corpus
+// What IndexedPatternModel::getreverseindex (include/patternmodel.h:1746-1824) answers one position at a time, for the whole corpus at once:
+// match[k][p] = (index + 1) of the model's n-gram of lengths[k] tokens that starts at position p, 0 if there is none.
+struct colibri_b200_rindex {
+    int                            device = 0;
+    colibri_b200_model*            model = nullptr;  // not owned; must outlive the index
+    cudaStream_t                   stream = nullptr;
+    uint64_t                       npos = 0, nsentences = 0;
+    int                            minn = 0, maxn = 0;
+    std::vector<int>               lengths;
+    std::vector<DevBuf<uint32_t>>  match;
+    DevBuf<uint32_t>               tok;
+    DevBuf<uint64_t>               sent_before;  // delimiters in tok[0..p)
+    DevBuf<uint32_t>               sent_start;   // first position of sentence k (0-based); sent_start[nsentences] = one past the last delimiter
+    DevBuf<const uint32_t*>        d_match_ptrs;
+    DevBuf<uint32_t>               d_lengths;
+};
+
 namespace colibri {
 // survivors of all levels -> the flat device-resident export of the model (engine.cu)
 int export_segments(int dev, cudaStream_t s, std::vector<Segment>& segs, const uint32_t* tok, colibri_b200_model* m, uint64_t& launches);

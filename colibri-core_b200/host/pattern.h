@@ -28,6 +28,12 @@ class KeyError : public std::exception {  // reference include/common.h:46-49
 
 enum PatternCategory { UNKNOWNPATTERN = 0, NGRAM = 1, SKIPGRAM = 2, FLEXGRAM = 3, SKIPGRAMORFLEXGRAM = 4 };
 
+/// thrown by queries about a pattern the model does not hold (reference include/common.h)
+class NoSuchPattern : public std::exception {
+  public:
+    const char* what() const noexcept override { return "Colibri FATAL ERROR: No such pattern"; }
+};
+
 class Pattern {
     std::string bytes_;
 

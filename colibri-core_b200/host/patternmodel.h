@@ -14,11 +14,14 @@
 // implementation behind this header: option combinations outside the accelerated subset throw, they do not fall back.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <istream>
 #include <iterator>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -574,4 +577,179 @@ class IndexedPatternModel : public DevicePatternModel<IndexedData, INDEXEDPATTER
         : DevicePatternModel<IndexedData, INDEXEDPATTERNMODEL>(filename, options, constrainmodel, corpus) {}
     IndexedPatternModel(std::istream& f, const PatternModelOptions& options, PatternModelInterface* constrainmodel = nullptr, IndexedCorpus* corpus = nullptr)
         : DevicePatternModel<IndexedData, INDEXEDPATTERNMODEL>(f, options, constrainmodel, corpus) {}
+    ~IndexedPatternModel() { drop_rindex(); }
+
+    typedef std::map<Pattern, uint64_t> t_relationmap;  // reference include/patternmodel.h:2650 (unordered there; ordered here for stable output)
+
+    /// The model's patterns that begin at a corpus position (reference include/patternmodel.h:1746-1824; n-grams).  The reverse index is built
+    /// on the device on first use: every window of the corpus is matched against the model once (colibri_b200_rindex_build).
+    std::vector<Pattern> getreverseindex(const IndexReference ref, int occurrencecount = 0, int category = 0, unsigned int size = 0) {
+        ensure_rindex();
+        std::vector<uint32_t> row(rlengths_.size(), 0);
+        if (!row.empty() && colibri_b200_rindex_query(rindex_, &ref.sentence, &ref.token, 1, row.data()) != COLIBRI_OK) colibri_b200_detail::fail(colibri_b200_last_error());
+        std::vector<Pattern> out;
+        for (size_t k = 0; k < row.size(); ++k) {
+            if (!row[k]) continue;
+            if (size && rlengths_[k] != size) continue;
+            if (category && category != NGRAM) continue;
+            if (occurrencecount && counts_[row[k] - 1] < (uint32_t)occurrencecount) continue;
+            out.push_back(pattern_at(row[k] - 1));
+        }
+        return out;
+    }
+    /// getrightcooc / getleftcooc (reference :3460-3493, :3502-3531) with the reference's arithmetic -- see include/colibri_b200.h, colibri_b200_rindex_cooc.
+    t_relationmap getrightcooc(const Pattern& pattern, unsigned int occurrencethreshold = 0, int category = 0, unsigned int size = 0) { return cooc_of(pattern, 0, occurrencethreshold, category, size); }
+    t_relationmap getleftcooc(const Pattern& pattern, unsigned int occurrencethreshold = 0, int category = 0, unsigned int size = 0) { return cooc_of(pattern, 1, occurrencethreshold, category, size); }
+    /// reference :3582-3585, the same expression (the product of the two counts is an unsigned 32-bit product there too)
+    double npmi(const Pattern& key1, const Pattern& key2, int jointcount) {
+        return log((double)jointcount / ((unsigned int)this->occurrencecount(key1) * (unsigned int)this->occurrencecount(key2))) / -log((double)jointcount / (double)totaloccurrences());
+    }
+    uint64_t totaloccurrences() const {  // totaloccurrencesingroup(0, 0)
+        uint64_t t = 0;
+        for (uint32_t c : counts_) t += c;
+        return t;
+    }
+    /// computeflexgrams_fromcooc (reference :3751-3774) over the patterns the model holds when it is called: P {**} Q for every right co-occurrence
+    /// whose npmi passes; every match of getrightcooc(P) adds its reference to each of P's flexgrams.  Returns the number of flexgrams found.
+    int computeflexgrams_fromcooc(double threshold) {
+        ensure_rindex();
+        load_cooc(0);
+        const uint64_t total = totaloccurrences();
+        std::vector<std::string>                 newkeys;
+        std::vector<std::vector<IndexReference>> newrefs;
+        size_t i = 0;
+        while (i < cooc_[0].size()) {
+            size_t j = i;
+            while (j < cooc_[0].size() && cooc_[0][j].p == cooc_[0][i].p) ++j;
+            const uint32_t p = cooc_[0][i].p;
+            std::vector<uint32_t> passing;
+            for (size_t k = i; k < j; ++k) {
+                const double v = log((double)cooc_[0][k].joint / (counts_[p] * counts_[cooc_[0][k].q])) / -log((double)cooc_[0][k].joint / (double)total);
+                if (v >= threshold) passing.push_back(cooc_[0][k].q);
+            }
+            if (!passing.empty()) {
+                // the matches of P: per occurrence, one per (position right of the pattern) x (pattern that starts at the occurrence)
+                const uint64_t nocc = ref_off_[p + 1] - ref_off_[p];
+                std::vector<uint32_t> rows(nocc * rlengths_.size(), 0);
+                if (nocc && colibri_b200_rindex_query(rindex_, ref_sentence_.data() + ref_off_[p], ref_token_.data() + ref_off_[p], nocc, rows.data()) != COLIBRI_OK)
+                    colibri_b200_detail::fail(colibri_b200_last_error());
+                const unsigned int n = pattern_at(p).n();
+                std::vector<IndexReference> plist;
+                for (uint64_t o = 0; o < nocc; ++o) {
+                    const uint32_t s = ref_sentence_[ref_off_[p] + o];
+                    const uint16_t t = ref_token_[ref_off_[p] + o];
+                    const int64_t  sl = (int64_t)sent_start_[s] - 1 - (int64_t)sent_start_[s - 1];
+                    const int64_t  w  = sl - 1 - ((int64_t)t + n);
+                    uint64_t here = 0;
+                    for (size_t k = 0; k < rlengths_.size(); ++k) here += rows[o * rlengths_.size() + k] != 0;
+                    for (int64_t r = 0; w > 0 && r < w * (int64_t)here; ++r) plist.push_back(IndexReference(s, t));
+                }
+                for (uint32_t q : passing) {
+                    std::string k(reinterpret_cast<const char*>(keys_.data() + off_[p]), off_[p + 1] - off_[p]);
+                    k.push_back((char)Pattern::flexclass);
+                    k.append(reinterpret_cast<const char*>(keys_.data() + off_[q]), off_[q + 1] - off_[q]);
+                    newkeys.push_back(k);
+                    newrefs.push_back(plist);
+                }
+            }
+            i = j;
+        }
+        if (newkeys.empty()) return 0;
+        const size_t np0 = counts_.size();
+        keys_.resize(off_[np0]);
+        ref_sentence_.resize(ref_off_[np0]);
+        ref_token_.resize(ref_off_[np0]);
+        for (size_t f = 0; f < newkeys.size(); ++f) {
+            keys_.insert(keys_.end(), newkeys[f].begin(), newkeys[f].end());
+            off_.push_back(keys_.size());
+            counts_.push_back((uint32_t)newrefs[f].size());
+            for (const auto& r : newrefs[f]) {
+                ref_sentence_.push_back(r.sentence);
+                ref_token_.push_back(r.token);
+            }
+            ref_off_.push_back(ref_sentence_.size());
+        }
+        keys_.push_back(0);
+        this->map_.clear();
+        this->map_ready_ = false;
+        this->hasflexgrams = true;
+        drop_rindex();
+        return (int)newkeys.size();
+    }
+
+  private:
+    struct Rel { uint32_t p, q; uint64_t joint; };
+    colibri_b200_rindex* rindex_ = nullptr;
+    colibri_b200_model*  rmodel_ = nullptr;
+    colibri_b200_corpus* rcorpus_ = nullptr;
+    std::vector<uint32_t> rlengths_, sent_start_;
+    std::vector<Rel>      cooc_[2];
+    bool                  cooc_ready_[2] = {false, false};
+
+    Pattern pattern_at(uint64_t i) const { return Pattern(keys_.data() + off_[i], (int)(off_[i + 1] - off_[i])); }
+    void drop_rindex() {
+        colibri_b200_rindex_free(rindex_);
+        colibri_b200_model_free(rmodel_);
+        colibri_b200_corpus_free(rcorpus_);
+        rindex_ = nullptr; rmodel_ = nullptr; rcorpus_ = nullptr;
+        cooc_ready_[0] = cooc_ready_[1] = false;
+    }
+    void ensure_rindex() {
+        using colibri_b200_detail::fail;
+        if (rindex_ != nullptr) return;
+        if (this->reverseindex == nullptr) {
+            std::cerr << "ERROR: No reverse index present" << std::endl;
+            throw InternalError();
+        }
+        const int      dev  = colibri_b200_detail::default_device();
+        const uint64_t zero = 0;
+        const bool     any  = !counts_.empty();
+        if (colibri_b200_model_from_flat(keys_.data(), any ? off_.data() : &zero, counts_.data(), counts_.size(), ref_sentence_.data(), ref_token_.data(), any ? ref_off_.data() : &zero,
+                                         totaltokens, totaltypes, INDEXEDPATTERNMODEL, dev, &rmodel_) != COLIBRI_OK)
+            fail(colibri_b200_last_error());
+        if (colibri_b200_corpus_stage(this->reverseindex->beginpointer(), this->reverseindex->bytesize(), dev, &rcorpus_) != COLIBRI_OK) fail(colibri_b200_last_error());
+        if (colibri_b200_rindex_build(rmodel_, rcorpus_, 0, &rindex_) != COLIBRI_OK) fail(colibri_b200_last_error());
+        uint32_t n = 0, buf[256];
+        if (colibri_b200_rindex_lengths(rindex_, buf, 256, &n) != COLIBRI_OK) fail(colibri_b200_last_error());
+        rlengths_.assign(buf, buf + n);
+        uint64_t info[4];
+        if (colibri_b200_rindex_info(rindex_, info) != COLIBRI_OK) fail(colibri_b200_last_error());
+        sent_start_.assign(info[0] + 1, 0);
+        if (colibri_b200_rindex_sentence_starts(rindex_, sent_start_.data(), sent_start_.size()) != COLIBRI_OK) fail(colibri_b200_last_error());
+    }
+    void load_cooc(int direction) {
+        using colibri_b200_detail::fail;
+        ensure_rindex();
+        if (cooc_ready_[direction]) return;
+        uint64_t n = 0;
+        if (colibri_b200_rindex_cooc(rindex_, direction, nullptr, nullptr, nullptr, 0, &n) != COLIBRI_OK) fail(colibri_b200_last_error());
+        std::vector<uint32_t> p(n + 1), q(n + 1);
+        std::vector<uint64_t> j(n + 1);
+        if (n && colibri_b200_rindex_cooc(rindex_, direction, p.data(), q.data(), j.data(), n, &n) != COLIBRI_OK) fail(colibri_b200_last_error());
+        cooc_[direction].resize(n);
+        for (uint64_t i = 0; i < n; ++i) cooc_[direction][i] = Rel{p[i], q[i], j[i]};
+        std::sort(cooc_[direction].begin(), cooc_[direction].end(), [](const Rel& a, const Rel& b) { return a.p < b.p || (a.p == b.p && a.q < b.q); });
+        cooc_ready_[direction] = true;
+    }
+    t_relationmap cooc_of(const Pattern& pattern, int direction, unsigned int occurrencethreshold, int category, unsigned int size) {
+        load_cooc(direction);
+        if (!this->has(pattern)) throw NoSuchPattern();
+        // the pattern's index in the flat arrays
+        uint64_t idx = counts_.size();
+        for (uint64_t i = 0; i < counts_.size(); ++i)
+            if (off_[i + 1] - off_[i] == pattern.bytesize() && memcmp(keys_.data() + off_[i], pattern.data(), pattern.bytesize()) == 0) {
+                idx = i;
+                break;
+            }
+        t_relationmap out;
+        auto lo = std::lower_bound(cooc_[direction].begin(), cooc_[direction].end(), (uint32_t)idx, [](const Rel& a, uint32_t v) { return a.p < v; });
+        for (; lo != cooc_[direction].end() && lo->p == idx; ++lo) {
+            const Pattern q = pattern_at(lo->q);
+            if (occurrencethreshold && (counts_[lo->q] < occurrencethreshold || lo->joint < occurrencethreshold)) continue;
+            if (category && (int)q.category() != category) continue;
+            if (size && q.n() != size) continue;
+            out[q] = lo->joint;
+        }
+        return out;
+    }
 };

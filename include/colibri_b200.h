@@ -137,6 +137,29 @@ int colibri_b200_model_lookup(colibri_b200_model* m, const uint8_t* key, uint32_
  * key_off[n+1]; counts[i] = 0 and index[i] = -1 when pattern i is absent, else its position in the export order.  Either output may be NULL. */
 int colibri_b200_model_lookup_batch(colibri_b200_model* m, const uint8_t* keys, const uint64_t* key_off, uint64_t n, uint32_t* counts, int64_t* index);
 
+/* ---- the reverse index of a model over a corpus, and the relations computed from it */
+typedef struct colibri_b200_rindex colibri_b200_rindex;
+/* Replaces the ReverseIndex / IndexedCorpus argument of IndexedPatternModel (include/patternmodel.h:2681-2720) for the queries below: every window of
+ * every length the model holds is matched against the model once (the kernels of constrained training), so that getreverseindex
+ * (:1746-1824) becomes a gather.  n-grams only: a model with skipgrams or flexgrams answers for its n-grams.  `streamed` as in
+ * the options struct (the sentence source).  The model and the corpus must stay alive while the index is used. */
+int  colibri_b200_rindex_build(colibri_b200_model* model, colibri_b200_corpus* corpus, int streamed, colibri_b200_rindex** out);
+void colibri_b200_rindex_free(colibri_b200_rindex* r);
+/* out[0] = sentences (IndexedCorpus::sentences()), out[1] = positions (tokens + delimiters), out[2], out[3] = shortest / longest n-gram length indexed */
+int  colibri_b200_rindex_info(const colibri_b200_rindex* r, uint64_t out[4]);
+/* the n-gram lengths the index holds, ascending: column k of a query answer is the pattern of lengths[k] tokens */
+int  colibri_b200_rindex_lengths(const colibri_b200_rindex* r, uint32_t* lengths, uint32_t cap, uint32_t* n);
+/* out[k] = position of the first token of sentence k + 1 (k = 0 .. sentences); sentence k + 1 has out[k + 1] - out[k] - 1 tokens (IndexedCorpus::sentencelength) */
+int  colibri_b200_rindex_sentence_starts(const colibri_b200_rindex* r, uint32_t* out, uint64_t cap);
+/* getreverseindex(IndexReference(sentence, token)) for nq references at once (sentences count from 1, tokens from 0): out[q * nlengths + k] = index + 1
+ * (export order of the model) of the model's n-gram of lengths[k] tokens that starts there, 0 if none -- also for a reference outside its sentence. */
+int  colibri_b200_rindex_query(colibri_b200_rindex* r, const uint32_t* sentence, const uint16_t* token, uint64_t nq, uint32_t* out);
+/* getrightcooc (direction 0, :3460-3493) / getleftcooc (direction 1, :3502-3531) of EVERY pattern, with the reference's arithmetic: its
+ * getreverseindex_right / _left (:1867-1878, :1885-1892) look each neighbouring position up at the original reference, so a relation (P, Q) joins two
+ * model patterns that start at the same position (s, t), which adds max(0, sl - 1 - (t + |P|)) (right) or max(0, t - |Q|) (left) to joint(P, Q).
+ * *nrel = relations found; when the three buffers are given (cap entries each) they receive (index of P, index of Q, joint) in no particular order. */
+int  colibri_b200_rindex_cooc(colibri_b200_rindex* r, int direction, uint32_t* idx_p, uint32_t* idx_q, uint64_t* joint, uint64_t cap, uint64_t* nrel);
+
 /* ---- models that do not come out of train() */
 /* a pattern set given as flat host arrays (the export form) becomes a device-resident model: replaces building a PatternModel /
  * PatternSetModel by insert() (include/patternstore.h:520, include/patternmodel.h:296-470).  counts and the three ref arrays may be NULL. */

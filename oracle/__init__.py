@@ -530,3 +530,105 @@ def parse_ref_passes(stderr: str):
             sk, pr, extra, kept = m.groups()
             out.append((0, int(sk), int(pr) + (int(extra) if extra else 0), int(kept)))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Relations on an indexed model: restatement of the reference's getreverseindex, getrightcooc, getleftcooc,
+# npmi, computenpmi and computeflexgrams_fromcooc.  Pure Python (small cases only); pinned to the unmodified reference through
+# oracle/ref_relations.cpp (tests/golden/make_golden_relations.py, tests/test_oracle_relations.py).
+def corpus_sentences(body) -> list:
+    """Sentences of a class-encoded corpus as lists of token byte strings, the way IndexedCorpus sees them (preloaded source:
+    a missing final delimiter still closes the last sentence; empty sentences are kept and numbered)."""
+    b = bytes(_as_u8(body).tobytes()) if not isinstance(body, (bytes, bytearray)) else bytes(body)
+    sentences, cur, tok = [], [], bytearray()
+    for x in b:
+        if x >= 128:
+            tok.append(x)
+        elif x == 0 and not tok:
+            sentences.append(cur)
+            cur = []
+        else:
+            tok.append(x)
+            cur.append(bytes(tok))
+            tok = bytearray()
+    if cur or tok:
+        sentences.append(cur)
+    return sentences
+
+
+def reverse_index(body, patterns: dict, minn: int | None = None, maxn: int | None = None) -> dict:
+    """getreverseindex for every position (include/patternmodel.h:1746-1824), n-grams: {(sentence, token): [pattern bytes, by length]}.
+    patterns: {pattern bytes: count} (n-grams); sentences count from 1."""
+    ntok = {k: len(_split_tokens(k)) for k in patterns}
+    if minn is None:
+        minn = min(ntok.values()) if ntok else 1
+    if maxn is None:
+        maxn = max(ntok.values()) if ntok else 0
+    out = {}
+    for s, sent in enumerate(corpus_sentences(body), start=1):
+        for t in range(len(sent)):
+            found = []
+            n = minn
+            while t + n <= len(sent) and n <= maxn:
+                key = b"".join(sent[t:t + n])
+                if key in patterns:
+                    found.append(key)
+                n += 1
+            out[(s, t)] = found
+    return out
+
+
+def _split_tokens(key: bytes) -> list:
+    toks, cur = [], bytearray()
+    for x in key:
+        cur.append(x)
+        if x < 128:
+            toks.append(bytes(cur))
+            cur = bytearray()
+    return toks
+
+
+def cooc(body, patterns: dict, left: bool = False) -> dict:
+    """getrightcooc / getleftcooc of every pattern as the reference computes them (:3460-3493, :3502-3531): getreverseindex_right / _left
+    (:1867-1878, :1885-1892) call getreverseindex(ref, ...) with the ORIGINAL reference for every neighbouring position ref2, so the
+    neighbours reported at ref2 are the patterns that start at ref itself.  Returns {(P, Q): joint}."""
+    rindex = reverse_index(body, patterns)
+    sents = corpus_sentences(body)
+    out = {}
+    for (s, t), here in rindex.items():
+        sl = len(sents[s - 1])
+        for P in here:  # every occurrence (s, t) of P: the model's occurrence list is the set of positions where the window is P
+            nP = len(_split_tokens(P))
+            for Q in here:
+                nQ = len(_split_tokens(Q))
+                if left:
+                    w = sum(1 for i in range(0, t) if i + nQ < t)  # ref2.token + n(neighbour) < ref.token
+                else:
+                    w = sum(1 for i in range(t + 1, sl) if i > t + nP)  # ref2.token > ref.token + n(pattern)
+                if w:
+                    out[(P, Q)] = out.get((P, Q), 0) + w
+    return out
+
+
+def npmi(count1: int, count2: int, joint: int, total: int) -> float:
+    """PatternModel::npmi (:3582-3585), the same expression in the same order (the product is an unsigned 32-bit product in the reference)."""
+    import math
+
+    prod = (count1 * count2) & 0xFFFFFFFF
+    return math.log(joint / prod) / -math.log(joint / total)
+
+
+def flexgrams_fromcooc(body, patterns: dict, threshold: float) -> tuple:
+    """computeflexgrams_fromcooc (:3751-3774) with a clean iteration over the patterns the model held before the call (the reference inserts
+    into the map it iterates over).  Every match (ref, ref2) of getrightcooc(P) adds ref to EVERY flexgram P {*} Q whose npmi passes, so a
+    flexgram's occurrence count is the number of matches of P.  Returns (found, {flexgram bytes: occurrence count})."""
+    right = cooc(body, patterns, left=False)
+    total = sum(patterns.values())
+    matches = {}
+    for (P, _Q), j in right.items():
+        matches[P] = matches.get(P, 0) + j
+    flex = {}
+    for (P, Q), j in right.items():
+        if npmi(patterns[P], patterns[Q], j, total) >= threshold:
+            flex[P + b"\x04" + Q] = matches[P]
+    return len(flex), flex

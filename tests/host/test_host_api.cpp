@@ -61,6 +61,28 @@ int main(int argc, char** argv) {
     if (argc > 1) {
         IndexedCorpus corpus{std::string(argv[1])};
         test("IndexedCorpus sentences (hamlet)", corpus.sentences(), 40u);  // reference src/test.cpp:1549
+        if (colibri_b200_device_count() > 0) {
+            // reverse index + co-occurrence relations of the indexed model (answers of the unmodified reference, oracle/_ref/ref_relations -t 2 -l 3)
+            PatternModelOptions ro;
+            ro.QUIET     = true;
+            ro.MINTOKENS = 2;
+            ro.MAXLENGTH = 3;
+            IndexedPatternModel<> im(&corpus);
+            im.train((std::istream*)nullptr, ro);
+            test("indexed model patterns (hamlet -t 2 -l 3)", im.size(), (size_t)81);
+            std::vector<Pattern> at = im.getreverseindex(IndexReference(1, 2));
+            test("getreverseindex((1, 2)) patterns", at.size(), (size_t)3);  // 0e, 0e0c, 0e0c07
+            test("getreverseindex outside the sentence", im.getreverseindex(IndexReference(1, 9999)).size(), (size_t)0);
+            Pattern six = Pattern::fromclasses({6});
+            auto    lc  = im.getleftcooc(six);
+            test("getleftcooc([06]) relations", lc.size(), (size_t)4);
+            test("getleftcooc([06])[06]", (unsigned long long)lc[six], 165ull);
+            test("getleftcooc([06])[06 07]", (unsigned long long)lc[Pattern::fromclasses({6, 7})], 12ull);
+            const size_t before = im.size();
+            int          found  = im.computeflexgrams_fromcooc(0.1);
+            test("computeflexgrams_fromcooc(0.1) found", found, 43);  // the clean iteration; the reference's own run adds one flexgram of a flexgram
+            test("model grew by the flexgrams", im.size(), before + 43);
+        }
         // without a GPU train() must throw InternalError, never compute on the CPU
         if (colibri_b200_device_count() == 0) {
             PatternModel<uint32_t> model;

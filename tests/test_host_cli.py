@@ -82,6 +82,13 @@ from conftest import constrained_case_id, corpus_body, load_constrained_cases  #
 CONSTRAINED_CLI_CASES = [c for c in load_constrained_cases() if c["corpus"] in ("hamlet", "republic") and c["stage1_corpus"] in ("hamlet", "republic")]
 
 
+@pytest.mark.gpu
+def test_host_api_mirror_cpp_on_gpu(cli, tmp_path):
+    """The same program on a GPU box: it also trains an IndexedPatternModel and checks getreverseindex / getleftcooc / computeflexgrams_fromcooc of the
+    C++ mirror against answers of the unmodified reference (oracle/_ref/ref_relations on hamlet, -t 2 -l 3)."""
+    test_host_api_mirror_cpp(cli, tmp_path)
+
+
 def test_cli_constrained_refusals(cli, tmp_path):
     hamlet = os.path.join(GOLDEN_DIR, "hamlet.colibri.dat")
     out = str(tmp_path / "m")

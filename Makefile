@@ -39,6 +39,10 @@ $(LIBDIR)/relations.o: $(CSRC)/relations.cu $(CSRC)/kernels.h $(CSRC)/engine_com
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/relations.ptxas.log || (cat $(LIBDIR)/relations.ptxas.log; false)
 
+$(LIBDIR)/shard_multi.o: $(CSRC)/shard_multi.cu $(CSRC)/shard.h $(CSRC)/kernels.h $(CSRC)/engine_common.h include/colibri_b200.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/shard_multi.ptxas.log || (cat $(LIBDIR)/shard_multi.ptxas.log; false)
+
 $(LIBDIR)/index.o: $(CSRC)/index.cu $(CSRC)/kernels.h $(CSRC)/device_utils.cuh
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/index.ptxas.log || (cat $(LIBDIR)/index.ptxas.log; false)
@@ -59,7 +63,7 @@ $(LIBDIR)/model_io.o: $(CSRC)/model_io.cu $(CSRC)/kernels.h $(CSRC)/engine_commo
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/model_io.ptxas.log || (cat $(LIBDIR)/model_io.ptxas.log; false)
 
-$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o $(LIBDIR)/shard_p2p.o $(LIBDIR)/partition.o $(LIBDIR)/relations.o $(LIBDIR)/index.o $(LIBDIR)/shard_kernels.o $(LIBDIR)/pattern_index.o $(LIBDIR)/model_io.o $(LIBDIR)/flexgrams.o
+$(LIB): $(LIBDIR)/kernels.o $(LIBDIR)/engine.o $(LIBDIR)/shard.o $(LIBDIR)/shard_p2p.o $(LIBDIR)/shard_multi.o $(LIBDIR)/partition.o $(LIBDIR)/relations.o $(LIBDIR)/index.o $(LIBDIR)/shard_kernels.o $(LIBDIR)/pattern_index.o $(LIBDIR)/model_io.o $(LIBDIR)/flexgrams.o
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^
 
 oracle:

@@ -143,6 +143,7 @@ def library():
     L.colibri_b200_shard_finish.argtypes = [C.c_void_p, _u64p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.colibri_b200_shard_free.argtypes = [C.c_void_p]
     L.colibri_b200_shard_free.restype = None
+    L.colibri_b200_train_multi.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(COptions), C.c_void_p, C.c_int, C.c_void_p]
     L.colibri_b200_rindex_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     L.colibri_b200_rindex_free.argtypes = [C.c_void_p]
     L.colibri_b200_rindex_free.restype = None
@@ -445,6 +446,16 @@ class Model:
             self.close()
         except Exception:
             pass
+
+
+def train_multi(body, devices, options: PatternModelOptions | None = None, **kw):
+    """colibri_b200_train_multi: one process, one host thread per GPU.  Returns the list of the devices' shares (Model objects)."""
+    o = options if options is not None else PatternModelOptions(**kw)
+    a = np.ascontiguousarray(np.frombuffer(bytes(body), dtype=np.uint8) if not isinstance(body, np.ndarray) else body, dtype=np.uint8)
+    devs = (C.c_int * len(devices))(*devices)
+    outs = (C.c_void_p * len(devices))()
+    _check(library().colibri_b200_train_multi(a.ctypes.data if a.size else None, a.size, C.byref(o._c), devs, len(devices), outs))
+    return [Model(C.c_void_p(h)) for h in outs]
 
 
 class ReverseIndex:

@@ -145,6 +145,10 @@ inline int& default_device() {  // CUDA device the next train() call uses (the r
     static int device = 0;
     return device;
 }
+inline std::vector<int>& device_list() {  // more than one entry: train() shards the corpus over these GPUs (colibri_b200_train_multi; CLI -d 0-7)
+    static std::vector<int> devices;
+    return devices;
+}
 inline void fail(const std::string& msg) {
     std::cerr << "ERROR: " << msg << std::endl;
     throw InternalError();
@@ -300,7 +304,16 @@ class DevicePatternModel : public PatternModelInterface {
         const int mintokens      = options.MINTOKENS == -1 ? 2 : (options.MINTOKENS == 0 ? 1 : options.MINTOKENS);
         if (!options.QUIET) std::cerr << "Training patternmodel, occurrence threshold: " << mintokens << std::endl;  // reference :922-931
         colibri_b200_detail::ModelHandle mh;
-        if (colibri_b200_train(body, nbytes, &o, &mh.h) != COLIBRI_OK) fail(colibri_b200_last_error());
+        const std::vector<int>&          devs = colibri_b200_detail::device_list();
+        std::vector<colibri_b200_model*> shares;
+        if (devs.size() > 1) {
+            // several GPUs: every device returns its share of the model (same header numbers in each); the shares are concatenated below
+            shares.assign(devs.size(), nullptr);
+            if (colibri_b200_train_multi(body, nbytes, &o, devs.data(), (int)devs.size(), shares.data()) != COLIBRI_OK) fail(colibri_b200_last_error());
+            mh.h      = shares[0];
+            shares[0] = nullptr;
+        } else if (colibri_b200_train(body, nbytes, &o, &mh.h) != COLIBRI_OK)
+            fail(colibri_b200_last_error());
         totaltokens  = colibri_b200_model_tokens(mh.h);
         totaltypes   = colibri_b200_model_types(mh.h);
         maxn         = colibri_b200_model_maxn(mh.h);
@@ -340,6 +353,33 @@ class DevicePatternModel : public PatternModelInterface {
             }
         }
         adopt(mh.h);
+        for (size_t r = 1; r < shares.size(); ++r) {  // the other devices' shares of a multi-GPU run
+            colibri_b200_detail::ModelHandle sh;
+            sh.h = shares[r];
+            append_share(sh.h);
+        }
+    }
+
+    /// append the flat export of another share of the same model (unindexed shares of colibri_b200_train_multi)
+    void append_share(colibri_b200_model* h) {
+        using colibri_b200_detail::fail;
+        uint64_t np = 0, kb = 0, nr = 0;
+        if (colibri_b200_model_export_sizes(h, &np, &kb, &nr) != COLIBRI_OK) fail(colibri_b200_last_error());
+        if (np == 0) return;
+        std::vector<uint8_t>  k(kb + 1);
+        std::vector<uint64_t> of(np + 1);
+        std::vector<uint32_t> c(np + 1);
+        if (colibri_b200_model_export(h, k.data(), of.data(), c.data(), nullptr, nullptr, nullptr) != COLIBRI_OK) fail(colibri_b200_last_error());
+        const size_t   np0  = counts_.size();
+        const uint64_t base = off_[np0];
+        keys_.resize(base);
+        keys_.insert(keys_.end(), k.begin(), k.begin() + kb);
+        keys_.push_back(0);
+        off_.resize(np0 + 1);
+        for (uint64_t i = 1; i <= np; ++i) off_.push_back(base + of[i]);
+        counts_.insert(counts_.end(), c.begin(), c.begin() + np);
+        map_.clear();
+        map_ready_ = false;
     }
 
   public:

@@ -33,7 +33,8 @@ static void usage() {
                  "  -I        constrained in-place rebuild of the input model (-i) on the corpus (-f)\n"
                  "  -2        two-stage building: an unindexed model first, then an indexed model constrained by it\n"
                  "  -q        quiet\n"
-                 "  -d N      CUDA device ordinal (default 0)\n";
+                 "  -d N      CUDA device ordinal (default 0); a list or range (-d 0-7, -d 0,2,5) shards the corpus over several GPUs\n"
+                 "            (unindexed n-gram models; the model is hash-partitioned over the GPUs while it is built)\n";
 }
 
 static bool g_flexfromskip = false;  // -F S / -S S: abstract flexgrams from the skipgrams after training (reference src/patternmodeller.cpp:330-337)
@@ -117,6 +118,7 @@ int main(int argc, char** argv) {
     PatternModelOptions options;
     bool                unindexed = false, inplace = false, twostage = false;
     int                 device    = 0;
+    std::string         devicespec;
     int                 c;
     while ((c = getopt(argc, argv, "hf:o:ut:l:m:b:sy:T:W:qd:c:i:j:PRHQDrgGF:S:xXNIVC:Y:L2Zvp:Ee:0M")) != -1) {
         switch (c) {
@@ -132,7 +134,7 @@ int main(int argc, char** argv) {
             case 'T': options.MINSKIPTYPES = atoi(optarg); break;
             case 'W': options.MINTOKENS_UNIGRAMS = atoi(optarg); break;
             case 'q': options.QUIET = true; break;
-            case 'd': device = atoi(optarg); break;
+            case 'd': devicespec = optarg; break;
             case 'c':  // the class file only matters to the views (decoding patterns for print/report); training never opens it (reference :506, :857-865)
                 if (!options.QUIET) std::cerr << "Note: class file " << optarg << " is not needed to build a model; ignored" << std::endl;
                 break;
@@ -159,6 +161,28 @@ int main(int argc, char** argv) {
                           << std::endl;
                 return 2;
         }
+    }
+    if (!devicespec.empty()) {  // N | A-B | A,B,C
+        std::vector<int> devs;
+        size_t           i = 0;
+        while (i < devicespec.size()) {
+            size_t j = devicespec.find(',', i);
+            if (j == std::string::npos) j = devicespec.size();
+            const std::string part = devicespec.substr(i, j - i);
+            const size_t      dash = part.find('-');
+            if (dash != std::string::npos && dash > 0) {
+                for (int d = atoi(part.substr(0, dash).c_str()); d <= atoi(part.substr(dash + 1).c_str()); ++d) devs.push_back(d);
+            } else if (!part.empty()) {
+                devs.push_back(atoi(part.c_str()));
+            }
+            i = j + 1;
+        }
+        if (devs.empty()) {
+            std::cerr << "ERROR: -d expects a device ordinal, a list (0,1,2) or a range (0-7)" << std::endl;
+            return 2;
+        }
+        device = devs[0];
+        if (devs.size() > 1) colibri_b200_detail::device_list() = devs;
     }
     colibri_b200_detail::default_device() = device;
     int stages = 1;

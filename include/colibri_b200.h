@@ -137,6 +137,13 @@ int colibri_b200_model_lookup(colibri_b200_model* m, const uint8_t* key, uint32_
  * key_off[n+1]; counts[i] = 0 and index[i] = -1 when pattern i is absent, else its position in the export order.  Either output may be NULL. */
 int colibri_b200_model_lookup_batch(colibri_b200_model* m, const uint8_t* keys, const uint64_t* key_off, uint64_t n, uint32_t* counts, int64_t* index);
 
+/* ---- several GPUs of one node from ONE process (the C++ host / CLI; torchrun-launched runs drive the shard phases above themselves) */
+/* PatternModel::train (include/patternmodel.h:880-1345), unindexed n-gram models: the corpus is cut at sentence boundaries into ndev shards, one host
+ * thread per device runs the shard phases, keys and replies travel through peer-mapped buffers over NVLink (cudaDeviceEnablePeerAccess).  out[r]
+ * receives device r's SHARE of the model -- the patterns it exports, with their global counts; tokens, types and passes are the global numbers in
+ * every share -- so the model is the union of the shares (disjoint).  Skipgrams, indexed models and MINLENGTH > 1 are refused here. */
+int  colibri_b200_train_multi(const uint8_t* host_body, size_t nbytes, const colibri_b200_options* opt, const int* devices, int ndev, colibri_b200_model** out /* ndev handles */);
+
 /* ---- the reverse index of a model over a corpus, and the relations computed from it */
 typedef struct colibri_b200_rindex colibri_b200_rindex;
 /* Replaces the ReverseIndex / IndexedCorpus argument of IndexedPatternModel (include/patternmodel.h:2681-2720) for the queries below: every window of

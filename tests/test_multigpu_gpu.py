@@ -74,3 +74,66 @@ def test_constrained_sharded_world2():
     if cb.device_count() < 2:
         pytest.skip("needs two GPUs")
     _run(2, 300000, 20000, 23, 5, 2, 29723, "constrained")
+
+
+def _merged(shares):
+    merged, head = {}, None
+    for m in shares:
+        keys, off, counts, _ = m.export()
+        kb = keys.tobytes()
+        for i in range(len(counts)):
+            k = kb[int(off[i]):int(off[i + 1])]
+            assert k not in merged, "pattern exported twice"
+            merged[k] = int(counts[i])
+        h = (m.tokens(), m.types(), m.passes(), m.maxlength(), m.minlength())
+        assert head is None or head == h
+        head = h
+    return merged, head
+
+
+@pytest.mark.parametrize("ndev", [1, 2])
+@pytest.mark.parametrize("dense", [False, True])
+def test_train_multi_in_process(ndev, dense, monkeypatch):
+    """colibri_b200_train_multi: the shard phases driven by one host thread per device inside ONE process (what the C++ CLI's -d 0-7 uses), peer-mapped
+    buffers instead of symmetric memory, host barriers.  One device exercises the whole machinery on any box; two need two GPUs."""
+    import colibri_core_b200 as cb
+    import oracle
+
+    if cb.device_count() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    for k, v in (DENSE if dense else {}).items():
+        monkeypatch.setenv(k, v)
+    for kw, t, l in ((dict(ntokens=400000, vocab=30000, seed=6, mean_sentence=15, phrase_permille=150, nphrases=500), 2, 5),
+                     (dict(ntokens=60000, vocab=800, seed=9, mean_sentence=7), 3, 6), (dict(ntokens=30000, vocab=500, seed=10, mean_sentence=12), 1, 3)):
+        body = oracle.synth_corpus(**kw).tobytes()
+        want = oracle.train(body, mintokens=t, maxlength=l)
+        shares = cb.train_multi(body, list(range(ndev)), MINTOKENS=t, MAXLENGTH=l, QUIET=1)
+        merged, head = _merged(shares)
+        assert merged == want.as_dict()
+        assert head == (want.tokens, want.types, want.passes, want.maxn, want.minn)
+    with pytest.raises(cb.ColibriError) as ei:
+        cb.train_multi(body, list(range(ndev)), MINTOKENS=2, MAXLENGTH=4, DOSKIPGRAMS_EXHAUSTIVE=1, streamed=0, QUIET=1)
+    assert ei.value.code == 2
+
+
+def test_cli_on_two_devices_writes_the_single_gpu_model(tmp_path):
+    """colibri-patternmodeller -d 0-1: the model file of a two-GPU run has the digest of the one-GPU run (and of the reference golden)."""
+    import colibri_core_b200 as cb
+    import oracle
+
+    if cb.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cli = os.path.join(ROOT, "colibri-core_b200", "bin", "colibri-patternmodeller")
+    corpus = str(tmp_path / "c.colibri.dat")
+    body = oracle.synth_corpus(500000, vocab=20000, seed=12, mean_sentence=18).tobytes()
+    with open(corpus, "wb") as f:
+        f.write(b"\xa2\x02" + body)
+    outs = []
+    for spec in ("0", "0-1", "1,0"):
+        out = str(tmp_path / ("m%s.patternmodel" % spec.replace(",", "_")))
+        r = subprocess.run([cli, "-f", corpus, "-u", "-t", "2", "-l", "5", "-o", out, "-d", spec], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(oracle.parse_modelfile(open(out, "rb").read()))
+    want = oracle.train(body, mintokens=2, maxlength=5)
+    for got in outs:
+        assert got.same_patterns(want) and (got.tokens, got.types) == (want.tokens, want.types)

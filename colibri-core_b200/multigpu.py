@@ -256,7 +256,21 @@ def _skipgram_level(engine, dist, torch, dev):
 
 
 def train_distributed(engine, dist, torch, mintokens=2, maxlength=5, skipgrams=False):
-    """Drive one rank through all levels.  Returns (local model share, global passes, global header dict)."""
+    """Drive one rank through all levels.  Returns (local model share, global passes, global header dict).
+
+    A rank whose phase fails (a receive slot that overflows, a table that cannot grow, a malformed shard) cannot tell the others: they are inside a
+    device-side barrier or a collective by then.  So the failing rank reports and leaves the PROCESS; torchrun (and any launcher that watches its
+    workers) then takes the other ranks down instead of letting them wait forever.  COLIBRI_B200_NO_ABORT=1 re-raises instead (single-rank tests)."""
+    try:
+        return _train_distributed(engine, dist, torch, mintokens, maxlength, skipgrams)
+    except Exception as e:
+        if dist.get_world_size() > 1 and not os.environ.get("COLIBRI_B200_NO_ABORT"):
+            print("colibri_b200: rank %d failed, aborting the job: %r" % (dist.get_rank(), e), file=sys.stderr, flush=True)
+            os._exit(13)
+        raise
+
+
+def _train_distributed(engine, dist, torch, mintokens=2, maxlength=5, skipgrams=False):
     world = dist.get_world_size()
     sw = _Stopwatch(engine)
     info = engine.info()

@@ -246,7 +246,7 @@ struct Segment {  // survivors of one (level, category)
 struct Tuning {
     uint64_t filter_min      = 1ull << 20;  // COLIBRI_B200_FILTER_MIN: smallest level (upper bound of its windows) that gets the occurrence filter
     int      filter_log2_min = 20;          // COLIBRI_B200_FILTER_LOG2_MIN / _LOG2: the filter has 2^min .. 2^max buckets (>= 2 per window where that fits)
-    int      filter_log2_max = 28;
+    int      filter_log2_max = 30;          // (2^28 until round 2: at 1 B tokens the 64 MB filter saturated and level 3 took a 15 GB table; 2^30 buckets = 256 MB, table 3 GB)
     bool     no_filter       = false;       // COLIBRI_B200_NO_FILTER
     int      hot_mode        = 1;           // COLIBRI_B200_HOT: per-block hot-key cache 0 never, 1 levels >= hot_min, 2 always
     uint64_t hot_min         = 1ull << 25;  // COLIBRI_B200_HOT_MIN

@@ -38,7 +38,6 @@ extern "C" int colibri_b200_shard_begin(colibri_b200_corpus* corpus, const colib
     colibri_b200_options o = *opt;
     TRY(check_options(o));
     if (o.model_type == COLIBRI_INDEXEDPATTERNMODEL) return set_err(COLIBRI_E_UNSUPPORTED, "indexed models are not on the multi-GPU path yet");
-    if (o.MINLENGTH > 1) return set_err(COLIBRI_E_UNSUPPORTED, "MINLENGTH > 1 is not on the multi-GPU path yet");
     if (corpus->nbytes == 0) return set_err(COLIBRI_E_FORMAT, "Attempting to read pattern from file, but file is empty?");
     CUDA_TRY(cudaSetDevice(corpus->device));
     auto* sh   = new colibri_b200_shard();
@@ -525,6 +524,25 @@ extern "C" int colibri_b200_shard_finish(colibri_b200_shard* sh, const uint64_t*
     for (int p = 0; p < npasses; ++p) {
         m->passes.push_back({passes[4 * p], passes[4 * p + 1], passes[4 * p + 2], passes[4 * p + 3]});
         if (passes[4 * p + 2]) m->hasskipgrams = 1;
+    }
+    {   // which levels end up in the model: the rules of the single-GPU driver (engine.cu, reference include/patternmodel.h:1221-1229, :1278-1280, :1337-1341)
+        const colibri_b200_options& o = sh->o;
+        const int last_pass = maxn;
+        std::vector<Segment> keep;
+        for (auto& sg : sh->segs) {
+            bool drop = false;
+            if (o.MINTOKENS > 1) {
+                if (!o.DOSKIPGRAMS_EXHAUSTIVE && !o.DOSKIPGRAMS) {
+                    const int k = sg.n;
+                    if (k < o.MINLENGTH && last_pass >= k + 1 && k != o.MAXBACKOFFLENGTH && !(k == 1 && o.MINTOKENS_UNIGRAMS > o.MINTOKENS)) drop = true;
+                    if (k == o.MAXBACKOFFLENGTH && o.MAXBACKOFFLENGTH < o.MINLENGTH) drop = true;
+                } else if (o.MINLENGTH > 1 && sg.n <= o.MINLENGTH - 1) {
+                    drop = true;
+                }
+            }
+            if (!drop && sg.count > 0) keep.push_back(std::move(sg));
+        }
+        sh->segs = std::move(keep);
     }
     int rc;
     {

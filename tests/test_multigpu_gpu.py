@@ -103,14 +103,15 @@ def test_train_multi_in_process(ndev, dense, monkeypatch):
         pytest.skip("needs %d GPUs" % ndev)
     for k, v in (DENSE if dense else {}).items():
         monkeypatch.setenv(k, v)
-    for kw, t, l in ((dict(ntokens=400000, vocab=30000, seed=6, mean_sentence=15, phrase_permille=150, nphrases=500), 2, 5),
-                     (dict(ntokens=60000, vocab=800, seed=9, mean_sentence=7), 3, 6), (dict(ntokens=30000, vocab=500, seed=10, mean_sentence=12), 1, 3)):
+    for kw, t, l, ml in ((dict(ntokens=400000, vocab=30000, seed=6, mean_sentence=15, phrase_permille=150, nphrases=500), 2, 5, 1),
+                         (dict(ntokens=60000, vocab=800, seed=9, mean_sentence=7), 3, 6, 1), (dict(ntokens=30000, vocab=500, seed=10, mean_sentence=12), 1, 3, 1),
+                         (dict(ntokens=80000, vocab=900, seed=11, mean_sentence=9), 2, 5, 3), (dict(ntokens=80000, vocab=900, seed=11, mean_sentence=9), 2, 4, 2)):
         body = oracle.synth_corpus(**kw).tobytes()
-        want = oracle.train(body, mintokens=t, maxlength=l)
-        shares = cb.train_multi(body, list(range(ndev)), MINTOKENS=t, MAXLENGTH=l, QUIET=1)
+        want = oracle.train(body, mintokens=t, maxlength=l, minlength=ml)
+        shares = cb.train_multi(body, list(range(ndev)), MINTOKENS=t, MAXLENGTH=l, MINLENGTH=ml, QUIET=1)
         merged, head = _merged(shares)
-        assert merged == want.as_dict()
-        assert head == (want.tokens, want.types, want.passes, want.maxn, want.minn)
+        assert merged == want.as_dict(), (kw, t, l, ml)
+        assert head == (want.tokens, want.types, want.passes, want.maxn, want.minn), (kw, t, l, ml)
     with pytest.raises(cb.ColibriError) as ei:
         cb.train_multi(body, list(range(ndev)), MINTOKENS=2, MAXLENGTH=4, DOSKIPGRAMS_EXHAUSTIVE=1, streamed=0, QUIET=1)
     assert ei.value.code == 2

@@ -408,6 +408,8 @@ def run_ours(a):
                 alg_bytes += 12.0 * lv["items"] + 4.0 * npos_l + 68.0 * table_w + (8.0 * lv["items"] if lv["filtered"] else 0.0)
             else:
                 alg_bytes += 8.0 * npos_l + 64.0 * table_w + (4.0 * npos_l if lv["filtered"] else 0.0)
+            if lv.get("fused_id1"):  # the level's time includes the sweep that reads the tokens and writes the level-1 ids (4 B in, 4 B out per position)
+                alg_bytes += 8.0 * npos_l
         if last is not None:
             last.close()
         last = m

@@ -434,7 +434,7 @@ class Model:
         out = (C.c_double * 8)()
         _check(library().colibri_b200_model_level_info(self._h, n, out))
         return {"windows": int(out[0]), "capacity": int(out[1]), "count_ms": float(out[2]), "singletons": int(out[3]), "items": int(out[4]),
-                "path": "partitioned" if out[5] else "table", "filtered": bool(out[6])}
+                "path": "partitioned" if out[5] else "table", "filtered": bool(out[6]), "fused_id1": bool(out[7])}
 
     def close(self):
         if self._h:

@@ -11,6 +11,7 @@
 using namespace colibri;
 
 thread_local char colibri::g_err[1024] = "";
+thread_local bool colibri::g_unwinding = false;
 colibri::Pool colibri::g_pool[16];
 colibri::EventCache colibri::g_events;
 thread_local colibri::HostTrace colibri::g_trace;
@@ -290,6 +291,7 @@ extern "C" int colibri_b200_model_level_info(const colibri_b200_model* m, int n,
     out[4] = (double)it->second.items;
     out[5] = (double)it->second.path;
     out[6] = (double)it->second.filtered;
+    out[7] = (double)it->second.fused_id1;
     return 0;
 }
 
@@ -430,7 +432,8 @@ struct Trainer {
     DevBuf<unsigned long long> part_rk1, part_rk2;
     DevBuf<uint32_t>           part_rp1, part_rp2, part_small, part_dense_id, part_dense_bits;
     int  level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint64_t npos, const uint32_t* list, uint64_t nlist, uint64_t wbound, uint32_t dense, uint32_t* dense_cnt,
-                           uint32_t t, uint32_t* tok_ext, Segment& sg, bool& overflow, double hashed_share, DevBuf<uint32_t>* slot_index);
+                           uint32_t t, uint32_t* tok_ext, Segment& sg, bool& overflow, double hashed_share, DevBuf<uint32_t>* slot_index, bool pre_hist);
+    int  part_small_layout(const PartPlan& pl);
     int  l2_pin(const void* base, size_t bytes);
     void l2_unpin();
     const uint32_t*            tok_for_sink = nullptr;
@@ -703,18 +706,22 @@ int Trainer::flush_sink(bool final) {
     return 0;
 }
 
+int Trainer::part_small_layout(const PartPlan& pl) {
+    const uint64_t small_words = 5ull * (1u << pl.b1) + 3ull * pl.nparts + 16;
+    if (part_small.n < small_words) TRY(part_small.alloc(dev, small_words));
+    return 0;
+}
+
 // One level on the partitioned path (partition.cu).  On return h_stats holds the level's device statistics (valid_windows, found, kept,
 // kept_occ, singletons = keys that occur once); sg.pos / sg.cnt hold the survivors, cur[] the final ids (survivor index + 1, 0 = pruned or no
 // window).  overflow: a partition did not fit its shared-memory table -- nothing of the level is usable, the caller reruns it on the HBM table.
 int Trainer::level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint64_t npos, const uint32_t* list, uint64_t nlist, uint64_t wbound, uint32_t dense,
-                               uint32_t* dense_cnt, uint32_t t, uint32_t* tok_ext, Segment& sg, bool& overflow, double hashed_share, DevBuf<uint32_t>* slot_index) {
+                               uint32_t* dense_cnt, uint32_t t, uint32_t* tok_ext, Segment& sg, bool& overflow, double hashed_share, DevBuf<uint32_t>* slot_index, bool pre_hist) {
     overflow = false;
     // partitions are sized for the windows expected to become records (an estimate that is too low shows up as an overflow, not as a wrong count)
     const PartPlan pl  = part_plan((uint64_t)((double)wbound * std::min(1.0, hashed_share)) + 1024);
     const uint32_t p1n = 1u << pl.b1;
-    // hist1 | off1 (+1) | cursor1 | group_tot | group_base (+1) | off (+1) | kept_of (first: hist2) | dst_off (+1)
-    const uint64_t small_words = 5ull * p1n + 3ull * pl.nparts + 16;
-    if (part_small.n < small_words) TRY(part_small.alloc(dev, small_words));
+    TRY(part_small_layout(pl));  // hist1 | off1 (+1) | cursor1 | group_tot | group_base (+1) | off (+1) | kept_of (first: hist2) | dst_off (+1)
     uint32_t* hist1      = part_small.p;
     uint32_t* off1       = hist1 + p1n;
     uint32_t* cursor1    = off1 + p1n + 1;
@@ -747,11 +754,13 @@ int Trainer::level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint6
 
     int hc = timer.begin(COLIBRI_T_COUNT, n);
     uint32_t* hist2 = kept_of;  // the final partitions' sizes (pass B) are consumed by the scan before pass E writes the survivor counts there
-    CUDA_TRY(cudaMemsetAsync(hist1, 0, (size_t)p1n * sizeof(uint32_t), s));
     CUDA_TRY(cudaMemsetAsync(hist2, 0, (size_t)pl.nparts * sizeof(uint32_t), s));
-    if (dense) CUDA_TRY(cudaMemsetAsync(dense_cnt, 0, dense_cells * sizeof(uint32_t), s));
-    TRY(zero_stats());
-    launches += launch_part_hist(s, prev, list, nitems, dense, dense_cnt, hist1, pl, d_stats.p, sms);
+    if (!pre_hist) {  // (pre_hist: pass A ran inside the level-1 id sweep, launch_make_id1_hist: hist1, the dense square and valid_windows are there)
+        CUDA_TRY(cudaMemsetAsync(hist1, 0, (size_t)p1n * sizeof(uint32_t), s));
+        if (dense) CUDA_TRY(cudaMemsetAsync(dense_cnt, 0, dense_cells * sizeof(uint32_t), s));
+        TRY(zero_stats());
+        launches += launch_part_hist(s, prev, list, nitems, dense, dense_cnt, hist1, pl, d_stats.p, sms);
+    }
     if (dense)  // prune(MINTOKENS, 2) of the dense square first: its survivors open the segment, dense_id[cell] = survivor index + 1
         launches += launch_prune_dense(s, dense_cnt, dense, 0, t, sg.pos.p, sg.cnt.p, part_dense_bits.p, part_dense_id.p, tok_ext, (uint32_t)(npos + 8), d_stats.p, sms);
     launches += launch_part_bases(s, hist1, p1n, off1, cursor1, nullptr);
@@ -956,9 +965,31 @@ int Trainer::run() {
     DevBuf<SkipSlot>        sktable;
     DevBuf<const uint32_t*> d_idptrs;
     DevBuf<SkipMask>        d_masks;
+    bool pre_hist2 = false;  // level 2's pass A (dense square, first-level histogram) was taken by the sweep that writes the level-1 ids
     if (last_pass == 1 && o.MAXLENGTH >= 2) {
         TRY(ids[1].alloc(dev, npos + 8));
-        launches += launch_make_id1(s, tok.p, npos + 1, count1.p, t1, ids[1].p);
+        // what level 2 will decide below, decided here already: a dense, partitioned level 2 lets one kernel do both sweeps
+        uint64_t bound2 = prev_occ;
+        if (prev_kept < (1ull << 31)) bound2 = std::min(bound2, prev_kept * prev_kept);
+        const uint64_t wbound2 = std::min<uint64_t>(prev_occ, npos);
+        const uint32_t dense2  = (bound2 >= tune.dense_min && tok_ext_cells) ? std::min<uint32_t>(tune.dense_dim, nclasses) : 0;
+        if (dense2 && bound2 > 0 && tune.use_partition(wbound2, true) && wbound2 < 0xFFFFFFF0ull && m->totaltokens && !getenv("COLIBRI_B200_NO_FUSE_ID1")) {
+            const double   f  = (double)dense_tokens / (double)m->totaltokens;
+            const PartPlan pl = part_plan((uint64_t)((double)wbound2 * std::min(1.0, 1.1 * (1.0 - f * f))) + 1024);
+            const uint64_t dense_cells2 = (uint64_t)dense2 * dense2;
+            TRY(part_small_layout(pl));
+            if (filter.n < dense_cells2 + 8) TRY(filter.alloc(dev, dense_cells2 + 8));
+            int hc = timer.begin(COLIBRI_T_COUNT, 2);
+            CUDA_TRY(cudaMemsetAsync(part_small.p, 0, ((size_t)1 << pl.b1) * sizeof(uint32_t), s));
+            CUDA_TRY(cudaMemsetAsync(filter.p, 0, dense_cells2 * sizeof(uint32_t), s));
+            TRY(zero_stats());
+            launches += launch_make_id1_hist(s, tok.p, npos, count1.p, t1, ids[1].p, dense2, filter.p, part_small.p, pl, d_stats.p, sms);
+            timer.end(hc);
+            pre_hist2 = true;
+            m->levels[2].fused_id1 = 1;
+        } else {
+            launches += launch_make_id1(s, tok.p, npos + 1, count1.p, t1, ids[1].p);
+        }
     }
     for (int n = 2; n <= o.MAXLENGTH && last_pass == n - 1; ++n) {
         // every valid window starts at a position whose (n-1)-gram survived, and is a pair of surviving (n-1)-grams
@@ -995,7 +1026,7 @@ int Trainer::run() {
                 const double f = (double)dense_tokens / (double)m->totaltokens;
                 share = 1.1 * (1.0 - f * f);
             }
-            TRY(level_partitioned(n, prev.p, cur.p, npos, list, nlist, wbound, dense, filter.p, t, tok.p + npos + 8, sg, overflow, share, indexed ? &slot_index : nullptr));
+            TRY(level_partitioned(n, prev.p, cur.p, npos, list, nlist, wbound, dense, filter.p, t, tok.p + npos + 8, sg, overflow, share, indexed ? &slot_index : nullptr, n == 2 && pre_hist2));
             parted = !overflow;
             if (parted) {
                 windows = h_stats.valid_windows;

@@ -21,11 +21,16 @@ namespace colibri {
 
 // ------------------------------------------------------------------------------------------------ errors
 extern thread_local char g_err[1024];
+// An error return unwinds through scopes that own device blocks (DevBuf): work that was enqueued before the error may still be writing to them.
+// set_err raises this flag; the first DevBuf released afterwards drains the device before its block goes back to the pool, where another
+// stream or thread could be handed it.  (The flag costs one thread-local load on the normal path.)
+extern thread_local bool g_unwinding;
 inline int set_err(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
+    g_unwinding = true;
     return code;
 }
 #define CUDA_TRY(expr)                                                                                                        \
@@ -134,6 +139,15 @@ struct DevBuf {
         return 0;
     }
     void reset() {
+        if (p && g_unwinding) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            cudaSetDevice(dev);
+            cudaDeviceSynchronize();
+            cudaGetLastError();
+            cudaSetDevice(cur);
+            g_unwinding = false;
+        }
         if (p) g_pool[dev & 15].release(p);
         p = nullptr;
         n = 0;
@@ -316,7 +330,7 @@ struct colibri_b200_corpus {
 
 
 struct PassStat { uint64_t n, found, foundskip, pruned; };
-struct LevelInfo { uint64_t windows = 0, cap = 0, singles = 0, items = 0; double ms = 0; int path = 0 /* 0 HBM table, 1 partitioned */; int filtered = 0; };
+struct LevelInfo { uint64_t windows = 0, cap = 0, singles = 0, items = 0; double ms = 0; int path = 0 /* 0 HBM table, 1 partitioned */; int filtered = 0; int fused_id1 = 0 /* the level's time includes the sweep that writes the level-1 ids */; };
 struct colibri_b200_model {
     int      device = 0;
     int      model_type = COLIBRI_UNINDEXEDPATTERNMODEL;

@@ -69,6 +69,9 @@ typedef struct colibri_b200_options {
     int32_t DORESET;                /* values start empty (counts 0, no references) */
 } colibri_b200_options;
 
+/* Thread safety: calls on DIFFERENT handles may run concurrently (the device pool, the stream / event caches and the error text are
+ * thread-safe or thread-local).  One handle must not be used by two calls at a time -- that includes a corpus or a constraint model shared by two
+ * concurrent trainings: training writes the sentence-source tail behind the staged body and counts inside the constraint model's index. */
 typedef struct colibri_b200_corpus colibri_b200_corpus; /* a corpus body resident in HBM, tokenised lazily */
 typedef struct colibri_b200_model  colibri_b200_model;  /* a trained model: device-resident survivors + host-side stats */
 
@@ -229,7 +232,8 @@ int colibri_b200_model_level_counters(const colibri_b200_model* m, int n, double
 /* same plus out[4]=items the level's kernels enumerated: every position (dense mode), or the length of the position list the previous
  * level left behind (list mode: only positions whose (n-1)-gram survived are visited); out[5]=1 if the level ran on the partitioned path
  * (shared-memory counting, out[1] = partitions, out[3] = n-grams that occur once) else 0 (HBM table, out[3] = windows the occurrence filter held
- * back); out[6]=1 if the occurrence filter ran; out[7] reserved (0) */
+ * back); out[6]=1 if the occurrence filter ran; out[7]=1 if out[2] includes the sweep that writes the level-1 ids
+ * (level 2 on the partitioned path: one kernel writes the ids and takes level 2's first pass) */
 int colibri_b200_model_level_info(const colibri_b200_model* m, int n, double out[8]);
 
 /* ---- multi-GPU: one process per GPU drives these per-rank phases and moves the buffers between ranks itself

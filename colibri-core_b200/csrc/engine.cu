@@ -958,6 +958,7 @@ int Trainer::run() {
     DevBuf<NgramSlot>       table;
     DevBuf<uint32_t>        bitmap;  // survivor bit per table slot of the level just pruned
     DevBuf<uint32_t>        filter;  // 2-bit occurrence filter of the level being counted
+    DevBuf<uint32_t>        filter1; // its "hit twice" bits, packed (Tuning::filter_1bit)
     DevBuf<uint32_t>        slot_index;  // indexed models: table slot -> survivor index + 1
     DevBuf<uint32_t>        list_cur, list_next;  // list mode: positions whose newest id is non-zero (see kernels.cu: load_window)
     uint64_t                nlist = 0;
@@ -1071,9 +1072,16 @@ int Trainer::run() {
             cap = std::max<uint64_t>(1024, 3 * h_stats.found + 1024);
             if (h_stats.found * 8 > nbuckets) cap = bound + bound / 2 + 16;  // a saturated filter says nothing about the number of keys
             cap = std::min(cap, std::max<uint64_t>(64, bound + bound / 2 + 16));
+            if (tune.filter_1bit && nbuckets >= 64) {
+                if (filter1.n < nbuckets / 32 + 8) TRY(filter1.alloc(dev, nbuckets / 32 + 8));
+                int hf1 = timer.begin(COLIBRI_T_COUNT, n);
+                launches += launch_filter_to_bitmap(s, filter.p, nbuckets, filter1.p);
+                timer.end(hf1);
+            }
         } else {
             cap = std::max<uint64_t>(64, bound + bound / 2 + 16);  // load factor <= 2/3
         }
+        const bool onebit = use_filter && tune.filter_1bit && nbuckets >= 64;
         const uint64_t cap_max = std::max<uint64_t>(64, bound + bound / 2 + 16);  // windows <= bound: a table this large cannot fill up
         for (;;) {
             cap = (cap + 31) / 32 * 32;  // the dense cells' survivor bits start on a bitmap word
@@ -1088,7 +1096,8 @@ int Trainer::run() {
             TRY(zero_stats());
             int hc = timer.begin(COLIBRI_T_COUNT, n);
             const bool hot = tune.use_hot(bound);
-            launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms, use_filter ? filter.p : nullptr, nbuckets, hot, dense, list, nlist, dense_cnt);
+            launches += launch_count_ngrams(s, prev.p, cur.p, npos, table.p, cap, d_stats.p, sms, use_filter ? (onebit ? filter1.p : filter.p) : nullptr, nbuckets, hot, dense, list, nlist, dense_cnt,
+                                            onebit);
             timer.end(hc);
             CUDA_TRY(cudaGetLastError());
             TRY(fetch_stats());

@@ -262,6 +262,8 @@ struct Tuning {
     int      filter_log2_min = 20;          // COLIBRI_B200_FILTER_LOG2_MIN / _LOG2: the filter has 2^min .. 2^max buckets (>= 2 per window where that fits)
     int      filter_log2_max = 30;          // (2^28 until round 2: at 1 B tokens the 64 MB filter saturated and level 3 took a 15 GB table; 2^30 buckets = 256 MB, table 3 GB)
     bool     no_filter       = false;       // COLIBRI_B200_NO_FILTER
+    bool     filter_1bit     = true;        // COLIBRI_B200_FILTER_1BIT=0: the count launch reads the 2-bit counters instead of their packed "hit twice" bits
+                                            // (half the footprint in L2: level 3 of the 100 M-token corpus 2.49 -> 2.30 ms)
     int      hot_mode        = 1;           // COLIBRI_B200_HOT: per-block hot-key cache 0 never, 1 levels >= hot_min, 2 always
     uint64_t hot_min         = 1ull << 25;  // COLIBRI_B200_HOT_MIN
     uint32_t dense_dim       = 2048;        // COLIBRI_B200_DENSE: side of the directly addressed square of level 2 (0 = off)
@@ -282,6 +284,7 @@ struct Tuning {
         t.filter_log2_min = std::max(6, std::min(t.filter_log2_min, 32));
         t.filter_log2_max = std::max(t.filter_log2_min, std::min(t.filter_log2_max, 32));
         t.no_filter       = getenv("COLIBRI_B200_NO_FILTER") != nullptr;
+        t.filter_1bit     = env_u64("COLIBRI_B200_FILTER_1BIT", t.filter_1bit ? 1 : 0) != 0;
         t.hot_mode        = (int)env_u64("COLIBRI_B200_HOT", t.hot_mode);
         t.hot_min         = env_u64("COLIBRI_B200_HOT_MIN", t.hot_min);
         t.dense_dim       = (uint32_t)std::min<uint64_t>(env_u64("COLIBRI_B200_DENSE", t.dense_dim), 16384);

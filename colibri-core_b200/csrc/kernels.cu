@@ -374,7 +374,7 @@ template <bool kFilter, bool kDense, bool kList>
 __global__ void __launch_bounds__(256, kDense ? 7 : 8) count_ngrams_kernel(const uint32_t* __restrict__ prev, const uint32_t* __restrict__ list, uint64_t nitems,
                                                                            uint32_t* __restrict__ cur, NgramSlot* __restrict__ table, uint64_t cap,
                                                                            const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, DeviceStats* __restrict__ st, const bool hot,
-                                                                           const uint32_t dense, uint32_t* __restrict__ dense_cnt) {
+                                                                           const uint32_t dense, uint32_t* __restrict__ dense_cnt, const bool onebit) {
     __shared__ uint64_t scratch[8];
     __shared__ unsigned long long hot_key[kHotLines];
     __shared__ uint32_t hot_slot[kHotLines];
@@ -419,8 +419,13 @@ __global__ void __launch_bounds__(256, kDense ? 7 : 8) count_ngrams_kernel(const
                 if (kFilter) {
                     uint64_t word;
                     uint32_t shift;
-                    filter_locate(h, nbuckets_mask, word, shift);
-                    go = ((__ldg(filter + word) >> shift) & 2u) != 0;
+                    if (onebit) {  // the "hit twice" bits alone, one per bucket: half the footprint of the 2-bit counters (launch_filter_to_bitmap)
+                        const uint64_t bucket = h & nbuckets_mask;
+                        go = ((__ldg(filter + (bucket >> 5)) >> (bucket & 31)) & 1u) != 0;
+                    } else {
+                        filter_locate(h, nbuckets_mask, word, shift);
+                        go = ((__ldg(filter + word) >> shift) & 2u) != 0;
+                    }
                     singles += !go;
                 }
                 if (go) {
@@ -713,24 +718,46 @@ int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uin
 }
 template <bool kFilter, bool kDense, bool kList>
 static void launch_count_variant(cudaStream_t s, const uint32_t* prev, const uint32_t* list, uint64_t nitems, uint32_t* cur, NgramSlot* table, uint64_t cap, const uint32_t* filter,
-                                 uint64_t nbuckets, DeviceStats* st, int sms, bool hot, uint32_t dense, uint32_t* dense_cnt = nullptr) {
+                                 uint64_t nbuckets, DeviceStats* st, int sms, bool hot, uint32_t dense, uint32_t* dense_cnt = nullptr, bool onebit = false) {
     static int bps  = blocks_per_sm((const void*)count_ngrams_kernel<kFilter, kDense, kList>, 256, 0);
     unsigned   grid = (unsigned)umin64(div_up(nitems, 256), (uint64_t)sms * bps * 4);
-    count_ngrams_kernel<kFilter, kDense, kList><<<grid, 256, 0, s>>>(prev, list, nitems, cur, table, cap, filter, kFilter ? nbuckets - 1 : 0, st, hot, dense, dense_cnt);
+    count_ngrams_kernel<kFilter, kDense, kList><<<grid, 256, 0, s>>>(prev, list, nitems, cur, table, cap, filter, kFilter ? nbuckets - 1 : 0, st, hot, dense, dense_cnt, onebit);
 }
+// the "hit twice" bit of every 2-bit counter, packed: bitmap[bucket >> 5] bit (bucket & 31); two filter words in, one bitmap word out
+__global__ void __launch_bounds__(256) filter_to_bitmap_kernel(const uint32_t* __restrict__ filter, uint64_t nwords_out, uint32_t* __restrict__ bitmap) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwords_out) return;
+    const uint2 in = __ldcs(reinterpret_cast<const uint2*>(filter) + w);
+    auto odd_bits  = [](uint32_t x) {
+        x = (x >> 1) & 0x55555555u;
+        x = (x | (x >> 1)) & 0x33333333u;
+        x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+        x = (x | (x >> 4)) & 0x00FF00FFu;
+        x = (x | (x >> 8)) & 0x0000FFFFu;
+        return x;
+    };
+    bitmap[w] = odd_bits(in.x) | (odd_bits(in.y) << 16);
+}
+int launch_filter_to_bitmap(cudaStream_t s, const uint32_t* filter, uint64_t nbuckets, uint32_t* bitmap) {
+    const uint64_t nwords_out = nbuckets / 32;
+    if (!nwords_out) return 0;
+    filter_to_bitmap_kernel<<<(unsigned)div_up(nwords_out, 256), 256, 0, s>>>(filter, nwords_out, bitmap);
+    return 1;
+}
+
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms, const uint32_t* filter,
-                        uint64_t nbuckets, bool hot, uint32_t dense, const uint32_t* list, uint64_t nlist, uint32_t* dense_cnt) {
+                        uint64_t nbuckets, bool hot, uint32_t dense, const uint32_t* list, uint64_t nlist, uint32_t* dense_cnt, bool onebit) {
     const uint64_t nitems = list ? nlist : npos;
     if (!nitems) return 0;
     const bool f = filter != nullptr;
     if (list) {  // (the dense square belongs to level 2, which never runs from a list: its input is the class ids themselves)
-        if (f) launch_count_variant<true, false, true>(s, prev, list, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, 0);
+        if (f) launch_count_variant<true, false, true>(s, prev, list, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, 0, nullptr, onebit);
         else launch_count_variant<false, false, true>(s, prev, list, nitems, cur, table, cap, nullptr, 0, st, sms, hot, 0);
     } else if (dense) {
-        if (f) launch_count_variant<true, true, false>(s, prev, nullptr, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, dense, dense_cnt);
+        if (f) launch_count_variant<true, true, false>(s, prev, nullptr, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, dense, dense_cnt, onebit);
         else launch_count_variant<false, true, false>(s, prev, nullptr, nitems, cur, table, cap, nullptr, 0, st, sms, hot, dense, dense_cnt);
     } else {
-        if (f) launch_count_variant<true, false, false>(s, prev, nullptr, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, 0);
+        if (f) launch_count_variant<true, false, false>(s, prev, nullptr, nitems, cur, table, cap, filter, nbuckets, st, sms, hot, 0, nullptr, onebit);
         else launch_count_variant<false, false, false>(s, prev, nullptr, nitems, cur, table, cap, nullptr, 0, st, sms, hot, 0);
     }
     return 1;

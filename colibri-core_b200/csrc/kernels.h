@@ -79,7 +79,10 @@ int launch_ngram_filter(cudaStream_t s, const uint32_t* prev, uint64_t npos, uin
 int launch_count_ngrams(cudaStream_t s, const uint32_t* prev, uint32_t* cur, uint64_t npos, NgramSlot* table, uint64_t cap, DeviceStats* st, int sms,
                         const uint32_t* filter = nullptr, uint64_t nbuckets = 0, bool hot = false /* per-block shared-memory cache for frequent keys */, uint32_t dense = 0,
                         const uint32_t* list = nullptr /* list mode: cur must have been zeroed by the caller */, uint64_t nlist = 0,
-                        uint32_t* dense_cnt = nullptr /* dense > 0: the zeroed u32 square dense x dense */);
+                        uint32_t* dense_cnt = nullptr /* dense > 0: the zeroed u32 square dense x dense */,
+                        bool onebit = false /* filter = the packed "hit twice" bits of launch_filter_to_bitmap instead of the 2-bit counters */);
+// bitmap[nbuckets / 32 words] = the "hit twice" bit of every bucket of the occurrence filter (nbuckets >= 32, a power of two)
+int launch_filter_to_bitmap(cudaStream_t s, const uint32_t* filter, uint64_t nbuckets, uint32_t* bitmap);
 // prune() over the dense square (cells = ids cap + 1 .. cap + dense^2); cap must be a multiple of 32.  Survivors get tok_ext[2 * cell ..] = their two class
 // ids and the position ext_pos0 + 2 * cell (tok_ext = token array + ext_pos0)
 int launch_prune_dense(cudaStream_t s, const uint32_t* dense_cnt, uint32_t dense, uint64_t cap, uint32_t threshold, uint32_t* sv_pos, uint32_t* sv_count, uint32_t* bitmap,
@@ -172,7 +175,7 @@ int launch_split_write(cudaStream_t s, const uint32_t* prev, uint64_t npos, uint
 int launch_stream_filter(cudaStream_t s, const void* keys, uint64_t n, uint32_t* filter, uint64_t nbuckets, DeviceStats* st, int sms, uint64_t slot_cap = 0,
                          const unsigned long long* slot_counts = nullptr, uint32_t world = 0);
 int launch_stream_count(cudaStream_t s, const void* keys, uint64_t n, NgramSlot* table, uint64_t cap, const uint32_t* filter, uint64_t nbuckets, uint32_t* rid, DeviceStats* st, int sms,
-                        uint64_t slot_cap = 0, const unsigned long long* slot_counts = nullptr, uint32_t world = 0);
+                        uint64_t slot_cap = 0, const unsigned long long* slot_counts = nullptr, uint32_t world = 0, bool onebit = false /* filter = packed "hit twice" bits */);
 int launch_owner_reply(cudaStream_t s, uint32_t* rid, uint64_t n, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* const* peer_reply = nullptr, uint64_t slot_cap = 0,
                        const unsigned long long* slot_counts = nullptr, uint32_t id_off = 0 /* global ids start above the dense square's */);
 int launch_owner_survivors_p2p(cudaStream_t s, const uint32_t* sv_idx, const uint32_t* sv_count, uint64_t n, uint32_t world, uint32_t rank, uint64_t slot_cap, uint64_t surv_cap,

@@ -253,7 +253,12 @@ extern "C" int colibri_b200_shard_level_owner(colibri_b200_shard* sh, const void
         sh->launches += launch_stream_filter(s, dev_recv_keys, nrecv, sh->filter.p, nbuckets, sh->d_stats.p, sh->sms);
         TRY(shard_read_stats(sh));
         if (sh->h_stats.found * 8 <= nbuckets) cap = std::min(cap, std::max<uint64_t>(1024, 3 * sh->h_stats.found + 1024));  // (a saturated filter says nothing about the number of keys)
+        if (tune.filter_1bit && nbuckets >= 64) {
+            if (sh->filter1.n < nbuckets / 32 + 8) TRY(sh->filter1.alloc(sh->dev, nbuckets / 32 + 8));
+            sh->launches += launch_filter_to_bitmap(s, sh->filter.p, nbuckets, sh->filter1.p);
+        }
     }
+    const bool onebit = use_filter && tune.filter_1bit && nbuckets >= 64;
     const uint64_t cap_max = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);  // a table this large cannot fill up
     uint64_t singles = 0;
     for (;;) {
@@ -261,7 +266,7 @@ extern "C" int colibri_b200_shard_level_owner(colibri_b200_shard* sh, const void
         if (sh->owner_table.n < cap) TRY(sh->owner_table.alloc(sh->dev, cap));
         CUDA_TRY(cudaMemsetAsync(sh->owner_table.p, 0, cap * sizeof(NgramSlot), s));
         TRY(shard_zero_stats(sh));
-        sh->launches += launch_stream_count(s, dev_recv_keys, nrecv, sh->owner_table.p, cap, use_filter ? sh->filter.p : nullptr, nbuckets, (uint32_t*)dev_reply, sh->d_stats.p, sh->sms);
+        sh->launches += launch_stream_count(s, dev_recv_keys, nrecv, sh->owner_table.p, cap, use_filter ? (onebit ? sh->filter1.p : sh->filter.p) : nullptr, nbuckets, (uint32_t*)dev_reply, sh->d_stats.p, sh->sms, 0, nullptr, 0, onebit);
         CUDA_TRY(cudaMemcpyAsync(&sh->h_stats, sh->d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (sh->h_stats.errflags & kErrTableFull) {  // the estimate was too small: go again with twice the slots

@@ -16,6 +16,7 @@ struct colibri_b200_shard {
     DeviceStats          h_stats;
     uint64_t             npos = 0, local_tokens = 0;
     uint32_t             local_maxclass = 0, nclasses = 0;
+    DevBuf<uint32_t>     filter1;  // the occurrence filter's "hit twice" bits, packed (Tuning::filter_1bit)
     DevBuf<uint32_t>     tok, count1, prev, cur, bitmap, filter, pos_of_rec, rec_of_pos, split_hist, sv_idx, sv_cnt;
     DevBuf<uint64_t>     split_off, scan_tmp;
     DevBuf<NgramSlot>    owner_table;

@@ -269,7 +269,7 @@ constexpr unsigned long long kHotBusy = ~0ull;
 
 __global__ void __launch_bounds__(256) stream_count_kernel(const unsigned long long* __restrict__ keys, uint64_t n, NgramSlot* __restrict__ table, uint64_t cap,
                                                            const uint32_t* __restrict__ filter, uint64_t nbuckets_mask, uint32_t* __restrict__ rid, DeviceStats* __restrict__ st,
-                                                           uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts, uint32_t world) {
+                                                           uint64_t slot_cap, const unsigned long long* __restrict__ slot_counts, uint32_t world, bool onebit) {
     __shared__ uint64_t scratch[8];
     __shared__ SlotMap  map;
     __shared__ unsigned long long hot_key[kHotLines];
@@ -295,8 +295,13 @@ __global__ void __launch_bounds__(256) stream_count_kernel(const unsigned long l
         if (filter != nullptr) {
             uint64_t word;
             uint32_t shift;
-            stream_filter_locate(h, nbuckets_mask, word, shift);
-            go = ((__ldg(filter + word) >> shift) & 2u) != 0;
+            if (onebit) {  // the packed "hit twice" bits (launch_filter_to_bitmap)
+                const uint64_t bucket = h & nbuckets_mask;
+                go = ((__ldg(filter + (bucket >> 5)) >> (bucket & 31)) & 1u) != 0;
+            } else {
+                stream_filter_locate(h, nbuckets_mask, word, shift);
+                go = ((__ldg(filter + word) >> shift) & 2u) != 0;
+            }
             singles += !go;
         }
         if (go) {
@@ -566,10 +571,10 @@ int launch_stream_filter(cudaStream_t s, const void* keys, uint64_t n, uint32_t*
     return 1;
 }
 int launch_stream_count(cudaStream_t s, const void* keys, uint64_t n, NgramSlot* table, uint64_t cap, const uint32_t* filter, uint64_t nbuckets, uint32_t* rid, DeviceStats* st, int sms,
-                        uint64_t slot_cap, const unsigned long long* slot_counts, uint32_t world) {
+                        uint64_t slot_cap, const unsigned long long* slot_counts, uint32_t world, bool onebit) {
     if (!n) return 0;
     unsigned grid = (unsigned)sk_min(sk_div_up(n, 256), (uint64_t)sms * 32);
-    stream_count_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)keys, n, table, cap, filter, nbuckets ? nbuckets - 1 : 0, rid, st, slot_cap, slot_counts, world);
+    stream_count_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)keys, n, table, cap, filter, nbuckets ? nbuckets - 1 : 0, rid, st, slot_cap, slot_counts, world, onebit);
     return 1;
 }
 int launch_owner_reply(cudaStream_t s, uint32_t* rid, uint64_t n, const uint32_t* bitmap, uint32_t world, uint32_t rank, void* const* peer_reply, uint64_t slot_cap,

@@ -98,7 +98,12 @@ extern "C" int colibri_b200_shard_p2p_owner(colibri_b200_shard* sh, uint64_t sta
         sh->launches += launch_stream_filter(s, keys, nrecv, sh->filter.p, nbuckets, sh->d_stats.p, sh->sms, sh->slot_cap, my_hdr, G);
         TRY(shard_read_stats(sh));
         if (sh->h_stats.found * 8 <= nbuckets) cap = std::min(cap, std::max<uint64_t>(1024, 3 * sh->h_stats.found + 1024));  // (a saturated filter says nothing about the number of keys)
+        if (tune.filter_1bit && nbuckets >= 64) {
+            if (sh->filter1.n < nbuckets / 32 + 8) TRY(sh->filter1.alloc(sh->dev, nbuckets / 32 + 8));
+            sh->launches += launch_filter_to_bitmap(s, sh->filter.p, nbuckets, sh->filter1.p);
+        }
     }
+    const bool onebit = use_filter && tune.filter_1bit && nbuckets >= 64;
     const uint64_t cap_max = std::max<uint64_t>(64, nrecv + nrecv / 2 + 16);  // a table this large cannot fill up
     uint64_t singles = 0;
     for (;;) {
@@ -106,7 +111,7 @@ extern "C" int colibri_b200_shard_p2p_owner(colibri_b200_shard* sh, uint64_t sta
         if (sh->owner_table.n < cap) TRY(sh->owner_table.alloc(sh->dev, cap));
         CUDA_TRY(cudaMemsetAsync(sh->owner_table.p, 0, cap * sizeof(NgramSlot), s));
         TRY(shard_zero_stats(sh));
-        sh->launches += launch_stream_count(s, keys, nrecv, sh->owner_table.p, cap, use_filter ? sh->filter.p : nullptr, nbuckets, sh->rid.p, sh->d_stats.p, sh->sms, sh->slot_cap, my_hdr, G);
+        sh->launches += launch_stream_count(s, keys, nrecv, sh->owner_table.p, cap, use_filter ? (onebit ? sh->filter1.p : sh->filter.p) : nullptr, nbuckets, sh->rid.p, sh->d_stats.p, sh->sms, sh->slot_cap, my_hdr, G, onebit);
         CUDA_TRY(cudaMemcpyAsync(&sh->h_stats, sh->d_stats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (sh->h_stats.errflags & kErrTableFull) {

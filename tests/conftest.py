@@ -80,7 +80,7 @@ def cli_load_and_train_options(case):
 FORCED_PATHS = {
     "default": {},
     "filter": {"COLIBRI_B200_FILTER_MIN": "0", "COLIBRI_B200_FILTER_LOG2_MIN": "8", "COLIBRI_B200_FILTER_LOG2": "12", "COLIBRI_B200_HOT": "0", "COLIBRI_B200_SPARSE_DIV": "0",
-               "COLIBRI_B200_DENSE": "0"},
+               "COLIBRI_B200_DENSE": "0", "COLIBRI_B200_FILTER_1BIT": "0"},  # (the 2-bit counters read directly; the other paths read their packed "hit twice" bits)
     "filter+hot+dense": {"COLIBRI_B200_FILTER_MIN": "0", "COLIBRI_B200_FILTER_LOG2_MIN": "10", "COLIBRI_B200_FILTER_LOG2": "16", "COLIBRI_B200_HOT": "2", "COLIBRI_B200_DENSE_MIN": "0",
                          "COLIBRI_B200_DENSE": "48", "COLIBRI_B200_SPARSE_DIV": "0"},
     "list": {"COLIBRI_B200_SPARSE_DIV": "1", "COLIBRI_B200_HOT": "0"},
@@ -97,7 +97,7 @@ FORCED_PATHS = {
 
 def force_path(monkeypatch, name):
     for k in ("COLIBRI_B200_FILTER_MIN", "COLIBRI_B200_FILTER_LOG2_MIN", "COLIBRI_B200_FILTER_LOG2", "COLIBRI_B200_HOT", "COLIBRI_B200_HOT_MIN", "COLIBRI_B200_DENSE",
-              "COLIBRI_B200_DENSE_MIN", "COLIBRI_B200_SPARSE_DIV", "COLIBRI_B200_NO_FILTER", "COLIBRI_B200_PART_MIN", "COLIBRI_B200_PART_ALL"):
+              "COLIBRI_B200_DENSE_MIN", "COLIBRI_B200_SPARSE_DIV", "COLIBRI_B200_NO_FILTER", "COLIBRI_B200_PART_MIN", "COLIBRI_B200_PART_ALL", "COLIBRI_B200_FILTER_1BIT"):
         monkeypatch.delenv(k, raising=False)
     for k, v in FORCED_PATHS[name].items():
         monkeypatch.setenv(k, v)

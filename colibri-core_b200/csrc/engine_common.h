@@ -266,7 +266,8 @@ struct Tuning {
                                             // (half the footprint in L2: level 3 of the 100 M-token corpus 2.49 -> 2.30 ms)
     int      hot_mode        = 1;           // COLIBRI_B200_HOT: per-block hot-key cache 0 never, 1 levels >= hot_min, 2 always
     uint64_t hot_min         = 1ull << 25;  // COLIBRI_B200_HOT_MIN
-    uint32_t dense_dim       = 2048;        // COLIBRI_B200_DENSE: side of the directly addressed square of level 2 (0 = off)
+    uint32_t dense_dim       = 3072;        // COLIBRI_B200_DENSE: side of the directly addressed square of level 2 (0 = off).  Measured with the partitioned level 2,
+                                            // 100 M tokens: 1024 -> 9.81 ms per step, 2048 -> 9.48, 3072 -> 9.25, 4096 -> 9.45 (the 64 MB square no longer lives in L2)
     uint64_t dense_min       = 1ull << 25;  // COLIBRI_B200_DENSE_MIN
     uint64_t part_min        = 1ull << 26;  // COLIBRI_B200_PART_MIN: smallest level (upper bound of its windows) counted on the partitioned path (partition.cu)
     bool     part_all        = false;       // COLIBRI_B200_PART_ALL: every level >= part_min, not only level 2 with its dense square (measured: the later

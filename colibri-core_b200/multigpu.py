@@ -298,7 +298,7 @@ def _train_distributed(engine, dist, torch, mintokens=2, maxlength=5, skipgrams=
     peers = getattr(engine, "peers", None)
     # dense pairs of level 2: decided from global quantities only, so that every rank decides alike (the ids of level 2 depend on it)
     dense_t = None
-    dense_dim = min(int(os.environ.get("COLIBRI_B200_DENSE", "2048")), nclasses, 16384)
+    dense_dim = min(int(os.environ.get("COLIBRI_B200_DENSE", "3072")), nclasses, 16384)
     if hasattr(engine, "enable_dense") and dense_dim >= 2 and global_tokens // world >= int(os.environ.get("COLIBRI_B200_DENSE_MIN", str(1 << 25))):
         dense_t = engine.enable_dense(dense_dim)
     while peers is not None and found and n <= maxlength and prev_kept > 0:

@@ -85,12 +85,12 @@ FORCED_PATHS = {
                          "COLIBRI_B200_DENSE": "48", "COLIBRI_B200_SPARSE_DIV": "0"},
     "list": {"COLIBRI_B200_SPARSE_DIV": "1", "COLIBRI_B200_HOT": "0"},
     "bench": {"COLIBRI_B200_FILTER_MIN": "0", "COLIBRI_B200_FILTER_LOG2_MIN": "12", "COLIBRI_B200_FILTER_LOG2": "20", "COLIBRI_B200_HOT": "2", "COLIBRI_B200_DENSE_MIN": "0",
-              "COLIBRI_B200_DENSE": "2048", "COLIBRI_B200_SPARSE_DIV": "1"},
+              "COLIBRI_B200_DENSE": "3072", "COLIBRI_B200_SPARSE_DIV": "1"},
     # the partitioned counting path (csrc/partition.cu: what bench.py's large levels run), alone and with the dense square + list mode around it
     "part": {"COLIBRI_B200_PART_MIN": "0", "COLIBRI_B200_PART_ALL": "1", "COLIBRI_B200_SPARSE_DIV": "0", "COLIBRI_B200_DENSE": "0"},
     "part+dense+list": {"COLIBRI_B200_PART_MIN": "0", "COLIBRI_B200_PART_ALL": "1", "COLIBRI_B200_DENSE_MIN": "0", "COLIBRI_B200_DENSE": "48", "COLIBRI_B200_SPARSE_DIV": "1"},
     # what bench.py runs at 100 M tokens: level 2 partitioned around its dense square, the later levels on the HBM table with filter, hot keys and list mode
-    "part-bench": {"COLIBRI_B200_PART_MIN": "0", "COLIBRI_B200_DENSE_MIN": "0", "COLIBRI_B200_DENSE": "2048", "COLIBRI_B200_SPARSE_DIV": "4", "COLIBRI_B200_FILTER_MIN": "0",
+    "part-bench": {"COLIBRI_B200_PART_MIN": "0", "COLIBRI_B200_DENSE_MIN": "0", "COLIBRI_B200_DENSE": "3072", "COLIBRI_B200_SPARSE_DIV": "4", "COLIBRI_B200_FILTER_MIN": "0",
                    "COLIBRI_B200_FILTER_LOG2_MIN": "12", "COLIBRI_B200_FILTER_LOG2": "20", "COLIBRI_B200_HOT": "2"},
 }
 

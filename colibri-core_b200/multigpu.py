@@ -471,7 +471,18 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
 
     ntok = int(a.tokens)
     opts = cb.PatternModelOptions(MINTOKENS=a.mintokens, MAXLENGTH=a.maxlength, DOSKIPGRAMS_EXHAUSTIVE=a.skipgrams, streamed=0 if a.skipgrams else 1, QUIET=1, device=local)
-    corpus = cb.Corpus.synthetic(ntok, vocab=a.vocab, seed=a.seed, device=local, first_token=rank * ntok)
+    strong = getattr(a, "scaling", "weak") == "strong"
+    if strong:
+        # one corpus of --tokens for the whole job, cut at sentence boundaries: every rank trains 1/N of it (the model is the 1-GPU model)
+        full = cb.Corpus.synthetic(ntok, vocab=a.vocab, seed=a.seed, device=local)
+        body = full.download()
+        full.close()
+        cuts = cut_at_sentences(body, world)
+        shard_bytes = np.ascontiguousarray(body[cuts[rank]:cuts[rank + 1]])
+        corpus = cb.Corpus.from_host_pointer(shard_bytes.ctypes.data, shard_bytes.size, device=local)
+        ntok = max(ntok // world, 1)
+    else:
+        corpus = cb.Corpus.synthetic(ntok, vocab=a.vocab, seed=a.seed, device=local, first_token=rank * ntok)
 
     def barrier():
         dist.barrier()
@@ -558,8 +569,8 @@ def bench(a, dist, rank, world, local, metric, unit, workload, ClockSampler, mea
         peak, peak_src = measured_peaks()
         line = {
             "metric": metric, "value": tokens * a.steps / elapsed, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * elapsed / a.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 (integer)", "data": "synthetic",
-            "config": {"workload": workload + " PER GPU (shards of one global stream)", "global_tokens": tokens, "patterns": int(npat[0].item()),
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8/u32 (integer)", "data": "synthetic",
+            "config": {"workload": workload + (" cut into %d shards at sentence boundaries" % world if strong else " PER GPU (shards of one global stream)"), "global_tokens": tokens, "patterns": int(npat[0].item()),
                        "parallelism": "corpus sharded by sentence x%d, model hash-partitioned; windows shipped to their owners by %s" % (
                            world, "NVLink peer stores from the split/reply kernels (symmetric memory)" if peers is not None else "NCCL all-to-all"),
                        "l2": "inputs exceed L2", "timing": "max over ranks of max(CUDA events, wall clock) around K steps"},

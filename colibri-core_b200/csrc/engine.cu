@@ -434,6 +434,13 @@ struct Trainer {
     int  level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint64_t npos, const uint32_t* list, uint64_t nlist, uint64_t wbound, uint32_t dense, uint32_t* dense_cnt,
                            uint32_t t, uint32_t* tok_ext, Segment& sg, bool& overflow, double hashed_share, DevBuf<uint32_t>* slot_index, bool pre_hist);
     int  part_small_layout(const PartPlan& pl);
+    // windows the partitions are sized for.  COLIBRI_B200_PART_SCALE (a test knob) scales it: a value far below 1 makes partitions that cannot fit their
+    // shared-memory tables, which exercises the overflow -> HBM-table fallback
+    static uint64_t plan_bound(uint64_t wbound, double hashed_share) {
+        const char*  e     = getenv("COLIBRI_B200_PART_SCALE");
+        const double scale = e && *e ? atof(e) : 1.0;
+        return (uint64_t)((double)wbound * std::min(1.0, hashed_share) * scale) + 1024;
+    }
     int  l2_pin(const void* base, size_t bytes);
     void l2_unpin();
     const uint32_t*            tok_for_sink = nullptr;
@@ -719,7 +726,7 @@ int Trainer::level_partitioned(int n, const uint32_t* prev, uint32_t* cur, uint6
                                uint32_t* dense_cnt, uint32_t t, uint32_t* tok_ext, Segment& sg, bool& overflow, double hashed_share, DevBuf<uint32_t>* slot_index, bool pre_hist) {
     overflow = false;
     // partitions are sized for the windows expected to become records (an estimate that is too low shows up as an overflow, not as a wrong count)
-    const PartPlan pl  = part_plan((uint64_t)((double)wbound * std::min(1.0, hashed_share)) + 1024);
+    const PartPlan pl  = part_plan(plan_bound(wbound, hashed_share));
     const uint32_t p1n = 1u << pl.b1;
     TRY(part_small_layout(pl));  // hist1 | off1 (+1) | cursor1 | group_tot | group_base (+1) | off (+1) | kept_of (first: hist2) | dst_off (+1)
     uint32_t* hist1      = part_small.p;
@@ -976,7 +983,7 @@ int Trainer::run() {
         const uint32_t dense2  = (bound2 >= tune.dense_min && tok_ext_cells) ? std::min<uint32_t>(tune.dense_dim, nclasses) : 0;
         if (dense2 && bound2 > 0 && tune.use_partition(wbound2, true) && wbound2 < 0xFFFFFFF0ull && m->totaltokens && !getenv("COLIBRI_B200_NO_FUSE_ID1")) {
             const double   f  = (double)dense_tokens / (double)m->totaltokens;
-            const PartPlan pl = part_plan((uint64_t)((double)wbound2 * std::min(1.0, 1.1 * (1.0 - f * f))) + 1024);
+            const PartPlan pl = part_plan(plan_bound(wbound2, 1.1 * (1.0 - f * f)));
             const uint64_t dense_cells2 = (uint64_t)dense2 * dense2;
             TRY(part_small_layout(pl));
             if (filter.n < dense_cells2 + 8) TRY(filter.alloc(dev, dense_cells2 + 8));

@@ -427,3 +427,20 @@ def test_tokeniser_following_a_chunked_copy_matches_oracle(golden, chunk, monkey
         assert len(lens) == len(want) and sm["passes"] == want.passes, (name, chunk)
         for k in env:
             monkeypatch.delenv(k)
+
+
+def test_partition_overflow_falls_back_to_the_table_path(monkeypatch):
+    """A partition with more distinct keys than its shared-memory table holds raises a flag and the level is rerun on the HBM table (engine.cu:
+    level_partitioned -> overflow).  Forced by sizing the partitions for a hundredth of the windows; with and without the dense square."""
+    monkeypatch.setenv("COLIBRI_B200_PART_MIN", "0")
+    monkeypatch.setenv("COLIBRI_B200_PART_ALL", "1")
+    monkeypatch.setenv("COLIBRI_B200_PART_SCALE", "0.01")
+    corpus = cb().Corpus.synthetic(3000000, vocab=100000, seed=11, mean_sentence=22)
+    want = oracle.train(corpus.download(), mintokens=2, maxlength=4)
+    for dense in ("0", "64"):
+        monkeypatch.setenv("COLIBRI_B200_DENSE_MIN", "0")
+        monkeypatch.setenv("COLIBRI_B200_DENSE", dense)
+        m = cb().train(corpus, MINTOKENS=2, MAXLENGTH=4, QUIET=1)
+        got = to_flat(m)
+        assert got.passes == want.passes and got.same_patterns(want)
+        assert m.level(2)["path"] == "table"  # the partitioned attempt was abandoned

@@ -966,6 +966,7 @@ int Trainer::run() {
     DevBuf<uint32_t>        bitmap;  // survivor bit per table slot of the level just pruned
     DevBuf<uint32_t>        filter;  // 2-bit occurrence filter of the level being counted
     DevBuf<uint32_t>        filter1; // its "hit twice" bits, packed (Tuning::filter_1bit)
+    DevBuf<uint32_t>        class_bits;  // one bit per class: kept at level 1 (launch_make_id1_hist)
     DevBuf<uint32_t>        slot_index;  // indexed models: table slot -> survivor index + 1
     DevBuf<uint32_t>        list_cur, list_next;  // list mode: positions whose newest id is non-zero (see kernels.cu: load_window)
     uint64_t                nlist = 0;
@@ -991,7 +992,8 @@ int Trainer::run() {
             CUDA_TRY(cudaMemsetAsync(part_small.p, 0, ((size_t)1 << pl.b1) * sizeof(uint32_t), s));
             CUDA_TRY(cudaMemsetAsync(filter.p, 0, dense_cells2 * sizeof(uint32_t), s));
             TRY(zero_stats());
-            launches += launch_make_id1_hist(s, tok.p, npos, count1.p, t1, ids[1].p, dense2, filter.p, part_small.p, pl, d_stats.p, sms);
+            TRY(class_bits.alloc(dev, (uint64_t)(nclasses + 255) / 256 * 8 + 8));
+            launches += launch_make_id1_hist(s, tok.p, npos, count1.p, nclasses, t1, class_bits.p, ids[1].p, dense2, filter.p, part_small.p, pl, d_stats.p, sms);
             timer.end(hc);
             pre_hist2 = true;
             m->levels[2].fused_id1 = 1;

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(1024) scan_block_counts_kernel(uint32_t* __res
 __global__ void __launch_bounds__(256) tokenise_write_kernel(const uint8_t* __restrict__ corpus, const uint32_t* __restrict__ blk_offsets, uint32_t* __restrict__ tok,
                                                              DeviceStats* __restrict__ st) {
     __shared__ __align__(16) uint8_t tile[16 + kTokTile];
+    __shared__ uint32_t staged[kTokTile];  // the tile's tokens in order (a token is at least one byte): written out coalesced below
     __shared__ uint32_t warp_tot[8];
     __shared__ uint64_t scratch[8];
     const uint8_t* base = corpus + (uint64_t)blockIdx.x * kTokTile;
@@ -93,9 +94,14 @@ __global__ void __launch_bounds__(256) tokenise_write_kernel(const uint8_t* __re
     uint32_t incl = warp_inclusive_scan(c);
     if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
     __syncthreads();
-    uint32_t woff = 0;
-    for (uint32_t i = 0; i < (threadIdx.x >> 5); ++i) woff += warp_tot[i];
-    uint64_t out = (uint64_t)blk_offsets[blockIdx.x] + woff + (incl - c);
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) {
+        const uint32_t t = warp_tot[i];
+        woff += i < (threadIdx.x >> 5) ? t : 0u;
+        total += t;
+    }
+    uint32_t at = woff + (incl - c);
 
     uint32_t ntok = 0, maxc = 0, err = 0;
     const uint8_t* mine = tile + 16 + threadIdx.x * 16;
@@ -113,10 +119,13 @@ __global__ void __launch_bounds__(256) tokenise_write_kernel(const uint8_t* __re
         if (len > 1 && q[0] == 0) err |= kErrNonCanonical;
         uint32_t cls = (uint32_t)val;
         if (cls == 3 || cls == 4) err |= kErrReservedClass;
-        tok[out++] = cls;
+        staged[at++] = cls;
         ntok += cls != 0;
         maxc = max(maxc, cls);
     }
+    __syncthreads();
+    uint32_t* dst = tok + blk_offsets[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < total; i += 256) dst[i] = staged[i];
     uint64_t tot = block_reduce_sum(ntok, scratch);
     maxc         = warp_reduce_max(maxc);
     if (threadIdx.x == 0 && tot) atomicAdd(&st->totaltokens, (unsigned long long)tot);
@@ -961,7 +970,22 @@ int launch_pack_nm(cudaStream_t s, uint32_t* nm, uint64_t count, uint32_t n) {
 __device__ __forceinline__ uint32_t pattern_bytes(const uint32_t* __restrict__ tok, uint32_t pos, uint32_t nm, uint8_t* out) {
     uint32_t n = nm & 0xFFu, mask = nm >> 8, len = 0;
     if (n == 1) return out ? varint_put(out, pos) : varint_len(pos);
-    for (uint32_t j = 0; j < n; ++j) {
+    // the first eight tokens are fetched before any of them is used: one memory latency per pattern instead of one per token
+    uint32_t head[8];
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j) head[j] = j < n ? __ldg(tok + pos + j) : 0u;
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j) {
+        if (j < n) {
+            if ((mask >> j) & 1u) {
+                if (out) out[len] = 3;
+                len += 1;
+            } else {
+                len += out ? varint_put(out + len, head[j]) : varint_len(head[j]);
+            }
+        }
+    }
+    for (uint32_t j = 8; j < n; ++j) {
         bool gap = j < 24 && ((mask >> j) & 1u);
         if (gap) {
             if (out) out[len] = 3;
@@ -983,10 +1007,30 @@ __global__ void __launch_bounds__(256) export_lengths_kernel(const uint32_t* __r
         lens16[i]  = (uint16_t)l;  // <= 255 tokens x 5 bytes
     }
 }
+// the 256 patterns of a block are neighbours in the key blob: their bytes are put together in shared memory and leave as aligned words
+// (a block whose patterns are too long for the stage writes them directly)
+constexpr uint32_t kKeyStage = 12288;
 __global__ void __launch_bounds__(256) export_write_kernel(const uint32_t* __restrict__ tok, const uint32_t* __restrict__ sv_pos, const uint32_t* __restrict__ sv_nm,
                                                            const uint64_t* __restrict__ off, uint64_t n, uint8_t* __restrict__ keys) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) pattern_bytes(tok, sv_pos[i], sv_nm[i], keys + off[i]);
+    __shared__ __align__(16) uint8_t stage[kKeyStage];
+    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x, i = first + threadIdx.x;
+    const uint64_t last  = first + blockDim.x < n ? first + blockDim.x : n;
+    const uint64_t base = off[first], span = off[last] - base;
+    if (span > kKeyStage) {
+        if (i < n) pattern_bytes(tok, sv_pos[i], sv_nm[i], keys + off[i]);
+        return;
+    }
+    if (i < n) pattern_bytes(tok, sv_pos[i], sv_nm[i], stage + (off[i] - base));
+    __syncthreads();
+    uint8_t*       dst  = keys + base;
+    const uint32_t lead = min((uint32_t)span, (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3));
+    const uint32_t nw   = ((uint32_t)span - lead) / 4, tail = lead + nw * 4;
+    if (threadIdx.x < lead) dst[threadIdx.x] = stage[threadIdx.x];
+    for (uint32_t w = threadIdx.x; w < nw; w += blockDim.x) {
+        const uint8_t* q = stage + lead + 4 * w;
+        reinterpret_cast<uint32_t*>(dst + lead)[w] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+    }
+    if (tail + threadIdx.x < span) dst[tail + threadIdx.x] = stage[tail + threadIdx.x];
 }
 // exclusive scan u32 -> u64 over n items, out has n+1 entries (out[n] = total).  Three small kernels, 2048 items per block.
 constexpr int kScanItems = 2048;

@@ -106,9 +106,10 @@ PartPlan part_plan(uint64_t window_bound);  // <= 256 windows per partition on a
 int launch_part_hist(cudaStream_t s, const uint32_t* prev, const uint32_t* list, uint64_t nitems, uint32_t dense, uint32_t* dense_cnt, uint32_t* hist1, const PartPlan& pl,
                      DeviceStats* st, int sms);
 // make_id1 + pass A of a dense level 2 in one sweep over the tokens: id1[0 .. npos] as launch_make_id1 writes them, and hist1 / dense_cnt / st->valid_windows
-// as launch_part_hist would leave them for level 2 (hist1, dense_cnt zeroed by the caller; dense > 0)
-int launch_make_id1_hist(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* count1, uint32_t threshold, uint32_t* id1, uint32_t dense, uint32_t* dense_cnt,
-                         uint32_t* hist1, const PartPlan& pl, DeviceStats* st, int sms);
+// as launch_part_hist would leave them for level 2 (hist1, dense_cnt zeroed by the caller; dense > 0).  keep_bits: scratch of (nclasses + 255) / 256 * 8 words
+// (one bit per class: does it stay at level 1); every token is a class below nclasses
+int launch_make_id1_hist(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* count1, uint32_t nclasses, uint32_t threshold, uint32_t* keep_bits, uint32_t* id1,
+                         uint32_t dense, uint32_t* dense_cnt, uint32_t* hist1, const PartPlan& pl, DeviceStats* st, int sms);
 // out[0..n] = exclusive scan of counts[0..n) (+ *base_ptr if given), out2 (may be NULL) = a second copy of out[0..n); n <= 2048 is cheap, larger n works
 int launch_part_bases(cudaStream_t s, const uint32_t* counts, uint32_t n, uint32_t* out, uint32_t* out2, const unsigned long long* base_ptr);
 // pass B: records (key, position) of the hashed windows grouped by their b1 bits (cursor1 = a copy of the partition offsets, advanced by the kernel);

@@ -99,10 +99,19 @@ __global__ void __launch_bounds__(256) part_hist_kernel(const uint32_t* __restri
 // ---- level-1 ids and pass A of level 2 in one sweep -----------------------------------------------------------------------------------
 // make_id1 (kernels.cu) streams the tokens once to write id1[p] = class of p, or 0 when the class was pruned or p is a delimiter; level 2's pass A would
 // stream id1 right afterwards to count the dense pairs and take the first-level histogram.  When level 2 is known to run on the partitioned path
-// the two are one kernel: the atomics of pass A hide behind the token stream (0.35 + 0.70 ms -> 0.45 ms at 100 M tokens).
+// the two are one kernel: the atomics of pass A hide behind the token stream.
 // dynamic shared memory: hist1 u32[nbins] | hot u32[64 * 64]
+// keep[c] = 1 if class c stays at level 1 (count1[c] >= threshold), one bit per class: 12.5 KB for 100 000 classes, at home in L1 where the
+// 400 KB of counts are not -- the id sweep below waits on its dependent loads, not on bandwidth
+__global__ void __launch_bounds__(256) class_keep_bits_kernel(const uint32_t* __restrict__ count1, uint32_t nclasses, uint32_t threshold, uint32_t* __restrict__ keep) {
+    const uint32_t i    = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool     k    = i != 0 && i < nclasses && count1[i] >= threshold;
+    const uint32_t bits = __ballot_sync(0xffffffffu, k);
+    if (lane_id() == 0) keep[i >> 5] = bits;
+}
+
 __global__ void __launch_bounds__(256) make_id1_hist_kernel(const uint32_t* __restrict__ tok, uint64_t n /* entries of id1 to write: positions + 1 */,
-                                                            const uint32_t* __restrict__ count1, uint32_t threshold, uint32_t* __restrict__ id1, uint32_t dense,
+                                                            const uint32_t* __restrict__ keep, uint32_t* __restrict__ id1, uint32_t dense,
                                                             uint32_t* __restrict__ dense_cnt, uint32_t* __restrict__ hist, uint32_t nbins, int shift1, DeviceStats* __restrict__ st) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t scratch[8];
@@ -111,7 +120,7 @@ __global__ void __launch_bounds__(256) make_id1_hist_kernel(const uint32_t* __re
     for (uint32_t i = threadIdx.x; i < nbins + kHotSide * kHotSide; i += blockDim.x) h1[i] = 0;
     __syncthreads();
     uint32_t valid = 0;
-    auto     idof  = [&](uint32_t c) { return (c != 0 && __ldg(count1 + c) >= threshold) ? c : 0u; };
+    auto     idof  = [&](uint32_t c) { return ((__ldg(keep + (c >> 5)) >> (c & 31u)) & 1u) ? c : 0u; };
     auto     one   = [&](uint32_t a, uint32_t b) {
         if (a == 0 || b == 0) return;
         ++valid;
@@ -122,14 +131,27 @@ __global__ void __launch_bounds__(256) make_id1_hist_kernel(const uint32_t* __re
         }
         atomicAdd(&h1[part_of(table_hash_u64(((unsigned long long)a << 32) | b), shift1)], 1u);
     };
+    // the tokens of the next round are on their way while this round's are looked up and counted (the token array has positions + 8 entries,
+    // zeros behind the last position; lane 31 also needs the first token of the next lane group)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
-    for (uint64_t p0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;; p0 += stride) {
+    auto fetch = [&](uint64_t p, uint4& t, uint32_t& edge) {
+        t    = make_uint4(0, 0, 0, 0);
+        edge = 0;
+        if (p < n) t = __ldcs(reinterpret_cast<const uint4*>(tok + p));
+        if (lane_id() == 31 && p + 4 < n) edge = __ldg(tok + p + 4);
+    };
+    uint64_t p0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    uint4    t;
+    uint32_t edge;
+    fetch(p0, t, edge);
+    for (;; p0 += stride) {
         if (p0 - (uint64_t)lane_id() * 4 >= n) break;  // whole warps leave together: the shuffle below always sees 32 lanes
-        uint4 t = make_uint4(0, 0, 0, 0);
-        if (p0 < n) t = __ldcs(reinterpret_cast<const uint4*>(tok + p0));  // the token array has positions + 8 entries, zeros behind the last position
+        uint4    tn;
+        uint32_t edgen;
+        fetch(p0 + stride, tn, edgen);
         const uint4 x = make_uint4(idof(t.x), idof(t.y), idof(t.z), idof(t.w));
         uint32_t nxt = __shfl_down_sync(0xffffffffu, x.x, 1);
-        if (lane_id() == 31) nxt = p0 + 4 < n ? idof(__ldg(tok + p0 + 4)) : 0u;
+        if (lane_id() == 31) nxt = idof(edge);
         if (p0 < n) {
             __stcs(reinterpret_cast<uint4*>(id1 + p0), x);  // (id1 has positions + 8 entries; what lies behind n is zero because the tokens there are)
             one(x.x, x.y);
@@ -137,6 +159,8 @@ __global__ void __launch_bounds__(256) make_id1_hist_kernel(const uint32_t* __re
             one(x.z, x.w);
             one(x.w, nxt);
         }
+        t    = tn;
+        edge = edgen;
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < nbins; i += blockDim.x)
@@ -800,14 +824,15 @@ int launch_part_hist(cudaStream_t s, const uint32_t* prev, const uint32_t* list,
     return 1;
 }
 
-int launch_make_id1_hist(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* count1, uint32_t threshold, uint32_t* id1, uint32_t dense, uint32_t* dense_cnt,
-                         uint32_t* hist1, const PartPlan& pl, DeviceStats* st, int sms) {
+int launch_make_id1_hist(cudaStream_t s, const uint32_t* tok, uint64_t npos, const uint32_t* count1, uint32_t nclasses, uint32_t threshold, uint32_t* keep_bits, uint32_t* id1,
+                         uint32_t dense, uint32_t* dense_cnt, uint32_t* hist1, const PartPlan& pl, DeviceStats* st, int sms) {
     const uint32_t nbins  = 1u << pl.b1;
     const size_t   smem   = (size_t)nbins * 4 + kHotSide * kHotSide * 4;
     const uint64_t n      = npos + 1;
     const unsigned grid   = (unsigned)std::min<uint64_t>((n + 1023) / 1024, (uint64_t)sms * 8);
-    make_id1_hist_kernel<<<grid, 256, smem, s>>>(tok, n, count1, threshold, id1, dense, dense_cnt, hist1, nbins, 64 - pl.b1, st);
-    return 1;
+    class_keep_bits_kernel<<<(nclasses + 255) / 256, 256, 0, s>>>(count1, nclasses, threshold, keep_bits);
+    make_id1_hist_kernel<<<grid, 256, smem, s>>>(tok, n, keep_bits, id1, dense, dense_cnt, hist1, nbins, 64 - pl.b1, st);
+    return 2;
 }
 
 int launch_part_bases(cudaStream_t s, const uint32_t* counts, uint32_t n, uint32_t* out, uint32_t* out2, const unsigned long long* base_ptr) {

@@ -6,7 +6,7 @@ timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 --timeout 300 -p no:c
 timeout 600 python bench.py > gpurun_out/bench_$T.json 2> gpurun_out/bench_$T.err; cut -c1-1500 gpurun_out/bench_$T.json; tail -3 gpurun_out/bench_$T.err
 Q="--no-cpu-baseline --no-e2e --no-extra --no-digest"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 1 $Q > gpurun_out/ncu_launch_$T.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"make_id1_hist|part_hist|part_split|part_count|part_gather|count_ngrams|ngram_filter|filter_to_bitmap" -s 14 -c 14 -f -o gpurun_out/prof_count_$T python bench.py --steps 2 --warmup 1 $Q > gpurun_out/ncu_full_$T.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"make_id1_hist|part_hist|part_split|part_count|part_gather|count_ngrams|ngram_filter|filter_to_bitmap" -s 14 -c 28 -f -o gpurun_out/prof_count_$T python bench.py --steps 2 --warmup 1 $Q > gpurun_out/ncu_full_$T.log 2>&1
 tail -2 gpurun_out/ncu_full_$T.log | cut -c1-200
 COLIBRI_B200_HOT=2 COLIBRI_B200_FILTER_MIN=0 COLIBRI_B200_FILTER_LOG2=16 COLIBRI_B200_DENSE_MIN=0 COLIBRI_B200_DENSE=64 COLIBRI_B200_PART_MIN=0 timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python -c "
 import colibri_core_b200 as cb

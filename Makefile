@@ -19,7 +19,7 @@ $(LIBDIR)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.h $(CSRC)/device_utils.c
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/kernels.ptxas.log || (cat $(LIBDIR)/kernels.ptxas.log; false)
 
-$(LIBDIR)/engine.o: $(CSRC)/engine.cu $(CSRC)/kernels.h $(CSRC)/shard.h $(CSRC)/engine_common.h include/colibri_b200.h
+$(LIBDIR)/engine.o: $(CSRC)/engine.cu $(CSRC)/relations.h $(CSRC)/kernels.h $(CSRC)/shard.h $(CSRC)/engine_common.h include/colibri_b200.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/engine.ptxas.log || (cat $(LIBDIR)/engine.ptxas.log; false)
 
@@ -35,7 +35,7 @@ $(LIBDIR)/partition.o: $(CSRC)/partition.cu $(CSRC)/kernels.h $(CSRC)/device_uti
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/partition.ptxas.log || (cat $(LIBDIR)/partition.ptxas.log; false)
 
-$(LIBDIR)/relations.o: $(CSRC)/relations.cu $(CSRC)/kernels.h $(CSRC)/engine_common.h $(CSRC)/device_utils.cuh include/colibri_b200.h
+$(LIBDIR)/relations.o: $(CSRC)/relations.cu $(CSRC)/relations.h $(CSRC)/kernels.h $(CSRC)/engine_common.h $(CSRC)/device_utils.cuh include/colibri_b200.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(LIBDIR)/relations.ptxas.log || (cat $(LIBDIR)/relations.ptxas.log; false)
 

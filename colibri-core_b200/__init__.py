@@ -152,6 +152,7 @@ def library():
     L.colibri_b200_rindex_sentence_starts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.colibri_b200_rindex_query.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.colibri_b200_rindex_cooc.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, _u64p]
+    L.colibri_b200_rindex_cooc_of.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, _u64p]
     L.colibri_b200_hash64_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
     L.colibri_b200_synth_corpus.argtypes = [C.POINTER(CSynthParams), C.c_int, C.POINTER(C.c_void_p)]
     _lib = L
@@ -497,6 +498,15 @@ class ReverseIndex:
         if n.value:
             _check(library().colibri_b200_rindex_cooc(self._h, 1 if left else 0, p.ctypes.data, q.ctypes.data, j.ctypes.data, n.value, C.byref(n)))
         return p[:n.value], q[:n.value], j[:n.value]
+
+    def cooc_of(self, pattern: int):
+        """getcooc of the pattern with export index `pattern` (both directions, no overlap): (index of Q, count) as two arrays."""
+        n = C.c_uint64()
+        _check(library().colibri_b200_rindex_cooc_of(self._h, pattern, None, None, 0, C.byref(n)))
+        q, c = np.empty(n.value, dtype=np.uint32), np.empty(n.value, dtype=np.uint64)
+        if n.value:
+            _check(library().colibri_b200_rindex_cooc_of(self._h, pattern, q.ctypes.data, c.ctypes.data, n.value, C.byref(n)))
+        return q[:n.value], c[:n.value]
 
     def close(self):
         if self._h:

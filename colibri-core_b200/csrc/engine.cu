@@ -6,6 +6,7 @@
 // (:1233-1243), MINLENGTH clean-up (:1221-1229, :1337-1341).  No CPU implementation of the counting exists here:
 // without a CUDA device every entry point fails with COLIBRI_E_CUDA.
 #include "engine_common.h"
+#include "relations.h"
 #include "spooky.h"
 
 using namespace colibri;
@@ -1937,6 +1938,7 @@ extern "C" void colibri_b200_rindex_free(colibri_b200_rindex* r) {
     if (!r) return;
     cudaSetDevice(r->device);
     cudaStreamSynchronize(r->stream);
+    colibri::rindex_cooc_forget(r);
     delete r;
 }
 extern "C" int colibri_b200_rindex_info(const colibri_b200_rindex* r, uint64_t out[4]) {

@@ -640,6 +640,28 @@ class IndexedPatternModel : public DevicePatternModel<IndexedData, INDEXEDPATTER
     /// getrightcooc / getleftcooc (reference :3460-3493, :3502-3531) with the reference's arithmetic -- see include/colibri_b200.h, colibri_b200_rindex_cooc.
     t_relationmap getrightcooc(const Pattern& pattern, unsigned int occurrencethreshold = 0, int category = 0, unsigned int size = 0) { return cooc_of(pattern, 0, occurrencethreshold, category, size); }
     t_relationmap getleftcooc(const Pattern& pattern, unsigned int occurrencethreshold = 0, int category = 0, unsigned int size = 0) { return cooc_of(pattern, 1, occurrencethreshold, category, size); }
+    /// getcooc (reference :3543-3576): both directions, neither overlapping nor adjacent; counted on the device (colibri_b200_rindex_cooc_of), the
+    /// reference's filters applied here (threshold on the neighbour's occurrence count, category, size, ordersignificant, prunerelations)
+    t_relationmap getcooc(const Pattern& pattern, unsigned int occurrencethreshold = 0, int category = 0, unsigned int size = 0, bool ordersignificant = false) {
+        ensure_rindex();
+        if (!this->has(pattern)) throw NoSuchPattern();
+        const uint64_t idx = index_of(pattern);
+        uint64_t n = 0;
+        if (colibri_b200_rindex_cooc_of(rindex_, idx, nullptr, nullptr, 0, &n) != COLIBRI_OK) colibri_b200_detail::fail(colibri_b200_last_error());
+        std::vector<uint32_t> q(n);
+        std::vector<uint64_t> c(n);
+        if (n && colibri_b200_rindex_cooc_of(rindex_, idx, q.data(), c.data(), n, &n) != COLIBRI_OK) colibri_b200_detail::fail(colibri_b200_last_error());
+        t_relationmap out;
+        for (uint64_t k = 0; k < n; ++k) {
+            const Pattern nb = pattern_at(q[k]);
+            if (ordersignificant && nb < pattern) continue;
+            if (occurrencethreshold && (counts_[q[k]] < occurrencethreshold || c[k] < occurrencethreshold)) continue;
+            if (category && (int)nb.category() != category) continue;
+            if (size && nb.n() != size) continue;
+            out[nb] = c[k];
+        }
+        return out;
+    }
     /// reference :3582-3585, the same expression (the product of the two counts is an unsigned 32-bit product there too)
     double npmi(const Pattern& key1, const Pattern& key2, int jointcount) {
         return log((double)jointcount / ((unsigned int)this->occurrencecount(key1) * (unsigned int)this->occurrencecount(key2))) / -log((double)jointcount / (double)totaloccurrences());
@@ -771,16 +793,16 @@ class IndexedPatternModel : public DevicePatternModel<IndexedData, INDEXEDPATTER
         std::sort(cooc_[direction].begin(), cooc_[direction].end(), [](const Rel& a, const Rel& b) { return a.p < b.p || (a.p == b.p && a.q < b.q); });
         cooc_ready_[direction] = true;
     }
+    // the pattern's index in the flat arrays (counts_.size() if it is not there)
+    uint64_t index_of(const Pattern& pattern) const {
+        for (uint64_t i = 0; i < counts_.size(); ++i)
+            if (off_[i + 1] - off_[i] == pattern.bytesize() && memcmp(keys_.data() + off_[i], pattern.data(), pattern.bytesize()) == 0) return i;
+        return counts_.size();
+    }
     t_relationmap cooc_of(const Pattern& pattern, int direction, unsigned int occurrencethreshold, int category, unsigned int size) {
         load_cooc(direction);
         if (!this->has(pattern)) throw NoSuchPattern();
-        // the pattern's index in the flat arrays
-        uint64_t idx = counts_.size();
-        for (uint64_t i = 0; i < counts_.size(); ++i)
-            if (off_[i + 1] - off_[i] == pattern.bytesize() && memcmp(keys_.data() + off_[i], pattern.data(), pattern.bytesize()) == 0) {
-                idx = i;
-                break;
-            }
+        const uint64_t idx = index_of(pattern);
         t_relationmap out;
         auto lo = std::lower_bound(cooc_[direction].begin(), cooc_[direction].end(), (uint32_t)idx, [](const Rel& a, uint32_t v) { return a.p < v; });
         for (; lo != cooc_[direction].end() && lo->p == idx; ++lo) {

@@ -479,6 +479,28 @@ class IndexedPatternModel(_PatternModel):
     def getleftcooc(self, pattern, occurrencethreshold: int = 0, category: int = 0, size: int = 0):
         return iter(self._cooc_of(pattern, True, occurrencethreshold, category, size))
 
+    def getcooc(self, pattern, occurrencethreshold: int = 0, category: int = 0, size: int = 0, ordersignificant: bool = False):
+        """Co-occurrence in both directions without overlap (:3543-3576): (neighbour, count) for every model n-gram that occurs in a sentence
+        of `pattern` and neither overlaps nor touches it; counted on the device (colibri_b200_rindex_cooc_of), filtered here as the reference
+        filters -- neighbours below occurrencethreshold, of another category or size, sorting before `pattern` (ordersignificant), and
+        relations counted less than occurrencethreshold times (prunerelations :3066-3078)."""
+        if pattern not in self:
+            raise KeyError(pattern)
+        keys, _, _ = self._flat()
+        q, c = self._ri().cooc_of(self._index[bytes(pattern)])
+        me = bytes(pattern)
+        out = []
+        for i, n in zip(q.tolist(), c.tolist()):
+            nb = Pattern(keys[i])
+            if ordersignificant and keys[i] < me:  # Pattern::operator< compares the bytes (src/pattern.cpp:1114-1125)
+                continue
+            if (occurrencethreshold and self.occurrencecount(nb) < occurrencethreshold) or (category and nb.category() != category) or (size and len(nb) != size):
+                continue
+            if occurrencethreshold and n < occurrencethreshold:
+                continue
+            out.append((nb, n))
+        return iter(out)
+
     def npmi(self, pattern1, pattern2, jointcount: int) -> float:
         """PatternModel::npmi (:3582-3585): the same expression in double precision (the product of the two counts is a 32-bit product there)."""
         prod = (self.occurrencecount(pattern1) * self.occurrencecount(pattern2)) & 0xFFFFFFFF
@@ -486,13 +508,21 @@ class IndexedPatternModel(_PatternModel):
 
     def computenpmi(self, threshold: float, right: bool = True, left: bool = False):
         """{pattern: {pattern2: npmi}} of the relations that pass the threshold (:3671-3691; right or left co-occurrence)."""
-        if right == left:
-            raise ColibriError(2, "computenpmi over both directions (getcooc) is not on the device path")
+        if not right and not left:
+            return {}
         keys, counts, _ = self._flat()
         total = self.totaloccurrencesingroup(0, 0)
         cnt = {k: int(c) for k, c in zip(keys, counts)}
         out = {}
-        for p, rel in self._cooc_all(left).items():
+        if right and left:  # getcooc of every pattern (:3681-3682): one device pass per pattern
+            rels = {}
+            for i, k in enumerate(keys):
+                q, c = self._ri().cooc_of(i)
+                if len(q):
+                    rels[k] = {keys[b]: n for b, n in zip(q.tolist(), c.tolist())}
+        else:
+            rels = self._cooc_all(left)
+        for p, rel in rels.items():
             for q, j in rel.items():
                 v = math.log(j / ((cnt[p] * cnt[q]) & 0xFFFFFFFF)) / -math.log(j / total)
                 if v >= threshold:

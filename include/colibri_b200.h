@@ -169,6 +169,12 @@ int  colibri_b200_rindex_query(colibri_b200_rindex* r, const uint32_t* sentence,
  * model patterns that start at the same position (s, t), which adds max(0, sl - 1 - (t + |P|)) (right) or max(0, t - |Q|) (left) to joint(P, Q).
  * *nrel = relations found; when the three buffers are given (cap entries each) they receive (index of P, index of Q, joint) in no particular order. */
 int  colibri_b200_rindex_cooc(colibri_b200_rindex* r, int direction, uint32_t* idx_p, uint32_t* idx_q, uint64_t* joint, uint64_t cap, uint64_t* nrel);
+/* getcooc (:3543-3576) of the pattern with export index `pattern`, both directions: count(Q) = pairs (occurrence of P at token t, start t2 of the model
+ * n-gram Q in the same sentence) with t2 + |Q| < t or t2 > t + |P| (no overlap, not adjacent).  *nrel = patterns Q with a count; when both buffers are
+ * given (cap entries each) they receive (index of Q, count) in no particular order.  The reference's occurrencethreshold / category / size /
+ * ordersignificant arguments are filters on this list and live on the host side (host/patternmodel.h, pybinding.py).  Asking twice for the same
+ * pattern (first for *nrel, then with buffers) counts once. */
+int  colibri_b200_rindex_cooc_of(colibri_b200_rindex* r, uint64_t pattern, uint32_t* idx_q, uint64_t* count, uint64_t cap, uint64_t* nrel);
 
 /* ---- models that do not come out of train() */
 /* a pattern set given as flat host arrays (the export form) becomes a device-resident model: replaces building a PatternModel /

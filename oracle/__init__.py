@@ -610,6 +610,35 @@ def cooc(body, patterns: dict, left: bool = False) -> dict:
     return out
 
 
+def cooc_both(body, patterns: dict, occurrencethreshold: int = 0, size: int = 0, ordersignificant: bool = False) -> dict:
+    """getcooc of every pattern (:3543-3576): for every occurrence (s, t) of P and every model pattern Q that starts at a position t2 of the
+    same sentence (getreverseindex_bysentence :1850-1862), one count if the two do not overlap and are not adjacent either --
+    t2 + |Q| < t or t2 > t + |P|.  Neighbours occurring less than occurrencethreshold times or of another size are skipped,
+    ordersignificant skips neighbours that sort before P (Pattern::operator<, src/pattern.cpp:1114-1125: bytewise), and relations counted
+    less than occurrencethreshold times are pruned (:3066-3078).  Returns {(P, Q): count}."""
+    rindex = reverse_index(body, patterns)
+    ntok = {k: len(_split_tokens(k)) for k in patterns}
+    by_sentence = {}
+    for (s, t), here in rindex.items():
+        by_sentence.setdefault(s, []).extend((t, q) for q in here)
+    out = {}
+    for s, items in by_sentence.items():
+        for t, P in items:
+            for t2, Q in items:
+                if ordersignificant and Q < P:
+                    continue
+                if not (t2 + ntok[Q] < t or t2 > t + ntok[P]):
+                    continue
+                if occurrencethreshold and patterns[Q] < occurrencethreshold:
+                    continue
+                if size and ntok[Q] != size:
+                    continue
+                out[(P, Q)] = out.get((P, Q), 0) + 1
+    if occurrencethreshold:
+        out = {k: v for k, v in out.items() if v >= occurrencethreshold}
+    return out
+
+
 def npmi(count1: int, count2: int, joint: int, total: int) -> float:
     """PatternModel::npmi (:3582-3585), the same expression in the same order (the product is an unsigned 32-bit product in the reference)."""
     import math

@@ -5,6 +5,7 @@
 //   G  getreverseindex(ref)            include/patternmodel.h:1746-1824   every position of the corpus
 //   R  getrightcooc(pattern)           :3460-3493                          every pattern
 //   L  getleftcooc(pattern)            :3502-3531
+//   C  getcooc(pattern)                :3543-3576 (both directions, no overlap), defaults; O: the same with occurrencethreshold 2 and ordersignificant
 //   N  npmi() :3582-3585 of every getrightcooc relation that passes the threshold (what computenpmi(map, th, true, false) :3671-3691 collects)
 //   F/X computeflexgrams_fromcooc(th)  :3751-3774                          found, then every flexgram with its occurrence count
 // as text lines (patterns as hex of their bytes), sorted, so that tests/golden/make_golden_relations.py can pin the oracle to them.
@@ -87,6 +88,10 @@ int main(int argc, char** argv) {
         for (const auto& kv : r) lines.push_back("R " + hexof(p) + " " + hexof(kv.first) + " " + std::to_string(kv.second));
         t_relationmap l = model->getleftcooc(p);
         for (const auto& kv : l) lines.push_back("L " + hexof(p) + " " + hexof(kv.first) + " " + std::to_string(kv.second));
+        t_relationmap c = model->getcooc(p);
+        for (const auto& kv : c) lines.push_back("C " + hexof(p) + " " + hexof(kv.first) + " " + std::to_string(kv.second));
+        t_relationmap o = model->getcooc(p, 2, 0, 0, true);
+        for (const auto& kv : o) lines.push_back("O " + hexof(p) + " " + hexof(kv.first) + " " + std::to_string(kv.second));
     }
     // computenpmi(map, threshold, right = true, left = false) keys its result map with PatternPointers into a loop-local Pattern (:3674, :3686: dangling
     // once the iteration moves on), so the map cannot be read back; its content is restated here with the reference's own getrightcooc() and npmi()

@@ -1,5 +1,5 @@
 """Writes tests/golden/golden_relations.json from the UNMODIFIED reference (oracle/_ref/ref_relations, built by `make -C oracle ref` where
-/root/reference is mounted): getreverseindex of every position, getrightcooc / getleftcooc of every pattern, computenpmi (right) and
+/root/reference is mounted): getreverseindex of every position, getrightcooc / getleftcooc / getcooc of every pattern, computenpmi (right) and
 computeflexgrams_fromcooc on a few corpora.  The flexgram cases are kept only where the reference's insert-while-iterating did not bite
 (its result equals the clean iteration of oracle.flexgrams_fromcooc); the others are listed under "reference_diverges"."""
 import json
@@ -34,14 +34,14 @@ def main():
         r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_relations"), "-f", path, "-t", str(kw["t"]), "-l", str(kw["l"]), "-Y", repr(kw["Y"]), "-x"],
                            capture_output=True, text=True, check=True)
         os.unlink(path)
-        case = {"corpus": name, "t": kw["t"], "l": kw["l"], "threshold": kw["Y"], "G": [], "R": [], "L": [], "N": [], "X": []}
+        case = {"corpus": name, "t": kw["t"], "l": kw["l"], "threshold": kw["Y"], "G": [], "R": [], "L": [], "C": [], "O": [], "N": [], "X": []}
         for line in r.stdout.splitlines():
             p = line.split()
             if p[0] == "H":
                 case["header"] = dict(x.split("=") for x in p[1:])
             elif p[0] == "G":
                 case["G"].append([int(p[1]), int(p[2]), p[3:]])
-            elif p[0] in "RL":
+            elif p[0] in "RLCO":
                 case[p[0]].append([p[1], p[2], int(p[3])])
             elif p[0] == "N":
                 case["N"].append([p[1], p[2], float(p[3])])

@@ -78,6 +78,10 @@ int main(int argc, char** argv) {
             test("getleftcooc([06]) relations", lc.size(), (size_t)4);
             test("getleftcooc([06])[06]", (unsigned long long)lc[six], 165ull);
             test("getleftcooc([06])[06 07]", (unsigned long long)lc[Pattern::fromclasses({6, 7})], 12ull);
+            auto bc = im.getcooc(six);  // both directions, no overlap (reference :3543-3576; numbers of oracle/_ref/ref_relations)
+            test("getcooc([06]) relations", bc.size(), (size_t)56);
+            test("getcooc([06])[06]", (unsigned long long)bc[six], 14ull);
+            test("getcooc([06], 2, 0, 0, ordersignificant) relations", im.getcooc(six, 2, 0, 0, true).size(), (size_t)24);
             const size_t before = im.size();
             int          found  = im.computeflexgrams_fromcooc(0.1);
             test("computeflexgrams_fromcooc(0.1) found", found, 43);  // the clean iteration; the reference's own run adds one flexgram of a flexgram

@@ -84,6 +84,15 @@ def test_reverse_index_and_cooccurrence_equal_reference(case, tmp_path):
     for tag, fn in (("R", model.getrightcooc), ("L", model.getleftcooc)):
         got = sorted([bytes(p).hex(), bytes(q).hex(), j] for p in model for q, j in fn(p))
         assert got == sorted(case[tag]), tag
+    # getcooc (both directions, no overlap) of every pattern: defaults, then occurrencethreshold 2 + ordersignificant; one size filter against the oracle
+    got = sorted([bytes(p).hex(), bytes(q).hex(), j] for p in model for q, j in model.getcooc(p))
+    assert got == sorted(case["C"])
+    got = sorted([bytes(p).hex(), bytes(q).hex(), j] for p in model for q, j in model.getcooc(p, occurrencethreshold=2, ordersignificant=True))
+    assert got == sorted(case["O"])
+    pats = {bytes(p): len(v) for p, v in model.items()}
+    want = oracle.cooc_both(body, pats, size=2)
+    got = {(bytes(p), bytes(q)): j for p in model for q, j in model.getcooc(p, size=2)}
+    assert got == want
     # npmi: the same doubles
     got_n = sorted([bytes(p).hex(), bytes(q).hex(), v] for p, rel in model.computenpmi(case["threshold"], right=True, left=False).items() for q, v in rel.items())
     want_n = sorted(case["N"])

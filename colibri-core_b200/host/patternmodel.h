@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <chrono>
 #include <fstream>
 #include <iostream>
 #include <istream>
@@ -65,6 +66,41 @@ class PatternModelOptions {
     bool DEBUG = false;
 };
 
+namespace colibri_b200_detail {
+// where the host side of a call spends its time (seconds, summed over the process): reading the corpus file, the device call (staging +
+// training), taking the flat result over (device -> host), building the unordered_map view, writing the model file.  The CLI prints it.
+struct HostTimes {
+    double read = 0, device = 0, adopt = 0, materialise = 0, write = 0;
+};
+inline HostTimes& host_times() {
+    static HostTimes t;
+    return t;
+}
+struct Stopwatch {
+    double&                               acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit Stopwatch(double& a) : acc(a) {}
+    ~Stopwatch() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+// a whole stream into memory: one read() when the stream can tell its size (a file), byte iterators otherwise
+inline std::vector<unsigned char> read_all(std::istream& in) {
+    std::vector<unsigned char> all;
+    in.seekg(0, std::ios::end);
+    const std::streamoff size = in.good() ? (std::streamoff)in.tellg() : (std::streamoff)-1;
+    in.clear();
+    in.seekg(0);
+    if (size > 0) {
+        all.resize((size_t)size);
+        in.read(reinterpret_cast<char*>(all.data()), size);
+        all.resize((size_t)std::max<std::streamsize>(in.gcount(), 0));
+        in.clear();
+    } else {
+        all.assign((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    }
+    return all;
+}
+}  // namespace colibri_b200_detail
+
 /// A corpus held in host memory (the reference's "reverse index").  Only what the training path uses: load(), sentences().
 class IndexedCorpus {
     std::vector<unsigned char> body_;  // bytes after the 0xA2 0x02 header
@@ -79,7 +115,11 @@ class IndexedCorpus {
             std::cerr << "ERROR: Supplied data file can not be opened. Check whether it exists and whether you have proper permissions..." << std::endl;
             throw InternalError();
         }
-        std::vector<unsigned char> all((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        std::vector<unsigned char> all;
+        {
+            colibri_b200_detail::Stopwatch sw(colibri_b200_detail::host_times().read);
+            all = colibri_b200_detail::read_all(in);
+        }
         if (all.size() < 2 || all[0] != 0xA2 || all[1] != 2) {
             std::cerr << "ERROR: the B200 build reads class-encoded corpora of data version 2 only (0xA2 0x02 header)" << std::endl;
             throw InternalError();
@@ -208,6 +248,7 @@ class DevicePatternModel : public PatternModelInterface {
     /// take over the result of a device call: header numbers + the flat export
     void adopt(colibri_b200_model* h) {
         using colibri_b200_detail::fail;
+        colibri_b200_detail::Stopwatch sw(colibri_b200_detail::host_times().adopt);
         totaltokens  = colibri_b200_model_tokens(h);
         totaltypes   = colibri_b200_model_types(h);
         maxn         = colibri_b200_model_maxn(h);
@@ -306,14 +347,17 @@ class DevicePatternModel : public PatternModelInterface {
         colibri_b200_detail::ModelHandle mh;
         const std::vector<int>&          devs = colibri_b200_detail::device_list();
         std::vector<colibri_b200_model*> shares;
-        if (devs.size() > 1) {
-            // several GPUs: every device returns its share of the model (same header numbers in each); the shares are concatenated below
-            shares.assign(devs.size(), nullptr);
-            if (colibri_b200_train_multi(body, nbytes, &o, devs.data(), (int)devs.size(), shares.data()) != COLIBRI_OK) fail(colibri_b200_last_error());
-            mh.h      = shares[0];
-            shares[0] = nullptr;
-        } else if (colibri_b200_train(body, nbytes, &o, &mh.h) != COLIBRI_OK)
-            fail(colibri_b200_last_error());
+        {
+            colibri_b200_detail::Stopwatch sw(colibri_b200_detail::host_times().device);
+            if (devs.size() > 1) {
+                // several GPUs: every device returns its share of the model (same header numbers in each); the shares are concatenated below
+                shares.assign(devs.size(), nullptr);
+                if (colibri_b200_train_multi(body, nbytes, &o, devs.data(), (int)devs.size(), shares.data()) != COLIBRI_OK) fail(colibri_b200_last_error());
+                mh.h      = shares[0];
+                shares[0] = nullptr;
+            } else if (colibri_b200_train(body, nbytes, &o, &mh.h) != COLIBRI_OK)
+                fail(colibri_b200_last_error());
+        }
         totaltokens  = colibri_b200_model_tokens(mh.h);
         totaltypes   = colibri_b200_model_types(mh.h);
         maxn         = colibri_b200_model_maxn(mh.h);
@@ -408,7 +452,11 @@ class DevicePatternModel : public PatternModelInterface {
     /// The record stream is scanned on the host; shapes, filters, the constraint test and the compaction run on the device.
     virtual void load(std::istream& f, const PatternModelOptions& options, PatternModelInterface* constrainmodel = nullptr) {
         using colibri_b200_detail::fail;
-        std::vector<unsigned char> all((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        std::vector<unsigned char> all;
+        {
+            colibri_b200_detail::Stopwatch sw(colibri_b200_detail::host_times().read);
+            all = colibri_b200_detail::read_all(f);
+        }
         if (all.size() < 3 || all[0] != 0 || (all[1] != UNINDEXEDPATTERNMODEL && all[1] != INDEXEDPATTERNMODEL)) {
             if (all.size() >= 3 && all[0] == 0 && (all[1] == UNINDEXEDPATTERNPOINTERMODEL || all[1] == INDEXEDPATTERNPOINTERMODEL || all[1] == PATTERNALIGNMENTMODEL))
                 fail("pointer models and alignment models are not read by the B200 build");
@@ -488,9 +536,12 @@ class DevicePatternModel : public PatternModelInterface {
             std::cerr << "ERROR: Supplied data file can not be opened. Check whether it exists and whether you have proper permissions..." << std::endl;  // classdecoder.cpp:263-266
             throw InternalError();
         }
-        in->clear();
-        in->seekg(0);
-        std::vector<unsigned char> all((std::istreambuf_iterator<char>(*in)), std::istreambuf_iterator<char>());
+        std::vector<unsigned char> all;
+        {
+            colibri_b200_detail::Stopwatch sw(colibri_b200_detail::host_times().read);
+            in->clear();
+            all = colibri_b200_detail::read_all(*in);
+        }
         if (all.size() < 2 || all[0] != 0xA2 || all[1] != 2)
             colibri_b200_detail::fail("the B200 build reads class-encoded corpora of data version 2 only (0xA2 0x02 header)");
         train_body(all.data() + 2, all.size() - 2, true, options, constrainbymodel, filter, continued, firstsentence);
@@ -531,6 +582,7 @@ class DevicePatternModel : public PatternModelInterface {
 
     /// Write the model in the reference's binary format (reference :1609-1624, patternstore.h:534-542, datatypes.h:216-221, :263-270).
     void write(std::ostream& out) {
+        colibri_b200_detail::Stopwatch sw(colibri_b200_detail::host_times().write);
         const char    null = 0;
         unsigned char t = (unsigned char)kModelType, v = 2;
         out.write(&null, 1);
@@ -541,17 +593,30 @@ class DevicePatternModel : public PatternModelInterface {
         out.write(reinterpret_cast<const char*>(&tp), sizeof(uint64_t));
         const uint64_t s = counts_.size();
         out.write(reinterpret_cast<const char*>(&s), sizeof(uint64_t));
+        // the records are put together in 4 MB pieces: one ostream call per piece instead of three per pattern
+        std::string buf;
+        buf.reserve((4u << 20) + 4096);
+        auto put = [&](const void* p, size_t n) { buf.append(reinterpret_cast<const char*>(p), n); };
         for (size_t i = 0; i < counts_.size(); ++i) {
-            out.write(reinterpret_cast<const char*>(keys_.data() + off_[i]), (std::streamsize)(off_[i + 1] - off_[i]));
-            out.write(&null, 1);
-            out.write(reinterpret_cast<const char*>(&counts_[i]), sizeof(uint32_t));
+            put(keys_.data() + off_[i], (size_t)(off_[i + 1] - off_[i]));
+            put(&null, 1);
+            put(&counts_[i], sizeof(uint32_t));
             if (kModelType == INDEXEDPATTERNMODEL) {
                 for (uint64_t j = ref_off_[i]; j < ref_off_[i + 1]; ++j) {
-                    out.write(reinterpret_cast<const char*>(&ref_sentence_[j]), 4);
-                    out.write(reinterpret_cast<const char*>(&ref_token_[j]), 2);
+                    put(&ref_sentence_[j], 4);
+                    put(&ref_token_[j], 2);
+                    if (buf.size() >= (4u << 20)) {
+                        out.write(buf.data(), (std::streamsize)buf.size());
+                        buf.clear();
+                    }
                 }
             }
+            if (buf.size() >= (4u << 20)) {
+                out.write(buf.data(), (std::streamsize)buf.size());
+                buf.clear();
+            }
         }
+        out.write(buf.data(), (std::streamsize)buf.size());
     }
     void write(const std::string& filename) {
         std::ofstream out(filename, std::ios::out | std::ios::binary);
@@ -563,6 +628,7 @@ class DevicePatternModel : public PatternModelInterface {
 template <class ValueType, int kModelType>
 inline void DevicePatternModel<ValueType, kModelType>::materialise() {
     if (map_ready_) return;
+    colibri_b200_detail::Stopwatch sw(colibri_b200_detail::host_times().materialise);
     map_.reserve(counts_.size());
     for (size_t i = 0; i < counts_.size(); ++i) {
         if constexpr (kModelType == INDEXEDPATTERNMODEL) {

@@ -299,6 +299,11 @@ int main(int argc, char** argv) {
                                       : run<IndexedPatternModel<>>(corpusfile, outputmodelfile, &corpus, options, "");
             }
             if (rc) return rc;
+            if (!options.QUIET) {  // (B200 build only: where the host side spent its time)
+                const colibri_b200_detail::HostTimes& ht = colibri_b200_detail::host_times();
+                std::cerr << "Host timing: read files " << ht.read << " s, device calls (staging + training) " << ht.device << " s, result to host " << ht.adopt
+                          << " s, map view " << ht.materialise << " s, write " << ht.write << " s" << std::endl;
+            }
         }
     } catch (const std::exception& e) {
         std::cerr << "FATAL: " << e.what() << std::endl;

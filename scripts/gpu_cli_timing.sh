@@ -10,8 +10,9 @@ with open("/tmp/cli/zipf100m.colibri.dat", "wb") as f:
     f.write(body.tobytes())
 print("corpus bytes", len(body) + 2)
 PY
+TIMEFORMAT="wall %R s (user %U, sys %S)"
 for i in 1 2 3; do
-  /usr/bin/time -f "wall %e s, max RSS %M KB" colibri-core_b200/bin/colibri-patternmodeller -f /tmp/cli/zipf100m.colibri.dat -u -t 2 -l 5 -o /tmp/cli/model.$i 2>&1 | grep -v "^Counting\|^ Found\|^Training pattern" 
+  { time colibri-core_b200/bin/colibri-patternmodeller -f /tmp/cli/zipf100m.colibri.dat -u -t 2 -l 5 -o /tmp/cli/model.$i 2>&1 | grep -v "^Counting\|^ Found\|^Training pattern"; } 2>&1
 done > gpurun_out/cli_timing.log 2>&1
 ls -l /tmp/cli/model.1 >> gpurun_out/cli_timing.log
 python - <<'PY' >> gpurun_out/cli_timing.log 2>&1

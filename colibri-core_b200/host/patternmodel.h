@@ -580,6 +580,47 @@ class DevicePatternModel : public PatternModelInterface {
     Pattern  flat_pattern(size_t i) const { return Pattern(keys_.data() + off_[i], (int)(off_[i + 1] - off_[i])); }
     uint32_t flat_count(size_t i) const { return counts_[i]; }
 
+    /// Group statistics (reference computestats :1903-1933, computecoveragestats :1946-1984): category 0 = all, NGRAM, SKIPGRAM, FLEXGRAM;
+    /// n = 0: all lengths (flexgrams have no per-length entry).  Computed from the flat result, nothing cached -- the reference's cache
+    /// answers 0 for a group asked after another one was computed alone; that is not reproduced.
+    unsigned int totaloccurrencesingroup(int category, int n) const { return (unsigned int)group_total(category, n, true); }
+    unsigned int totalpatternsingroup(int category, int n) const { return (unsigned int)group_total(category, n, false); }
+    /// distinct tokens of the group's patterns (a gap counts as a token); asked for length 1, the unigram patterns themselves
+    unsigned int totalwordtypesingroup(int category, int n) const {
+        std::unordered_map<std::string, char> types;
+        for (size_t i = 0; i < counts_.size(); ++i) {
+            const Pattern p = flat_pattern(i);
+            if (category != 0 && (int)p.category() != category) continue;
+            const int pn = (int)p.n();
+            if (pn == 1 && n <= 1) {
+                types[std::string(reinterpret_cast<const char*>(p.data()), p.bytesize())] = 1;
+            } else if (n == 0 || pn == n) {
+                const unsigned char* d = p.data();
+                size_t               b = 0;
+                for (size_t e = 0; e < p.bytesize(); ++e)
+                    if (d[e] < 128) {  // a token ends at its first byte below 128
+                        types[std::string(reinterpret_cast<const char*>(d + b), e + 1 - b)] = 1;
+                        b = e + 1;
+                    }
+            }
+        }
+        return (unsigned int)types.size();
+    }
+
+  protected:
+    uint64_t group_total(int category, int n, bool occurrences) const {
+        uint64_t t = 0;
+        for (size_t i = 0; i < counts_.size(); ++i) {
+            const Pattern p = flat_pattern(i);
+            const int     c = (int)p.category();
+            if (category != 0 && c != category) continue;
+            if (n != 0 && (c == FLEXGRAM || (int)p.n() != n)) continue;
+            t += occurrences ? counts_[i] : 1;
+        }
+        return t;
+    }
+
+  public:
     /// Write the model in the reference's binary format (reference :1609-1624, patternstore.h:534-542, datatypes.h:216-221, :263-270).
     void write(std::ostream& out) {
         colibri_b200_detail::Stopwatch sw(colibri_b200_detail::host_times().write);

@@ -343,8 +343,31 @@ class _PatternModel:
         return (Pattern(k) for k in self._flat()[0])
 
     def totaloccurrencesingroup(self, category: int = 0, n: int = 0) -> int:
+        """(computestats :1903-1933; flexgrams have no per-length entry)"""
         keys, counts, _ = self._flat()
-        return sum(int(c) for k, c in zip(keys, counts) if (not n or len(_split(k)) == n) and (not category or Pattern(k).category() == category))
+        return sum(int(c) for k, c in zip(keys, counts) if self._in_group(k, category, n))
+
+    def totalpatternsingroup(self, category: int = 0, n: int = 0) -> int:
+        return sum(1 for k in self._flat()[0] if self._in_group(k, category, n))
+
+    def totalwordtypesingroup(self, category: int = 0, n: int = 0) -> int:
+        """Distinct tokens of the group's patterns, a gap counting as a token; asked for length 1, the unigram patterns themselves
+        (computecoveragestats :1946-1984, without its cache: see tests/golden/make_golden_stats.py)."""
+        types = set()
+        for k in self._flat()[0]:
+            if category and Pattern(k).category() != category:
+                continue
+            toks = _split(k)
+            if len(toks) == 1 and n <= 1:
+                types.add(k)
+            elif n == 0 or len(toks) == n:
+                types.update(toks)
+        return len(types)
+
+    @staticmethod
+    def _in_group(key: bytes, category: int, n: int) -> bool:
+        cat = Pattern(key).category()
+        return (not category or cat == category) and (not n or (cat != FLEXGRAM and len(_split(key)) == n))
 
     # ---- views (text only; the numbers come from the model)
     def printmodel(self, decoder: ClassDecoder):

@@ -639,6 +639,37 @@ def cooc_both(body, patterns: dict, occurrencethreshold: int = 0, size: int = 0,
     return out
 
 
+def group_stats(patterns: dict) -> dict:
+    """The model's group statistics {(category, n): (occurrences, patterns, word types)} for category 0..3 (0 = all, 1 n-gram, 2 skipgram,
+    3 flexgram) and n = 0 (all lengths) .. longest pattern: computestats (:1903-1933; flexgrams have no per-length entry) and
+    computecoveragestats (:1946-1984; the word types of a group are the distinct tokens of its patterns, a gap counts as a token; asked for
+    length 1 only the unigram patterns themselves count).  patterns: {pattern bytes: occurrence count}."""
+    shape = {}
+    maxn = 0
+    for k in patterns:
+        toks = _split_tokens(k)
+        cat = 3 if b"\x04" in toks else 2 if b"\x03" in toks else 1
+        shape[k] = (cat, len(toks), toks)
+        maxn = max(maxn, len(toks))
+    out = {}
+    for c in range(4):
+        for n in range(maxn + 1):
+            occ = npat = 0
+            types = set()
+            for k, (cat, pn, toks) in shape.items():
+                if c and cat != c:
+                    continue
+                if n == 0 or (pn == n and cat != 3):
+                    occ += patterns[k]
+                    npat += 1
+                if pn == 1 and n <= 1:
+                    types.add(k)
+                elif n == 0 or pn == n:
+                    types.update(toks)
+            out[(c, n)] = (occ, npat, len(types))
+    return out
+
+
 def npmi(count1: int, count2: int, joint: int, total: int) -> float:
     """PatternModel::npmi (:3582-3585), the same expression in the same order (the product is an unsigned 32-bit product in the reference)."""
     import math

@@ -10,7 +10,7 @@
 //   F/X computeflexgrams_fromcooc(th)  :3751-3774                          found, then every flexgram with its occurrence count
 // as text lines (patterns as hex of their bytes), sorted, so that tests/golden/make_golden_relations.py can pin the oracle to them.
 //
-// usage: ref_relations -f corpus.colibri.dat [-t N] [-l N] [-Y npmi-threshold] [-x (also run computeflexgrams_fromcooc)]
+// usage: ref_relations -f corpus.colibri.dat [-t N] [-l N] [-Y npmi-threshold] [-x (also run computeflexgrams_fromcooc)] [-s (skipgrams)] [-S (group statistics only)]
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -41,6 +41,7 @@ int main(int argc, char** argv) {
     options.QUIET     = true;
     double threshold  = 0.0;
     bool   doflex     = false;
+    bool   statsonly  = false;  // -S: print the group statistics (computestats :1903-1933, computecoveragestats :1946-1984) and stop
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "-f" && i + 1 < argc) corpusfile = argv[++i];
@@ -48,6 +49,8 @@ int main(int argc, char** argv) {
         else if (a == "-l" && i + 1 < argc) options.MAXLENGTH = atoi(argv[++i]);
         else if (a == "-Y" && i + 1 < argc) threshold = atof(argv[++i]);
         else if (a == "-x") doflex = true;
+        else if (a == "-s") options.DOSKIPGRAMS = true;
+        else if (a == "-S") statsonly = true;
         else {
             std::cerr << "unknown argument " << a << std::endl;
             return 2;
@@ -63,6 +66,12 @@ int main(int argc, char** argv) {
     model->train(corpusfile, options, NULL, NULL, false, 1, false);
     printf("H patterns=%llu tokens=%llu types=%llu sentences=%d total=%llu\n", (unsigned long long)model->size(), (unsigned long long)model->tokens(),
            (unsigned long long)model->types(), corpus->sentences(), (unsigned long long)model->totaloccurrencesingroup(0, 0));
+    if (statsonly) {
+        for (int c = 0; c <= 3; ++c)
+            for (int n = 0; n <= model->maxlength(); ++n)
+                printf("S %d %d %u %u %u\n", c, n, model->totaloccurrencesingroup(c, n), model->totalpatternsingroup(c, n), model->totalwordtypesingroup(c, n));
+        return 0;
+    }
     // snapshot of the patterns (the model must not be iterated while it changes)
     std::vector<Pattern> patterns;
     for (IndexedPatternModel<>::iterator it = model->begin(); it != model->end(); ++it) patterns.push_back(it->first);

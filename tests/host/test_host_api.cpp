@@ -2,6 +2,7 @@
 // (reference include/pattern.h, src/pattern.cpp) and train() refuses loudly without a GPU.  Prints "ok"/"FAILED" lines in
 // the spirit of the reference's own src/test.cpp and exits 2 on the first failure.
 #include <cstdlib>
+#include <cstdio>
 #include <iostream>
 #include <sstream>
 #include <string>
@@ -62,6 +63,61 @@ int main(int argc, char** argv) {
         IndexedCorpus corpus{std::string(argv[1])};
         test("IndexedCorpus sentences (hamlet)", corpus.sentences(), 40u);  // reference src/test.cpp:1549
         if (colibri_b200_device_count() > 0) {
+            // the training part of the reference's own test program (src/test.cpp:1207-1340) with its expected numbers; patterns are given by
+            // their classes in tests/golden/hamlet.colibri.cls ("or not to" = 14 12 7, "give us fortune" = 156 27 135)
+            {
+                const std::string   infilename = argv[1];
+                PatternModelOptions options;
+                options.QUIET = true;
+                PatternModel<uint32_t> unindexedmodelNSR(&corpus);  // from the preloaded corpus, no skipgrams (:1210-1219)
+                unindexedmodelNSR.train(infilename, options);
+                test("unindexed, preloaded: patterns", unindexedmodelNSR.size(), (size_t)111);
+                test("unindexed, preloaded: types", unindexedmodelNSR.types(), (size_t)186);
+                test("unindexed, preloaded: tokens", unindexedmodelNSR.tokens(), (size_t)354);
+                PatternModel<uint32_t> unindexedmodelNS;  // streamed from the file (:1224-1233)
+                unindexedmodelNS.train(infilename, options);
+                test("unindexed, streamed: patterns", unindexedmodelNS.size(), (size_t)111);
+                test("unindexed, streamed: types", unindexedmodelNS.types(), (size_t)186);
+                test("unindexed, streamed: tokens", unindexedmodelNS.tokens(), (size_t)354);
+                const Pattern ngram    = Pattern::fromclasses({14, 12, 7});
+                const Pattern ngram_ne = Pattern::fromclasses({156, 27, 135});
+                test("unindexedmodel.has(or not to)", unindexedmodelNS.has(ngram), true);             // :1241-1243
+                test("!unindexedmodel.has(give us fortune)", unindexedmodelNS.has(ngram_ne), false);  // :1244-1246
+                test("unindexedmodel.occurrencecount(or not to)", unindexedmodelNS.occurrencecount(ngram), (size_t)6);  // :1247-1248
+                options.DOSKIPGRAMS_EXHAUSTIVE = true;  // :1262-1283
+                options.DOSKIPGRAMS            = false;
+                PatternModel<uint32_t> unindexedmodelR(&corpus);
+                unindexedmodelR.train(infilename, options);
+                test("unindexed + skipgrams, preloaded: patterns", unindexedmodelR.size(), (size_t)385);
+                PatternModel<uint32_t> unindexedmodel;
+                unindexedmodel.train(infilename, options);
+                test("unindexed + skipgrams, streamed: patterns", unindexedmodel.size(), (size_t)385);
+                test("unindexed + skipgrams: types", unindexedmodel.types(), (size_t)186);
+                test("unindexed + skipgrams: tokens", unindexedmodel.tokens(), (size_t)354);
+                test("unindexed + skipgrams: has", unindexedmodel.has(ngram), true);
+                test("unindexed + skipgrams: occurrencecount", unindexedmodel.occurrencecount(ngram), (size_t)6);
+                const std::string outputfilename = "/tmp/colibri_b200_host_test.colibri.patternmodel";  // write, read back (:1303-1322)
+                unindexedmodel.write(outputfilename);
+                PatternModel<uint32_t> unindexedmodel2(outputfilename, options);
+                test("read back: equal tokens", unindexedmodel.tokens() == unindexedmodel2.tokens(), true);
+                test("read back: equal types", unindexedmodel.types() == unindexedmodel2.types(), true);
+                test("read back: equal size", unindexedmodel.size() == unindexedmodel2.size(), true);
+                test("read back: has", unindexedmodel2.has(ngram), true);
+                test("read back: occurrencecount", unindexedmodel2.occurrencecount(ngram), (size_t)6);
+                remove(outputfilename.c_str());
+                options.DOSKIPGRAMS_EXHAUSTIVE = false;  // indexed model with skipgrams (:1324-1340)
+                options.DOSKIPGRAMS            = true;
+                IndexedPatternModel<> indexedmodel(&corpus);
+                indexedmodel.train(infilename, options);
+                test("indexed + skipgrams: patterns", indexedmodel.size(), (size_t)133);
+                test("indexed: equal tokens", unindexedmodel.tokens() == indexedmodel.tokens(), true);
+                test("indexed: equal types", unindexedmodel.types() == indexedmodel.types(), true);
+                test("indexed: has", indexedmodel.has(ngram), true);
+                test("indexed: occurrencecount", indexedmodel.occurrencecount(ngram), (size_t)6);
+                test("indexed: size = n-grams + skipgrams", indexedmodel.size(), unindexedmodelNS.size() + indexedmodel.totalpatternsingroup(SKIPGRAM, 0));  // :1329-1330
+                test("indexed: unigram types", indexedmodel.totalwordtypesingroup(0, 1), 45u);              // :1344-1345
+                test("unindexed: unigram types", unindexedmodelNSR.totalwordtypesingroup(0, 1), 45u);      // :1221-1222
+            }
             // reverse index + co-occurrence relations of the indexed model (answers of the unmodified reference, oracle/_ref/ref_relations -t 2 -l 3)
             PatternModelOptions ro;
             ro.QUIET     = true;

@@ -138,3 +138,22 @@ def test_cooccurrence_at_scale_matches_oracle_properties():
         w = np.maximum(0, sl - 1 - (rt[int(ro[i]):int(ro[i + 1])].astype(np.int64) + n))
         assert int(w.sum()) == self_rel[i]
     ri.close()
+
+
+with open(os.path.join(GOLDEN_DIR, "golden_stats.json")) as f:
+    STATS_CASES = json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", STATS_CASES, ids=["%s-t%d-l%d-s%d" % (c["corpus"], c["t"], c["l"], c["skipgrams"]) for c in STATS_CASES])
+def test_group_statistics_equal_reference(case, tmp_path):
+    """totaloccurrencesingroup / totalpatternsingroup / totalwordtypesingroup of every (category, n) of a model trained on the device equal the
+    unmodified reference's (tests/golden/make_golden_stats.py)."""
+    colibricore = cc()
+    path = str(tmp_path / "c.colibri.dat")
+    with open(path, "wb") as f:
+        f.write(b"\xa2\x02" + relations_corpus(case["corpus"]))
+    corpus = colibricore.IndexedCorpus(path)
+    model = colibricore.IndexedPatternModel(reverseindex=corpus)
+    model.train(path, colibricore.PatternModelOptions(mintokens=case["t"], maxlength=case["l"], doskipgrams=bool(case["skipgrams"])))
+    for c, n, occ, npat, wtypes in case["S"]:
+        assert (model.totaloccurrencesingroup(c, n), model.totalpatternsingroup(c, n), model.totalwordtypesingroup(c, n)) == (occ, npat, wtypes), (c, n)

@@ -82,19 +82,26 @@ struct Stopwatch {
     explicit Stopwatch(double& a) : acc(a) {}
     ~Stopwatch() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
 };
-// a whole stream into memory: one read() when the stream can tell its size (a file), byte iterators otherwise
+// the rest of a stream into memory: one read() when the stream can tell how much is left (a file), byte iterators otherwise
 inline std::vector<unsigned char> read_all(std::istream& in) {
     std::vector<unsigned char> all;
-    in.seekg(0, std::ios::end);
-    const std::streamoff size = in.good() ? (std::streamoff)in.tellg() : (std::streamoff)-1;
-    in.clear();
-    in.seekg(0);
-    if (size > 0) {
-        all.resize((size_t)size);
-        in.read(reinterpret_cast<char*>(all.data()), size);
+    std::streamoff             left = -1;
+    const std::streampos       cur  = in.tellg();
+    if (in.good() && cur != std::streampos(-1)) {
+        in.seekg(0, std::ios::end);
+        const std::streampos end = in.tellg();
+        if (in.good() && end != std::streampos(-1)) left = end - cur;
+        in.clear();
+        in.seekg(cur);
+    } else {
+        in.clear();
+    }
+    if (left > 0) {
+        all.resize((size_t)left);
+        in.read(reinterpret_cast<char*>(all.data()), left);
         all.resize((size_t)std::max<std::streamsize>(in.gcount(), 0));
         in.clear();
-    } else {
+    } else if (left != 0) {
         all.assign((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
     }
     return all;
@@ -540,6 +547,7 @@ class DevicePatternModel : public PatternModelInterface {
         {
             colibri_b200_detail::Stopwatch sw(colibri_b200_detail::host_times().read);
             in->clear();
+            in->seekg(0);
             all = colibri_b200_detail::read_all(*in);
         }
         if (all.size() < 2 || all[0] != 0xA2 || all[1] != 2)

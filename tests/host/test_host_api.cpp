@@ -3,9 +3,11 @@
 // the spirit of the reference's own src/test.cpp and exits 2 on the first failure.
 #include <cstdlib>
 #include <cstdio>
+#include <fstream>
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <vector>
 
 #include "patternmodel.h"
 
@@ -59,6 +61,32 @@ int main(int argc, char** argv) {
     test("MAXSKIPS default", o.MAXSKIPS, 3);
     test("DOSKIPGRAMS default", o.DOSKIPGRAMS, false);
 
+    {  // the file readers take what is left of a stream, with one read() when the stream knows its size
+        const std::string tmp = "/tmp/colibri_b200_host_test.bin";
+        {
+            std::ofstream out(tmp, std::ios::binary);
+            for (int i = 0; i < 100000; ++i) out.put((char)(i * 7));
+        }
+        std::ifstream f(tmp, std::ios::binary);
+        std::vector<unsigned char> all = colibri_b200_detail::read_all(f);
+        test("read_all(file) size", all.size(), (size_t)100000);
+        test("read_all(file) content", (int)all[3], 21);
+        f.clear();
+        f.seekg(10);
+        all = colibri_b200_detail::read_all(f);
+        test("read_all from a position", all.size(), (size_t)99990);
+        test("read_all from a position: first byte", (int)all[0], 70);
+        std::istringstream text(std::string("hello"));
+        test("read_all(stringstream)", colibri_b200_detail::read_all(text).size(), (size_t)5);
+        std::ifstream missing("/nonexistent/file", std::ios::binary);
+        test("read_all(unopened stream)", colibri_b200_detail::read_all(missing).size(), (size_t)0);
+        remove(tmp.c_str());
+        PatternModel<uint32_t> empty;  // an empty model is its 27-byte header (reference include/patternmodel.h:1609-1624)
+        std::ostringstream     blob;
+        empty.write(blob);
+        test("empty model file size", blob.str().size(), (size_t)27);
+        test("empty model file type byte", (int)(unsigned char)blob.str()[1], (int)UNINDEXEDPATTERNMODEL);
+    }
     if (argc > 1) {
         IndexedCorpus corpus{std::string(argv[1])};
         test("IndexedCorpus sentences (hamlet)", corpus.sentences(), 40u);  // reference src/test.cpp:1549

@@ -321,3 +321,27 @@ def test_distributed_constrained_orchestration_matches_oracle(world, mintokens, 
     for model, tokens in gathered:  # every rank holds the same model
         assert model == want.as_dict()
         assert tokens == per * world
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_strong_scaling_cuts_fall_on_sentence_boundaries(seed, world):
+    """The strong-scaling parity step cuts ONE corpus into `world` shards (multigpu.cut_at_sentences): every cut must follow a real delimiter
+    (a 0x00 that is not the last byte of a multi-byte class), the shards must tile the corpus, and the sentences of the shards are the
+    sentences of the corpus -- so the n-grams of the shards are exactly the n-grams of the whole (windows never cross a sentence)."""
+    import colibri_core_b200.multigpu as mg
+    import oracle
+
+    rng = np.random.default_rng(seed)
+    # one-, two- and three-byte classes, empty sentences among them
+    sentences = [[int(rng.choice([6, 7, 127, 128, 256, 300, 16384, 16512, 40000])) for _ in range(int(rng.integers(0, 9)))] for _ in range(int(rng.integers(1, 60)))]
+    body = np.frombuffer(np.asarray(oracle.encode_corpus(sentences), dtype=np.uint8).tobytes(), dtype=np.uint8)
+    cuts = mg.cut_at_sentences(body, world)
+    assert cuts[0] == 0 and cuts[-1] == len(body) and len(cuts) == world + 1
+    assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+    for c in cuts[1:-1]:
+        if 0 < c < len(body):
+            assert body[c - 1] == 0 and (c < 2 or body[c - 2] < 128), (c, body[max(0, c - 3):c + 1])
+    whole = oracle.corpus_sentences(body)
+    parts = [s for a, b in zip(cuts, cuts[1:]) for s in oracle.corpus_sentences(body[a:b])]
+    assert [s for s in parts if s] == [s for s in whole if s]

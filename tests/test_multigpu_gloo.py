@@ -335,7 +335,7 @@ def test_strong_scaling_cuts_fall_on_sentence_boundaries(seed, world):
     rng = np.random.default_rng(seed)
     # one-, two- and three-byte classes, empty sentences among them
     sentences = [[int(rng.choice([6, 7, 127, 128, 256, 300, 16384, 16512, 40000])) for _ in range(int(rng.integers(0, 9)))] for _ in range(int(rng.integers(1, 60)))]
-    body = np.frombuffer(np.asarray(oracle.encode_corpus(sentences), dtype=np.uint8).tobytes(), dtype=np.uint8)
+    body = np.frombuffer(bytes(oracle.encode_corpus(sentences)), dtype=np.uint8)
     cuts = mg.cut_at_sentences(body, world)
     assert cuts[0] == 0 and cuts[-1] == len(body) and len(cuts) == world + 1
     assert all(a <= b for a, b in zip(cuts, cuts[1:]))

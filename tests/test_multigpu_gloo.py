@@ -345,3 +345,40 @@ def test_strong_scaling_cuts_fall_on_sentence_boundaries(seed, world):
     whole = oracle.corpus_sentences(body)
     parts = [s for a, b in zip(cuts, cuts[1:]) for s in oracle.corpus_sentences(body[a:b])]
     assert [s for s in parts if s] == [s for s in whole if s]
+
+
+class _FailingEngine(NumpyShardEngine):
+    """Rank 1's second level fails the way a CUDA phase does (an exception out of the engine) while rank 0 is already inside the next collective."""
+
+    def level_split_write(self, nsend):
+        if self.rank == 1 and self.level >= 2:  # (level 3 of this corpus always exists)
+            raise RuntimeError("receive slot overflow (injected)")
+        return super().level_split_write(nsend)
+
+
+def _failing_worker(rank, world, port, bodies):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import colibri_core_b200.multigpu as mg
+
+    mg.train_distributed(_FailingEngine(bodies[rank], 2, rank, world), dist, torch, 2, 4, False)
+
+
+def test_a_failing_rank_leaves_the_process_instead_of_hanging_the_job():
+    """multigpu.train_distributed: the rank whose phase raises prints the reason and exits the process with status 13, so that the launcher
+    (torchrun, or this test) can take the other ranks down; without that they would wait in their collective forever."""
+    import oracle
+
+    bodies = [oracle.synth_corpus(3000, vocab=40, seed=5, mean_sentence=9, first_token=r * 3000).tobytes() for r in range(2)]
+    ctx = mp.get_context("spawn")
+    port = 29600 + (os.getpid() + 77) % 300
+    procs = [ctx.Process(target=_failing_worker, args=(r, 2, port, bodies)) for r in range(2)]
+    for p in procs:
+        p.start()
+    procs[1].join(timeout=120)
+    assert procs[1].exitcode == 13
+    procs[0].join(timeout=5)  # rank 0 is stuck in (or failed out of) its collective: what a launcher does next
+    if procs[0].is_alive():
+        procs[0].terminate()
+        procs[0].join(timeout=30)
+    assert procs[0].exitcode != 0

@@ -118,3 +118,51 @@ def test_oracle_constrained_equals_reference_cli_on_random_input(seed):
     assert (mine.tokens, mine.types, len(mine)) == (ref.tokens, ref.types, len(ref)), args
     assert [(p[1], p[3]) for p in mine.passes] == [(p[0], p[2]) for p in oracle.parse_ref_passes(err)], args
     assert mine.same_patterns(ref), args
+
+
+REF_RELATIONS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_relations")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_RELATIONS), reason="oracle/_ref/ref_relations (the reference's relation queries) is not built")
+@pytest.mark.parametrize("seed", range(40))
+def test_oracle_relations_equal_reference_on_random_input(seed):
+    """getreverseindex, getrightcooc / getleftcooc, getcooc (defaults and occurrencethreshold 2 + ordersignificant) and the group statistics of the
+    oracle against the unmodified reference (oracle/ref_relations.cpp) on random corpora: what pins the device's relation queries."""
+    import subprocess
+
+    rng = random.Random(5000 + seed)
+    body = b""
+    while not body:
+        vocab = rng.choice([3, 6, 15, 60])
+        sentences = [[6 + min(int(rng.paretovariate(1.1)) - 1, vocab - 1) for _ in range(rng.choice([0, 1, 2, 3, 5, 8, 13, 21]))] for _ in range(rng.randint(1, 40))]
+        body = bytes(oracle.encode_corpus(sentences))
+    t, l = rng.choice([2, 2, 3]), rng.choice([2, 3, 4, 5])  # (threshold 1 trips the reference's statistics cache, tests/golden/make_golden_stats.py)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "c.colibri.dat")
+        with open(path, "wb") as f:
+            f.write(b"\xa2\x02" + body)
+        rel = subprocess.run([REF_RELATIONS, "-f", path, "-t", str(t), "-l", str(l)], capture_output=True, text=True, check=True).stdout
+        sta = subprocess.run([REF_RELATIONS, "-f", path, "-t", str(t), "-l", str(l), "-S"], capture_output=True, text=True, check=True).stdout
+    patterns = oracle.train(body, mintokens=t, maxlength=l, indexed=1, streamed=0).as_dict()
+    ref = {k: [] for k in "GRLCO"}
+    for line in rel.splitlines():
+        p = line.split()
+        if p[0] == "G":
+            ref["G"].append((int(p[1]), int(p[2]), sorted(p[3:])))
+        elif p[0] in "RLCO":
+            ref[p[0]].append((p[1], p[2], int(p[3])))
+    if not patterns:
+        assert not any(ref[k] for k in "RLCO")
+        return
+    rindex = oracle.reverse_index(body, patterns)
+    assert sorted((s, tk, sorted(k.hex() for k in v)) for (s, tk), v in rindex.items()) == sorted(ref["G"])
+    flat = lambda rel: sorted((p.hex(), q.hex(), j) for (p, q), j in rel.items())  # noqa: E731
+    assert flat(oracle.cooc(body, patterns, left=False)) == sorted(ref["R"])
+    assert flat(oracle.cooc(body, patterns, left=True)) == sorted(ref["L"])
+    assert flat(oracle.cooc_both(body, patterns)) == sorted(ref["C"])
+    assert flat(oracle.cooc_both(body, patterns, occurrencethreshold=2, ordersignificant=True)) == sorted(ref["O"])
+    got = oracle.group_stats(patterns)
+    for line in sta.splitlines():
+        p = line.split()
+        if p[0] == "S":
+            assert got.get((int(p[1]), int(p[2])), (0, 0, 0)) == (int(p[3]), int(p[4]), int(p[5])), line

@@ -157,3 +157,40 @@ def test_group_statistics_equal_reference(case, tmp_path):
     model.train(path, colibricore.PatternModelOptions(mintokens=case["t"], maxlength=case["l"], doskipgrams=bool(case["skipgrams"])))
     for c, n, occ, npat, wtypes in case["S"]:
         assert (model.totaloccurrencesingroup(c, n), model.totalpatternsingroup(c, n), model.totalwordtypesingroup(c, n)) == (occ, npat, wtypes), (c, n)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_relations_equal_oracle_on_random_input(seed, tmp_path):
+    """Random corpora (the ones tests/test_oracle_vs_ref_random.py pins the oracle to the reference with): reverse index, right / left
+    co-occurrence, getcooc with and without its filters, group statistics -- device against oracle."""
+    import random
+
+    colibricore = cc()
+    rng = random.Random(5000 + seed)
+    body = b""
+    while not body:
+        vocab = rng.choice([3, 6, 15, 60])
+        sentences = [[6 + min(int(rng.paretovariate(1.1)) - 1, vocab - 1) for _ in range(rng.choice([0, 1, 2, 3, 5, 8, 13, 21]))] for _ in range(rng.randint(1, 40))]
+        body = bytes(oracle.encode_corpus(sentences))
+    t, l = rng.choice([2, 2, 3]), rng.choice([2, 3, 4, 5])
+    patterns = oracle.train(body, mintokens=t, maxlength=l, indexed=1, streamed=0).as_dict()
+    if not patterns:
+        pytest.skip("no pattern survives")
+    path = str(tmp_path / "c.colibri.dat")
+    with open(path, "wb") as f:
+        f.write(b"\xa2\x02" + body)
+    corpus = colibricore.IndexedCorpus(path)
+    model = colibricore.IndexedPatternModel(reverseindex=corpus)
+    model.train(path, colibricore.PatternModelOptions(mintokens=t, maxlength=l))
+    assert {bytes(p): len(v) for p, v in model.items()} == patterns
+    rindex = oracle.reverse_index(body, patterns)
+    refs = sorted(rindex)
+    got = model.getreverseindex_batch(refs)
+    assert [sorted(bytes(p) for p in g) for g in got] == [sorted(rindex[r]) for r in refs]
+    for left, fn in ((False, model.getrightcooc), (True, model.getleftcooc)):
+        assert {(bytes(p), bytes(q)): j for p in model for q, j in fn(p)} == oracle.cooc(body, patterns, left=left)
+    assert {(bytes(p), bytes(q)): j for p in model for q, j in model.getcooc(p)} == oracle.cooc_both(body, patterns)
+    assert {(bytes(p), bytes(q)): j for p in model for q, j in model.getcooc(p, occurrencethreshold=2, size=1, ordersignificant=True)} == \
+        oracle.cooc_both(body, patterns, occurrencethreshold=2, size=1, ordersignificant=True)
+    for (c, n), (occ, npat, wtypes) in oracle.group_stats(patterns).items():
+        assert (model.totaloccurrencesingroup(c, n), model.totalpatternsingroup(c, n), model.totalwordtypesingroup(c, n)) == (occ, npat, wtypes), (c, n)

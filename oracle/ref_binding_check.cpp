@@ -7,7 +7,10 @@
 // and a comparison of the two models with the reference's own accessors: size(), tokens(), types(), maxlength(), minlength(), and
 // occurrencecount() of every pattern of A in B and of B in A.  Prints "IDENTICAL ..." and exits 0, or the first differences and exits 1.
 //
+//   -i: the same with IndexedPatternModel<> / B200IndexedPatternModel, comparing the (sentence, token) list of every pattern
+//
 // usage: ref_binding_check -f corpus.colibri.dat [-t N] [-l N] [-s (exhaustive skipgrams)] [-p (preloaded corpus instead of the stream)]
+//                          [-i (indexed models) [-S (trainskipgrams)]]
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -16,6 +19,49 @@
 
 #include "b200_patternmodel.h"
 
+static int indexed_check(const std::string& corpusfile, const PatternModelOptions& options) {
+    std::ifstream  f(corpusfile, std::ifstream::in | std::ifstream::binary);
+    IndexedCorpus* corpus = new IndexedCorpus(f, false);
+    IndexedPatternModel<> a(corpus);
+    a.train(corpusfile, options);
+    B200IndexedPatternModel b(corpus);
+    try {
+        b.train(corpusfile, options);
+    } catch (const InternalError&) {
+        printf("B200 train() failed\n");
+        return 3;
+    }
+    int bad = 0;
+    if (a.size() != b.size() || a.tokens() != b.tokens() || a.types() != b.types() || a.maxlength() != b.maxlength() || a.minlength() != b.minlength()) {
+        printf("DIFFERENT header: reference %llu patterns / %llu tokens / %llu types / %d..%d, B200 binding %llu / %llu / %llu / %d..%d\n", (unsigned long long)a.size(),
+               (unsigned long long)a.tokens(), (unsigned long long)a.types(), a.minlength(), a.maxlength(), (unsigned long long)b.size(), (unsigned long long)b.tokens(),
+               (unsigned long long)b.types(), b.minlength(), b.maxlength());
+        ++bad;
+    }
+    unsigned long long refs = 0;
+    for (IndexedPatternModel<>::iterator it = a.begin(); it != a.end() && bad < 10; ++it) {
+        const Pattern p = it->first;
+        IndexedData*  x = a.getdata(p);
+        IndexedData*  y = b.getdata(p);
+        if (y == NULL || x->data.size() != y->data.size()) {
+            printf("DIFFERENT pattern of the reference model: %u occurrences there, %u in the binding's\n", (unsigned)x->data.size(), (unsigned)(y ? y->data.size() : 0));
+            ++bad;
+            continue;
+        }
+        for (size_t j = 0; j < x->data.size(); ++j)
+            if (x->data[j].sentence != y->data[j].sentence || x->data[j].token != y->data[j].token) {
+                printf("DIFFERENT reference %zu of a pattern: (%u, %u) there, (%u, %u) in the binding's\n", j, x->data[j].sentence, (unsigned)x->data[j].token, y->data[j].sentence,
+                       (unsigned)y->data[j].token);
+                ++bad;
+                break;
+            }
+        refs += x->data.size();
+    }
+    if (bad) return 1;
+    printf("IDENTICAL indexed patterns=%llu references=%llu tokens=%llu types=%llu\n", (unsigned long long)a.size(), refs, (unsigned long long)a.tokens(), (unsigned long long)a.types());
+    return 0;
+}
+
 int main(int argc, char** argv) {
     std::string         corpusfile;
     PatternModelOptions options;
@@ -23,6 +69,7 @@ int main(int argc, char** argv) {
     options.MAXLENGTH = 5;
     options.QUIET     = true;
     bool preloaded    = false;
+    bool indexed      = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "-f" && i + 1 < argc) corpusfile = argv[++i];
@@ -30,11 +77,14 @@ int main(int argc, char** argv) {
         else if (a == "-l" && i + 1 < argc) options.MAXLENGTH = atoi(argv[++i]);
         else if (a == "-s") options.DOSKIPGRAMS_EXHAUSTIVE = true;
         else if (a == "-p") preloaded = true;
+        else if (a == "-i") indexed = true;
+        else if (a == "-S") options.DOSKIPGRAMS = true;
         else {
             std::cerr << "unknown argument " << a << std::endl;
             return 2;
         }
     }
+    if (indexed) return indexed_check(corpusfile, options);
     IndexedCorpus* corpus = NULL;
     if (preloaded || options.DOSKIPGRAMS_EXHAUSTIVE) {  // (the CLI preloads the corpus for exhaustive skipgrams, src/patternmodeller.cpp:721-737)
         std::ifstream f(corpusfile, std::ifstream::in | std::ifstream::binary);

@@ -24,6 +24,23 @@ def test_reference_class_with_the_b200_override_builds_the_reference_model_hamle
     assert r.returncode == 0 and r.stdout.startswith("IDENTICAL"), r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("args", [["-i", "-t", "2", "-l", "3"], ["-i", "-t", "2", "-l", "8"], ["-i", "-t", "1", "-l", "4"], ["-i", "-S", "-t", "2", "-l", "6"]], ids=lambda a: "".join(a))
+def test_reference_indexed_class_with_the_b200_override_builds_the_reference_model_hamlet(args):
+    """IndexedPatternModel<> with the same override: the (sentence, token) list of every pattern, -S with trainskipgrams (the 133-pattern KAT)."""
+    r = subprocess.run([CHECK, "-f", os.path.join(GOLDEN_DIR, "hamlet.colibri.dat")] + args, capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("IDENTICAL indexed"), r.stdout + r.stderr
+
+
+def test_reference_indexed_class_with_the_b200_override_synthetic():
+    body = oracle.synth_corpus(200000, vocab=3000, seed=4, mean_sentence=15, phrase_permille=150, nphrases=400)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "c.colibri.dat")
+        with open(path, "wb") as f:
+            f.write(b"\xa2\x02" + body.tobytes())
+        r = subprocess.run([CHECK, "-f", path, "-i", "-t", "2", "-l", "5"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("IDENTICAL indexed"), r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("seed,skip", [(1, False), (2, False), (3, True)])
 def test_reference_class_with_the_b200_override_builds_the_reference_model_synthetic(seed, skip):
     body = oracle.synth_corpus(200000, vocab=3000, seed=seed, mean_sentence=15, phrase_permille=150, nphrases=400)

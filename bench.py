@@ -431,7 +431,7 @@ def run_ours(a):
                    "timing": "max(torch CUDA events, wall clock) around K synchronous ABI calls"},
         "device_ms_per_step": sum(dev_ms) / len(dev_ms),
         "phase_ms_per_step": {k: v / a.steps for k, v in phase_ms.items()},
-        "roofline": {"bound": "hbm", "kernel": "count family, levels 2..%d: part_hist/split1/split2/count (level 2, partitioned, dense pair square) + ngram_filter_kernel + count_ngrams_kernel (HBM table)" % last.maxlength(), "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "count family, levels 2..%d: make_id1_hist + part_split1/split2/count/gather (level 2, partitioned, dense pair square; the level-1 id sweep carries its first pass) + ngram_filter_kernel + count_ngrams_kernel (HBM table)" % last.maxlength(), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "alg_bytes_per_step": alg_bytes / a.steps, "kernel_ms_per_step": count_ms / a.steps,
                      "kernel_share_of_step": (count_ms / a.steps) / (sum(dev_ms) / len(dev_ms)),
                      "traffic": traffic["dram_bytes_per_step"] if traffic else None, "traffic_source": traffic_note,

@@ -113,7 +113,7 @@ class ClassDecoder:
     """class -> word, from a .colibri.cls file (one `class<TAB>word` line per class; src/classdecoder.cpp)."""
 
     def __init__(self, filename: str | None = None):
-        self.words = {0: "\n", 1: "{?}", 2: "{|}", 3: "{*}", 4: "{**}"}
+        self.words = {0: "\n", 1: "{|}", 2: "{?}", 3: "{*}", 4: "{**}"}  # boundary, unknown, skip, flex (include/classdecoder.h:48-52, src/classdecoder.cpp:86-89)
         if filename:
             with open(filename, encoding="utf-8") as f:
                 for line in f:
@@ -133,7 +133,7 @@ class ClassEncoder:
     """word -> class, from a .colibri.cls file (src/classencoder.cpp); buildpattern() encodes a space-separated string."""
 
     def __init__(self, filename: str | None = None):
-        self.classes = {"{?}": 1, "{|}": 2, "{*}": 3, "{**}": 4}
+        self.classes = {"{|}": 1, "{?}": 2, "{*}": 3, "{**}": 4}  # src/classencoder.cpp:128-131
         if filename:
             with open(filename, encoding="utf-8") as f:
                 for line in f:
@@ -146,24 +146,38 @@ class ClassEncoder:
         return len(self.classes)
 
     def buildpattern(self, text: str, allowunknown: bool = True, autoaddunknown: bool = False) -> Pattern:
+        """(src/classencoder.cpp:364-433) `{*}` a gap, `{**}` a flexible gap, `{?}` the unknown word, `{*N*}` N gaps in a row; a word that is
+        not in the class file becomes the unknown class (2), gets a new class (autoaddunknown) or raises KeyError (allowunknown=False)."""
         out = bytearray()
         for w in text.split():
-            if w not in self.classes:
-                if not allowunknown:
-                    raise KeyError(w)
-                out += _bytes_of(1)
-            else:
+            if len(w) > 4 and w.startswith("{*") and w.endswith("*}") and w[2:-2].isdigit():
+                out += _bytes_of(3) * int(w[2:-2])
+            elif w in self.classes:
                 out += _bytes_of(self.classes[w])
+            elif autoaddunknown:
+                self.classes[w] = max(max(self.classes.values()), 5) + 1
+                out += _bytes_of(self.classes[w])
+            elif not allowunknown:
+                raise KeyError(w)
+            else:
+                out += _bytes_of(2)
         return Pattern(bytes(out))
 
 
 class PatternModelOptions:
-    """The reference binding's option object: lower-case attribute names (colibricore_wrapper.in.pyx, PatternModelOptions.__setattr__)."""
+    """The reference binding's option object (colibricore_wrapper.in.pyx:870-990): attributes MINTOKENS, MAXLENGTH, ... (any case here), the same
+    names as constructor keywords."""
 
     _MAP = {"mintokens": "MINTOKENS", "maxlength": "MAXLENGTH", "minlength": "MINLENGTH", "maxbackofflength": "MAXBACKOFFLENGTH", "mintokens_unigrams": "MINTOKENS_UNIGRAMS",
             "mintokens_skipgrams": "MINTOKENS_SKIPGRAMS", "minskiptypes": "MINSKIPTYPES", "maxskips": "MAXSKIPS", "doskipgrams": "DOSKIPGRAMS",
             "doskipgrams_exhaustive": "DOSKIPGRAMS_EXHAUSTIVE", "doreverseindex": "DOREVERSEINDEX", "dopatternperline": "DOPATTERNPERLINE", "doreset": "DORESET",
             "prunenonsubsumed": "PRUNENONSUBSUMED", "quiet": "QUIET", "debug": "DEBUG", "device": "device"}
+
+    # what an option reads as before it is set: the reference's defaults (include/patternmodel.h:105-180); QUIET is on here because the
+    # progress lines are the C++ front end's business, not the binding's
+    _DEFAULTS = {"mintokens": -1, "maxlength": 100, "minlength": 1, "maxbackofflength": 100, "mintokens_unigrams": 1, "mintokens_skipgrams": -1, "minskiptypes": 2,
+                 "maxskips": 3, "doskipgrams": False, "doskipgrams_exhaustive": False, "doreverseindex": True, "dopatternperline": False, "doreset": False,
+                 "prunenonsubsumed": 0, "quiet": True, "debug": False, "device": 0}
 
     def __init__(self, **kw):
         object.__setattr__(self, "_kw", {"quiet": True})
@@ -171,13 +185,14 @@ class PatternModelOptions:
             setattr(self, k, v)
 
     def __setattr__(self, k, v):
+        k = k.lower()  # the reference's attributes are upper case, its constructor keywords any case (colibricore_wrapper.in.pyx:898-900)
         if k not in self._MAP:
             raise KeyError("No such option: " + k)
         self._kw[k] = int(v) if isinstance(v, bool) else v
 
     def __getattr__(self, k):
-        if k in self._MAP:
-            return self._kw.get(k)
+        if k.lower() in self._MAP:
+            return self._kw.get(k.lower(), self._DEFAULTS[k.lower()])
         raise AttributeError(k)
 
     def to_native(self, model_type: int, streamed: int) -> _Options:

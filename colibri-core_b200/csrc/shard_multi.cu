@@ -8,7 +8,8 @@
 // exactly as there.  Level 1 and the header numbers are reduced through host memory (a few hundred KB); the dense square of level 2 is
 // summed by a kernel that reads the peers' squares.  A rank that fails raises a shared flag that every barrier checks, so the others
 // leave instead of waiting forever.
-// Not here (refused): exhaustive skipgrams (their exchange is an NCCL all-to-all in the torchrun variant), indexed models, MINLENGTH > 1.
+// Not here (refused): exhaustive skipgrams (their exchange is an NCCL all-to-all in the torchrun variant) and indexed models.  MINLENGTH > 1 is
+// handled by the drop rules of shard_finish (shard.cu).
 #include <condition_variable>
 #include <mutex>
 #include <string>
